@@ -1,0 +1,11 @@
+"""gridfour_b200 -- GVRS tile codecs as sm_100a CUDA kernels behind Gridfour's codec plugin API.
+
+Host-side mirror (Python, over the C ABI in include/g4codec.h) of the reference's Java interfaces:
+ICompressionEncoder / ICompressionDecoder, the codec classes, GvrsFileSpecification.addCompressionCodec and
+CodecMaster, plus the new batched encodeTiles / decodeTiles entry.  See DESIGN.md and INTEGRATION.md.
+"""
+from .codecs import (  # noqa: F401
+    CodecCanonHuffman, CodecDeflate, CodecFloat, CodecHuffman, CodecMaster, CodecSpecification, Context,
+    ICompressionDecoder, ICompressionEncoder, LsDecoder12, LsEncoder12, TileBatch, INT4_NULL_CODE,
+)
+from ._lib import FormatError, G4Error  # noqa: F401

@@ -1,0 +1,565 @@
+// g4_api.cu -- host side of the C ABI declared in include/g4codec.h.
+//
+// Mirrors the reference's selection layer around the codec kernels:
+//   CodecMaster.encodeSingleThread / decode   gvrs/CodecMaster.java:142-203
+//   TileElementInt.encode / decode            gvrs/TileElementInt.java:196-219
+// (paths under /root/reference/core/src/main/java/org/gridfour/).  No CPU compute path exists here:
+// every entry point launches CUDA kernels and fails with G4_ERR_CUDA when that is impossible.
+#include <cstdio>
+#include <cstring>
+#include <string>
+#include <vector>
+#include "g4_kernels.h"
+
+using namespace g4;
+
+namespace {
+
+thread_local std::string tlsError;
+
+int cuda_fail(cudaError_t e, const char* what) {
+  tlsError = std::string(what) + ": " + cudaGetErrorString(e);
+  return G4_ERR_CUDA;
+}
+#define CK(call)                                           \
+  do {                                                     \
+    cudaError_t e_ = (call);                               \
+    if (e_ != cudaSuccess) return cuda_fail(e_, #call);    \
+  } while (0)
+
+struct DevBuf {
+  void* p = nullptr;
+  size_t cap = 0;
+  cudaError_t ensure(size_t bytes) {
+    if (bytes <= cap) return cudaSuccess;
+    if (p) cudaFree(p);
+    p = nullptr;
+    cap = 0;
+    size_t want = bytes + bytes / 8 + 256;
+    cudaError_t e = cudaMalloc(&p, want);
+    if (e == cudaSuccess) cap = want;
+    return e;
+  }
+  void release() {
+    if (p) cudaFree(p);
+    p = nullptr;
+    cap = 0;
+  }
+  template <class T>
+  T* as() const { return static_cast<T*>(p); }
+};
+
+size_t round_up(size_t x, size_t a) { return (x + a - 1) / a * a; }
+
+}  // namespace
+
+struct g4_context {
+  int device = 0;
+  cudaStream_t stream = nullptr;
+  bool ownStream = false;
+  int smCount = 148;
+  uint64_t launches = 0;
+  DevBuf slots[G4_MAX_CODECS];
+  DevBuf candLens, candPreds, candStatus;
+  DevBuf counters;     // 64 ints: [0..15] encode counters, [16..31] decode counters, [32..47] list counts
+  DevBuf scratch;      // per-CTA scratch
+  DevBuf lists, src, total;
+  // staging used by the host-memory entry points
+  DevBuf sGrid, sArena, sOffsets, sLens, sCodec, sPred, sStatus;
+};
+
+namespace {
+
+bool codec_is_float(int id) { return id == G4_CODEC_FLOAT; }
+
+int persistent_ctas(const g4_context* ctx, int nTiles, int perSm) {
+  int cap = ctx->smCount * perSm;
+  return nTiles < cap ? nTiles : cap;
+}
+
+// Launch one candidate encoder over every tile of the band.
+int launch_encoder(g4_context* ctx, int codecId, EncodeArgs& a, int nTiles) {
+  switch (codecId) {
+    case G4_CODEC_HUFFMAN: {
+      int n = persistent_ctas(ctx, nTiles, 4);
+      CK(launch_huffman_encode(a, n, ctx->stream));
+      ctx->launches++;
+      return G4_OK;
+    }
+    default:
+      tlsError = "codec not implemented on the GPU yet";
+      return G4_ERR_UNSUPPORTED;
+  }
+}
+
+int decoder_ctas(const g4_context* ctx, int nTiles) { return persistent_ctas(ctx, nTiles, 8); }
+
+int launch_decoder(g4_context* ctx, int codecId, DecodeArgs& a, int nCtas) {
+  switch (codecId) {
+    case G4_CODEC_HUFFMAN:
+      CK(launch_huffman_decode(a, nCtas, ctx->stream));
+      ctx->launches++;
+      return G4_OK;
+    default:
+      tlsError = "codec not implemented on the GPU yet";
+      return G4_ERR_UNSUPPORTED;
+  }
+}
+
+int check_band(const g4_band_desc* b) {
+  if (!b) return G4_ERR_ARG;
+  if (b->elem_type != G4_ELEM_I32 && b->elem_type != G4_ELEM_F32) return G4_ERR_ARG;
+  if (b->tile_rows < 2 || b->tile_cols < 2) return G4_ERR_UNSUPPORTED;
+  if (b->tiles_down < 1 || b->tiles_across < 1) return G4_ERR_ARG;
+  if (int64_t(b->tile_rows) * b->tile_cols > (1 << 20)) return G4_ERR_UNSUPPORTED;
+  if (b->grid_pitch < int64_t(b->tiles_across) * b->tile_cols) return G4_ERR_ARG;
+  if (int64_t(b->tiles_down) * b->tiles_across > (1 << 24)) return G4_ERR_ARG;
+  return G4_OK;
+}
+
+size_t band_samples(const g4_band_desc& b) {
+  return size_t(int64_t(b.tiles_down) * b.tile_rows - 1) * size_t(b.grid_pitch) + size_t(b.tiles_across) * b.tile_cols;
+}
+
+// Encode with every applicable codec of `codecs`, select, compact.  All pointers are device pointers.
+// slotBytes: capacity of each candidate slot.
+int encode_device(g4_context* ctx, const g4_codec_list* codecs, const g4_band_desc* band, void* grid, uint8_t* arena,
+                  uint64_t arenaCap, uint64_t* offsets, uint32_t* lens, uint8_t* codecOut, uint8_t* predOut, int32_t* status,
+                  uint64_t* totalHost, size_t slotBytes) {
+  const int nTiles = band->tiles_down * band->tiles_across;
+  const int n = band->tile_rows * band->tile_cols;
+  const bool isFloat = band->elem_type == G4_ELEM_F32;
+  int cand[G4_MAX_CODECS], nCand = 0;
+  for (int k = 0; k < codecs->n_codecs; k++) {
+    int id = codecs->codec_ids[k];
+    if (id < 0 || id >= G4_CODEC_COUNT) return G4_ERR_ARG;
+    if (codec_is_float(id) == isFloat) cand[nCand++] = k;
+  }
+  CK(ctx->candLens.ensure(size_t(nCand + 1) * nTiles * 4));
+  CK(ctx->candPreds.ensure(size_t(nCand + 1) * nTiles));
+  CK(ctx->candStatus.ensure(size_t(nCand + 1) * nTiles * 4));
+  CK(ctx->counters.ensure(64 * sizeof(int)));
+  CK(ctx->src.ensure(size_t(nTiles) * 4));
+  CK(ctx->total.ensure(8));
+  CK(cudaMemsetAsync(ctx->counters.p, 0, 64 * sizeof(int), ctx->stream));
+  SelectArgs sel{};
+  CompactArgs cmp{};
+  for (int c = 0; c < nCand; c++) {
+    CK(ctx->slots[c].ensure(size_t(nTiles) * slotBytes));
+    EncodeArgs a{};
+    a.band = *band;
+    a.grid = grid;
+    a.slots = ctx->slots[c].as<uint8_t>();
+    a.slotBytes = slotBytes;
+    a.lens = ctx->candLens.as<uint32_t>() + size_t(c) * nTiles;
+    a.preds = ctx->candPreds.as<uint8_t>() + size_t(c) * nTiles;
+    a.status = ctx->candStatus.as<int32_t>() + size_t(c) * nTiles;
+    a.counter = ctx->counters.as<int>() + c;
+    a.codecIndex = cand[c];
+    a.scratch = nullptr;
+    a.scratchStride = 0;
+    int rc = launch_encoder(ctx, codecs->codec_ids[cand[c]], a, nTiles);
+    if (rc != G4_OK) return rc;
+    sel.candIndex[c] = cand[c];
+    cmp.slots[c] = a.slots;
+  }
+  sel.nTiles = nTiles;
+  sel.nCand = nCand;
+  sel.rawLen = uint32_t(n) * 4u;
+  sel.candLens = ctx->candLens.as<uint32_t>();
+  sel.candPreds = ctx->candPreds.as<uint8_t>();
+  sel.candStatus = ctx->candStatus.as<int32_t>();
+  sel.lens = lens;
+  sel.codecOut = codecOut;
+  sel.predOut = predOut;
+  sel.src = ctx->src.as<int>();
+  sel.status = status;
+  CK(launch_select(sel, ctx->stream));
+  CK(launch_offsets(lens, offsets, nTiles, ctx->total.as<uint64_t>(), ctx->stream));
+  cmp.band = *band;
+  cmp.grid = grid;
+  cmp.slotBytes = slotBytes;
+  cmp.lens = lens;
+  cmp.offsets = offsets;
+  cmp.src = ctx->src.as<int>();
+  cmp.arena = arena;
+  cmp.arenaCap = arenaCap;
+  cmp.status = status;
+  CK(launch_compact(cmp, nTiles, ctx->stream));
+  ctx->launches += 3;
+  uint64_t total = 0;
+  CK(cudaMemcpyAsync(&total, ctx->total.p, 8, cudaMemcpyDeviceToHost, ctx->stream));
+  CK(cudaStreamSynchronize(ctx->stream));
+  if (totalHost) *totalHost = total;
+  return G4_OK;
+}
+
+int decode_device(g4_context* ctx, const g4_codec_list* codecs, const g4_band_desc* band, const uint8_t* arena,
+                  const uint64_t* offsets, const uint32_t* lens, void* grid, int32_t* status) {
+  const int nTiles = band->tiles_down * band->tiles_across;
+  const int n = band->tile_rows * band->tile_cols;
+  const int kinds = G4_CODEC_COUNT + 1;
+  CK(ctx->counters.ensure(64 * sizeof(int)));
+  CK(ctx->lists.ensure(size_t(kinds) * nTiles * sizeof(int)));
+  CK(cudaMemsetAsync(ctx->counters.p, 0, 64 * sizeof(int), ctx->stream));
+  ClassifyArgs cl{};
+  cl.nTiles = nTiles;
+  cl.elemType = band->elem_type;
+  cl.rawLen = uint32_t(n) * 4u;
+  cl.codecs = *codecs;
+  cl.arena = arena;
+  cl.offsets = offsets;
+  cl.lens = lens;
+  cl.lists = ctx->lists.as<int>();
+  cl.counts = ctx->counters.as<int>() + 32;
+  cl.status = status;
+  CK(launch_classify(cl, ctx->stream));
+  ctx->launches++;
+  const int nCtas = decoder_ctas(ctx, nTiles);
+  const size_t stride = round_up(size_t(n) * 6 + 64, 16);
+  CK(ctx->scratch.ensure(stride * nCtas));
+  bool present[G4_CODEC_COUNT] = {false};
+  for (int k = 0; k < codecs->n_codecs; k++) {
+    int id = codecs->codec_ids[k];
+    if (id < 0 || id >= G4_CODEC_COUNT) return G4_ERR_ARG;
+    present[id] = true;
+  }
+  for (int kind = 0; kind <= G4_CODEC_COUNT; kind++) {
+    if (kind < G4_CODEC_COUNT && !present[kind]) continue;
+    DecodeArgs a{};
+    a.band = *band;
+    a.grid = grid;
+    a.arena = arena;
+    a.offsets = offsets;
+    a.lens = lens;
+    a.list = ctx->lists.as<int>() + size_t(kind) * nTiles;
+    a.listCount = ctx->counters.as<int>() + 32 + kind;
+    a.status = status;
+    a.counter = ctx->counters.as<int>() + 16 + kind;
+    a.scratch = ctx->scratch.as<uint8_t>();
+    a.scratchStride = stride;
+    if (kind == G4_CODEC_COUNT) {
+      CK(launch_raw_decode(a, nTiles, ctx->stream));
+      ctx->launches++;
+    } else {
+      int rc = launch_decoder(ctx, kind, a, nCtas);
+      if (rc != G4_OK) return rc;
+    }
+  }
+  return G4_OK;
+}
+
+int first_bad_status(const std::vector<int32_t>& st) {
+  for (int32_t s : st)
+    if (s != G4_OK) return s;
+  return G4_OK;
+}
+
+}  // namespace
+
+extern "C" {
+
+int g4_abi_version(void) { return G4_ABI_VERSION; }
+
+const char* g4_status_string(int s) {
+  switch (s) {
+    case G4_OK: return "ok";
+    case G4_DECLINED: return "declined (codec returns null for this tile)";
+    case G4_ERR_ARG: return "bad argument";
+    case G4_ERR_FORMAT: return "malformed packing";
+    case G4_ERR_CAPACITY: return "output buffer too small";
+    case G4_ERR_CUDA: return "CUDA error";
+    case G4_ERR_UNSUPPORTED: return "unsupported";
+    default: return "unknown status";
+  }
+}
+
+const char* g4_last_error(void) { return tlsError.c_str(); }
+
+int g4_device_count(void) {
+  int n = 0;
+  if (cudaGetDeviceCount(&n) != cudaSuccess) return 0;
+  return n;
+}
+
+static const char* kCodecNames[G4_CODEC_COUNT] = {"GvrsHuffman", "GvrsDeflate", "GvrsFloat", "GvrsCanonicalHuffman", "LSOP12"};
+
+int g4_codec_id_from_name(const char* name) {
+  if (!name) return -1;
+  for (int i = 0; i < G4_CODEC_COUNT; i++)
+    if (std::strcmp(name, kCodecNames[i]) == 0) return i;
+  return -1;
+}
+const char* g4_codec_name(int id) { return (id >= 0 && id < G4_CODEC_COUNT) ? kCodecNames[id] : nullptr; }
+
+int g4_context_create(int device, void* cuda_stream, g4_context** out) {
+  if (!out) return G4_ERR_ARG;
+  *out = nullptr;
+  int nDev = 0;
+  cudaError_t e = cudaGetDeviceCount(&nDev);
+  if (e != cudaSuccess || nDev == 0) {
+    tlsError = "no CUDA device available (the codec kernels have no CPU fallback)";
+    return G4_ERR_CUDA;
+  }
+  if (device < 0 || device >= nDev) return G4_ERR_ARG;
+  CK(cudaSetDevice(device));
+  g4_context* ctx = new g4_context();
+  ctx->device = device;
+  cudaDeviceProp prop;
+  CK(cudaGetDeviceProperties(&prop, device));
+  ctx->smCount = prop.multiProcessorCount;
+  if (cuda_stream) ctx->stream = static_cast<cudaStream_t>(cuda_stream);
+  else {
+    CK(cudaStreamCreateWithFlags(&ctx->stream, cudaStreamNonBlocking));
+    ctx->ownStream = true;
+  }
+  *out = ctx;
+  return G4_OK;
+}
+
+void g4_context_destroy(g4_context* ctx) {
+  if (!ctx) return;
+  cudaSetDevice(ctx->device);
+  cudaStreamSynchronize(ctx->stream);
+  for (auto& b : ctx->slots) b.release();
+  DevBuf* bufs[] = {&ctx->candLens, &ctx->candPreds, &ctx->candStatus, &ctx->counters, &ctx->scratch, &ctx->lists, &ctx->src,
+                    &ctx->total, &ctx->sGrid, &ctx->sArena, &ctx->sOffsets, &ctx->sLens, &ctx->sCodec, &ctx->sPred, &ctx->sStatus};
+  for (DevBuf* b : bufs) b->release();
+  if (ctx->ownStream) cudaStreamDestroy(ctx->stream);
+  delete ctx;
+}
+
+int g4_context_synchronize(g4_context* ctx) {
+  if (!ctx) return G4_ERR_ARG;
+  CK(cudaStreamSynchronize(ctx->stream));
+  return G4_OK;
+}
+
+uint64_t g4_launch_count(const g4_context* ctx) { return ctx ? ctx->launches : 0; }
+
+uint64_t g4_encode_arena_bound(const g4_band_desc* b) {
+  if (!b) return 0;
+  uint64_t n = uint64_t(b->tile_rows) * b->tile_cols;
+  return uint64_t(b->tiles_down) * b->tiles_across * ((n * 4 + 7) & ~7ull);
+}
+
+int g4_fill_terrain(g4_context* ctx, int elem_type, uint64_t seed, int64_t row0, int64_t col0, int64_t n_rows, int64_t n_cols,
+                    void* device_out) {
+  if (!ctx || !device_out || n_rows < 1 || n_cols < 1) return G4_ERR_ARG;
+  CK(cudaSetDevice(ctx->device));
+  CK(launch_fill_terrain(elem_type, seed, row0, col0, n_rows, n_cols, device_out, ctx->stream));
+  ctx->launches++;
+  return G4_OK;
+}
+
+int g4_encode_tiles(g4_context* ctx, const g4_codec_list* codecs, const g4_band_desc* band, int mem_space, const void* grid,
+                    uint8_t* arena, uint64_t arena_cap, uint64_t* offsets, uint32_t* lens, uint8_t* codec_out,
+                    uint8_t* predictor_out, int32_t* status, uint64_t* total_bytes) {
+  if (!ctx || !codecs || !grid || !arena || !offsets || !lens || !codec_out || !predictor_out || !status) return G4_ERR_ARG;
+  int rc = check_band(band);
+  if (rc != G4_OK) return rc;
+  if (codecs->n_codecs < 0 || codecs->n_codecs > G4_MAX_CODECS) return G4_ERR_ARG;
+  CK(cudaSetDevice(ctx->device));
+  const int nTiles = band->tiles_down * band->tiles_across;
+  const size_t n = size_t(band->tile_rows) * band->tile_cols;
+  const size_t slotBytes = round_up(n * 4 + 64, 16);
+  std::vector<int32_t> st(nTiles);
+  uint64_t total = 0;
+  if (mem_space == G4_MEM_DEVICE) {
+    rc = encode_device(ctx, codecs, band, const_cast<void*>(grid), arena, arena_cap, offsets, lens, codec_out, predictor_out,
+                       status, &total, slotBytes);
+    if (rc != G4_OK) return rc;
+    CK(cudaMemcpyAsync(st.data(), status, size_t(nTiles) * 4, cudaMemcpyDeviceToHost, ctx->stream));
+    CK(cudaStreamSynchronize(ctx->stream));
+  } else if (mem_space == G4_MEM_HOST) {
+    const size_t gridBytes = band_samples(*band) * 4;
+    const uint64_t bound = g4_encode_arena_bound(band);
+    CK(ctx->sGrid.ensure(gridBytes));
+    CK(ctx->sArena.ensure(bound + 16));
+    CK(ctx->sOffsets.ensure(size_t(nTiles) * 8));
+    CK(ctx->sLens.ensure(size_t(nTiles) * 4));
+    CK(ctx->sCodec.ensure(nTiles));
+    CK(ctx->sPred.ensure(nTiles));
+    CK(ctx->sStatus.ensure(size_t(nTiles) * 4));
+    CK(cudaMemcpyAsync(ctx->sGrid.p, grid, gridBytes, cudaMemcpyHostToDevice, ctx->stream));
+    rc = encode_device(ctx, codecs, band, ctx->sGrid.p, ctx->sArena.as<uint8_t>(), bound, ctx->sOffsets.as<uint64_t>(),
+                       ctx->sLens.as<uint32_t>(), ctx->sCodec.as<uint8_t>(), ctx->sPred.as<uint8_t>(), ctx->sStatus.as<int32_t>(),
+                       &total, slotBytes);
+    if (rc != G4_OK) return rc;
+    if (total > arena_cap) {
+      if (total_bytes) *total_bytes = total;
+      return G4_ERR_CAPACITY;
+    }
+    CK(cudaMemcpyAsync(arena, ctx->sArena.p, total, cudaMemcpyDeviceToHost, ctx->stream));
+    CK(cudaMemcpyAsync(offsets, ctx->sOffsets.p, size_t(nTiles) * 8, cudaMemcpyDeviceToHost, ctx->stream));
+    CK(cudaMemcpyAsync(lens, ctx->sLens.p, size_t(nTiles) * 4, cudaMemcpyDeviceToHost, ctx->stream));
+    CK(cudaMemcpyAsync(codec_out, ctx->sCodec.p, nTiles, cudaMemcpyDeviceToHost, ctx->stream));
+    CK(cudaMemcpyAsync(predictor_out, ctx->sPred.p, nTiles, cudaMemcpyDeviceToHost, ctx->stream));
+    CK(cudaMemcpyAsync(status, ctx->sStatus.p, size_t(nTiles) * 4, cudaMemcpyDeviceToHost, ctx->stream));
+    CK(cudaStreamSynchronize(ctx->stream));
+    std::memcpy(st.data(), status, size_t(nTiles) * 4);
+  } else {
+    return G4_ERR_ARG;
+  }
+  if (total_bytes) *total_bytes = total;
+  return first_bad_status(st);
+}
+
+int g4_decode_tiles(g4_context* ctx, const g4_codec_list* codecs, const g4_band_desc* band, int mem_space, const uint8_t* arena,
+                    const uint64_t* offsets, const uint32_t* lens, void* grid, int32_t* status) {
+  if (!ctx || !codecs || !grid || !arena || !offsets || !lens || !status) return G4_ERR_ARG;
+  int rc = check_band(band);
+  if (rc != G4_OK) return rc;
+  if (codecs->n_codecs < 0 || codecs->n_codecs > G4_MAX_CODECS) return G4_ERR_ARG;
+  CK(cudaSetDevice(ctx->device));
+  const int nTiles = band->tiles_down * band->tiles_across;
+  std::vector<int32_t> st(nTiles);
+  if (mem_space == G4_MEM_DEVICE) {
+    rc = decode_device(ctx, codecs, band, arena, offsets, lens, grid, status);
+    if (rc != G4_OK) return rc;
+    CK(cudaMemcpyAsync(st.data(), status, size_t(nTiles) * 4, cudaMemcpyDeviceToHost, ctx->stream));
+    CK(cudaStreamSynchronize(ctx->stream));
+  } else if (mem_space == G4_MEM_HOST) {
+    uint64_t arenaBytes = 0;
+    for (int t = 0; t < nTiles; t++) {
+      uint64_t end = offsets[t] + lens[t];
+      if (end > arenaBytes) arenaBytes = end;
+    }
+    const size_t gridBytes = band_samples(*band) * 4;
+    CK(ctx->sGrid.ensure(gridBytes));
+    CK(ctx->sArena.ensure(arenaBytes + 16));
+    CK(ctx->sOffsets.ensure(size_t(nTiles) * 8));
+    CK(ctx->sLens.ensure(size_t(nTiles) * 4));
+    CK(ctx->sStatus.ensure(size_t(nTiles) * 4));
+    CK(cudaMemcpyAsync(ctx->sArena.p, arena, arenaBytes, cudaMemcpyHostToDevice, ctx->stream));
+    CK(cudaMemcpyAsync(ctx->sOffsets.p, offsets, size_t(nTiles) * 8, cudaMemcpyHostToDevice, ctx->stream));
+    CK(cudaMemcpyAsync(ctx->sLens.p, lens, size_t(nTiles) * 4, cudaMemcpyHostToDevice, ctx->stream));
+    rc = decode_device(ctx, codecs, band, ctx->sArena.as<uint8_t>(), ctx->sOffsets.as<uint64_t>(), ctx->sLens.as<uint32_t>(),
+                       ctx->sGrid.p, ctx->sStatus.as<int32_t>());
+    if (rc != G4_OK) return rc;
+    CK(cudaMemcpyAsync(grid, ctx->sGrid.p, gridBytes, cudaMemcpyDeviceToHost, ctx->stream));
+    CK(cudaMemcpyAsync(status, ctx->sStatus.p, size_t(nTiles) * 4, cudaMemcpyDeviceToHost, ctx->stream));
+    CK(cudaStreamSynchronize(ctx->stream));
+    std::memcpy(st.data(), status, size_t(nTiles) * 4);
+  } else {
+    return G4_ERR_ARG;
+  }
+  return first_bad_status(st);
+}
+
+// ---- per-tile entry points: one-tile bands through the same kernels --------------------------------
+
+static int encode_one(g4_context* ctx, int codec_id, int codec_index, int elem, int n_rows, int n_cols, const void* values,
+                      uint8_t* out, size_t out_cap, size_t* out_len, int* predictor) {
+  if (!ctx || !values || !out || !out_len) return G4_ERR_ARG;
+  if (codec_id < 0 || codec_id >= G4_CODEC_COUNT || codec_index < 0 || codec_index > 255) return G4_ERR_ARG;
+  if (codec_is_float(codec_id) != (elem == G4_ELEM_F32)) return G4_DECLINED;  // e.g. CodecHuffman.encodeFloats -> null
+  g4_band_desc band{elem, n_rows, n_cols, 1, 1, n_cols};
+  int rc = check_band(&band);
+  if (rc != G4_OK) return rc;
+  CK(cudaSetDevice(ctx->device));
+  const size_t n = size_t(n_rows) * n_cols;
+  const size_t slotBytes = round_up(n * 6 + 1024, 16);  // worst case of any codec stream for this tile
+  CK(ctx->sGrid.ensure(n * 4));
+  CK(ctx->slots[0].ensure(slotBytes));
+  CK(ctx->candLens.ensure(4));
+  CK(ctx->candPreds.ensure(1));
+  CK(ctx->candStatus.ensure(4));
+  CK(ctx->counters.ensure(64 * sizeof(int)));
+  CK(cudaMemsetAsync(ctx->counters.p, 0, 64 * sizeof(int), ctx->stream));
+  CK(cudaMemcpyAsync(ctx->sGrid.p, values, n * 4, cudaMemcpyHostToDevice, ctx->stream));
+  EncodeArgs a{};
+  a.band = band;
+  a.grid = ctx->sGrid.p;
+  a.slots = ctx->slots[0].as<uint8_t>();
+  a.slotBytes = slotBytes;
+  a.lens = ctx->candLens.as<uint32_t>();
+  a.preds = ctx->candPreds.as<uint8_t>();
+  a.status = ctx->candStatus.as<int32_t>();
+  a.counter = ctx->counters.as<int>();
+  a.codecIndex = codec_index;
+  rc = launch_encoder(ctx, codec_id, a, 1);
+  if (rc != G4_OK) return rc;
+  uint32_t len = 0;
+  int32_t st = 0;
+  uint8_t pred = 0;
+  CK(cudaMemcpyAsync(&len, a.lens, 4, cudaMemcpyDeviceToHost, ctx->stream));
+  CK(cudaMemcpyAsync(&st, a.status, 4, cudaMemcpyDeviceToHost, ctx->stream));
+  CK(cudaMemcpyAsync(&pred, a.preds, 1, cudaMemcpyDeviceToHost, ctx->stream));
+  CK(cudaStreamSynchronize(ctx->stream));
+  if (st != G4_OK) return st;
+  *out_len = len;
+  if (predictor) *predictor = pred;
+  if (len > out_cap) return G4_ERR_CAPACITY;
+  CK(cudaMemcpyAsync(out, a.slots, len, cudaMemcpyDeviceToHost, ctx->stream));
+  CK(cudaStreamSynchronize(ctx->stream));
+  return G4_OK;
+}
+
+static int decode_one(g4_context* ctx, int codec_id, int elem, int n_rows, int n_cols, const uint8_t* packing, size_t len, void* out) {
+  if (!ctx || !packing || !out || len == 0 || len > 0xffffffffull) return G4_ERR_ARG;
+  if (codec_id < 0 || codec_id >= G4_CODEC_COUNT) return G4_ERR_ARG;
+  if (codec_is_float(codec_id) != (elem == G4_ELEM_F32)) return G4_DECLINED;  // decodeFloats on an int codec -> null
+  g4_band_desc band{elem, n_rows, n_cols, 1, 1, n_cols};
+  int rc = check_band(&band);
+  if (rc != G4_OK) return rc;
+  CK(cudaSetDevice(ctx->device));
+  const size_t n = size_t(n_rows) * n_cols;
+  CK(ctx->sGrid.ensure(n * 4));
+  CK(ctx->sArena.ensure(len + 16));
+  CK(ctx->sOffsets.ensure(8));
+  CK(ctx->sLens.ensure(4));
+  CK(ctx->sStatus.ensure(4));
+  CK(ctx->lists.ensure(4));
+  CK(ctx->counters.ensure(64 * sizeof(int)));
+  const size_t stride = round_up(n * 6 + 64, 16);
+  CK(ctx->scratch.ensure(stride));
+  CK(cudaMemsetAsync(ctx->counters.p, 0, 64 * sizeof(int), ctx->stream));
+  CK(cudaMemsetAsync(ctx->sOffsets.p, 0, 8, ctx->stream));
+  CK(cudaMemsetAsync(ctx->lists.p, 0, 4, ctx->stream));
+  const uint32_t len32 = uint32_t(len);
+  const int one = 1;
+  const int32_t pending = G4_ERR_CUDA;
+  CK(cudaMemcpyAsync(ctx->sArena.p, packing, len, cudaMemcpyHostToDevice, ctx->stream));
+  CK(cudaMemcpyAsync(ctx->sLens.p, &len32, 4, cudaMemcpyHostToDevice, ctx->stream));
+  CK(cudaMemcpyAsync(ctx->counters.as<int>() + 32, &one, 4, cudaMemcpyHostToDevice, ctx->stream));
+  CK(cudaMemcpyAsync(ctx->sStatus.p, &pending, 4, cudaMemcpyHostToDevice, ctx->stream));
+  DecodeArgs a{};
+  a.band = band;
+  a.grid = ctx->sGrid.p;
+  a.arena = ctx->sArena.as<uint8_t>();
+  a.offsets = ctx->sOffsets.as<uint64_t>();
+  a.lens = ctx->sLens.as<uint32_t>();
+  a.list = ctx->lists.as<int>();
+  a.listCount = ctx->counters.as<int>() + 32;
+  a.status = ctx->sStatus.as<int32_t>();
+  a.counter = ctx->counters.as<int>() + 16;
+  a.scratch = ctx->scratch.as<uint8_t>();
+  a.scratchStride = stride;
+  rc = launch_decoder(ctx, codec_id, a, 1);
+  if (rc != G4_OK) return rc;
+  int32_t st = 0;
+  CK(cudaMemcpyAsync(&st, ctx->sStatus.p, 4, cudaMemcpyDeviceToHost, ctx->stream));
+  CK(cudaStreamSynchronize(ctx->stream));
+  if (st != G4_OK) return st;
+  CK(cudaMemcpyAsync(out, ctx->sGrid.p, n * 4, cudaMemcpyDeviceToHost, ctx->stream));
+  CK(cudaStreamSynchronize(ctx->stream));
+  return G4_OK;
+}
+
+int g4_encode_i32(g4_context* ctx, int codec_id, int codec_index, int n_rows, int n_cols, const int32_t* values, uint8_t* out,
+                  size_t out_cap, size_t* out_len, int* predictor) {
+  return encode_one(ctx, codec_id, codec_index, G4_ELEM_I32, n_rows, n_cols, values, out, out_cap, out_len, predictor);
+}
+int g4_decode_i32(g4_context* ctx, int codec_id, int n_rows, int n_cols, const uint8_t* packing, size_t len, int32_t* out) {
+  return decode_one(ctx, codec_id, G4_ELEM_I32, n_rows, n_cols, packing, len, out);
+}
+int g4_encode_f32(g4_context* ctx, int codec_id, int codec_index, int n_rows, int n_cols, const float* values, uint8_t* out,
+                  size_t out_cap, size_t* out_len) {
+  return encode_one(ctx, codec_id, codec_index, G4_ELEM_F32, n_rows, n_cols, values, out, out_cap, out_len, nullptr);
+}
+int g4_decode_f32(g4_context* ctx, int codec_id, int n_rows, int n_cols, const uint8_t* packing, size_t len, float* out) {
+  return decode_one(ctx, codec_id, G4_ELEM_F32, n_rows, n_cols, packing, len, out);
+}
+
+}  // extern "C"

@@ -1,0 +1,618 @@
+// g4_huffman.cu -- CodecHuffman (legacy byte-alphabet Huffman over M32 predictor residuals) on sm_100a.
+//
+// Reference: compress/CodecHuffman.java:70-153, compress/HuffmanEncoder.java:124-305,
+//            compress/HuffmanDecoder.java:65-187   (under /root/reference/core/src/main/java/org/gridfour/).
+//
+// Encode, one persistent CTA per tile at a time:
+//   pass 1  coalesced sweep of the tile: residuals of all three predictors per cell, M32 lengths/bytes,
+//           three 256-bin shared-memory histograms
+//   trees   rank sort of (count,symbol); size of every candidate = header + tree + sum of branch counts;
+//           the winner's tree is rebuilt by one thread with the reference's tie-breaking (a new branch
+//           goes in front of every node of equal count)
+//   pass 2  the winner's residuals in stream order -> M32 bytes -> codes; bit offsets from a block scan;
+//           bits are OR-ed into a shared-memory window and flushed with coalesced word stores
+// Decode:
+//   tree parse by one thread -> 11-bit lookup table filled by all threads; text decoded by all threads as
+//   self-synchronising sub-sequences (speculative start, iterate until hand-over positions agree), count
+//   scan -> byte offsets -> second pass writes the M32 bytes; then g4_predict.cuh.
+#include "g4_kernels.h"
+#include "g4_predict.cuh"
+
+namespace g4 {
+
+// =================================================================================================
+// Encode
+// =================================================================================================
+namespace {
+
+constexpr int kWinWords = 4096;                 // 16 KB output window
+constexpr uint32_t kWinBits = kWinWords * 32u;
+constexpr int kEmitItems = 8;                   // residuals per thread per chunk
+
+struct HuffEncShared {
+  uint32_t hist[3][256];
+  uint32_t skey[3][256];     // sorted (count<<8 | symbol), ascending
+  uint32_t bq[3][256];       // branch-count queues for the size-only merges
+  uint32_t bcount[256];      // winner: branch counts by creation order
+  uint16_t bqueue[256];      // winner: branch ids in list order
+  uint16_t left[256], right[256];
+  uint64_t code[512];        // node code, path order LSB first (leaves 0..255 by symbol, branches 256+id)
+  uint8_t len[512];
+  uint32_t win[kWinWords + 4];
+  uint32_t scan[kWarps + 1];
+  uint32_t nLeaf[3];
+  unsigned long long textBits[3];
+  uint32_t nBytes[3];
+  int hasNull;
+  int winner;
+};
+
+// size-only Huffman merge: returns the sum of all branch counts (== text bits).  Tie order is irrelevant
+// for the total.  keys ascending, first `256-L` entries have count 0.
+__device__ unsigned long long merge_size_only(const uint32_t* skey, uint32_t* bq, int L) {
+  int li = 256 - L, bi = 0, bt = 0;
+  unsigned long long total = 0;
+  for (int m = 0; m < L - 1; m++) {
+    uint32_t c[2];
+#pragma unroll
+    for (int k = 0; k < 2; k++) {
+      bool takeBranch = (bi < bt) && (li > 255 || bq[bi] <= (skey[li] >> 8));
+      if (takeBranch) c[k] = bq[bi++];
+      else c[k] = skey[li++] >> 8;
+    }
+    uint32_t s = c[0] + c[1];
+    bq[bt++] = s;
+    total += s;
+  }
+  return total;
+}
+
+// Winner tree with the reference's list-insertion rule (HuffmanEncoder.java:165-194): a new branch is
+// placed in front of the first remaining node whose count is >= its own, so among equal counts the order
+// is: newest branch ... oldest branch, then leaves by symbol.
+__device__ void build_winner_tree(HuffEncShared& S, int p, int L) {
+  const uint32_t* skey = S.skey[p];
+  int li = 256 - L, bi = 0, bt = 0, nb = 0;
+  for (int m = 0; m < L - 1; m++) {
+    uint16_t node[2];
+    uint32_t cnt[2];
+#pragma unroll
+    for (int k = 0; k < 2; k++) {
+      bool takeBranch = (bi < bt) && (li > 255 || S.bcount[S.bqueue[bi]] <= (skey[li] >> 8));
+      if (takeBranch) { uint16_t id = S.bqueue[bi++]; node[k] = 256 + id; cnt[k] = S.bcount[id]; }
+      else { uint32_t key = skey[li++]; node[k] = key & 0xff; cnt[k] = key >> 8; }
+    }
+    int id = nb++;
+    uint32_t s = cnt[0] + cnt[1];
+    S.bcount[id] = s;
+    S.left[id] = node[0];
+    S.right[id] = node[1];
+    int pos = bt;
+    while (pos > bi && S.bcount[S.bqueue[pos - 1]] >= s) { S.bqueue[pos] = S.bqueue[pos - 1]; pos--; }
+    S.bqueue[pos] = uint16_t(id);
+    bt++;
+  }
+  // depths and codes, root first (children are always created before their parent)
+  int root = 256 + (L - 2);
+  S.len[root] = 0;
+  S.code[root] = 0;
+  for (int id = L - 2; id >= 0; id--) {
+    int n = 256 + id;
+    uint8_t l = S.len[n];
+    uint64_t c = S.code[n];
+    S.len[S.left[id]] = l + 1;
+    S.code[S.left[id]] = c;
+    S.len[S.right[id]] = l + 1;
+    S.code[S.right[id]] = c | (uint64_t(1) << l);
+  }
+}
+
+// header (CodecHuffman.java:121-130) + pre-order tree (HuffmanEncoder.java:221-294) into the window
+__device__ uint32_t write_header_and_tree(HuffEncShared& S, int codecIndex, int pred, int32_t seed, uint32_t nM32, int L,
+                                          int singleSymbol) {
+  BitSink sink{S.win, 0};
+  sink.put(uint32_t(codecIndex) & 0xff, 8);
+  sink.put(uint32_t(pred), 8);
+  sink.put(uint32_t(seed), 32);
+  sink.put(nM32, 32);
+  if (L == 1) {  // HuffmanEncoder.java:147-157
+    sink.put(0, 8);
+    sink.put(1, 1);
+    sink.put(uint32_t(singleSymbol), 8);
+    return sink.pos;
+  }
+  sink.put(uint32_t(L - 1), 8);
+  uint16_t stack[256];
+  int sp = 0;
+  stack[sp++] = uint16_t(256 + (L - 2));
+  while (sp > 0) {
+    uint16_t n = stack[--sp];
+    if (n < 256) { sink.put(1, 1); sink.put(n, 8); }
+    else { sink.put(0, 1); stack[sp++] = S.right[n - 256]; stack[sp++] = S.left[n - 256]; }
+  }
+  return sink.pos;
+}
+
+// Flush the complete words of the window to the tile's slot and re-base the window.
+// All threads call.  bitPos = total bits produced so far; *gbase = global word index of win[0].
+__device__ void window_flush(HuffEncShared& S, uint32_t* outWords, uint32_t bitPos, uint32_t* gbase, uint32_t capWords) {
+  __syncthreads();
+  uint32_t nWords = (bitPos >> 5) - *gbase;
+  for (uint32_t i = threadIdx.x; i < nWords; i += kThreads)
+    if (*gbase + i < capWords) outWords[*gbase + i] = S.win[i];
+  uint32_t carry = S.win[nWords];
+  __syncthreads();
+  for (uint32_t i = threadIdx.x; i < kWinWords + 4; i += kThreads) S.win[i] = 0;
+  __syncthreads();
+  if (threadIdx.x == 0) S.win[0] = carry;
+  *gbase += nWords;
+  __syncthreads();
+}
+
+// Emit `count` residuals starting at stream index k0 (IPT consecutive per thread).  Returns false (for
+// IPT > 1 only) when the chunk cannot fit the window even after a flush; nothing is written then.
+template <int IPT>
+__device__ bool emit_chunk(HuffEncShared& S, const TileView& t, int pred, uint32_t k0, uint32_t count, uint32_t* outWords,
+                           uint32_t capWords, uint32_t* bitPos, uint32_t* gbase) {
+  uint64_t packed[IPT];
+  int nb[IPT];
+  uint32_t myBits = 0;
+  const uint32_t kBase = k0 + threadIdx.x * IPT;
+#pragma unroll
+  for (int j = 0; j < IPT; j++) {
+    nb[j] = 0;
+    packed[j] = 0;
+    uint32_t k = kBase + j;
+    if (k < k0 + count) {
+      int r, c;
+      stream_to_cell(pred, int(k), t.R, t.C, &r, &c);
+      int32_t res = residual_at(pred, t, r, c);
+      nb[j] = m32_encode(res, &packed[j]);
+      for (int q = 0; q < nb[j]; q++) myBits += S.len[(packed[j] >> (8 * q)) & 0xff];
+    }
+  }
+  uint32_t chunkBits;
+  uint32_t ex = block_exclusive_scan(myBits, S.scan, &chunkBits);
+  if (((*bitPos + chunkBits + 31) >> 5) + 1 - *gbase > uint32_t(kWinWords)) {
+    window_flush(S, outWords, *bitPos, gbase, capWords);
+    if (((*bitPos + chunkBits + 31) >> 5) + 1 - *gbase > uint32_t(kWinWords)) return false;
+  }
+  uint32_t pos = *bitPos + ex;
+  uint32_t w = (pos >> 5) - *gbase;
+  int nacc = int(pos & 31);
+  uint64_t acc = 0;
+  bool first = true;
+#pragma unroll
+  for (int j = 0; j < IPT; j++) {
+    for (int q = 0; q < nb[j]; q++) {
+      uint32_t sym = uint32_t(packed[j] >> (8 * q)) & 0xff;
+      uint64_t c = S.code[sym];
+      int l = S.len[sym];
+      while (l > 0) {
+        int take = l < 64 - nacc ? l : 64 - nacc;
+        uint64_t part = take == 64 ? c : (c & ((uint64_t(1) << take) - 1));
+        acc |= part << nacc;
+        nacc += take;
+        l -= take;
+        c = take == 64 ? 0 : (c >> take);
+        while (nacc >= 32) {
+          if (first) { atomicOr(&S.win[w], uint32_t(acc)); first = false; }
+          else S.win[w] = uint32_t(acc);
+          w++;
+          acc >>= 32;
+          nacc -= 32;
+        }
+      }
+    }
+  }
+  if (nacc > 0 && acc != 0) atomicOr(&S.win[w], uint32_t(acc));
+  *bitPos += chunkBits;
+  return true;
+}
+
+}  // namespace
+
+__global__ void __launch_bounds__(kThreads) huffman_encode_kernel(EncodeArgs a) {
+  extern __shared__ __align__(16) unsigned char smemRaw[];
+  HuffEncShared& S = *reinterpret_cast<HuffEncShared*>(smemRaw);
+  __shared__ int sTile;
+  const int tid = threadIdx.x;
+  const int nTiles = a.band.tiles_down * a.band.tiles_across;
+  for (;;) {
+    __syncthreads();
+    if (tid == 0) sTile = atomicAdd(a.counter, 1);
+    __syncthreads();
+    const int tIdx = sTile;
+    if (tIdx >= nTiles) break;
+    const TileView t = tile_view(a.band, a.grid, tIdx);
+    const int R = t.R, C = t.C, n = R * C;
+    uint8_t* slot = a.slots + size_t(tIdx) * a.slotBytes;
+    uint32_t* outWords = reinterpret_cast<uint32_t*>(slot);
+    const uint32_t capWords = uint32_t(a.slotBytes / 4);
+
+    for (int i = tid; i < 3 * 256; i += kThreads) (&S.hist[0][0])[i] = 0;
+    for (int i = tid; i < kWinWords + 4; i += kThreads) S.win[i] = 0;
+    if (tid == 0) S.hasNull = 0;
+    __syncthreads();
+
+    // ---- pass 1: histograms of the M32 bytes of all three predictors -------------------------------
+    bool sawNull = false;
+    for (int i = tid; i < n; i += kThreads) {
+      int r = i / C, c = i - r * C;
+      if (t.at(r, c) == kNull) sawNull = true;
+      if (i == 0) continue;
+#pragma unroll
+      for (int p = 0; p < 3; p++) {
+        uint64_t packed;
+        int nb = m32_encode(residual_at(p + 1, t, r, c), &packed);
+        for (int q = 0; q < nb; q++) atomicAdd(&S.hist[p][(packed >> (8 * q)) & 0xff], 1u);
+      }
+    }
+    if (sawNull) S.hasNull = 1;
+    __syncthreads();
+    if (S.hasNull) {  // TODO(next): PredictorModelDifferencingWithNulls on the GPU
+      if (tid == 0) { a.lens[tIdx] = 0; a.status[tIdx] = G4_ERR_UNSUPPORTED; a.preds[tIdx] = 0; }
+      continue;
+    }
+
+    // ---- rank sort of (count<<8|symbol) for the three histograms ------------------------------------
+    {
+      uint32_t key[3];
+      int rank[3] = {0, 0, 0};
+#pragma unroll
+      for (int p = 0; p < 3; p++) key[p] = (S.hist[p][tid] << 8) | uint32_t(tid);
+      for (int j = 0; j < 256; j++) {
+#pragma unroll
+        for (int p = 0; p < 3; p++) {
+          uint32_t other = (S.hist[p][j] << 8) | uint32_t(j);
+          rank[p] += other < key[p];
+        }
+      }
+#pragma unroll
+      for (int p = 0; p < 3; p++) S.skey[p][rank[p]] = key[p];
+    }
+    __syncthreads();
+    // ---- candidate sizes ------------------------------------------------------------------------------
+    if ((tid & 31) == 0 && (tid >> 5) < 3) {
+      int p = tid >> 5;
+      int L = 0;
+      uint32_t nBytes = 0;
+      for (int j = 0; j < 256; j++) { uint32_t c = S.skey[p][j] >> 8; L += c > 0; nBytes += c; }
+      S.nLeaf[p] = L;
+      S.nBytes[p] = nBytes;
+      S.textBits[p] = L >= 2 ? merge_size_only(S.skey[p], S.bq[p], L) : 0ull;
+    }
+    __syncthreads();
+    if (tid == 0) {
+      // CodecHuffman.java:89-112: Differencing, Linear, Triangle; keep the strictly smallest byte length
+      unsigned long long best = ~0ull;
+      int win = 0;
+      for (int p = 0; p < 3; p++) {
+        int L = S.nLeaf[p];
+        unsigned long long bits = 80ull + (L == 1 ? 17ull : 8ull + 9ull * L + (L - 1) + S.textBits[p]);
+        unsigned long long bytes = (bits + 7) / 8;
+        if (bytes < best) { best = bytes; win = p; }
+      }
+      S.winner = win;
+      int L = S.nLeaf[win];
+      if (L >= 2) build_winner_tree(S, win, L);
+      uint32_t hdrBits = write_header_and_tree(S, a.codecIndex, win + 1, t.at(0, 0), S.nBytes[win], L,
+                                               int(S.skey[win][255] & 0xff));
+      S.scan[kWarps] = hdrBits;
+      a.lens[tIdx] = uint32_t(best);
+      a.preds[tIdx] = uint8_t(win + 1);
+      a.status[tIdx] = best <= a.slotBytes ? G4_OK : G4_ERR_CAPACITY;
+    }
+    __syncthreads();
+    const int win = S.winner;
+    const int L = S.nLeaf[win];
+    uint32_t bitPos = S.scan[kWarps];
+    uint32_t gbase = 0;
+    const uint32_t nRes = uint32_t(n - 1);
+    if (L >= 2) {
+      // ---- pass 2: emit the winner's text --------------------------------------------------------------
+      for (uint32_t k0 = 0; k0 < nRes; k0 += kThreads * kEmitItems) {
+        uint32_t count = nRes - k0 < uint32_t(kThreads * kEmitItems) ? nRes - k0 : uint32_t(kThreads * kEmitItems);
+        if (!emit_chunk<kEmitItems>(S, t, win + 1, k0, count, outWords, capWords, &bitPos, &gbase)) {
+          for (uint32_t s0 = 0; s0 < count; s0 += kThreads) {
+            uint32_t c1 = count - s0 < uint32_t(kThreads) ? count - s0 : uint32_t(kThreads);
+            emit_chunk<1>(S, t, win + 1, k0 + s0, c1, outWords, capWords, &bitPos, &gbase);
+          }
+        }
+      }
+    }
+    // final flush including the partial last word
+    __syncthreads();
+    {
+      uint32_t nWords = ((bitPos + 31) >> 5) - gbase;
+      for (uint32_t i = tid; i < nWords; i += kThreads)
+        if (gbase + i < capWords) outWords[gbase + i] = S.win[i];
+    }
+  }
+}
+
+// =================================================================================================
+// Decode
+// =================================================================================================
+namespace {
+
+constexpr int kLutBits = 11;
+constexpr int kMaxSub = 2048;                   // sub-sequences per tile (shared arrays)
+constexpr int kSubPerThread = kMaxSub / kThreads;
+
+struct HuffDecShared {
+  uint16_t lut[1 << kLutBits];  // bit15: node reference (low 9 bits = node); else sym | len<<9
+  uint16_t kid[512][2];
+  int16_t leafSym[512];         // -1 for branch nodes
+  uint32_t endpos[kMaxSub];
+  uint16_t cnt[kMaxSub];
+  uint32_t scan[kWarps + 1];
+  uint32_t treeBits;
+  int nLeaf;
+  int single;                   // single-symbol stream: the symbol, else -1
+  int error;
+  int changed;
+};
+
+// HuffmanDecoder.decodeTree (HuffmanDecoder.java:65-161), bounds-checked.  One thread.
+__device__ void parse_tree(HuffDecShared& S, const BitSrc& src) {
+  S.error = 0;
+  S.single = -1;
+  int L = int(src.bits(0, 8)) + 1;
+  S.nLeaf = L;
+  uint32_t pos = 8;
+  if (src.bits(pos, 1)) {
+    S.single = int(src.bits(pos + 1, 8));
+    S.treeBits = 17;
+    if (17 > src.nBits) S.error = 1;
+    return;
+  }
+  pos = 9;
+  uint16_t stack[260];
+  uint8_t slot[512];
+  int nodes = 1, sp = 1, leaves = 0;
+  stack[0] = 0;
+  slot[0] = 0;
+  S.leafSym[0] = -1;
+  while (leaves < L) {
+    if (sp == 0 || nodes >= 511 || pos + 9 > src.nBits + 8) { S.error = 1; return; }
+    int parent = stack[sp - 1];
+    uint32_t bit = src.bits(pos, 1);
+    pos++;
+    int id = nodes++;
+    S.kid[parent][slot[parent]++] = uint16_t(id);
+    if (bit) {
+      S.leafSym[id] = int16_t(src.bits(pos, 8));
+      pos += 8;
+      leaves++;
+      while (sp > 0 && slot[stack[sp - 1]] == 2) sp--;
+    } else {
+      if (sp >= 258) { S.error = 1; return; }
+      S.leafSym[id] = -1;
+      slot[id] = 0;
+      stack[sp++] = uint16_t(id);
+    }
+  }
+  if (sp != 0 || pos > src.nBits) { S.error = 1; return; }  // incomplete tree / truncated stream
+  S.treeBits = pos;
+}
+
+// Decode one symbol at *pos.
+__device__ __forceinline__ int decode_symbol(const HuffDecShared& S, const BitSrc& src, uint32_t* pos) {
+  uint32_t v = src.peek32(*pos);
+  uint32_t e = S.lut[v & ((1u << kLutBits) - 1)];
+  if (!(e & 0x8000u)) {
+    *pos += (e >> 9) & 15u;
+    return int(e & 0xffu);
+  }
+  int n = int(e & 0x1ffu);
+  int consumed = kLutBits;
+  uint32_t p = *pos;
+  while (S.leafSym[n] < 0) {
+    if (consumed == 32) { p += 32; v = src.peek32(p); consumed = 0; }
+    n = S.kid[n][(v >> consumed) & 1u];
+    consumed++;
+  }
+  *pos = p + consumed;
+  return S.leafSym[n];
+}
+
+__device__ __forceinline__ void decode_subseq(const HuffDecShared& S, const BitSrc& src, uint32_t start, uint32_t limit,
+                                              uint32_t* endOut, uint32_t* cntOut) {
+  uint32_t pos = start, c = 0;
+  while (pos < limit) { decode_symbol(S, src, &pos); c++; }
+  *endOut = pos;
+  *cntOut = c;
+}
+
+}  // namespace
+
+// Decodes the legacy Huffman text of `nSym` symbols that starts at bit `src` position 0 (tree first) into
+// `out` (memory visible to the CTA).  Returns the bit position just after the last symbol through
+// *endBit.  Shared by CodecHuffman decode and the LSOP12 legacy-Huffman variant.  All threads call.
+__device__ bool huffman_decode_stream(HuffDecShared& S, const BitSrc& src, uint32_t nSym, uint8_t* out, uint32_t* endBit) {
+  const int tid = threadIdx.x;
+  __syncthreads();
+  if (tid == 0) parse_tree(S, src);
+  __syncthreads();
+  if (S.error) return false;
+  if (S.single >= 0) {
+    for (uint32_t i = tid; i < nSym; i += kThreads) out[i] = uint8_t(S.single);
+    *endBit = S.treeBits;
+    __syncthreads();
+    return true;
+  }
+  // lookup table: every thread resolves a slice of the 2^11 prefixes by walking the tree
+  for (int e = tid; e < (1 << kLutBits); e += kThreads) {
+    int n = 0;
+    uint16_t entry = 0;
+    int d = 0;
+    for (; d < kLutBits; d++) {
+      n = S.kid[n][(e >> d) & 1];
+      if (S.leafSym[n] >= 0) { entry = uint16_t(S.leafSym[n] | ((d + 1) << 9)); break; }
+    }
+    if (d == kLutBits) entry = uint16_t(0x8000u | n);
+    S.lut[e] = entry;
+  }
+  __syncthreads();
+  const uint32_t T0 = S.treeBits;
+  const uint32_t avail = src.nBits - T0;
+  uint32_t B = (avail + kMaxSub - 1) / kMaxSub;
+  B = (B + 31u) & ~31u;
+  if (B < 128u) B = 128u;
+  const int nSub = int((avail + B - 1) / B);
+  // pass 0: speculative decode of every sub-sequence from its nominal start
+  uint32_t myStart[kSubPerThread];
+#pragma unroll
+  for (int j = 0; j < kSubPerThread; j++) {
+    int i = tid + j * kThreads;
+    myStart[j] = T0 + uint32_t(i) * B;
+    if (i < nSub) {
+      uint32_t limit = T0 + uint32_t(i + 1) * B;
+      if (limit > src.nBits) limit = src.nBits;
+      uint32_t e, c;
+      decode_subseq(S, src, myStart[j], limit, &e, &c);
+      S.endpos[i] = e;
+      S.cnt[i] = uint16_t(c);
+    }
+  }
+  // synchronisation passes: sub-sequence i must start where i-1 ended
+  for (int pass = 0; pass < nSub; pass++) {
+    __syncthreads();
+    if (tid == 0) S.changed = 0;
+    uint32_t ns[kSubPerThread];
+#pragma unroll
+    for (int j = 0; j < kSubPerThread; j++) {
+      int i = tid + j * kThreads;
+      ns[j] = (i > 0 && i < nSub) ? S.endpos[i - 1] : myStart[j];
+    }
+    __syncthreads();
+    bool any = false;
+#pragma unroll
+    for (int j = 0; j < kSubPerThread; j++) {
+      int i = tid + j * kThreads;
+      if (i < nSub && ns[j] != myStart[j]) {
+        myStart[j] = ns[j];
+        uint32_t limit = T0 + uint32_t(i + 1) * B;
+        if (limit > src.nBits) limit = src.nBits;
+        uint32_t e, c;
+        decode_subseq(S, src, myStart[j], limit, &e, &c);
+        S.endpos[i] = e;
+        S.cnt[i] = uint16_t(c);
+        any = true;
+      }
+    }
+    if (any) S.changed = 1;
+    __syncthreads();
+    if (!S.changed) break;
+  }
+  // symbol offsets of the sub-sequences
+  uint32_t local[kSubPerThread];
+  uint32_t mySum = 0;
+  // thread tid owns sub-sequences tid*kSubPerThread .. +kSubPerThread-1 for the scan (contiguous)
+#pragma unroll
+  for (int j = 0; j < kSubPerThread; j++) {
+    int i = tid * kSubPerThread + j;
+    local[j] = i < nSub ? S.cnt[i] : 0u;
+    mySum += local[j];
+  }
+  uint32_t total;
+  uint32_t ex = block_exclusive_scan(mySum, S.scan, &total);
+  if (total < nSym) return false;  // text shorter than the header claims
+  __syncthreads();
+  __shared__ uint32_t sOff[kMaxSub];  // first output symbol index of every sub-sequence
+  {
+    uint32_t run = ex;
+#pragma unroll
+    for (int j = 0; j < kSubPerThread; j++) {
+      int i = tid * kSubPerThread + j;
+      if (i < nSub) sOff[i] = run;
+      run += local[j];
+    }
+  }
+  __syncthreads();
+  // write pass
+  uint32_t lastEnd = 0;
+#pragma unroll
+  for (int j = 0; j < kSubPerThread; j++) {
+    int i = tid + j * kThreads;
+    if (i < nSub) {
+      uint32_t pos = myStart[j];
+      uint32_t limit = T0 + uint32_t(i + 1) * B;
+      if (limit > src.nBits) limit = src.nBits;
+      uint32_t o = sOff[i];
+      while (pos < limit && o < nSym) {
+        int s = decode_symbol(S, src, &pos);
+        out[o++] = uint8_t(s);
+        if (o == nSym) lastEnd = pos;  // this thread decoded the final symbol
+      }
+    }
+  }
+  if (lastEnd) S.scan[kWarps] = lastEnd;
+  __syncthreads();
+  *endBit = S.scan[kWarps];
+  return true;
+}
+
+__global__ void __launch_bounds__(kThreads) huffman_decode_kernel(DecodeArgs a) {
+  __shared__ HuffDecShared S;
+  __shared__ int sTile;
+  const int tid = threadIdx.x;
+  for (;;) {
+    __syncthreads();
+    if (tid == 0) sTile = atomicAdd(a.counter, 1);
+    __syncthreads();
+    const int li = sTile;
+    if (li >= *a.listCount) break;
+    const int tIdx = a.list[li];
+    const TileView t = tile_view(a.band, a.grid, tIdx);
+    const int n = t.R * t.C;
+    const uint8_t* packing = a.arena + a.offsets[tIdx];
+    const uint32_t len = a.lens[tIdx];
+    int status = G4_OK;
+    // CodecHuffman.decode header (CodecHuffman.java:134-143)
+    int pred = len >= 10 ? int(packing[1]) : 0;
+    int32_t seed = len >= 10 ? int32_t(load_le32(packing + 2)) : 0;
+    uint32_t nM32 = len >= 10 ? load_le32(packing + 6) : 0;
+    const uint32_t expect = pred == G4_PRED_DIFF_NULLS ? uint32_t(n) : uint32_t(n - 1);
+    if (len < 12 || pred < 1 || pred > 4 || nM32 < expect || nM32 > uint32_t(6 * n)) status = G4_ERR_FORMAT;
+    else if (pred == G4_PRED_DIFF_NULLS) status = G4_ERR_UNSUPPORTED;  // TODO(next): nulls on the GPU
+    if (status == G4_OK) {
+      BitSrc src;
+      src.init(packing + 10, len - 10);
+      uint8_t* m32 = a.scratch + size_t(blockIdx.x) * a.scratchStride;
+      uint32_t endBit;
+      if (!huffman_decode_stream(S, src, nM32, m32, &endBit)) status = G4_ERR_FORMAT;
+      else {
+        __syncthreads();
+        if (tid == 0) t.at(0, 0) = seed;
+        if (!m32_parse_to_cells(m32, nM32, pred, t, expect, S.scan)) status = G4_ERR_FORMAT;
+        else {
+          __syncthreads();
+          if (tid == 0) t.at(0, 0) = seed;
+          __syncthreads();
+          predictor_inverse(pred, t, S.scan);
+        }
+      }
+    }
+    if (tid == 0) a.status[tIdx] = status;
+  }
+}
+
+cudaError_t launch_huffman_encode(const EncodeArgs& a, int nCtas, cudaStream_t s) {
+  static bool attr = false;
+  if (!attr) {
+    cudaError_t e = cudaFuncSetAttribute(huffman_encode_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, int(sizeof(HuffEncShared)));
+    if (e != cudaSuccess) return e;
+    attr = true;
+  }
+  huffman_encode_kernel<<<nCtas, kThreads, sizeof(HuffEncShared), s>>>(a);
+  return cudaGetLastError();
+}
+
+cudaError_t launch_huffman_decode(const DecodeArgs& a, int nCtas, cudaStream_t s) {
+  huffman_decode_kernel<<<nCtas, kThreads, 0, s>>>(a);
+  return cudaGetLastError();
+}
+
+}  // namespace g4

@@ -1,0 +1,94 @@
+// g4_kernels.h -- kernel argument blocks and launch entry points shared by the codec translation units.
+#pragma once
+#include <cstddef>
+#include <cstdint>
+#include <cuda_runtime.h>
+#include "../../include/g4codec.h"
+
+namespace g4 {
+
+// One candidate-encoder launch: every tile of the band is encoded by ONE codec into its own fixed-size
+// slot (slot t at slots + t*slotBytes, 16-byte aligned).  lens[t] = packing length (0 = declined).
+struct EncodeArgs {
+  g4_band_desc band;
+  void* grid;           // device raster (band upper-left cell)
+  uint8_t* slots;
+  size_t slotBytes;
+  uint32_t* lens;
+  uint8_t* preds;       // packing[1] of the candidate
+  int32_t* status;      // G4_OK / G4_DECLINED / error
+  int* counter;         // persistent-CTA work counter (zeroed before launch)
+  int codecIndex;       // list position of this codec == packing[0]
+  uint8_t* scratch;     // per-CTA scratch (codec specific)
+  size_t scratchStride;
+};
+
+// One decoder launch over the tiles of one codec kind: list[0..*listCount) are tile indices.
+struct DecodeArgs {
+  g4_band_desc band;
+  void* grid;
+  const uint8_t* arena;
+  const uint64_t* offsets;
+  const uint32_t* lens;
+  const int* list;
+  const int* listCount;
+  int32_t* status;
+  int* counter;
+  uint8_t* scratch;     // per-CTA scratch (M32 bytes etc.), blockIdx.x * scratchStride
+  size_t scratchStride;
+};
+
+struct SelectArgs {
+  int nTiles, nCand;
+  uint32_t rawLen;              // 4 * tile_rows * tile_cols
+  const uint32_t* candLens;     // [nCand][nTiles]
+  const uint8_t* candPreds;     // [nCand][nTiles]
+  const int32_t* candStatus;    // [nCand][nTiles]
+  int candIndex[G4_MAX_CODECS]; // codec list position of candidate c
+  uint32_t* lens;               // out: payload length per tile
+  uint8_t* codecOut;
+  uint8_t* predOut;
+  int* src;                     // out: winning candidate (-1 = raw)
+  int32_t* status;
+};
+
+struct CompactArgs {
+  g4_band_desc band;
+  void* grid;
+  const uint8_t* slots[G4_MAX_CODECS];
+  size_t slotBytes;
+  const uint32_t* lens;
+  const uint64_t* offsets;
+  const int* src;
+  uint8_t* arena;
+  uint64_t arenaCap;
+  int32_t* status;
+};
+
+struct ClassifyArgs {
+  int nTiles;
+  int elemType;
+  uint32_t rawLen;
+  g4_codec_list codecs;
+  const uint8_t* arena;
+  const uint64_t* offsets;
+  const uint32_t* lens;
+  int* lists;    // [G4_CODEC_COUNT + 1][nTiles]
+  int* counts;   // [G4_CODEC_COUNT + 1], zeroed before launch
+  int32_t* status;
+};
+
+cudaError_t launch_fill_terrain(int elemType, uint64_t seed, int64_t row0, int64_t col0, int64_t nRows, int64_t nCols, void* out,
+                                cudaStream_t s);
+cudaError_t launch_select(const SelectArgs& a, cudaStream_t s);
+cudaError_t launch_offsets(const uint32_t* lens, uint64_t* offsets, int nTiles, uint64_t* total, cudaStream_t s);
+cudaError_t launch_compact(const CompactArgs& a, int nTiles, cudaStream_t s);
+cudaError_t launch_classify(const ClassifyArgs& a, cudaStream_t s);
+cudaError_t launch_raw_decode(const DecodeArgs& a, int nTiles, cudaStream_t s);
+
+// ---- codec kernels -----------------------------------------------------------------------------
+// Host-side launchers (defined next to their kernels).  nCtas persistent CTAs of kThreads threads.
+cudaError_t launch_huffman_encode(const EncodeArgs& a, int nCtas, cudaStream_t s);
+cudaError_t launch_huffman_decode(const DecodeArgs& a, int nCtas, cudaStream_t s);
+
+}  // namespace g4

@@ -1,0 +1,141 @@
+/* g4codec.h -- C ABI of the B200-native GVRS tile-codec library (libg4codec.so).
+ *
+ * Drop-in boundary for Gridfour's codec plugin API.  Paths cite the reference tree
+ * /root/reference/core/src/main/java/org/gridfour/ ("C/").  A Java host binds these symbols through
+ * Panama FFM / JNI over pinned direct ByteBuffers (see INTEGRATION.md and java/); every pointer here
+ * is a plain address + size, no CUDA or torch types cross the boundary.
+ *
+ * Reference interfaces replaced:
+ *   ICompressionEncoder.encode / encodeFloats          C/compress/ICompressionEncoder.java:61,76
+ *   ICompressionDecoder.decode / decodeFloats          C/compress/ICompressionDecoder.java:62,105
+ *   CodecMaster.encode / decode (best-of + dispatch)   C/gvrs/CodecMaster.java:142-203
+ *   TileElementInt/Float.encode/decode (raw fallback)  C/gvrs/TileElementInt.java:196-219
+ *   + the NEW batched encodeTiles / decodeTiles entry the tile cache calls
+ *     (natural call sites: C/gvrs/RasterTileCache.java:286-294,339-426, C/gvrs/RecordManager.java:386-515)
+ *
+ * All compute runs in CUDA kernels for sm_100a.  There is no CPU fallback: every entry point returns
+ * G4_ERR_CUDA when no device is usable.
+ */
+#ifndef G4CODEC_H
+#define G4CODEC_H
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define G4_ABI_VERSION 1
+
+/* Status codes.  G4_DECLINED is the Java `null` return of ICompressionEncoder.encode ("codec cannot or
+ * should not encode this tile": all-null tile, tile too small for the predictor, singular LSOP matrix).
+ * Negative values are errors; the Java shim maps G4_ERR_FORMAT to IOException
+ * (C/compress/CodecHuffman.java:166-167, C/compress/CodecDeflate.java:150-152). */
+enum {
+  G4_OK = 0,
+  G4_DECLINED = 1,
+  G4_ERR_ARG = -1,      /* bad argument (IllegalArgumentException in the reference) */
+  G4_ERR_FORMAT = -2,   /* malformed packing (IOException) */
+  G4_ERR_CAPACITY = -3, /* caller's output buffer too small; *out_len holds the size needed */
+  G4_ERR_CUDA = -4,     /* no device / CUDA failure; g4_last_error() has the text */
+  G4_ERR_UNSUPPORTED = -5
+};
+
+/* Codec kinds, named by the identification strings the GVRS file header stores
+ * (C/gvrs/GvrsCodecType.java:43-61, C/lsop/LsCodecUtility.java:53). */
+enum {
+  G4_CODEC_HUFFMAN = 0,       /* "GvrsHuffman"          C/compress/CodecHuffman.java */
+  G4_CODEC_DEFLATE = 1,       /* "GvrsDeflate"          C/compress/CodecDeflate.java */
+  G4_CODEC_FLOAT = 2,         /* "GvrsFloat"            C/compress/CodecFloat.java */
+  G4_CODEC_CANON_HUFFMAN = 3, /* "GvrsCanonicalHuffman" C/compress/canonicalHuffman/CodecCanonHuffman.java */
+  G4_CODEC_LSOP12 = 4,        /* "LSOP12"               C/lsop/LsEncoder12.java + LsDecoder12.java */
+  G4_CODEC_COUNT = 5
+};
+
+/* Predictor codes stored in packing[1] (C/compress/PredictorModelType.java:46-63). */
+enum { G4_PRED_NONE = 0, G4_PRED_DIFFERENCING = 1, G4_PRED_LINEAR = 2, G4_PRED_TRIANGLE = 3, G4_PRED_DIFF_NULLS = 4 };
+
+enum { G4_ELEM_I32 = 0, G4_ELEM_F32 = 1 };
+enum { G4_MEM_HOST = 0, G4_MEM_DEVICE = 1 };
+
+#define G4_MAX_CODECS 16
+#define G4_CODEC_RAW 255 /* per-tile codec byte for "stored raw" (len == 4*nRows*nCols) */
+
+typedef struct g4_context g4_context; /* one CUDA stream + scratch; not shareable between threads */
+
+/* The codec list of a GvrsFileSpecification: position k is the codec index written to packing[0]
+ * (C/gvrs/GvrsFileSpecification.java:1576-1631, C/gvrs/CodecMaster.java:153-167). */
+typedef struct {
+  int32_t n_codecs;
+  int32_t codec_ids[G4_MAX_CODECS];
+} g4_codec_list;
+
+/* A rectangular band of full-size tiles inside a row-major raster of 4-byte samples.
+ * Tile t = tr * tiles_across + tc covers rows [tr*tile_rows, ...) and cols [tc*tile_cols, ...) of the
+ * buffer passed as `grid` (whose first sample is the band's upper-left cell). */
+typedef struct {
+  int32_t elem_type; /* G4_ELEM_I32 or G4_ELEM_F32 */
+  int32_t tile_rows, tile_cols;
+  int32_t tiles_down, tiles_across;
+  int64_t grid_pitch; /* samples per raster row (>= tiles_across*tile_cols) */
+} g4_band_desc;
+
+int g4_abi_version(void);
+const char* g4_status_string(int status);
+const char* g4_last_error(void); /* thread-local text of the last G4_ERR_CUDA */
+int g4_device_count(void);
+
+/* "GvrsHuffman" -> G4_CODEC_HUFFMAN ...; -1 for an unknown name. */
+int g4_codec_id_from_name(const char* name);
+const char* g4_codec_name(int codec_id);
+
+/* device: CUDA ordinal.  cuda_stream: an existing cudaStream_t to launch on (NULL = the context
+ * creates its own non-blocking stream). */
+int g4_context_create(int device, void* cuda_stream, g4_context** out);
+void g4_context_destroy(g4_context* ctx);
+int g4_context_synchronize(g4_context* ctx);
+
+/* ---- per-tile entry points (exact ICompressionEncoder / ICompressionDecoder semantics) ----------
+ * Host buffers.  encode: packing[0] == codec_index; returns G4_DECLINED where the Java codec returns
+ * null.  *predictor (optional) receives packing[1]'s predictor code (LSOP12: the compression type). */
+int g4_encode_i32(g4_context* ctx, int codec_id, int codec_index, int n_rows, int n_cols, const int32_t* values,
+                  uint8_t* out, size_t out_cap, size_t* out_len, int* predictor);
+int g4_decode_i32(g4_context* ctx, int codec_id, int n_rows, int n_cols, const uint8_t* packing, size_t len,
+                  int32_t* out);
+int g4_encode_f32(g4_context* ctx, int codec_id, int codec_index, int n_rows, int n_cols, const float* values,
+                  uint8_t* out, size_t out_cap, size_t* out_len);
+int g4_decode_f32(g4_context* ctx, int codec_id, int n_rows, int n_cols, const uint8_t* packing, size_t len,
+                  float* out);
+
+/* ---- batched entry points (new) -----------------------------------------------------------------
+ * encode: for every tile run every integer (or float) codec of `codecs`, keep the strictly smallest
+ * (ties -> lowest index, CodecMaster.encodeSingleThread), store raw little-endian samples when nothing
+ * beats 4*n bytes (TileElementInt.encode).  Payloads are packed back to back into `arena` in tile
+ * order; offsets[t]/lens[t] locate tile t.  codec_out[t] = winning codec index or G4_CODEC_RAW;
+ * predictor_out[t] = packing[1].  All buffers live in `mem_space` (host buffers should be pinned:
+ * direct ByteBuffers).  *total_bytes receives the arena bytes used (host value, always).
+ * decode: the inverse; len == 4*n means raw (TileElementInt.decode), otherwise packing[0] indexes
+ * `codecs`.  status[t] is per tile; the call's return value is the first non-OK tile status or G4_OK. */
+int g4_encode_tiles(g4_context* ctx, const g4_codec_list* codecs, const g4_band_desc* band, int mem_space,
+                    const void* grid, uint8_t* arena, uint64_t arena_cap, uint64_t* offsets, uint32_t* lens,
+                    uint8_t* codec_out, uint8_t* predictor_out, int32_t* status, uint64_t* total_bytes);
+int g4_decode_tiles(g4_context* ctx, const g4_codec_list* codecs, const g4_band_desc* band, int mem_space,
+                    const uint8_t* arena, const uint64_t* offsets, const uint32_t* lens, void* grid,
+                    int32_t* status);
+
+/* Upper bound of the arena bytes g4_encode_tiles can produce for a band (4*n per tile). */
+uint64_t g4_encode_arena_bound(const g4_band_desc* band);
+
+/* ---- benchmark support --------------------------------------------------------------------------
+ * Fills a device raster with the synthetic fractal terrain of include/g4terrain.h
+ * (rows [row0,row0+n_rows) x cols [col0,col0+n_cols) of the virtual global grid). */
+int g4_fill_terrain(g4_context* ctx, int elem_type, uint64_t seed, int64_t row0, int64_t col0, int64_t n_rows,
+                    int64_t n_cols, void* device_out);
+/* Kernel launches issued through this context since creation (bench.py's gpu_launches claim). */
+uint64_t g4_launch_count(const g4_context* ctx);
+
+#ifdef __cplusplus
+}
+#endif
+#endif
