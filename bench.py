@@ -1,0 +1,316 @@
+#!/usr/bin/env python3
+"""bench.py -- GVRS tile decode/encode throughput (BASELINE.json metric) on N B200s of one node.
+
+Workload (N=1 and per rank at N>1, weak scaling): the per-GPU shard of BASELINE.json config 3 --
+30 tile rows x 360 tile columns = 10,800 tiles of 180x240 int32 samples (5,400 x 86,400 samples,
+1.866 GB raw) of the synthetic fractal terrain (include/g4terrain.h), rank r holding tile rows
+[30r, 30r+30) of the 240-row global grid.  Codec list = config 3's [GvrsHuffman, GvrsDeflate, LSOP12]
+restricted to the codecs whose CUDA kernels exist (named in config.workload).
+
+A step = one decode pass over the shard (the headline direction).  `value` = 4 B x samples / device
+time with compressed payloads resident in HBM; `e2e` = the same through g4_decode_tiles with HOST
+(pinned) buffers, H2D of the payloads and D2H of the decoded raster inside the timed region.
+Encode throughput of the same shard is reported in `encode`.
+
+--impl reference: the reference's algorithm on the host cores.  The reference is Java and no JVM exists
+in this image, so this arm times the C++ oracle (oracle/, a line-by-line restatement) with a tile thread
+pool over all host cores on a bounded sample of the same workload.
+"""
+import argparse
+import json
+import os
+import subprocess
+import sys
+import threading
+import time
+
+import numpy as np
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, ROOT)
+
+TILE_R, TILE_C = 180, 240
+TILE_ROWS_PER_GPU, TILES_ACROSS = 30, 360
+GLOBAL_TILE_ROWS = 240
+CONFIG3 = ["GvrsHuffman", "GvrsDeflate", "LSOP12"]
+ORACLE_IDS = {"GvrsHuffman": 0, "GvrsDeflate": 1, "GvrsFloat": 2, "GvrsCanonicalHuffman": 3, "LSOP12": 4}
+METRIC = "GVRS tile decode GB/s of raw samples (config 3 shard, 180x240 tiles)"
+
+
+def peaks():
+    p = os.path.join(ROOT, "MEASURED_PEAKS.json")
+    if os.path.exists(p):
+        return float(json.load(open(p))["hbm_gbs"]), "measured (MEASURED_PEAKS.json)"
+    return 6650.0, "fallback (B200_PROFILING.md)"
+
+
+class ClockSampler(threading.Thread):
+    """nvidia-smi clocks + throttle reasons during the timed region (B200_PROFILING.md)."""
+
+    def __init__(self, index):
+        super().__init__(daemon=True)
+        self.index, self.rows, self.stop_flag, self.proc = index, [], False, None
+
+    def run(self):
+        q = ("clocks.sm,clocks.max.sm,clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown,"
+             "clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap")
+        try:
+            self.proc = subprocess.Popen(["nvidia-smi", "-i", str(self.index), "--query-gpu=" + q, "--format=csv,noheader,nounits",
+                                          "-lms", "100"], stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
+            for line in self.proc.stdout:
+                if self.stop_flag:
+                    break
+                self.rows.append([x.strip() for x in line.split(",")])
+        except Exception:
+            pass
+
+    def finish(self):
+        self.stop_flag = True
+        if self.proc:
+            self.proc.terminate()
+        sm = [float(r[0]) for r in self.rows if len(r) >= 6 and r[0].replace(".", "").isdigit()]
+        mx = [float(r[1]) for r in self.rows if len(r) >= 6 and r[1].replace(".", "").isdigit()]
+        names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
+        reasons = sorted({names[i] for r in self.rows if len(r) >= 6 for i in range(4) if r[2 + i].lower().startswith("active")})
+        return {"sm_mhz": float(np.median(sm)) if sm else None, "sm_max_mhz": max(mx) if mx else None, "reasons": reasons,
+                "samples": len(sm)}
+
+
+def cpu_arm(codecs, threads, budget_s, oracle):
+    """Times the oracle's decode (and encode) of a bounded sample: whole tile columns of the shard's first tile row."""
+    ids = [ORACLE_IDS[c] for c in codecs]
+    n_tiles = 24
+    while True:
+        grid = oracle.terrain_i32(0, 0, TILE_R, n_tiles * TILE_C, n_threads=threads)
+        t0 = time.perf_counter()
+        arena, slot, lens = oracle.encode_grid(ids, grid, TILE_R, TILE_C, n_threads=threads)
+        t_enc = time.perf_counter() - t0
+        off = (np.arange(lens.size) * slot).astype(np.uint64)
+        t0 = time.perf_counter()
+        out = oracle.decode_grid(ids, arena, off, lens, TILE_R, n_tiles * TILE_C, TILE_R, TILE_C, n_threads=threads)
+        t_dec = time.perf_counter() - t0
+        assert np.array_equal(out, grid)
+        if t_enc + t_dec > budget_s / 4 or n_tiles >= TILES_ACROSS:
+            break
+        n_tiles = min(TILES_ACROSS, n_tiles * 4)
+    raw = grid.size * 4
+    return {"decode_gbs": raw / t_dec / 1e9, "encode_gbs": raw / t_enc / 1e9, "tiles": n_tiles, "dec_s": t_dec, "enc_s": t_enc,
+            "bits_per_sample": 8.0 * float(lens.sum()) / grid.size}
+
+
+def run_reference(args, rank):
+    if rank != 0:
+        return
+    from oracle import g4oracle as oracle
+
+    oracle.build()
+    threads = oracle.hardware_threads()
+    codecs = CONFIG3
+    vals = []
+    res = None
+    for _ in range(args.warmup):
+        res = cpu_arm(codecs, threads, 6.0, oracle)
+    t0 = time.perf_counter()
+    for _ in range(args.steps):
+        res = cpu_arm(codecs, threads, 6.0, oracle)
+        vals.append(res["decode_gbs"])
+    wall = time.perf_counter() - t0
+    v = float(np.mean(vals))
+    sample = "%d tiles of 180x240 (first tile row of the shard) per step, decode timed separately from encode" % res["tiles"]
+    line = {
+        "impl": "reference", "metric": METRIC, "value": v, "unit": "GB/s", "n_gpus": args.gpus, "steps": args.steps,
+        "warmup": args.warmup, "ms_per_step": 1000.0 * wall / max(1, args.steps), "higher_is_better": True, "scaling": "weak",
+        "vs_baseline": None, "dtype": "int32", "data": "synthetic",
+        "config": {"workload": "config3 shard sample, codecs=%s, C++ restatement of the reference (no JVM in this image), tile "
+                               "thread pool" % "+".join(codecs)},
+        "cpu_baseline": {"value": v, "unit": "GB/s", "cores": threads, "kind": "port", "sample": sample,
+                         "encode_value": res["encode_gbs"], "bits_per_sample": res["bits_per_sample"]},
+        "e2e": {"value": v, "unit": "GB/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+    }
+    print(json.dumps(line))
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=10)
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--impl", default="ours")
+    ap.add_argument("--tile-rows", type=int, default=TILE_ROWS_PER_GPU, help="tile rows per GPU (default: the config-3 shard)")
+    ap.add_argument("--cpu-seconds", type=float, default=12.0)
+    ap.add_argument("--no-e2e", action="store_true")
+    args = ap.parse_args()
+    args.warmup = max(args.warmup, 3)
+    rank = int(os.environ.get("RANK", "0"))
+    local_rank = int(os.environ.get("LOCAL_RANK", "0"))
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    if args.impl == "reference":
+        run_reference(args, rank)
+        return
+
+    import torch
+    import torch.distributed as dist
+
+    import gridfour_b200 as g4
+    from gridfour_b200 import _lib
+
+    torch.cuda.set_device(local_rank)
+    dev = torch.device("cuda", local_rank)
+    if world > 1:
+        os.environ.setdefault("MASTER_ADDR", "127.0.0.1")
+        dist.init_process_group("nccl", device_id=dev)
+    L = _lib.lib()
+    codecs = [c for c in CONFIG3 if L.g4_codec_supported(ORACLE_IDS[c], 0) and L.g4_codec_supported(ORACLE_IDS[c], 1)]
+    missing = [c for c in CONFIG3 if c not in codecs]
+    spec = g4.CodecSpecification(default=False)
+    std = {"GvrsHuffman": (g4.CodecHuffman, g4.CodecHuffman), "GvrsDeflate": (g4.CodecDeflate, g4.CodecDeflate),
+           "LSOP12": (g4.LsEncoder12, g4.LsDecoder12)}
+    for c in codecs:
+        spec.addCompressionCodec(c, *std[c])
+    # the context launches on torch's current stream so torch.cuda.Event brackets exactly the library's kernels
+    stream = torch.cuda.Stream(dev)
+    torch.cuda.set_stream(stream)
+    ctx = g4.Context(local_rank, stream.cuda_stream)
+    master = g4.CodecMaster(spec, ctx)
+
+    rows, cols = args.tile_rows * TILE_R, TILES_ACROSS * TILE_C
+    n_tiles = args.tile_rows * TILES_ACROSS
+    samples = rows * cols
+    grid = torch.empty((rows, cols), dtype=torch.int32, device=dev)
+    row0 = (rank % (GLOBAL_TILE_ROWS // args.tile_rows)) * rows
+    ctx.fill_terrain(grid.data_ptr(), 0, row0, 0, rows, cols)
+    torch.cuda.synchronize(dev)
+
+    def barrier():
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize(dev)
+
+    # ---- encode (also produces the decode input) --------------------------------------------------------
+    ctx.set_timing(True)
+    enc_ms = []
+    batch = None
+    for i in range(3):
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        barrier()
+        e0.record(stream)
+        batch = master.encodeTiles(grid, TILE_R, TILE_C)
+        e1.record(stream)
+        torch.cuda.synchronize(dev)
+        enc_ms.append(e0.elapsed_time(e1))
+    enc_kernel_ms = {c: ctx.kernel_time_ms(1, ORACLE_IDS[c]) for c in codecs}
+    lens = batch.lens.cpu().numpy().astype(np.int64)
+    codec_hist = np.bincount(batch.codec.cpu().numpy(), minlength=256)
+    total_payload = int(lens.sum())
+    bits_per_sample = 8.0 * total_payload / samples
+    out = torch.zeros_like(grid)
+
+    # ---- decode: device-resident, K timed steps ------------------------------------------------------------
+    launches0 = ctx.launch_count
+    for _ in range(args.warmup):
+        master.decodeTiles(batch, out=out)
+    torch.cuda.synchronize(dev)
+    assert torch.equal(out, grid), "decode does not reproduce the input raster"
+    launches_per_step = (ctx.launch_count - launches0) // args.warmup
+    sampler = ClockSampler(local_rank)
+    sampler.start()
+    time.sleep(0.3)
+    kernel_ms = {}
+    barrier()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    e0.record(stream)
+    for _ in range(args.steps):
+        master.decodeTiles(batch, out=out)
+        for c in codecs:
+            ms = ctx.kernel_time_ms(0, ORACLE_IDS[c])
+            if ms is not None:
+                kernel_ms.setdefault(c, []).append(ms)
+    e1.record(stream)
+    barrier()
+    t_dec = e0.elapsed_time(e1) / 1000.0
+    clocks = sampler.finish()
+    t = torch.tensor([t_dec, float(np.mean(enc_ms[1:])) / 1000.0], dtype=torch.float64, device=dev)
+    if world > 1:
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+    t_dec, t_enc = float(t[0]), float(t[1])
+    value = 4.0 * samples * world * args.steps / t_dec / 1e9
+    enc_value = 4.0 * samples * world / t_enc / 1e9
+
+    # ---- e2e: host buffers through the C ABI ------------------------------------------------------------------
+    e2e = None
+    if not args.no_e2e:
+        h_arena = torch.empty(batch.total_bytes, dtype=torch.uint8).pin_memory()
+        h_arena.copy_(batch.arena[: batch.total_bytes])
+        h_off = batch.offsets.cpu().numpy().astype(np.uint64)
+        h_len = batch.lens.cpu().numpy().astype(np.uint32)
+        h_grid = torch.empty((rows, cols), dtype=torch.int32).pin_memory()
+        hb = g4.TileBatch(h_arena.numpy(), h_off, h_len, None, None, None, batch.total_bytes, batch.band)
+        e2e_steps = max(2, min(args.steps, 4))
+        master.decodeTiles(hb, out=h_grid.numpy())
+        barrier()
+        t0 = time.perf_counter()
+        for _ in range(e2e_steps):
+            master.decodeTiles(hb, out=h_grid.numpy())
+        torch.cuda.synchronize(dev)
+        t_e2e = time.perf_counter() - t0
+        tt = torch.tensor([t_e2e], dtype=torch.float64, device=dev)
+        if world > 1:
+            dist.all_reduce(tt, op=dist.ReduceOp.MAX)
+        assert np.array_equal(h_grid.numpy()[:TILE_R], grid[:TILE_R].cpu().numpy())
+        e2e = {"value": 4.0 * samples * world * e2e_steps / float(tt[0]) / 1e9, "unit": "GB/s",
+               "h2d_bytes_per_step": int(batch.total_bytes + h_off.nbytes + h_len.nbytes),
+               "d2h_bytes_per_step": int(samples * 4 + n_tiles * 4), "steps": e2e_steps}
+
+    if rank != 0:
+        if world > 1:
+            dist.destroy_process_group()
+        return
+    # ---- roofline of the dominant decode kernel ----------------------------------------------------------------
+    peak, peak_src = peaks()
+    dom = max(kernel_ms, key=lambda c: np.mean(kernel_ms[c])) if kernel_ms else None
+    roofline = None
+    if dom:
+        kind = ORACLE_IDS[dom]
+        idx = [k for k, c in enumerate(codecs) if c == dom][0]
+        tiles_dom = int(codec_hist[idx])
+        bytes_dom = int(lens[batch.codec.cpu().numpy() == idx].sum())
+        alg_bytes = 4.0 * tiles_dom * TILE_R * TILE_C + bytes_dom  # raw samples written once + payload read once
+        ms = float(np.mean(kernel_ms[dom]))
+        achieved = alg_bytes / (ms / 1000.0) / 1e9
+        roofline = {"bound": "hbm", "kernel": "%s decode" % dom, "achieved": achieved, "peak": peak, "unit": "GB/s",
+                    "frac": achieved / peak, "traffic": None, "peak_source": peak_src, "kernel_ms": ms,
+                    "algorithmic_bytes_per_launch": alg_bytes, "kind": kind}
+    # ---- CPU baseline (rank 0, N=1 only) ------------------------------------------------------------------------
+    cpu = None
+    if world == 1:
+        from oracle import g4oracle as oracle
+
+        oracle.build()
+        threads = oracle.hardware_threads()
+        r1 = cpu_arm(codecs, 1, args.cpu_seconds / 3, oracle)
+        rn = cpu_arm(codecs, threads, args.cpu_seconds / 2, oracle)
+        cpu = {"value": rn["decode_gbs"], "unit": "GB/s", "cores": threads, "kind": "port",
+               "sample": "%d tiles of 180x240 from the shard's first tile row; oracle = C++ restatement of the Java reference "
+                         "(no JVM in this image)" % rn["tiles"],
+               "single_thread_value": r1["decode_gbs"], "encode_value": rn["encode_gbs"],
+               "encode_single_thread_value": r1["encode_gbs"], "bits_per_sample": rn["bits_per_sample"]}
+    line = {
+        "metric": METRIC, "value": value, "unit": "GB/s", "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
+        "ms_per_step": 1000.0 * t_dec / args.steps, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
+        "dtype": "int32", "data": "synthetic",
+        "config": {"workload": "config3 per-GPU shard: %d tiles of %dx%d int32 (%d x %d samples), codecs=%s%s" % (
+            n_tiles, TILE_R, TILE_C, rows, cols, "+".join(codecs), (" (not yet on the GPU: %s)" % "+".join(missing)) if missing else ""),
+            "l2": "inputs larger than L2 (payload %.0f MB + raster %.0f MB per step)" % (total_payload / 1e6, samples * 4 / 1e6),
+            "tile_choice": {c: int(codec_hist[k]) for k, c in enumerate(codecs)} | {"raw": int(codec_hist[255])}},
+        "bits_per_sample": bits_per_sample,
+        "encode": {"value": enc_value, "unit": "GB/s", "ms": 1000.0 * t_enc, "kernel_ms": enc_kernel_ms},
+        "roofline": roofline, "cpu_baseline": cpu, "e2e": e2e, "gpu_launches": int(launches_per_step * args.steps),
+        "clocks": clocks,
+    }
+    print(json.dumps(line))
+    if world > 1:
+        dist.destroy_process_group()
+
+
+if __name__ == "__main__":
+    main()

@@ -22,7 +22,7 @@ EXPORTS = [
     "g4_abi_version", "g4_status_string", "g4_last_error", "g4_device_count", "g4_codec_id_from_name", "g4_codec_name",
     "g4_context_create", "g4_context_destroy", "g4_context_synchronize", "g4_encode_i32", "g4_decode_i32",
     "g4_encode_f32", "g4_decode_f32", "g4_encode_tiles", "g4_decode_tiles", "g4_encode_arena_bound",
-    "g4_fill_terrain", "g4_launch_count",
+    "g4_fill_terrain", "g4_launch_count", "g4_context_set_timing", "g4_kernel_time_ms", "g4_codec_supported",
 ]
 
 
@@ -69,6 +69,9 @@ def lib():
         L.g4_decode_tiles.argtypes = [C.c_void_p, C.POINTER(CodecList), C.POINTER(BandDesc), C.c_int, C.c_void_p, C.c_void_p,
                                       C.c_void_p, C.c_void_p, C.c_void_p]
         L.g4_fill_terrain.argtypes = [C.c_void_p, C.c_int, C.c_uint64, C.c_int64, C.c_int64, C.c_int64, C.c_int64, C.c_void_p]
+        L.g4_context_set_timing.argtypes = [C.c_void_p, C.c_int]
+        L.g4_kernel_time_ms.argtypes = [C.c_void_p, C.c_int, C.c_int]
+        L.g4_kernel_time_ms.restype = C.c_double
         _lib = L
     return _lib
 

@@ -41,6 +41,14 @@ class Context:
     def launch_count(self):
         return int(_lib.lib().g4_launch_count(self._h))
 
+    def set_timing(self, enabled):
+        check(_lib.lib().g4_context_set_timing(self._h, int(bool(enabled))))
+
+    def kernel_time_ms(self, direction, codec_kind):
+        """Device time of the latest decode (0) / encode (1) kernel launch of a codec kind; None if not run."""
+        ms = _lib.lib().g4_kernel_time_ms(self._h, direction, codec_kind)
+        return None if ms < 0 else ms
+
     def fill_terrain(self, device_ptr, elem_type, row0, col0, n_rows, n_cols, seed=0x9E3779B97F4A7C15):
         check(_lib.lib().g4_fill_terrain(self._h, elem_type, C.c_uint64(seed), row0, col0, n_rows, n_cols,
                                          C.c_void_p(device_ptr)), "g4_fill_terrain")

@@ -66,6 +66,10 @@ struct g4_context {
   DevBuf lists, src, total;
   // staging used by the host-memory entry points
   DevBuf sGrid, sArena, sOffsets, sLens, sCodec, sPred, sStatus;
+  // optional per-kernel timing (CUDA events on the launching stream): [0]=decode, [1]=encode, by codec kind
+  bool timing = false;
+  cudaEvent_t ev[2][G4_CODEC_COUNT + 1][2] = {};
+  bool evUsed[2][G4_CODEC_COUNT + 1] = {};
 };
 
 namespace {
@@ -78,7 +82,8 @@ int persistent_ctas(const g4_context* ctx, int nTiles, int perSm) {
 }
 
 // Launch one candidate encoder over every tile of the band.
-int launch_encoder(g4_context* ctx, int codecId, EncodeArgs& a, int nTiles) {
+struct KernelTimer;
+int launch_encoder_impl(g4_context* ctx, int codecId, EncodeArgs& a, int nTiles) {
   switch (codecId) {
     case G4_CODEC_HUFFMAN: {
       int n = persistent_ctas(ctx, nTiles, 4);
@@ -94,7 +99,22 @@ int launch_encoder(g4_context* ctx, int codecId, EncodeArgs& a, int nTiles) {
 
 int decoder_ctas(const g4_context* ctx, int nTiles) { return persistent_ctas(ctx, nTiles, 8); }
 
+struct KernelTimer {  // brackets one launch with events when timing is enabled
+  g4_context* c;
+  int dir, kind;
+  KernelTimer(g4_context* ctx, int dir_, int kind_) : c(ctx), dir(dir_), kind(kind_) {
+    if (c->timing) {
+      if (!c->ev[dir][kind][0]) { cudaEventCreate(&c->ev[dir][kind][0]); cudaEventCreate(&c->ev[dir][kind][1]); }
+      cudaEventRecord(c->ev[dir][kind][0], c->stream);
+    }
+  }
+  ~KernelTimer() {
+    if (c->timing) { cudaEventRecord(c->ev[dir][kind][1], c->stream); c->evUsed[dir][kind] = true; }
+  }
+};
+
 int launch_decoder(g4_context* ctx, int codecId, DecodeArgs& a, int nCtas) {
+  KernelTimer timer(ctx, 0, codecId);
   switch (codecId) {
     case G4_CODEC_HUFFMAN:
       CK(launch_huffman_decode(a, nCtas, ctx->stream));
@@ -104,6 +124,11 @@ int launch_decoder(g4_context* ctx, int codecId, DecodeArgs& a, int nCtas) {
       tlsError = "codec not implemented on the GPU yet";
       return G4_ERR_UNSUPPORTED;
   }
+}
+
+int launch_encoder(g4_context* ctx, int codecId, EncodeArgs& a, int nTiles) {
+  KernelTimer timer(ctx, 1, codecId);
+  return launch_encoder_impl(ctx, codecId, a, nTiles);
 }
 
 int check_band(const g4_band_desc* b) {
@@ -239,6 +264,7 @@ int decode_device(g4_context* ctx, const g4_codec_list* codecs, const g4_band_de
     a.scratch = ctx->scratch.as<uint8_t>();
     a.scratchStride = stride;
     if (kind == G4_CODEC_COUNT) {
+      KernelTimer timer(ctx, 0, kind);
       CK(launch_raw_decode(a, nTiles, ctx->stream));
       ctx->launches++;
     } else {
@@ -336,6 +362,31 @@ int g4_context_synchronize(g4_context* ctx) {
 }
 
 uint64_t g4_launch_count(const g4_context* ctx) { return ctx ? ctx->launches : 0; }
+
+int g4_context_set_timing(g4_context* ctx, int enabled) {
+  if (!ctx) return G4_ERR_ARG;
+  ctx->timing = enabled != 0;
+  for (auto& d : ctx->evUsed) for (bool& u : d) u = false;
+  return G4_OK;
+}
+
+int g4_codec_supported(int codec_id, int direction) {
+  // direction 0 = decode, 1 = encode.  Grows as codec kernels land; bench.py and the tests ask instead of guessing.
+  (void)direction;
+  switch (codec_id) {
+    case G4_CODEC_HUFFMAN: return 1;
+    default: return 0;
+  }
+}
+
+double g4_kernel_time_ms(g4_context* ctx, int direction, int codec_kind) {
+  if (!ctx || direction < 0 || direction > 1 || codec_kind < 0 || codec_kind > G4_CODEC_COUNT) return -1.0;
+  if (!ctx->evUsed[direction][codec_kind]) return -1.0;
+  float ms = -1.0f;
+  if (cudaEventSynchronize(ctx->ev[direction][codec_kind][1]) != cudaSuccess) return -1.0;
+  if (cudaEventElapsedTime(&ms, ctx->ev[direction][codec_kind][0], ctx->ev[direction][codec_kind][1]) != cudaSuccess) return -1.0;
+  return double(ms);
+}
 
 uint64_t g4_encode_arena_bound(const g4_band_desc* b) {
   if (!b) return 0;

@@ -134,6 +134,13 @@ int g4_fill_terrain(g4_context* ctx, int elem_type, uint64_t seed, int64_t row0,
                     int64_t n_cols, void* device_out);
 /* Kernel launches issued through this context since creation (bench.py's gpu_launches claim). */
 uint64_t g4_launch_count(const g4_context* ctx);
+/* Per-kernel device timing: when enabled, every codec kernel launch is bracketed by CUDA events on the
+ * context's stream.  g4_kernel_time_ms returns the duration of the most recent launch of the decode
+ * (direction 0) or encode (direction 1) kernel of `codec_kind` (G4_CODEC_COUNT = raw copy); < 0 if none. */
+int g4_context_set_timing(g4_context* ctx, int enabled);
+/* 1 when the CUDA kernels for codec_id exist for direction (0 = decode, 1 = encode), else 0. */
+int g4_codec_supported(int codec_id, int direction);
+double g4_kernel_time_ms(g4_context* ctx, int direction, int codec_kind);
 
 #ifdef __cplusplus
 }
