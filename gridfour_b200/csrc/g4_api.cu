@@ -64,6 +64,7 @@ struct g4_context {
   DevBuf counters;     // 64 ints: [0..15] encode counters, [16..31] decode counters, [32..47] list counts
   DevBuf scratch;      // per-CTA scratch
   DevBuf lists, src, total;
+  DevBuf coef;         // LSOP12 decode: 12 float32 coefficients per tile
   // staging used by the host-memory entry points
   DevBuf sGrid, sArena, sOffsets, sLens, sCodec, sPred, sStatus;
   // optional per-kernel timing (CUDA events on the launching stream): [0]=decode, [1]=encode, by codec kind
@@ -115,10 +116,20 @@ struct KernelTimer {  // brackets one launch with events when timing is enabled
 
 int launch_decoder(g4_context* ctx, int codecId, DecodeArgs& a, int nCtas) {
   KernelTimer timer(ctx, 0, codecId);
+  const int nTiles = a.band.tiles_down * a.band.tiles_across;
   switch (codecId) {
     case G4_CODEC_HUFFMAN:
       CK(launch_huffman_decode(a, nCtas, ctx->stream));
       ctx->launches++;
+      return G4_OK;
+    case G4_CODEC_CANON_HUFFMAN:
+      CK(launch_canon_decode(a, nCtas, ctx->stream));
+      ctx->launches++;
+      return G4_OK;
+    case G4_CODEC_LSOP12:
+      CK(ctx->coef.ensure(size_t(nTiles) * 12 * sizeof(float)));
+      CK(launch_lsop_decode(a, ctx->coef.as<float>(), nCtas, nTiles, ctx->stream));
+      ctx->launches += 2;
       return G4_OK;
     default:
       tlsError = "codec not implemented on the GPU yet";
@@ -349,7 +360,7 @@ void g4_context_destroy(g4_context* ctx) {
   cudaStreamSynchronize(ctx->stream);
   for (auto& b : ctx->slots) b.release();
   DevBuf* bufs[] = {&ctx->candLens, &ctx->candPreds, &ctx->candStatus, &ctx->counters, &ctx->scratch, &ctx->lists, &ctx->src,
-                    &ctx->total, &ctx->sGrid, &ctx->sArena, &ctx->sOffsets, &ctx->sLens, &ctx->sCodec, &ctx->sPred, &ctx->sStatus};
+                    &ctx->total, &ctx->coef, &ctx->sGrid, &ctx->sArena, &ctx->sOffsets, &ctx->sLens, &ctx->sCodec, &ctx->sPred, &ctx->sStatus};
   for (DevBuf* b : bufs) b->release();
   if (ctx->ownStream) cudaStreamDestroy(ctx->stream);
   delete ctx;
@@ -372,9 +383,10 @@ int g4_context_set_timing(g4_context* ctx, int enabled) {
 
 int g4_codec_supported(int codec_id, int direction) {
   // direction 0 = decode, 1 = encode.  Grows as codec kernels land; bench.py and the tests ask instead of guessing.
-  (void)direction;
   switch (codec_id) {
     case G4_CODEC_HUFFMAN: return 1;
+    case G4_CODEC_CANON_HUFFMAN: return direction == 0;
+    case G4_CODEC_LSOP12: return direction == 0;
     default: return 0;
   }
 }

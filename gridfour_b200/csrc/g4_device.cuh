@@ -15,6 +15,9 @@ namespace g4 {
 constexpr int kThreads = 256;  // threads per CTA for all tile kernels (8 warps)
 constexpr int kWarps = kThreads / 32;
 constexpr int32_t kNull = INT32_MIN;  // util/GridfourConstants.java:61
+// residual stream orders beyond the predictor codes (used with stream_to_cell)
+constexpr int kStreamLsopInit = 5;
+constexpr int kStreamLsopInterior = 6;
 
 // ------------------------------------------------------------------------------------------------
 // Tile view: a tile is a strided window of the row-major raster held in HBM.
@@ -159,6 +162,22 @@ __device__ __forceinline__ void stream_to_cell(int pred, int k, int R, int C, in
     if (k < C - 1) { *r = 0; *c = k + 1; }
     else if (k < C + R - 2) { *r = k - (C - 1) + 1; *c = 0; }
     else { int j = k - (C + R - 2); int rr = j / (C - 1); *r = 1 + rr; *c = 1 + j - rr * (C - 1); }
+  } else if (pred == kStreamLsopInit) {
+    // LsOptimalPredictor12.java:143-209: row 0 | column 0 | row 1 | column 1 (rows 2..) | last two columns per row 2..
+    if (k < C - 1) { *r = 0; *c = k + 1; return; }
+    k -= C - 1;
+    if (k < R - 1) { *r = k + 1; *c = 0; return; }
+    k -= R - 1;
+    if (k < C - 1) { *r = 1; *c = k + 1; return; }
+    k -= C - 1;
+    if (k < R - 2) { *r = k + 2; *c = 1; return; }
+    k -= R - 2;
+    *r = 2 + (k >> 1);
+    *c = C - 2 + (k & 1);
+  } else if (pred == kStreamLsopInterior) {
+    // LsOptimalPredictor12.java:254-282: rows 2.., columns 2..C-3, row-major
+    int rr = k / (C - 4);
+    *r = 2 + rr; *c = 2 + k - rr * (C - 4);
   } else {  // DifferencingWithNulls: one residual per cell
     int rr = k / C;
     *r = rr; *c = k - rr * C;

@@ -1,0 +1,111 @@
+"""-m gpu: CodecCanonHuffman and LSOP12 CUDA paths vs the CPU oracle and the reference's LSOP fixture."""
+import json
+import math
+import os
+
+import numpy as np
+import pytest
+
+from gpu_common import first_diff, parity_grids
+
+pytestmark = pytest.mark.gpu
+GOLD = json.load(open(os.path.join(os.path.dirname(__file__), "golden", "fixtures.json")))["samples"]
+
+
+@pytest.fixture(scope="module")
+def g4():
+    import gridfour_b200
+
+    return gridfour_b200
+
+
+def test_canon_decode_bit_exact(g4, oracle):
+    codec = g4.CodecCanonHuffman()
+    for name, grid in parity_grids(oracle).items():
+        packing, _ = oracle.codec_encode_i32(oracle.CODEC_CANON_HUFFMAN, 3, grid)
+        out = codec.decode(grid.shape[0], grid.shape[1], packing)
+        assert np.array_equal(out, grid), "%s: %s" % (name, first_diff(out, grid))
+
+
+def test_canon_decode_escape_ranges(g4, oracle):
+    """Residual magnitudes that exercise every escape form (2/4/6-bit, 8/16/24-bit)."""
+    codec = g4.CodecCanonHuffman()
+    rng = np.random.default_rng(5)
+    for lim in (300, 1500, 7000, 30000, 4_000_000, 2 ** 30):
+        grid = rng.integers(-lim, lim, (40, 52), dtype=np.int64).cumsum(axis=1).astype(np.int32)
+        packing, _ = oracle.codec_encode_i32(oracle.CODEC_CANON_HUFFMAN, 0, grid)
+        if packing is None:
+            continue
+        out = codec.decode(40, 52, packing)
+        assert np.array_equal(out, grid), "lim %d: %s" % (lim, first_diff(out, grid))
+
+
+def test_lsop_reference_fixture_decodes_on_gpu(g4):
+    """Sample14_LSOP.gvrs: legacy header + legacy Huffman + M32, written by the reference's Java LsEncoder."""
+    s = GOLD["Sample14_LSOP"]
+    payload = bytes.fromhex(s["tiles"]["0"])
+    out = g4.LsDecoder12().decode(101, 101, payload)
+    exp = np.zeros((101, 101), np.int32)
+    for r in range(101):
+        for c in range(101):
+            exp[r, c] = math.floor(math.sin(c / 100.0 * math.pi) * math.sin(r / 100.0 * math.pi) * 1000.0 + 0.5)
+    assert np.array_equal(out, exp), first_diff(out, exp)
+
+
+def test_lsop_decode_bit_exact(g4, oracle):
+    dec = g4.LsDecoder12()
+    n = 0
+    for name, grid in parity_grids(oracle).items():
+        for kwargs in ({"deflate": False}, {"deflate": False, "checksum": True}):
+            packing = oracle.lsop12_encode(2, grid, **kwargs)
+            if packing is None:
+                continue
+            out = dec.decode(grid.shape[0], grid.shape[1], packing)
+            assert np.array_equal(out, grid), "%s %s: %s" % (name, kwargs, first_diff(out, grid))
+            n += 1
+    assert n >= 10
+
+
+def test_lsop_decode_many_shapes(g4, oracle):
+    dec = g4.LsDecoder12()
+    for (R, C) in [(6, 6), (7, 9), (33, 40), (34, 37), (35, 100), (64, 64), (66, 130), (120, 120), (200, 50)]:
+        grid = oracle.terrain_i32(R * 7, C * 3, R, C)
+        packing = oracle.lsop12_encode(0, grid, deflate=False)
+        if packing is None:
+            continue
+        out = dec.decode(R, C, packing)
+        assert np.array_equal(out, grid), "%dx%d: %s" % (R, C, first_diff(out, grid))
+
+
+def test_batch_decode_mixed_codecs(g4, oracle):
+    """decodeTiles over payloads the ORACLE encoded with best-of [Huffman, CanonHuffman, LSOP12 (canonical only)]."""
+    spec = g4.CodecSpecification(default=False)
+    spec.addCompressionCodec("GvrsHuffman", g4.CodecHuffman)
+    spec.addCompressionCodec("GvrsCanonicalHuffman", g4.CodecCanonHuffman)
+    spec.addCompressionCodec("LSOP12", g4.LsEncoder12, g4.LsDecoder12)
+    master = g4.CodecMaster(spec)
+    R, C, TR, TC = 90, 120, 3, 4
+    grid = oracle.terrain_i32(2000, 1000, TR * R, TC * C)
+    grid[0:R, C:2 * C] = 7  # uniform tile (t=1) -> canonical 6-byte shortcut
+    payloads = []
+    for t in range(TR * TC):
+        tr, tc = divmod(t, TC)
+        tile = grid[tr * R:(tr + 1) * R, tc * C:(tc + 1) * C]
+        cands = [oracle.codec_encode_i32(0, 0, tile)[0], oracle.codec_encode_i32(3, 1, tile)[0],
+                 oracle.lsop12_encode(2, tile, deflate=False)]
+        cands = [c for c in cands if c is not None]
+        best = min(cands, key=len)
+        payloads.append(best if t % 3 else cands[t % len(cands)])  # mix codecs regardless of size
+    offsets, arena, pos = [], bytearray(), 0
+    for p in payloads:
+        offsets.append(pos)
+        arena += p + b"\0" * ((-len(p)) % 8)
+        pos = len(arena)
+    band = master._band(grid.shape, np.int32, R, C)
+    batch = g4.TileBatch(np.frombuffer(bytes(arena), np.uint8), np.array(offsets, np.uint64),
+                         np.array([len(p) for p in payloads], np.uint32), None, None, None, len(arena), band)
+    out = master.decodeTiles(batch)
+    assert np.array_equal(out, grid), first_diff(out, grid)
+    used = sorted({p[0] for p in payloads})
+    assert used == [0, 1, 2], used
+    assert len(payloads[1]) == 6
