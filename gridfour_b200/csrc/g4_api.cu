@@ -64,6 +64,7 @@ struct g4_context {
   DevBuf counters;     // 64 ints: [0..15] encode counters, [16..31] decode counters, [32..47] list counts
   DevBuf scratch;      // per-CTA scratch
   DevBuf lists, src, total;
+  DevBuf encScratch;   // per-CTA encoder scratch
   DevBuf coef;         // LSOP12 decode: 12 float32 coefficients per tile
   // staging used by the host-memory entry points
   DevBuf sGrid, sArena, sOffsets, sLens, sCodec, sPred, sStatus;
@@ -89,6 +90,18 @@ int launch_encoder_impl(g4_context* ctx, int codecId, EncodeArgs& a, int nTiles)
     case G4_CODEC_HUFFMAN: {
       int n = persistent_ctas(ctx, nTiles, 4);
       CK(launch_huffman_encode(a, n, ctx->stream));
+      ctx->launches++;
+      return G4_OK;
+    }
+    case G4_CODEC_CANON_HUFFMAN:
+    case G4_CODEC_LSOP12: {
+      int n = persistent_ctas(ctx, nTiles, 4);
+      const size_t stride = 32 * 1024;  // package-merge scratch (g4_canon_enc.cuh)
+      CK(ctx->encScratch.ensure(stride * n));
+      a.scratch = ctx->encScratch.as<uint8_t>();
+      a.scratchStride = stride;
+      if (codecId == G4_CODEC_CANON_HUFFMAN) CK(launch_canon_encode(a, n, ctx->stream));
+      else CK(launch_lsop_encode(a, n, ctx->stream));
       ctx->launches++;
       return G4_OK;
     }
@@ -360,7 +373,7 @@ void g4_context_destroy(g4_context* ctx) {
   cudaStreamSynchronize(ctx->stream);
   for (auto& b : ctx->slots) b.release();
   DevBuf* bufs[] = {&ctx->candLens, &ctx->candPreds, &ctx->candStatus, &ctx->counters, &ctx->scratch, &ctx->lists, &ctx->src,
-                    &ctx->total, &ctx->coef, &ctx->sGrid, &ctx->sArena, &ctx->sOffsets, &ctx->sLens, &ctx->sCodec, &ctx->sPred, &ctx->sStatus};
+                    &ctx->total, &ctx->coef, &ctx->encScratch, &ctx->sGrid, &ctx->sArena, &ctx->sOffsets, &ctx->sLens, &ctx->sCodec, &ctx->sPred, &ctx->sStatus};
   for (DevBuf* b : bufs) b->release();
   if (ctx->ownStream) cudaStreamDestroy(ctx->stream);
   delete ctx;
@@ -385,8 +398,8 @@ int g4_codec_supported(int codec_id, int direction) {
   // direction 0 = decode, 1 = encode.  Grows as codec kernels land; bench.py and the tests ask instead of guessing.
   switch (codec_id) {
     case G4_CODEC_HUFFMAN: return 1;
-    case G4_CODEC_CANON_HUFFMAN: return direction == 0;
-    case G4_CODEC_LSOP12: return direction == 0;
+    case G4_CODEC_CANON_HUFFMAN: return 1;
+    case G4_CODEC_LSOP12: return 1;  // encode: canonical-Huffman body only (no Deflate alternative yet)
     default: return 0;
   }
 }

@@ -5,6 +5,7 @@
 #include "g4_kernels.h"
 #include "g4_predict.cuh"
 #include "g4_canon.cuh"
+#include "g4_canon_enc.cuh"
 
 namespace g4 {
 
@@ -63,6 +64,115 @@ __global__ void __launch_bounds__(kThreads) canon_decode_kernel(DecodeArgs a) {
     }
     if (tid == 0) a.status[tIdx] = status;
   }
+}
+
+// ---- encode ---------------------------------------------------------------------------------------------
+namespace {
+struct CanonEncKernelShared {
+  CanonEncShared E;
+  BitWindow W;
+};
+struct PredResidualGet {
+  TileView t;
+  int pred;
+  __device__ __forceinline__ int32_t operator()(uint32_t k) const {
+    int r, c;
+    stream_to_cell(pred, int(k), t.R, t.C, &r, &c);
+    return residual_at(pred, t, r, c);
+  }
+};
+}  // namespace
+
+// CodecCanonHuffman.encode (:79-142) + compress (:144-159)
+__global__ void __launch_bounds__(kThreads) canon_encode_kernel(EncodeArgs a) {
+  __shared__ CanonEncKernelShared S;
+  __shared__ int sTile;
+  const int tid = threadIdx.x;
+  const int nTiles = a.band.tiles_down * a.band.tiles_across;
+  uint8_t* pm = a.scratch + size_t(blockIdx.x) * a.scratchStride;
+  for (;;) {
+    __syncthreads();
+    if (tid == 0) sTile = atomicAdd(a.counter, 1);
+    __syncthreads();
+    const int tIdx = sTile;
+    if (tIdx >= nTiles) break;
+    const TileView t = tile_view(a.band, a.grid, tIdx);
+    const int n = t.R * t.C;
+    uint32_t* outWords = reinterpret_cast<uint32_t*>(a.slots + size_t(tIdx) * a.slotBytes);
+    const uint32_t capWords = uint32_t(a.slotBytes / 4);
+    // nulls / uniformity scan (:83-110)
+    bool sawNull = false, sawValid = false, differs = false;
+    const int32_t v0 = t.at(0, 0);
+    for (int i = tid; i < n; i += kThreads) {
+      int r = i / t.C, c = i - r * t.C;
+      int32_t v = t.at(r, c);
+      if (v == kNull) sawNull = true; else sawValid = true;
+      if (v != v0) differs = true;
+    }
+    const bool anyNull = __syncthreads_or(sawNull) != 0;
+    const bool anyValid = __syncthreads_or(sawValid) != 0;
+    const bool anyDiff = __syncthreads_or(differs) != 0;
+    if (!anyValid) {
+      if (tid == 0) { a.lens[tIdx] = 0; a.preds[tIdx] = 0; a.status[tIdx] = G4_DECLINED; }
+      continue;
+    }
+    if (!anyDiff) {  // uniform tile: 6-byte packing, predictor 0
+      if (tid == 0) {
+        outWords[0] = (uint32_t(a.codecIndex) & 0xffu) | ((uint32_t(v0) & 0xffffu) << 16);
+        outWords[1] = uint32_t(v0) >> 16;
+        a.lens[tIdx] = 6; a.preds[tIdx] = 0; a.status[tIdx] = G4_OK;
+      }
+      continue;
+    }
+    if (anyNull) {  // TODO(next): PredictorModelDifferencingWithNulls on the GPU
+      if (tid == 0) { a.lens[tIdx] = 0; a.preds[tIdx] = 0; a.status[tIdx] = G4_ERR_UNSUPPORTED; }
+      continue;
+    }
+    const uint32_t nRes = uint32_t(n - 1);
+    unsigned long long best = ~0ull;
+    int win = -1, built = -1;
+    bool bug = false;
+    for (int p = 0; p < 3; p++) {
+      PredResidualGet get{t, p + 1};
+      if (!canon_histogram(S.E, get, nRes)) { bug = true; break; }
+      canon_build_code(S.E, pm);
+      built = p;
+      unsigned long long bytes = 6ull + (S.E.totalBits + 7ull) / 8ull;
+      if (bytes < best) { best = bytes; win = p; }
+    }
+    if (bug) {  // reference escape-range inconsistency (see g4_canon_enc.cuh): decline
+      if (tid == 0) { a.lens[tIdx] = 0; a.preds[tIdx] = 0; a.status[tIdx] = G4_DECLINED; }
+      continue;
+    }
+    PredResidualGet get{t, win + 1};
+    if (built != win) {
+      canon_histogram(S.E, get, nRes);
+      canon_build_code(S.E, pm);
+    }
+    BitOut o;
+    bitwin_reset(S.W, o, outWords, capWords);
+    if (tid == 0) {
+      WinSink sink{S.W.win, 0};
+      sink.put(uint32_t(a.codecIndex) & 0xffu, 8);
+      sink.put(uint32_t(win + 1), 8);
+      sink.put(uint32_t(v0), 32);
+    }
+    o.bitPos = 48;
+    __syncthreads();
+    canon_emit_stream(S.E, S.W, o, get, nRes);
+    bitwin_finish(S.W, o);
+    if (tid == 0) {
+      uint32_t len = (o.bitPos + 7) >> 3;
+      a.lens[tIdx] = len;
+      a.preds[tIdx] = uint8_t(win + 1);
+      a.status[tIdx] = len <= a.slotBytes ? G4_OK : G4_ERR_CAPACITY;
+    }
+  }
+}
+
+cudaError_t launch_canon_encode(const EncodeArgs& a, int nCtas, cudaStream_t s) {
+  canon_encode_kernel<<<nCtas, kThreads, 0, s>>>(a);
+  return cudaGetLastError();
 }
 
 cudaError_t launch_canon_decode(const DecodeArgs& a, int nCtas, cudaStream_t s) {

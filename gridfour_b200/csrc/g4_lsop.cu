@@ -15,6 +15,7 @@
 #include "g4_predict.cuh"
 #include "g4_huffdec.cuh"
 #include "g4_canon.cuh"
+#include "g4_canon_enc.cuh"
 
 namespace g4 {
 
@@ -272,6 +273,262 @@ __global__ void __launch_bounds__(kThreads) lsop_wavefront_kernel(DecodeArgs a, 
     __syncwarp();
     __threadfence_block();
   }
+}
+
+// =====================================================================================================
+// Encode (LsEncoder12.encode :122-219 with the canonical-Huffman body; LsOptimalPredictor12.encode :109-292)
+// =====================================================================================================
+namespace {
+
+constexpr int kMomentQuantities = 104;  // 13 sums + 91 products (upper triangle incl. diagonal)
+constexpr int kMomentPerRole = 26;
+
+// quantity q: q < 13 -> z[q]; otherwise the (i,j) product with i <= j in row-major order of the upper triangle
+__host__ __device__ constexpr int moment_i(int q) {
+  int k = q - 13, i = 0;
+  while (k >= 13 - i) { k -= 13 - i; i++; }
+  return i;
+}
+__host__ __device__ constexpr int moment_j(int q) {
+  int k = q - 13, i = 0;
+  while (k >= 13 - i) { k -= 13 - i; i++; }
+  return i + k;
+}
+
+template <int ROLE>
+__device__ __forceinline__ void moment_accumulate(const double (&z)[13], double (&acc)[kMomentPerRole]) {
+#pragma unroll
+  for (int a = 0; a < kMomentPerRole; a++) {
+    constexpr int dummy = 0;
+    (void)dummy;
+    const int q = a * 4 + ROLE;
+    if (q < 13) acc[a] += z[q];
+    else acc[a] += z[moment_i(q)] * z[moment_j(q)];
+  }
+}
+
+struct LsopEncShared {
+  CanonEncShared E;
+  BitWindow W;
+  double part[kWarps][kMomentPerRole];
+  double sums[kMomentQuantities];
+  double M[13][13];
+  double rhs[13];
+  float u[12];
+  int singular;
+};
+
+// JAMA LUDecomposition ctor + solve (util/jama/LUDecomposition.java:70-135, :253-286), one thread, FP64,
+// identical operation order (compiled with -fmad=false).
+__device__ bool lu_solve13(double (*LU)[13], double* X) {
+  const int n = 13;
+  int piv[13];
+  for (int i = 0; i < n; i++) piv[i] = i;
+  double col[13];
+  for (int j = 0; j < n; j++) {
+    for (int i = 0; i < n; i++) col[i] = LU[i][j];
+    for (int i = 0; i < n; i++) {
+      int kmax = i < j ? i : j;
+      double s = 0.0;
+      for (int k = 0; k < kmax; k++) s += LU[i][k] * col[k];
+      col[i] -= s;
+      LU[i][j] = col[i];
+    }
+    int p = j;
+    for (int i = j + 1; i < n; i++)
+      if (fabs(col[i]) > fabs(col[p])) p = i;
+    if (p != j) {
+      for (int k = 0; k < n; k++) { double t = LU[p][k]; LU[p][k] = LU[j][k]; LU[j][k] = t; }
+      int k = piv[p]; piv[p] = piv[j]; piv[j] = k;
+    }
+    if (LU[j][j] != 0.0)
+      for (int i = j + 1; i < n; i++) LU[i][j] /= LU[j][j];
+  }
+  for (int j = 0; j < n; j++)
+    if (LU[j][j] == 0.0) return false;
+  double B[13];
+  for (int i = 0; i < n; i++) B[i] = X[piv[i]];
+  for (int i = 0; i < n; i++) X[i] = B[i];
+  for (int k = 0; k < n; k++)
+    for (int i = k + 1; i < n; i++) X[i] -= X[k] * LU[i][k];
+  for (int k = n - 1; k >= 0; k--) {
+    X[k] /= LU[k][k];
+    for (int i = 0; i < k; i++) X[i] -= X[k] * LU[i][k];
+  }
+  return true;
+}
+
+struct LsInitGet {  // initializer residuals in stream order (LsOptimalPredictor12.java:143-209)
+  TileView t;
+  __device__ __forceinline__ int32_t operator()(uint32_t k) const {
+    int r, c;
+    stream_to_cell(kStreamLsopInit, int(k), t.R, t.C, &r, &c);
+    return residual_at(G4_PRED_TRIANGLE, t, r, c);  // row 0 / column 0 degrade to plain differences
+  }
+};
+
+struct LsInteriorGet {  // interior residuals (LsOptimalPredictor12.java:254-282)
+  TileView t;
+  const float* u;
+  __device__ __forceinline__ int32_t operator()(uint32_t k) const {
+    const int w = t.C - 4;
+    int rr = int(k) / w;
+    int r = 2 + rr, c = 2 + int(k) - rr * w;
+    const int32_t* row = t.row(r);
+    const int32_t* up1 = row - t.pitch;
+    const int32_t* up2 = up1 - t.pitch;
+    float p = u[0] * float(row[c - 1]);
+    p = p + u[1] * float(up1[c - 1]);
+    p = p + u[2] * float(up1[c]);
+    p = p + u[3] * float(up1[c + 1]);
+    p = p + u[4] * float(up1[c + 2]);
+    p = p + u[5] * float(row[c - 2]);
+    p = p + u[6] * float(up1[c - 2]);
+    p = p + u[7] * float(up2[c - 2]);
+    p = p + u[8] * float(up2[c - 1]);
+    p = p + u[9] * float(up2[c]);
+    p = p + u[10] * float(up2[c + 1]);
+    p = p + u[11] * float(up2[c + 2]);
+    return int32_t(uint32_t(row[c]) - uint32_t(java_round(p)));
+  }
+};
+
+}  // namespace
+
+__global__ void __launch_bounds__(kThreads) lsop_encode_kernel(EncodeArgs a) {
+  extern __shared__ __align__(16) unsigned char smemRaw[];
+  LsopEncShared& S = *reinterpret_cast<LsopEncShared*>(smemRaw);
+  __shared__ int sTile;
+  const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+  const int nTiles = a.band.tiles_down * a.band.tiles_across;
+  uint8_t* pm = a.scratch + size_t(blockIdx.x) * a.scratchStride;
+  for (;;) {
+    __syncthreads();
+    if (tid == 0) sTile = atomicAdd(a.counter, 1);
+    __syncthreads();
+    const int tIdx = sTile;
+    if (tIdx >= nTiles) break;
+    const TileView t = tile_view(a.band, a.grid, tIdx);
+    const int R = t.R, C = t.C;
+    uint32_t* outWords = reinterpret_cast<uint32_t*>(a.slots + size_t(tIdx) * a.slotBytes);
+    const uint32_t capWords = uint32_t(a.slotBytes / 4);
+    if (R < 6 || C < 6) {  // LsOptimalPredictor12.java:114-116
+      if (tid == 0) { a.lens[tIdx] = 0; a.preds[tIdx] = 0; a.status[tIdx] = G4_DECLINED; }
+      continue;
+    }
+    // ---- normal equations: s[i] += z[i], c[i][j] += z[i]*z[j] over the interior cells (:319-344) --------
+    {
+      const int role = warp & 3, group = warp >> 2;
+      const int w = C - 4;
+      const int nInterior = (R - 2) * w;
+      double acc[kMomentPerRole];
+#pragma unroll
+      for (int i = 0; i < kMomentPerRole; i++) acc[i] = 0.0;
+      for (int m = group * 32 + lane; m < nInterior; m += 64) {
+        int rr = m / w;
+        int r = 2 + rr, c = 2 + m - rr * w;
+        const int32_t* row = t.row(r);
+        const int32_t* up1 = row - t.pitch;
+        const int32_t* up2 = up1 - t.pitch;
+        double z[13];
+        z[0] = row[c]; z[1] = row[c - 1]; z[2] = up1[c - 1]; z[3] = up1[c]; z[4] = up1[c + 1]; z[5] = up1[c + 2];
+        z[6] = row[c - 2]; z[7] = up1[c - 2]; z[8] = up2[c - 2]; z[9] = up2[c - 1]; z[10] = up2[c]; z[11] = up2[c + 1];
+        z[12] = up2[c + 2];
+        switch (role) {
+          case 0: moment_accumulate<0>(z, acc); break;
+          case 1: moment_accumulate<1>(z, acc); break;
+          case 2: moment_accumulate<2>(z, acc); break;
+          default: moment_accumulate<3>(z, acc); break;
+        }
+      }
+#pragma unroll
+      for (int i = 0; i < kMomentPerRole; i++) {
+        double v = acc[i];
+#pragma unroll
+        for (int d = 16; d >= 1; d >>= 1) v += __shfl_xor_sync(0xffffffffu, v, d);
+        if (lane == 0) S.part[warp][i] = v;
+      }
+      __syncthreads();
+      if (tid < kMomentQuantities) S.sums[tid] = S.part[tid & 3][tid >> 2] + S.part[(tid & 3) + 4][tid >> 2];
+      __syncthreads();
+    }
+    if (tid == 0) {
+      // design matrix (:346-368): 12x12 moment block bordered by the sums (Lagrange constraint)
+      double cfull[13][13];
+      for (int q = 13; q < kMomentQuantities; q++) {
+        int i = moment_i(q), j = moment_j(q);
+        cfull[i][j] = S.sums[q];
+        cfull[j][i] = S.sums[q];
+      }
+      for (int i = 0; i < 13; i++) for (int j = 0; j < 13; j++) S.M[i][j] = 0.0;
+      for (int i = 1; i < 13; i++) {
+        for (int j = 1; j < 13; j++) S.M[i - 1][j - 1] = cfull[i][j];
+        S.M[i - 1][12] = S.sums[i];
+      }
+      for (int j = 1; j < 13; j++) S.M[12][j - 1] = S.sums[j];
+      for (int i = 1; i < 13; i++) S.rhs[i - 1] = cfull[0][i];
+      S.rhs[12] = S.sums[0];
+      bool ok = lu_solve13(S.M, S.rhs);
+      S.singular = ok ? 0 : 1;
+      if (ok)
+        for (int i = 0; i < 12; i++) S.u[i] = __double2float_rn(S.rhs[i]);
+    }
+    __syncthreads();
+    if (S.singular) {  // RuntimeException("Matrix is singular.") -> null (:377-381)
+      if (tid == 0) { a.lens[tIdx] = 0; a.preds[tIdx] = 0; a.status[tIdx] = G4_DECLINED; }
+      continue;
+    }
+    // ---- packing: revised header (LsHeader.java:210-265) + two canonical streams in one bit store --------
+    const uint32_t nInit = uint32_t(4 * R + 2 * C - 9);
+    const uint32_t nInterior = uint32_t(R - 2) * uint32_t(C - 4);
+    BitOut o;
+    bitwin_reset(S.W, o, outWords, capWords);
+    if (tid == 0) {
+      WinSink sink{S.W.win, 0};
+      sink.put(uint32_t(a.codecIndex) & 0xffu, 8);
+      sink.put(0x40u | 2u, 8);  // revision flag | COMPRESSION_TYPE_CANON_HUFFMAN
+      sink.put(12, 8);
+      sink.put(uint32_t(t.at(0, 0)), 32);
+      for (int i = 0; i < 12; i++) sink.put(__float_as_uint(S.u[i]), 32);
+    }
+    o.bitPos = 55u * 8u;
+    __syncthreads();
+    LsInitGet g1{t};
+    LsInteriorGet g2{t, S.u};
+    bool bad = false;
+    if (!canon_histogram(S.E, g1, nInit)) bad = true;
+    else {
+      canon_build_code(S.E, pm);
+      canon_emit_stream(S.E, S.W, o, g1, nInit);
+      if (!canon_histogram(S.E, g2, nInterior)) bad = true;
+      else {
+        canon_build_code(S.E, pm);
+        canon_emit_stream(S.E, S.W, o, g2, nInterior);
+      }
+    }
+    if (bad) {
+      if (tid == 0) { a.lens[tIdx] = 0; a.preds[tIdx] = 0; a.status[tIdx] = G4_DECLINED; }
+      continue;
+    }
+    bitwin_finish(S.W, o);
+    if (tid == 0) {
+      uint32_t len = (o.bitPos + 7) >> 3;
+      a.lens[tIdx] = len;
+      a.preds[tIdx] = 2;  // compression type: canonical Huffman
+      a.status[tIdx] = len <= a.slotBytes ? G4_OK : G4_ERR_CAPACITY;
+    }
+  }
+}
+
+cudaError_t launch_lsop_encode(const EncodeArgs& a, int nCtas, cudaStream_t s) {
+  static bool attr = false;
+  if (!attr) {
+    cudaError_t e = cudaFuncSetAttribute(lsop_encode_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, int(sizeof(LsopEncShared)));
+    if (e != cudaSuccess) return e;
+    attr = true;
+  }
+  lsop_encode_kernel<<<nCtas, kThreads, sizeof(LsopEncShared), s>>>(a);
+  return cudaGetLastError();
 }
 
 cudaError_t launch_lsop_decode(const DecodeArgs& a, float* coef, int nCtas, int nTilesUpper, cudaStream_t s) {

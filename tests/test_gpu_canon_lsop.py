@@ -109,3 +109,71 @@ def test_batch_decode_mixed_codecs(g4, oracle):
     used = sorted({p[0] for p in payloads})
     assert used == [0, 1, 2], used
     assert len(payloads[1]) == 6
+
+
+def test_canon_encode_streams_byte_exact(g4, oracle):
+    codec = g4.CodecCanonHuffman()
+    for name, grid in parity_grids(oracle).items():
+        exp, pred = oracle.codec_encode_i32(oracle.CODEC_CANON_HUFFMAN, 3, grid)
+        got = codec.encode(3, grid.shape[0], grid.shape[1], grid)
+        assert got is not None, name
+        assert got == exp, "%s (pred gpu %d, oracle %d): %s" % (name, codec.lastPredictor, pred, first_diff(got, exp))
+
+
+def test_canon_encode_package_merge_path(g4, oracle):
+    """A tile whose residual histogram is Fibonacci-like pushes the Huffman depth past 15 (PackageMerge.java)."""
+    fib = [1, 1]
+    while len(fib) < 24:
+        fib.append(fib[-1] + fib[-2])
+    vals = np.repeat(np.arange(23) - 11, fib[1:24]).astype(np.int64)
+    np.random.default_rng(0).shuffle(vals)
+    n = 200 * 300
+    res = np.zeros(n, np.int64)
+    res[: vals.size] = vals[: n]
+    grid = res.reshape(200, 300).cumsum(axis=1).astype(np.int32)
+    exp, pred = oracle.codec_encode_i32(oracle.CODEC_CANON_HUFFMAN, 0, grid)
+    got = g4.CodecCanonHuffman().encode(0, 200, 300, grid)
+    assert got == exp, first_diff(got, exp)
+
+
+def test_lsop_coefficients_and_streams_byte_exact(g4, oracle):
+    enc = g4.LsEncoder12()
+    checked = 0
+    for name, grid in parity_grids(oracle).items():
+        exp = oracle.lsop12_encode(1, grid, deflate=False)
+        got = enc.encode(1, grid.shape[0], grid.shape[1], grid)
+        if exp is None:
+            assert got is None, name
+            continue
+        assert got is not None, name
+        # 12 float32 coefficients at bytes 7..55: bit-identical (north_star allows 1 ulp)
+        assert got[7:55] == exp[7:55], "%s coefficients differ" % name
+        assert got == exp, "%s: %s" % (name, first_diff(got, exp))
+        checked += 1
+    assert checked >= 8
+
+
+def test_batch_best_of_three_matches_oracle(g4, oracle):
+    """encodeTiles with [GvrsHuffman, GvrsCanonicalHuffman, LSOP12]: per-tile choice and bytes equal the oracle's
+    CodecMaster rule (LSOP12 with the Deflate alternative disabled on both sides)."""
+    spec = g4.CodecSpecification(default=False)
+    spec.addCompressionCodec("GvrsHuffman", g4.CodecHuffman)
+    spec.addCompressionCodec("GvrsCanonicalHuffman", g4.CodecCanonHuffman)
+    spec.addCompressionCodec("LSOP12", g4.LsEncoder12, g4.LsDecoder12)
+    master = g4.CodecMaster(spec)
+    R, C, TR, TC = 90, 120, 3, 3
+    grid = oracle.terrain_i32(4000, 8000, TR * R, TC * C)
+    grid[0:R, 0:C] = -5
+    batch = master.encodeTiles(grid, R, C)
+    for t in range(TR * TC):
+        tr, tc = divmod(t, TC)
+        tile = grid[tr * R:(tr + 1) * R, tc * C:(tc + 1) * C]
+        cands = [oracle.codec_encode_i32(0, 0, tile)[0], oracle.codec_encode_i32(3, 1, tile)[0],
+                 oracle.lsop12_encode(2, tile, deflate=False)]
+        best = None
+        for c in cands:
+            if c is not None and (best is None or len(c) < len(best)):
+                best = c
+        assert batch.payload(t) == best, "tile %d: %s" % (t, first_diff(batch.payload(t), best))
+    out = master.decodeTiles(batch)
+    assert np.array_equal(out, grid)
