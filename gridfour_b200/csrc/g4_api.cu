@@ -65,6 +65,7 @@ struct g4_context {
   DevBuf scratch;      // per-CTA scratch
   DevBuf lists, src, total;
   DevBuf encScratch;   // per-CTA encoder scratch
+  DevBuf region;       // inflate staging (CodecDeflate / CodecFloat decode)
   DevBuf coef;         // LSOP12 decode: 12 float32 coefficients per tile
   // staging used by the host-memory entry points
   DevBuf sGrid, sArena, sOffsets, sLens, sCodec, sPred, sStatus;
@@ -139,6 +140,20 @@ int launch_decoder(g4_context* ctx, int codecId, DecodeArgs& a, int nCtas) {
       CK(launch_canon_decode(a, nCtas, ctx->stream));
       ctx->launches++;
       return G4_OK;
+    case G4_CODEC_DEFLATE: {
+      const size_t stride = round_up(size_t(a.band.tile_rows) * a.band.tile_cols * 6 + 64, 16);
+      CK(ctx->region.ensure(stride * nTiles));
+      CK(launch_deflate_decode(a, ctx->region.as<uint8_t>(), stride, nCtas, nTiles, ctx->stream));
+      ctx->launches += 2;
+      return G4_OK;
+    }
+    case G4_CODEC_FLOAT: {
+      const size_t stride = 5 * round_up(size_t(a.band.tile_rows) * a.band.tile_cols, 16);
+      CK(ctx->region.ensure(stride * nTiles));
+      CK(launch_float_decode(a, ctx->region.as<uint8_t>(), stride, nCtas, nTiles, ctx->stream));
+      ctx->launches += 2;
+      return G4_OK;
+    }
     case G4_CODEC_LSOP12:
       CK(ctx->coef.ensure(size_t(nTiles) * 12 * sizeof(float)));
       CK(launch_lsop_decode(a, ctx->coef.as<float>(), nCtas, nTiles, ctx->stream));
@@ -373,7 +388,7 @@ void g4_context_destroy(g4_context* ctx) {
   cudaStreamSynchronize(ctx->stream);
   for (auto& b : ctx->slots) b.release();
   DevBuf* bufs[] = {&ctx->candLens, &ctx->candPreds, &ctx->candStatus, &ctx->counters, &ctx->scratch, &ctx->lists, &ctx->src,
-                    &ctx->total, &ctx->coef, &ctx->encScratch, &ctx->sGrid, &ctx->sArena, &ctx->sOffsets, &ctx->sLens, &ctx->sCodec, &ctx->sPred, &ctx->sStatus};
+                    &ctx->total, &ctx->coef, &ctx->encScratch, &ctx->region, &ctx->sGrid, &ctx->sArena, &ctx->sOffsets, &ctx->sLens, &ctx->sCodec, &ctx->sPred, &ctx->sStatus};
   for (DevBuf* b : bufs) b->release();
   if (ctx->ownStream) cudaStreamDestroy(ctx->stream);
   delete ctx;
@@ -398,6 +413,8 @@ int g4_codec_supported(int codec_id, int direction) {
   // direction 0 = decode, 1 = encode.  Grows as codec kernels land; bench.py and the tests ask instead of guessing.
   switch (codec_id) {
     case G4_CODEC_HUFFMAN: return 1;
+    case G4_CODEC_DEFLATE: return direction == 0;
+    case G4_CODEC_FLOAT: return direction == 0;
     case G4_CODEC_CANON_HUFFMAN: return 1;
     case G4_CODEC_LSOP12: return 1;  // encode: canonical-Huffman body only (no Deflate alternative yet)
     default: return 0;
@@ -595,7 +612,7 @@ static int decode_one(g4_context* ctx, int codec_id, int elem, int n_rows, int n
   CK(cudaMemsetAsync(ctx->lists.p, 0, 4, ctx->stream));
   const uint32_t len32 = uint32_t(len);
   const int one = 1;
-  const int32_t pending = G4_ERR_CUDA;
+  const int32_t pending = 99;  // positive sentinel: a kernel that never reports leaves an unknown status
   CK(cudaMemcpyAsync(ctx->sArena.p, packing, len, cudaMemcpyHostToDevice, ctx->stream));
   CK(cudaMemcpyAsync(ctx->sLens.p, &len32, 4, cudaMemcpyHostToDevice, ctx->stream));
   CK(cudaMemcpyAsync(ctx->counters.as<int>() + 32, &one, 4, cudaMemcpyHostToDevice, ctx->stream));

@@ -93,6 +93,11 @@ cudaError_t launch_huffman_decode(const DecodeArgs& a, int nCtas, cudaStream_t s
 cudaError_t launch_canon_decode(const DecodeArgs& a, int nCtas, cudaStream_t s);
 cudaError_t launch_canon_encode(const EncodeArgs& a, int nCtas, cudaStream_t s);  // needs 32 KB scratch per CTA
 cudaError_t launch_lsop_encode(const EncodeArgs& a, int nCtas, cudaStream_t s);   // needs 32 KB scratch per CTA
+// region: HBM staging for inflated bytes, one slot of regionStride bytes per list position
+cudaError_t launch_deflate_decode(const DecodeArgs& a, uint8_t* region, size_t regionStride, int nCtas, int nTilesUpper,
+                                  cudaStream_t s);
+cudaError_t launch_float_decode(const DecodeArgs& a, uint8_t* region, size_t regionStride, int nCtas, int nTilesUpper,
+                                cudaStream_t s);
 // coef: [nTiles][12] floats of device scratch; nTilesUpper bounds the number of LSOP tiles in the list
 cudaError_t launch_lsop_decode(const DecodeArgs& a, float* coef, int nCtas, int nTilesUpper, cudaStream_t s);
 

@@ -16,6 +16,7 @@
 #include "g4_huffdec.cuh"
 #include "g4_canon.cuh"
 #include "g4_canon_enc.cuh"
+#include "g4_inflate.cuh"
 
 namespace g4 {
 
@@ -24,6 +25,7 @@ namespace {
 union LsopDecShared {
   HuffDecShared h;
   CanonDecShared c;
+  InflateWarpShared inf;
 };
 
 // StrictMath.round(float): floor(a + 1/2) evaluated on the bit pattern (java.lang.Math.round(float), JDK >= 8)
@@ -127,7 +129,6 @@ __global__ void __launch_bounds__(kThreads) lsop_decode_entropy_kernel(DecodeArg
     const uint32_t nInit = uint32_t(4 * R + 2 * C - 9);
     const uint32_t nInterior = uint32_t(R - 2) * uint32_t(C - 4);
     if (!h.ok || R < 6 || C < 6) status = G4_ERR_FORMAT;
-    else if (h.type == 1) status = G4_ERR_UNSUPPORTED;  // TODO(next): zlib streams (needs the GPU inflate)
     if (status == G4_OK) {
       BitSrc src;
       src.init(packing + h.headerSize, len - h.headerSize);
@@ -137,15 +138,38 @@ __global__ void __launch_bounds__(kThreads) lsop_decode_entropy_kernel(DecodeArg
         CellSink s2{t, kStreamLsopInterior};
         if (!canon_decode_stream(S.c, src, 0, nInit, 32768u, s1, &endBit, &nv) || nv != nInit) status = G4_ERR_FORMAT;
         else if (!canon_decode_stream(S.c, src, endBit, nInterior, 0u, s2, &endBit, &nv) || nv != nInterior) status = G4_ERR_FORMAT;
-      } else {  // type 0: two legacy Huffman streams back to back, each M32 coded (LsDecoder12.java:119-124)
+      } else {
+        // type 0: two legacy Huffman streams back to back, each M32 coded (LsDecoder12.java:119-124)
+        // type 1: two zlib streams; the second starts where the first one's input ended (:126-145)
         if (h.nInitCodes < nInit || h.nInitCodes > 6 * nInit || h.nInteriorCodes < nInterior || h.nInteriorCodes > 6 * nInterior)
           status = G4_ERR_FORMAT;
         else {
           uint8_t* m32a = a.scratch + size_t(blockIdx.x) * a.scratchStride;
           uint8_t* m32b = m32a + ((size_t(h.nInitCodes) + 31) & ~size_t(15));
           uint32_t endBit = 0;
-          if (!huffman_decode_stream(S.h, src, 0, h.nInitCodes, m32a, &endBit)) status = G4_ERR_FORMAT;
-          else if (!huffman_decode_stream(S.h, src, endBit, h.nInteriorCodes, m32b, &endBit)) status = G4_ERR_FORMAT;
+          bool entropyOk;
+          if (h.type == 1) {
+            __shared__ int sInfOk;
+            if (warp == 0) {
+              const uint8_t* z = packing + h.headerSize;
+              const uint32_t zLen = len - h.headerSize;
+              uint32_t produced = 0, consumed = 0;
+              int rc = inflate_warp(S.inf, z, zLen, m32a, h.nInitCodes, &produced, &consumed);
+              bool ok = rc == kInfOk && produced == h.nInitCodes && consumed <= zLen;
+              if (ok) {
+                uint32_t c1 = consumed;
+                rc = inflate_warp(S.inf, z + c1, zLen - c1, m32b, h.nInteriorCodes, &produced, &consumed);
+                ok = rc == kInfOk && produced == h.nInteriorCodes;
+              }
+              if (lane == 0) sInfOk = ok ? 1 : 0;
+            }
+            __syncthreads();
+            entropyOk = sInfOk != 0;
+          } else {
+            entropyOk = huffman_decode_stream(S.h, src, 0, h.nInitCodes, m32a, &endBit) &&
+                        huffman_decode_stream(S.h, src, endBit, h.nInteriorCodes, m32b, &endBit);
+          }
+          if (!entropyOk) status = G4_ERR_FORMAT;
           else {
             __syncthreads();
             if (!m32_parse_to_cells(m32a, h.nInitCodes, kStreamLsopInit, t, nInit, S.h.scan)) status = G4_ERR_FORMAT;
