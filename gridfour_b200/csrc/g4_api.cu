@@ -6,6 +6,7 @@
 // (paths under /root/reference/core/src/main/java/org/gridfour/).  No CPU compute path exists here:
 // every entry point launches CUDA kernels and fails with G4_ERR_CUDA when that is impossible.
 #include <cstdio>
+#include <cstdlib>
 #include <cstring>
 #include <string>
 #include <vector>
@@ -67,6 +68,10 @@ struct g4_context {
   DevBuf encScratch;   // per-CTA encoder scratch
   DevBuf region;       // inflate staging (CodecDeflate / CodecFloat decode)
   DevBuf coef;         // LSOP12 decode: 12 float32 coefficients per tile
+  // zlib-stream encode stages (CodecDeflate, CodecFloat, LSOP12 Deflate alternative)
+  DevBuf jobLen, jobOff, jobOut, jobTotal, streamIn, streamOut, deflateWork;
+  int deflateWorkers = 0;   // resident stream-worker threads (0 = default, see g4_context_create)
+  bool lsopDeflate = true;  // LsEncoder12.deflateEnabled (lsop/LsEncoder12.java:78)
   // staging used by the host-memory entry points
   DevBuf sGrid, sArena, sOffsets, sLens, sCodec, sPred, sStatus;
   // optional per-kernel timing (CUDA events on the launching stream): [0]=decode, [1]=encode, by codec kind
@@ -84,10 +89,79 @@ int persistent_ctas(const g4_context* ctx, int nTiles, int perSm) {
   return nTiles < cap ? nTiles : cap;
 }
 
+// ---- zlib-stream stages shared by the Deflate-based encoders ---------------------------------------------------------
+int ensure_jobs(g4_context* ctx, int nStreams) {
+  CK(ctx->jobLen.ensure(size_t(nStreams) * 4));
+  CK(ctx->jobOff.ensure(size_t(nStreams) * 8));
+  CK(ctx->jobOut.ensure(size_t(nStreams) * 4));
+  CK(ctx->jobTotal.ensure(8));
+  return G4_OK;
+}
+// jobLen is filled: offsets, then exact-size staging buffers (one host round trip for the total).
+int prepare_streams(g4_context* ctx, int nStreams) {
+  CK(launch_stream_offsets(ctx->jobLen.as<uint32_t>(), ctx->jobOff.as<uint64_t>(), nStreams, ctx->jobTotal.as<uint64_t>(), ctx->stream));
+  uint64_t total = 0;
+  CK(cudaMemcpyAsync(&total, ctx->jobTotal.p, 8, cudaMemcpyDeviceToHost, ctx->stream));
+  CK(cudaStreamSynchronize(ctx->stream));
+  CK(ctx->streamIn.ensure(total + 64));
+  CK(ctx->streamOut.ensure(total + 112ull * uint64_t(nStreams) + 256));
+  ctx->launches++;
+  return G4_OK;
+}
+int run_streams(g4_context* ctx, int nStreams, int capExtra, int level, int* counter) {
+  int nWorkers = nStreams < ctx->deflateWorkers ? nStreams : ctx->deflateWorkers;
+  nWorkers = (nWorkers + 31) / 32 * 32;
+  CK(ctx->deflateWork.ensure(size_t(nWorkers) * deflate_work_bytes()));
+  StreamArgs sa{};
+  sa.inBuf = ctx->streamIn.as<uint8_t>();
+  sa.inOff = ctx->jobOff.as<uint64_t>();
+  sa.inLen = ctx->jobLen.as<uint32_t>();
+  sa.outBuf = ctx->streamOut.as<uint8_t>();
+  sa.outLen = ctx->jobOut.as<uint32_t>();
+  sa.nStreams = nStreams;
+  sa.capExtra = capExtra;
+  sa.level = level;
+  sa.work = ctx->deflateWork.p;
+  sa.counter = counter;
+  CK(launch_deflate_streams(sa, nWorkers, ctx->stream));
+  ctx->launches++;
+  return G4_OK;
+}
+
 // Launch one candidate encoder over every tile of the band.
 struct KernelTimer;
 int launch_encoder_impl(g4_context* ctx, int codecId, EncodeArgs& a, int nTiles) {
+  const int nGrid = persistent_ctas(ctx, nTiles, 8);
+  uint32_t* jl = nullptr;
+  uint64_t* jo = nullptr;
+  uint32_t* jout = nullptr;
   switch (codecId) {
+    case G4_CODEC_DEFLATE: {
+      const int nStreams = 3 * nTiles;
+      int rc = ensure_jobs(ctx, nStreams);
+      if (rc != G4_OK) return rc;
+      jl = ctx->jobLen.as<uint32_t>(); jo = ctx->jobOff.as<uint64_t>(); jout = ctx->jobOut.as<uint32_t>();
+      CK(launch_deflate_m32_size(a, jl, nGrid, ctx->stream));
+      if ((rc = prepare_streams(ctx, nStreams)) != G4_OK) return rc;
+      CK(launch_deflate_m32_write(a, jl, jo, ctx->streamIn.as<uint8_t>(), nGrid, ctx->stream));
+      if ((rc = run_streams(ctx, nStreams, 118, 6, a.counter + 48)) != G4_OK) return rc;
+      CK(launch_deflate_pick(a, jl, jo, ctx->streamOut.as<uint8_t>(), jout, nGrid, ctx->stream));
+      ctx->launches += 3;
+      return G4_OK;
+    }
+    case G4_CODEC_FLOAT: {
+      const int nStreams = 5 * nTiles;
+      int rc = ensure_jobs(ctx, nStreams);
+      if (rc != G4_OK) return rc;
+      jl = ctx->jobLen.as<uint32_t>(); jo = ctx->jobOff.as<uint64_t>(); jout = ctx->jobOut.as<uint32_t>();
+      CK(launch_float_plane_size(nTiles, uint32_t(a.band.tile_rows) * uint32_t(a.band.tile_cols), jl, ctx->stream));
+      if ((rc = prepare_streams(ctx, nStreams)) != G4_OK) return rc;
+      CK(launch_float_plane_write(a, jo, ctx->streamIn.as<uint8_t>(), nGrid, ctx->stream));
+      if ((rc = run_streams(ctx, nStreams, 128, 9, a.counter + 48)) != G4_OK) return rc;
+      CK(launch_float_pick(a, jo, ctx->streamOut.as<uint8_t>(), jout, nGrid, ctx->stream));
+      ctx->launches += 3;
+      return G4_OK;
+    }
     case G4_CODEC_HUFFMAN: {
       int n = persistent_ctas(ctx, nTiles, 4);
       CK(launch_huffman_encode(a, n, ctx->stream));
@@ -104,6 +178,18 @@ int launch_encoder_impl(g4_context* ctx, int codecId, EncodeArgs& a, int nTiles)
       if (codecId == G4_CODEC_CANON_HUFFMAN) CK(launch_canon_encode(a, n, ctx->stream));
       else CK(launch_lsop_encode(a, n, ctx->stream));
       ctx->launches++;
+      if (codecId == G4_CODEC_LSOP12 && ctx->lsopDeflate) {  // LsEncoder12.java:170-218
+        const int nStreams = 2 * nTiles;
+        int rc = ensure_jobs(ctx, nStreams);
+        if (rc != G4_OK) return rc;
+        jl = ctx->jobLen.as<uint32_t>(); jo = ctx->jobOff.as<uint64_t>(); jout = ctx->jobOut.as<uint32_t>();
+        CK(launch_lsop_m32_size(a, jl, nGrid, ctx->stream));
+        if ((rc = prepare_streams(ctx, nStreams)) != G4_OK) return rc;
+        CK(launch_lsop_m32_write(a, jl, jo, ctx->streamIn.as<uint8_t>(), nGrid, ctx->stream));
+        if ((rc = run_streams(ctx, nStreams, 128, 6, a.counter + 48)) != G4_OK) return rc;
+        CK(launch_lsop_pick(a, jl, jo, ctx->streamOut.as<uint8_t>(), jout, nGrid, ctx->stream));
+        ctx->launches += 3;
+      }
       return G4_OK;
     }
     default:
@@ -373,6 +459,9 @@ int g4_context_create(int device, void* cuda_stream, g4_context** out) {
   cudaDeviceProp prop;
   CK(cudaGetDeviceProperties(&prop, device));
   ctx->smCount = prop.multiProcessorCount;
+  // resident zlib-stream worker threads: each owns a ~310 KB hash/symbol work area in HBM
+  ctx->deflateWorkers = ctx->smCount * 256;
+  if (const char* e = std::getenv("G4_DEFLATE_WORKERS")) { int v = std::atoi(e); if (v >= 32) ctx->deflateWorkers = v; }
   if (cuda_stream) ctx->stream = static_cast<cudaStream_t>(cuda_stream);
   else {
     CK(cudaStreamCreateWithFlags(&ctx->stream, cudaStreamNonBlocking));
@@ -388,7 +477,8 @@ void g4_context_destroy(g4_context* ctx) {
   cudaStreamSynchronize(ctx->stream);
   for (auto& b : ctx->slots) b.release();
   DevBuf* bufs[] = {&ctx->candLens, &ctx->candPreds, &ctx->candStatus, &ctx->counters, &ctx->scratch, &ctx->lists, &ctx->src,
-                    &ctx->total, &ctx->coef, &ctx->encScratch, &ctx->region, &ctx->sGrid, &ctx->sArena, &ctx->sOffsets, &ctx->sLens, &ctx->sCodec, &ctx->sPred, &ctx->sStatus};
+                    &ctx->total, &ctx->coef, &ctx->encScratch, &ctx->region, &ctx->jobLen, &ctx->jobOff, &ctx->jobOut, &ctx->jobTotal,
+                    &ctx->streamIn, &ctx->streamOut, &ctx->deflateWork, &ctx->sGrid, &ctx->sArena, &ctx->sOffsets, &ctx->sLens, &ctx->sCodec, &ctx->sPred, &ctx->sStatus};
   for (DevBuf* b : bufs) b->release();
   if (ctx->ownStream) cudaStreamDestroy(ctx->stream);
   delete ctx;
@@ -413,10 +503,10 @@ int g4_codec_supported(int codec_id, int direction) {
   // direction 0 = decode, 1 = encode.  Grows as codec kernels land; bench.py and the tests ask instead of guessing.
   switch (codec_id) {
     case G4_CODEC_HUFFMAN: return 1;
-    case G4_CODEC_DEFLATE: return direction == 0;
-    case G4_CODEC_FLOAT: return direction == 0;
+    case G4_CODEC_DEFLATE: return 1;
+    case G4_CODEC_FLOAT: return 1;
     case G4_CODEC_CANON_HUFFMAN: return 1;
-    case G4_CODEC_LSOP12: return 1;  // encode: canonical-Huffman body only (no Deflate alternative yet)
+    case G4_CODEC_LSOP12: return 1;
     default: return 0;
   }
 }

@@ -78,6 +78,21 @@ struct ClassifyArgs {
   int32_t* status;
 };
 
+// zlib streams of a band: stream j reads inBuf + inOff[j] (inLen[j] bytes, 0 = skip) and writes at most
+// inLen[j] + capExtra bytes to outBuf + inOff[j] + 112*j; outLen[j] = bytes written (g4_deflate_encode.cu).
+struct StreamArgs {
+  const uint8_t* inBuf;
+  const uint64_t* inOff;
+  const uint32_t* inLen;
+  uint8_t* outBuf;
+  uint32_t* outLen;
+  int nStreams;
+  int capExtra;  // 118 CodecDeflate (:206-210), 128 CodecFloat / LSOP12
+  int level;     // 6 or 9
+  void* work;    // nWorkers * deflate_work_bytes()
+  int* counter;  // zeroed before launch
+};
+
 cudaError_t launch_fill_terrain(int elemType, uint64_t seed, int64_t row0, int64_t col0, int64_t nRows, int64_t nCols, void* out,
                                 cudaStream_t s);
 cudaError_t launch_select(const SelectArgs& a, cudaStream_t s);
@@ -100,5 +115,26 @@ cudaError_t launch_float_decode(const DecodeArgs& a, uint8_t* region, size_t reg
                                 cudaStream_t s);
 // coef: [nTiles][12] floats of device scratch; nTilesUpper bounds the number of LSOP tiles in the list
 cudaError_t launch_lsop_decode(const DecodeArgs& a, float* coef, int nCtas, int nTilesUpper, cudaStream_t s);
+
+
+// ---- zlib-stream encode stages (g4_deflate_encode.cu, g4_lsop.cu) ------------------------------------------------
+size_t deflate_work_bytes();
+cudaError_t launch_stream_offsets(const uint32_t* inLen, uint64_t* inOff, int nStreams, uint64_t* total, cudaStream_t s);
+cudaError_t launch_deflate_streams(const StreamArgs& a, int nWorkers, cudaStream_t s);
+cudaError_t launch_deflate_m32_size(const EncodeArgs& a, uint32_t* inLen, int nCtas, cudaStream_t s);
+cudaError_t launch_deflate_m32_write(const EncodeArgs& a, const uint32_t* inLen, const uint64_t* inOff, uint8_t* inBuf, int nCtas,
+                                     cudaStream_t s);
+cudaError_t launch_deflate_pick(const EncodeArgs& a, const uint32_t* inLen, const uint64_t* inOff, const uint8_t* outBuf,
+                                const uint32_t* outLen, int nCtas, cudaStream_t s);
+cudaError_t launch_float_plane_size(int nTiles, uint32_t n, uint32_t* inLen, cudaStream_t s);
+cudaError_t launch_float_plane_write(const EncodeArgs& a, const uint64_t* inOff, uint8_t* inBuf, int nCtas, cudaStream_t s);
+cudaError_t launch_float_pick(const EncodeArgs& a, const uint64_t* inOff, const uint8_t* outBuf, const uint32_t* outLen, int nCtas,
+                              cudaStream_t s);
+// LSOP12 Deflate alternative (LsEncoder12.java:170-218): streams 2t (initializers) and 2t+1 (interior)
+cudaError_t launch_lsop_m32_size(const EncodeArgs& a, uint32_t* inLen, int nCtas, cudaStream_t s);
+cudaError_t launch_lsop_m32_write(const EncodeArgs& a, const uint32_t* inLen, const uint64_t* inOff, uint8_t* inBuf, int nCtas,
+                                  cudaStream_t s);
+cudaError_t launch_lsop_pick(const EncodeArgs& a, const uint32_t* inLen, const uint64_t* inOff, const uint8_t* outBuf,
+                             const uint32_t* outLen, int nCtas, cudaStream_t s);
 
 }  // namespace g4

@@ -17,6 +17,7 @@
 #include "g4_canon.cuh"
 #include "g4_canon_enc.cuh"
 #include "g4_inflate.cuh"
+#include "g4_m32stream.cuh"
 
 namespace g4 {
 
@@ -542,6 +543,103 @@ __global__ void __launch_bounds__(kThreads) lsop_encode_kernel(EncodeArgs a) {
       a.status[tIdx] = len <= a.slotBytes ? G4_OK : G4_ERR_CAPACITY;
     }
   }
+}
+
+// ---- Deflate alternative (LsEncoder12.java:170-218) ---------------------------------------------------------------
+// After lsop_encode_kernel has written the canonical-Huffman packing (type 2) into the tile's slot, the initializer
+// and interior residuals are M32 coded (LsOptimalPredictor12.java:143-282 fills both the int and the M32 forms),
+// deflated at level 6 by the stream workers, and the packing is replaced by the type-1 form when
+// insideN < canonLength and initN + insideN < canonLength (the reference compares bodies only, headers excluded).
+namespace {
+__device__ __forceinline__ void load_slot_coefficients(const uint8_t* slot, float* u) {
+  if (threadIdx.x < 12) u[threadIdx.x] = __uint_as_float(load_le32(slot + 7 + 4 * threadIdx.x));
+  __syncthreads();
+}
+}  // namespace
+
+__global__ void __launch_bounds__(kThreads) lsop_m32_size_kernel(EncodeArgs a, uint32_t* inLen) {
+  __shared__ uint32_t scan[kWarps + 1];
+  __shared__ float u[12];
+  const int nTiles = a.band.tiles_down * a.band.tiles_across;
+  for (int tIdx = blockIdx.x; tIdx < nTiles; tIdx += gridDim.x) {
+    __syncthreads();
+    if (a.status[tIdx] != G4_OK || a.lens[tIdx] < 55) {  // declined (too small / singular): nothing to deflate
+      if (threadIdx.x == 0) inLen[2 * tIdx] = inLen[2 * tIdx + 1] = 0;
+      continue;
+    }
+    const TileView t = tile_view(a.band, a.grid, tIdx);
+    load_slot_coefficients(a.slots + size_t(tIdx) * a.slotBytes, u);
+    const uint32_t nInit = uint32_t(4 * t.R + 2 * t.C - 9);
+    const uint32_t nInterior = uint32_t(t.R - 2) * uint32_t(t.C - 4);
+    uint32_t s0 = m32_stream_size(LsInitGet{t}, nInit, scan);
+    uint32_t s1 = m32_stream_size(LsInteriorGet{t, u}, nInterior, scan);
+    if (threadIdx.x == 0) { inLen[2 * tIdx] = s0; inLen[2 * tIdx + 1] = s1; }
+  }
+}
+
+__global__ void __launch_bounds__(kThreads) lsop_m32_write_kernel(EncodeArgs a, const uint32_t* inLen, const uint64_t* inOff,
+                                                                  uint8_t* inBuf) {
+  __shared__ uint32_t scan[kWarps + 1];
+  __shared__ float u[12];
+  const int nTiles = a.band.tiles_down * a.band.tiles_across;
+  for (int tIdx = blockIdx.x; tIdx < nTiles; tIdx += gridDim.x) {
+    __syncthreads();
+    if (inLen[2 * tIdx + 1] == 0) continue;
+    const TileView t = tile_view(a.band, a.grid, tIdx);
+    load_slot_coefficients(a.slots + size_t(tIdx) * a.slotBytes, u);
+    const uint32_t nInit = uint32_t(4 * t.R + 2 * t.C - 9);
+    const uint32_t nInterior = uint32_t(t.R - 2) * uint32_t(t.C - 4);
+    uint8_t* d0 = inBuf + inOff[2 * tIdx];
+    uint8_t* d1 = inBuf + inOff[2 * tIdx + 1];
+    uint32_t w0 = m32_stream_write(LsInitGet{t}, nInit, d0, scan);
+    uint32_t w1 = m32_stream_write(LsInteriorGet{t, u}, nInterior, d1, scan);
+    if (threadIdx.x < 16) { d0[w0 + threadIdx.x] = 0; d1[w1 + threadIdx.x] = 0; }
+  }
+}
+
+__global__ void __launch_bounds__(kThreads) lsop_pick_kernel(EncodeArgs a, const uint32_t* inLen, const uint64_t* inOff,
+                                                             const uint8_t* outBuf, const uint32_t* outLen) {
+  const int tid = threadIdx.x;
+  const int nTiles = a.band.tiles_down * a.band.tiles_across;
+  for (int tIdx = blockIdx.x; tIdx < nTiles; tIdx += gridDim.x) {
+    if (inLen[2 * tIdx + 1] == 0) continue;
+    const uint32_t canonLength = a.lens[tIdx] - 55u;
+    const uint32_t initN = outLen[2 * tIdx], insideN = outLen[2 * tIdx + 1];
+    if (insideN == 0 || insideN >= canonLength) continue;         // LsEncoder12.java:185-190
+    if (initN == 0 || initN + insideN >= canonLength) continue;   // :197-201
+    const uint32_t len = 63u + initN + insideN;
+    if (len > a.slotBytes) {
+      if (tid == 0) a.status[tIdx] = G4_ERR_CAPACITY;
+      continue;
+    }
+    uint8_t* slot = a.slots + size_t(tIdx) * a.slotBytes;
+    if (tid == 0) {
+      slot[1] = uint8_t(0x40u | 1u);  // revision flag | COMPRESSION_TYPE_DEFLATE (LsHeader.java:220-245)
+      const uint32_t n0 = inLen[2 * tIdx], n1 = inLen[2 * tIdx + 1];
+      for (int k = 0; k < 4; k++) { slot[55 + k] = uint8_t(n0 >> (8 * k)); slot[59 + k] = uint8_t(n1 >> (8 * k)); }
+      a.lens[tIdx] = len;
+      a.preds[tIdx] = 1;
+    }
+    const uint8_t* s0 = outBuf + inOff[2 * tIdx] + 112ull * uint64_t(2 * tIdx);
+    const uint8_t* s1 = outBuf + inOff[2 * tIdx + 1] + 112ull * uint64_t(2 * tIdx + 1);
+    for (uint32_t i = tid; i < initN; i += kThreads) slot[63 + i] = s0[i];
+    for (uint32_t i = tid; i < insideN; i += kThreads) slot[63 + initN + i] = s1[i];
+  }
+}
+
+cudaError_t launch_lsop_m32_size(const EncodeArgs& a, uint32_t* inLen, int nCtas, cudaStream_t s) {
+  lsop_m32_size_kernel<<<nCtas, kThreads, 0, s>>>(a, inLen);
+  return cudaGetLastError();
+}
+cudaError_t launch_lsop_m32_write(const EncodeArgs& a, const uint32_t* inLen, const uint64_t* inOff, uint8_t* inBuf, int nCtas,
+                                  cudaStream_t s) {
+  lsop_m32_write_kernel<<<nCtas, kThreads, 0, s>>>(a, inLen, inOff, inBuf);
+  return cudaGetLastError();
+}
+cudaError_t launch_lsop_pick(const EncodeArgs& a, const uint32_t* inLen, const uint64_t* inOff, const uint8_t* outBuf,
+                             const uint32_t* outLen, int nCtas, cudaStream_t s) {
+  lsop_pick_kernel<<<nCtas, kThreads, 0, s>>>(a, inLen, inOff, outBuf, outLen);
+  return cudaGetLastError();
 }
 
 cudaError_t launch_lsop_encode(const EncodeArgs& a, int nCtas, cudaStream_t s) {

@@ -140,7 +140,7 @@ def test_lsop_coefficients_and_streams_byte_exact(g4, oracle):
     enc = g4.LsEncoder12()
     checked = 0
     for name, grid in parity_grids(oracle).items():
-        exp = oracle.lsop12_encode(1, grid, deflate=False)
+        exp = oracle.lsop12_encode(1, grid)
         got = enc.encode(1, grid.shape[0], grid.shape[1], grid)
         if exp is None:
             assert got is None, name
@@ -155,7 +155,7 @@ def test_lsop_coefficients_and_streams_byte_exact(g4, oracle):
 
 def test_batch_best_of_three_matches_oracle(g4, oracle):
     """encodeTiles with [GvrsHuffman, GvrsCanonicalHuffman, LSOP12]: per-tile choice and bytes equal the oracle's
-    CodecMaster rule (LSOP12 with the Deflate alternative disabled on both sides)."""
+    CodecMaster rule (LSOP12 with its default Deflate alternative)."""
     spec = g4.CodecSpecification(default=False)
     spec.addCompressionCodec("GvrsHuffman", g4.CodecHuffman)
     spec.addCompressionCodec("GvrsCanonicalHuffman", g4.CodecCanonHuffman)
@@ -169,7 +169,7 @@ def test_batch_best_of_three_matches_oracle(g4, oracle):
         tr, tc = divmod(t, TC)
         tile = grid[tr * R:(tr + 1) * R, tc * C:(tc + 1) * C]
         cands = [oracle.codec_encode_i32(0, 0, tile)[0], oracle.codec_encode_i32(3, 1, tile)[0],
-                 oracle.lsop12_encode(2, tile, deflate=False)]
+                 oracle.lsop12_encode(2, tile)]
         best = None
         for c in cands:
             if c is not None and (best is None or len(c) < len(best)):
