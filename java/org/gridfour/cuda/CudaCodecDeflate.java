@@ -1,0 +1,16 @@
+/* CudaCodecDeflate.java -- drop-in for compress/CodecDeflate.java behind the codec plugin API.  SOURCE ONLY.
+ * The class lists both interfaces DIRECTLY because GvrsFileSpecification.addCompressionCodec inspects
+ * getInterfaces() of the class itself (gvrs/GvrsFileSpecification.java:1608-1626); a public no-argument
+ * constructor is invoked lazily by CodecHolder (gvrs/CodecHolder.java:189-234).
+ */
+package org.gridfour.cuda;
+
+import org.gridfour.compress.ICompressionDecoder;
+import org.gridfour.compress.ICompressionEncoder;
+
+public class CudaCodecDeflate extends CudaCodecBase implements ICompressionEncoder, ICompressionDecoder {
+
+  public CudaCodecDeflate() {
+    super(G4Native.CODEC_DEFLATE);
+  }
+}
