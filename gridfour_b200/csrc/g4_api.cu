@@ -68,6 +68,8 @@ struct g4_context {
   DevBuf encScratch;   // per-CTA encoder scratch
   DevBuf region;       // inflate staging (CodecDeflate / CodecFloat decode)
   DevBuf coef;         // LSOP12 decode: 12 float32 coefficients per tile
+  DevBuf defer;        // LSOP12 decode: tiles the fast entropy kernel hands to the general one
+  DevBuf lsopMeta;     // LSOP12 decode: interior code lengths + text position, kernel H -> kernel T
   // zlib-stream encode stages (CodecDeflate, CodecFloat, LSOP12 Deflate alternative)
   DevBuf jobLen, jobOff, jobOut, jobTotal, streamIn, streamOut, deflateWork;
   int deflateWorkers = 0;   // resident stream-worker threads (0 = default, see g4_context_create)
@@ -242,8 +244,11 @@ int launch_decoder(g4_context* ctx, int codecId, DecodeArgs& a, int nCtas) {
     }
     case G4_CODEC_LSOP12:
       CK(ctx->coef.ensure(size_t(nTiles) * 12 * sizeof(float)));
-      CK(launch_lsop_decode(a, ctx->coef.as<float>(), nCtas, nTiles, ctx->stream));
-      ctx->launches += 2;
+      CK(ctx->defer.ensure(size_t(nTiles) * sizeof(int)));
+      CK(ctx->lsopMeta.ensure(size_t(nTiles) * lsop_meta_bytes()));
+      CK(launch_lsop_decode(a, ctx->coef.as<float>(), ctx->lsopMeta.as<uint8_t>(), ctx->defer.as<int>(), ctx->counters.as<int>() + 56,
+                            nCtas, nTiles, ctx->stream));
+      ctx->launches += 4;
       return G4_OK;
     default:
       tlsError = "codec not implemented on the GPU yet";
@@ -477,7 +482,7 @@ void g4_context_destroy(g4_context* ctx) {
   cudaStreamSynchronize(ctx->stream);
   for (auto& b : ctx->slots) b.release();
   DevBuf* bufs[] = {&ctx->candLens, &ctx->candPreds, &ctx->candStatus, &ctx->counters, &ctx->scratch, &ctx->lists, &ctx->src,
-                    &ctx->total, &ctx->coef, &ctx->encScratch, &ctx->region, &ctx->jobLen, &ctx->jobOff, &ctx->jobOut, &ctx->jobTotal,
+                    &ctx->total, &ctx->coef, &ctx->defer, &ctx->lsopMeta, &ctx->encScratch, &ctx->region, &ctx->jobLen, &ctx->jobOff, &ctx->jobOut, &ctx->jobTotal,
                     &ctx->streamIn, &ctx->streamOut, &ctx->deflateWork, &ctx->sGrid, &ctx->sArena, &ctx->sOffsets, &ctx->sLens, &ctx->sCodec, &ctx->sPred, &ctx->sStatus};
   for (DevBuf* b : bufs) b->release();
   if (ctx->ownStream) cudaStreamDestroy(ctx->stream);

@@ -36,8 +36,9 @@ struct CanonDecShared {
 
 // ---- serial table parse (one thread) ------------------------------------------------------------------
 // canonical decode of one symbol by arithmetic on (firstCode,count,offset); codes are MSB-first
+template <class Src>
 __device__ inline int canon_slow_symbol(const uint16_t* firstCode, const uint16_t* count, const uint16_t* offset,
-                                        const uint16_t* sorted, const BitSrc& src, uint32_t* pos, int minLen) {
+                                        const uint16_t* sorted, const Src& src, uint32_t* pos, int minLen) {
   uint32_t v = __brev(src.peek32(*pos));  // first stream bit is now the MSB
   for (int len = minLen; len <= 15; len++) {
     uint32_t code = v >> (32 - len);

@@ -1,0 +1,437 @@
+// g4_canon_fast.cuh -- canonical Huffman text decoder, fast path: the packing is staged in shared memory and every
+// thread decodes from a 64-bit register bit buffer.
+//
+// Same stream format and the same self-synchronising sub-sequence scheme as g4_canon.cuh (reference:
+// compress/canonicalHuffman/CanonicalHuffman.java:441-519, CanonHuffTreeDecoder.java:68-177, LengthEncoder.java:197-236
+// under /root/reference/core/src/main/java/org/gridfour/).  What changes is where the bits come from and how often
+// they are touched:
+//   * the whole packing (typically ~19 KB for a 180x240 tile) is copied once, coalesced, into shared memory,
+//   * a symbol costs one shared-memory LUT read and two 64-bit shifts; the buffer is refilled a word at a time,
+//   * the serial table parse uses an 8-bit LUT for the 20-symbol code-table code,
+//   * pass 0 only needs each sub-sequence's END, so it starts a fixed distance before the limit instead of decoding the
+//     whole sub-sequence (a wrong guess is repaired by the later passes; the result never depends on it),
+//   * values leave through a sink that is handed runs of consecutive value indices (begin / put / end), so the caller
+//     can keep a running cell address instead of dividing per value.
+// Packings that do not fit the staging buffer fall back to g4_canon.cuh.
+#pragma once
+#include "g4_canon.cuh"
+
+namespace g4 {
+
+constexpr int kFastStageWords = 8192;  // 32 KB of packing
+constexpr int kFastMaxSub = 1536;
+constexpr int kFastSubPerThread = kFastMaxSub / kThreads;
+constexpr int kFastLutBits = 11;
+constexpr uint32_t kFastSpecial = 0x8000u;  // LUT flag: symbol >= 256 (null, escapes, end of text)
+
+struct CanonFastShared {
+  uint32_t sw[kFastStageWords + 8];   // staged packing; word 0 = packing bytes 0..3
+  uint16_t lut[1 << kFastLutBits];    // sym | len << 9 | special; 0 = code longer than the LUT
+  uint16_t sorted[kCanonSymbols];
+  uint16_t firstCode[17], count[17], offset[17];
+  uint8_t lens[kCanonSymbols + 4];
+  uint16_t ctLut[256];                // code-table code: sym | len << 8; 0 = longer than 8 bits
+  uint32_t endpos[kFastMaxSub];
+  uint32_t off[kFastMaxSub];
+  uint16_t cnt[kFastMaxSub];
+  uint8_t eot[kFastMaxSub];
+  uint32_t scan[kWarps + 1];
+  uint32_t textStart;
+  int error, changed, firstEot;
+};
+
+// Bit source over the staged words (absolute bit positions inside the packing).
+struct SmemBitSrc {
+  const uint32_t* w;
+  uint32_t nBits;
+  __device__ __forceinline__ uint32_t peek32(uint32_t pos) const {
+    uint32_t i = pos >> 5;
+    return __funnelshift_r(w[i], w[i + 1], pos & 31);  // the staging buffer is zero padded past the data
+  }
+  __device__ __forceinline__ uint32_t bits(uint32_t pos, int n) const {
+    uint32_t v = peek32(pos);
+    return n == 32 ? v : (v & ((1u << n) - 1u));
+  }
+};
+
+// 64-bit register bit buffer; at least 32 valid bits after every skip().
+struct BitCursor {
+  const uint32_t* w;
+  uint32_t pos, next;
+  uint64_t buf;
+  int avail;
+  __device__ __forceinline__ void init(const uint32_t* words, uint32_t p) {
+    w = words;
+    pos = p;
+    uint32_t i = p >> 5, s = p & 31;
+    buf = ((uint64_t(w[i + 1]) << 32) | w[i]) >> s;
+    avail = 64 - int(s);
+    next = i + 2;
+  }
+  __device__ __forceinline__ uint32_t peek() const { return uint32_t(buf); }
+  __device__ __forceinline__ void skip(int n) {
+    buf >>= n;
+    avail -= n;
+    pos += uint32_t(n);
+    if (avail < 32) {
+      buf |= uint64_t(w[next++]) << avail;
+      avail += 32;
+    }
+  }
+};
+
+// Copies the packing into S.sw (coalesced 32-bit loads; `packing` is 4-byte aligned) and zero pads.  All threads call.
+__device__ inline void canon_fast_stage(CanonFastShared& S, const uint8_t* packing, uint32_t len) {
+  const uint32_t nWords = (len + 3) >> 2;
+  const uint32_t* g = reinterpret_cast<const uint32_t*>(packing);
+  for (uint32_t i = threadIdx.x; i < nWords; i += kThreads) S.sw[i] = __ldg(g + i);
+  if (threadIdx.x < 8) S.sw[nWords + threadIdx.x] = 0;
+  __syncthreads();
+  if (threadIdx.x == 0 && (len & 3)) S.sw[nWords - 1] &= (1u << (8 * (len & 3))) - 1u;  // bytes past the packing read as zero
+  __syncthreads();
+}
+
+// LengthEncoder.readEncodedLengths (:197-236) + CanonHuffTreeDecoder.decodeTree (:131-177).  One thread.
+__device__ inline void canon_fast_parse_header(CanonFastShared& S, const SmemBitSrc& src, uint32_t startBit) {
+  S.error = 0;
+  uint32_t pos = startBit + 1;  // reserved bit
+  uint8_t ctLens[20];
+  {
+    int k = 0, prior = 0;
+    while (k < 20) {
+      if (pos + 5 > src.nBits) { S.error = 1; return; }
+      int index = int(src.bits(pos, 5));
+      pos += 5;
+      int n = 1, val = index;
+      if (index <= 15) prior = index;
+      else if (index == 16) { n = int(src.bits(pos, 2)) + 3; pos += 2; val = prior; }
+      else if (index == 17) { n = int(src.bits(pos, 3)) + 3; pos += 3; val = 0; prior = 0; }
+      else if (index == 18) { n = int(src.bits(pos, 7)) + 11; pos += 7; val = 0; prior = 0; }
+      else continue;  // reference ignores other values
+      if (k + n > 20) { S.error = 1; return; }
+      for (int i = 0; i < n; i++) ctLens[k++] = uint8_t(val);
+    }
+  }
+  uint16_t fc[17], cn[17], of[17], so[20];
+  if (!canon_build_tables(ctLens, 20, fc, cn, of, so)) { S.error = 1; return; }
+  int minLen = 1;
+  while (minLen < 15 && cn[minLen] == 0) minLen++;
+  // 8-bit LUT of the code-table code: a code of length l (MSB first in the LSB-first stream) owns every index whose
+  // low l bits are the bit-reversed code
+  for (int i = 0; i < 256; i++) S.ctLut[i] = 0;
+  for (int l = 1; l <= 8; l++)
+    for (int d = 0; d < cn[l]; d++) {
+      uint32_t rev = __brev(uint32_t(fc[l] + d)) >> (32 - l);
+      uint16_t entry = uint16_t(so[of[l] + d] | (l << 8));
+      for (uint32_t hi = 0; hi < (1u << (8 - l)); hi++) S.ctLut[rev | (hi << l)] = entry;
+    }
+  int prior = 0;
+  for (int i = 0; i < kCanonSymbols; i++) S.lens[i] = 0;
+  for (int i = 0; i < kCanonSymbols; i++) {
+    if (pos >= src.nBits) { S.error = 1; return; }
+    int test;
+    uint32_t e = S.ctLut[src.peek32(pos) & 0xffu];
+    if (e) { test = int(e & 0xffu); pos += e >> 8; }
+    else test = canon_slow_symbol(fc, cn, of, so, src, &pos, minLen > 9 ? minLen : 9);
+    if (test < 0) { S.error = 1; return; }
+    if (test <= 15) { S.lens[i] = uint8_t(test); prior = test; }
+    else {
+      int n, val = 0;
+      if (test == 16) { n = int(src.bits(pos, 2)) + 3; pos += 2; val = prior; }
+      else if (test == 17) { n = int(src.bits(pos, 3)) + 3; pos += 3; prior = 0; }
+      else if (test == 18) { n = int(src.bits(pos, 7)) + 11; pos += 7; prior = 0; }
+      else continue;  // the code table's own end-of-text symbol: leaves a zero length
+      if (i + n > kCanonSymbols) { S.error = 1; return; }
+      for (int j = 0; j < n; j++) S.lens[i + j] = uint8_t(val);
+      i += n - 1;
+    }
+  }
+  if (!canon_build_tables(S.lens, kCanonSymbols, S.firstCode, S.count, S.offset, S.sorted)) { S.error = 1; return; }
+  if (S.lens[kSymEot] == 0) { S.error = 1; return; }
+  S.textStart = pos;
+}
+
+// One symbol at the cursor: returns the LUT-style entry (sym | special flag) and advances past the code.
+// Returns -1 for an invalid code.
+__device__ __forceinline__ int canon_fast_symbol(const CanonFastShared& S, BitCursor& cur, uint32_t nBits) {
+  uint32_t e = S.lut[cur.peek() & ((1u << kFastLutBits) - 1u)];
+  if (e) {
+    cur.skip(int((e >> 9) & 15u));
+    return int(e & (0x1ffu | kFastSpecial));
+  }
+  SmemBitSrc src{cur.w, nBits};
+  uint32_t p = cur.pos;
+  int sym = canon_slow_symbol(S.firstCode, S.count, S.offset, S.sorted, src, &p, kFastLutBits + 1);
+  if (sym < 0) return -1;
+  cur.init(cur.w, p);
+  return sym >= 256 ? int(uint32_t(sym) | kFastSpecial) : sym;
+}
+
+// Counting decode of one sub-sequence: from `start` to the first value boundary at or after `limit`.
+// flag: 1 = end of text consumed, 2 = invalid code / ran past the data.
+__device__ __forceinline__ void canon_fast_count(const CanonFastShared& S, uint32_t nBits, uint32_t start, uint32_t limit,
+                                                 uint32_t* endOut, uint32_t* cntOut, int* flagOut) {
+  BitCursor cur;
+  cur.init(S.sw, start);
+  uint32_t c = 0;
+  int flag = 0;
+  uint32_t end;
+  for (;;) {
+    const uint32_t p0 = cur.pos;
+    if (p0 >= nBits) { flag = 2; end = p0; break; }
+    int e = canon_fast_symbol(S, cur, nBits);
+    if (e < 0) { flag = 2; end = p0; break; }
+    if (!(uint32_t(e) & kFastSpecial)) {
+      if (p0 >= limit) { end = p0; break; }
+      c++;
+      continue;
+    }
+    const int sym = e & 0x1ff;
+    if (sym == kSymEsc2) cur.skip(2);
+    else if (sym == kSymEsc8) cur.skip(8);
+    else {
+      if (p0 >= limit) { end = p0; break; }
+      if (sym == kSymEot) { flag = 1; end = cur.pos; break; }
+      c++;  // null symbol: a value
+    }
+  }
+  *endOut = end;
+  *cntOut = c;
+  *flagOut = flag;
+}
+
+// Parallel construction of firstCode / count / offset / sorted from S.lens (CanonHuffTreeDecoder.java:68-129 builds
+// the equivalent tree).  Sets S.error for an over-subscribed or empty code.  All threads call.
+__device__ inline void canon_fast_tables_cta(CanonFastShared& S) {
+  __shared__ uint32_t cnt32[17];
+  const int tid = threadIdx.x;
+  if (tid < 17) cnt32[tid] = 0;
+  __syncthreads();
+  for (int i = tid; i < kCanonSymbols; i += kThreads) {
+    int l = S.lens[i];
+    if (l > 15) S.error = 1;
+    else if (l) atomicAdd(&cnt32[l], 1u);
+  }
+  __syncthreads();
+  if (tid == 0) {
+    uint32_t code = 0, off = 0;
+    S.count[0] = 0; S.firstCode[0] = 0; S.offset[0] = 0;
+    S.count[16] = 0; S.firstCode[16] = 0; S.offset[16] = 0;
+    for (int l = 1; l <= 15; l++) {
+      uint32_t c = cnt32[l];
+      S.firstCode[l] = uint16_t(code);
+      S.offset[l] = uint16_t(off);
+      S.count[l] = uint16_t(c);
+      if (code + c > (1u << l)) S.error = 1;  // over-subscribed
+      code = (code + c) << 1;
+      off += c;
+    }
+    if (off == 0 || S.lens[kSymEot] == 0) S.error = 1;
+  }
+  __syncthreads();
+  for (int i = tid; i < kCanonSymbols; i += kThreads) {
+    const int l = S.lens[i];
+    if (l == 0 || l > 15) continue;
+    int rank = 0;
+    for (int j = 0; j < i; j++) rank += S.lens[j] == l;
+    S.sorted[S.offset[l] + rank] = uint16_t(i);
+  }
+  __syncthreads();
+}
+
+// 11-bit lookup table: thread per prefix, canonical arithmetic on the bit-reversed prefix.  All threads call.
+__device__ inline void canon_fast_build_lut(CanonFastShared& S) {
+  for (int e = threadIdx.x; e < (1 << kFastLutBits); e += kThreads) {
+    uint32_t v = __brev(uint32_t(e));
+    uint16_t entry = 0;
+    for (int len = 1; len <= kFastLutBits; len++) {
+      uint32_t code = v >> (32 - len);
+      uint32_t d = code - S.firstCode[len];
+      if (d < S.count[len]) {
+        uint32_t sym = S.sorted[S.offset[len] + d];
+        entry = uint16_t(sym | (uint32_t(len) << 9) | (sym >= 256 ? kFastSpecial : 0u));
+        break;
+      }
+    }
+    S.lut[e] = entry;
+  }
+  __syncthreads();
+}
+
+// Decodes the TEXT of one canonical stream staged in S.sw; tables and LUT are ready and the text starts at bit T0.
+// *endBit are absolute bit positions inside the packing, nBits = 8 * packing length.  The sink receives runs:
+// begin(firstValueIndex), put(value) ..., end().  hintBits bounds the region searched first (0 = everything).
+// All threads call.
+template <class Sink>
+__device__ bool canon_fast_decode_text(CanonFastShared& S, uint32_t nBits, const uint32_t T0, uint32_t maxValues, uint32_t hintBits,
+                                       Sink sink, uint32_t* endBit, uint32_t* nValues) {
+  const int tid = threadIdx.x;
+  uint32_t regionEnd = nBits;
+  if (hintBits && T0 + hintBits < regionEnd) regionEnd = T0 + hintBits;
+  for (;;) {  // region growth until the end-of-text code is inside the region
+    const uint32_t avail = regionEnd - T0;
+    // sub-sequence size: ~112 bits, adjusted so that the sub-sequences fill whole rounds of kThreads threads
+    uint32_t rounds = (avail / 112u + kThreads - 1) / kThreads;
+    if (rounds < 1u) rounds = 1u;
+    if (rounds > uint32_t(kFastSubPerThread)) rounds = kFastSubPerThread;
+    uint32_t B = (avail + rounds * kThreads - 1) / (rounds * kThreads);
+    if (B < 96u) B = 96u;
+    const int nSub = int((avail + B - 1) / B);
+    // pass 0: only the END of every sub-sequence matters here, so start late (64 bits before the limit) and rely on
+    // self-synchronisation; sub-sequence 0 starts at the true text start.
+    uint32_t myStart[kFastSubPerThread];
+#pragma unroll
+    for (int j = 0; j < kFastSubPerThread; j++) {
+      int i = tid + j * kThreads;
+      myStart[j] = T0 + uint32_t(i) * B;
+      if (i < nSub) {
+        uint32_t limit = T0 + uint32_t(i + 1) * B;
+        if (limit > regionEnd) limit = regionEnd;
+        uint32_t from = myStart[j];
+        if (i > 0 && limit - from > 64u) from = limit - 64u;
+        uint32_t e, c;
+        int f;
+        canon_fast_count(S, nBits, from, limit, &e, &c, &f);
+        S.endpos[i] = e;
+        S.cnt[i] = uint16_t(c);
+        S.eot[i] = uint8_t(f);
+        if (i > 0) myStart[j] = 0xffffffffu;  // forces the exact re-decode in the first synchronisation pass
+      }
+    }
+    for (int pass = 0; pass <= nSub; pass++) {
+      __syncthreads();
+      if (tid == 0) S.changed = 0;
+      uint32_t ns[kFastSubPerThread];
+#pragma unroll
+      for (int j = 0; j < kFastSubPerThread; j++) {
+        int i = tid + j * kThreads;
+        ns[j] = (i > 0 && i < nSub) ? S.endpos[i - 1] : myStart[j];
+      }
+      __syncthreads();
+      bool any = false;
+#pragma unroll
+      for (int j = 0; j < kFastSubPerThread; j++) {
+        int i = tid + j * kThreads;
+        if (i < nSub && ns[j] != myStart[j]) {
+          myStart[j] = ns[j];
+          uint32_t limit = T0 + uint32_t(i + 1) * B;
+          if (limit > regionEnd) limit = regionEnd;
+          uint32_t e, c;
+          int f;
+          canon_fast_count(S, nBits, myStart[j], limit, &e, &c, &f);
+          S.endpos[i] = e;
+          S.cnt[i] = uint16_t(c);
+          S.eot[i] = uint8_t(f);
+          any = true;
+        }
+      }
+      if (any) S.changed = 1;
+      __syncthreads();
+      if (!S.changed) break;
+    }
+    __syncthreads();
+    if (tid == 0) S.firstEot = nSub;
+    __syncthreads();
+#pragma unroll
+    for (int j = 0; j < kFastSubPerThread; j++) {
+      int i = tid + j * kThreads;
+      if (i < nSub && S.eot[i]) atomicMin(&S.firstEot, i);
+    }
+    __syncthreads();
+    const int fe = S.firstEot;
+    if (fe < nSub && S.eot[fe] == 2) return false;  // invalid code, or the data ended before end-of-text
+    if (fe == nSub) {                               // no end-of-text inside the region: widen it
+      if (regionEnd >= nBits) return false;
+      uint32_t grown = (regionEnd - T0) * 4u;
+      regionEnd = (grown > nBits - T0) ? nBits : T0 + grown;
+      __syncthreads();
+      continue;
+    }
+    // value offsets (contiguous ownership for the scan)
+    uint32_t local[kFastSubPerThread];
+    uint32_t mySum = 0;
+#pragma unroll
+    for (int j = 0; j < kFastSubPerThread; j++) {
+      int i = tid * kFastSubPerThread + j;
+      local[j] = (i <= fe) ? S.cnt[i] : 0u;
+      mySum += local[j];
+    }
+    uint32_t total;
+    uint32_t ex = block_exclusive_scan(mySum, S.scan, &total);
+    if (total > maxValues) return false;
+    {
+      uint32_t run = ex;
+#pragma unroll
+      for (int j = 0; j < kFastSubPerThread; j++) {
+        int i = tid * kFastSubPerThread + j;
+        if (i < nSub) S.off[i] = run;
+        run += local[j];
+      }
+    }
+    __syncthreads();
+    // write pass: decode again, assembling escapes into values
+    bool bad = false;
+#pragma unroll
+    for (int j = 0; j < kFastSubPerThread; j++) {
+      int i = tid + j * kThreads;
+      if (i <= fe && i < nSub) {
+        uint32_t limit = T0 + uint32_t(i + 1) * B;
+        if (limit > regionEnd) limit = regionEnd;
+        BitCursor cur;
+        cur.init(S.sw, myStart[j]);
+        sink.begin(S.off[i]);
+        bool have = false;
+        uint32_t v = 0;
+        for (;;) {
+          const uint32_t p0 = cur.pos;
+          if (p0 >= nBits) { bad = true; break; }
+          int e = canon_fast_symbol(S, cur, nBits);
+          if (e < 0) { bad = true; break; }
+          if (!(uint32_t(e) & kFastSpecial)) {
+            if (p0 >= limit) break;
+            if (have) sink.put(int32_t(v));
+            have = true;
+            v = uint32_t(e - 128);
+            continue;
+          }
+          const int sym = e & 0x1ff;
+          if (sym == kSymEsc2 || sym == kSymEsc8) {
+            if (!have) { bad = true; break; }  // an escape with nothing to extend (CanonicalHuffman.java:495-504 would index -1)
+            const int nb = sym == kSymEsc2 ? 2 : 8;
+            v = (v << nb) | (cur.peek() & ((1u << nb) - 1u));
+            cur.skip(nb);
+          } else {
+            if (p0 >= limit) break;
+            if (sym == kSymEot) break;
+            if (have) sink.put(int32_t(v));
+            have = true;
+            v = uint32_t(INT32_MIN);  // null symbol
+          }
+        }
+        if (have) sink.put(int32_t(v));
+        sink.end();
+      }
+    }
+    if (__syncthreads_or(bad ? 1 : 0)) return false;
+    *endBit = S.endpos[fe];
+    *nValues = total;
+    return true;
+  }
+}
+
+// Header + text of one canonical stream staged in S.sw (startBit absolute).  All threads call.
+template <class Sink>
+__device__ bool canon_fast_decode_stream(CanonFastShared& S, uint32_t nBits, uint32_t startBit, uint32_t maxValues, uint32_t hintBits,
+                                         Sink sink, uint32_t* endBit, uint32_t* nValues) {
+  __syncthreads();
+  if (threadIdx.x == 0) {
+    SmemBitSrc src{S.sw, nBits};
+    canon_fast_parse_header(S, src, startBit);
+  }
+  __syncthreads();
+  if (S.error) return false;
+  canon_fast_build_lut(S);
+  return canon_fast_decode_text(S, nBits, S.textStart, maxValues, hintBits, sink, endBit, nValues);
+}
+
+}  // namespace g4

@@ -114,7 +114,11 @@ cudaError_t launch_deflate_decode(const DecodeArgs& a, uint8_t* region, size_t r
 cudaError_t launch_float_decode(const DecodeArgs& a, uint8_t* region, size_t regionStride, int nCtas, int nTilesUpper,
                                 cudaStream_t s);
 // coef: [nTiles][12] floats of device scratch; nTilesUpper bounds the number of LSOP tiles in the list
-cudaError_t launch_lsop_decode(const DecodeArgs& a, float* coef, int nCtas, int nTilesUpper, cudaStream_t s);
+// defer: nTilesUpper ints; deferCounters: 2 zeroed ints (deferred-tile count, work counter of the general kernel)
+// meta: nTilesUpper * lsop_meta_bytes() bytes (interior code lengths + text position handed from kernel H to kernel T)
+size_t lsop_meta_bytes();
+cudaError_t launch_lsop_decode(const DecodeArgs& a, float* coef, uint8_t* meta, int* defer, int* deferCounters, int nCtas,
+                               int nTilesUpper, cudaStream_t s);
 
 
 // ---- zlib-stream encode stages (g4_deflate_encode.cu, g4_lsop.cu) ------------------------------------------------

@@ -15,6 +15,7 @@
 #include "g4_predict.cuh"
 #include "g4_huffdec.cuh"
 #include "g4_canon.cuh"
+#include "g4_canon_fast.cuh"
 #include "g4_canon_enc.cuh"
 #include "g4_inflate.cuh"
 #include "g4_m32stream.cuh"
@@ -29,17 +30,18 @@ union LsopDecShared {
   InflateWarpShared inf;
 };
 
-// StrictMath.round(float): floor(a + 1/2) evaluated on the bit pattern (java.lang.Math.round(float), JDK >= 8)
+// StrictMath.round(float): floor(a + 1/2) evaluated on the bit pattern (java.lang.Math.round(float), JDK >= 8):
+//   shift = 149 - biasedExp;  0 <= shift < 32 ? ((+-significand >> shift) + 1) >> 1 : (int) a
+// For shift >= 32 (|a| < 2^-9) the cast gives 0, and so does the shifted form with the shift clamped to 31
+// (the 24-bit significand shifts out completely: (0 + 1) >> 1 == 0, (-1 + 1) >> 1 == 0), which leaves one rare
+// branch for shift < 0 (|a| >= 2^24, infinities, NaN: saturating cast, NaN -> 0).
 __device__ __forceinline__ int32_t java_round(float a) {
-  int32_t bits = __float_as_int(a);
-  int biasedExp = (bits & 0x7F800000) >> 23;
-  int shift = (24 - 2 + 127) - biasedExp;
-  if ((shift & -32) == 0) {
-    int32_t r = (bits & 0x007FFFFF) | 0x00800000;
-    if (bits < 0) r = -r;
-    return ((r >> shift) + 1) >> 1;
-  }
-  return __float2int_rz(a);  // (int) a: saturating, NaN -> 0
+  const int32_t bits = __float_as_int(a);
+  const int shift = 149 - ((bits >> 23) & 0xff);
+  if (shift < 0) return __float2int_rz(a);
+  int32_t r = (bits & 0x007FFFFF) | 0x00800000;
+  r = bits < 0 ? -r : r;
+  return ((r >> min(shift, 31)) + 1) >> 1;
 }
 
 struct LsHeaderInfo {
@@ -107,7 +109,362 @@ struct CellSink {
   }
 };
 
+// Run sinks for canon_fast_decode_stream: begin(first value index), put(value) ..., end().
+struct CellRunSink {  // any stream order, one stream_to_cell per value (initializers: ~1200 values per tile)
+  TileView t;
+  int order;
+  uint32_t k;
+  __device__ __forceinline__ void begin(uint32_t k0) { k = k0; }
+  __device__ __forceinline__ void put(int32_t v) {
+    int r, c;
+    stream_to_cell(order, int(k++), t.R, t.C, &r, &c);
+    t.at(r, c) = v;
+  }
+  __device__ __forceinline__ void end() {}
+};
+struct InteriorRunSink {  // LSOP12 interior order: rows 2.., columns 2..C-3 row-major; running cell address, no division per value
+  TileView t;
+  int32_t* p;  // column 2 of the current row
+  int c, w;
+  __device__ __forceinline__ void begin(uint32_t k0) {
+    w = t.C - 4;
+    int rr = int(k0) / w;
+    c = int(k0) - rr * w;
+    p = t.row(2 + rr) + 2;
+  }
+  __device__ __forceinline__ void put(int32_t v) {
+    p[c] = v;
+    if (++c == w) { c = 0; p += t.pitch; }
+  }
+  __device__ __forceinline__ void end() {}
+};
+
 }  // namespace
+
+// LsDecoder12.unpackInitializers (:204-241): row 0 and column 0 by differencing, row 1 and column 1 by Triangle.
+// Precondition: every initializer cell holds its residual.  All threads call.
+__device__ inline void lsop_init_scans(const TileView& t, int32_t seed) {
+  __shared__ uint32_t scan[kWarps + 1];
+  const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+  const int R = t.R, C = t.C;
+  __syncthreads();
+  if (tid == 0) t.at(0, 0) = seed;
+  __syncthreads();
+  if (warp == 0) row_scan_warp(t.row(0), C, 0);
+  column0_scan(t, scan);  // ends with __syncthreads
+  if (warp == 0) {
+    // row 1: T[c] = v[1][c] - v[0][c];  T[c] = T[c-1] + residual(1,c)
+    uint32_t carry = uint32_t(t.at(1, 0)) - uint32_t(t.at(0, 0));
+    for (int c0 = 1; c0 < C; c0 += 32) {
+      int c = c0 + lane;
+      uint32_t x = c < C ? uint32_t(t.at(1, c)) : 0u;
+      uint32_t inc = warp_inclusive_scan(x);
+      if (c < C) t.at(1, c) = int32_t(carry + inc + uint32_t(t.at(0, c)));
+      carry += __shfl_sync(0xffffffffu, inc, 31);
+    }
+  }
+  __syncthreads();
+  {
+    // column 1, rows 2..: U[r] = v[r][1] - v[r][0];  U[r] = U[r-1] + residual(r,1)
+    uint32_t carry = uint32_t(t.at(1, 1)) - uint32_t(t.at(1, 0));
+    for (int r0 = 2; r0 < R; r0 += kThreads) {
+      int r = r0 + tid;
+      uint32_t x = r < R ? uint32_t(t.at(r, 1)) : 0u;
+      uint32_t tot;
+      uint32_t ex = block_exclusive_scan(x, scan, &tot);
+      if (r < R) t.at(r, 1) = int32_t(carry + ex + x + uint32_t(t.at(r, 0)));
+      carry += tot;
+    }
+  }
+}
+
+// ---- kernel A, fast path: canonical-Huffman packings (type 2) ------------------------------------------------------
+// Two kernels, so that no CTA ever waits on a serial table parse:
+//   H  one WARP per tile: LSOP header, both canonical code tables, the short initializer stream (decoded serially
+//      by lane 0 -- ~1200 values -- while the other warps of the SM work on their own tiles), rows 0,1 / columns 0,1 by
+//      warp scans.  Exports the interior stream's 260 code lengths and text position to `meta`.
+//   T  one CTA per tile: the interior text (the bulk of the bits) with the staged sub-sequence decoder of
+//      g4_canon_fast.cuh; no serial section.
+// Legacy-Huffman, Deflate, oversized or unaligned packings are appended to `defer` for the general kernel below.
+constexpr int kLsopMetaBytes = 272;  // [0..3] interior text start (absolute bit, 0 = tile not on the fast path), [8..267] lengths
+
+struct CanonWarpShared {
+  uint8_t lens[kCanonSymbols + 4];
+  uint16_t sorted[kCanonSymbols];
+  uint16_t firstCode[17], count[17], offset[17];
+  uint16_t ctFirst[17], ctCount[17], ctOffset[17], ctSorted[20];
+  uint16_t lut8[256];   // text code: sym | len << 9 | special; 0 = longer than 8 bits
+  uint16_t ctLut[256];  // code-table code: sym | len << 8
+  uint32_t cnt32[17], next[17];
+  uint32_t textStart;
+  int error;
+};
+
+// Warp-cooperative version of canon_fast_parse_header over a global-memory bit source.  All 32 lanes call.
+__device__ inline void canon_warp_parse_header(CanonWarpShared& W, const BitSrc& src, uint32_t startBit) {
+  const int lane = threadIdx.x & 31;
+  __syncwarp();
+  if (lane == 0) {
+    W.error = 0;
+    uint32_t pos = startBit + 1;  // reserved bit
+    int k = 0, prior = 0;
+    while (k < 20 && !W.error) {
+      if (pos + 5 > src.nBits) { W.error = 1; break; }
+      int index = int(src.bits(pos, 5));
+      pos += 5;
+      int n = 1, val = index;
+      if (index <= 15) prior = index;
+      else if (index == 16) { n = int(src.bits(pos, 2)) + 3; pos += 2; val = prior; }
+      else if (index == 17) { n = int(src.bits(pos, 3)) + 3; pos += 3; val = 0; prior = 0; }
+      else if (index == 18) { n = int(src.bits(pos, 7)) + 11; pos += 7; val = 0; prior = 0; }
+      else continue;  // reference ignores other values
+      if (k + n > 20) { W.error = 1; break; }
+      for (int i = 0; i < n; i++) W.lens[k++] = uint8_t(val);
+    }
+    if (!W.error && !canon_build_tables(W.lens, 20, W.ctFirst, W.ctCount, W.ctOffset, W.ctSorted)) W.error = 1;
+    W.textStart = pos;
+  }
+  __syncwarp();
+  if (W.error) return;
+  for (int e = lane; e < 256; e += 32) {  // 8-bit LUT of the code-table code
+    uint32_t v = __brev(uint32_t(e));
+    uint16_t entry = 0;
+    for (int len = 1; len <= 8; len++) {
+      uint32_t d = (v >> (32 - len)) - W.ctFirst[len];
+      if (d < W.ctCount[len]) { entry = uint16_t(W.ctSorted[W.ctOffset[len] + d] | (len << 8)); break; }
+    }
+    W.ctLut[e] = entry;
+  }
+  __syncwarp();
+  if (lane == 0) {  // the 260 text code lengths: serial by nature (variable-length codes)
+    uint32_t pos = W.textStart;
+    int prior = 0;
+    for (int i = 0; i < kCanonSymbols; i++) W.lens[i] = 0;
+    for (int i = 0; i < kCanonSymbols; i++) {
+      if (pos >= src.nBits) { W.error = 1; break; }
+      int test;
+      uint32_t e = W.ctLut[src.peek32(pos) & 0xffu];
+      if (e) { test = int(e & 0xffu); pos += e >> 8; }
+      else test = canon_slow_symbol(W.ctFirst, W.ctCount, W.ctOffset, W.ctSorted, src, &pos, 9);
+      if (test < 0) { W.error = 1; break; }
+      if (test <= 15) { W.lens[i] = uint8_t(test); prior = test; }
+      else {
+        int n, val = 0;
+        if (test == 16) { n = int(src.bits(pos, 2)) + 3; pos += 2; val = prior; }
+        else if (test == 17) { n = int(src.bits(pos, 3)) + 3; pos += 3; prior = 0; }
+        else if (test == 18) { n = int(src.bits(pos, 7)) + 11; pos += 7; prior = 0; }
+        else continue;  // the code table's own end-of-text symbol: leaves a zero length
+        if (i + n > kCanonSymbols) { W.error = 1; break; }
+        for (int j = 0; j < n; j++) W.lens[i + j] = uint8_t(val);
+        i += n - 1;
+      }
+    }
+    if (W.lens[kSymEot] == 0) W.error = 1;
+    W.textStart = pos;
+  }
+  if (lane < 17) W.cnt32[lane] = 0;
+  __syncwarp();
+  if (W.error) return;
+  // tables of the text code, in parallel
+  for (int i = lane; i < kCanonSymbols; i += 32) {
+    int l = W.lens[i];
+    if (l) atomicAdd(&W.cnt32[l], 1u);
+  }
+  __syncwarp();
+  if (lane == 0) {
+    uint32_t code = 0, off = 0;
+    W.count[0] = 0; W.firstCode[0] = 0; W.offset[0] = 0; W.next[0] = 0;
+    W.count[16] = 0; W.firstCode[16] = 0; W.offset[16] = 0; W.next[16] = 0;
+    for (int l = 1; l <= 15; l++) {
+      uint32_t c = W.cnt32[l];
+      W.firstCode[l] = uint16_t(code);
+      W.offset[l] = uint16_t(off);
+      W.count[l] = uint16_t(c);
+      W.next[l] = off;
+      if (code + c > (1u << l)) W.error = 1;  // over-subscribed
+      code = (code + c) << 1;
+      off += c;
+    }
+  }
+  __syncwarp();
+  if (W.error) return;
+  for (int i0 = 0; i0 < kCanonSymbols; i0 += 32) {  // sorted[]: symbols by (length, symbol)
+    const int i = i0 + lane;
+    const int l = i < kCanonSymbols ? W.lens[i] : 0;
+    const uint32_t same = __match_any_sync(0xffffffffu, l);
+    if (l) {
+      const uint32_t rank = __popc(same & ((1u << lane) - 1u));
+      W.sorted[W.next[l] + rank] = uint16_t(i);
+    }
+    __syncwarp();
+    if (l && (same & ((1u << lane) - 1u)) == 0) W.next[l] += __popc(same);
+    __syncwarp();
+  }
+  for (int e = lane; e < 256; e += 32) {  // 8-bit LUT of the text code
+    uint32_t v = __brev(uint32_t(e));
+    uint16_t entry = 0;
+    for (int len = 1; len <= 8; len++) {
+      uint32_t d = (v >> (32 - len)) - W.firstCode[len];
+      if (d < W.count[len]) {
+        uint32_t sym = W.sorted[W.offset[len] + d];
+        entry = uint16_t(sym | (uint32_t(len) << 9) | (sym >= 256 ? kFastSpecial : 0u));
+        break;
+      }
+    }
+    W.lut8[e] = entry;
+  }
+  __syncwarp();
+}
+
+// Column scan by one warp: cell (r0-1, c) holds a final value, cells (r, c) r >= r0 hold d[r]; after the call
+// v[r][c] = base[r] + (carry0 + d[r0] + ... + d[r]) with base[r] = v[r][c-1] when addLeft, else 0.
+__device__ inline void lsop_warp_column_scan(const TileView& t, int col, int r0, uint32_t carry, bool addLeft) {
+  const int lane = threadIdx.x & 31;
+  for (int rb = r0; rb < t.R; rb += 32) {
+    const int r = rb + lane;
+    uint32_t x = r < t.R ? uint32_t(t.at(r, col)) : 0u;
+    uint32_t inc = warp_inclusive_scan(x);
+    if (r < t.R) t.at(r, col) = int32_t(carry + inc + (addLeft ? uint32_t(t.at(r, col - 1)) : 0u));
+    carry += __shfl_sync(0xffffffffu, inc, 31);
+  }
+  __syncwarp();
+}
+
+__global__ void __launch_bounds__(kThreads) lsop_decode_head_kernel(DecodeArgs a, float* coefOut, uint8_t* meta, int* defer,
+                                                                    int* deferCount) {
+  __shared__ CanonWarpShared WS[kWarps];
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  CanonWarpShared& W = WS[warp];
+  const int li = blockIdx.x * kWarps + warp;
+  if (li >= *a.listCount) return;
+  const int tIdx = a.list[li];
+  uint8_t* m = meta + size_t(tIdx) * kLsopMetaBytes;
+  if (lane == 0) *reinterpret_cast<uint32_t*>(m) = 0;
+  const TileView t = tile_view(a.band, a.grid, tIdx);
+  const int R = t.R, C = t.C;
+  const uint8_t* packing = a.arena + a.offsets[tIdx];
+  const uint32_t len = a.lens[tIdx];
+  LsHeaderInfo h = parse_ls_header(packing, len, coefOut + size_t(tIdx) * 12, lane == 0);
+  if (!h.ok || R < 6 || C < 6) {
+    if (lane == 0) a.status[tIdx] = G4_ERR_FORMAT;
+    return;
+  }
+  if (h.type != 2 || len > uint32_t(kFastStageWords) * 4u || (reinterpret_cast<uintptr_t>(packing) & 3) != 0) {
+    if (lane == 0) defer[atomicAdd(deferCount, 1)] = tIdx;
+    return;
+  }
+  const uint32_t nInit = uint32_t(4 * R + 2 * C - 9);
+  BitSrc src;
+  src.init(packing, len);  // absolute bit positions inside the packing
+  canon_warp_parse_header(W, src, h.headerSize * 8u);
+  int status = W.error ? G4_ERR_FORMAT : G4_OK;
+  uint32_t endBit = 0;
+  if (status == G4_OK) {
+    // initializer text, serially by lane 0 (CanonicalHuffman.decodeText :469-519): values go straight to their cells
+    if (lane == 0) {
+      uint32_t pos = W.textStart, k = 0, v = 0;
+      bool have = false, bad = false;
+      for (;;) {
+        if (pos >= src.nBits) { bad = true; break; }
+        uint32_t e = W.lut8[src.peek32(pos) & 0xffu];
+        int sym;
+        if (e) { sym = int(e & 0x1ffu); pos += (e >> 9) & 15u; }
+        else {
+          sym = canon_slow_symbol(W.firstCode, W.count, W.offset, W.sorted, src, &pos, 9);
+          if (sym < 0) { bad = true; break; }
+        }
+        if (sym == kSymEsc2 || sym == kSymEsc8) {
+          if (!have) { bad = true; break; }
+          const int nb = sym == kSymEsc2 ? 2 : 8;
+          v = (v << nb) | src.bits(pos, nb);
+          pos += nb;
+          continue;
+        }
+        if (have) {
+          if (k >= nInit) { bad = true; break; }
+          int r, c;
+          stream_to_cell(kStreamLsopInit, int(k++), R, C, &r, &c);
+          t.at(r, c) = int32_t(v);
+          have = false;
+        }
+        if (sym == kSymEot) break;
+        have = true;
+        v = sym == kSymNull ? uint32_t(INT32_MIN) : uint32_t(sym - 128);
+      }
+      if (bad || k != nInit) W.error = 1;
+      W.textStart = pos;
+    }
+    __syncwarp();
+    if (W.error) status = G4_ERR_FORMAT;
+    endBit = W.textStart;
+  }
+  if (status == G4_OK) {
+    canon_warp_parse_header(W, src, endBit);  // interior stream: tables only, exported for kernel T
+    if (W.error) status = G4_ERR_FORMAT;
+    else {
+      for (int i = lane; i < kCanonSymbols; i += 32) m[8 + i] = W.lens[i];
+      if (lane == 0) *reinterpret_cast<uint32_t*>(m) = W.textStart;
+    }
+  }
+  if (status == G4_OK) {
+    // LsDecoder12.unpackInitializers (:204-241): row 0 and column 0 by differencing, row 1 and column 1 by Triangle
+    if (lane == 0) t.at(0, 0) = h.seed;
+    __syncwarp();
+    row_scan_warp(t.row(0), C, 0);
+    __syncwarp();
+    lsop_warp_column_scan(t, 0, 1, uint32_t(h.seed), false);
+    {
+      // row 1: T[c] = v[1][c] - v[0][c];  T[c] = T[c-1] + residual(1,c)
+      uint32_t carry = uint32_t(t.at(1, 0)) - uint32_t(t.at(0, 0));
+      for (int c0 = 1; c0 < C; c0 += 32) {
+        int c = c0 + lane;
+        uint32_t x = c < C ? uint32_t(t.at(1, c)) : 0u;
+        uint32_t inc = warp_inclusive_scan(x);
+        if (c < C) t.at(1, c) = int32_t(carry + inc + uint32_t(t.at(0, c)));
+        carry += __shfl_sync(0xffffffffu, inc, 31);
+      }
+    }
+    __syncwarp();
+    // column 1, rows 2..: U[r] = v[r][1] - v[r][0];  U[r] = U[r-1] + residual(r,1)
+    lsop_warp_column_scan(t, 1, 2, uint32_t(t.at(1, 1)) - uint32_t(t.at(1, 0)), true);
+  }
+  if (lane == 0) a.status[tIdx] = status;
+}
+
+__global__ void __launch_bounds__(kThreads, 4) lsop_decode_text_kernel(DecodeArgs a, const uint8_t* meta) {
+  extern __shared__ __align__(16) unsigned char lsopFastSmem[];
+  CanonFastShared& F = *reinterpret_cast<CanonFastShared*>(lsopFastSmem);
+  __shared__ int sTile;
+  const int tid = threadIdx.x;
+  for (;;) {
+    __syncthreads();
+    if (tid == 0) sTile = atomicAdd(a.counter, 1);
+    __syncthreads();
+    const int li = sTile;
+    if (li >= *a.listCount) break;
+    const int tIdx = a.list[li];
+    const uint8_t* m = meta + size_t(tIdx) * kLsopMetaBytes;
+    const uint32_t T0 = *reinterpret_cast<const uint32_t*>(m);
+    if (T0 == 0) continue;  // deferred or rejected by kernel H
+    const TileView t = tile_view(a.band, a.grid, tIdx);
+    const uint8_t* packing = a.arena + a.offsets[tIdx];
+    const uint32_t len = a.lens[tIdx];
+    const uint32_t nInterior = uint32_t(t.R - 2) * uint32_t(t.C - 4);
+    canon_fast_stage(F, packing, len);
+    for (int i = tid; i < kCanonSymbols; i += kThreads) F.lens[i] = m[8 + i];
+    if (tid == 0) F.error = 0;
+    __syncthreads();
+    canon_fast_tables_cta(F);
+    bool ok = F.error == 0;
+    if (ok) {
+      canon_fast_build_lut(F);
+      uint32_t endBit = 0, nv = 0;
+      InteriorRunSink s2{t, nullptr, 0, 0};
+      ok = canon_fast_decode_text(F, len * 8u, T0, nInterior, 0u, s2, &endBit, &nv) && nv == nInterior;
+    }
+    if (!ok && tid == 0) a.status[tIdx] = G4_ERR_FORMAT;
+  }
+}
 
 // ---- kernel A ----------------------------------------------------------------------------------------
 __global__ void __launch_bounds__(kThreads) lsop_decode_entropy_kernel(DecodeArgs a, float* coefOut) {
@@ -173,45 +530,14 @@ __global__ void __launch_bounds__(kThreads) lsop_decode_entropy_kernel(DecodeArg
           if (!entropyOk) status = G4_ERR_FORMAT;
           else {
             __syncthreads();
-            if (!m32_parse_to_cells(m32a, h.nInitCodes, kStreamLsopInit, t, nInit, S.h.scan)) status = G4_ERR_FORMAT;
-            else if (!m32_parse_to_cells(m32b, h.nInteriorCodes, kStreamLsopInterior, t, nInterior, S.h.scan)) status = G4_ERR_FORMAT;
+            __shared__ uint32_t scanM[kWarps + 1];
+            if (!m32_parse_to_cells(m32a, h.nInitCodes, kStreamLsopInit, t, nInit, scanM)) status = G4_ERR_FORMAT;
+            else if (!m32_parse_to_cells(m32b, h.nInteriorCodes, kStreamLsopInterior, t, nInterior, scanM)) status = G4_ERR_FORMAT;
           }
         }
       }
     }
-    if (status == G4_OK) {
-      // LsDecoder12.unpackInitializers (:204-241): row 0 and column 0 by differencing, row 1 and column 1 by Triangle
-      __syncthreads();
-      if (tid == 0) t.at(0, 0) = h.seed;
-      __syncthreads();
-      uint32_t* scan = S.h.scan;
-      if (warp == 0) row_scan_warp(t.row(0), C, 0);
-      column0_scan(t, scan);  // ends with __syncthreads
-      if (warp == 0) {
-        // row 1: T[c] = v[1][c] - v[0][c];  T[c] = T[c-1] + residual(1,c)
-        uint32_t carry = uint32_t(t.at(1, 0)) - uint32_t(t.at(0, 0));
-        for (int c0 = 1; c0 < C; c0 += 32) {
-          int c = c0 + lane;
-          uint32_t x = c < C ? uint32_t(t.at(1, c)) : 0u;
-          uint32_t inc = warp_inclusive_scan(x);
-          if (c < C) t.at(1, c) = int32_t(carry + inc + uint32_t(t.at(0, c)));
-          carry += __shfl_sync(0xffffffffu, inc, 31);
-        }
-      }
-      __syncthreads();
-      {
-        // column 1, rows 2..: U[r] = v[r][1] - v[r][0];  U[r] = U[r-1] + residual(r,1)
-        uint32_t carry = uint32_t(t.at(1, 1)) - uint32_t(t.at(1, 0));
-        for (int r0 = 2; r0 < R; r0 += kThreads) {
-          int r = r0 + tid;
-          uint32_t x = r < R ? uint32_t(t.at(r, 1)) : 0u;
-          uint32_t tot;
-          uint32_t ex = block_exclusive_scan(x, scan, &tot);
-          if (r < R) t.at(r, 1) = int32_t(carry + ex + x + uint32_t(t.at(r, 0)));
-          carry += tot;
-        }
-      }
-    }
+    if (status == G4_OK) lsop_init_scans(t, h.seed);
     __syncthreads();
     if (tid == 0) a.status[tIdx] = status;
   }
@@ -297,6 +623,108 @@ __global__ void __launch_bounds__(kThreads) lsop_wavefront_kernel(DecodeArgs a, 
     }
     __syncwarp();
     __threadfence_block();
+  }
+}
+
+// ---- kernel B, vectorised: 4-column skew, int4 traffic, row groups pipelined back to back -----------------------------
+// Same recurrence and operation order as lsop_wavefront_kernel; used when every tile row is 16-byte aligned
+// (tile_cols % 4 == 0, grid_pitch % 4 == 0, aligned base).  Lane l owns rows 2+l, 34+l, ... and runs ONE 4-column
+// block behind lane l-1, so all lanes are at the same column phase: residuals are read and values written as int4.
+// Row r-1 at column c+2 is lane l-1's output of two steps ago (shuffle of its float history f2); row r-2 at column
+// c+2 is the oldest element lane l-1 still holds of ITS row above (shuffle of av[j]).  Lane 0 (and lane 1 for r-2)
+// read the rows of the previous 32-row group from L2; a row takes P = max(C,132) steps so that lane 31 of the previous
+// group is always at least two blocks ahead of lane 0 of the next one and the groups need no drain between them.
+__global__ void __launch_bounds__(kThreads) lsop_wavefront4_kernel(DecodeArgs a, const float* coef) {
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  const int li = blockIdx.x * kWarps + warp;
+  if (li >= *a.listCount) return;
+  const int tIdx = a.list[li];
+  if (a.status[tIdx] != G4_OK) return;
+  const TileView t = tile_view(a.band, a.grid, tIdx);
+  const int R = t.R, C = t.C;
+  float u[12];
+#pragma unroll
+  for (int i = 0; i < 12; i++) u[i] = coef[size_t(tIdx) * 12 + i];
+  const int P = C > 132 ? C : 132;
+  const int nB = P >> 2, cBlocks = C >> 2;
+  const int nGroups = (R - 2 + 31) >> 5;
+  const int nIter = nGroups * nB + 31;
+  float av[8], bv[8];  // rows r-1 / r-2 as float, columns c0-2 .. c0+5
+#pragma unroll
+  for (int i = 0; i < 8; i++) { av[i] = 0.f; bv[i] = 0.f; }
+  float f1 = 0.f, f2 = 0.f;  // own row, columns c-1 and c-2
+  int32_t h1 = 0;            // own row, column c-1 (integer, for the two Triangle columns)
+  int cb = -lane, r = 2 + lane;
+  for (int it = 0; it < nIter; it++) {
+    const bool act = cb >= 0 && cb < cBlocks && r < R;
+    const int c0 = cb << 2;
+    int32_t* rowp = t.row(act ? r : 2);
+    int4 v = make_int4(0, 0, 0, 0);
+    if (act) v = *reinterpret_cast<const int4*>(rowp + c0);  // residuals (columns >= 2) or final values (columns 0,1)
+#pragma unroll
+    for (int i = 0; i < 4; i++) { av[i] = av[i + 4]; bv[i] = bv[i + 4]; }
+    if (act && cb == 0) {  // row start: columns 0,1 of the two rows above (final since kernel A)
+      int2 p1 = __ldcg(reinterpret_cast<const int2*>(rowp - t.pitch));
+      int2 p2 = __ldcg(reinterpret_cast<const int2*>(rowp - 2 * t.pitch));
+      av[2] = float(p1.x); av[3] = float(p1.y);
+      bv[2] = float(p2.x); bv[3] = float(p2.y);
+    }
+    float m1[4] = {0.f, 0.f, 0.f, 0.f}, m2[4] = {0.f, 0.f, 0.f, 0.f};
+    if (lane < 2 && act) {  // rows written by the previous row group (or rows 0,1): columns c0+2 .. c0+5 from L2
+      const int32_t* q2 = rowp - 2 * t.pitch + c0 + 2;
+      int2 x = __ldcg(reinterpret_cast<const int2*>(q2));
+      m2[0] = float(x.x); m2[1] = float(x.y);
+      if (c0 + 4 < C) { int2 y = __ldcg(reinterpret_cast<const int2*>(q2 + 2)); m2[2] = float(y.x); m2[3] = float(y.y); }
+      if (lane == 0) {
+        const int32_t* q1 = rowp - t.pitch + c0 + 2;
+        int2 x1 = __ldcg(reinterpret_cast<const int2*>(q1));
+        m1[0] = float(x1.x); m1[1] = float(x1.y);
+        if (c0 + 4 < C) { int2 y1 = __ldcg(reinterpret_cast<const int2*>(q1 + 2)); m1[2] = float(y1.x); m1[3] = float(y1.y); }
+      }
+    }
+    int4 up = make_int4(0, 0, 0, 0);
+    if (act && cb == cBlocks - 1) up = __ldcg(reinterpret_cast<const int4*>(rowp - t.pitch + c0));  // Triangle columns
+    int32_t out[4];
+#pragma unroll
+    for (int j = 0; j < 4; j++) {
+      float ra = __shfl_up_sync(0xffffffffu, f2, 1);
+      float rb = __shfl_up_sync(0xffffffffu, av[j], 1);
+      if (lane == 0) ra = m1[j];
+      if (lane < 2) rb = m2[j];
+      av[4 + j] = ra;
+      bv[4 + j] = rb;
+      const int32_t res = j == 0 ? v.x : j == 1 ? v.y : j == 2 ? v.z : v.w;
+      // LsDecoder12.java:424-438 -- evaluated left to right in float32, no fused multiply-add.  Computed for every
+      // column and discarded (select, no branch) for columns 0,1 and the two Triangle columns.
+      float p = u[0] * f1;
+      p = p + u[1] * av[j + 1];
+      p = p + u[2] * av[j + 2];
+      p = p + u[3] * av[j + 3];
+      p = p + u[4] * av[j + 4];
+      p = p + u[5] * f2;
+      p = p + u[6] * av[j];
+      p = p + u[7] * bv[j];
+      p = p + u[8] * bv[j + 1];
+      p = p + u[9] * bv[j + 2];
+      p = p + u[10] * bv[j + 3];
+      p = p + u[11] * bv[j + 4];
+      uint32_t add = uint32_t(java_round(p));
+      if (j < 2) {
+        if (cb == 0) add = 0u;  // columns 0,1 hold their final values already
+      } else {
+        // last two columns: Triangle predictor (LsDecoder12.java:459-468); tile_cols % 4 == 0 puts them at j = 2,3
+        const int32_t upc = j == 2 ? up.z : up.w, upl = j == 2 ? up.y : up.z;
+        if (cb == cBlocks - 1) add = (uint32_t(h1) + uint32_t(upc)) - uint32_t(upl);
+      }
+      const int32_t val = int32_t(uint32_t(res) + add);
+      out[j] = val;
+      h1 = val;
+      f2 = f1;
+      f1 = float(val);
+    }
+    if (act) *reinterpret_cast<int4*>(rowp + c0) = make_int4(out[0], out[1], out[2], out[3]);
+    if (++cb == nB) { cb = 0; r += 32; }
+    __syncwarp();
   }
 }
 
@@ -653,11 +1081,35 @@ cudaError_t launch_lsop_encode(const EncodeArgs& a, int nCtas, cudaStream_t s) {
   return cudaGetLastError();
 }
 
-cudaError_t launch_lsop_decode(const DecodeArgs& a, float* coef, int nCtas, int nTilesUpper, cudaStream_t s) {
-  lsop_decode_entropy_kernel<<<nCtas, kThreads, 0, s>>>(a, coef);
+size_t lsop_meta_bytes() { return kLsopMetaBytes; }
+
+cudaError_t launch_lsop_decode(const DecodeArgs& a, float* coef, uint8_t* meta, int* defer, int* deferCounters, int nCtas,
+                               int nTilesUpper, cudaStream_t s) {
+  static bool attr = false;
+  if (!attr) {
+    cudaError_t ea = cudaFuncSetAttribute(lsop_decode_text_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                          int(sizeof(CanonFastShared)));
+    if (ea != cudaSuccess) return ea;
+    attr = true;
+  }
+  // deferCounters[0] = number of deferred tiles (filled by kernel H), [1] = work counter of the general kernel
+  lsop_decode_head_kernel<<<(nTilesUpper + kWarps - 1) / kWarps, kThreads, 0, s>>>(a, coef, meta, defer, deferCounters);
   cudaError_t e = cudaGetLastError();
   if (e != cudaSuccess) return e;
-  lsop_wavefront_kernel<<<(nTilesUpper + kWarps - 1) / kWarps, kThreads, 0, s>>>(a, coef);
+  lsop_decode_text_kernel<<<nCtas, kThreads, sizeof(CanonFastShared), s>>>(a, meta);
+  e = cudaGetLastError();
+  if (e != cudaSuccess) return e;
+  DecodeArgs d = a;
+  d.list = defer;
+  d.listCount = deferCounters;
+  d.counter = deferCounters + 1;
+  lsop_decode_entropy_kernel<<<nCtas < 296 ? nCtas : 296, kThreads, 0, s>>>(d, coef);
+  e = cudaGetLastError();
+  if (e != cudaSuccess) return e;
+  const bool aligned = (a.band.tile_cols % 4) == 0 && (a.band.grid_pitch % 4) == 0 && a.band.tile_cols >= 8 &&
+                       (reinterpret_cast<uintptr_t>(a.grid) & 15) == 0;
+  if (aligned) lsop_wavefront4_kernel<<<(nTilesUpper + kWarps - 1) / kWarps, kThreads, 0, s>>>(a, coef);
+  else lsop_wavefront_kernel<<<(nTilesUpper + kWarps - 1) / kWarps, kThreads, 0, s>>>(a, coef);
   return cudaGetLastError();
 }
 
