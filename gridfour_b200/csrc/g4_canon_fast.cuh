@@ -18,25 +18,28 @@
 
 namespace g4 {
 
-constexpr int kFastStageWords = 8192;  // 32 KB of packing
-constexpr int kFastMaxSub = 1536;
-constexpr int kFastSubPerThread = kFastMaxSub / kThreads;
+constexpr int kFastStageWords = 7168;  // 28 KB of packing (5.3 bits/sample for a 180x240 tile)
+constexpr int kFastMaxSub = 1280;
+constexpr int kFastRounds = kFastMaxSub / kThreads;
+constexpr uint32_t kFastSubBits = 160;   // target sub-sequence size
+constexpr uint32_t kFastLookback = 48;   // pass 0 starts this many bits before the limit
 constexpr int kFastLutBits = 11;
 constexpr uint32_t kFastSpecial = 0x8000u;  // LUT flag: symbol >= 256 (null, escapes, end of text)
 
 struct CanonFastShared {
   uint32_t sw[kFastStageWords + 8];   // staged packing; word 0 = packing bytes 0..3
+  uint32_t mlut[1 << kFastLutBits];   // up to 3 plain values per lookup: s1 | s2 << 8 | s3 << 16 | bits << 24 | n << 28
   uint16_t lut[1 << kFastLutBits];    // sym | len << 9 | special; 0 = code longer than the LUT
   uint16_t sorted[kCanonSymbols];
   uint16_t firstCode[17], count[17], offset[17];
   uint8_t lens[kCanonSymbols + 4];
   uint16_t ctLut[256];                // code-table code: sym | len << 8; 0 = longer than 8 bits
   uint32_t endpos[kFastMaxSub];
-  uint32_t off[kFastMaxSub];
+  uint32_t startv[kFastMaxSub];       // start position endpos[i] was computed from
   uint16_t cnt[kFastMaxSub];
   uint8_t eot[kFastMaxSub];
   uint32_t scan[kWarps + 1];
-  uint32_t textStart;
+  uint32_t textStart, endBit;
   int error, changed, firstEot;
 };
 
@@ -54,27 +57,26 @@ struct SmemBitSrc {
   }
 };
 
-// 64-bit register bit buffer; at least 32 valid bits after every skip().
+// 64-bit register bit buffer over S.sw; at least 32 valid bits after every skip().  The staged words are addressed
+// through the shared-memory struct itself so that the loads stay LDS with an immediate base.
 struct BitCursor {
-  const uint32_t* w;
   uint32_t pos, next;
   uint64_t buf;
   int avail;
-  __device__ __forceinline__ void init(const uint32_t* words, uint32_t p) {
-    w = words;
+  __device__ __forceinline__ void init(const CanonFastShared& S, uint32_t p) {
     pos = p;
     uint32_t i = p >> 5, s = p & 31;
-    buf = ((uint64_t(w[i + 1]) << 32) | w[i]) >> s;
+    buf = ((uint64_t(S.sw[i + 1]) << 32) | S.sw[i]) >> s;
     avail = 64 - int(s);
     next = i + 2;
   }
   __device__ __forceinline__ uint32_t peek() const { return uint32_t(buf); }
-  __device__ __forceinline__ void skip(int n) {
+  __device__ __forceinline__ void skip(const CanonFastShared& S, uint32_t n) {
     buf >>= n;
-    avail -= n;
-    pos += uint32_t(n);
+    avail -= int(n);
+    pos += n;
     if (avail < 32) {
-      buf |= uint64_t(w[next++]) << avail;
+      buf |= uint64_t(S.sw[next++]) << avail;
       avail += 32;
     }
   }
@@ -151,49 +153,58 @@ __device__ inline void canon_fast_parse_header(CanonFastShared& S, const SmemBit
   S.textStart = pos;
 }
 
-// One symbol at the cursor: returns the LUT-style entry (sym | special flag) and advances past the code.
-// Returns -1 for an invalid code.
-__device__ __forceinline__ int canon_fast_symbol(const CanonFastShared& S, BitCursor& cur, uint32_t nBits) {
-  uint32_t e = S.lut[cur.peek() & ((1u << kFastLutBits) - 1u)];
+// The uncommon symbols: special symbols (null, escapes, end of text) and codes longer than the LUT.  `e` is the LUT
+// entry read at position p0.  Returns the symbol (0..259) and the position after its code, or -1 for an invalid code.
+__device__ __forceinline__ int canon_fast_rare_symbol(const CanonFastShared& S, uint32_t e, uint32_t p0, uint32_t nBits, uint32_t* after) {
   if (e) {
-    cur.skip(int((e >> 9) & 15u));
-    return int(e & (0x1ffu | kFastSpecial));
+    *after = p0 + ((e >> 9) & 15u);
+    return int(e & 0x1ffu);
   }
-  SmemBitSrc src{cur.w, nBits};
-  uint32_t p = cur.pos;
+  SmemBitSrc src{S.sw, nBits};
+  uint32_t p = p0;
   int sym = canon_slow_symbol(S.firstCode, S.count, S.offset, S.sorted, src, &p, kFastLutBits + 1);
-  if (sym < 0) return -1;
-  cur.init(cur.w, p);
-  return sym >= 256 ? int(uint32_t(sym) | kFastSpecial) : sym;
+  *after = p;
+  return sym;
 }
 
-// Counting decode of one sub-sequence: from `start` to the first value boundary at or after `limit`.
+// Counting decode of one sub-sequence: from `start` to the first value boundary at or after `limit` (<= nBits).
 // flag: 1 = end of text consumed, 2 = invalid code / ran past the data.
 __device__ __forceinline__ void canon_fast_count(const CanonFastShared& S, uint32_t nBits, uint32_t start, uint32_t limit,
                                                  uint32_t* endOut, uint32_t* cntOut, int* flagOut) {
   BitCursor cur;
-  cur.init(S.sw, start);
-  uint32_t c = 0;
+  cur.init(S, start);
+  uint32_t c = 0, end;
   int flag = 0;
-  uint32_t end;
   for (;;) {
     const uint32_t p0 = cur.pos;
-    if (p0 >= nBits) { flag = 2; end = p0; break; }
-    int e = canon_fast_symbol(S, cur, nBits);
-    if (e < 0) { flag = 2; end = p0; break; }
-    if (!(uint32_t(e) & kFastSpecial)) {
+    if (p0 + uint32_t(kFastLutBits) <= limit) {
+      // the whole 11-bit window lies before the limit: every value coded inside it is consumed (up to 3 per lookup)
+      const uint32_t m = S.mlut[cur.peek() & ((1u << kFastLutBits) - 1u)];
+      if (m >> 28) {
+        cur.skip(S, (m >> 24) & 15u);
+        c += m >> 28;
+        continue;
+      }
+    }
+    const uint32_t e = S.lut[cur.peek() & ((1u << kFastLutBits) - 1u)];
+    if (e - 1u < 0x7fffu) {  // LUT hit on a plain value: e = sym | len << 9
       if (p0 >= limit) { end = p0; break; }
+      cur.skip(S, e >> 9);
       c++;
       continue;
     }
-    const int sym = e & 0x1ff;
-    if (sym == kSymEsc2) cur.skip(2);
-    else if (sym == kSymEsc8) cur.skip(8);
-    else {
+    uint32_t after;
+    const int sym = canon_fast_rare_symbol(S, e, p0, nBits, &after);
+    if (sym < 0) { flag = 2; end = p0; break; }
+    if (sym == kSymEsc2 || sym == kSymEsc8) {
+      after += sym == kSymEsc2 ? 2u : 8u;
+      if (after > nBits) { flag = 2; end = p0; break; }
+    } else {
       if (p0 >= limit) { end = p0; break; }
-      if (sym == kSymEot) { flag = 1; end = cur.pos; break; }
-      c++;  // null symbol: a value
+      if (sym == kSymEot) { flag = 1; end = after; break; }
+      c++;  // long-code value or null symbol
     }
+    cur.init(S, after);
   }
   *endOut = end;
   *cntOut = c;
@@ -256,6 +267,20 @@ __device__ inline void canon_fast_build_lut(CanonFastShared& S) {
     S.lut[e] = entry;
   }
   __syncthreads();
+  // multi-symbol table: the plain values whose codes lie completely inside the 11-bit window (at most 3)
+  for (int e = threadIdx.x; e < (1 << kFastLutBits); e += kThreads) {
+    uint32_t used = 0, n = 0, syms = 0;
+    while (n < 3) {
+      const uint32_t x = S.lut[(uint32_t(e) >> used) & ((1u << kFastLutBits) - 1u)];
+      const uint32_t len = x >> 9;
+      if (x - 1u >= 0x7fffu || used + len > uint32_t(kFastLutBits)) break;  // long code, special symbol, or cut by the window
+      syms |= (x & 0xffu) << (8 * n);
+      used += len;
+      n++;
+    }
+    S.mlut[e] = syms | (used << 24) | (n << 28);
+  }
+  __syncthreads();
 }
 
 // Decodes the TEXT of one canonical stream staged in S.sw; tables and LUT are ready and the text starts at bit T0.
@@ -270,56 +295,50 @@ __device__ bool canon_fast_decode_text(CanonFastShared& S, uint32_t nBits, const
   if (hintBits && T0 + hintBits < regionEnd) regionEnd = T0 + hintBits;
   for (;;) {  // region growth until the end-of-text code is inside the region
     const uint32_t avail = regionEnd - T0;
-    // sub-sequence size: ~112 bits, adjusted so that the sub-sequences fill whole rounds of kThreads threads
-    uint32_t rounds = (avail / 112u + kThreads - 1) / kThreads;
+    // sub-sequence size: about kFastSubBits, adjusted so that the sub-sequences fill whole rounds of kThreads threads
+    uint32_t rounds = (avail / kFastSubBits + kThreads - 1) / kThreads;
     if (rounds < 1u) rounds = 1u;
-    if (rounds > uint32_t(kFastSubPerThread)) rounds = kFastSubPerThread;
+    if (rounds > uint32_t(kFastRounds)) rounds = kFastRounds;
     uint32_t B = (avail + rounds * kThreads - 1) / (rounds * kThreads);
     if (B < 96u) B = 96u;
     const int nSub = int((avail + B - 1) / B);
-    // pass 0: only the END of every sub-sequence matters here, so start late (64 bits before the limit) and rely on
+    // pass 0: only the END of every sub-sequence matters here, so start kFastLookback bits before the limit and rely on
     // self-synchronisation; sub-sequence 0 starts at the true text start.
-    uint32_t myStart[kFastSubPerThread];
-#pragma unroll
-    for (int j = 0; j < kFastSubPerThread; j++) {
-      int i = tid + j * kThreads;
-      myStart[j] = T0 + uint32_t(i) * B;
-      if (i < nSub) {
-        uint32_t limit = T0 + uint32_t(i + 1) * B;
-        if (limit > regionEnd) limit = regionEnd;
-        uint32_t from = myStart[j];
-        if (i > 0 && limit - from > 64u) from = limit - 64u;
-        uint32_t e, c;
-        int f;
-        canon_fast_count(S, nBits, from, limit, &e, &c, &f);
-        S.endpos[i] = e;
-        S.cnt[i] = uint16_t(c);
-        S.eot[i] = uint8_t(f);
-        if (i > 0) myStart[j] = 0xffffffffu;  // forces the exact re-decode in the first synchronisation pass
-      }
+#pragma unroll 1
+    for (int i = tid; i < nSub; i += kThreads) {
+      uint32_t limit = T0 + uint32_t(i + 1) * B;
+      if (limit > regionEnd) limit = regionEnd;
+      uint32_t from = T0 + uint32_t(i) * B;
+      if (i > 0 && limit - from > kFastLookback) from = limit - kFastLookback;
+      uint32_t e, c;
+      int f;
+      canon_fast_count(S, nBits, from, limit, &e, &c, &f);
+      S.endpos[i] = e;
+      S.cnt[i] = uint16_t(c);
+      S.eot[i] = uint8_t(f);
+      S.startv[i] = i > 0 ? 0xffffffffu : T0;  // forces the exact decode of every later sub-sequence in the first pass below
     }
+    // synchronisation passes: sub-sequence i must start where i-1 ended.  Reads of endpos[i-1] may see this pass's or
+    // the previous pass's value (both are candidates); the loop ends only after a pass in which nothing was rewritten,
+    // and in that pass every start was compared against final values.
+    volatile uint32_t* vend = S.endpos;
     for (int pass = 0; pass <= nSub; pass++) {
       __syncthreads();
       if (tid == 0) S.changed = 0;
-      uint32_t ns[kFastSubPerThread];
-#pragma unroll
-      for (int j = 0; j < kFastSubPerThread; j++) {
-        int i = tid + j * kThreads;
-        ns[j] = (i > 0 && i < nSub) ? S.endpos[i - 1] : myStart[j];
-      }
       __syncthreads();
       bool any = false;
-#pragma unroll
-      for (int j = 0; j < kFastSubPerThread; j++) {
-        int i = tid + j * kThreads;
-        if (i < nSub && ns[j] != myStart[j]) {
-          myStart[j] = ns[j];
+#pragma unroll 1
+      for (int i = tid; i < nSub; i += kThreads) {
+        if (i == 0) continue;
+        const uint32_t ns = vend[i - 1];
+        if (ns != S.startv[i]) {
+          S.startv[i] = ns;
           uint32_t limit = T0 + uint32_t(i + 1) * B;
           if (limit > regionEnd) limit = regionEnd;
           uint32_t e, c;
           int f;
-          canon_fast_count(S, nBits, myStart[j], limit, &e, &c, &f);
-          S.endpos[i] = e;
+          canon_fast_count(S, nBits, ns, limit, &e, &c, &f);
+          vend[i] = e;
           S.cnt[i] = uint16_t(c);
           S.eot[i] = uint8_t(f);
           any = true;
@@ -332,11 +351,9 @@ __device__ bool canon_fast_decode_text(CanonFastShared& S, uint32_t nBits, const
     __syncthreads();
     if (tid == 0) S.firstEot = nSub;
     __syncthreads();
-#pragma unroll
-    for (int j = 0; j < kFastSubPerThread; j++) {
-      int i = tid + j * kThreads;
-      if (i < nSub && S.eot[i]) atomicMin(&S.firstEot, i);
-    }
+#pragma unroll 1
+    for (int i = tid; i < nSub; i += kThreads)
+      if (S.eot[i]) atomicMin(&S.firstEot, i);
     __syncthreads();
     const int fe = S.firstEot;
     if (fe < nSub && S.eot[fe] == 2) return false;  // invalid code, or the data ended before end-of-text
@@ -347,73 +364,97 @@ __device__ bool canon_fast_decode_text(CanonFastShared& S, uint32_t nBits, const
       __syncthreads();
       continue;
     }
-    // value offsets (contiguous ownership for the scan)
-    uint32_t local[kFastSubPerThread];
+    // value offsets: thread tid owns sub-sequences tid*kFastRounds .. +kFastRounds-1 for the scan
     uint32_t mySum = 0;
 #pragma unroll
-    for (int j = 0; j < kFastSubPerThread; j++) {
-      int i = tid * kFastSubPerThread + j;
-      local[j] = (i <= fe) ? S.cnt[i] : 0u;
-      mySum += local[j];
+    for (int j = 0; j < kFastRounds; j++) {
+      int i = tid * kFastRounds + j;
+      mySum += (i <= fe && i < nSub) ? S.cnt[i] : 0u;
     }
     uint32_t total;
     uint32_t ex = block_exclusive_scan(mySum, S.scan, &total);
     if (total > maxValues) return false;
+    if (tid == 0) S.endBit = S.endpos[fe];
+    __syncthreads();
+    uint32_t* offv = S.endpos;  // end positions are no longer needed: the array now holds the first value index of every sub-sequence
     {
       uint32_t run = ex;
 #pragma unroll
-      for (int j = 0; j < kFastSubPerThread; j++) {
-        int i = tid * kFastSubPerThread + j;
-        if (i < nSub) S.off[i] = run;
-        run += local[j];
+      for (int j = 0; j < kFastRounds; j++) {
+        int i = tid * kFastRounds + j;
+        if (i < nSub) {
+          offv[i] = run;
+          run += (i <= fe) ? S.cnt[i] : 0u;
+        }
       }
     }
     __syncthreads();
     // write pass: decode again, assembling escapes into values
     bool bad = false;
-#pragma unroll
-    for (int j = 0; j < kFastSubPerThread; j++) {
-      int i = tid + j * kThreads;
-      if (i <= fe && i < nSub) {
-        uint32_t limit = T0 + uint32_t(i + 1) * B;
-        if (limit > regionEnd) limit = regionEnd;
-        BitCursor cur;
-        cur.init(S.sw, myStart[j]);
-        sink.begin(S.off[i]);
-        bool have = false;
-        uint32_t v = 0;
-        for (;;) {
-          const uint32_t p0 = cur.pos;
-          if (p0 >= nBits) { bad = true; break; }
-          int e = canon_fast_symbol(S, cur, nBits);
-          if (e < 0) { bad = true; break; }
-          if (!(uint32_t(e) & kFastSpecial)) {
-            if (p0 >= limit) break;
+    const int last = fe < nSub - 1 ? fe : nSub - 1;
+#pragma unroll 1
+    for (int i = tid; i <= last; i += kThreads) {
+      uint32_t limit = T0 + uint32_t(i + 1) * B;
+      if (limit > regionEnd) limit = regionEnd;
+      BitCursor cur;
+      cur.init(S, S.startv[i]);
+      sink.begin(offv[i]);
+      bool have = false;
+      uint32_t v = 0;
+      for (;;) {
+        const uint32_t p0 = cur.pos;
+        if (p0 + uint32_t(kFastLutBits) <= limit) {
+          const uint32_t m = S.mlut[cur.peek() & ((1u << kFastLutBits) - 1u)];
+          const uint32_t n = m >> 28;
+          if (n) {
+            cur.skip(S, (m >> 24) & 15u);
             if (have) sink.put(int32_t(v));
             have = true;
-            v = uint32_t(e - 128);
+            if (n == 1) v = (m & 0xffu) - 128u;
+            else {
+              sink.put(int32_t((m & 0xffu) - 128u));
+              if (n == 2) v = ((m >> 8) & 0xffu) - 128u;
+              else {
+                sink.put(int32_t(((m >> 8) & 0xffu) - 128u));
+                v = ((m >> 16) & 0xffu) - 128u;
+              }
+            }
             continue;
           }
-          const int sym = e & 0x1ff;
-          if (sym == kSymEsc2 || sym == kSymEsc8) {
-            if (!have) { bad = true; break; }  // an escape with nothing to extend (CanonicalHuffman.java:495-504 would index -1)
-            const int nb = sym == kSymEsc2 ? 2 : 8;
-            v = (v << nb) | (cur.peek() & ((1u << nb) - 1u));
-            cur.skip(nb);
-          } else {
-            if (p0 >= limit) break;
-            if (sym == kSymEot) break;
-            if (have) sink.put(int32_t(v));
-            have = true;
-            v = uint32_t(INT32_MIN);  // null symbol
-          }
         }
-        if (have) sink.put(int32_t(v));
-        sink.end();
+        const uint32_t e = S.lut[cur.peek() & ((1u << kFastLutBits) - 1u)];
+        if (e - 1u < 0x7fffu) {  // plain value
+          if (p0 >= limit) break;
+          cur.skip(S, e >> 9);
+          if (have) sink.put(int32_t(v));
+          have = true;
+          v = (e & 0xffu) - 128u;
+          continue;
+        }
+        uint32_t after;
+        const int sym = canon_fast_rare_symbol(S, e, p0, nBits, &after);
+        if (sym < 0) { bad = true; break; }
+        if (sym == kSymEsc2 || sym == kSymEsc8) {
+          if (!have) { bad = true; break; }  // an escape with nothing to extend (CanonicalHuffman.java:495-504 would index -1)
+          const int nb = sym == kSymEsc2 ? 2 : 8;
+          if (after + nb > nBits) { bad = true; break; }
+          SmemBitSrc src{S.sw, nBits};
+          v = (v << nb) | src.bits(after, nb);
+          after += nb;
+        } else {
+          if (p0 >= limit) break;
+          if (sym == kSymEot) break;
+          if (have) sink.put(int32_t(v));
+          have = true;
+          v = sym == kSymNull ? uint32_t(INT32_MIN) : uint32_t(sym - 128);
+        }
+        cur.init(S, after);
       }
+      if (have) sink.put(int32_t(v));
+      sink.end();
     }
     if (__syncthreads_or(bad ? 1 : 0)) return false;
-    *endBit = S.endpos[fe];
+    *endBit = S.endBit;
     *nValues = total;
     return true;
   }

@@ -138,6 +138,45 @@ struct InteriorRunSink {  // LSOP12 interior order: rows 2.., columns 2..C-3 row
   }
   __device__ __forceinline__ void end() {}
 };
+// Same order, for 16-byte aligned tile rows: the last (up to) four values of the current row are kept in registers
+// and leave as one int4 store whenever they fill an aligned group of four columns; the unaligned head of a run, the
+// two-column tail of every row and the end of a run are flushed as scalars.  A sub-sequence decodes ~45 consecutive
+// values, so most of them go out 16 bytes at a time instead of as 32 scattered 4-byte sector writes per warp store.
+struct InteriorRunSink4 {
+  TileView t;
+  int32_t* rowp;  // column 0 of the current row
+  int col, n;     // next column to be written (2 .. C-3); number of buffered values (columns col-n .. col-1)
+  int32_t q0, q1, q2, q3;
+  __device__ __forceinline__ void begin(uint32_t k0) {
+    const int w = t.C - 4;
+    int rr = int(k0) / w;
+    col = 2 + int(k0) - rr * w;
+    rowp = t.row(2 + rr);
+    n = 0;
+  }
+  __device__ __forceinline__ void flush_scalars() {
+    if (n >= 4) rowp[col - 4] = q0;
+    if (n >= 3) rowp[col - 3] = q1;
+    if (n >= 2) rowp[col - 2] = q2;
+    if (n >= 1) rowp[col - 1] = q3;
+    n = 0;
+  }
+  __device__ __forceinline__ void put(int32_t v) {
+    q0 = q1; q1 = q2; q2 = q3; q3 = v;
+    n++;
+    col++;
+    if ((col & 3) == 0) {
+      if (n == 4) { *reinterpret_cast<int4*>(rowp + col - 4) = make_int4(q0, q1, q2, q3); n = 0; }
+      else flush_scalars();  // head of a run that started inside a group
+    }
+    if (col == t.C - 2) {  // end of the row's interior: columns C-4, C-3 (tile_cols % 4 == 0)
+      flush_scalars();
+      col = 2;
+      rowp += t.pitch;
+    }
+  }
+  __device__ __forceinline__ void end() { flush_scalars(); }
+};
 
 }  // namespace
 
@@ -196,8 +235,9 @@ struct CanonWarpShared {
   uint16_t lut8[256];   // text code: sym | len << 9 | special; 0 = longer than 8 bits
   uint16_t ctLut[256];  // code-table code: sym | len << 8
   uint32_t cnt32[17], next[17];
+  int32_t vals[256];    // initializer values staged by lane 0, scattered to their cells by all lanes
   uint32_t textStart;
-  int error;
+  int error, nvals, done;
 };
 
 // Warp-cooperative version of canon_fast_parse_header over a global-memory bit source.  All 32 lanes call.
@@ -360,39 +400,56 @@ __global__ void __launch_bounds__(kThreads) lsop_decode_head_kernel(DecodeArgs a
   int status = W.error ? G4_ERR_FORMAT : G4_OK;
   uint32_t endBit = 0;
   if (status == G4_OK) {
-    // initializer text, serially by lane 0 (CanonicalHuffman.decodeText :469-519): values go straight to their cells
-    if (lane == 0) {
-      uint32_t pos = W.textStart, k = 0, v = 0;
-      bool have = false, bad = false;
-      for (;;) {
-        if (pos >= src.nBits) { bad = true; break; }
-        uint32_t e = W.lut8[src.peek32(pos) & 0xffu];
-        int sym;
-        if (e) { sym = int(e & 0x1ffu); pos += (e >> 9) & 15u; }
-        else {
-          sym = canon_slow_symbol(W.firstCode, W.count, W.offset, W.sorted, src, &pos, 9);
-          if (sym < 0) { bad = true; break; }
+    // initializer text (CanonicalHuffman.decodeText :469-519): lane 0 decodes serially into a 256-value stage, then
+    // all lanes scatter the stage to the cells of the initializer stream order
+    uint32_t pos = W.textStart, k = 0, v = 0, kBase = 0;
+    bool have = false;
+    for (;;) {
+      if (lane == 0) {
+        int n = 0;
+        bool bad = false, done = false;
+        while (n < 256) {
+          if (pos >= src.nBits) { bad = true; break; }
+          uint32_t e = W.lut8[src.peek32(pos) & 0xffu];
+          int sym;
+          if (e) { sym = int(e & 0x1ffu); pos += (e >> 9) & 15u; }
+          else {
+            sym = canon_slow_symbol(W.firstCode, W.count, W.offset, W.sorted, src, &pos, 9);
+            if (sym < 0) { bad = true; break; }
+          }
+          if (sym == kSymEsc2 || sym == kSymEsc8) {
+            if (!have) { bad = true; break; }
+            const int nb = sym == kSymEsc2 ? 2 : 8;
+            v = (v << nb) | src.bits(pos, nb);
+            pos += nb;
+            continue;
+          }
+          if (have) {
+            if (k >= nInit) { bad = true; break; }
+            W.vals[n++] = int32_t(v);
+            k++;
+            have = false;
+          }
+          if (sym == kSymEot) { done = true; break; }
+          have = true;
+          v = sym == kSymNull ? uint32_t(INT32_MIN) : uint32_t(sym - 128);
         }
-        if (sym == kSymEsc2 || sym == kSymEsc8) {
-          if (!have) { bad = true; break; }
-          const int nb = sym == kSymEsc2 ? 2 : 8;
-          v = (v << nb) | src.bits(pos, nb);
-          pos += nb;
-          continue;
-        }
-        if (have) {
-          if (k >= nInit) { bad = true; break; }
-          int r, c;
-          stream_to_cell(kStreamLsopInit, int(k++), R, C, &r, &c);
-          t.at(r, c) = int32_t(v);
-          have = false;
-        }
-        if (sym == kSymEot) break;
-        have = true;
-        v = sym == kSymNull ? uint32_t(INT32_MIN) : uint32_t(sym - 128);
+        if (bad || (done && k != nInit)) W.error = 1;
+        W.nvals = n;
+        W.done = (done || bad) ? 1 : 0;
+        W.textStart = pos;
       }
-      if (bad || k != nInit) W.error = 1;
-      W.textStart = pos;
+      __syncwarp();
+      const int n = W.nvals;
+      for (int i = lane; i < n; i += 32) {
+        int r, c;
+        stream_to_cell(kStreamLsopInit, int(kBase) + i, R, C, &r, &c);
+        t.at(r, c) = W.vals[i];
+      }
+      kBase += uint32_t(n);
+      const int done = W.done;
+      __syncwarp();
+      if (done) break;
     }
     __syncwarp();
     if (W.error) status = G4_ERR_FORMAT;
@@ -431,6 +488,7 @@ __global__ void __launch_bounds__(kThreads) lsop_decode_head_kernel(DecodeArgs a
   if (lane == 0) a.status[tIdx] = status;
 }
 
+template <class InteriorSink>
 __global__ void __launch_bounds__(kThreads, 4) lsop_decode_text_kernel(DecodeArgs a, const uint8_t* meta) {
   extern __shared__ __align__(16) unsigned char lsopFastSmem[];
   CanonFastShared& F = *reinterpret_cast<CanonFastShared*>(lsopFastSmem);
@@ -459,7 +517,8 @@ __global__ void __launch_bounds__(kThreads, 4) lsop_decode_text_kernel(DecodeArg
     if (ok) {
       canon_fast_build_lut(F);
       uint32_t endBit = 0, nv = 0;
-      InteriorRunSink s2{t, nullptr, 0, 0};
+      InteriorSink s2{};
+      s2.t = t;
       ok = canon_fast_decode_text(F, len * 8u, T0, nInterior, 0u, s2, &endBit, &nv) && nv == nInterior;
     }
     if (!ok && tid == 0) a.status[tIdx] = G4_ERR_FORMAT;
@@ -1087,16 +1146,22 @@ cudaError_t launch_lsop_decode(const DecodeArgs& a, float* coef, uint8_t* meta, 
                                int nTilesUpper, cudaStream_t s) {
   static bool attr = false;
   if (!attr) {
-    cudaError_t ea = cudaFuncSetAttribute(lsop_decode_text_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
+    cudaError_t ea = cudaFuncSetAttribute(lsop_decode_text_kernel<InteriorRunSink>, cudaFuncAttributeMaxDynamicSharedMemorySize,
                                           int(sizeof(CanonFastShared)));
+    if (ea == cudaSuccess)
+      ea = cudaFuncSetAttribute(lsop_decode_text_kernel<InteriorRunSink4>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                int(sizeof(CanonFastShared)));
     if (ea != cudaSuccess) return ea;
     attr = true;
   }
+  const bool aligned = (a.band.tile_cols % 4) == 0 && (a.band.grid_pitch % 4) == 0 && a.band.tile_cols >= 8 &&
+                       (reinterpret_cast<uintptr_t>(a.grid) & 15) == 0;
   // deferCounters[0] = number of deferred tiles (filled by kernel H), [1] = work counter of the general kernel
   lsop_decode_head_kernel<<<(nTilesUpper + kWarps - 1) / kWarps, kThreads, 0, s>>>(a, coef, meta, defer, deferCounters);
   cudaError_t e = cudaGetLastError();
   if (e != cudaSuccess) return e;
-  lsop_decode_text_kernel<<<nCtas, kThreads, sizeof(CanonFastShared), s>>>(a, meta);
+  if (aligned) lsop_decode_text_kernel<InteriorRunSink4><<<nCtas, kThreads, sizeof(CanonFastShared), s>>>(a, meta);
+  else lsop_decode_text_kernel<InteriorRunSink><<<nCtas, kThreads, sizeof(CanonFastShared), s>>>(a, meta);
   e = cudaGetLastError();
   if (e != cudaSuccess) return e;
   DecodeArgs d = a;
@@ -1106,8 +1171,6 @@ cudaError_t launch_lsop_decode(const DecodeArgs& a, float* coef, uint8_t* meta, 
   lsop_decode_entropy_kernel<<<nCtas < 296 ? nCtas : 296, kThreads, 0, s>>>(d, coef);
   e = cudaGetLastError();
   if (e != cudaSuccess) return e;
-  const bool aligned = (a.band.tile_cols % 4) == 0 && (a.band.grid_pitch % 4) == 0 && a.band.tile_cols >= 8 &&
-                       (reinterpret_cast<uintptr_t>(a.grid) & 15) == 0;
   if (aligned) lsop_wavefront4_kernel<<<(nTilesUpper + kWarps - 1) / kWarps, kThreads, 0, s>>>(a, coef);
   else lsop_wavefront_kernel<<<(nTilesUpper + kWarps - 1) / kWarps, kThreads, 0, s>>>(a, coef);
   return cudaGetLastError();
