@@ -691,9 +691,10 @@ __global__ void __launch_bounds__(kThreads) lsop_wavefront_kernel(DecodeArgs a, 
 // block behind lane l-1, so all lanes are at the same column phase: residuals are read and values written as int4.
 // Row r-1 at column c+2 is lane l-1's output of two steps ago (shuffle of its float history f2); row r-2 at column
 // c+2 is the oldest element lane l-1 still holds of ITS row above (shuffle of av[j]).  Lane 0 (and lane 1 for r-2)
-// read the rows of the previous 32-row group from L2; a row takes P = max(C,132) steps so that lane 31 of the previous
-// group is always at least two blocks ahead of lane 0 of the next one and the groups need no drain between them.
-__global__ void __launch_bounds__(kThreads) lsop_wavefront4_kernel(DecodeArgs a, const float* coef) {
+// read the rows of the previous 32-row group from L2, one iteration ahead of their use; a row takes P = max(C,136)
+// steps so that lane 31 of the previous group is always at least three blocks ahead of lane 0 of the next one and
+// the groups need no drain between them.
+__global__ void __launch_bounds__(kThreads, 4) lsop_wavefront4_kernel(DecodeArgs a, const float* coef) {
   const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
   const int li = blockIdx.x * kWarps + warp;
   if (li >= *a.listCount) return;
@@ -704,45 +705,74 @@ __global__ void __launch_bounds__(kThreads) lsop_wavefront4_kernel(DecodeArgs a,
   float u[12];
 #pragma unroll
   for (int i = 0; i < 12; i++) u[i] = coef[size_t(tIdx) * 12 + i];
-  const int P = C > 132 ? C : 132;
+  const int P = C > 136 ? C : 136;
   const int nB = P >> 2, cBlocks = C >> 2;
   const int nGroups = (R - 2 + 31) >> 5;
   const int nIter = nGroups * nB + 31;
+  const int64_t pitch = t.pitch;
   float av[8], bv[8];  // rows r-1 / r-2 as float, columns c0-2 .. c0+5
 #pragma unroll
   for (int i = 0; i < 8; i++) { av[i] = 0.f; bv[i] = 0.f; }
-  float f1 = 0.f, f2 = 0.f;  // own row, columns c-1 and c-2
-  int32_t h1 = 0;            // own row, column c-1 (integer, for the two Triangle columns)
+  float f1 = 0.f, f2 = 0.f;           // own row, columns c-1 and c-2
+  int32_t h1 = 0;                     // own row, column c-1 (integer, for the two Triangle columns)
+  int32_t po1 = 0, po2 = 0, po3 = 0;  // own outputs of the previous block (Triangle operands of the lane below)
+  // Operands that come from memory are fetched ONE ITERATION AHEAD so that their latency overlaps a block of arithmetic:
+  // the block's own four cells (residuals, or final values in columns 0,1), and for lanes 0,1 the rows written by the
+  // previous row group (lane 0: row r-1 and r-2, lane 1: row r-2; columns c0+2..c0+5).  The once-per-row operands
+  // (columns 0,1 of the rows above; lane 0's Triangle operands) are loaded where they are used.
+  // The fetch is branch-free: every lane issues the same five loads; lanes (or iterations) that do not need a value
+  // read the tile's first cells instead (one broadcast sector), which keeps the loop free of divergent control flow.
+  int4 vN;
+  int2 a0, a1, b0, b1;
   int cb = -lane, r = 2 + lane;
+  int32_t* rowp = t.row(r < R ? r : 2);  // row r (any valid row while the lane has nothing to do)
+  const int32_t* const safe = t.base;
+  const bool l01 = lane < 2, l0 = lane == 0;
+  auto fetch = [&](const int32_t* rp, int cbX, bool actX) {
+    const int cX = cbX << 2;
+    const int32_t* pv = actX ? rp + cX : safe;
+    const int32_t* q2 = (actX && l01) ? rp - 2 * pitch + cX + 2 : safe;
+    const int32_t* q1 = (actX && l0) ? rp - pitch + cX + 2 : safe;
+    const int step = cX + 4 < C ? 2 : 0;  // columns C, C+1 do not exist; their operands are never used
+    vN = *reinterpret_cast<const int4*>(pv);
+    b0 = __ldcg(reinterpret_cast<const int2*>(q2));
+    b1 = __ldcg(reinterpret_cast<const int2*>(q2 + step));
+    a0 = __ldcg(reinterpret_cast<const int2*>(q1));
+    a1 = __ldcg(reinterpret_cast<const int2*>(q1 + step));
+  };
+  fetch(rowp, cb, cb == 0 && r < R);
   for (int it = 0; it < nIter; it++) {
     const bool act = cb >= 0 && cb < cBlocks && r < R;
     const int c0 = cb << 2;
-    int32_t* rowp = t.row(act ? r : 2);
-    int4 v = make_int4(0, 0, 0, 0);
-    if (act) v = *reinterpret_cast<const int4*>(rowp + c0);  // residuals (columns >= 2) or final values (columns 0,1)
+    // consume everything fetched during the previous iteration BEFORE issuing the next fetch
+    const int4 v = vN;
+    const float m1[4] = {float(a0.x), float(a0.y), float(a1.x), float(a1.y)};
+    const float m2[4] = {float(b0.x), float(b0.y), float(b1.x), float(b1.y)};
+    int32_t* const rowCur = rowp;
+    {
+      int cbN = cb + 1;
+      if (cbN == nB) { cbN = 0; r += 32; rowp += 32 * pitch; }
+      fetch(rowp, cbN, cbN >= 0 && cbN < cBlocks && r < R);
+      cb = cbN;
+    }
 #pragma unroll
     for (int i = 0; i < 4; i++) { av[i] = av[i + 4]; bv[i] = bv[i + 4]; }
-    if (act && cb == 0) {  // row start: columns 0,1 of the two rows above (final since kernel A)
-      int2 p1 = __ldcg(reinterpret_cast<const int2*>(rowp - t.pitch));
-      int2 p2 = __ldcg(reinterpret_cast<const int2*>(rowp - 2 * t.pitch));
-      av[2] = float(p1.x); av[3] = float(p1.y);
-      bv[2] = float(p2.x); bv[3] = float(p2.y);
+    if (act && c0 == 0) {  // row start (once per row): columns 0,1 of the two rows above, final since kernel H
+      const int2 s1 = __ldcg(reinterpret_cast<const int2*>(rowCur - pitch));
+      const int2 s2 = __ldcg(reinterpret_cast<const int2*>(rowCur - 2 * pitch));
+      av[2] = float(s1.x); av[3] = float(s1.y);
+      bv[2] = float(s2.x); bv[3] = float(s2.y);
     }
-    float m1[4] = {0.f, 0.f, 0.f, 0.f}, m2[4] = {0.f, 0.f, 0.f, 0.f};
-    if (lane < 2 && act) {  // rows written by the previous row group (or rows 0,1): columns c0+2 .. c0+5 from L2
-      const int32_t* q2 = rowp - 2 * t.pitch + c0 + 2;
-      int2 x = __ldcg(reinterpret_cast<const int2*>(q2));
-      m2[0] = float(x.x); m2[1] = float(x.y);
-      if (c0 + 4 < C) { int2 y = __ldcg(reinterpret_cast<const int2*>(q2 + 2)); m2[2] = float(y.x); m2[3] = float(y.y); }
-      if (lane == 0) {
-        const int32_t* q1 = rowp - t.pitch + c0 + 2;
-        int2 x1 = __ldcg(reinterpret_cast<const int2*>(q1));
-        m1[0] = float(x1.x); m1[1] = float(x1.y);
-        if (c0 + 4 < C) { int2 y1 = __ldcg(reinterpret_cast<const int2*>(q1 + 2)); m1[2] = float(y1.x); m1[3] = float(y1.y); }
-      }
+    const bool lastBlock = c0 == C - 4;
+    // Triangle columns: row r-1, columns C-3..C-1 = lane l-1's outputs of its previous (= its last) block; lane 0 reads
+    // them from the previous row group's memory (once per row)
+    int32_t upy = __shfl_up_sync(0xffffffffu, po1, 1);
+    int32_t upz = __shfl_up_sync(0xffffffffu, po2, 1);
+    int32_t upw = __shfl_up_sync(0xffffffffu, po3, 1);
+    if (lane == 0 && act && lastBlock) {
+      const int4 m = __ldcg(reinterpret_cast<const int4*>(rowCur - pitch + c0));
+      upy = m.y; upz = m.z; upw = m.w;
     }
-    int4 up = make_int4(0, 0, 0, 0);
-    if (act && cb == cBlocks - 1) up = __ldcg(reinterpret_cast<const int4*>(rowp - t.pitch + c0));  // Triangle columns
     int32_t out[4];
 #pragma unroll
     for (int j = 0; j < 4; j++) {
@@ -769,11 +799,11 @@ __global__ void __launch_bounds__(kThreads) lsop_wavefront4_kernel(DecodeArgs a,
       p = p + u[11] * bv[j + 4];
       uint32_t add = uint32_t(java_round(p));
       if (j < 2) {
-        if (cb == 0) add = 0u;  // columns 0,1 hold their final values already
+        if (c0 == 0) add = 0u;  // columns 0,1 hold their final values already
       } else {
         // last two columns: Triangle predictor (LsDecoder12.java:459-468); tile_cols % 4 == 0 puts them at j = 2,3
-        const int32_t upc = j == 2 ? up.z : up.w, upl = j == 2 ? up.y : up.z;
-        if (cb == cBlocks - 1) add = (uint32_t(h1) + uint32_t(upc)) - uint32_t(upl);
+        const int32_t upc = j == 2 ? upz : upw, upl = j == 2 ? upy : upz;
+        if (lastBlock) add = (uint32_t(h1) + uint32_t(upc)) - uint32_t(upl);
       }
       const int32_t val = int32_t(uint32_t(res) + add);
       out[j] = val;
@@ -781,8 +811,8 @@ __global__ void __launch_bounds__(kThreads) lsop_wavefront4_kernel(DecodeArgs a,
       f2 = f1;
       f1 = float(val);
     }
-    if (act) *reinterpret_cast<int4*>(rowp + c0) = make_int4(out[0], out[1], out[2], out[3]);
-    if (++cb == nB) { cb = 0; r += 32; }
+    if (act) *reinterpret_cast<int4*>(rowCur + c0) = make_int4(out[0], out[1], out[2], out[3]);
+    po1 = out[1]; po2 = out[2]; po3 = out[3];
     __syncwarp();
   }
 }
