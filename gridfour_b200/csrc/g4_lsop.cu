@@ -227,6 +227,33 @@ __device__ inline void lsop_init_scans(const TileView& t, int32_t seed) {
 // Legacy-Huffman, Deflate, oversized or unaligned packings are appended to `defer` for the general kernel below.
 constexpr int kLsopMetaBytes = 272;  // [0..3] interior text start (absolute bit, 0 = tile not on the fast path), [8..267] lengths
 
+// 64-bit register bit buffer over a global-memory BitSrc (clamped word reads); >= 32 valid bits after every skip().
+struct GlobalCursor {
+  const BitSrc* src;
+  uint32_t pos, next;
+  uint64_t buf;
+  int avail;
+  __device__ __forceinline__ uint32_t word(uint32_t i) const { return i <= src->lastWord ? __ldg(src->words + i) : 0u; }
+  __device__ __forceinline__ void init(const BitSrc& s, uint32_t p) {
+    src = &s;
+    pos = p;
+    const uint32_t a = s.bit0 + p, i = a >> 5, sh = a & 31;
+    buf = ((uint64_t(word(i + 1)) << 32) | word(i)) >> sh;
+    avail = 64 - int(sh);
+    next = i + 2;
+  }
+  __device__ __forceinline__ uint32_t peek() const { return uint32_t(buf); }
+  __device__ __forceinline__ void skip(uint32_t n) {
+    buf >>= n;
+    avail -= int(n);
+    pos += n;
+    if (avail < 32) {
+      buf |= uint64_t(word(next++)) << avail;
+      avail += 32;
+    }
+  }
+};
+
 struct CanonWarpShared {
   uint8_t lens[kCanonSymbols + 4];
   uint16_t sorted[kCanonSymbols];
@@ -235,9 +262,8 @@ struct CanonWarpShared {
   uint16_t lut8[256];   // text code: sym | len << 9 | special; 0 = longer than 8 bits
   uint16_t ctLut[256];  // code-table code: sym | len << 8
   uint32_t cnt32[17], next[17];
-  int32_t vals[256];    // initializer values staged by lane 0, scattered to their cells by all lanes
   uint32_t textStart;
-  int error, nvals, done;
+  int error;
 };
 
 // Warp-cooperative version of canon_fast_parse_header over a global-memory bit source.  All 32 lanes call.
@@ -277,22 +303,27 @@ __device__ inline void canon_warp_parse_header(CanonWarpShared& W, const BitSrc&
   }
   __syncwarp();
   if (lane == 0) {  // the 260 text code lengths: serial by nature (variable-length codes)
-    uint32_t pos = W.textStart;
+    GlobalCursor cur;
+    cur.init(src, W.textStart);
     int prior = 0;
     for (int i = 0; i < kCanonSymbols; i++) W.lens[i] = 0;
     for (int i = 0; i < kCanonSymbols; i++) {
-      if (pos >= src.nBits) { W.error = 1; break; }
+      if (cur.pos >= src.nBits) { W.error = 1; break; }
       int test;
-      uint32_t e = W.ctLut[src.peek32(pos) & 0xffu];
-      if (e) { test = int(e & 0xffu); pos += e >> 8; }
-      else test = canon_slow_symbol(W.ctFirst, W.ctCount, W.ctOffset, W.ctSorted, src, &pos, 9);
+      uint32_t e = W.ctLut[cur.peek() & 0xffu];
+      if (e) { test = int(e & 0xffu); cur.skip(e >> 8); }
+      else {
+        uint32_t p = cur.pos;
+        test = canon_slow_symbol(W.ctFirst, W.ctCount, W.ctOffset, W.ctSorted, src, &p, 9);
+        if (test >= 0) cur.init(src, p);
+      }
       if (test < 0) { W.error = 1; break; }
       if (test <= 15) { W.lens[i] = uint8_t(test); prior = test; }
       else {
         int n, val = 0;
-        if (test == 16) { n = int(src.bits(pos, 2)) + 3; pos += 2; val = prior; }
-        else if (test == 17) { n = int(src.bits(pos, 3)) + 3; pos += 3; prior = 0; }
-        else if (test == 18) { n = int(src.bits(pos, 7)) + 11; pos += 7; prior = 0; }
+        if (test == 16) { n = int(cur.peek() & 3u) + 3; cur.skip(2); val = prior; }
+        else if (test == 17) { n = int(cur.peek() & 7u) + 3; cur.skip(3); prior = 0; }
+        else if (test == 18) { n = int(cur.peek() & 127u) + 11; cur.skip(7); prior = 0; }
         else continue;  // the code table's own end-of-text symbol: leaves a zero length
         if (i + n > kCanonSymbols) { W.error = 1; break; }
         for (int j = 0; j < n; j++) W.lens[i + j] = uint8_t(val);
@@ -300,7 +331,7 @@ __device__ inline void canon_warp_parse_header(CanonWarpShared& W, const BitSrc&
       }
     }
     if (W.lens[kSymEot] == 0) W.error = 1;
-    W.textStart = pos;
+    W.textStart = cur.pos;
   }
   if (lane < 17) W.cnt32[lane] = 0;
   __syncwarp();
@@ -356,6 +387,125 @@ __device__ inline void canon_warp_parse_header(CanonWarpShared& W, const BitSrc&
   __syncwarp();
 }
 
+// One symbol for the warp-level decoder: 8-bit LUT, canonical arithmetic for longer codes.  Returns the symbol and the
+// position after its code, or -1.
+__device__ __forceinline__ int canon_warp_symbol(const CanonWarpShared& W, const BitSrc& src, GlobalCursor& cur) {
+  const uint32_t e = W.lut8[cur.peek() & 0xffu];
+  if (e) {
+    cur.skip((e >> 9) & 15u);
+    return int(e & 0x1ffu);
+  }
+  uint32_t p = cur.pos;
+  const int sym = canon_slow_symbol(W.firstCode, W.count, W.offset, W.sorted, src, &p, 9);
+  if (sym >= 0) cur.init(src, p);
+  return sym;
+}
+
+// Counting decode of one lane's sub-sequence (same rules as canon_fast_count): from `start` to the first value
+// boundary at or after `limit` (<= src.nBits).  flag: 1 = end of text consumed, 2 = invalid code / ran past the data.
+__device__ inline void canon_warp_count(const CanonWarpShared& W, const BitSrc& src, uint32_t start, uint32_t limit, uint32_t* endOut,
+                                        uint32_t* cntOut, int* flagOut) {
+  GlobalCursor cur;
+  cur.init(src, start);
+  uint32_t c = 0, end;
+  int flag = 0;
+  for (;;) {
+    const uint32_t p0 = cur.pos;
+    const int sym = canon_warp_symbol(W, src, cur);
+    if (sym < 0) { flag = 2; end = p0; break; }
+    if (sym == kSymEsc2 || sym == kSymEsc8) {
+      cur.skip(sym == kSymEsc2 ? 2u : 8u);
+      if (cur.pos > src.nBits) { flag = 2; end = p0; break; }
+      continue;
+    }
+    if (p0 >= limit) { end = p0; break; }
+    if (sym == kSymEot) { flag = 1; end = cur.pos; break; }
+    c++;
+  }
+  *endOut = end;
+  *cntOut = c;
+  *flagOut = flag;
+}
+
+// Warp-level version of the self-synchronising sub-sequence decoder (g4_canon_fast.cuh) for SHORT texts: 32 lanes,
+// one sub-sequence of kWarpSubBits bits per lane and region; regions follow each other until the end-of-text code is
+// found.  emit(valueIndex, value) is called once per value by the lane that decoded it.  All 32 lanes call.
+constexpr uint32_t kWarpSubBits = 192;  // > 84 bits, the longest value (code + three escapes), so a sub-sequence never overshoots the next one
+template <class Emit>
+__device__ inline bool canon_warp_decode_text(const CanonWarpShared& W, const BitSrc& src, uint32_t T0, uint32_t maxValues, Emit emit,
+                                              uint32_t* endBit, uint32_t* nValues) {
+  const int lane = threadIdx.x & 31;
+  uint32_t kBase = 0, regionStart = T0;
+  for (;;) {
+    if (regionStart >= src.nBits) return false;  // data ended before end-of-text
+    uint32_t regionEnd = regionStart + 32u * kWarpSubBits;
+    if (regionEnd > src.nBits) regionEnd = src.nBits;
+    const uint32_t lo = regionStart + uint32_t(lane) * kWarpSubBits;
+    const bool has = lo < regionEnd;
+    uint32_t limit = lo + kWarpSubBits;
+    if (limit > regionEnd) limit = regionEnd;
+    uint32_t start = lane == 0 ? regionStart : 0xffffffffu, end = regionEnd, cnt = 0;
+    int flag = 0;
+    if (has) {  // pass 0: only the end matters, start 48 bits before the limit and rely on self-synchronisation
+      uint32_t from = lo;
+      if (lane > 0 && limit - lo > 48u) from = limit - 48u;
+      canon_warp_count(W, src, from, limit, &end, &cnt, &flag);
+    }
+    for (int pass = 0; pass < 34; pass++) {  // lane i starts where lane i-1 ended; converges in <= 32 passes
+      uint32_t ns = __shfl_up_sync(0xffffffffu, end, 1);
+      if (lane == 0) ns = regionStart;
+      const bool ch = has && ns != start;
+      if (ch) {
+        start = ns;
+        canon_warp_count(W, src, start, limit, &end, &cnt, &flag);
+      }
+      if (__ballot_sync(0xffffffffu, ch) == 0) break;
+    }
+    const uint32_t flagged = __ballot_sync(0xffffffffu, has && flag != 0);
+    const int fe = flagged ? __ffs(flagged) - 1 : 32;
+    if (fe < 32 && __shfl_sync(0xffffffffu, flag, fe) == 2) return false;
+    const bool mine = has && lane <= fe;
+    const uint32_t c = mine ? cnt : 0u;
+    const uint32_t inc = warp_inclusive_scan(c);
+    const uint32_t total = __shfl_sync(0xffffffffu, inc, 31);
+    if (kBase + total > maxValues) return false;
+    bool bad = false;
+    if (mine) {  // write pass: decode again, assembling escapes into values
+      uint32_t k = kBase + inc - c;
+      GlobalCursor cur;
+      cur.init(src, start);
+      bool have = false;
+      uint32_t v = 0;
+      for (;;) {
+        const uint32_t p0 = cur.pos;
+        const int sym = canon_warp_symbol(W, src, cur);
+        if (sym < 0) { bad = true; break; }
+        if (sym == kSymEsc2 || sym == kSymEsc8) {
+          if (!have) { bad = true; break; }  // an escape with nothing to extend
+          const uint32_t nb = sym == kSymEsc2 ? 2u : 8u;
+          v = (v << nb) | (cur.peek() & ((1u << nb) - 1u));
+          cur.skip(nb);
+          continue;
+        }
+        if (p0 >= limit || sym == kSymEot) break;
+        if (have) emit(k++, int32_t(v));
+        have = true;
+        v = sym == kSymNull ? uint32_t(INT32_MIN) : uint32_t(sym - 128);
+      }
+      if (have) emit(k, int32_t(v));
+    }
+    if (__ballot_sync(0xffffffffu, bad)) return false;
+    kBase += total;
+    if (fe < 32) {
+      *endBit = __shfl_sync(0xffffffffu, end, fe);
+      *nValues = kBase;
+      return true;
+    }
+    const uint32_t hasMask = __ballot_sync(0xffffffffu, has);
+    regionStart = __shfl_sync(0xffffffffu, end, 31 - __clz(hasMask));  // the last sub-sequence's end
+  }
+}
+
 // Column scan by one warp: cell (r0-1, c) holds a final value, cells (r, c) r >= r0 hold d[r]; after the call
 // v[r][c] = base[r] + (carry0 + d[r0] + ... + d[r]) with base[r] = v[r][c-1] when addLeft, else 0.
 __device__ inline void lsop_warp_column_scan(const TileView& t, int col, int r0, uint32_t carry, bool addLeft) {
@@ -400,56 +550,19 @@ __global__ void __launch_bounds__(kThreads) lsop_decode_head_kernel(DecodeArgs a
   int status = W.error ? G4_ERR_FORMAT : G4_OK;
   uint32_t endBit = 0;
   if (status == G4_OK) {
-    // initializer text (CanonicalHuffman.decodeText :469-519): lane 0 decodes serially into a 256-value stage, then
-    // all lanes scatter the stage to the cells of the initializer stream order
-    uint32_t pos = W.textStart, k = 0, v = 0, kBase = 0;
-    bool have = false;
-    for (;;) {
-      if (lane == 0) {
-        int n = 0;
-        bool bad = false, done = false;
-        while (n < 256) {
-          if (pos >= src.nBits) { bad = true; break; }
-          uint32_t e = W.lut8[src.peek32(pos) & 0xffu];
-          int sym;
-          if (e) { sym = int(e & 0x1ffu); pos += (e >> 9) & 15u; }
-          else {
-            sym = canon_slow_symbol(W.firstCode, W.count, W.offset, W.sorted, src, &pos, 9);
-            if (sym < 0) { bad = true; break; }
-          }
-          if (sym == kSymEsc2 || sym == kSymEsc8) {
-            if (!have) { bad = true; break; }
-            const int nb = sym == kSymEsc2 ? 2 : 8;
-            v = (v << nb) | src.bits(pos, nb);
-            pos += nb;
-            continue;
-          }
-          if (have) {
-            if (k >= nInit) { bad = true; break; }
-            W.vals[n++] = int32_t(v);
-            k++;
-            have = false;
-          }
-          if (sym == kSymEot) { done = true; break; }
-          have = true;
-          v = sym == kSymNull ? uint32_t(INT32_MIN) : uint32_t(sym - 128);
-        }
-        if (bad || (done && k != nInit)) W.error = 1;
-        W.nvals = n;
-        W.done = (done || bad) ? 1 : 0;
-        W.textStart = pos;
-      }
-      __syncwarp();
-      const int n = W.nvals;
-      for (int i = lane; i < n; i += 32) {
-        int r, c;
-        stream_to_cell(kStreamLsopInit, int(kBase) + i, R, C, &r, &c);
-        t.at(r, c) = W.vals[i];
-      }
-      kBase += uint32_t(n);
-      const int done = W.done;
-      __syncwarp();
-      if (done) break;
+    // initializer text (CanonicalHuffman.decodeText :469-519), ~1200 values: warp-level sub-sequence decode, every
+    // lane scatters the values it decoded to the cells of the initializer stream order
+    uint32_t eb = 0, nv = 0;
+    auto emit = [&](uint32_t k, int32_t v) {
+      int r, c;
+      stream_to_cell(kStreamLsopInit, int(k), R, C, &r, &c);
+      t.at(r, c) = v;
+    };
+    const bool ok = canon_warp_decode_text(W, src, W.textStart, nInit, emit, &eb, &nv) && nv == nInit;
+    __syncwarp();
+    if (lane == 0) {
+      if (!ok) W.error = 1;
+      W.textStart = eb;
     }
     __syncwarp();
     if (W.error) status = G4_ERR_FORMAT;
