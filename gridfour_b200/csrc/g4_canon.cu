@@ -47,14 +47,14 @@ __global__ void __launch_bounds__(kThreads) canon_decode_kernel(DecodeArgs a) {
         t.at(r, c) = seed;
       }
     } else if (pred < 1 || pred > 4) status = G4_ERR_FORMAT;
-    else if (pred == G4_PRED_DIFF_NULLS) status = G4_ERR_UNSUPPORTED;  // TODO(next): nulls on the GPU
     else {
       BitSrc src;
       src.init(packing + 6, len - 6);
       uint32_t endBit = 0, nv = 0;
       PredCellSink sink{t, pred};
-      const uint32_t expect = uint32_t(n - 1);
+      const uint32_t expect = pred == G4_PRED_DIFF_NULLS ? uint32_t(n) : uint32_t(n - 1);
       if (!canon_decode_stream(S, src, 0, expect, 0u, sink, &endBit, &nv) || nv != expect) status = G4_ERR_FORMAT;
+      else if (pred == G4_PRED_DIFF_NULLS) predictor_inverse_nulls(t, seed);
       else {
         __syncthreads();
         if (tid == 0) t.at(0, 0) = seed;
@@ -75,10 +75,11 @@ struct CanonEncKernelShared {
 struct PredResidualGet {
   TileView t;
   int pred;
+  int32_t seed;  // PredictorModelDifferencingWithNulls only
   __device__ __forceinline__ int32_t operator()(uint32_t k) const {
     int r, c;
     stream_to_cell(pred, int(k), t.R, t.C, &r, &c);
-    return residual_at(pred, t, r, c);
+    return pred == G4_PRED_DIFF_NULLS ? residual_nulls_at(t, r, c, seed) : residual_at(pred, t, r, c);
   }
 };
 }  // namespace
@@ -124,16 +125,16 @@ __global__ void __launch_bounds__(kThreads) canon_encode_kernel(EncodeArgs a) {
       }
       continue;
     }
-    if (anyNull) {  // TODO(next): PredictorModelDifferencingWithNulls on the GPU
-      if (tid == 0) { a.lens[tIdx] = 0; a.preds[tIdx] = 0; a.status[tIdx] = G4_ERR_UNSUPPORTED; }
-      continue;
-    }
-    const uint32_t nRes = uint32_t(n - 1);
+    // nulls: only PredictorModelDifferencingWithNulls applies (:117-125), one residual per cell
+    int nStart = 0;
+    const int32_t seedNulls = anyNull ? nulls_seed(t, &nStart) : 0;
+    const uint32_t nRes = anyNull ? uint32_t(n) : uint32_t(n - 1);
+    const int firstPred = anyNull ? 3 : 0, lastPred = anyNull ? 4 : 3;
     unsigned long long best = ~0ull;
     int win = -1, built = -1;
     bool bug = false;
-    for (int p = 0; p < 3; p++) {
-      PredResidualGet get{t, p + 1};
+    for (int p = firstPred; p < lastPred; p++) {
+      PredResidualGet get{t, p + 1, seedNulls};
       if (!canon_histogram(S.E, get, nRes)) { bug = true; break; }
       canon_build_code(S.E, pm);
       built = p;
@@ -144,7 +145,7 @@ __global__ void __launch_bounds__(kThreads) canon_encode_kernel(EncodeArgs a) {
       if (tid == 0) { a.lens[tIdx] = 0; a.preds[tIdx] = 0; a.status[tIdx] = G4_DECLINED; }
       continue;
     }
-    PredResidualGet get{t, win + 1};
+    PredResidualGet get{t, win + 1, seedNulls};
     if (built != win) {
       canon_histogram(S.E, get, nRes);
       canon_build_code(S.E, pm);
@@ -155,7 +156,7 @@ __global__ void __launch_bounds__(kThreads) canon_encode_kernel(EncodeArgs a) {
       WinSink sink{S.W.win, 0};
       sink.put(uint32_t(a.codecIndex) & 0xffu, 8);
       sink.put(uint32_t(win + 1), 8);
-      sink.put(uint32_t(v0), 32);
+      sink.put(anyNull ? uint32_t(seedNulls) : uint32_t(v0), 32);
     }
     o.bitPos = 48;
     __syncthreads();

@@ -28,7 +28,6 @@ __global__ void __launch_bounds__(kThreads) deflate_inflate_kernel(DecodeArgs a,
   const uint32_t nM32 = len >= 10 ? load_le32(packing + 6) : 0;
   const uint32_t expect = pred == G4_PRED_DIFF_NULLS ? uint32_t(n) : uint32_t(n - 1);
   if (len < 12 || pred < 1 || pred > 4 || nM32 < expect || nM32 > uint32_t(6 * n)) status = G4_ERR_FORMAT;
-  else if (pred == G4_PRED_DIFF_NULLS) status = G4_ERR_UNSUPPORTED;  // TODO(next): nulls on the GPU
   else {
     uint32_t produced = 0, consumed = 0;
     int rc = inflate_warp(S[warp], packing + 10, len - 10, region + size_t(li) * regionStride, nM32, &produced, &consumed);
@@ -57,7 +56,9 @@ __global__ void __launch_bounds__(kThreads) deflate_finish_kernel(DecodeArgs a, 
     const uint32_t nM32 = load_le32(packing + 6);
     const uint8_t* m32 = region + size_t(li) * regionStride;
     int status = G4_OK;
-    if (!m32_parse_to_cells(m32, nM32, pred, t, uint32_t(n - 1), scan)) status = G4_ERR_FORMAT;
+    const uint32_t expect = pred == G4_PRED_DIFF_NULLS ? uint32_t(n) : uint32_t(n - 1);
+    if (!m32_parse_to_cells(m32, nM32, pred, t, expect, scan)) status = G4_ERR_FORMAT;
+    else if (pred == G4_PRED_DIFF_NULLS) predictor_inverse_nulls(t, seed);
     else {
       __syncthreads();
       if (tid == 0) t.at(0, 0) = seed;

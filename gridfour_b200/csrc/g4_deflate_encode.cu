@@ -14,6 +14,7 @@
 //   pick   one CTA per tile selects / assembles the packing in the tile's candidate slot
 #include "g4_kernels.h"
 #include "g4_device.cuh"
+#include "g4_predict.cuh"
 #include "g4_m32stream.cuh"
 #include "g4_deflate_enc.cuh"
 
@@ -75,6 +76,14 @@ struct PredResidualGet {
     return residual_at(pred, t, r, c);
   }
 };
+struct NullsResidualGet {  // PredictorModelDifferencingWithNulls: one residual per cell, row-major
+  TileView t;
+  int32_t seed;
+  __device__ __forceinline__ int32_t operator()(uint32_t k) const {
+    int r = int(k) / t.C, c = int(k) - r * t.C;
+    return residual_nulls_at(t, r, c, seed);
+  }
+};
 }  // namespace
 
 __global__ void __launch_bounds__(kThreads) deflate_m32_size_kernel(EncodeArgs a, uint32_t* inLen) {
@@ -91,13 +100,24 @@ __global__ void __launch_bounds__(kThreads) deflate_m32_size_kernel(EncodeArgs a
     }
     const bool anyNull = __syncthreads_or(sawNull) != 0;
     const bool anyValid = __syncthreads_or(sawValid) != 0;
-    if (!anyValid || anyNull) {  // all-null tile -> null (:167-169); nulls: TODO(next) PredictorModelDifferencingWithNulls
+    if (!anyValid) {  // all-null tile -> null (:167-169)
       if (tid == 0) {
-        a.lens[tIdx] = 0; a.preds[tIdx] = 0; a.status[tIdx] = anyValid ? G4_ERR_UNSUPPORTED : G4_DECLINED;
+        a.lens[tIdx] = 0; a.preds[tIdx] = 0; a.status[tIdx] = G4_DECLINED;
         inLen[3 * tIdx] = inLen[3 * tIdx + 1] = inLen[3 * tIdx + 2] = 0;
       }
       continue;
     }
+    if (anyNull) {  // only PredictorModelDifferencingWithNulls applies (:178-186): one stream, a.preds marks the case
+      int nStart;
+      const int32_t seed = nulls_seed(t, &nStart);
+      uint32_t sz = m32_stream_size(NullsResidualGet{t, seed}, uint32_t(n), scan);
+      if (tid == 0) {
+        inLen[3 * tIdx] = sz; inLen[3 * tIdx + 1] = inLen[3 * tIdx + 2] = 0;
+        a.preds[tIdx] = G4_PRED_DIFF_NULLS; a.status[tIdx] = G4_OK;
+      }
+      continue;
+    }
+    if (tid == 0) a.preds[tIdx] = 0;
     for (int p = 0; p < 3; p++) {
       PredResidualGet get{t, p + 1};
       uint32_t sz = m32_stream_size(get, uint32_t(n - 1), scan);
@@ -115,6 +135,14 @@ __global__ void __launch_bounds__(kThreads) deflate_m32_write_kernel(EncodeArgs 
     if (inLen[3 * tIdx] == 0) continue;
     const TileView t = tile_view(a.band, a.grid, tIdx);
     const int n = t.R * t.C;
+    if (a.preds[tIdx] == G4_PRED_DIFF_NULLS) {
+      int nStart;
+      const int32_t seed = nulls_seed(t, &nStart);
+      uint8_t* dst = inBuf + inOff[3 * tIdx];
+      uint32_t w = m32_stream_write(NullsResidualGet{t, seed}, uint32_t(n), dst, scan);
+      if (threadIdx.x < 16) dst[w + threadIdx.x] = 0;
+      continue;
+    }
     for (int p = 0; p < 3; p++) {
       PredResidualGet get{t, p + 1};
       uint8_t* dst = inBuf + inOff[3 * tIdx + p];
@@ -144,19 +172,24 @@ __global__ void __launch_bounds__(kThreads) deflate_pick_kernel(EncodeArgs a, co
     const int j = 3 * tIdx + win;
     const uint32_t len = best + 10u;
     const bool fits = len <= a.slotBytes;
+    const bool nulls = a.preds[tIdx] == G4_PRED_DIFF_NULLS;
+    const TileView t = tile_view(a.band, a.grid, tIdx);
+    int nStart = 0;
+    const int32_t seedNulls = nulls ? nulls_seed(t, &nStart) : 0;
+    const int predCode = nulls ? G4_PRED_DIFF_NULLS : win + 1;
     if (fits) {
       uint8_t* slot = a.slots + size_t(tIdx) * a.slotBytes;
       const uint8_t* src = outBuf + inOff[j] + 112ull * uint64_t(j);
       if (tid == 0) {
-        const TileView t = tile_view(a.band, a.grid, tIdx);
-        const uint32_t seed = uint32_t(t.at(0, 0)), nM32 = inLen[j];
+        const uint32_t seed = nulls ? uint32_t(seedNulls) : uint32_t(t.at(0, 0)), nM32 = inLen[j];
         slot[0] = uint8_t(a.codecIndex);
-        slot[1] = uint8_t(win + 1);
+        slot[1] = uint8_t(predCode);
         for (int k = 0; k < 4; k++) { slot[2 + k] = uint8_t(seed >> (8 * k)); slot[6 + k] = uint8_t(nM32 >> (8 * k)); }
       }
       for (uint32_t i = tid; i < best; i += kThreads) slot[10 + i] = src[i];
     }
-    if (tid == 0) { a.lens[tIdx] = len; a.preds[tIdx] = uint8_t(win + 1); a.status[tIdx] = fits ? G4_OK : G4_ERR_CAPACITY; }
+    __syncthreads();
+    if (tid == 0) { a.lens[tIdx] = len; a.preds[tIdx] = uint8_t(predCode); a.status[tIdx] = fits ? G4_OK : G4_ERR_CAPACITY; }
   }
 }
 

@@ -153,7 +153,7 @@ __device__ void window_flush(HuffEncShared& S, uint32_t* outWords, uint32_t bitP
 // Emit `count` residuals starting at stream index k0 (IPT consecutive per thread).  Returns false (for
 // IPT > 1 only) when the chunk cannot fit the window even after a flush; nothing is written then.
 template <int IPT>
-__device__ bool emit_chunk(HuffEncShared& S, const TileView& t, int pred, uint32_t k0, uint32_t count, uint32_t* outWords,
+__device__ bool emit_chunk(HuffEncShared& S, const TileView& t, int pred, int32_t seed, uint32_t k0, uint32_t count, uint32_t* outWords,
                            uint32_t capWords, uint32_t* bitPos, uint32_t* gbase) {
   uint64_t packed[IPT];
   int nb[IPT];
@@ -167,7 +167,7 @@ __device__ bool emit_chunk(HuffEncShared& S, const TileView& t, int pred, uint32
     if (k < k0 + count) {
       int r, c;
       stream_to_cell(pred, int(k), t.R, t.C, &r, &c);
-      int32_t res = residual_at(pred, t, r, c);
+      int32_t res = pred == G4_PRED_DIFF_NULLS ? residual_nulls_at(t, r, c, seed) : residual_at(pred, t, r, c);
       nb[j] = m32_encode(res, &packed[j]);
       for (int q = 0; q < nb[j]; q++) myBits += S.len[(packed[j] >> (8 * q)) & 0xff];
     }
@@ -237,10 +237,10 @@ __global__ void __launch_bounds__(kThreads) huffman_encode_kernel(EncodeArgs a) 
     __syncthreads();
 
     // ---- pass 1: histograms of the M32 bytes of all three predictors -------------------------------
-    bool sawNull = false;
+    bool sawNull = false, sawValid = false;
     for (int i = tid; i < n; i += kThreads) {
       int r = i / C, c = i - r * C;
-      if (t.at(r, c) == kNull) sawNull = true;
+      if (t.at(r, c) == kNull) sawNull = true; else sawValid = true;
       if (i == 0) continue;
 #pragma unroll
       for (int p = 0; p < 3; p++) {
@@ -250,10 +250,26 @@ __global__ void __launch_bounds__(kThreads) huffman_encode_kernel(EncodeArgs a) 
       }
     }
     if (sawNull) S.hasNull = 1;
-    __syncthreads();
-    if (S.hasNull) {  // TODO(next): PredictorModelDifferencingWithNulls on the GPU
-      if (tid == 0) { a.lens[tIdx] = 0; a.status[tIdx] = G4_ERR_UNSUPPORTED; a.preds[tIdx] = 0; }
+    const bool anyValid = __syncthreads_or(sawValid ? 1 : 0) != 0;
+    if (!anyValid) {  // all-null tile -> null (CodecHuffman.java:80-82)
+      if (tid == 0) { a.lens[tIdx] = 0; a.status[tIdx] = G4_DECLINED; a.preds[tIdx] = 0; }
       continue;
+    }
+    const bool hasNull = S.hasNull != 0;
+    int32_t seedNulls = 0;
+    if (hasNull) {
+      // only PredictorModelDifferencingWithNulls supports nulls (CodecHuffman.java:91-99): one candidate, kept in slot 0
+      int nStart;
+      seedNulls = nulls_seed(t, &nStart);
+      for (int i = tid; i < 3 * 256; i += kThreads) (&S.hist[0][0])[i] = 0;
+      __syncthreads();
+      for (int i = tid; i < n; i += kThreads) {
+        int r = i / C, c = i - r * C;
+        uint64_t packed;
+        int nb = m32_encode(residual_nulls_at(t, r, c, seedNulls), &packed);
+        for (int q = 0; q < nb; q++) atomicAdd(&S.hist[0][(packed >> (8 * q)) & 0xff], 1u);
+      }
+      __syncthreads();
     }
 
     // ---- rank sort of (count<<8|symbol) for the three histograms ------------------------------------
@@ -288,7 +304,7 @@ __global__ void __launch_bounds__(kThreads) huffman_encode_kernel(EncodeArgs a) 
       // CodecHuffman.java:89-112: Differencing, Linear, Triangle; keep the strictly smallest byte length
       unsigned long long best = ~0ull;
       int win = 0;
-      for (int p = 0; p < 3; p++) {
+      for (int p = 0; p < (hasNull ? 1 : 3); p++) {
         int L = S.nLeaf[p];
         unsigned long long bits = 80ull + (L == 1 ? 17ull : 8ull + 9ull * L + (L - 1) + S.textBits[p]);
         unsigned long long bytes = (bits + 7) / 8;
@@ -297,11 +313,12 @@ __global__ void __launch_bounds__(kThreads) huffman_encode_kernel(EncodeArgs a) 
       S.winner = win;
       int L = S.nLeaf[win];
       if (L >= 2) build_winner_tree(S, win, L);
-      uint32_t hdrBits = write_header_and_tree(S, a.codecIndex, win + 1, t.at(0, 0), S.nBytes[win], L,
+      const int predCode = hasNull ? G4_PRED_DIFF_NULLS : win + 1;
+      uint32_t hdrBits = write_header_and_tree(S, a.codecIndex, predCode, hasNull ? seedNulls : t.at(0, 0), S.nBytes[win], L,
                                                int(S.skey[win][255] & 0xff));
       S.scan[kWarps] = hdrBits;
       a.lens[tIdx] = uint32_t(best);
-      a.preds[tIdx] = uint8_t(win + 1);
+      a.preds[tIdx] = uint8_t(predCode);
       a.status[tIdx] = best <= a.slotBytes ? G4_OK : G4_ERR_CAPACITY;
     }
     __syncthreads();
@@ -309,15 +326,16 @@ __global__ void __launch_bounds__(kThreads) huffman_encode_kernel(EncodeArgs a) 
     const int L = S.nLeaf[win];
     uint32_t bitPos = S.scan[kWarps];
     uint32_t gbase = 0;
-    const uint32_t nRes = uint32_t(n - 1);
+    const uint32_t nRes = hasNull ? uint32_t(n) : uint32_t(n - 1);
+    const int predEmit = hasNull ? G4_PRED_DIFF_NULLS : win + 1;
     if (L >= 2) {
       // ---- pass 2: emit the winner's text --------------------------------------------------------------
       for (uint32_t k0 = 0; k0 < nRes; k0 += kThreads * kEmitItems) {
         uint32_t count = nRes - k0 < uint32_t(kThreads * kEmitItems) ? nRes - k0 : uint32_t(kThreads * kEmitItems);
-        if (!emit_chunk<kEmitItems>(S, t, win + 1, k0, count, outWords, capWords, &bitPos, &gbase)) {
+        if (!emit_chunk<kEmitItems>(S, t, predEmit, seedNulls, k0, count, outWords, capWords, &bitPos, &gbase)) {
           for (uint32_t s0 = 0; s0 < count; s0 += kThreads) {
             uint32_t c1 = count - s0 < uint32_t(kThreads) ? count - s0 : uint32_t(kThreads);
-            emit_chunk<1>(S, t, win + 1, k0 + s0, c1, outWords, capWords, &bitPos, &gbase);
+            emit_chunk<1>(S, t, predEmit, seedNulls, k0 + s0, c1, outWords, capWords, &bitPos, &gbase);
           }
         }
       }
@@ -357,7 +375,6 @@ __global__ void __launch_bounds__(kThreads) huffman_decode_kernel(DecodeArgs a) 
     uint32_t nM32 = len >= 10 ? load_le32(packing + 6) : 0;
     const uint32_t expect = pred == G4_PRED_DIFF_NULLS ? uint32_t(n) : uint32_t(n - 1);
     if (len < 12 || pred < 1 || pred > 4 || nM32 < expect || nM32 > uint32_t(6 * n)) status = G4_ERR_FORMAT;
-    else if (pred == G4_PRED_DIFF_NULLS) status = G4_ERR_UNSUPPORTED;  // TODO(next): nulls on the GPU
     if (status == G4_OK) {
       BitSrc src;
       src.init(packing + 10, len - 10);
@@ -366,13 +383,15 @@ __global__ void __launch_bounds__(kThreads) huffman_decode_kernel(DecodeArgs a) 
       if (!huffman_decode_stream(S, src, 0, nM32, m32, &endBit)) status = G4_ERR_FORMAT;
       else {
         __syncthreads();
-        if (tid == 0) t.at(0, 0) = seed;
         if (!m32_parse_to_cells(m32, nM32, pred, t, expect, S.scan)) status = G4_ERR_FORMAT;
         else {
           __syncthreads();
-          if (tid == 0) t.at(0, 0) = seed;
-          __syncthreads();
-          predictor_inverse(pred, t, S.scan);
+          if (pred == G4_PRED_DIFF_NULLS) predictor_inverse_nulls(t, seed);
+          else {
+            if (tid == 0) t.at(0, 0) = seed;
+            __syncthreads();
+            predictor_inverse(pred, t, S.scan);
+          }
         }
       }
     }

@@ -207,4 +207,70 @@ __device__ inline void predictor_inverse(int pred, const TileView& t, uint32_t* 
   __syncthreads();
 }
 
+// ---- PredictorModelDifferencingWithNulls (compress/PredictorModelDifferencingWithNulls.java:66-269) -------------------
+// The predecessor of cell (r,c) is the previous cell of the row, or for c == 0 the first cell of the previous row;
+// when that predecessor is null (or for cell (0,0)) the prediction restarts from the seed.  Null cells are coded as
+// INT_MIN.  All of it is pointwise on the ORIGINAL values, so the encode side needs no scan.
+
+// Seed = floor(mean of every valid value whose predecessor is null (or missing) + 0.5), evaluated in FP64 like the
+// reference (:79-106).  *nStart = number of such values (0 -> the model declines).  All threads call.
+__device__ inline int32_t nulls_seed(const TileView& t, int* nStart) {
+  __shared__ unsigned long long sSum;
+  __shared__ unsigned int sCnt;
+  __syncthreads();
+  if (threadIdx.x == 0) { sSum = 0; sCnt = 0; }
+  __syncthreads();
+  long long sum = 0;
+  unsigned int cnt = 0;
+  const int n = t.R * t.C;
+  for (int i = threadIdx.x; i < n; i += kThreads) {
+    const int r = i / t.C, c = i - r * t.C;
+    const int32_t v = t.at(r, c);
+    if (v == kNull) continue;
+    const bool starts = c > 0 ? t.at(r, c - 1) == kNull : (r == 0 ? true : t.at(r - 1, 0) == kNull);
+    if (starts) { sum += v; cnt++; }
+  }
+  if (cnt) { atomicAdd(&sSum, (unsigned long long)sum); atomicAdd(&sCnt, cnt); }
+  __syncthreads();
+  *nStart = int(sCnt);
+  if (sCnt == 0) return 0;
+  const double avg = double((long long)sSum) / double(sCnt);
+  return int32_t(floor(avg + 0.5));  // values are ints, so the mean is inside the int range
+}
+
+// Residual of cell (r,c) (one per cell, INT_MIN for a null cell).
+__device__ __forceinline__ int32_t residual_nulls_at(const TileView& t, int r, int c, int32_t seed) {
+  const int32_t v = t.at(r, c);
+  if (v == kNull) return kNull;
+  int32_t prior = seed;
+  if (c > 0) { int32_t p = t.at(r, c - 1); if (p != kNull) prior = p; }
+  else if (r > 0) { int32_t p = t.at(r - 1, 0); if (p != kNull) prior = p; }
+  return int32_t(uint32_t(v) - uint32_t(prior));  // (int)(long delta) wraps
+}
+
+// Inverse, in place: every cell holds its residual.  Tiles with nulls are the rare path, so this is the plain
+// restatement: column 0 serially, then one thread per row.  All threads call.
+__device__ inline void predictor_inverse_nulls(const TileView& t, int32_t seed) {
+  __syncthreads();
+  if (threadIdx.x == 0) {
+    int32_t prior = seed;
+    for (int r = 0; r < t.R; r++) {
+      const int32_t res = t.at(r, 0);
+      if (res == kNull) prior = seed;  // a null first cell: the next row restarts from the seed
+      else { prior = int32_t(uint32_t(prior) + uint32_t(res)); t.at(r, 0) = prior; }
+    }
+  }
+  __syncthreads();
+  for (int r = threadIdx.x; r < t.R; r += kThreads) {
+    int32_t* row = t.row(r);
+    int32_t prior = row[0] == kNull ? seed : row[0];
+    for (int c = 1; c < t.C; c++) {
+      const int32_t res = row[c];
+      if (res == kNull) prior = seed;
+      else { prior = int32_t(uint32_t(prior) + uint32_t(res)); row[c] = prior; }
+    }
+  }
+  __syncthreads();
+}
+
 }  // namespace g4
