@@ -1,20 +1,20 @@
 #!/usr/bin/env python3
 """bench.py -- GVRS tile decode/encode throughput (BASELINE.json metric) on N B200s of one node.
 
-Workload (N=1 and per rank at N>1, weak scaling): the per-GPU shard of BASELINE.json config 3 --
-30 tile rows x 360 tile columns = 10,800 tiles of 180x240 int32 samples (5,400 x 86,400 samples,
-1.866 GB raw) of the synthetic fractal terrain (include/g4terrain.h), rank r holding tile rows
-[30r, 30r+30) of the 240-row global grid.  Codec list = config 3's [GvrsHuffman, GvrsDeflate, LSOP12]
-restricted to the codecs whose CUDA kernels exist (named in config.workload).
+Default workload (N=1 and per rank at N>1, weak scaling): the per-GPU shard of BASELINE.json config 3 --
+30 tile rows x 360 tile columns = 10,800 tiles of 180x240 int32 samples (5,400 x 86,400 samples, 1.866 GB raw)
+of the synthetic fractal terrain (include/g4terrain.h); rank r holds tile rows [30r, 30r+30) of the 240-row
+global grid; codec list [GvrsHuffman, GvrsDeflate, LSOP12] with best-of selection (CodecMaster rule).
+`--config 1|2|4|5` runs the other BASELINE.json configs (parity-test / report cases, not the headline line).
 
-A step = one decode pass over the shard (the headline direction).  `value` = 4 B x samples / device
-time with compressed payloads resident in HBM; `e2e` = the same through g4_decode_tiles with HOST
-(pinned) buffers, H2D of the payloads and D2H of the decoded raster inside the timed region.
-Encode throughput of the same shard is reported in `encode`.
+A step = one decode pass over the shard (the headline direction).  `value` = 4 B x samples / device time with the
+compressed payloads resident in HBM; `e2e` = the same through g4_decode_tiles with HOST (pinned) buffers, H2D of
+the payloads and D2H of the decoded raster inside the timed region.  Encode throughput of the same shard is
+reported in `encode`.
 
---impl reference: the reference's algorithm on the host cores.  The reference is Java and no JVM exists
-in this image, so this arm times the C++ oracle (oracle/, a line-by-line restatement) with a tile thread
-pool over all host cores on a bounded sample of the same workload.
+--impl reference: the reference's algorithm on the host cores.  The reference is Java and no JVM exists in this
+image, so this arm times the C++ oracle (oracle/, a line-by-line restatement) with a tile thread pool over all host
+cores on a bounded sample of the same workload.
 """
 import argparse
 import json
@@ -29,11 +29,22 @@ import numpy as np
 ROOT = os.path.dirname(os.path.abspath(__file__))
 sys.path.insert(0, ROOT)
 
-TILE_R, TILE_C = 180, 240
-TILE_ROWS_PER_GPU, TILES_ACROSS = 30, 360
-GLOBAL_TILE_ROWS = 240
-CONFIG3 = ["GvrsHuffman", "GvrsDeflate", "LSOP12"]
 ORACLE_IDS = {"GvrsHuffman": 0, "GvrsDeflate": 1, "GvrsFloat": 2, "GvrsCanonicalHuffman": 3, "LSOP12": 4}
+GLOBAL_TILE_ROWS = 240  # config 3: 43200 / 180
+
+# per-GPU workloads; `rows`/`cols` are the samples one GPU holds
+CONFIGS = {
+    1: dict(name="config1: int32 4320x8640 (GEBCO 5-arcmin shape), 90x120 tiles", rows=4320, cols=8640, tr=90, tc=120, dtype="int32",
+            codecs=["GvrsHuffman", "GvrsDeflate"]),
+    2: dict(name="config2: int32 4320x8640, 90x120 tiles, LSOP12 only", rows=4320, cols=8640, tr=90, tc=120, dtype="int32",
+            codecs=["LSOP12"]),
+    3: dict(name="config3 per-GPU shard: 10800 tiles of 180x240 int32 (5400 x 86400 samples)", rows=5400, cols=86400, tr=180, tc=240,
+            dtype="int32", codecs=["GvrsHuffman", "GvrsDeflate", "LSOP12"]),
+    4: dict(name="config4: float32 10800x21600 (ETOPO shape), 120x120 tiles, CodecFloat", rows=10800, cols=21600, tr=120, tc=120,
+            dtype="float32", codecs=["GvrsFloat"]),
+}
+SWEEP_TILES = [(60, 60), (90, 120), (120, 120), (128, 128), (180, 240), (256, 256), (512, 512)]
+SWEEP_GRID = (23040, 7680)  # rows = lcm of the tile heights, cols = lcm of the tile widths; 0.71 GB raw per GPU
 METRIC = "GVRS tile decode GB/s of raw samples (config 3 shard, 180x240 tiles)"
 
 
@@ -42,6 +53,14 @@ def peaks():
     if os.path.exists(p):
         return float(json.load(open(p))["hbm_gbs"]), "measured (MEASURED_PEAKS.json)"
     return 6650.0, "fallback (B200_PROFILING.md)"
+
+
+def profiled_traffic():
+    """DRAM bytes per decode launch set from the committed ncu capture (profiles/decode_traffic.json), or None."""
+    p = os.path.join(ROOT, "profiles", "decode_traffic.json")
+    if os.path.exists(p):
+        return json.load(open(p))
+    return None
 
 
 class ClockSampler(threading.Thread):
@@ -56,7 +75,7 @@ class ClockSampler(threading.Thread):
              "clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap")
         try:
             self.proc = subprocess.Popen(["nvidia-smi", "-i", str(self.index), "--query-gpu=" + q, "--format=csv,noheader,nounits",
-                                          "-lms", "100"], stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
+                                          "-lms", "50"], stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
             for line in self.proc.stdout:
                 if self.stop_flag:
                     break
@@ -76,58 +95,118 @@ class ClockSampler(threading.Thread):
                 "samples": len(sm)}
 
 
-def cpu_arm(codecs, threads, budget_s, oracle):
-    """Times the oracle's decode (and encode) of a bounded sample: whole tile columns of the shard's first tile row."""
-    ids = [ORACLE_IDS[c] for c in codecs]
-    n_tiles = 24
+def cpu_arm(cfg, threads, budget_s, oracle):
+    """Times the oracle's decode (and encode) of a bounded sample: whole tile columns of the workload's first tile row."""
+    ids = [ORACLE_IDS[c] for c in cfg["codecs"]]
+    tr, tc = cfg["tr"], cfg["tc"]
+    across = cfg["cols"] // tc
+    is_f = cfg["dtype"] == "float32"
+    n_tiles = min(across, 24)
     while True:
-        grid = oracle.terrain_i32(0, 0, TILE_R, n_tiles * TILE_C, n_threads=threads)
+        gen = oracle.terrain_f32 if is_f else oracle.terrain_i32
+        grid = gen(0, 0, tr, n_tiles * tc, n_threads=threads)
         t0 = time.perf_counter()
-        arena, slot, lens = oracle.encode_grid(ids, grid, TILE_R, TILE_C, n_threads=threads)
+        arena, slot, lens = oracle.encode_grid(ids, grid, tr, tc, n_threads=threads)
         t_enc = time.perf_counter() - t0
         off = (np.arange(lens.size) * slot).astype(np.uint64)
         t0 = time.perf_counter()
-        out = oracle.decode_grid(ids, arena, off, lens, TILE_R, n_tiles * TILE_C, TILE_R, TILE_C, n_threads=threads)
+        out = oracle.decode_grid(ids, arena, off, lens, tr, n_tiles * tc, tr, tc, dtype=np.float32 if is_f else np.int32, n_threads=threads)
         t_dec = time.perf_counter() - t0
-        assert np.array_equal(out, grid)
-        if t_enc + t_dec > budget_s / 4 or n_tiles >= TILES_ACROSS:
+        assert np.array_equal(out.view(np.uint32), grid.view(np.uint32))
+        if t_enc + t_dec > budget_s / 4 or n_tiles >= across:
             break
-        n_tiles = min(TILES_ACROSS, n_tiles * 4)
+        n_tiles = min(across, n_tiles * 4)
     raw = grid.size * 4
     return {"decode_gbs": raw / t_dec / 1e9, "encode_gbs": raw / t_enc / 1e9, "tiles": n_tiles, "dec_s": t_dec, "enc_s": t_enc,
             "bits_per_sample": 8.0 * float(lens.sum()) / grid.size}
 
 
-def run_reference(args, rank):
+def run_reference(args, rank, cfg):
     if rank != 0:
         return
     from oracle import g4oracle as oracle
 
     oracle.build()
     threads = oracle.hardware_threads()
-    codecs = CONFIG3
     vals = []
     res = None
     for _ in range(args.warmup):
-        res = cpu_arm(codecs, threads, 6.0, oracle)
+        res = cpu_arm(cfg, threads, 6.0, oracle)
     t0 = time.perf_counter()
     for _ in range(args.steps):
-        res = cpu_arm(codecs, threads, 6.0, oracle)
+        res = cpu_arm(cfg, threads, 6.0, oracle)
         vals.append(res["decode_gbs"])
     wall = time.perf_counter() - t0
     v = float(np.mean(vals))
-    sample = "%d tiles of 180x240 (first tile row of the shard) per step, decode timed separately from encode" % res["tiles"]
+    sample = "%d tiles of %dx%d (first tile row of the workload) per step, decode timed separately from encode" % (
+        res["tiles"], cfg["tr"], cfg["tc"])
+    metric = METRIC if args.config == 3 else "GVRS tile decode GB/s of raw samples (%s)" % cfg["name"].split(":")[0]
     line = {
-        "impl": "reference", "metric": METRIC, "value": v, "unit": "GB/s", "n_gpus": args.gpus, "steps": args.steps,
+        "impl": "reference", "metric": metric, "value": v, "unit": "GB/s", "n_gpus": args.gpus, "steps": args.steps,
         "warmup": args.warmup, "ms_per_step": 1000.0 * wall / max(1, args.steps), "higher_is_better": True, "scaling": "weak",
-        "vs_baseline": None, "dtype": "int32", "data": "synthetic",
-        "config": {"workload": "config3 shard sample, codecs=%s, C++ restatement of the reference (no JVM in this image), tile "
-                               "thread pool" % "+".join(codecs)},
+        "vs_baseline": None, "dtype": cfg["dtype"], "data": "synthetic",
+        "config": {"workload": "%s, codecs=%s; C++ restatement of the reference (no JVM in this image), tile thread pool" % (
+            cfg["name"], "+".join(cfg["codecs"]))},
         "cpu_baseline": {"value": v, "unit": "GB/s", "cores": threads, "kind": "port", "sample": sample,
                          "encode_value": res["encode_gbs"], "bits_per_sample": res["bits_per_sample"]},
         "e2e": {"value": v, "unit": "GB/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
     }
     print(json.dumps(line))
+
+
+def build_master(g4, L, cfg, ctx):
+    codecs = [c for c in cfg["codecs"] if L.g4_codec_supported(ORACLE_IDS[c], 0) and L.g4_codec_supported(ORACLE_IDS[c], 1)]
+    missing = [c for c in cfg["codecs"] if c not in codecs]
+    spec = g4.CodecSpecification(default=False)
+    std = {"GvrsHuffman": (g4.CodecHuffman, g4.CodecHuffman), "GvrsDeflate": (g4.CodecDeflate, g4.CodecDeflate),
+           "GvrsFloat": (g4.CodecFloat, g4.CodecFloat), "GvrsCanonicalHuffman": (g4.CodecCanonHuffman, g4.CodecCanonHuffman),
+           "LSOP12": (g4.LsEncoder12, g4.LsDecoder12)}
+    for c in codecs:
+        spec.addCompressionCodec(c, *std[c])
+    return g4.CodecMaster(spec, ctx), codecs, missing
+
+
+def run_sweep(args, torch, dist, g4, L, ctx, dev, stream, rank, world, barrier):
+    """Config 5: decode-only GB/s per tile size on one fixed grid (all sizes divide it), config-3 codec list."""
+    rows, cols = SWEEP_GRID
+    grid = torch.empty((rows, cols), dtype=torch.int32, device=dev)
+    ctx.fill_terrain(grid.data_ptr(), 0, rank * rows, 0, rows, cols)
+    peak, peak_src = peaks()
+    out = torch.empty_like(grid)
+    sweep = []
+    for tr, tc in SWEEP_TILES:
+        cfg = dict(CONFIGS[3], tr=tr, tc=tc)
+        master, codecs, _ = build_master(g4, L, cfg, ctx)
+        batch = master.encodeTiles(grid, tr, tc)
+        for _ in range(args.warmup):
+            master.decodeTiles(batch, out=out)
+        torch.cuda.synchronize(dev)
+        assert torch.equal(out, grid), "decode does not reproduce the input raster (%dx%d)" % (tr, tc)
+        barrier()
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record(stream)
+        for _ in range(args.steps):
+            master.decodeTiles(batch, out=out)
+        e1.record(stream)
+        barrier()
+        t = torch.tensor([e0.elapsed_time(e1) / 1000.0], dtype=torch.float64, device=dev)
+        if world > 1:
+            dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        lens = batch.lens.cpu().numpy().astype(np.int64)
+        hist = np.bincount(batch.codec.cpu().numpy(), minlength=256)
+        gbs = 4.0 * rows * cols * world * args.steps / float(t[0]) / 1e9
+        bps = 8.0 * float(lens.sum()) / (rows * cols)
+        sweep.append({"tile": "%dx%d" % (tr, tc), "decode_gbs": gbs, "ms_per_step": 1000.0 * float(t[0]) / args.steps,
+                      "bits_per_sample": bps, "hbm_frac_per_gpu": (4.0 + bps / 8.0) / 4.0 * gbs / world / peak,
+                      "tile_choice": {c: int(hist[k]) for k, c in enumerate(codecs)} | {"raw": int(hist[255])}})
+    if rank == 0:
+        best = max(sweep, key=lambda s: s["decode_gbs"])
+        print(json.dumps({"metric": "GVRS tile decode GB/s of raw samples (config 5 tile-size sweep)", "value": best["decode_gbs"],
+                          "unit": "GB/s", "n_gpus": world, "steps": args.steps, "warmup": args.warmup, "ms_per_step": best["ms_per_step"],
+                          "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "int32", "data": "synthetic",
+                          "config": {"workload": "config5: decode-only tile-size sweep on %dx%d int32 per GPU, codecs=%s; value = best size (%s)" % (
+                              rows, cols, "+".join(CONFIGS[3]["codecs"]), best["tile"]), "l2": "inputs larger than L2"},
+                          "peak": peak, "peak_source": peak_src, "sweep": sweep}))
 
 
 def main():
@@ -136,7 +215,8 @@ def main():
     ap.add_argument("--steps", type=int, default=10)
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="ours")
-    ap.add_argument("--tile-rows", type=int, default=TILE_ROWS_PER_GPU, help="tile rows per GPU (default: the config-3 shard)")
+    ap.add_argument("--config", type=int, default=3, choices=[1, 2, 3, 4, 5])
+    ap.add_argument("--tile-rows", type=int, default=0, help="tile rows per GPU (default: the config's own)")
     ap.add_argument("--cpu-seconds", type=float, default=12.0)
     ap.add_argument("--no-e2e", action="store_true")
     args = ap.parse_args()
@@ -144,8 +224,11 @@ def main():
     rank = int(os.environ.get("RANK", "0"))
     local_rank = int(os.environ.get("LOCAL_RANK", "0"))
     world = int(os.environ.get("WORLD_SIZE", "1"))
+    cfg = dict(CONFIGS[3 if args.config == 5 else args.config])
+    if args.tile_rows:
+        cfg["rows"] = args.tile_rows * cfg["tr"]
     if args.impl == "reference":
-        run_reference(args, rank)
+        run_reference(args, rank, cfg)
         return
 
     import torch
@@ -160,33 +243,39 @@ def main():
         os.environ.setdefault("MASTER_ADDR", "127.0.0.1")
         dist.init_process_group("nccl", device_id=dev)
     L = _lib.lib()
-    codecs = [c for c in CONFIG3 if L.g4_codec_supported(ORACLE_IDS[c], 0) and L.g4_codec_supported(ORACLE_IDS[c], 1)]
-    missing = [c for c in CONFIG3 if c not in codecs]
-    spec = g4.CodecSpecification(default=False)
-    std = {"GvrsHuffman": (g4.CodecHuffman, g4.CodecHuffman), "GvrsDeflate": (g4.CodecDeflate, g4.CodecDeflate),
-           "LSOP12": (g4.LsEncoder12, g4.LsDecoder12)}
-    for c in codecs:
-        spec.addCompressionCodec(c, *std[c])
     # the context launches on torch's current stream so torch.cuda.Event brackets exactly the library's kernels
     stream = torch.cuda.Stream(dev)
     torch.cuda.set_stream(stream)
     ctx = g4.Context(local_rank, stream.cuda_stream)
-    master = g4.CodecMaster(spec, ctx)
-
-    rows, cols = args.tile_rows * TILE_R, TILES_ACROSS * TILE_C
-    n_tiles = args.tile_rows * TILES_ACROSS
-    samples = rows * cols
-    grid = torch.empty((rows, cols), dtype=torch.int32, device=dev)
-    # weak scaling: every rank holds one 30-tile-row band of the 240-tile-row global grid (rank r = band r at N = 8)
-    first_tile_row, _ = g4.shard_tile_rows(GLOBAL_TILE_ROWS, GLOBAL_TILE_ROWS // args.tile_rows, rank % (GLOBAL_TILE_ROWS // args.tile_rows))
-    row0 = first_tile_row * TILE_R
-    ctx.fill_terrain(grid.data_ptr(), 0, row0, 0, rows, cols)
-    torch.cuda.synchronize(dev)
 
     def barrier():
         if world > 1:
             dist.barrier()
         torch.cuda.synchronize(dev)
+
+    if args.config == 5:
+        run_sweep(args, torch, dist, g4, L, ctx, dev, stream, rank, world, barrier)
+        if world > 1:
+            dist.destroy_process_group()
+        return
+
+    master, codecs, missing = build_master(g4, L, cfg, ctx)
+    TILE_R, TILE_C = cfg["tr"], cfg["tc"]
+    rows, cols = cfg["rows"], cfg["cols"]
+    tile_rows = rows // TILE_R
+    n_tiles = tile_rows * (cols // TILE_C)
+    samples = rows * cols
+    is_f = cfg["dtype"] == "float32"
+    grid = torch.empty((rows, cols), dtype=torch.float32 if is_f else torch.int32, device=dev)
+    if args.config == 3:
+        # weak scaling: every rank holds one 30-tile-row band of the 240-tile-row global grid (rank r = band r at N = 8)
+        bands = max(1, GLOBAL_TILE_ROWS // tile_rows)
+        first_tile_row, _ = g4.shard_tile_rows(GLOBAL_TILE_ROWS, bands, rank % bands)
+        row0 = first_tile_row * TILE_R
+    else:
+        row0 = rank * rows
+    ctx.fill_terrain(grid.data_ptr(), 1 if is_f else 0, row0, 0, rows, cols)
+    torch.cuda.synchronize(dev)
 
     # ---- encode (also produces the decode input) --------------------------------------------------------
     ctx.set_timing(True)
@@ -202,7 +291,8 @@ def main():
         enc_ms.append(e0.elapsed_time(e1))
     enc_kernel_ms = {c: ctx.kernel_time_ms(1, ORACLE_IDS[c]) for c in codecs}
     lens = batch.lens.cpu().numpy().astype(np.int64)
-    codec_hist = np.bincount(batch.codec.cpu().numpy(), minlength=256)
+    codec_of_tile = batch.codec.cpu().numpy()
+    codec_hist = np.bincount(codec_of_tile, minlength=256)
     total_payload = int(lens.sum())
     bits_per_sample = 8.0 * total_payload / samples
     out = torch.zeros_like(grid)
@@ -212,7 +302,7 @@ def main():
     for _ in range(args.warmup):
         master.decodeTiles(batch, out=out)
     torch.cuda.synchronize(dev)
-    assert torch.equal(out, grid), "decode does not reproduce the input raster"
+    assert torch.equal(out.view(torch.int32), grid.view(torch.int32)), "decode does not reproduce the input raster"
     launches_per_step = (ctx.launch_count - launches0) // args.warmup
     sampler = ClockSampler(local_rank)
     sampler.start()
@@ -245,7 +335,7 @@ def main():
         h_arena.copy_(batch.arena[: batch.total_bytes])
         h_off = batch.offsets.cpu().numpy().astype(np.uint64)
         h_len = batch.lens.cpu().numpy().astype(np.uint32)
-        h_grid = torch.empty((rows, cols), dtype=torch.int32).pin_memory()
+        h_grid = torch.empty((rows, cols), dtype=grid.dtype).pin_memory()
         hb = g4.TileBatch(h_arena.numpy(), h_off, h_len, None, None, None, batch.total_bytes, batch.band)
         e2e_steps = max(2, min(args.steps, 4))
         master.decodeTiles(hb, out=h_grid.numpy())
@@ -260,7 +350,7 @@ def main():
         tt = torch.tensor([t_e2e], dtype=torch.float64, device=dev)
         if world > 1:
             dist.all_reduce(tt, op=dist.ReduceOp.MAX)
-        assert np.array_equal(h_grid.numpy()[:TILE_R], grid[:TILE_R].cpu().numpy())
+        assert np.array_equal(h_grid.numpy()[:TILE_R].view(np.uint32), grid[:TILE_R].cpu().numpy().view(np.uint32))
         e2e = {"value": 4.0 * samples * world * e2e_steps / float(tt[0]) / 1e9, "unit": "GB/s",
                "h2d_bytes_per_step": int(batch.total_bytes + h_off.nbytes + h_len.nbytes),
                "d2h_bytes_per_step": int(samples * 4 + n_tiles * 4), "steps": e2e_steps}
@@ -269,7 +359,7 @@ def main():
         if world > 1:
             dist.destroy_process_group()
         return
-    # ---- roofline of the dominant decode kernel ----------------------------------------------------------------
+    # ---- roofline of the dominant decode kernel set ------------------------------------------------------------
     peak, peak_src = peaks()
     dom = max(kernel_ms, key=lambda c: np.mean(kernel_ms[c])) if kernel_ms else None
     roofline = None
@@ -277,13 +367,17 @@ def main():
         kind = ORACLE_IDS[dom]
         idx = [k for k, c in enumerate(codecs) if c == dom][0]
         tiles_dom = int(codec_hist[idx])
-        bytes_dom = int(lens[batch.codec.cpu().numpy() == idx].sum())
+        bytes_dom = int(lens[codec_of_tile == idx].sum())
         alg_bytes = 4.0 * tiles_dom * TILE_R * TILE_C + bytes_dom  # raw samples written once + payload read once
         ms = float(np.mean(kernel_ms[dom]))
         achieved = alg_bytes / (ms / 1000.0) / 1e9
-        roofline = {"bound": "hbm", "kernel": "%s decode" % dom, "achieved": achieved, "peak": peak, "unit": "GB/s",
-                    "frac": achieved / peak, "traffic": None, "peak_source": peak_src, "kernel_ms": ms,
-                    "algorithmic_bytes_per_launch": alg_bytes, "kind": kind}
+        traffic = None
+        tr_prof = profiled_traffic()
+        if tr_prof and tr_prof.get("codec") == dom and args.config == 3 and not args.tile_rows:
+            traffic = tr_prof["dram_bytes_per_launch_set"]
+        roofline = {"bound": "hbm", "kernel": "%s decode (its kernels, bracketed by CUDA events on the launching stream)" % dom,
+                    "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak, "traffic": traffic,
+                    "peak_source": peak_src, "kernel_ms": ms, "algorithmic_bytes_per_launch": alg_bytes, "kind": kind}
     # ---- CPU baseline (rank 0, N=1 only) ------------------------------------------------------------------------
     cpu = None
     if world == 1:
@@ -291,21 +385,23 @@ def main():
 
         oracle.build()
         threads = oracle.hardware_threads()
-        r1 = cpu_arm(codecs, 1, args.cpu_seconds / 3, oracle)
-        rn = cpu_arm(codecs, threads, args.cpu_seconds / 2, oracle)
+        ccfg = dict(cfg, codecs=codecs)
+        r1 = cpu_arm(ccfg, 1, args.cpu_seconds / 3, oracle)
+        rn = cpu_arm(ccfg, threads, args.cpu_seconds / 2, oracle)
         cpu = {"value": rn["decode_gbs"], "unit": "GB/s", "cores": threads, "kind": "port",
-               "sample": "%d tiles of 180x240 from the shard's first tile row; oracle = C++ restatement of the Java reference "
-                         "(no JVM in this image)" % rn["tiles"],
+               "sample": "%d tiles of %dx%d from the workload's first tile row; oracle = C++ restatement of the Java reference "
+                         "(no JVM in this image)" % (rn["tiles"], TILE_R, TILE_C),
                "single_thread_value": r1["decode_gbs"], "encode_value": rn["encode_gbs"],
                "encode_single_thread_value": r1["encode_gbs"], "bits_per_sample": rn["bits_per_sample"]}
+    metric = METRIC if args.config == 3 else "GVRS tile decode GB/s of raw samples (%s)" % cfg["name"].split(":")[0]
     line = {
-        "metric": METRIC, "value": value, "unit": "GB/s", "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
+        "metric": metric, "value": value, "unit": "GB/s", "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
         "ms_per_step": 1000.0 * t_dec / args.steps, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
-        "dtype": "int32", "data": "synthetic",
-        "config": {"workload": "config3 per-GPU shard: %d tiles of %dx%d int32 (%d x %d samples), codecs=%s%s" % (
-            n_tiles, TILE_R, TILE_C, rows, cols, "+".join(codecs), (" (not yet on the GPU: %s)" % "+".join(missing)) if missing else ""),
-            "l2": "inputs larger than L2 (payload %.0f MB + raster %.0f MB per step)" % (total_payload / 1e6, samples * 4 / 1e6),
-            "tile_choice": {c: int(codec_hist[k]) for k, c in enumerate(codecs)} | {"raw": int(codec_hist[255])}},
+        "dtype": cfg["dtype"], "data": "synthetic",
+        "config": {"workload": "%s, codecs=%s%s" % (cfg["name"], "+".join(codecs),
+                                                    (" (not yet on the GPU: %s)" % "+".join(missing)) if missing else ""),
+                   "l2": "inputs larger than L2 (payload %.0f MB + raster %.0f MB per step)" % (total_payload / 1e6, samples * 4 / 1e6),
+                   "tile_choice": {c: int(codec_hist[k]) for k, c in enumerate(codecs)} | {"raw": int(codec_hist[255])}},
         "bits_per_sample": bits_per_sample,
         "encode": {"value": enc_value, "unit": "GB/s", "ms": 1000.0 * t_enc, "kernel_ms": enc_kernel_ms},
         "roofline": roofline, "cpu_baseline": cpu, "e2e": e2e, "gpu_launches": int(launches_per_step * args.steps),
