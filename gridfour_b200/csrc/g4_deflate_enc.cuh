@@ -473,19 +473,25 @@ G4_HD inline uint32_t deflate_stream(const uint8_t* in, uint32_t n, uint8_t* out
       const uint8_t* scan = in + strstart;
       uint8_t scanEnd1 = scan[bestLen - 1], scanEnd = scan[bestLen];
       uint32_t cur = hashHead;
-      do {
+      // The next chain link is loaded BEFORE the candidate is examined: both loads depend only on `cur`, and a GPU
+      // thread does not speculate past the candidate's branches, so this halves the dependent memory latency per link.
+      for (;;) {
+        const uint32_t nextLink = W->prev[cur & kDefWMask];
         const uint8_t* match = in + cur;
-        if (match[bestLen] != scanEnd || match[bestLen - 1] != scanEnd1 || match[0] != scan[0] || match[1] != scan[1]) continue;
-        int len = 2;
-        while (len < maxLen && scan[len] == match[len]) len++;
-        if (len > bestLen) {
-          matchStart = cur;
-          bestLen = len;
-          if (len >= niceMatch) break;
-          scanEnd1 = scan[bestLen - 1];
-          scanEnd = scan[bestLen];
+        if (match[bestLen] == scanEnd && match[bestLen - 1] == scanEnd1 && match[0] == scan[0] && match[1] == scan[1]) {
+          int len = 2;
+          while (len < maxLen && scan[len] == match[len]) len++;
+          if (len > bestLen) {
+            matchStart = cur;
+            bestLen = len;
+            if (len >= niceMatch) break;
+            scanEnd1 = scan[bestLen - 1];
+            scanEnd = scan[bestLen];
+          }
         }
-      } while ((cur = W->prev[cur & kDefWMask]) > limit && --chainLength != 0);
+        cur = nextLink;
+        if (!(cur > limit && --chainLength != 0)) break;
+      }
       matchLength = uint32_t(bestLen) <= lookahead ? bestLen : int(lookahead);
       if (matchLength <= 5 && (matchLength == kDefMinMatch && strstart - matchStart > uint32_t(kDefTooFar))) matchLength = kDefMinMatch - 1;
     }

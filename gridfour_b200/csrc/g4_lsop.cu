@@ -11,6 +11,7 @@
 //      Cells with equal c+3r are independent: lane l owns row r0+l and runs three columns behind lane l-1.
 //      Row r-1/r-2 operands travel between lanes by warp shuffles; the two last columns of every row
 //      (Triangle predictor) ride the same schedule.  Float arithmetic is strictly left to right, no FMA.
+#include <utility>
 #include "g4_kernels.h"
 #include "g4_predict.cuh"
 #include "g4_huffdec.cuh"
@@ -950,16 +951,23 @@ __host__ __device__ constexpr int moment_j(int q) {
   return i + k;
 }
 
+// One accumulated quantity with COMPILE-TIME indices: `constexpr int i = moment_i(Q)` forces the index arithmetic out
+// of the kernel, and z[] stays in registers (a run-time index would send it to local memory).
+template <int Q>
+__device__ __forceinline__ double moment_term(const double (&z)[13]) {
+  if constexpr (Q < 13) return z[Q];
+  else {
+    constexpr int i = moment_i(Q), j = moment_j(Q);
+    return z[i] * z[j];
+  }
+}
+template <int ROLE, int... A>
+__device__ __forceinline__ void moment_accumulate_seq(const double (&z)[13], double (&acc)[kMomentPerRole], std::integer_sequence<int, A...>) {
+  ((acc[A] += moment_term<A * 4 + ROLE>(z)), ...);
+}
 template <int ROLE>
 __device__ __forceinline__ void moment_accumulate(const double (&z)[13], double (&acc)[kMomentPerRole]) {
-#pragma unroll
-  for (int a = 0; a < kMomentPerRole; a++) {
-    constexpr int dummy = 0;
-    (void)dummy;
-    const int q = a * 4 + ROLE;
-    if (q < 13) acc[a] += z[q];
-    else acc[a] += z[moment_i(q)] * z[moment_j(q)];
-  }
+  moment_accumulate_seq<ROLE>(z, acc, std::make_integer_sequence<int, kMomentPerRole>{});
 }
 
 struct LsopEncShared {
