@@ -21,8 +21,14 @@ namespace g4 {
 constexpr int kFastStageWords = 7168;  // 28 KB of packing (5.3 bits/sample for a 180x240 tile)
 constexpr int kFastMaxSub = 1280;
 constexpr int kFastRounds = kFastMaxSub / kThreads;
-constexpr uint32_t kFastSubBits = 160;   // target sub-sequence size
-constexpr uint32_t kFastLookback = 48;   // pass 0 starts this many bits before the limit
+#ifndef G4_FAST_SUBBITS
+#define G4_FAST_SUBBITS 160
+#endif
+#ifndef G4_FAST_LOOKBACK
+#define G4_FAST_LOOKBACK 48
+#endif
+constexpr uint32_t kFastSubBits = G4_FAST_SUBBITS;    // target sub-sequence size
+constexpr uint32_t kFastLookback = G4_FAST_LOOKBACK;  // pass 0 starts this many bits before the limit
 constexpr int kFastLutBits = 11;
 constexpr uint32_t kFastSpecial = 0x8000u;  // LUT flag: symbol >= 256 (null, escapes, end of text)
 
