@@ -16,6 +16,8 @@ using namespace g4;
 
 namespace {
 
+constexpr int kMaxChunks = 16;  // host-buffer decode pipeline depth (g4_decode_tiles, G4_MEM_HOST)
+
 thread_local std::string tlsError;
 
 int cuda_fail(cudaError_t e, const char* what) {
@@ -76,6 +78,9 @@ struct g4_context {
   bool lsopDeflate = true;  // LsEncoder12.deflateEnabled (lsop/LsEncoder12.java:78)
   // staging used by the host-memory entry points
   DevBuf sGrid, sArena, sOffsets, sLens, sCodec, sPred, sStatus;
+  // host-buffer decode pipeline: payload H2D / kernels / raster D2H of consecutive chunks overlap
+  cudaStream_t copyIn = nullptr, copyOut = nullptr;
+  cudaEvent_t evIn[16] = {}, evDone[16] = {}, evStart = nullptr;
   // optional per-kernel timing (CUDA events on the launching stream): [0]=decode, [1]=encode, by codec kind
   bool timing = false;
   cudaEvent_t ev[2][G4_CODEC_COUNT + 1][2] = {};
@@ -472,6 +477,7 @@ int g4_context_create(int device, void* cuda_stream, g4_context** out) {
     CK(cudaStreamCreateWithFlags(&ctx->stream, cudaStreamNonBlocking));
     ctx->ownStream = true;
   }
+  CK(cudaEventCreateWithFlags(&ctx->evStart, cudaEventDisableTiming));
   *out = ctx;
   return G4_OK;
 }
@@ -480,6 +486,14 @@ void g4_context_destroy(g4_context* ctx) {
   if (!ctx) return;
   cudaSetDevice(ctx->device);
   cudaStreamSynchronize(ctx->stream);
+  if (ctx->copyIn) {
+    cudaStreamSynchronize(ctx->copyIn);
+    cudaStreamSynchronize(ctx->copyOut);
+    cudaStreamDestroy(ctx->copyIn);
+    cudaStreamDestroy(ctx->copyOut);
+    for (int k = 0; k < kMaxChunks; k++) { cudaEventDestroy(ctx->evIn[k]); cudaEventDestroy(ctx->evDone[k]); }
+  }
+  if (ctx->evStart) cudaEventDestroy(ctx->evStart);
   for (auto& b : ctx->slots) b.release();
   DevBuf* bufs[] = {&ctx->candLens, &ctx->candPreds, &ctx->candStatus, &ctx->counters, &ctx->scratch, &ctx->lists, &ctx->src,
                     &ctx->total, &ctx->coef, &ctx->defer, &ctx->lsopMeta, &ctx->encScratch, &ctx->region, &ctx->jobLen, &ctx->jobOff, &ctx->jobOut, &ctx->jobTotal,
@@ -619,13 +633,57 @@ int g4_decode_tiles(g4_context* ctx, const g4_codec_list* codecs, const g4_band_
     CK(ctx->sOffsets.ensure(size_t(nTiles) * 8));
     CK(ctx->sLens.ensure(size_t(nTiles) * 4));
     CK(ctx->sStatus.ensure(size_t(nTiles) * 4));
-    CK(cudaMemcpyAsync(ctx->sArena.p, arena, arenaBytes, cudaMemcpyHostToDevice, ctx->stream));
     CK(cudaMemcpyAsync(ctx->sOffsets.p, offsets, size_t(nTiles) * 8, cudaMemcpyHostToDevice, ctx->stream));
     CK(cudaMemcpyAsync(ctx->sLens.p, lens, size_t(nTiles) * 4, cudaMemcpyHostToDevice, ctx->stream));
-    rc = decode_device(ctx, codecs, band, ctx->sArena.as<uint8_t>(), ctx->sOffsets.as<uint64_t>(), ctx->sLens.as<uint32_t>(),
-                       ctx->sGrid.p, ctx->sStatus.as<int32_t>());
-    if (rc != G4_OK) return rc;
-    CK(cudaMemcpyAsync(grid, ctx->sGrid.p, gridBytes, cudaMemcpyDeviceToHost, ctx->stream));
+    // The decoded raster (4 B/sample) crossing PCIe dominates this call, so the band is cut into chunks of whole tile
+    // rows and pipelined over three streams: payload H2D of chunk k+1, kernels of chunk k and raster D2H of chunk k-1
+    // overlap.  Needs payloads in ascending tile order (what g4_encode_tiles produces); otherwise one chunk.
+    bool ascending = true;
+    for (int t = 1; t < nTiles && ascending; t++) ascending = offsets[t] >= offsets[t - 1] + lens[t - 1];
+    int nChunks = ascending ? (band->tiles_down < kMaxChunks ? band->tiles_down : kMaxChunks) : 1;
+    if (gridBytes < (size_t(32) << 20)) nChunks = 1;  // small bands: the fixed cost per chunk is not worth it
+    if (nChunks > 1 && !ctx->copyIn) {
+      CK(cudaStreamCreateWithFlags(&ctx->copyIn, cudaStreamNonBlocking));
+      CK(cudaStreamCreateWithFlags(&ctx->copyOut, cudaStreamNonBlocking));
+      for (int k = 0; k < kMaxChunks; k++) {
+        CK(cudaEventCreateWithFlags(&ctx->evIn[k], cudaEventDisableTiming));
+        CK(cudaEventCreateWithFlags(&ctx->evDone[k], cudaEventDisableTiming));
+      }
+    }
+    if (nChunks == 1) {
+      CK(cudaMemcpyAsync(ctx->sArena.p, arena, arenaBytes, cudaMemcpyHostToDevice, ctx->stream));
+      rc = decode_device(ctx, codecs, band, ctx->sArena.as<uint8_t>(), ctx->sOffsets.as<uint64_t>(), ctx->sLens.as<uint32_t>(),
+                         ctx->sGrid.p, ctx->sStatus.as<int32_t>());
+      if (rc != G4_OK) return rc;
+      CK(cudaMemcpyAsync(grid, ctx->sGrid.p, gridBytes, cudaMemcpyDeviceToHost, ctx->stream));
+    } else {
+      CK(cudaEventRecord(ctx->evStart, ctx->stream));
+      CK(cudaStreamWaitEvent(ctx->copyIn, ctx->evStart, 0));   // the staging buffers may still be in use by an earlier call
+      CK(cudaStreamWaitEvent(ctx->copyOut, ctx->evStart, 0));
+      const size_t rowBytes = size_t(band->grid_pitch) * 4;
+      for (int k = 0; k < nChunks; k++) {
+        const int r0 = int(int64_t(band->tiles_down) * k / nChunks), r1 = int(int64_t(band->tiles_down) * (k + 1) / nChunks);
+        const int t0 = r0 * band->tiles_across, t1 = r1 * band->tiles_across;
+        const uint64_t lo = offsets[t0], hi = offsets[t1 - 1] + lens[t1 - 1];
+        CK(cudaMemcpyAsync(ctx->sArena.as<uint8_t>() + lo, arena + lo, hi - lo, cudaMemcpyHostToDevice, ctx->copyIn));
+        CK(cudaEventRecord(ctx->evIn[k], ctx->copyIn));
+        CK(cudaStreamWaitEvent(ctx->stream, ctx->evIn[k], 0));
+        g4_band_desc sub = *band;
+        sub.tiles_down = r1 - r0;
+        uint8_t* gdev = ctx->sGrid.as<uint8_t>() + size_t(r0) * band->tile_rows * rowBytes;
+        rc = decode_device(ctx, codecs, &sub, ctx->sArena.as<uint8_t>(), ctx->sOffsets.as<uint64_t>() + t0, ctx->sLens.as<uint32_t>() + t0,
+                           gdev, ctx->sStatus.as<int32_t>() + t0);
+        if (rc != G4_OK) return rc;
+        CK(cudaEventRecord(ctx->evDone[k], ctx->stream));
+        CK(cudaStreamWaitEvent(ctx->copyOut, ctx->evDone[k], 0));
+        const size_t rows = size_t(r1 - r0) * band->tile_rows;
+        const size_t bytes = k == nChunks - 1 ? gridBytes - size_t(r0) * band->tile_rows * rowBytes : rows * rowBytes;
+        CK(cudaMemcpyAsync(static_cast<uint8_t*>(grid) + size_t(r0) * band->tile_rows * rowBytes, gdev, bytes, cudaMemcpyDeviceToHost,
+                           ctx->copyOut));
+      }
+      CK(cudaEventRecord(ctx->evIn[0], ctx->copyOut));
+      CK(cudaStreamWaitEvent(ctx->stream, ctx->evIn[0], 0));  // the call's stream completes only after the last D2H
+    }
     CK(cudaMemcpyAsync(status, ctx->sStatus.p, size_t(nTiles) * 4, cudaMemcpyDeviceToHost, ctx->stream));
     CK(cudaStreamSynchronize(ctx->stream));
     std::memcpy(st.data(), status, size_t(nTiles) * 4);
