@@ -117,8 +117,21 @@ def cpu_arm(cfg, threads, budget_s, oracle):
             break
         n_tiles = min(across, n_tiles * 4)
     raw = grid.size * 4
-    return {"decode_gbs": raw / t_dec / 1e9, "encode_gbs": raw / t_enc / 1e9, "tiles": n_tiles, "dec_s": t_dec, "enc_s": t_enc,
-            "bits_per_sample": 8.0 * float(lens.sum()) / grid.size}
+    res = {"decode_gbs": raw / t_dec / 1e9, "encode_gbs": raw / t_enc / 1e9, "tiles": n_tiles, "dec_s": t_dec, "enc_s": t_enc,
+           "bits_per_sample": 8.0 * float(lens.sum()) / grid.size}
+    if not is_f:
+        # input distribution check: Triangle-predictor M32 stream of the sample's first tiles
+        one_byte, total_codes, hist = 0, 0, np.zeros(256, np.int64)
+        for k in range(min(n_tiles, 8)):
+            n, _seed, m32 = oracle.predictor_encode(oracle.PRED_TRIANGLE, grid[:, k * tc:(k + 1) * tc])
+            b = np.frombuffer(m32, np.uint8)
+            hist += np.bincount(b, minlength=256)
+            total_codes += tr * tc - 1
+            one_byte += (tr * tc - 1) - int(((b == 0x7F) | (b == 0x81)).sum())
+        p = hist[hist > 0] / hist.sum()
+        res["input_stats"] = {"m32_one_byte_fraction": one_byte / max(1, total_codes),
+                              "m32_byte_entropy_bits": float(-(p * np.log2(p)).sum())}
+    return res
 
 
 def run_reference(args, rank, cfg):
@@ -392,7 +405,8 @@ def main():
                "sample": "%d tiles of %dx%d from the workload's first tile row; oracle = C++ restatement of the Java reference "
                          "(no JVM in this image)" % (rn["tiles"], TILE_R, TILE_C),
                "single_thread_value": r1["decode_gbs"], "encode_value": rn["encode_gbs"],
-               "encode_single_thread_value": r1["encode_gbs"], "bits_per_sample": rn["bits_per_sample"]}
+               "encode_single_thread_value": r1["encode_gbs"], "bits_per_sample": rn["bits_per_sample"],
+               "input_stats": rn.get("input_stats")}
     metric = METRIC if args.config == 3 else "GVRS tile decode GB/s of raw samples (%s)" % cfg["name"].split(":")[0]
     line = {
         "metric": metric, "value": value, "unit": "GB/s", "n_gpus": world, "steps": args.steps, "warmup": args.warmup,

@@ -58,3 +58,24 @@ def gather_layout(local_lens, group=None):
     first = int(sum(counts[:rank]))
     base = int(off[first]) if first < off.size else total
     return lens, off, base, total
+
+
+def tile_content(element_payloads):
+    """Tile content of a compressed tile record: for every element [len:int32 LE][payload]
+    (gvrs/RasterTile.java:234-256, getCompressedPacking).  `element_payloads` = what g4_encode_tiles produced for the
+    tile's elements (a payload of exactly the element's standard size is the raw form, gvrs/TileElementInt.java:198-204)."""
+    out = bytearray()
+    for p in element_payloads:
+        out += int(len(p)).to_bytes(4, "little")
+        out += bytes(p)
+    return bytes(out)
+
+
+def tile_record_is_compressed(element_lens, standard_tile_bytes):
+    """gvrs/RecordManager.java:403-461 (writeTile): the compressed form of a tile (4-byte tile index + [len][payload] per
+    element) is stored only if it is strictly smaller than the uncompressed record, 4 + 4*E + standardTileDataSizeInBytes.
+    Returns (use_compressed, record_payload_bytes)."""
+    e = len(element_lens)
+    compressed = 4 + sum(4 + int(n) for n in element_lens)
+    payload = 4 + 4 * e + int(standard_tile_bytes)
+    return (compressed < payload), (compressed if compressed < payload else payload)

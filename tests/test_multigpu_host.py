@@ -7,7 +7,7 @@ import numpy as np
 import torch.distributed as dist
 import torch.multiprocessing as mp
 
-from gridfour_b200.sharding import gather_layout, record_offsets, shard_tile_rows
+from gridfour_b200.sharding import gather_layout, record_offsets, shard_tile_rows, tile_content, tile_record_is_compressed
 
 
 def test_shard_tile_rows_partitions_every_row_once():
@@ -23,6 +23,15 @@ def test_shard_tile_rows_partitions_every_row_once():
 def test_record_offsets_round_to_8_bytes():
     off, total = record_offsets([10, 8, 1, 172800])
     assert off.tolist() == [0, 16, 24, 32] and total == 32 + 172800
+
+
+def test_tile_record_rule_matches_record_manager():
+    """RecordManager.writeTile (:403-461): compressed form only if 4 + sum(4 + len) < 4 + 4E + standard size."""
+    n = 90 * 120 * 4
+    assert tile_record_is_compressed([n - 1], n) == (True, 4 + 4 + n - 1)
+    assert tile_record_is_compressed([n], n) == (False, 4 + 4 + n)  # raw element: same size, not "compressed"
+    assert tile_record_is_compressed([100, n], 2 * n) == (True, 4 + 8 + 100 + n)
+    assert tile_content([b"\x01\x02\x03", b""]) == b"\x03\x00\x00\x00\x01\x02\x03\x00\x00\x00\x00"
 
 
 def _worker(rank, world, port, q):
