@@ -5,6 +5,7 @@
 #include "g4_kernels.h"
 #include "g4_predict.cuh"
 #include "g4_canon.cuh"
+#include "g4_canon_fast.cuh"
 #include "g4_canon_enc.cuh"
 
 namespace g4 {
@@ -21,8 +22,18 @@ struct PredCellSink {
 };
 }  // namespace
 
-__global__ void __launch_bounds__(kThreads) canon_decode_kernel(DecodeArgs a) {
-  __shared__ CanonDecShared S;
+// Decode: the packing is staged in shared memory and decoded with g4_canon_fast.cuh when it fits (<= 28 KB, 4-byte
+// aligned); otherwise the global-memory decoder of g4_canon.cuh.
+union CanonDecodeSmem {
+  CanonFastShared f;
+  CanonDecShared s;
+};
+
+__global__ void __launch_bounds__(kThreads, 4) canon_decode_kernel(DecodeArgs a) {
+  extern __shared__ __align__(16) unsigned char canonDecSmem[];
+  CanonFastShared& F = *reinterpret_cast<CanonFastShared*>(canonDecSmem);
+  CanonDecShared& S = *reinterpret_cast<CanonDecShared*>(canonDecSmem);
+  __shared__ uint32_t scan[kWarps + 1];
   __shared__ int sTile;
   const int tid = threadIdx.x;
   for (;;) {
@@ -48,18 +59,26 @@ __global__ void __launch_bounds__(kThreads) canon_decode_kernel(DecodeArgs a) {
       }
     } else if (pred < 1 || pred > 4) status = G4_ERR_FORMAT;
     else {
-      BitSrc src;
-      src.init(packing + 6, len - 6);
       uint32_t endBit = 0, nv = 0;
-      PredCellSink sink{t, pred};
       const uint32_t expect = pred == G4_PRED_DIFF_NULLS ? uint32_t(n) : uint32_t(n - 1);
-      if (!canon_decode_stream(S, src, 0, expect, 0u, sink, &endBit, &nv) || nv != expect) status = G4_ERR_FORMAT;
+      bool ok;
+      if (len <= uint32_t(kFastStageWords) * 4u && (reinterpret_cast<uintptr_t>(packing) & 3) == 0) {
+        canon_fast_stage(F, packing, len);
+        CellRunSink sink{t, pred, 0};
+        ok = canon_fast_decode_stream(F, len * 8u, 48u, expect, 0u, sink, &endBit, &nv);
+      } else {
+        BitSrc src;
+        src.init(packing + 6, len - 6);
+        PredCellSink sink{t, pred};
+        ok = canon_decode_stream(S, src, 0, expect, 0u, sink, &endBit, &nv);
+      }
+      if (!ok || nv != expect) status = G4_ERR_FORMAT;
       else if (pred == G4_PRED_DIFF_NULLS) predictor_inverse_nulls(t, seed);
       else {
         __syncthreads();
         if (tid == 0) t.at(0, 0) = seed;
         __syncthreads();
-        predictor_inverse(pred, t, S.scan);
+        predictor_inverse(pred, t, scan);
       }
     }
     if (tid == 0) a.status[tIdx] = status;
@@ -177,7 +196,13 @@ cudaError_t launch_canon_encode(const EncodeArgs& a, int nCtas, cudaStream_t s) 
 }
 
 cudaError_t launch_canon_decode(const DecodeArgs& a, int nCtas, cudaStream_t s) {
-  canon_decode_kernel<<<nCtas, kThreads, 0, s>>>(a);
+  static bool attr = false;
+  if (!attr) {
+    cudaError_t e = cudaFuncSetAttribute(canon_decode_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, int(sizeof(CanonDecodeSmem)));
+    if (e != cudaSuccess) return e;
+    attr = true;
+  }
+  canon_decode_kernel<<<nCtas, kThreads, sizeof(CanonDecodeSmem), s>>>(a);
   return cudaGetLastError();
 }
 

@@ -466,6 +466,20 @@ __device__ bool canon_fast_decode_text(CanonFastShared& S, uint32_t nBits, const
   }
 }
 
+// Run sink for any residual stream order: one stream_to_cell per value (begin(first value index), put(value) ..., end()).
+struct CellRunSink {
+  TileView t;
+  int order;
+  uint32_t k;
+  __device__ __forceinline__ void begin(uint32_t k0) { k = k0; }
+  __device__ __forceinline__ void put(int32_t v) {
+    int r, c;
+    stream_to_cell(order, int(k++), t.R, t.C, &r, &c);
+    t.at(r, c) = v;
+  }
+  __device__ __forceinline__ void end() {}
+};
+
 // Header + text of one canonical stream staged in S.sw (startBit absolute).  All threads call.
 template <class Sink>
 __device__ bool canon_fast_decode_stream(CanonFastShared& S, uint32_t nBits, uint32_t startBit, uint32_t maxValues, uint32_t hintBits,

@@ -110,19 +110,6 @@ struct CellSink {
   }
 };
 
-// Run sinks for canon_fast_decode_stream: begin(first value index), put(value) ..., end().
-struct CellRunSink {  // any stream order, one stream_to_cell per value (initializers: ~1200 values per tile)
-  TileView t;
-  int order;
-  uint32_t k;
-  __device__ __forceinline__ void begin(uint32_t k0) { k = k0; }
-  __device__ __forceinline__ void put(int32_t v) {
-    int r, c;
-    stream_to_cell(order, int(k++), t.R, t.C, &r, &c);
-    t.at(r, c) = v;
-  }
-  __device__ __forceinline__ void end() {}
-};
 struct InteriorRunSink {  // LSOP12 interior order: rows 2.., columns 2..C-3 row-major; running cell address, no division per value
   TileView t;
   int32_t* p;  // column 2 of the current row
