@@ -236,6 +236,33 @@ struct BitSrc {
   }
 };
 
+// 64-bit register bit buffer over a global-memory BitSrc (clamped word reads); >= 32 valid bits after every skip().
+struct GlobalCursor {
+  const BitSrc* src;
+  uint32_t pos, next;
+  uint64_t buf;
+  int avail;
+  __device__ __forceinline__ uint32_t word(uint32_t i) const { return i <= src->lastWord ? __ldg(src->words + i) : 0u; }
+  __device__ __forceinline__ void init(const BitSrc& s, uint32_t p) {
+    src = &s;
+    pos = p;
+    const uint32_t a = s.bit0 + p, i = a >> 5, sh = a & 31;
+    buf = ((uint64_t(word(i + 1)) << 32) | word(i)) >> sh;
+    avail = 64 - int(sh);
+    next = i + 2;
+  }
+  __device__ __forceinline__ uint32_t peek() const { return uint32_t(buf); }
+  __device__ __forceinline__ void skip(uint32_t n) {
+    buf >>= n;
+    avail -= int(n);
+    pos += n;
+    if (avail < 32) {
+      buf |= uint64_t(word(next++)) << avail;
+      avail += 32;
+    }
+  }
+};
+
 // Single-thread LSB-first bit writer into a word buffer (used for headers / trees).
 struct BitSink {
   uint32_t* words;

@@ -195,30 +195,54 @@ __device__ inline int inflate_warp(InflateWarpShared& S, const uint8_t* in, uint
       int ev = 0;  // 1 = match, 2 = end of block, 3 = error/truncated, 4 = output full
       uint32_t mlen = 0, mdist = 0;
       if (lane == 0) {
+        // 64-bit register bit buffer: one LUT read per symbol, a global word load every 32 consumed bits
+        GlobalCursor cur;
+        cur.init(src, pos);
         for (;;) {
-          if (pos >= src.nBits) { ev = 3; break; }
-          uint32_t p0 = pos;
-          int sym = inflate_symbol(S.litLut, kInfLitBits, S.litFirst, S.litCount, S.litOffset, S.litSorted, src, &pos);
+          if (cur.pos >= src.nBits) { ev = 3; break; }
+          const uint32_t p0 = cur.pos;
+          int sym;
+          {
+            const uint32_t e = S.litLut[cur.peek() & ((1u << kInfLitBits) - 1)];
+            if (e) { cur.skip(e >> 9); sym = int(e & 0x1ffu); }
+            else {
+              uint32_t p = cur.pos;
+              sym = canon_slow_symbol(S.litFirst, S.litCount, S.litOffset, S.litSorted, src, &p, kInfLitBits + 1);
+              if (sym >= 0) cur.init(src, p);
+            }
+          }
           if (sym < 0) { ev = 3; break; }
           if (sym < 256) {
-            if (op >= cap) { pos = p0; ev = 4; break; }
+            if (op >= cap) { cur.pos = p0; ev = 4; break; }
             out[op++] = uint8_t(sym);
             continue;
           }
           if (sym == 256) { ev = 2; break; }
           if (sym > 285) { ev = 3; break; }
-          if (op >= cap) { pos = p0; ev = 4; break; }
+          if (op >= cap) { cur.pos = p0; ev = 4; break; }
           int li = sym - 257;
-          mlen = kInfLenBase[li] + src.bits(pos, kInfLenExtra[li]);
-          pos += kInfLenExtra[li];
-          int ds = inflate_symbol(S.distLut, kInfDistBits, S.distFirst, S.distCount, S.distOffset, S.distSorted, src, &pos);
+          const uint32_t le = kInfLenExtra[li];
+          mlen = kInfLenBase[li] + (le ? (cur.peek() & ((1u << le) - 1u)) : 0u);
+          cur.skip(le);
+          int ds;
+          {
+            const uint32_t e = S.distLut[cur.peek() & ((1u << kInfDistBits) - 1)];
+            if (e) { cur.skip(e >> 9); ds = int(e & 0x1ffu); }
+            else {
+              uint32_t p = cur.pos;
+              ds = canon_slow_symbol(S.distFirst, S.distCount, S.distOffset, S.distSorted, src, &p, kInfDistBits + 1);
+              if (ds >= 0) cur.init(src, p);
+            }
+          }
           if (ds < 0 || ds > 29) { ev = 3; break; }
-          mdist = kInfDistBase[ds] + src.bits(pos, kInfDistExtra[ds]);
-          pos += kInfDistExtra[ds];
+          const uint32_t de = kInfDistExtra[ds];
+          mdist = kInfDistBase[ds] + (de ? (cur.peek() & ((1u << de) - 1u)) : 0u);
+          cur.skip(de);
           if (mdist > op) { ev = 3; break; }  // distance too far back
           ev = 1;
           break;
         }
+        pos = cur.pos;
       }
       ev = __shfl_sync(0xffffffffu, ev, 0);
       pos = __shfl_sync(0xffffffffu, pos, 0);

@@ -215,33 +215,6 @@ __device__ inline void lsop_init_scans(const TileView& t, int32_t seed) {
 // Legacy-Huffman, Deflate, oversized or unaligned packings are appended to `defer` for the general kernel below.
 constexpr int kLsopMetaBytes = 272;  // [0..3] interior text start (absolute bit, 0 = tile not on the fast path), [8..267] lengths
 
-// 64-bit register bit buffer over a global-memory BitSrc (clamped word reads); >= 32 valid bits after every skip().
-struct GlobalCursor {
-  const BitSrc* src;
-  uint32_t pos, next;
-  uint64_t buf;
-  int avail;
-  __device__ __forceinline__ uint32_t word(uint32_t i) const { return i <= src->lastWord ? __ldg(src->words + i) : 0u; }
-  __device__ __forceinline__ void init(const BitSrc& s, uint32_t p) {
-    src = &s;
-    pos = p;
-    const uint32_t a = s.bit0 + p, i = a >> 5, sh = a & 31;
-    buf = ((uint64_t(word(i + 1)) << 32) | word(i)) >> sh;
-    avail = 64 - int(sh);
-    next = i + 2;
-  }
-  __device__ __forceinline__ uint32_t peek() const { return uint32_t(buf); }
-  __device__ __forceinline__ void skip(uint32_t n) {
-    buf >>= n;
-    avail -= int(n);
-    pos += n;
-    if (avail < 32) {
-      buf |= uint64_t(word(next++)) << avail;
-      avail += 32;
-    }
-  }
-};
-
 struct CanonWarpShared {
   uint8_t lens[kCanonSymbols + 4];
   uint16_t sorted[kCanonSymbols];
