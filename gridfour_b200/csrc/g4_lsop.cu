@@ -135,12 +135,15 @@ struct InteriorRunSink4 {
   int32_t* rowp;  // column 0 of the current row
   int col, n;     // next column to be written (2 .. C-3); number of buffered values (columns col-n .. col-1)
   int32_t q0, q1, q2, q3;
+  int4 hold;      // the lower half of a 32-byte sector, waiting for its upper half
+  bool held;
   __device__ __forceinline__ void begin(uint32_t k0) {
     const int w = t.C - 4;
     int rr = int(k0) / w;
     col = 2 + int(k0) - rr * w;
     rowp = t.row(2 + rr);
     n = 0;
+    held = false;
   }
   __device__ __forceinline__ void flush_scalars() {
     if (n >= 4) rowp[col - 4] = q0;
@@ -149,21 +152,35 @@ struct InteriorRunSink4 {
     if (n >= 1) rowp[col - 1] = q3;
     n = 0;
   }
+  __device__ __forceinline__ void flush_hold() {  // columns col-n-4 .. col-n-1
+    if (held) { *reinterpret_cast<int4*>(rowp + col - n - 4) = hold; held = false; }
+  }
   __device__ __forceinline__ void put(int32_t v) {
     q0 = q1; q1 = q2; q2 = q3; q3 = v;
     n++;
     col++;
     if ((col & 3) == 0) {
-      if (n == 4) { *reinterpret_cast<int4*>(rowp + col - 4) = make_int4(q0, q1, q2, q3); n = 0; }
-      else flush_scalars();  // head of a run that started inside a group
+      if (n == 4) {
+        // a complete aligned group of four: pair it with its neighbour so that whole 32-byte sectors leave together
+        if (col & 4) { hold = make_int4(q0, q1, q2, q3); held = true; }
+        else {
+          if (held) { *reinterpret_cast<int4*>(rowp + col - 8) = hold; held = false; }
+          *reinterpret_cast<int4*>(rowp + col - 4) = make_int4(q0, q1, q2, q3);
+        }
+        n = 0;
+      } else flush_scalars();  // head of a run that started inside a group
     }
     if (col == t.C - 2) {  // end of the row's interior: columns C-4, C-3 (tile_cols % 4 == 0)
+      flush_hold();
       flush_scalars();
       col = 2;
       rowp += t.pitch;
     }
   }
-  __device__ __forceinline__ void end() { flush_scalars(); }
+  __device__ __forceinline__ void end() {
+    flush_hold();
+    flush_scalars();
+  }
 };
 
 }  // namespace
