@@ -46,16 +46,18 @@ __device__ inline void parse_tree(HuffDecShared& S, const BitSrc& src, uint32_t 
   stack[0] = 0;
   slot[0] = 0;
   S.leafSym[0] = -1;
+  GlobalCursor cur;  // register bit buffer: the tree is read one and eight bits at a time
+  cur.init(src, pos);
   while (leaves < L) {
-    if (sp == 0 || nodes >= 511 || pos + 9 > src.nBits + 8) { S.error = 1; return; }
+    if (sp == 0 || nodes >= 511 || cur.pos + 9 > src.nBits + 8) { S.error = 1; return; }
     int parent = stack[sp - 1];
-    uint32_t bit = src.bits(pos, 1);
-    pos++;
+    uint32_t bit = cur.peek() & 1u;
+    cur.skip(1);
     int id = nodes++;
     S.kid[parent][slot[parent]++] = uint16_t(id);
     if (bit) {
-      S.leafSym[id] = int16_t(src.bits(pos, 8));
-      pos += 8;
+      S.leafSym[id] = int16_t(cur.peek() & 0xffu);
+      cur.skip(8);
       leaves++;
       while (sp > 0 && slot[stack[sp - 1]] == 2) sp--;
     } else {
@@ -65,6 +67,7 @@ __device__ inline void parse_tree(HuffDecShared& S, const BitSrc& src, uint32_t 
       stack[sp++] = uint16_t(id);
     }
   }
+  pos = cur.pos;
   if (sp != 0 || pos > src.nBits) { S.error = 1; return; }  // incomplete tree / truncated stream
   S.treeBits = pos;
 }
