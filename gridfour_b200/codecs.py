@@ -12,7 +12,7 @@ import numpy as np
 
 from . import _lib
 from ._lib import (G4_CODEC_CANON_HUFFMAN, G4_CODEC_DEFLATE, G4_CODEC_FLOAT, G4_CODEC_HUFFMAN, G4_CODEC_LSOP12, G4_DECLINED,
-                   G4_ELEM_F32, G4_ELEM_I32, G4_MEM_DEVICE, G4_MEM_HOST, G4_OK, BandDesc, CodecList, check)
+                   G4_ELEM_F32, G4_ELEM_I16, G4_ELEM_I32, G4_MEM_DEVICE, G4_MEM_HOST, G4_OK, BandDesc, CodecList, check)
 
 INT4_NULL_CODE = -(2 ** 31)  # util/GridfourConstants.java:61
 
@@ -313,27 +313,32 @@ class CodecMaster:
 
     # -- batched (new): a band of tiles in one call -------------------------------------------------------
     @staticmethod
-    def _band(grid_shape, dtype, tileRows, tileCols, pitch=None):
+    def _band(grid_shape, dtype, tileRows, tileCols, pitch=None, fillValue=None):
         rows, cols = grid_shape
         if rows % tileRows or cols % tileCols:
             raise ValueError("grid dimensions must be multiples of the tile size (GVRS tiles are full size)")
         b = BandDesc()
-        b.elem_type = G4_ELEM_F32 if np.dtype(dtype) == np.float32 else G4_ELEM_I32
+        dt = np.dtype(dtype)
+        b.elem_type = G4_ELEM_F32 if dt == np.float32 else G4_ELEM_I16 if dt == np.int16 else G4_ELEM_I32
+        # TileElementShort: the element's fill value is coded as null (gvrs/TileElementShort.java:213-218); the default
+        # fill of a short element is SHORT_NULL_CODE
+        b.fill_value = int(fillValue) if fillValue is not None else -32768
         b.tile_rows, b.tile_cols = tileRows, tileCols
         b.tiles_down, b.tiles_across = rows // tileRows, cols // tileCols
         b.grid_pitch = pitch or cols
         return b
 
-    def encodeTiles(self, grid, tileRows, tileCols):
-        """grid: 2-D numpy array (host path) or torch CUDA tensor (device path), int32 or float32."""
+    def encodeTiles(self, grid, tileRows, tileCols, fillValue=None):
+        """grid: 2-D numpy array (host path) or torch CUDA tensor (device path); int32, float32, or int16 (a short
+        element, TileElementShort: `fillValue` is coded as null, raw tiles take 2 bytes per sample)."""
         L = _lib.lib()
         cl = self.spec.native_list()
         total = C.c_uint64(0)
         if isinstance(grid, np.ndarray):
             g = np.ascontiguousarray(grid)
-            if g.dtype not in (np.int32, np.float32):
-                raise ValueError("int32 or float32 rasters only")
-            band = self._band(g.shape, g.dtype, tileRows, tileCols)
+            if g.dtype not in (np.int32, np.float32, np.int16):
+                raise ValueError("int32, float32 or int16 rasters only")
+            band = self._band(g.shape, g.dtype, tileRows, tileCols, fillValue=fillValue)
             nT = band.tiles_down * band.tiles_across
             cap = int(L.g4_encode_arena_bound(C.byref(band)))
             arena = np.empty(cap, np.uint8)
@@ -351,8 +356,8 @@ class CodecMaster:
 
         if not (isinstance(grid, torch.Tensor) and grid.is_cuda and grid.dim() == 2 and grid.is_contiguous()):
             raise ValueError("expected a contiguous 2-D CUDA tensor")
-        npdt = np.float32 if grid.dtype == torch.float32 else np.int32
-        band = self._band(tuple(grid.shape), npdt, tileRows, tileCols)
+        npdt = np.float32 if grid.dtype == torch.float32 else np.int16 if grid.dtype == torch.int16 else np.int32
+        band = self._band(tuple(grid.shape), npdt, tileRows, tileCols, fillValue=fillValue)
         nT = band.tiles_down * band.tiles_across
         cap = int(L.g4_encode_arena_bound(C.byref(band)))
         dev = grid.device
@@ -375,7 +380,7 @@ class CodecMaster:
         band = batch.band
         rows, cols = band.tiles_down * band.tile_rows, band.tiles_across * band.tile_cols
         if isinstance(batch.arena, np.ndarray):
-            dt = np.float32 if band.elem_type == G4_ELEM_F32 else np.int32
+            dt = np.float32 if band.elem_type == G4_ELEM_F32 else np.int16 if band.elem_type == G4_ELEM_I16 else np.int32
             grid = out if out is not None else np.empty((rows, cols), dt)
             status = np.empty(band.tiles_down * band.tiles_across, np.int32)
             arena = np.ascontiguousarray(batch.arena)
@@ -388,7 +393,7 @@ class CodecMaster:
             return grid
         import torch
 
-        dt = torch.float32 if band.elem_type == G4_ELEM_F32 else torch.int32
+        dt = torch.float32 if band.elem_type == G4_ELEM_F32 else torch.int16 if band.elem_type == G4_ELEM_I16 else torch.int32
         grid = out if out is not None else torch.empty((rows, cols), dtype=dt, device=batch.arena.device)
         status = torch.empty(band.tiles_down * band.tiles_across, dtype=torch.int32, device=batch.arena.device)
         st = L.g4_decode_tiles(self._context()._h, C.byref(cl), C.byref(band), G4_MEM_DEVICE, batch.arena.data_ptr(),

@@ -72,6 +72,7 @@ struct g4_context {
   DevBuf coef;         // LSOP12 decode: 12 float32 coefficients per tile
   DevBuf defer;        // LSOP12 decode: tiles the fast entropy kernel hands to the general one
   DevBuf lsopMeta;     // LSOP12 decode: interior code lengths + text position, kernel H -> kernel T
+  DevBuf wide;         // TileElementShort: int32 staging raster around the integer codecs
   // zlib-stream encode stages (CodecDeflate, CodecFloat, LSOP12 Deflate alternative)
   DevBuf jobLen, jobOff, jobOut, jobTotal, streamIn, streamOut, deflateWork;
   int deflateWorkers = 0;   // resident stream-worker threads (0 = default, see g4_context_create)
@@ -268,7 +269,7 @@ int launch_encoder(g4_context* ctx, int codecId, EncodeArgs& a, int nTiles) {
 
 int check_band(const g4_band_desc* b) {
   if (!b) return G4_ERR_ARG;
-  if (b->elem_type != G4_ELEM_I32 && b->elem_type != G4_ELEM_F32) return G4_ERR_ARG;
+  if (b->elem_type != G4_ELEM_I32 && b->elem_type != G4_ELEM_F32 && b->elem_type != G4_ELEM_I16) return G4_ERR_ARG;
   if (b->tile_rows < 2 || b->tile_cols < 2) return G4_ERR_UNSUPPORTED;
   if (b->tiles_down < 1 || b->tiles_across < 1) return G4_ERR_ARG;
   if (int64_t(b->tile_rows) * b->tile_cols > (1 << 20)) return G4_ERR_UNSUPPORTED;
@@ -277,15 +278,22 @@ int check_band(const g4_band_desc* b) {
   return G4_OK;
 }
 
+size_t elem_bytes(const g4_band_desc& b) { return b.elem_type == G4_ELEM_I16 ? 2 : 4; }
+// TileElement.standardSizeInBytes (gvrs/TileElement.java:85-93): 4n, or 2n rounded up to a multiple of 4 for shorts
+uint32_t standard_size(const g4_band_desc& b) {
+  const uint32_t n = uint32_t(b.tile_rows) * uint32_t(b.tile_cols);
+  return b.elem_type == G4_ELEM_I16 ? ((2u * n + 3u) & ~3u) : 4u * n;
+}
+
 size_t band_samples(const g4_band_desc& b) {
   return size_t(int64_t(b.tiles_down) * b.tile_rows - 1) * size_t(b.grid_pitch) + size_t(b.tiles_across) * b.tile_cols;
 }
 
 // Encode with every applicable codec of `codecs`, select, compact.  All pointers are device pointers.
 // slotBytes: capacity of each candidate slot.
-int encode_device(g4_context* ctx, const g4_codec_list* codecs, const g4_band_desc* band, void* grid, uint8_t* arena,
-                  uint64_t arenaCap, uint64_t* offsets, uint32_t* lens, uint8_t* codecOut, uint8_t* predOut, int32_t* status,
-                  uint64_t* totalHost, size_t slotBytes) {
+int encode_device_i32(g4_context* ctx, const g4_codec_list* codecs, const g4_band_desc* band, void* grid, uint8_t* arena,
+                      uint64_t arenaCap, uint64_t* offsets, uint32_t* lens, uint8_t* codecOut, uint8_t* predOut, int32_t* status,
+                      uint64_t* totalHost, size_t slotBytes, const int16_t* raw16, int64_t raw16Pitch) {
   const int nTiles = band->tiles_down * band->tiles_across;
   const int n = band->tile_rows * band->tile_cols;
   const bool isFloat = band->elem_type == G4_ELEM_F32;
@@ -325,7 +333,7 @@ int encode_device(g4_context* ctx, const g4_codec_list* codecs, const g4_band_de
   }
   sel.nTiles = nTiles;
   sel.nCand = nCand;
-  sel.rawLen = uint32_t(n) * 4u;
+  sel.rawLen = raw16 ? ((2u * uint32_t(n) + 3u) & ~3u) : uint32_t(n) * 4u;
   sel.candLens = ctx->candLens.as<uint32_t>();
   sel.candPreds = ctx->candPreds.as<uint8_t>();
   sel.candStatus = ctx->candStatus.as<int32_t>();
@@ -345,6 +353,8 @@ int encode_device(g4_context* ctx, const g4_codec_list* codecs, const g4_band_de
   cmp.arena = arena;
   cmp.arenaCap = arenaCap;
   cmp.status = status;
+  cmp.raw16 = raw16;
+  cmp.raw16Pitch = raw16Pitch;
   CK(launch_compact(cmp, nTiles, ctx->stream));
   ctx->launches += 3;
   uint64_t total = 0;
@@ -354,8 +364,8 @@ int encode_device(g4_context* ctx, const g4_codec_list* codecs, const g4_band_de
   return G4_OK;
 }
 
-int decode_device(g4_context* ctx, const g4_codec_list* codecs, const g4_band_desc* band, const uint8_t* arena,
-                  const uint64_t* offsets, const uint32_t* lens, void* grid, int32_t* status) {
+int decode_device_i32(g4_context* ctx, const g4_codec_list* codecs, const g4_band_desc* band, const uint8_t* arena,
+                      const uint64_t* offsets, const uint32_t* lens, void* grid, int32_t* status, bool rawShorts) {
   const int nTiles = band->tiles_down * band->tiles_across;
   const int n = band->tile_rows * band->tile_cols;
   const int kinds = G4_CODEC_COUNT + 1;
@@ -365,7 +375,7 @@ int decode_device(g4_context* ctx, const g4_codec_list* codecs, const g4_band_de
   ClassifyArgs cl{};
   cl.nTiles = nTiles;
   cl.elemType = band->elem_type;
-  cl.rawLen = uint32_t(n) * 4u;
+  cl.rawLen = rawShorts ? ((2u * uint32_t(n) + 3u) & ~3u) : uint32_t(n) * 4u;
   cl.codecs = *codecs;
   cl.arena = arena;
   cl.offsets = offsets;
@@ -398,6 +408,7 @@ int decode_device(g4_context* ctx, const g4_codec_list* codecs, const g4_band_de
     a.counter = ctx->counters.as<int>() + 16 + kind;
     a.scratch = ctx->scratch.as<uint8_t>();
     a.scratchStride = stride;
+    a.rawShorts = rawShorts ? 1 : 0;
     if (kind == G4_CODEC_COUNT) {
       KernelTimer timer(ctx, 0, kind);
       CK(launch_raw_decode(a, nTiles, ctx->stream));
@@ -407,6 +418,45 @@ int decode_device(g4_context* ctx, const g4_codec_list* codecs, const g4_band_de
       if (rc != G4_OK) return rc;
     }
   }
+  return G4_OK;
+}
+
+// TileElementShort around the integer codecs (gvrs/TileElementShort.java:211-248): the 2-byte raster is widened into an
+// int32 staging raster (fill value -> INT4_NULL_CODE) before encoding and narrowed after decoding (INT4_NULL_CODE ->
+// SHORT_NULL_CODE); raw tiles keep 2 bytes per sample.  All pointers are device pointers.
+g4_band_desc widened(const g4_band_desc& b) {
+  g4_band_desc w = b;
+  w.elem_type = G4_ELEM_I32;
+  w.grid_pitch = int64_t(b.tiles_across) * b.tile_cols;
+  return w;
+}
+
+int encode_device(g4_context* ctx, const g4_codec_list* codecs, const g4_band_desc* band, void* grid, uint8_t* arena,
+                  uint64_t arenaCap, uint64_t* offsets, uint32_t* lens, uint8_t* codecOut, uint8_t* predOut, int32_t* status,
+                  uint64_t* totalHost, size_t slotBytes) {
+  if (band->elem_type != G4_ELEM_I16)
+    return encode_device_i32(ctx, codecs, band, grid, arena, arenaCap, offsets, lens, codecOut, predOut, status, totalHost, slotBytes,
+                             nullptr, 0);
+  const g4_band_desc w = widened(*band);
+  const int64_t rows = int64_t(band->tiles_down) * band->tile_rows, cols = w.grid_pitch;
+  CK(ctx->wide.ensure(size_t(rows) * size_t(cols) * 4));
+  CK(launch_widen_i16(static_cast<const int16_t*>(grid), band->grid_pitch, ctx->wide.as<int32_t>(), rows, cols, band->fill_value,
+                      ctx->stream));
+  ctx->launches++;
+  return encode_device_i32(ctx, codecs, &w, ctx->wide.p, arena, arenaCap, offsets, lens, codecOut, predOut, status, totalHost, slotBytes,
+                           static_cast<const int16_t*>(grid), band->grid_pitch);
+}
+
+int decode_device(g4_context* ctx, const g4_codec_list* codecs, const g4_band_desc* band, const uint8_t* arena,
+                  const uint64_t* offsets, const uint32_t* lens, void* grid, int32_t* status) {
+  if (band->elem_type != G4_ELEM_I16) return decode_device_i32(ctx, codecs, band, arena, offsets, lens, grid, status, false);
+  const g4_band_desc w = widened(*band);
+  const int64_t rows = int64_t(band->tiles_down) * band->tile_rows, cols = w.grid_pitch;
+  CK(ctx->wide.ensure(size_t(rows) * size_t(cols) * 4));
+  int rc = decode_device_i32(ctx, codecs, &w, arena, offsets, lens, ctx->wide.p, status, true);
+  if (rc != G4_OK) return rc;
+  CK(launch_narrow_i16(ctx->wide.as<int32_t>(), static_cast<int16_t*>(grid), band->grid_pitch, rows, cols, ctx->stream));
+  ctx->launches++;
   return G4_OK;
 }
 
@@ -496,7 +546,7 @@ void g4_context_destroy(g4_context* ctx) {
   if (ctx->evStart) cudaEventDestroy(ctx->evStart);
   for (auto& b : ctx->slots) b.release();
   DevBuf* bufs[] = {&ctx->candLens, &ctx->candPreds, &ctx->candStatus, &ctx->counters, &ctx->scratch, &ctx->lists, &ctx->src,
-                    &ctx->total, &ctx->coef, &ctx->defer, &ctx->lsopMeta, &ctx->encScratch, &ctx->region, &ctx->jobLen, &ctx->jobOff, &ctx->jobOut, &ctx->jobTotal,
+                    &ctx->total, &ctx->coef, &ctx->defer, &ctx->lsopMeta, &ctx->wide, &ctx->encScratch, &ctx->region, &ctx->jobLen, &ctx->jobOff, &ctx->jobOut, &ctx->jobTotal,
                     &ctx->streamIn, &ctx->streamOut, &ctx->deflateWork, &ctx->sGrid, &ctx->sArena, &ctx->sOffsets, &ctx->sLens, &ctx->sCodec, &ctx->sPred, &ctx->sStatus};
   for (DevBuf* b : bufs) b->release();
   if (ctx->ownStream) cudaStreamDestroy(ctx->stream);
@@ -565,6 +615,7 @@ int g4_encode_tiles(g4_context* ctx, const g4_codec_list* codecs, const g4_band_
   const int nTiles = band->tiles_down * band->tiles_across;
   const size_t n = size_t(band->tile_rows) * band->tile_cols;
   const size_t slotBytes = round_up(n * 4 + 64, 16);
+  const size_t eb = elem_bytes(*band);
   std::vector<int32_t> st(nTiles);
   uint64_t total = 0;
   if (mem_space == G4_MEM_DEVICE) {
@@ -574,7 +625,7 @@ int g4_encode_tiles(g4_context* ctx, const g4_codec_list* codecs, const g4_band_
     CK(cudaMemcpyAsync(st.data(), status, size_t(nTiles) * 4, cudaMemcpyDeviceToHost, ctx->stream));
     CK(cudaStreamSynchronize(ctx->stream));
   } else if (mem_space == G4_MEM_HOST) {
-    const size_t gridBytes = band_samples(*band) * 4;
+    const size_t gridBytes = band_samples(*band) * eb;
     const uint64_t bound = g4_encode_arena_bound(band);
     CK(ctx->sGrid.ensure(gridBytes));
     CK(ctx->sArena.ensure(bound + 16));
@@ -627,7 +678,7 @@ int g4_decode_tiles(g4_context* ctx, const g4_codec_list* codecs, const g4_band_
       uint64_t end = offsets[t] + lens[t];
       if (end > arenaBytes) arenaBytes = end;
     }
-    const size_t gridBytes = band_samples(*band) * 4;
+    const size_t gridBytes = band_samples(*band) * elem_bytes(*band);
     CK(ctx->sGrid.ensure(gridBytes));
     CK(ctx->sArena.ensure(arenaBytes + 16));
     CK(ctx->sOffsets.ensure(size_t(nTiles) * 8));
@@ -660,7 +711,7 @@ int g4_decode_tiles(g4_context* ctx, const g4_codec_list* codecs, const g4_band_
       CK(cudaEventRecord(ctx->evStart, ctx->stream));
       CK(cudaStreamWaitEvent(ctx->copyIn, ctx->evStart, 0));   // the staging buffers may still be in use by an earlier call
       CK(cudaStreamWaitEvent(ctx->copyOut, ctx->evStart, 0));
-      const size_t rowBytes = size_t(band->grid_pitch) * 4;
+      const size_t rowBytes = size_t(band->grid_pitch) * elem_bytes(*band);
       for (int k = 0; k < nChunks; k++) {
         const int r0 = int(int64_t(band->tiles_down) * k / nChunks), r1 = int(int64_t(band->tiles_down) * (k + 1) / nChunks);
         const int t0 = r0 * band->tiles_across, t1 = r1 * band->tiles_across;

@@ -89,7 +89,21 @@ __global__ void __launch_bounds__(kThreads) compact_kernel(CompactArgs a) {
   }
   uint8_t* dst = a.arena + off;
   const int src = a.src[t];
-  if (src < 0) {
+  if (src < 0 && a.raw16) {  // TileElementShort raw form: little-endian shorts, zero padded to a multiple of 4 bytes
+    const int R = a.band.tile_rows, C = a.band.tile_cols, n = R * C;
+    const int tr = t / a.band.tiles_across, tc = t - tr * a.band.tiles_across;
+    const int16_t* base = a.raw16 + int64_t(tr) * R * a.raw16Pitch + int64_t(tc) * C;
+    uint32_t* d32 = reinterpret_cast<uint32_t*>(dst);
+    const int nWords = int((len + 3u) >> 2);
+    for (int i = threadIdx.x; i < ((nWords + 1) & ~1); i += kThreads) {
+      uint32_t w = 0;
+      for (int h = 0; h < 2; h++) {
+        int k = 2 * i + h;
+        if (k < n) { int r = k / C, c = k - r * C; w |= uint32_t(uint16_t(base[int64_t(r) * a.raw16Pitch + c])) << (16 * h); }
+      }
+      d32[i] = w;
+    }
+  } else if (src < 0) {
     const TileView tv = tile_view(a.band, a.grid, t);
     uint32_t* d32 = reinterpret_cast<uint32_t*>(dst);
     const int n = tv.R * tv.C;
@@ -147,6 +161,13 @@ __global__ void __launch_bounds__(kThreads) raw_decode_kernel(DecodeArgs a) {
   const TileView tv = tile_view(a.band, a.grid, t);
   const uint8_t* src = a.arena + a.offsets[t];
   const int n = tv.R * tv.C;
+  if (a.rawShorts) {
+    for (int i = threadIdx.x; i < n; i += kThreads) {
+      int r = i / tv.C, c = i - r * tv.C;
+      tv.at(r, c) = int32_t(int16_t(uint16_t(src[2 * size_t(i)]) | (uint16_t(src[2 * size_t(i) + 1]) << 8)));
+    }
+    return;
+  }
   const bool aligned = (reinterpret_cast<uintptr_t>(src) & 3) == 0;
   for (int i = threadIdx.x; i < n; i += kThreads) {
     int r = i / tv.C, c = i - r * tv.C;
@@ -155,9 +176,36 @@ __global__ void __launch_bounds__(kThreads) raw_decode_kernel(DecodeArgs a) {
   }
 }
 
+// TileElementShort.encode (:213-220): widen, fill value -> INT4_NULL_CODE
+__global__ void widen_i16_kernel(const int16_t* src, int64_t srcPitch, int32_t* dst, int64_t rows, int64_t cols, int32_t fill) {
+  const int64_t total = rows * cols;
+  for (int64_t i = blockIdx.x * int64_t(blockDim.x) + threadIdx.x; i < total; i += int64_t(gridDim.x) * blockDim.x) {
+    int64_t r = i / cols, c = i - r * cols;
+    int32_t v = src[r * srcPitch + c];
+    dst[i] = v == fill ? kNull : v;
+  }
+}
+// TileElementShort.decode (:236-245): INT4_NULL_CODE -> SHORT_NULL_CODE, everything else narrowed with a (short) cast
+__global__ void narrow_i16_kernel(const int32_t* src, int16_t* dst, int64_t dstPitch, int64_t rows, int64_t cols) {
+  const int64_t total = rows * cols;
+  for (int64_t i = blockIdx.x * int64_t(blockDim.x) + threadIdx.x; i < total; i += int64_t(gridDim.x) * blockDim.x) {
+    int64_t r = i / cols, c = i - r * cols;
+    int32_t v = src[i];
+    dst[r * dstPitch + c] = v == kNull ? int16_t(-32768) : int16_t(v);
+  }
+}
+
 cudaError_t launch_fill_terrain(int elemType, uint64_t seed, int64_t row0, int64_t col0, int64_t nRows, int64_t nCols, void* out,
                                 cudaStream_t s) {
   fill_terrain_kernel<<<148 * 8, 256, 0, s>>>(elemType, seed, row0, col0, nRows, nCols, out);
+  return cudaGetLastError();
+}
+cudaError_t launch_widen_i16(const int16_t* src, int64_t srcPitch, int32_t* dst, int64_t rows, int64_t cols, int32_t fill, cudaStream_t s) {
+  widen_i16_kernel<<<148 * 8, 256, 0, s>>>(src, srcPitch, dst, rows, cols, fill);
+  return cudaGetLastError();
+}
+cudaError_t launch_narrow_i16(const int32_t* src, int16_t* dst, int64_t dstPitch, int64_t rows, int64_t cols, cudaStream_t s) {
+  narrow_i16_kernel<<<148 * 8, 256, 0, s>>>(src, dst, dstPitch, rows, cols);
   return cudaGetLastError();
 }
 cudaError_t launch_select(const SelectArgs& a, cudaStream_t s) {

@@ -36,6 +36,7 @@ struct DecodeArgs {
   int* counter;
   uint8_t* scratch;     // per-CTA scratch (M32 bytes etc.), blockIdx.x * scratchStride
   size_t scratchStride;
+  int rawShorts;        // raw tiles hold 2-byte samples (TileElementShort): widen them into the int32 raster
 };
 
 struct SelectArgs {
@@ -63,6 +64,8 @@ struct CompactArgs {
   uint8_t* arena;
   uint64_t arenaCap;
   int32_t* status;
+  const int16_t* raw16;   // TileElementShort: raw tiles are copied from this 2-byte raster (pitch raw16Pitch), else nullptr
+  int64_t raw16Pitch;
 };
 
 struct ClassifyArgs {
@@ -100,6 +103,9 @@ cudaError_t launch_offsets(const uint32_t* lens, uint64_t* offsets, int nTiles, 
 cudaError_t launch_compact(const CompactArgs& a, int nTiles, cudaStream_t s);
 cudaError_t launch_classify(const ClassifyArgs& a, cudaStream_t s);
 cudaError_t launch_raw_decode(const DecodeArgs& a, int nTiles, cudaStream_t s);
+// TileElementShort (gvrs/TileElementShort.java:211-248): int16 raster <-> the int32 raster the codecs work on
+cudaError_t launch_widen_i16(const int16_t* src, int64_t srcPitch, int32_t* dst, int64_t rows, int64_t cols, int32_t fill, cudaStream_t s);
+cudaError_t launch_narrow_i16(const int32_t* src, int16_t* dst, int64_t dstPitch, int64_t rows, int64_t cols, cudaStream_t s);
 
 // ---- codec kernels -----------------------------------------------------------------------------
 // Host-side launchers (defined next to their kernels).  nCtas persistent CTAs of kThreads threads.

@@ -26,7 +26,7 @@
 extern "C" {
 #endif
 
-#define G4_ABI_VERSION 1
+#define G4_ABI_VERSION 2
 
 /* Status codes.  G4_DECLINED is the Java `null` return of ICompressionEncoder.encode ("codec cannot or
  * should not encode this tile": all-null tile, tile too small for the predictor, singular LSOP matrix).
@@ -56,7 +56,10 @@ enum {
 /* Predictor codes stored in packing[1] (C/compress/PredictorModelType.java:46-63). */
 enum { G4_PRED_NONE = 0, G4_PRED_DIFFERENCING = 1, G4_PRED_LINEAR = 2, G4_PRED_TRIANGLE = 3, G4_PRED_DIFF_NULLS = 4 };
 
-enum { G4_ELEM_I32 = 0, G4_ELEM_F32 = 1 };
+/* Sample types of a raster.  G4_ELEM_I16 mirrors TileElementShort (C/gvrs/TileElementShort.java:211-248): samples are
+ * widened to int for the codecs with fill_value -> INT4_NULL_CODE, a decoded INT4_NULL_CODE comes back as
+ * SHORT_NULL_CODE (-32768), and the raw form is 2 bytes per sample rounded up to a multiple of 4 (TileElement.java:85-93). */
+enum { G4_ELEM_I32 = 0, G4_ELEM_F32 = 1, G4_ELEM_I16 = 2 };
 enum { G4_MEM_HOST = 0, G4_MEM_DEVICE = 1 };
 
 #define G4_MAX_CODECS 16
@@ -75,10 +78,12 @@ typedef struct {
  * Tile t = tr * tiles_across + tc covers rows [tr*tile_rows, ...) and cols [tc*tile_cols, ...) of the
  * buffer passed as `grid` (whose first sample is the band's upper-left cell). */
 typedef struct {
-  int32_t elem_type; /* G4_ELEM_I32 or G4_ELEM_F32 */
+  int32_t elem_type; /* G4_ELEM_I32, G4_ELEM_F32 or G4_ELEM_I16 */
   int32_t tile_rows, tile_cols;
   int32_t tiles_down, tiles_across;
   int64_t grid_pitch; /* samples per raster row (>= tiles_across*tile_cols) */
+  int32_t fill_value; /* G4_ELEM_I16 encode only: the element's fill value, coded as null */
+  int32_t reserved;
 } g4_band_desc;
 
 int g4_abi_version(void);
