@@ -395,16 +395,19 @@ __device__ bool canon_fast_decode_text(CanonFastShared& S, uint32_t nBits, const
       }
     }
     __syncthreads();
-    // write pass: decode again, assembling escapes into values
+    // write pass: decode again, assembling escapes into values.  Every thread takes `rounds` CONSECUTIVE sub-sequences
+    // as one run (they are contiguous in the stream and in the value order), so the sink sees one long run per thread
+    // instead of one short run per sub-sequence.
     bool bad = false;
     const int last = fe < nSub - 1 ? fe : nSub - 1;
-#pragma unroll 1
-    for (int i = tid; i <= last; i += kThreads) {
-      uint32_t limit = T0 + uint32_t(i + 1) * B;
+    const int i0 = tid * int(rounds);
+    if (i0 <= last) {
+      const int i1 = i0 + int(rounds) - 1 < last ? i0 + int(rounds) - 1 : last;
+      uint32_t limit = T0 + uint32_t(i1 + 1) * B;
       if (limit > regionEnd) limit = regionEnd;
       BitCursor cur;
-      cur.init(S, S.startv[i]);
-      sink.begin(offv[i]);
+      cur.init(S, S.startv[i0]);
+      sink.begin(offv[i0]);
       bool have = false;
       uint32_t v = 0;
       for (;;) {
