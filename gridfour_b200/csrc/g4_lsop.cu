@@ -36,6 +36,8 @@ union LsopDecShared {
 // For shift >= 32 (|a| < 2^-9) the cast gives 0, and so does the shifted form with the shift clamped to 31
 // (the 24-bit significand shifts out completely: (0 + 1) >> 1 == 0, (-1 + 1) >> 1 == 0), which leaves one rare
 // branch for shift < 0 (|a| >= 2^24, infinities, NaN: saturating cast, NaN -> 0).
+// Integer form on purpose: floorf + __float2int_rd (FRND.FLOOR / F2I.FLOOR) measured 10x slower for the whole wavefront
+// kernel on sm_100a (15.3 ms instead of 1.5 ms), see profiles/README.md.
 __device__ __forceinline__ int32_t java_round(float a) {
   const int32_t bits = __float_as_int(a);
   const int shift = 149 - ((bits >> 23) & 0xff);
@@ -778,13 +780,18 @@ __global__ void __launch_bounds__(kThreads) lsop_wavefront_kernel(DecodeArgs a, 
 
 // ---- kernel B, vectorised: 4-column skew, int4 traffic, row groups pipelined back to back -----------------------------
 // Same recurrence and operation order as lsop_wavefront_kernel; used when every tile row is 16-byte aligned
-// (tile_cols % 4 == 0, grid_pitch % 4 == 0, aligned base).  Lane l owns rows 2+l, 34+l, ... and runs ONE 4-column
-// block behind lane l-1, so all lanes are at the same column phase: residuals are read and values written as int4.
-// Row r-1 at column c+2 is lane l-1's output of two steps ago (shuffle of its float history f2); row r-2 at column
-// c+2 is the oldest element lane l-1 still holds of ITS row above (shuffle of av[j]).  Lane 0 (and lane 1 for r-2)
-// read the rows of the previous 32-row group from L2, one iteration ahead of their use; a row takes P = max(C,136)
-// steps so that lane 31 of the previous group is always at least three blocks ahead of lane 0 of the next one and
-// the groups need no drain between them.
+// (tile_cols % 4 == 0, grid_pitch % 4 == 0, aligned base).  A warp walks the tile in groups of 30 rows.  Lane l runs ONE
+// 4-column block behind lane l-1, so all lanes are at the same column phase: one int4 load (residuals) and one int4
+// store (values) per lane and iteration, and nothing else touches memory.  Lanes 0 and 1 are FEEDERS: they own the two
+// finished rows above the group (rows 0,1 from kernel H, later the rows lanes 30,31 wrote for the previous group), load
+// them like any other lane and pass them through with all-zero coefficients, so every operand of a computing lane
+// arrives by shuffle from the lane above it and the loop has no lane-specific loads or selects:
+//   row r-1, column c+2 = lane l-1's output of two steps ago (its float history f2);
+//   row r-2, column c+2 = the oldest element lane l-1 still holds of ITS row above (its av[j]);
+//   columns 0,1 of both rows (needed once per row) = lane l-1's first two outputs / first two av elements of its
+//   previous block, shuffled before the windows shift.
+// A row takes P = max(C,136) steps so that lanes 30,31 of a group have stored a block (and passed the __syncwarp that
+// ends their iteration) at least one iteration before the next group's feeders fetch it; groups need no drain.
 __global__ void __launch_bounds__(kThreads, 4) lsop_wavefront4_kernel(DecodeArgs a, const float* coef) {
   const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
   const int li = blockIdx.x * kWarps + warp;
@@ -793,116 +800,88 @@ __global__ void __launch_bounds__(kThreads, 4) lsop_wavefront4_kernel(DecodeArgs
   if (a.status[tIdx] != G4_OK) return;
   const TileView t = tile_view(a.band, a.grid, tIdx);
   const int R = t.R, C = t.C;
+  const bool feeder = lane < 2;
   float u[12];
 #pragma unroll
-  for (int i = 0; i < 12; i++) u[i] = coef[size_t(tIdx) * 12 + i];
+  for (int i = 0; i < 12; i++) u[i] = feeder ? 0.f : coef[size_t(tIdx) * 12 + i];
   const int P = C > 136 ? C : 136;
   const int nB = P >> 2, cBlocks = C >> 2;
-  const int nGroups = (R - 2 + 31) >> 5;
+  const int nGroups = (R - 2 + 29) / 30;
   const int nIter = nGroups * nB + 31;
-  const int64_t pitch = t.pitch;
+  const int64_t wrapStep = 30 * t.pitch - 4 * int64_t(nB);  // block nB of row r -> block 0 of row r+30
   float av[8], bv[8];  // rows r-1 / r-2 as float, columns c0-2 .. c0+5
 #pragma unroll
   for (int i = 0; i < 8; i++) { av[i] = 0.f; bv[i] = 0.f; }
   float f1 = 0.f, f2 = 0.f;           // own row, columns c-1 and c-2
+  float pf0 = 0.f, pf1 = 0.f;         // own outputs 0,1 of the previous block as float (columns 0,1 for the lane below)
   int32_t h1 = 0;                     // own row, column c-1 (integer, for the two Triangle columns)
   int32_t po1 = 0, po2 = 0, po3 = 0;  // own outputs of the previous block (Triangle operands of the lane below)
-  // Operands that come from memory are fetched ONE ITERATION AHEAD so that their latency overlaps a block of arithmetic:
-  // the block's own four cells (residuals, or final values in columns 0,1), and for lanes 0,1 the rows written by the
-  // previous row group (lane 0: row r-1 and r-2, lane 1: row r-2; columns c0+2..c0+5).  The once-per-row operands
-  // (columns 0,1 of the rows above; lane 0's Triangle operands) are loaded where they are used.
-  // The fetch is branch-free: every lane issues the same five loads; lanes (or iterations) that do not need a value
-  // read the tile's first cells instead (one broadcast sector), which keeps the loop free of divergent control flow.
-  int4 vN;
-  int2 a0, a1, b0, b1;
-  int cb = -lane, r = 2 + lane;
-  int32_t* rowp = t.row(r < R ? r : 2);  // row r (any valid row while the lane has nothing to do)
-  const int32_t* const safe = t.base;
-  const bool l01 = lane < 2, l0 = lane == 0;
-  auto fetch = [&](const int32_t* rp, int cbX, bool actX) {
-    const int cX = cbX << 2;
-    const int32_t* pv = actX ? rp + cX : safe;
-    const int32_t* q2 = (actX && l01) ? rp - 2 * pitch + cX + 2 : safe;
-    const int32_t* q1 = (actX && l0) ? rp - pitch + cX + 2 : safe;
-    const int step = cX + 4 < C ? 2 : 0;  // columns C, C+1 do not exist; their operands are never used
-    vN = *reinterpret_cast<const int4*>(pv);
-    b0 = __ldcg(reinterpret_cast<const int2*>(q2));
-    b1 = __ldcg(reinterpret_cast<const int2*>(q2 + step));
-    a0 = __ldcg(reinterpret_cast<const int2*>(q1));
-    a1 = __ldcg(reinterpret_cast<const int2*>(q1 + step));
-  };
-  fetch(rowp, cb, cb == 0 && r < R);
+  int cb = -lane, r = lane;
+  int32_t* p = t.base + int64_t(r) * t.pitch + 4 * cb;  // block cb of row r; dereferenced only while in range
+  // The block's four cells (residuals; final values for the feeders and in columns 0,1) are fetched ONE ITERATION AHEAD.
+  // Plain loads are enough for the feeders: the rows they read were stored by lanes of this same warp at least two
+  // iterations earlier, and the __syncwarp that ends every iteration orders memory among the warp's lanes.
+  int4 vN = make_int4(0, 0, 0, 0);
+  if (cb == 0 && r < R) vN = *reinterpret_cast<const int4*>(p);
   for (int it = 0; it < nIter; it++) {
     const bool act = cb >= 0 && cb < cBlocks && r < R;
-    const int c0 = cb << 2;
-    // consume everything fetched during the previous iteration BEFORE issuing the next fetch
+    const bool first = cb == 0;
+    const bool triangle = cb == cBlocks - 1 && !feeder;
     const int4 v = vN;
-    const float m1[4] = {float(a0.x), float(a0.y), float(a1.x), float(a1.y)};
-    const float m2[4] = {float(b0.x), float(b0.y), float(b1.x), float(b1.y)};
-    int32_t* const rowCur = rowp;
-    {
-      int cbN = cb + 1;
-      if (cbN == nB) { cbN = 0; r += 32; rowp += 32 * pitch; }
-      fetch(rowp, cbN, cbN >= 0 && cbN < cBlocks && r < R);
-      cb = cbN;
-    }
+    int32_t* const cur = p;
+    cb++;
+    p += 4;
+    if (cb == nB) { cb = 0; r += 30; p += wrapStep; }
+    if (cb >= 0 && cb < cBlocks && r < R) vN = *reinterpret_cast<const int4*>(p);
+    // once-per-row operands, taken from the lane above BEFORE the windows shift (it finished its block 0 last iteration)
+    const float s0 = __shfl_up_sync(0xffffffffu, pf0, 1);
+    const float s1 = __shfl_up_sync(0xffffffffu, pf1, 1);
+    const float s2 = __shfl_up_sync(0xffffffffu, av[2], 1);
+    const float s3 = __shfl_up_sync(0xffffffffu, av[3], 1);
 #pragma unroll
     for (int i = 0; i < 4; i++) { av[i] = av[i + 4]; bv[i] = bv[i + 4]; }
-    if (act && c0 == 0) {  // row start (once per row): columns 0,1 of the two rows above, final since kernel H
-      const int2 s1 = __ldcg(reinterpret_cast<const int2*>(rowCur - pitch));
-      const int2 s2 = __ldcg(reinterpret_cast<const int2*>(rowCur - 2 * pitch));
-      av[2] = float(s1.x); av[3] = float(s1.y);
-      bv[2] = float(s2.x); bv[3] = float(s2.y);
-    }
-    const bool lastBlock = c0 == C - 4;
-    // Triangle columns: row r-1, columns C-3..C-1 = lane l-1's outputs of its previous (= its last) block; lane 0 reads
-    // them from the previous row group's memory (once per row)
-    int32_t upy = __shfl_up_sync(0xffffffffu, po1, 1);
-    int32_t upz = __shfl_up_sync(0xffffffffu, po2, 1);
-    int32_t upw = __shfl_up_sync(0xffffffffu, po3, 1);
-    if (lane == 0 && act && lastBlock) {
-      const int4 m = __ldcg(reinterpret_cast<const int4*>(rowCur - pitch + c0));
-      upy = m.y; upz = m.z; upw = m.w;
-    }
+    if (first) { av[2] = s0; av[3] = s1; bv[2] = s2; bv[3] = s3; }
+    // Triangle columns: row r-1, columns C-3..C-1 = lane l-1's outputs of its previous (= its last) block
+    const int32_t upy = __shfl_up_sync(0xffffffffu, po1, 1);
+    const int32_t upz = __shfl_up_sync(0xffffffffu, po2, 1);
+    const int32_t upw = __shfl_up_sync(0xffffffffu, po3, 1);
     int32_t out[4];
 #pragma unroll
     for (int j = 0; j < 4; j++) {
-      float ra = __shfl_up_sync(0xffffffffu, f2, 1);
-      float rb = __shfl_up_sync(0xffffffffu, av[j], 1);
-      if (lane == 0) ra = m1[j];
-      if (lane < 2) rb = m2[j];
-      av[4 + j] = ra;
-      bv[4 + j] = rb;
+      av[4 + j] = __shfl_up_sync(0xffffffffu, f2, 1);
+      bv[4 + j] = __shfl_up_sync(0xffffffffu, av[j], 1);
       const int32_t res = j == 0 ? v.x : j == 1 ? v.y : j == 2 ? v.z : v.w;
       // LsDecoder12.java:424-438 -- evaluated left to right in float32, no fused multiply-add.  Computed for every
       // column and discarded (select, no branch) for columns 0,1 and the two Triangle columns.
-      float p = u[0] * f1;
-      p = p + u[1] * av[j + 1];
-      p = p + u[2] * av[j + 2];
-      p = p + u[3] * av[j + 3];
-      p = p + u[4] * av[j + 4];
-      p = p + u[5] * f2;
-      p = p + u[6] * av[j];
-      p = p + u[7] * bv[j];
-      p = p + u[8] * bv[j + 1];
-      p = p + u[9] * bv[j + 2];
-      p = p + u[10] * bv[j + 3];
-      p = p + u[11] * bv[j + 4];
-      uint32_t add = uint32_t(java_round(p));
+      float q = u[0] * f1;
+      q = q + u[1] * av[j + 1];
+      q = q + u[2] * av[j + 2];
+      q = q + u[3] * av[j + 3];
+      q = q + u[4] * av[j + 4];
+      q = q + u[5] * f2;
+      q = q + u[6] * av[j];
+      q = q + u[7] * bv[j];
+      q = q + u[8] * bv[j + 1];
+      q = q + u[9] * bv[j + 2];
+      q = q + u[10] * bv[j + 3];
+      q = q + u[11] * bv[j + 4];
+      uint32_t add = uint32_t(java_round(q));
       if (j < 2) {
-        if (c0 == 0) add = 0u;  // columns 0,1 hold their final values already
+        if (first) add = 0u;  // columns 0,1 hold their final values already
       } else {
         // last two columns: Triangle predictor (LsDecoder12.java:459-468); tile_cols % 4 == 0 puts them at j = 2,3
         const int32_t upc = j == 2 ? upz : upw, upl = j == 2 ? upy : upz;
-        if (lastBlock) add = (uint32_t(h1) + uint32_t(upc)) - uint32_t(upl);
+        if (triangle) add = (uint32_t(h1) + uint32_t(upc)) - uint32_t(upl);
       }
       const int32_t val = int32_t(uint32_t(res) + add);
       out[j] = val;
       h1 = val;
       f2 = f1;
       f1 = float(val);
+      if (j == 0) pf0 = f1;
+      if (j == 1) pf1 = f1;
     }
-    if (act) *reinterpret_cast<int4*>(rowCur + c0) = make_int4(out[0], out[1], out[2], out[3]);
+    if (act && !feeder) *reinterpret_cast<int4*>(cur) = make_int4(out[0], out[1], out[2], out[3]);
     po1 = out[1]; po2 = out[2]; po3 = out[3];
     __syncwarp();
   }
