@@ -75,7 +75,13 @@ struct g4_context {
   DevBuf wide;         // TileElementShort: int32 staging raster around the integer codecs
   // zlib-stream encode stages (CodecDeflate, CodecFloat, LSOP12 Deflate alternative)
   DevBuf jobLen, jobOff, jobOut, jobTotal, streamIn, streamOut, deflateWork;
+  // staged zlib encode (streams <= deflate_staged_max() bytes): sorted positions, bucket ranks, match table, sort tables
+  DevBuf stSorted, stRank, stTable, stTabs, stWork, stCounters;
+  std::vector<uint64_t> hostOff;   // jobOff / jobLen mirrored on the host (chunking of the staged encode)
+  std::vector<uint32_t> hostLen;
+  uint64_t hostTotal = 0;
   int deflateWorkers = 0;   // resident stream-worker threads (0 = default, see g4_context_create)
+  uint64_t stagedChunkBytes = 1ull << 30;  // staged zlib encode: input bytes per chunk (scratch = 12x)
   bool lsopDeflate = true;  // LsEncoder12.deflateEnabled (lsop/LsEncoder12.java:78)
   // staging used by the host-memory entry points
   DevBuf sGrid, sArena, sOffsets, sLens, sCodec, sPred, sStatus;
@@ -109,30 +115,79 @@ int ensure_jobs(g4_context* ctx, int nStreams) {
 int prepare_streams(g4_context* ctx, int nStreams) {
   CK(launch_stream_offsets(ctx->jobLen.as<uint32_t>(), ctx->jobOff.as<uint64_t>(), nStreams, ctx->jobTotal.as<uint64_t>(), ctx->stream));
   uint64_t total = 0;
+  ctx->hostOff.resize(size_t(nStreams) + 1);
+  ctx->hostLen.resize(size_t(nStreams));
   CK(cudaMemcpyAsync(&total, ctx->jobTotal.p, 8, cudaMemcpyDeviceToHost, ctx->stream));
+  CK(cudaMemcpyAsync(ctx->hostOff.data(), ctx->jobOff.p, size_t(nStreams) * 8, cudaMemcpyDeviceToHost, ctx->stream));
+  CK(cudaMemcpyAsync(ctx->hostLen.data(), ctx->jobLen.p, size_t(nStreams) * 4, cudaMemcpyDeviceToHost, ctx->stream));
   CK(cudaStreamSynchronize(ctx->stream));
+  ctx->hostOff[size_t(nStreams)] = total;
+  ctx->hostTotal = total;
   CK(ctx->streamIn.ensure(total + 64));
   CK(ctx->streamOut.ensure(total + 112ull * uint64_t(nStreams) + 256));
   ctx->launches++;
   return G4_OK;
 }
+// zlib streams of the band: the staged kernels (sort / match / emit) take every stream of at most deflate_staged_max()
+// bytes, in chunks that bound the per-position scratch (12 bytes per input byte); longer streams go to the general
+// one-thread-per-stream kernel.
 int run_streams(g4_context* ctx, int nStreams, int capExtra, int level, int* counter) {
-  int nWorkers = nStreams < ctx->deflateWorkers ? nStreams : ctx->deflateWorkers;
-  nWorkers = (nWorkers + 31) / 32 * 32;
-  CK(ctx->deflateWork.ensure(size_t(nWorkers) * deflate_work_bytes()));
-  StreamArgs sa{};
-  sa.inBuf = ctx->streamIn.as<uint8_t>();
-  sa.inOff = ctx->jobOff.as<uint64_t>();
-  sa.inLen = ctx->jobLen.as<uint32_t>();
-  sa.outBuf = ctx->streamOut.as<uint8_t>();
-  sa.outLen = ctx->jobOut.as<uint32_t>();
-  sa.nStreams = nStreams;
-  sa.capExtra = capExtra;
-  sa.level = level;
-  sa.work = ctx->deflateWork.p;
-  sa.counter = counter;
-  CK(launch_deflate_streams(sa, nWorkers, ctx->stream));
-  ctx->launches++;
+  const uint32_t stagedMax = deflate_staged_max();
+  int nBig = 0;
+  for (int j = 0; j < nStreams; j++) nBig += ctx->hostLen[size_t(j)] > stagedMax;
+  if (nBig > 0) {
+    int nWorkers = nBig < ctx->deflateWorkers ? nBig : ctx->deflateWorkers;
+    nWorkers = (nWorkers + 31) / 32 * 32;
+    CK(ctx->deflateWork.ensure(size_t(nWorkers) * deflate_work_bytes()));
+    StreamArgs sa{};
+    sa.inBuf = ctx->streamIn.as<uint8_t>();
+    sa.inOff = ctx->jobOff.as<uint64_t>();
+    sa.inLen = ctx->jobLen.as<uint32_t>();
+    sa.outBuf = ctx->streamOut.as<uint8_t>();
+    sa.outLen = ctx->jobOut.as<uint32_t>();
+    sa.nStreams = nStreams;
+    sa.capExtra = capExtra;
+    sa.level = level;
+    sa.work = ctx->deflateWork.p;
+    sa.counter = counter;
+    sa.bigOnly = 1;
+    CK(launch_deflate_streams(sa, nWorkers, ctx->stream));
+    ctx->launches++;
+  }
+  const uint64_t budget = ctx->stagedChunkBytes;
+  CK(ctx->stCounters.ensure(4 * sizeof(int)));
+  int j0 = 0;
+  while (j0 < nStreams) {
+    int j1 = j0 + 1;
+    while (j1 < nStreams && ctx->hostOff[size_t(j1) + 1] - ctx->hostOff[size_t(j0)] <= budget) j1++;
+    const uint64_t base = ctx->hostOff[size_t(j0)];
+    const uint64_t span = ctx->hostOff[size_t(j1)] - base;
+    const int nChunk = j1 - j0;
+    CK(ctx->stSorted.ensure(span * 2 + 64));
+    CK(ctx->stRank.ensure(span * 2 + 64));
+    CK(ctx->stTable.ensure(span * 8 + 64));
+    CK(ctx->stWork.ensure(size_t(nChunk) * deflate_blocks_bytes()));
+    CK(cudaMemsetAsync(ctx->stCounters.p, 0, 4 * sizeof(int), ctx->stream));
+    StagedArgs st{};
+    st.inBuf = ctx->streamIn.as<uint8_t>();
+    st.inOff = ctx->jobOff.as<uint64_t>();
+    st.inLen = ctx->jobLen.as<uint32_t>();
+    st.outBuf = ctx->streamOut.as<uint8_t>();
+    st.outLen = ctx->jobOut.as<uint32_t>();
+    st.jBegin = j0;
+    st.jEnd = j1;
+    st.baseOff = base;
+    st.sorted = ctx->stSorted.as<uint16_t>();
+    st.rank = ctx->stRank.as<uint16_t>();
+    st.table = ctx->stTable.as<uint2>();
+    st.blocks = static_cast<DeflateBlocks*>(ctx->stWork.p);
+    st.capExtra = capExtra;
+    st.level = level;
+    st.counters = ctx->stCounters.as<int>();
+    CK(launch_deflate_staged(st, ctx->smCount, ctx->stream));
+    ctx->launches += 4;
+    j0 = j1;
+  }
   return G4_OK;
 }
 
@@ -522,6 +577,7 @@ int g4_context_create(int device, void* cuda_stream, g4_context** out) {
   // resident zlib-stream worker threads: each owns a ~310 KB hash/symbol work area in HBM
   ctx->deflateWorkers = ctx->smCount * 256;
   if (const char* e = std::getenv("G4_DEFLATE_WORKERS")) { int v = std::atoi(e); if (v >= 32) ctx->deflateWorkers = v; }
+  if (const char* e = std::getenv("G4_STAGED_CHUNK_MB")) { long v = std::atol(e); if (v >= 1) ctx->stagedChunkBytes = uint64_t(v) << 20; }
   if (cuda_stream) ctx->stream = static_cast<cudaStream_t>(cuda_stream);
   else {
     CK(cudaStreamCreateWithFlags(&ctx->stream, cudaStreamNonBlocking));
@@ -547,7 +603,8 @@ void g4_context_destroy(g4_context* ctx) {
   for (auto& b : ctx->slots) b.release();
   DevBuf* bufs[] = {&ctx->candLens, &ctx->candPreds, &ctx->candStatus, &ctx->counters, &ctx->scratch, &ctx->lists, &ctx->src,
                     &ctx->total, &ctx->coef, &ctx->defer, &ctx->lsopMeta, &ctx->wide, &ctx->encScratch, &ctx->region, &ctx->jobLen, &ctx->jobOff, &ctx->jobOut, &ctx->jobTotal,
-                    &ctx->streamIn, &ctx->streamOut, &ctx->deflateWork, &ctx->sGrid, &ctx->sArena, &ctx->sOffsets, &ctx->sLens, &ctx->sCodec, &ctx->sPred, &ctx->sStatus};
+                    &ctx->streamIn, &ctx->streamOut, &ctx->deflateWork, &ctx->stSorted, &ctx->stRank, &ctx->stTable, &ctx->stTabs,
+                    &ctx->stWork, &ctx->stCounters, &ctx->sGrid, &ctx->sArena, &ctx->sOffsets, &ctx->sLens, &ctx->sCodec, &ctx->sPred, &ctx->sStatus};
   for (DevBuf* b : bufs) b->release();
   if (ctx->ownStream) cudaStreamDestroy(ctx->stream);
   delete ctx;

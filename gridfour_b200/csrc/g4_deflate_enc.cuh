@@ -14,6 +14,7 @@
 // comes from streams: thousands of (tile, predictor) streams are in flight, one per thread, with their hash
 // tables and symbol buffers in HBM scratch.
 #pragma once
+#include <cstddef>
 #include <cstdint>
 #include <cuda_runtime.h>
 
@@ -66,15 +67,20 @@ struct CtData {
   uint16_t dl;  // dad or length
 };
 
-// Per-stream work area in HBM.
-struct DeflateWork {
-  uint32_t head[kDefWSize];
-  uint32_t prev[kDefWSize];
-  uint16_t symDist[kDefLitBufSize];
-  uint8_t symLc[kDefLitBufSize];
+// Huffman construction state of one block (trees.c): small enough for shared memory.
+struct DeflateTrees {
   CtData ltree[kDefHeapSize], dtree[2 * kDefDCodes + 1], bltree[2 * kDefBlCodes + 1];
   int16_t heap[kDefHeapSize];
   uint8_t depth[kDefHeapSize];
+};
+
+// Per-stream work area in HBM (one-thread-per-stream encoder).
+struct DeflateWork {
+  uint16_t symDist[kDefLitBufSize];
+  uint8_t symLc[kDefLitBufSize];
+  DeflateTrees T;
+  uint32_t head[kDefWSize];
+  uint32_t prev[kDefWSize];
 };
 
 struct DeflateOut {
@@ -139,7 +145,8 @@ G4_HD __forceinline__ int def_extra_bits(const DeflateTreeDesc& d, int n) {
 G4_HD __forceinline__ int def_static_len(const DeflateTreeDesc& d, int n) { return d.kind == 0 ? def_static_llen(n) : d.kind == 1 ? 5 : 0; }
 
 struct DeflateState {
-  DeflateWork* W;
+  DeflateWork* W;    // symbol buffer (and hash chains) of the serial encoder; unused by the tree code
+  DeflateTrees* T;
   unsigned long long optLen, staticLen;
   int heapLen, heapMax;
   uint16_t blCount[16];
@@ -150,8 +157,8 @@ G4_HD __forceinline__ bool def_smaller(const CtData* tree, int n, int m, const u
 }
 
 G4_HD inline void def_pqdownheap(DeflateState& s, const CtData* tree, int k) {
-  int16_t* heap = s.W->heap;
-  const uint8_t* depth = s.W->depth;
+  int16_t* heap = s.T->heap;
+  const uint8_t* depth = s.T->depth;
   int v = heap[k];
   int j = k << 1;
   while (j <= s.heapLen) {
@@ -167,7 +174,7 @@ G4_HD inline void def_pqdownheap(DeflateState& s, const CtData* tree, int k) {
 // trees.c gen_bitlen
 G4_HD inline void def_gen_bitlen(DeflateState& s, DeflateTreeDesc& d) {
   CtData* tree = d.tree;
-  int16_t* heap = s.W->heap;
+  int16_t* heap = s.T->heap;
   const int maxLength = d.maxLength;
   for (int b = 0; b <= 15; b++) s.blCount[b] = 0;
   tree[heap[s.heapMax]].dl = 0;
@@ -211,8 +218,8 @@ G4_HD inline void def_gen_bitlen(DeflateState& s, DeflateTreeDesc& d) {
 // trees.c build_tree (+ gen_codes)
 G4_HD inline void def_build_tree(DeflateState& s, DeflateTreeDesc& d) {
   CtData* tree = d.tree;
-  int16_t* heap = s.W->heap;
-  uint8_t* depth = s.W->depth;
+  int16_t* heap = s.T->heap;
+  uint8_t* depth = s.T->depth;
   const int elems = d.elems;
   int maxCode = -1;
   s.heapLen = 0;
@@ -259,7 +266,7 @@ G4_HD inline void def_build_tree(DeflateState& s, DeflateTreeDesc& d) {
 
 // trees.c scan_tree: run-length statistics of a code-length sequence into the bit-length tree
 G4_HD inline void def_scan_tree(DeflateState& s, CtData* tree, int maxCode) {
-  CtData* bl = s.W->bltree;
+  CtData* bl = s.T->bltree;
   int prevlen = -1, nextlen = tree[0].dl, count = 0, maxCount = 7, minCount = 4;
   if (nextlen == 0) { maxCount = 138; minCount = 3; }
   tree[maxCode + 1].dl = 0xffff;  // guard
@@ -280,8 +287,9 @@ G4_HD inline void def_scan_tree(DeflateState& s, CtData* tree, int maxCode) {
 }
 
 // trees.c send_tree
-G4_HD inline void def_send_tree(DeflateState& s, DeflateOut& o, CtData* tree, int maxCode) {
-  const CtData* bl = s.W->bltree;
+template <class Out>
+G4_HD inline void def_send_tree(DeflateState& s, Out& o, CtData* tree, int maxCode) {
+  const CtData* bl = s.T->bltree;
   int prevlen = -1, nextlen = tree[0].dl, count = 0, maxCount = 7, minCount = 4;
   if (nextlen == 0) { maxCount = 138; minCount = 3; }
   for (int n = 0; n <= maxCode; n++) {
@@ -304,7 +312,7 @@ G4_HD inline void def_send_tree(DeflateState& s, DeflateOut& o, CtData* tree, in
 }
 
 G4_HD inline void def_init_block(DeflateState& s) {
-  DeflateWork* W = s.W;
+  DeflateTrees* W = s.T;
   for (int n = 0; n < kDefLCodes; n++) W->ltree[n].fc = 0;
   for (int n = 0; n < kDefDCodes; n++) W->dtree[n].fc = 0;
   for (int n = 0; n < kDefBlCodes; n++) W->bltree[n].fc = 0;
@@ -314,10 +322,10 @@ G4_HD inline void def_init_block(DeflateState& s) {
 
 // trees.c compress_block
 G4_HD inline void def_compress_block(DeflateState& s, DeflateOut& o, int nSym, bool useStatic) {
-  const DeflateWork* W = s.W;
+  const DeflateTrees* W = s.T;
   for (int i = 0; i < nSym; i++) {
-    unsigned dist = W->symDist[i];
-    int lc = W->symLc[i];
+    unsigned dist = s.W->symDist[i];
+    int lc = s.W->symLc[i];
     if (dist == 0) {
       if (useStatic) o.send_bits(def_static_lcode(lc), def_static_llen(lc));
       else o.send_bits(W->ltree[lc].fc, W->ltree[lc].dl);
@@ -340,11 +348,17 @@ G4_HD inline void def_compress_block(DeflateState& s, DeflateOut& o, int nSym, b
   else o.send_bits(W->ltree[256].fc, W->ltree[256].dl);
 }
 
-// trees.c _tr_flush_block
-G4_HD inline void def_flush_block(DeflateState& s, DeflateOut& o, const uint8_t* buf, uint32_t storedLen, int nSym, bool last,
-                                  bool storedOk) {
-  DeflateWork* W = s.W;
+// trees.c _tr_flush_block, first half: Huffman trees of the block and the stored / fixed / dynamic choice.
+struct DeflateBlockPlan {
+  int type;  // 0 stored, 1 fixed, 2 dynamic
+  int lMaxCode, dMaxCode, maxBlIndex;
+};
+G4_HD __forceinline__ int def_bl_order(int i) {
   const uint8_t blOrder[19] = {16, 17, 18, 0, 8, 7, 9, 6, 10, 5, 11, 4, 12, 3, 13, 2, 14, 1, 15};
+  return blOrder[i];
+}
+G4_HD inline DeflateBlockPlan def_plan_block(DeflateState& s, uint32_t storedLen, bool storedOk) {
+  DeflateTrees* W = s.T;
   DeflateTreeDesc ld{W->ltree, kDefLCodes, 15, 257, 0, 0};
   DeflateTreeDesc dd{W->dtree, kDefDCodes, 15, 0, 1, 0};
   DeflateTreeDesc bd{W->bltree, kDefBlCodes, 7, 0, 2, 0};
@@ -356,12 +370,35 @@ G4_HD inline void def_flush_block(DeflateState& s, DeflateOut& o, const uint8_t*
   def_build_tree(s, bd);
   int maxBlIndex;
   for (maxBlIndex = kDefBlCodes - 1; maxBlIndex >= 3; maxBlIndex--)
-    if (W->bltree[blOrder[maxBlIndex]].dl != 0) break;
+    if (W->bltree[def_bl_order(maxBlIndex)].dl != 0) break;
   s.optLen += 3ull * (maxBlIndex + 1) + 5 + 5 + 4;
   unsigned long long optLenb = (s.optLen + 3 + 7) >> 3;
   unsigned long long staticLenb = (s.staticLen + 3 + 7) >> 3;
   if (staticLenb <= optLenb) optLenb = staticLenb;
-  if (storedLen + 4ull <= optLenb && storedOk) {
+  DeflateBlockPlan P;
+  P.lMaxCode = ld.maxCode;
+  P.dMaxCode = dd.maxCode;
+  P.maxBlIndex = maxBlIndex;
+  P.type = (storedLen + 4ull <= optLenb && storedOk) ? 0 : staticLenb == optLenb ? 1 : 2;
+  return P;
+}
+// header of a dynamic block after the 3 type bits (trees.c send_all_trees)
+template <class Out>
+G4_HD inline void def_send_all_trees(DeflateState& s, Out& o, const DeflateBlockPlan& P) {
+  DeflateTrees* W = s.T;
+  o.send_bits(uint32_t(P.lMaxCode + 1 - 257), 5);
+  o.send_bits(uint32_t(P.dMaxCode + 1 - 1), 5);
+  o.send_bits(uint32_t(P.maxBlIndex + 1 - 4), 4);
+  for (int rank = 0; rank <= P.maxBlIndex; rank++) o.send_bits(W->bltree[def_bl_order(rank)].dl, 3);
+  def_send_tree(s, o, W->ltree, P.lMaxCode);
+  def_send_tree(s, o, W->dtree, P.dMaxCode);
+}
+
+// trees.c _tr_flush_block
+G4_HD inline void def_flush_block(DeflateState& s, DeflateOut& o, const uint8_t* buf, uint32_t storedLen, int nSym, bool last,
+                                  bool storedOk) {
+  const DeflateBlockPlan P = def_plan_block(s, storedLen, storedOk);
+  if (P.type == 0) {
     o.send_bits(uint32_t(0 << 1) + (last ? 1u : 0u), 3);
     o.windup();
     o.put_byte(storedLen & 0xff);
@@ -369,17 +406,12 @@ G4_HD inline void def_flush_block(DeflateState& s, DeflateOut& o, const uint8_t*
     o.put_byte((~storedLen) & 0xff);
     o.put_byte(((~storedLen) >> 8) & 0xff);
     for (uint32_t i = 0; i < storedLen; i++) o.put_byte(buf[i]);
-  } else if (staticLenb == optLenb) {
+  } else if (P.type == 1) {
     o.send_bits((1u << 1) + (last ? 1u : 0u), 3);
     def_compress_block(s, o, nSym, true);
   } else {
     o.send_bits((2u << 1) + (last ? 1u : 0u), 3);
-    o.send_bits(uint32_t(ld.maxCode + 1 - 257), 5);
-    o.send_bits(uint32_t(dd.maxCode + 1 - 1), 5);
-    o.send_bits(uint32_t(maxBlIndex + 1 - 4), 4);
-    for (int rank = 0; rank <= maxBlIndex; rank++) o.send_bits(W->bltree[blOrder[rank]].dl, 3);
-    def_send_tree(s, o, W->ltree, ld.maxCode);
-    def_send_tree(s, o, W->dtree, dd.maxCode);
+    def_send_all_trees(s, o, P);
     def_compress_block(s, o, nSym, false);
   }
   def_init_block(s);
@@ -398,6 +430,7 @@ G4_HD inline uint32_t deflate_stream(const uint8_t* in, uint32_t n, uint8_t* out
   const DeflateLevel L = deflate_level(level);
   DeflateState s;
   s.W = W;
+  s.T = &W->T;
   DeflateOut o{out, cap, 0, 0, 0, false};
   o.put_byte(L.zlibHeader >> 8);
   o.put_byte(L.zlibHeader & 0xff);
@@ -423,7 +456,7 @@ G4_HD inline uint32_t deflate_stream(const uint8_t* in, uint32_t n, uint8_t* out
     W->symDist[nSym] = 0;
     W->symLc[nSym] = uint8_t(c);
     nSym++;
-    W->ltree[c].fc++;
+    W->T.ltree[c].fc++;
     return nSym == kDefLitBufSize - 1;
   };
   auto tally_dist = [&](uint32_t dist, uint32_t lc) -> bool {
@@ -431,8 +464,8 @@ G4_HD inline uint32_t deflate_stream(const uint8_t* in, uint32_t n, uint8_t* out
     W->symLc[nSym] = uint8_t(lc);
     nSym++;
     dist--;
-    W->ltree[def_length_code(int(lc)) + 257].fc++;
-    W->dtree[def_dist_code(int(dist))].fc++;
+    W->T.ltree[def_length_code(int(lc)) + 257].fc++;
+    W->T.dtree[def_dist_code(int(dist))].fc++;
     return nSym == kDefLitBufSize - 1;
   };
   auto flush = [&](bool last) {
@@ -531,6 +564,266 @@ G4_HD inline uint32_t deflate_stream(const uint8_t* in, uint32_t n, uint8_t* out
   o.put_byte(s1 >> 8);
   o.put_byte(s1 & 0xff);
   return o.overflow ? cap : o.pos;
+}
+
+// =====================================================================================================================
+// Staged form of the same encoder for streams of at most kDefStagedMax bytes (no window slide: zlib loads the whole
+// input at once and positions fit 16 bits).  deflate_slow inserts EVERY position p <= n-3 into the hash chains, in
+// order, whether or not it searches there, so the chain of p -- "earlier positions with the same 3-byte hash, nearest
+// first" -- is a property of the input alone.  That splits the work into
+//   sort    positions ordered by (hash, position): the chain of the position in slot i is slots i-1, i-2, ... of its
+//           bucket (rank[i] = number of earlier positions in the bucket),
+//   match   for EVERY position, in parallel, longest_match() over that list: once with the level's full chain length
+//           and once with a quarter of it (the walk zlib does when prev_length >= good_match), started from
+//           best_len = 2.  Starting from 2 instead of prev_length changes nothing that the caller can observe: the
+//           walk visits the same candidates and stops at the same nice_match candidate, so its result is the
+//           first-in-chain longest candidate, which zlib's walk also ends with whenever that is longer than prev_length
+//           -- and when it is not, both forms leave match_length <= prev_length and the previous match is emitted,
+//   emit    the serial lazy-evaluation loop (one thread per stream) reads the table instead of walking chains, and
+//           produces the same symbols, blocks and bytes as deflate_stream().
+// =====================================================================================================================
+constexpr uint32_t kDefStagedMax = 65535;
+
+// Table entry: match length (9 bits, 2 = none) | distance << 9.
+G4_HD __forceinline__ uint32_t def_pack_match(int len, uint32_t dist) { return uint32_t(len) | (dist << 9); }
+
+// longest_match for the position in `slot` of the stream's sorted position list.  x = full chain, y = quarter chain.
+G4_HD inline uint2 def_find_match(const uint8_t* in, uint32_t n, const DeflateLevel& L, const uint16_t* sorted, uint32_t slot,
+                                  uint32_t rank) {
+  const uint32_t p = sorted[slot];
+  const uint32_t lookahead = n - p;
+  const int maxLen = lookahead < uint32_t(kDefMaxMatch) ? int(lookahead) : kDefMaxMatch;
+  const int niceMatch = uint32_t(L.niceLength) > lookahead ? int(lookahead) : L.niceLength;
+  const uint32_t limit = p > uint32_t(kDefMaxDist) ? p - uint32_t(kDefMaxDist) : 0u;
+  const uint32_t nCand = rank < uint32_t(L.maxChain) ? rank : uint32_t(L.maxChain);
+  const uint32_t quarter = uint32_t(L.maxChain) >> 2;
+  const uint8_t* scan = in + p;
+  int bestLen = kDefMinMatch - 1;
+  uint32_t bestStart = 0;
+  uint8_t scanEnd1 = scan[bestLen - 1], scanEnd = scan[bestLen];
+  const uint8_t s0 = scan[0], s1 = scan[1];
+  uint32_t quarterEntry = 0;
+  bool haveQuarter = false;
+  for (uint32_t k = 1; k <= nCand; k++) {
+    if (k - 1 == quarter) { quarterEntry = def_pack_match(bestLen, p - bestStart); haveQuarter = true; }
+    const uint32_t cur = sorted[slot - k];
+    // the first candidate may sit at distance MAX_DIST exactly (deflate_slow tests strstart - hash_head <= MAX_DIST),
+    // later ones must be nearer (longest_match continues while cur_match > limit); position 0 doubles as NIL
+    if (k == 1 ? (cur == 0 || p - cur > uint32_t(kDefMaxDist)) : cur <= limit) break;
+    const uint8_t* match = in + cur;
+    if (match[bestLen] == scanEnd && match[bestLen - 1] == scanEnd1 && match[0] == s0 && match[1] == s1) {
+      int len = 2;
+      while (len < maxLen && scan[len] == match[len]) len++;
+      if (len > bestLen) {
+        bestStart = cur;
+        bestLen = len;
+        if (len >= niceMatch) break;
+        scanEnd1 = scan[bestLen - 1];
+        scanEnd = scan[bestLen];
+      }
+    }
+  }
+  const uint32_t full = def_pack_match(bestLen, p - bestStart);
+  return make_uint2(full, haveQuarter ? quarterEntry : full);
+}
+
+// deflate_stream() with longest_match replaced by the table (table[p] for every p <= n-3).  n <= kDefStagedMax.
+G4_HD inline uint32_t deflate_stream_table(const uint8_t* in, uint32_t n, uint8_t* out, uint32_t cap, DeflateWork* W, int level,
+                                           const uint2* table) {
+  const DeflateLevel L = deflate_level(level);
+  DeflateState s;
+  s.W = W;
+  s.T = &W->T;
+  DeflateOut o{out, cap, 0, 0, 0, false};
+  o.put_byte(L.zlibHeader >> 8);
+  o.put_byte(L.zlibHeader & 0xff);
+  def_init_block(s);
+  uint32_t strstart = 0, blockStart = 0, matchStart = 0, prevMatch = 0;
+  int matchLength = kDefMinMatch - 1, prevLength = kDefMinMatch - 1;
+  bool matchAvailable = false;
+  int nSym = 0;
+  auto tally_lit = [&](uint32_t c) -> bool {
+    W->symDist[nSym] = 0;
+    W->symLc[nSym] = uint8_t(c);
+    nSym++;
+    W->T.ltree[c].fc++;
+    return nSym == kDefLitBufSize - 1;
+  };
+  auto tally_dist = [&](uint32_t dist, uint32_t lc) -> bool {
+    W->symDist[nSym] = uint16_t(dist);
+    W->symLc[nSym] = uint8_t(lc);
+    nSym++;
+    dist--;
+    W->T.ltree[def_length_code(int(lc)) + 257].fc++;
+    W->T.dtree[def_dist_code(int(dist))].fc++;
+    return nSym == kDefLitBufSize - 1;
+  };
+  auto flush = [&](bool last) {
+    def_flush_block(s, o, in + blockStart, strstart - blockStart, nSym, last, true);
+    blockStart = strstart;
+    nSym = 0;
+  };
+  while (strstart < n) {
+    const uint32_t lookahead = n - strstart;
+    prevLength = matchLength;
+    prevMatch = matchStart;
+    matchLength = kDefMinMatch - 1;
+    if (lookahead >= uint32_t(kDefMinMatch) && prevLength < L.maxLazy) {
+      const uint2 e = table[strstart];
+      const uint32_t w = prevLength >= L.goodLength ? e.y : e.x;
+      const int len = int(w & 0x1ffu);
+      if (len > prevLength) {
+        matchLength = len;
+        matchStart = strstart - (w >> 9);
+        if (matchLength == kDefMinMatch && strstart - matchStart > uint32_t(kDefTooFar)) matchLength = kDefMinMatch - 1;
+      }
+    }
+    if (prevLength >= kDefMinMatch && matchLength <= prevLength) {
+      const bool bflush = tally_dist(strstart - 1 - prevMatch, uint32_t(prevLength - kDefMinMatch));
+      strstart += uint32_t(prevLength - 1);
+      matchAvailable = false;
+      matchLength = kDefMinMatch - 1;
+      if (bflush) flush(false);
+    } else if (matchAvailable) {
+      const bool bflush = tally_lit(in[strstart - 1]);
+      if (bflush) flush(false);
+      strstart++;
+    } else {
+      matchAvailable = true;
+      strstart++;
+    }
+  }
+  if (matchAvailable) tally_lit(in[strstart - 1]);
+  flush(true);
+  uint32_t s1 = 1, s2 = 0;
+  for (uint32_t i = 0; i < n;) {
+    uint32_t chunk = n - i < 5552u ? n - i : 5552u;
+    for (uint32_t k = 0; k < chunk; k++) { s1 += in[i + k]; s2 += s1; }
+    s1 %= 65521u;
+    s2 %= 65521u;
+    i += chunk;
+  }
+  o.put_byte(s2 >> 8);
+  o.put_byte(s2 & 0xff);
+  o.put_byte(s1 >> 8);
+  o.put_byte(s1 & 0xff);
+  return o.overflow ? cap : o.pos;
+}
+
+// ---- staged form, split for the device: decisions (one thread per stream) / block emission (one CTA per stream) --------
+constexpr int kDefMaxBlocks = 8;  // <= 65535 symbols in blocks of 16383, plus a possibly empty final block
+struct DeflateBlocks {
+  uint32_t nBlocks;
+  uint32_t symEnd[kDefMaxBlocks];  // symbols [symEnd[b-1], symEnd[b]) belong to block b
+  uint32_t posEnd[kDefMaxBlocks];  // input bytes [posEnd[b-1], posEnd[b]) are what a stored block b would carry
+};
+
+// The lazy-evaluation loop of deflate_stream_table() alone: writes the symbol list (dist 0 = literal) and the block
+// boundaries zlib's symbol buffer (16383 entries) imposes.
+G4_HD inline void deflate_decide_table(const uint8_t* in, uint32_t n, int level, const uint2* table, uint16_t* symDist, uint8_t* symLc,
+                                       DeflateBlocks* B) {
+  const DeflateLevel L = deflate_level(level);
+  uint32_t strstart = 0, matchStart = 0, prevMatch = 0, k = 0, inBlock = 0, nBlocks = 0;
+  int matchLength = kDefMinMatch - 1, prevLength = kDefMinMatch - 1;
+  bool matchAvailable = false;
+  auto tally = [&](uint32_t dist, uint32_t lc) -> bool {
+    symDist[k] = uint16_t(dist);
+    symLc[k] = uint8_t(lc);
+    k++;
+    return ++inBlock == uint32_t(kDefLitBufSize - 1);
+  };
+  auto flush = [&]() {
+    B->symEnd[nBlocks] = k;
+    B->posEnd[nBlocks] = strstart;
+    nBlocks++;
+    inBlock = 0;
+  };
+  while (strstart < n) {
+    const uint32_t lookahead = n - strstart;
+    prevLength = matchLength;
+    prevMatch = matchStart;
+    matchLength = kDefMinMatch - 1;
+    if (lookahead >= uint32_t(kDefMinMatch) && prevLength < L.maxLazy) {
+      const uint2 e = table[strstart];
+      const uint32_t w = prevLength >= L.goodLength ? e.y : e.x;
+      const int len = int(w & 0x1ffu);
+      if (len > prevLength) {
+        matchLength = len;
+        matchStart = strstart - (w >> 9);
+        if (matchLength == kDefMinMatch && strstart - matchStart > uint32_t(kDefTooFar)) matchLength = kDefMinMatch - 1;
+      }
+    }
+    if (prevLength >= kDefMinMatch && matchLength <= prevLength) {
+      const bool bflush = tally(strstart - 1 - prevMatch, uint32_t(prevLength - kDefMinMatch));
+      strstart += uint32_t(prevLength - 1);
+      matchAvailable = false;
+      matchLength = kDefMinMatch - 1;
+      if (bflush) flush();
+    } else if (matchAvailable) {
+      const bool bflush = tally(0, in[strstart - 1]);
+      if (bflush) flush();
+      strstart++;
+    } else {
+      matchAvailable = true;
+      strstart++;
+    }
+  }
+  if (matchAvailable) tally(0, in[strstart - 1]);
+  flush();
+  B->nBlocks = nBlocks;
+}
+
+// Serial emission of the blocks deflate_decide_table() produced (host harness; the device emits them CTA-parallel in
+// g4_deflate_encode.cu with the same plan / header / code functions).
+inline uint32_t deflate_emit_blocks_serial(const uint8_t* in, uint32_t n, uint8_t* out, uint32_t cap, DeflateWork* W, int level,
+                                           const uint16_t* symDist, const uint8_t* symLc, const DeflateBlocks& B) {
+  const DeflateLevel L = deflate_level(level);
+  DeflateState s;
+  s.W = W;
+  s.T = &W->T;
+  DeflateOut o{out, cap, 0, 0, 0, false};
+  o.put_byte(L.zlibHeader >> 8);
+  o.put_byte(L.zlibHeader & 0xff);
+  uint32_t sym0 = 0, pos0 = 0;
+  for (uint32_t b = 0; b < B.nBlocks; b++) {
+    def_init_block(s);
+    const uint32_t nSym = B.symEnd[b] - sym0;
+    for (uint32_t i = 0; i < nSym; i++) {
+      const uint32_t dist = symDist[sym0 + i], lc = symLc[sym0 + i];
+      W->symDist[i] = uint16_t(dist);
+      W->symLc[i] = uint8_t(lc);
+      if (dist == 0) W->T.ltree[lc].fc++;
+      else { W->T.ltree[def_length_code(int(lc)) + 257].fc++; W->T.dtree[def_dist_code(int(dist - 1))].fc++; }
+    }
+    def_flush_block(s, o, in + pos0, B.posEnd[b] - pos0, int(nSym), b + 1 == B.nBlocks, true);
+    sym0 = B.symEnd[b];
+    pos0 = B.posEnd[b];
+  }
+  uint32_t s1 = 1, s2 = 0;
+  for (uint32_t i = 0; i < n; i++) { s1 = (s1 + in[i]) % 65521u; s2 = (s2 + s1) % 65521u; }
+  o.put_byte(s2 >> 8);
+  o.put_byte(s2 & 0xff);
+  o.put_byte(s1 >> 8);
+  o.put_byte(s1 & 0xff);
+  return o.overflow ? cap : o.pos;
+}
+
+// Serial construction of the sorted position list (host harness / reference for the warp-cooperative device version).
+inline void def_sort_positions_host(const uint8_t* in, uint32_t n, uint16_t* sorted, uint16_t* rank) {
+  if (n < 3) return;
+  const uint32_t nPos = n - 2;
+  static uint32_t cnt[kDefWSize + 1];
+  for (int i = 0; i <= kDefWSize; i++) cnt[i] = 0;
+  for (uint32_t p = 0; p < nPos; p++) cnt[def_hash3(in + p) + 1]++;
+  for (int i = 0; i < kDefWSize; i++) cnt[i + 1] += cnt[i];
+  static uint32_t start[kDefWSize];
+  for (int i = 0; i < kDefWSize; i++) start[i] = cnt[i];
+  for (uint32_t p = 0; p < nPos; p++) {
+    const uint32_t h = def_hash3(in + p);
+    const uint32_t slot = cnt[h]++;
+    sorted[slot] = uint16_t(p);
+    rank[slot] = uint16_t(slot - start[h]);
+  }
 }
 
 }  // namespace g4

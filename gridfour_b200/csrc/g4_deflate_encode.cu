@@ -17,6 +17,7 @@
 #include "g4_predict.cuh"
 #include "g4_m32stream.cuh"
 #include "g4_deflate_enc.cuh"
+#include "g4_bitpack.cuh"
 
 namespace g4 {
 
@@ -53,15 +54,360 @@ __global__ void __launch_bounds__(kThreads) stream_offsets_kernel(const uint32_t
 }
 
 // ---- one thread per zlib stream ---------------------------------------------------------------------------------
+// General form (any length; the only one for streams longer than kDefStagedMax).  With a.bigOnly set it leaves the
+// short streams to the staged kernels below.
 __global__ void __launch_bounds__(32) deflate_streams_kernel(StreamArgs a) {
   DeflateWork* W = static_cast<DeflateWork*>(a.work) + (size_t(blockIdx.x) * blockDim.x + threadIdx.x);
   for (;;) {
     const int j = atomicAdd(a.counter, 1);
     if (j >= a.nStreams) break;
     const uint32_t n = a.inLen[j];
+    if (a.bigOnly && n <= kDefStagedMax) continue;
     if (n == 0) { a.outLen[j] = 0; continue; }  // stream not produced (tile declined by the size stage)
     const uint64_t off = a.inOff[j];
     a.outLen[j] = deflate_stream(a.inBuf + off, n, a.outBuf + off + 112ull * uint64_t(j), n + uint32_t(a.capExtra), W, a.level);
+  }
+}
+
+// ---- staged form for streams of at most kDefStagedMax bytes (g4_deflate_enc.cuh, "Staged form") ------------------------
+// sort: one WARP (a 32-thread CTA) per stream, bucket cursors (32768 x uint16 = 64 KB) in shared memory.  Positions are
+// taken 32 at a time in stream order; __match_any_sync groups the lanes of a chunk by hash, so a position's slot is
+// (bucket cursor) + (lanes below it with the same hash) and the highest lane of every group advances the cursor by the
+// group's size.  Pass 1 counts, a warp scan turns counts into bucket starts, pass 2 assigns slots (and parks the hash in
+// rank[]), pass 3 turns the parked hash into the rank: after pass 2 the cursor of bucket h-1 is the start of bucket h.
+// Eight chunks of hashes are loaded ahead of the serial cursor updates so that their latency overlaps.
+__global__ void __launch_bounds__(32) deflate_sort_kernel(StagedArgs a) {
+  extern __shared__ uint16_t sortTab[];
+  const int lane = threadIdx.x;
+  const uint32_t ltMask = (1u << lane) - 1u;
+  for (;;) {
+    int j = 0;
+    if (lane == 0) j = a.jBegin + atomicAdd(a.counters + 0, 1);
+    j = __shfl_sync(0xffffffffu, j, 0);
+    if (j >= a.jEnd) break;
+    const uint32_t n = a.inLen[j];
+    if (n < 3 || n > kDefStagedMax) continue;
+    const uint64_t off = a.inOff[j];
+    const uint8_t* in = a.inBuf + off;
+    uint16_t* sorted = a.sorted + (off - a.baseOff);
+    uint16_t* rank = a.rank + (off - a.baseOff);
+    const uint32_t nPos = n - 2;
+    __syncwarp();
+    {
+      uint4* t4 = reinterpret_cast<uint4*>(sortTab);
+      for (int i = lane; i < kDefWSize * 2 / 16; i += 32) t4[i] = make_uint4(0, 0, 0, 0);
+    }
+    __syncwarp();
+    for (uint32_t base = 0; base < nPos; base += 256) {
+      uint32_t h[8];
+#pragma unroll
+      for (int c = 0; c < 8; c++) {
+        const uint32_t p = base + uint32_t(c) * 32u + uint32_t(lane);
+        h[c] = p < nPos ? def_hash3(in + p) : (0x10000u | uint32_t(lane));
+      }
+#pragma unroll
+      for (int c = 0; c < 8; c++) {
+        const uint32_t m = __match_any_sync(0xffffffffu, h[c]);
+        if (h[c] < 0x10000u && (m >> lane) == 1u) sortTab[h[c]] = uint16_t(sortTab[h[c]] + __popc(m));
+        __syncwarp();
+      }
+    }
+    {  // exclusive scan of the 32768 counts, two per lane and step
+      uint32_t* t32 = reinterpret_cast<uint32_t*>(sortTab);
+      uint32_t carry = 0;
+      for (int i0 = 0; i0 < kDefWSize / 2; i0 += 32) {
+        const uint32_t v = t32[i0 + lane];
+        const uint32_t c0 = v & 0xffffu, c1 = v >> 16;
+        uint32_t inc = c0 + c1;
+#pragma unroll
+        for (int d = 1; d < 32; d <<= 1) {
+          const uint32_t y = __shfl_up_sync(0xffffffffu, inc, d);
+          if (lane >= d) inc += y;
+        }
+        const uint32_t ex = carry + inc - (c0 + c1);
+        t32[i0 + lane] = (ex & 0xffffu) | ((ex + c0) << 16);
+        carry += __shfl_sync(0xffffffffu, inc, 31);
+      }
+    }
+    __syncwarp();
+    for (uint32_t base = 0; base < nPos; base += 256) {
+      uint32_t h[8];
+#pragma unroll
+      for (int c = 0; c < 8; c++) {
+        const uint32_t p = base + uint32_t(c) * 32u + uint32_t(lane);
+        h[c] = p < nPos ? def_hash3(in + p) : (0x10000u | uint32_t(lane));
+      }
+#pragma unroll
+      for (int c = 0; c < 8; c++) {
+        const uint32_t m = __match_any_sync(0xffffffffu, h[c]);
+        if (h[c] < 0x10000u) {
+          const uint32_t cur = sortTab[h[c]];
+          const uint32_t slot = cur + uint32_t(__popc(m & ltMask));
+          sorted[slot] = uint16_t(base + uint32_t(c) * 32u + uint32_t(lane));
+          rank[slot] = uint16_t(h[c]);
+          if ((m >> lane) == 1u) sortTab[h[c]] = uint16_t(cur + __popc(m));
+        }
+        __syncwarp();
+      }
+    }
+    __syncwarp();
+    for (uint32_t slot = lane; slot < nPos; slot += 32) {
+      const uint32_t hh = rank[slot];
+      rank[slot] = uint16_t(slot - (hh ? uint32_t(sortTab[hh - 1]) : 0u));
+    }
+  }
+}
+
+// match: one CTA per stream, one thread per slot of the sorted list (neighbouring threads hold neighbouring chain
+// positions of the same bucket: their candidate lists overlap, so the loads of a warp hit the same few lines).
+__global__ void __launch_bounds__(kThreads) deflate_match_kernel(StagedArgs a) {
+  __shared__ int sj;
+  const DeflateLevel L = deflate_level(a.level);
+  for (;;) {
+    __syncthreads();
+    if (threadIdx.x == 0) sj = a.jBegin + atomicAdd(a.counters + 1, 1);
+    __syncthreads();
+    const int j = sj;
+    if (j >= a.jEnd) break;
+    const uint32_t n = a.inLen[j];
+    if (n < 3 || n > kDefStagedMax) continue;
+    const uint64_t off = a.inOff[j];
+    const uint8_t* in = a.inBuf + off;
+    const uint16_t* sorted = a.sorted + (off - a.baseOff);
+    const uint16_t* rank = a.rank + (off - a.baseOff);
+    uint2* table = a.table + (off - a.baseOff);
+    const uint32_t nPos = n - 2;
+    for (uint32_t slot = threadIdx.x; slot < nPos; slot += kThreads)
+      table[sorted[slot]] = def_find_match(in, n, L, sorted, slot, rank[slot]);
+  }
+}
+
+// decide: one THREAD per stream runs the table-driven lazy loop and leaves the symbol list in the (now dead) sorted /
+// rank arrays of the stream: distances where the positions were, length codes / literals over the ranks.
+__global__ void __launch_bounds__(32) deflate_decide_kernel(StagedArgs a) {
+  for (;;) {
+    const int j = a.jBegin + atomicAdd(a.counters + 2, 1);
+    if (j >= a.jEnd) break;
+    const uint32_t n = a.inLen[j];
+    if (n == 0 || n > kDefStagedMax) continue;
+    const uint64_t off = a.inOff[j];
+    deflate_decide_table(a.inBuf + off, n, a.level, a.table + (off - a.baseOff), a.sorted + (off - a.baseOff),
+                         reinterpret_cast<uint8_t*>(a.rank + (off - a.baseOff)), a.blocks + (j - a.jBegin));
+  }
+}
+
+// emit: one CTA per stream.  Per block: symbol histogram by shared-memory atomics, trees.c on one thread over
+// shared-memory trees (def_plan_block), header by that thread, then the symbols of the block in parallel -- every
+// thread sizes four consecutive symbols, a block scan gives the bit offsets, and the codes are OR-ed into the
+// shared-memory bit window (g4_bitpack.cuh).  Adler-32 by a block reduction (s2 = n + sum (n-i) b_i).
+namespace {
+struct DeflateEmitShared {
+  DeflateTrees T;
+  BitWindow W;
+  uint32_t lhist[kDefLCodes + 2], dhist[kDefDCodes + 2];
+  uint32_t scan[kWarps + 1];
+  DeflateBlockPlan plan;
+  uint32_t hdrEnd;
+  unsigned long long red[kWarps][2];
+  int j;
+};
+struct WinOut {  // serial writer for block headers (the Out of def_send_all_trees)
+  WinSink s;
+  __device__ __forceinline__ void send_bits(uint32_t v, int n) { if (n) s.put(v, n); }
+};
+__device__ __forceinline__ uint32_t emit_sym_bits(const DeflateTrees& T, bool useStatic, uint32_t dist, uint32_t lc) {
+  if (dist == 0) return useStatic ? uint32_t(def_static_llen(int(lc))) : T.ltree[lc].dl;
+  const int lcode = def_length_code(int(lc));
+  const int dcode = def_dist_code(int(dist - 1));
+  const uint32_t l = useStatic ? uint32_t(def_static_llen(lcode + 257)) : T.ltree[lcode + 257].dl;
+  const uint32_t d = useStatic ? 5u : T.dtree[dcode].dl;
+  return l + uint32_t(def_length_extra(lcode)) + d + uint32_t(def_dist_extra(dcode));
+}
+__device__ __forceinline__ void emit_sym_put(ThreadBits& tb, const DeflateTrees& T, bool useStatic, uint32_t dist, uint32_t lc) {
+  if (dist == 0) {
+    if (useStatic) tb.put(def_static_lcode(int(lc)), def_static_llen(int(lc)));
+    else tb.put(T.ltree[lc].fc, T.ltree[lc].dl);
+    return;
+  }
+  const int lcode = def_length_code(int(lc));
+  if (useStatic) tb.put(def_static_lcode(lcode + 257), def_static_llen(lcode + 257));
+  else tb.put(T.ltree[lcode + 257].fc, T.ltree[lcode + 257].dl);
+  const int lx = def_length_extra(lcode);
+  if (lx) tb.put(uint32_t(int(lc) - def_length_base(lcode)), lx);
+  const int d1 = int(dist - 1);
+  const int dcode = def_dist_code(d1);
+  if (useStatic) tb.put(def_bi_reverse(uint32_t(dcode), 5), 5);
+  else tb.put(T.dtree[dcode].fc, T.dtree[dcode].dl);
+  const int dx = def_dist_extra(dcode);
+  if (dx) tb.put(uint32_t(d1 - def_dist_base(dcode)), dx);
+}
+}  // namespace
+
+__global__ void __launch_bounds__(kThreads) deflate_emit_kernel(StagedArgs a) {
+  __shared__ DeflateEmitShared S;
+  const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+  const DeflateLevel L = deflate_level(a.level);
+  for (;;) {
+    __syncthreads();
+    if (tid == 0) S.j = a.jBegin + atomicAdd(a.counters + 3, 1);
+    __syncthreads();
+    const int j = S.j;
+    if (j >= a.jEnd) break;
+    const uint32_t n = a.inLen[j];
+    if (n > kDefStagedMax) continue;
+    if (n == 0) { if (tid == 0) a.outLen[j] = 0; continue; }
+    const uint64_t off = a.inOff[j];
+    const uint8_t* in = a.inBuf + off;
+    const uint16_t* symDist = a.sorted + (off - a.baseOff);
+    const uint8_t* symLc = reinterpret_cast<const uint8_t*>(a.rank + (off - a.baseOff));
+    const DeflateBlocks& B = a.blocks[j - a.jBegin];
+    const uint32_t cap = n + uint32_t(a.capExtra);
+    BitOut o;
+    bitwin_reset(S.W, o, reinterpret_cast<uint32_t*>(a.outBuf + off + 112ull * uint64_t(j)), (cap + 3) >> 2);
+    if (tid == 0) {
+      WinSink hs{S.W.win, 0};
+      hs.put(L.zlibHeader >> 8, 8);
+      hs.put(L.zlibHeader & 0xffu, 8);
+    }
+    o.bitPos = 16;
+    const uint32_t nBlocks = B.nBlocks;
+    uint32_t sym0 = 0, pos0 = 0;
+    for (uint32_t b = 0; b < nBlocks; b++) {
+      const uint32_t sym1 = B.symEnd[b], pos1 = B.posEnd[b];
+      const bool last = b + 1 == nBlocks;
+      __syncthreads();
+      for (int i = tid; i < kDefLCodes + 2; i += kThreads) S.lhist[i] = 0;
+      if (tid < kDefDCodes + 2) S.dhist[tid] = 0;
+      __syncthreads();
+      for (uint32_t i = sym0 + tid; i < sym1; i += kThreads) {
+        const uint32_t dist = symDist[i], lc = symLc[i];
+        if (dist == 0) atomicAdd(&S.lhist[lc], 1u);
+        else {
+          atomicAdd(&S.lhist[def_length_code(int(lc)) + 257], 1u);
+          atomicAdd(&S.dhist[def_dist_code(int(dist - 1))], 1u);
+        }
+      }
+      __syncthreads();
+      for (int i = tid; i < kDefLCodes; i += kThreads) S.T.ltree[i].fc = uint16_t(i == 256 ? 1u : S.lhist[i]);
+      if (tid < kDefDCodes) S.T.dtree[tid].fc = uint16_t(S.dhist[tid]);
+      if (tid < kDefBlCodes) S.T.bltree[tid].fc = 0;
+      bitwin_reserve(S.W, o, 8192);  // room for the block header (<= 17 + 57 + 316 * 14 bits); contains the barrier
+      __syncthreads();
+      if (tid == 0) {
+        DeflateState st;
+        st.W = nullptr;
+        st.T = &S.T;
+        st.optLen = st.staticLen = 0;
+        const DeflateBlockPlan P = def_plan_block(st, pos1 - pos0, true);
+        S.plan = P;
+        WinOut wo{WinSink{S.W.win, o.bitPos - o.gbase * 32u}};
+        wo.send_bits((uint32_t(P.type) << 1) + (last ? 1u : 0u), 3);
+        if (P.type == 2) def_send_all_trees(st, wo, P);
+        S.hdrEnd = wo.s.pos + o.gbase * 32u;
+      }
+      __syncthreads();
+      o.bitPos = S.hdrEnd;
+      const int type = S.plan.type;
+      if (type == 0) {
+        // stored: pad to a byte boundary, LEN, NLEN, then the raw bytes (eight per thread and step)
+        const uint32_t len = pos1 - pos0;
+        o.bitPos = (o.bitPos + 7u) & ~7u;
+        bitwin_reserve(S.W, o, 64);
+        if (tid == 0) {
+          WinSink hs{S.W.win, o.bitPos - o.gbase * 32u};
+          hs.put(len & 0xffffu, 16);
+          hs.put((~len) & 0xffffu, 16);
+        }
+        o.bitPos += 32;
+        __syncthreads();
+        for (uint32_t i0 = 0; i0 < len; i0 += kThreads * 8) {
+          const uint32_t rem = len - i0;
+          const uint32_t chunk = rem < uint32_t(kThreads * 8) ? rem : uint32_t(kThreads * 8);
+          bitwin_reserve(S.W, o, chunk * 8);
+          const uint32_t mine = i0 + uint32_t(tid) * 8u;
+          if (mine < i0 + chunk) {
+            ThreadBits tb;
+            tb.begin(S.W, o, o.bitPos + uint32_t(tid) * 64u);
+            const uint32_t cnt = (i0 + chunk - mine) < 8u ? (i0 + chunk - mine) : 8u;
+            for (uint32_t q = 0; q < cnt; q++) tb.put(in[pos0 + mine + q], 8);
+            tb.end();
+          }
+          o.bitPos += chunk * 8;
+          __syncthreads();
+        }
+      } else {
+        const bool useStatic = type == 1;
+        constexpr int kIpt = 4;
+        for (uint32_t k0 = sym0; k0 < sym1; k0 += kThreads * kIpt) {
+          uint32_t dist[kIpt], lc[kIpt];
+          uint32_t myBits = 0;
+          int nv = 0;
+#pragma unroll
+          for (int q = 0; q < kIpt; q++) {
+            const uint32_t k = k0 + uint32_t(tid) * kIpt + q;
+            if (k < sym1) {
+              dist[q] = symDist[k];
+              lc[q] = symLc[k];
+              myBits += emit_sym_bits(S.T, useStatic, dist[q], lc[q]);
+              nv = q + 1;
+            }
+          }
+          uint32_t chunkBits;
+          const uint32_t ex = block_exclusive_scan(myBits, S.scan, &chunkBits);
+          bitwin_reserve(S.W, o, chunkBits);  // 1024 symbols * 48 bits always fit an empty window
+          ThreadBits tb;
+          tb.begin(S.W, o, o.bitPos + ex);
+#pragma unroll
+          for (int q = 0; q < kIpt; q++)
+            if (q < nv) emit_sym_put(tb, S.T, useStatic, dist[q], lc[q]);
+          tb.end();
+          o.bitPos += chunkBits;
+          __syncthreads();
+        }
+        bitwin_reserve(S.W, o, 32);
+        if (tid == 0) {
+          WinSink es{S.W.win, o.bitPos - o.gbase * 32u};
+          if (useStatic) es.put(def_static_lcode(256), 7);
+          else es.put(S.T.ltree[256].fc, S.T.ltree[256].dl);
+        }
+        o.bitPos += useStatic ? 7u : uint32_t(S.T.ltree[256].dl);
+        __syncthreads();
+      }
+      sym0 = sym1;
+      pos0 = pos1;
+    }
+    o.bitPos = (o.bitPos + 7u) & ~7u;  // bi_windup after the last block
+    // Adler-32: s1 = 1 + sum b_i, s2 = n + sum (n - i) b_i  (mod 65521)
+    unsigned long long sa = 0, sb = 0;
+    for (uint32_t i = tid; i < n; i += kThreads) {
+      const unsigned long long v = in[i];
+      sa += v;
+      sb += v * (n - i);
+    }
+#pragma unroll
+    for (int d = 16; d > 0; d >>= 1) {
+      sa += __shfl_down_sync(0xffffffffu, sa, d);
+      sb += __shfl_down_sync(0xffffffffu, sb, d);
+    }
+    __syncthreads();
+    if (lane == 0) { S.red[warp][0] = sa; S.red[warp][1] = sb; }
+    bitwin_reserve(S.W, o, 64);
+    __syncthreads();
+    if (tid == 0) {
+      unsigned long long ta = 1, tb2 = n;
+      for (int w = 0; w < kWarps; w++) { ta += S.red[w][0]; tb2 += S.red[w][1]; }
+      const uint32_t s1 = uint32_t(ta % 65521ull), s2 = uint32_t(tb2 % 65521ull);
+      WinSink ts{S.W.win, o.bitPos - o.gbase * 32u};
+      ts.put(s2 >> 8, 8);
+      ts.put(s2 & 0xffu, 8);
+      ts.put(s1 >> 8, 8);
+      ts.put(s1 & 0xffu, 8);
+    }
+    o.bitPos += 32;
+    __syncthreads();
+    bitwin_finish(S.W, o);
+    const uint32_t total = o.bitPos >> 3;
+    if (tid == 0) a.outLen[j] = total > cap ? cap : total;
   }
 }
 
@@ -277,6 +623,30 @@ cudaError_t launch_stream_offsets(const uint32_t* inLen, uint64_t* inOff, int nS
 }
 cudaError_t launch_deflate_streams(const StreamArgs& a, int nWorkers, cudaStream_t s) {
   deflate_streams_kernel<<<(nWorkers + 31) / 32, 32, 0, s>>>(a);
+  return cudaGetLastError();
+}
+uint32_t deflate_staged_max() { return kDefStagedMax; }
+size_t deflate_blocks_bytes() { return sizeof(DeflateBlocks); }
+cudaError_t launch_deflate_staged(const StagedArgs& a, int smCount, cudaStream_t s) {
+  static bool attr = false;
+  if (!attr) {
+    cudaError_t ea = cudaFuncSetAttribute(deflate_sort_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, kDefWSize * 2);
+    if (ea != cudaSuccess) return ea;
+    attr = true;
+  }
+  const int nChunk = a.jEnd - a.jBegin;
+  const int sortCtas = nChunk < smCount * 3 ? nChunk : smCount * 3;
+  deflate_sort_kernel<<<sortCtas, 32, kDefWSize * 2, s>>>(a);
+  cudaError_t e = cudaGetLastError();
+  if (e != cudaSuccess) return e;
+  const int matchCtas = nChunk < smCount * 8 ? nChunk : smCount * 8;
+  deflate_match_kernel<<<matchCtas, kThreads, 0, s>>>(a);
+  e = cudaGetLastError();
+  if (e != cudaSuccess) return e;
+  deflate_decide_kernel<<<(nChunk + 31) / 32, 32, 0, s>>>(a);
+  e = cudaGetLastError();
+  if (e != cudaSuccess) return e;
+  deflate_emit_kernel<<<matchCtas, kThreads, 0, s>>>(a);
   return cudaGetLastError();
 }
 cudaError_t launch_deflate_m32_size(const EncodeArgs& a, uint32_t* inLen, int nCtas, cudaStream_t s) {

@@ -7,6 +7,8 @@
 
 namespace g4 {
 
+struct DeflateBlocks;  // g4_deflate_enc.cuh
+
 // One candidate-encoder launch: every tile of the band is encoded by ONE codec into its own fixed-size
 // slot (slot t at slots + t*slotBytes, 16-byte aligned).  lens[t] = packing length (0 = declined).
 struct EncodeArgs {
@@ -94,6 +96,25 @@ struct StreamArgs {
   int level;     // 6 or 9
   void* work;    // nWorkers * deflate_work_bytes()
   int* counter;  // zeroed before launch
+  int bigOnly;   // 1: only streams longer than deflate_staged_max() (the staged kernels take the rest)
+};
+
+// Staged zlib encode of the streams [jBegin, jEnd) that are at most deflate_staged_max() bytes long
+// (g4_deflate_enc.cuh, "Staged form").  The per-position scratch arrays are indexed by inOff[j] - baseOff + position.
+struct StagedArgs {
+  const uint8_t* inBuf;
+  const uint64_t* inOff;
+  const uint32_t* inLen;
+  uint8_t* outBuf;
+  uint32_t* outLen;
+  int jBegin, jEnd;
+  uint64_t baseOff;
+  uint16_t* sorted;   // positions ordered by (hash, position)
+  uint16_t* rank;     // number of earlier positions in the slot's hash bucket
+  uint2* table;       // per position: longest match with the full / quarter chain
+  DeflateBlocks* blocks;  // per stream of the chunk: block boundaries (decide kernel -> emit kernel), deflate_blocks_bytes() each
+  int capExtra, level;
+  int* counters;      // 4 ints, zeroed before launch
 };
 
 cudaError_t launch_fill_terrain(int elemType, uint64_t seed, int64_t row0, int64_t col0, int64_t nRows, int64_t nCols, void* out,
@@ -129,6 +150,9 @@ cudaError_t launch_lsop_decode(const DecodeArgs& a, float* coef, uint8_t* meta, 
 
 // ---- zlib-stream encode stages (g4_deflate_encode.cu, g4_lsop.cu) ------------------------------------------------
 size_t deflate_work_bytes();
+size_t deflate_blocks_bytes();
+uint32_t deflate_staged_max();
+cudaError_t launch_deflate_staged(const StagedArgs& a, int smCount, cudaStream_t s);
 cudaError_t launch_stream_offsets(const uint32_t* inLen, uint64_t* inOff, int nStreams, uint64_t* total, cudaStream_t s);
 cudaError_t launch_deflate_streams(const StreamArgs& a, int nWorkers, cudaStream_t s);
 cudaError_t launch_deflate_m32_size(const EncodeArgs& a, uint32_t* inLen, int nCtas, cudaStream_t s);

@@ -48,6 +48,35 @@ int main(int argc, char** argv) {
           deflateEnd(&s);
           uint32_t gotLen = g4::deflate_stream(in.data(), uint32_t(n), got.data(), uint32_t(cap), W, level);
           runs++;
+          if (n <= g4::kDefStagedMax) {  // staged form: sorted position list -> match table -> table-driven lazy loop
+            std::vector<uint16_t> sorted(n + 8), rank(n + 8);
+            std::vector<uint2> table(n + 8);
+            g4::def_sort_positions_host(in.data(), uint32_t(n), sorted.data(), rank.data());
+            const g4::DeflateLevel L = g4::deflate_level(level);
+            for (size_t slot = 0; slot + 2 < n; slot++)
+              table[sorted[slot]] = g4::def_find_match(in.data(), uint32_t(n), L, sorted.data(), uint32_t(slot), rank[slot]);
+            std::vector<uint8_t> got2(cap + 8, 0xAA);
+            uint32_t got2Len = g4::deflate_stream_table(in.data(), uint32_t(n), got2.data(), uint32_t(cap), W, level, table.data());
+            runs++;
+            {  // the split form the device uses: decisions, then block emission from the symbol list
+              std::vector<uint16_t> sd(n + 8);
+              std::vector<uint8_t> sl(n + 8), got3(cap + 8, 0xAA);
+              g4::DeflateBlocks B;
+              g4::deflate_decide_table(in.data(), uint32_t(n), level, table.data(), sd.data(), sl.data(), &B);
+              uint32_t got3Len = g4::deflate_emit_blocks_serial(in.data(), uint32_t(n), got3.data(), uint32_t(cap), W, level, sd.data(), sl.data(), B);
+              runs++;
+              if (got3Len != refLen || memcmp(ref.data(), got3.data(), refLen) != 0) {
+                printf("MISMATCH (decide+emit) level=%d kind=%d n=%zu cap=%zu ref=%zu got=%u\n", level, kind, n, cap, refLen, got3Len);
+                fails++;
+              }
+            }
+            if (got2Len != refLen || memcmp(ref.data(), got2.data(), refLen) != 0) {
+              size_t d = 0;
+              while (d < refLen && d < got2Len && ref[d] == got2[d]) d++;
+              printf("MISMATCH (staged) level=%d kind=%d n=%zu cap=%zu ref=%zu got=%u firstdiff=%zu\n", level, kind, n, cap, refLen, got2Len, d);
+              fails++;
+            }
+          }
           if (gotLen != refLen || memcmp(ref.data(), got.data(), refLen) != 0) {
             size_t d = 0;
             while (d < refLen && d < gotLen && ref[d] == got[d]) d++;
