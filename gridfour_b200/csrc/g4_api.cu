@@ -81,7 +81,7 @@ struct g4_context {
   std::vector<uint32_t> hostLen;
   uint64_t hostTotal = 0;
   int deflateWorkers = 0;   // resident stream-worker threads (0 = default, see g4_context_create)
-  uint64_t stagedChunkBytes = 1ull << 30;  // staged zlib encode: input bytes per chunk (scratch = 12x)
+  uint64_t stagedChunkBytes = 2ull << 30;  // staged zlib encode: input bytes per chunk (scratch = 12x)
   bool lsopDeflate = true;  // LsEncoder12.deflateEnabled (lsop/LsEncoder12.java:78)
   // staging used by the host-memory entry points
   DevBuf sGrid, sArena, sOffsets, sLens, sCodec, sPred, sStatus;

@@ -587,6 +587,14 @@ constexpr uint32_t kDefStagedMax = 65535;
 // Table entry: match length (9 bits, 2 = none) | distance << 9.
 G4_HD __forceinline__ uint32_t def_pack_match(int len, uint32_t dist) { return uint32_t(len) | (dist << 9); }
 
+#ifdef __CUDA_ARCH__
+__device__ __forceinline__ uint32_t def_load32(const uint8_t* p) {
+  const uintptr_t a = reinterpret_cast<uintptr_t>(p);
+  const uint32_t* q = reinterpret_cast<const uint32_t*>(a & ~uintptr_t(3));
+  return __funnelshift_r(q[0], q[1], uint32_t(a & 3u) * 8u);
+}
+#endif
+
 // longest_match for the position in `slot` of the stream's sorted position list.  x = full chain, y = quarter chain.
 G4_HD inline uint2 def_find_match(const uint8_t* in, uint32_t n, const DeflateLevel& L, const uint16_t* sorted, uint32_t slot,
                                   uint32_t rank) {
@@ -613,6 +621,16 @@ G4_HD inline uint2 def_find_match(const uint8_t* in, uint32_t n, const DeflateLe
     const uint8_t* match = in + cur;
     if (match[bestLen] == scanEnd && match[bestLen - 1] == scanEnd1 && match[0] == s0 && match[1] == s1) {
       int len = 2;
+#ifdef __CUDA_ARCH__
+      // four bytes per step: unaligned 32-bit reads assembled from aligned words (in[] is padded past n)
+      bool differ = false;
+      while (len + 4 <= maxLen) {
+        const uint32_t x = def_load32(scan + len) ^ def_load32(match + len);
+        if (x) { len += (__ffs(int(x)) - 1) >> 3; differ = true; break; }
+        len += 4;
+      }
+      if (!differ)
+#endif
       while (len < maxLen && scan[len] == match[len]) len++;
       if (len > bestLen) {
         bestStart = cur;
@@ -744,6 +762,11 @@ G4_HD inline void deflate_decide_table(const uint8_t* in, uint32_t n, int level,
     prevMatch = matchStart;
     matchLength = kDefMinMatch - 1;
     if (lookahead >= uint32_t(kDefMinMatch) && prevLength < L.maxLazy) {
+#ifdef __CUDA_ARCH__
+      // the walk only moves forward: pull the table (and the input) a few hundred bytes ahead into L2/L1
+      asm volatile("prefetch.global.L1 [%0];" ::"l"(table + (strstart + 48u < n ? strstart + 48u : strstart)));
+      asm volatile("prefetch.global.L1 [%0];" ::"l"(in + (strstart + 256u < n ? strstart + 256u : strstart)));
+#endif
       const uint2 e = table[strstart];
       const uint32_t w = prevLength >= L.goodLength ? e.y : e.x;
       const int len = int(w & 0x1ffu);

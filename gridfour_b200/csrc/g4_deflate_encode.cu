@@ -70,20 +70,31 @@ __global__ void __launch_bounds__(32) deflate_streams_kernel(StreamArgs a) {
 }
 
 // ---- staged form for streams of at most kDefStagedMax bytes (g4_deflate_enc.cuh, "Staged form") ------------------------
-// sort: one WARP (a 32-thread CTA) per stream, bucket cursors (32768 x uint16 = 64 KB) in shared memory.  Positions are
-// taken 32 at a time in stream order; __match_any_sync groups the lanes of a chunk by hash, so a position's slot is
-// (bucket cursor) + (lanes below it with the same hash) and the highest lane of every group advances the cursor by the
-// group's size.  Pass 1 counts, a warp scan turns counts into bucket starts, pass 2 assigns slots (and parks the hash in
-// rank[]), pass 3 turns the parked hash into the rank: after pass 2 the cursor of bucket h-1 is the start of bucket h.
-// Eight chunks of hashes are loaded ahead of the serial cursor updates so that their latency overlaps.
-__global__ void __launch_bounds__(32) deflate_sort_kernel(StagedArgs a) {
+// sort: one 128-thread CTA per stream, bucket cursors (32768 x uint16 = 64 KB) in shared memory.
+//   pass 1 (all threads)  hash of every position, parked in rank[]; bucket counts by shared-memory atomics (order-free),
+//   scan   (all threads)  counts -> bucket starts,
+//   pass 2 (warp 0)       slots in stream order: positions are taken 32 at a time; __match_any_sync groups the lanes
+//                         of a chunk by hash, a position's slot is (bucket cursor) + (lanes below it with the same
+//                         hash) and the highest lane of every group advances the cursor by the group's size.  Eight
+//                         chunks of hashes are loaded and grouped ahead of the serial cursor updates; the hash is
+//                         parked in rank[slot],
+//   pass 3 (all threads)  rank of a slot = slot - start of its bucket; after pass 2 the cursor of bucket h-1 is the start
+//                         of bucket h.
+// (Tried and dropped: per-position shared-memory atomics instead of the grouped update, with a fix-up of the order
+// inside a chunk -- the two extra passes over HBM cost more than the grouping, 64 ms instead of 41 ms.)
+constexpr int kSortThreads = 128;
+__global__ void __launch_bounds__(kSortThreads) deflate_sort_kernel(StagedArgs a) {
   extern __shared__ uint16_t sortTab[];
-  const int lane = threadIdx.x;
+  __shared__ uint32_t warpSum[kSortThreads / 32];
+  __shared__ int sj;
+  const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
   const uint32_t ltMask = (1u << lane) - 1u;
+  uint32_t* t32 = reinterpret_cast<uint32_t*>(sortTab);
   for (;;) {
-    int j = 0;
-    if (lane == 0) j = a.jBegin + atomicAdd(a.counters + 0, 1);
-    j = __shfl_sync(0xffffffffu, j, 0);
+    __syncthreads();
+    if (tid == 0) sj = a.jBegin + atomicAdd(a.counters + 0, 1);
+    __syncthreads();
+    const int j = sj;
     if (j >= a.jEnd) break;
     const uint32_t n = a.inLen[j];
     if (n < 3 || n > kDefStagedMax) continue;
@@ -91,32 +102,26 @@ __global__ void __launch_bounds__(32) deflate_sort_kernel(StagedArgs a) {
     const uint8_t* in = a.inBuf + off;
     uint16_t* sorted = a.sorted + (off - a.baseOff);
     uint16_t* rank = a.rank + (off - a.baseOff);
+    uint16_t* hashOf = reinterpret_cast<uint16_t*>(a.table + (off - a.baseOff));  // the match table is not written yet
     const uint32_t nPos = n - 2;
-    __syncwarp();
     {
       uint4* t4 = reinterpret_cast<uint4*>(sortTab);
-      for (int i = lane; i < kDefWSize * 2 / 16; i += 32) t4[i] = make_uint4(0, 0, 0, 0);
+      for (int i = tid; i < kDefWSize * 2 / 16; i += kSortThreads) t4[i] = make_uint4(0, 0, 0, 0);
     }
-    __syncwarp();
-    for (uint32_t base = 0; base < nPos; base += 256) {
-      uint32_t h[8];
-#pragma unroll
-      for (int c = 0; c < 8; c++) {
-        const uint32_t p = base + uint32_t(c) * 32u + uint32_t(lane);
-        h[c] = p < nPos ? def_hash3(in + p) : (0x10000u | uint32_t(lane));
-      }
-#pragma unroll
-      for (int c = 0; c < 8; c++) {
-        const uint32_t m = __match_any_sync(0xffffffffu, h[c]);
-        if (h[c] < 0x10000u && (m >> lane) == 1u) sortTab[h[c]] = uint16_t(sortTab[h[c]] + __popc(m));
-        __syncwarp();
-      }
+    __syncthreads();
+#pragma unroll 8
+    for (uint32_t p = tid; p < nPos; p += kSortThreads) {
+      const uint32_t hh = def_hash3(in + p);
+      hashOf[p] = uint16_t(hh);
+      atomicAdd(&t32[hh >> 1], (hh & 1u) ? 0x10000u : 1u);
     }
-    {  // exclusive scan of the 32768 counts, two per lane and step
-      uint32_t* t32 = reinterpret_cast<uint32_t*>(sortTab);
+    __syncthreads();
+    {  // exclusive scan of the 32768 counts: every warp scans a quarter (two counts per lane and step), then the
+       // quarters are offset by the sums of the quarters before them
+      const int q0 = warp * (kDefWSize / 2 / 4);
       uint32_t carry = 0;
-      for (int i0 = 0; i0 < kDefWSize / 2; i0 += 32) {
-        const uint32_t v = t32[i0 + lane];
+      for (int i0 = 0; i0 < kDefWSize / 2 / 4; i0 += 32) {
+        const uint32_t v = t32[q0 + i0 + lane];
         const uint32_t c0 = v & 0xffffu, c1 = v >> 16;
         uint32_t inc = c0 + c1;
 #pragma unroll
@@ -125,33 +130,54 @@ __global__ void __launch_bounds__(32) deflate_sort_kernel(StagedArgs a) {
           if (lane >= d) inc += y;
         }
         const uint32_t ex = carry + inc - (c0 + c1);
-        t32[i0 + lane] = (ex & 0xffffu) | ((ex + c0) << 16);
+        t32[q0 + i0 + lane] = (ex & 0xffffu) | ((ex + c0) << 16);
         carry += __shfl_sync(0xffffffffu, inc, 31);
       }
-    }
-    __syncwarp();
-    for (uint32_t base = 0; base < nPos; base += 256) {
-      uint32_t h[8];
-#pragma unroll
-      for (int c = 0; c < 8; c++) {
-        const uint32_t p = base + uint32_t(c) * 32u + uint32_t(lane);
-        h[c] = p < nPos ? def_hash3(in + p) : (0x10000u | uint32_t(lane));
+      if (lane == 0) warpSum[warp] = carry;
+      __syncthreads();
+      uint32_t add = 0;
+      for (int w = 0; w < warp; w++) add += warpSum[w];
+      if (add) {
+        const uint32_t add2 = add | (add << 16);  // no carry between the halves: every start is < 65536
+        for (int i0 = 0; i0 < kDefWSize / 2 / 4; i0 += 32) t32[q0 + i0 + lane] += add2;
       }
+    }
+    __syncthreads();
+    if (warp == 0) {
+      uint32_t hN[8];
 #pragma unroll
       for (int c = 0; c < 8; c++) {
-        const uint32_t m = __match_any_sync(0xffffffffu, h[c]);
-        if (h[c] < 0x10000u) {
-          const uint32_t cur = sortTab[h[c]];
-          const uint32_t slot = cur + uint32_t(__popc(m & ltMask));
-          sorted[slot] = uint16_t(base + uint32_t(c) * 32u + uint32_t(lane));
-          rank[slot] = uint16_t(h[c]);
-          if ((m >> lane) == 1u) sortTab[h[c]] = uint16_t(cur + __popc(m));
+        const uint32_t p = uint32_t(c) * 32u + uint32_t(lane);
+        hN[c] = p < nPos ? uint32_t(hashOf[p]) : (0x10000u | uint32_t(lane));
+      }
+      for (uint32_t base = 0; base < nPos; base += 256) {
+        uint32_t h[8], mm[8];
+#pragma unroll
+        for (int c = 0; c < 8; c++) h[c] = hN[c];
+#pragma unroll
+        for (int c = 0; c < 8; c++) {  // next group's hashes: in flight during this group's serial part
+          const uint32_t p = base + 256u + uint32_t(c) * 32u + uint32_t(lane);
+          hN[c] = p < nPos ? uint32_t(hashOf[p]) : (0x10000u | uint32_t(lane));
         }
-        __syncwarp();
+#pragma unroll
+        for (int c = 0; c < 8; c++) mm[c] = __match_any_sync(0xffffffffu, h[c]);
+#pragma unroll
+        for (int c = 0; c < 8; c++) {
+          const uint32_t m = mm[c];
+          if (h[c] < 0x10000u) {
+            const uint32_t cur = sortTab[h[c]];
+            const uint32_t slot = cur + uint32_t(__popc(m & ltMask));
+            sorted[slot] = uint16_t(base + uint32_t(c) * 32u + uint32_t(lane));
+            rank[slot] = uint16_t(h[c]);  // parked: pass 3 turns it into the rank
+            if ((m >> lane) == 1u) sortTab[h[c]] = uint16_t(cur + __popc(m));
+          }
+          __syncwarp();
+        }
       }
     }
-    __syncwarp();
-    for (uint32_t slot = lane; slot < nPos; slot += 32) {
+    __syncthreads();
+#pragma unroll 8
+    for (uint32_t slot = tid; slot < nPos; slot += kSortThreads) {
       const uint32_t hh = rank[slot];
       rank[slot] = uint16_t(slot - (hh ? uint32_t(sortTab[hh - 1]) : 0u));
     }
@@ -636,7 +662,7 @@ cudaError_t launch_deflate_staged(const StagedArgs& a, int smCount, cudaStream_t
   }
   const int nChunk = a.jEnd - a.jBegin;
   const int sortCtas = nChunk < smCount * 3 ? nChunk : smCount * 3;
-  deflate_sort_kernel<<<sortCtas, 32, kDefWSize * 2, s>>>(a);
+  deflate_sort_kernel<<<sortCtas, kSortThreads, kDefWSize * 2, s>>>(a);
   cudaError_t e = cudaGetLastError();
   if (e != cudaSuccess) return e;
   const int matchCtas = nChunk < smCount * 8 ? nChunk : smCount * 8;
