@@ -401,7 +401,59 @@ __device__ bool canon_fast_decode_text(CanonFastShared& S, uint32_t nBits, const
     bool bad = false;
     const int last = fe < nSub - 1 ? fe : nSub - 1;
     const int i0 = tid * int(rounds);
-    if (i0 <= last) {
+    if constexpr (Sink::kPacked) {
+      // Packed form of the write pass: the sink takes the (up to three) symbol bytes of a lookup in one call and keeps
+      // them in a register byte queue, so the common path has no per-value work at all.
+      if (i0 <= last) {
+        const int i1 = i0 + int(rounds) - 1 < last ? i0 + int(rounds) - 1 : last;
+        uint32_t limit = T0 + uint32_t(i1 + 1) * B;
+        if (limit > regionEnd) limit = regionEnd;
+        BitCursor cur;
+        cur.init(S, S.startv[i0]);
+        sink.begin(offv[i0]);
+        bool have = false;
+        for (;;) {
+          const uint32_t p0 = cur.pos;
+          if (p0 + uint32_t(kFastLutBits) <= limit) {
+            const uint32_t m = S.mlut[cur.peek() & ((1u << kFastLutBits) - 1u)];
+            const uint32_t n = m >> 28;
+            if (n) {
+              cur.skip(S, (m >> 24) & 15u);
+              sink.push(m & 0xffffffu, int(n));
+              have = true;
+              continue;
+            }
+          }
+          const uint32_t e = S.lut[cur.peek() & ((1u << kFastLutBits) - 1u)];
+          if (e - 1u < 0x7fffu) {  // plain value
+            if (p0 >= limit) break;
+            cur.skip(S, e >> 9);
+            sink.push(e & 0xffu, 1);
+            have = true;
+            continue;
+          }
+          uint32_t after;
+          const int sym = canon_fast_rare_symbol(S, e, p0, nBits, &after);
+          if (sym < 0) { bad = true; break; }
+          if (sym == kSymEsc2 || sym == kSymEsc8) {
+            if (!have) { bad = true; break; }  // an escape with nothing to extend (CanonicalHuffman.java:495-504 would index -1)
+            const int nb = sym == kSymEsc2 ? 2 : 8;
+            if (after + nb > nBits) { bad = true; break; }
+            SmemBitSrc src{S.sw, nBits};
+            sink.amend(nb, src.bits(after, nb));
+            after += nb;
+          } else {
+            if (p0 >= limit) break;
+            if (sym == kSymEot) break;
+            if (sym == kSymNull) sink.put_rare(INT32_MIN);
+            else sink.push(uint32_t(sym), 1);  // a byte value with a code longer than the LUT
+            have = true;
+          }
+          cur.init(S, after);
+        }
+        sink.end();
+      }
+    } else if (i0 <= last) {
       const int i1 = i0 + int(rounds) - 1 < last ? i0 + int(rounds) - 1 : last;
       uint32_t limit = T0 + uint32_t(i1 + 1) * B;
       if (limit > regionEnd) limit = regionEnd;
@@ -471,6 +523,7 @@ __device__ bool canon_fast_decode_text(CanonFastShared& S, uint32_t nBits, const
 
 // Run sink for any residual stream order: one stream_to_cell per value (begin(first value index), put(value) ..., end()).
 struct CellRunSink {
+  static constexpr bool kPacked = false;
   TileView t;
   int order;
   uint32_t k;

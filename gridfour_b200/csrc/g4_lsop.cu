@@ -113,6 +113,7 @@ struct CellSink {
 };
 
 struct InteriorRunSink {  // LSOP12 interior order: rows 2.., columns 2..C-3 row-major; running cell address, no division per value
+  static constexpr bool kPacked = false;
   TileView t;
   int32_t* p;  // column 2 of the current row
   int c, w;
@@ -128,61 +129,90 @@ struct InteriorRunSink {  // LSOP12 interior order: rows 2.., columns 2..C-3 row
   }
   __device__ __forceinline__ void end() {}
 };
-// Same order, for 16-byte aligned tile rows: the last (up to) four values of the current row are kept in registers
-// and leave as one int4 store whenever they fill an aligned group of four columns; the unaligned head of a run, the
-// two-column tail of every row and the end of a run are flushed as scalars.  A sub-sequence decodes ~45 consecutive
-// values, so most of them go out 16 bytes at a time instead of as 32 scattered 4-byte sector writes per warp store.
-struct InteriorRunSink4 {
+// Packed form for 16-byte aligned tile rows (canon_fast_decode_text, Sink::kPacked): the symbol bytes (value + 128) of
+// every lookup are appended to a register byte queue; whenever the queue covers the rest of the current 8-column group
+// (32-byte sector) the group leaves as two int4 stores -- bytes to ints by one XOR per four bytes and one sign-extending
+// PRMT per value.  Only the 6-column groups at both ends of a row's interior (columns 2..7 and C-8..C-3), the unaligned
+// head and the tail of a run, and the rare values (escapes, nulls) take the scalar path.
+// prmt with the sign-replicating selector nibbles (8 | byte index); __byte_perm masks that bit away
+__device__ __forceinline__ int32_t sx_byte(uint32_t x, uint32_t sel) {
+  uint32_t d;
+  asm("prmt.b32 %0, %1, %2, %3;" : "=r"(d) : "r"(x), "r"(0u), "r"(sel));
+  return int32_t(d);
+}
+struct InteriorPackedSink {
+  static constexpr bool kPacked = true;
   TileView t;
   int32_t* rowp;  // column 0 of the current row
-  int col, n;     // next column to be written (2 .. C-3); number of buffered values (columns col-n .. col-1)
-  int32_t q0, q1, q2, q3;
-  int4 hold;      // the lower half of a 32-byte sector, waiting for its upper half
-  bool held;
+  int col;        // next column to be written (2 .. C-3)
+  int cnt, need;  // queued bytes; bytes that complete the current group (cnt < need between calls)
+  uint64_t lo;    // queue bytes 0..7, oldest in the low byte
+  uint32_t hi;    // queue bytes 8..9
+  __device__ __forceinline__ int group_need() const {
+    const int a = 8 - (col & 7), b = t.C - 2 - col;
+    return a < b ? a : b;
+  }
   __device__ __forceinline__ void begin(uint32_t k0) {
     const int w = t.C - 4;
-    int rr = int(k0) / w;
+    const int rr = int(k0) / w;
     col = 2 + int(k0) - rr * w;
     rowp = t.row(2 + rr);
-    n = 0;
-    held = false;
+    cnt = 0;
+    lo = 0;
+    hi = 0;
+    need = group_need();
   }
-  __device__ __forceinline__ void flush_scalars() {
-    if (n >= 4) rowp[col - 4] = q0;
-    if (n >= 3) rowp[col - 3] = q1;
-    if (n >= 2) rowp[col - 2] = q2;
-    if (n >= 1) rowp[col - 1] = q3;
-    n = 0;
+  __device__ __forceinline__ void advance_group() {
+    if (col == t.C - 2) { col = 2; rowp += t.pitch; }
+    need = group_need();
   }
-  __device__ __forceinline__ void flush_hold() {  // columns col-n-4 .. col-n-1
-    if (held) { *reinterpret_cast<int4*>(rowp + col - n - 4) = hold; held = false; }
+  __device__ __forceinline__ void write_scalars(int k) {  // the k oldest queue bytes, k <= cnt, inside the current group
+    for (int i = 0; i < k; i++) {
+      rowp[col + i] = int32_t(uint32_t(lo) & 0xffu) - 128;
+      lo = (lo >> 8) | (uint64_t(hi & 0xffu) << 56);
+      hi >>= 8;
+    }
+    col += k;
+    cnt -= k;
   }
-  __device__ __forceinline__ void put(int32_t v) {
-    q0 = q1; q1 = q2; q2 = q3; q3 = v;
-    n++;
+  __device__ __forceinline__ void flush() {
+    do {
+      if (need == 8) {
+        const uint32_t x0 = uint32_t(lo) ^ 0x80808080u, x1 = uint32_t(lo >> 32) ^ 0x80808080u;
+        int4 a, b;
+        a.x = sx_byte(x0, 0x8880); a.y = sx_byte(x0, 0x9991); a.z = sx_byte(x0, 0xaaa2); a.w = sx_byte(x0, 0xbbb3);
+        b.x = sx_byte(x1, 0x8880); b.y = sx_byte(x1, 0x9991); b.z = sx_byte(x1, 0xaaa2); b.w = sx_byte(x1, 0xbbb3);
+        *reinterpret_cast<int4*>(rowp + col) = a;
+        *reinterpret_cast<int4*>(rowp + col + 4) = b;
+        col += 8;
+        cnt -= 8;
+        lo = hi;
+        hi = 0;
+      } else write_scalars(need);
+      advance_group();
+    } while (cnt >= need);
+  }
+  __device__ __forceinline__ void push(uint32_t bytes, int n) {  // n = 1..3 symbol bytes, first value in the low byte
+    const int sh = cnt * 8;  // cnt <= 7
+    lo |= uint64_t(bytes) << sh;
+    if (sh > 40) hi |= bytes >> (64 - sh);
+    cnt += n;
+    if (cnt >= need) flush();
+  }
+  __device__ __forceinline__ void put_rare(int32_t v) {
+    write_scalars(cnt);
+    rowp[col] = v;
     col++;
-    if ((col & 3) == 0) {
-      if (n == 4) {
-        // a complete aligned group of four: pair it with its neighbour so that whole 32-byte sectors leave together
-        if (col & 4) { hold = make_int4(q0, q1, q2, q3); held = true; }
-        else {
-          if (held) { *reinterpret_cast<int4*>(rowp + col - 8) = hold; held = false; }
-          *reinterpret_cast<int4*>(rowp + col - 4) = make_int4(q0, q1, q2, q3);
-        }
-        n = 0;
-      } else flush_scalars();  // head of a run that started inside a group
-    }
-    if (col == t.C - 2) {  // end of the row's interior: columns C-4, C-3 (tile_cols % 4 == 0)
-      flush_hold();
-      flush_scalars();
-      col = 2;
-      rowp += t.pitch;
-    }
+    advance_group();
   }
-  __device__ __forceinline__ void end() {
-    flush_hold();
-    flush_scalars();
+  // an escape extends the value before it (CanonicalHuffman.java:495-504): v = (v << nb) | bits, in place
+  __device__ __forceinline__ void amend(int nb, uint32_t bits) {
+    write_scalars(cnt);
+    need = group_need();
+    int32_t* cell = col > 2 ? rowp + col - 1 : rowp - t.pitch + (t.C - 3);
+    *cell = int32_t((uint32_t(*cell) << nb) | bits);
   }
+  __device__ __forceinline__ void end() { write_scalars(cnt); }
 };
 
 }  // namespace
@@ -1256,7 +1286,7 @@ cudaError_t launch_lsop_decode(const DecodeArgs& a, float* coef, uint8_t* meta, 
     cudaError_t ea = cudaFuncSetAttribute(lsop_decode_text_kernel<InteriorRunSink>, cudaFuncAttributeMaxDynamicSharedMemorySize,
                                           int(sizeof(CanonFastShared)));
     if (ea == cudaSuccess)
-      ea = cudaFuncSetAttribute(lsop_decode_text_kernel<InteriorRunSink4>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+      ea = cudaFuncSetAttribute(lsop_decode_text_kernel<InteriorPackedSink>, cudaFuncAttributeMaxDynamicSharedMemorySize,
                                 int(sizeof(CanonFastShared)));
     if (ea != cudaSuccess) return ea;
     attr = true;
@@ -1267,7 +1297,7 @@ cudaError_t launch_lsop_decode(const DecodeArgs& a, float* coef, uint8_t* meta, 
   lsop_decode_head_kernel<<<(nTilesUpper + kWarps - 1) / kWarps, kThreads, 0, s>>>(a, coef, meta, defer, deferCounters);
   cudaError_t e = cudaGetLastError();
   if (e != cudaSuccess) return e;
-  if (aligned) lsop_decode_text_kernel<InteriorRunSink4><<<nCtas, kThreads, sizeof(CanonFastShared), s>>>(a, meta);
+  if (aligned) lsop_decode_text_kernel<InteriorPackedSink><<<nCtas, kThreads, sizeof(CanonFastShared), s>>>(a, meta);
   else lsop_decode_text_kernel<InteriorRunSink><<<nCtas, kThreads, sizeof(CanonFastShared), s>>>(a, meta);
   e = cudaGetLastError();
   if (e != cudaSuccess) return e;
