@@ -33,7 +33,6 @@ constexpr int kFastLutBits = 11;
 constexpr uint32_t kFastSpecial = 0x8000u;  // LUT flag: symbol >= 256 (null, escapes, end of text)
 
 struct CanonFastShared {
-  uint32_t sw[kFastStageWords + 8];   // staged packing; word 0 = packing bytes 0..3
   uint32_t mlut[1 << kFastLutBits];   // up to 3 plain values per lookup: s1 | s2 << 8 | s3 << 16 | bits << 24 | n << 28
   uint16_t lut[1 << kFastLutBits];    // sym | len << 9 | special; 0 = code longer than the LUT
   uint16_t sorted[kCanonSymbols];
@@ -47,7 +46,13 @@ struct CanonFastShared {
   uint32_t scan[kWarps + 1];
   uint32_t textStart, endBit;
   int error, changed, firstEot;
+  // staged packing, word 0 = packing bytes 0..3.  LAST member: a kernel may allocate more dynamic shared memory than
+  // sizeof(CanonFastShared) and stage packings of up to canon_fast_stage_words(allocated bytes) words.
+  uint32_t sw[kFastStageWords + 8];
 };
+__host__ __device__ constexpr size_t canon_fast_smem_bytes(uint32_t stageWords) {
+  return sizeof(CanonFastShared) + (stageWords > uint32_t(kFastStageWords) ? size_t(stageWords - kFastStageWords) * 4 : 0);
+}
 
 // Bit source over the staged words (absolute bit positions inside the packing).
 struct SmemBitSrc {

@@ -531,7 +531,7 @@ __device__ inline void lsop_warp_column_scan(const TileView& t, int col, int r0,
 }
 
 __global__ void __launch_bounds__(kThreads) lsop_decode_head_kernel(DecodeArgs a, float* coefOut, uint8_t* meta, int* defer,
-                                                                    int* deferCount) {
+                                                                    int* deferCount, uint32_t stageWords) {
   __shared__ CanonWarpShared WS[kWarps];
   const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
   CanonWarpShared& W = WS[warp];
@@ -549,7 +549,7 @@ __global__ void __launch_bounds__(kThreads) lsop_decode_head_kernel(DecodeArgs a
     if (lane == 0) a.status[tIdx] = G4_ERR_FORMAT;
     return;
   }
-  if (h.type != 2 || len > uint32_t(kFastStageWords) * 4u || (reinterpret_cast<uintptr_t>(packing) & 3) != 0) {
+  if (h.type != 2 || len > stageWords * 4u || (reinterpret_cast<uintptr_t>(packing) & 3) != 0) {
     if (lane == 0) defer[atomicAdd(deferCount, 1)] = tIdx;
     return;
   }
@@ -1281,24 +1281,31 @@ size_t lsop_meta_bytes() { return kLsopMetaBytes; }
 
 cudaError_t launch_lsop_decode(const DecodeArgs& a, float* coef, uint8_t* meta, int* defer, int* deferCounters, int nCtas,
                                int nTilesUpper, cudaStream_t s) {
+  // Staging capacity of the text kernel: 5 bits per sample of the tile, at least the default 28 KB (four CTAs per SM; 5.3
+  // bits per sample of a 180x240 tile), at most what leaves one CTA per SM; packings beyond it go to the general kernels.
+  constexpr uint32_t kMaxStageWords = (192u * 1024u) / 4u;
+  uint32_t stageWords = uint32_t((uint64_t(a.band.tile_rows) * uint64_t(a.band.tile_cols) * 5 / 8 + 3) / 4);
+  if (stageWords < uint32_t(kFastStageWords)) stageWords = kFastStageWords;
+  if (stageWords > kMaxStageWords) stageWords = kMaxStageWords;
+  stageWords = (stageWords + 255u) & ~255u;
+  const size_t textSmem = canon_fast_smem_bytes(stageWords);
   static bool attr = false;
   if (!attr) {
-    cudaError_t ea = cudaFuncSetAttribute(lsop_decode_text_kernel<InteriorRunSink>, cudaFuncAttributeMaxDynamicSharedMemorySize,
-                                          int(sizeof(CanonFastShared)));
+    const int maxSmem = int(canon_fast_smem_bytes(kMaxStageWords));
+    cudaError_t ea = cudaFuncSetAttribute(lsop_decode_text_kernel<InteriorRunSink>, cudaFuncAttributeMaxDynamicSharedMemorySize, maxSmem);
     if (ea == cudaSuccess)
-      ea = cudaFuncSetAttribute(lsop_decode_text_kernel<InteriorPackedSink>, cudaFuncAttributeMaxDynamicSharedMemorySize,
-                                int(sizeof(CanonFastShared)));
+      ea = cudaFuncSetAttribute(lsop_decode_text_kernel<InteriorPackedSink>, cudaFuncAttributeMaxDynamicSharedMemorySize, maxSmem);
     if (ea != cudaSuccess) return ea;
     attr = true;
   }
   const bool aligned = (a.band.tile_cols % 4) == 0 && (a.band.grid_pitch % 4) == 0 && a.band.tile_cols >= 8 &&
                        (reinterpret_cast<uintptr_t>(a.grid) & 15) == 0;
   // deferCounters[0] = number of deferred tiles (filled by kernel H), [1] = work counter of the general kernel
-  lsop_decode_head_kernel<<<(nTilesUpper + kWarps - 1) / kWarps, kThreads, 0, s>>>(a, coef, meta, defer, deferCounters);
+  lsop_decode_head_kernel<<<(nTilesUpper + kWarps - 1) / kWarps, kThreads, 0, s>>>(a, coef, meta, defer, deferCounters, stageWords);
   cudaError_t e = cudaGetLastError();
   if (e != cudaSuccess) return e;
-  if (aligned) lsop_decode_text_kernel<InteriorPackedSink><<<nCtas, kThreads, sizeof(CanonFastShared), s>>>(a, meta);
-  else lsop_decode_text_kernel<InteriorRunSink><<<nCtas, kThreads, sizeof(CanonFastShared), s>>>(a, meta);
+  if (aligned) lsop_decode_text_kernel<InteriorPackedSink><<<nCtas, kThreads, textSmem, s>>>(a, meta);
+  else lsop_decode_text_kernel<InteriorRunSink><<<nCtas, kThreads, textSmem, s>>>(a, meta);
   e = cudaGetLastError();
   if (e != cudaSuccess) return e;
   DecodeArgs d = a;
