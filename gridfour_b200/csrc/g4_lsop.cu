@@ -166,28 +166,43 @@ struct InteriorPackedSink {
     if (col == t.C - 2) { col = 2; rowp += t.pitch; }
     need = group_need();
   }
-  __device__ __forceinline__ void write_scalars(int k) {  // the k oldest queue bytes, k <= cnt, inside the current group
-    for (int i = 0; i < k; i++) {
-      rowp[col + i] = int32_t(uint32_t(lo) & 0xffu) - 128;
-      lo = (lo >> 8) | (uint64_t(hi & 0xffu) << 56);
-      hi >>= 8;
-    }
+  __device__ __forceinline__ void write_scalars(int k) {  // the k oldest queue bytes, k <= cnt <= 9, inside the current group
+    const uint32_t x0 = uint32_t(lo) ^ 0x80808080u, x1 = uint32_t(lo >> 32) ^ 0x80808080u;
+    int32_t* const q = rowp + col;
+    if (k > 0) q[0] = sx_byte(x0, 0x8880);
+    if (k > 1) q[1] = sx_byte(x0, 0x9991);
+    if (k > 2) q[2] = sx_byte(x0, 0xaaa2);
+    if (k > 3) q[3] = sx_byte(x0, 0xbbb3);
+    if (k > 4) q[4] = sx_byte(x1, 0x8880);
+    if (k > 5) q[5] = sx_byte(x1, 0x9991);
+    if (k > 6) q[6] = sx_byte(x1, 0xaaa2);
+    if (k > 7) q[7] = sx_byte(x1, 0xbbb3);
+    if (k > 8) q[8] = int32_t(hi & 0xffu) - 128;
+    drop(k);
     col += k;
+  }
+  __device__ __forceinline__ void drop(int k) {  // removes the k oldest queue bytes (k <= 9)
+    const int sh = 8 * k;
+    if (k >= 8) { lo = uint64_t(hi) >> (sh - 64); hi = 0; }
+    else if (k > 0) { lo = (lo >> sh) | (uint64_t(hi) << (64 - sh)); hi = 0; }  // hi holds at most 2 bytes: they all move into lo
     cnt -= k;
   }
   __device__ __forceinline__ void flush() {
     do {
-      if (need == 8) {
-        const uint32_t x0 = uint32_t(lo) ^ 0x80808080u, x1 = uint32_t(lo >> 32) ^ 0x80808080u;
-        int4 a, b;
-        a.x = sx_byte(x0, 0x8880); a.y = sx_byte(x0, 0x9991); a.z = sx_byte(x0, 0xaaa2); a.w = sx_byte(x0, 0xbbb3);
-        b.x = sx_byte(x1, 0x8880); b.y = sx_byte(x1, 0x9991); b.z = sx_byte(x1, 0xaaa2); b.w = sx_byte(x1, 0xbbb3);
-        *reinterpret_cast<int4*>(rowp + col) = a;
-        *reinterpret_cast<int4*>(rowp + col + 4) = b;
-        col += 8;
-        cnt -= 8;
-        lo = hi;
-        hi = 0;
+      const int ph = col & 7;
+      if (need == 8 || (need == 6 && (ph == 0 || ph == 2))) {
+        // an aligned group of eight, or the six-column group at either end of a row's interior (columns 2..7 as
+        // int2 + int4, columns C-8..C-3 as int4 + int2): queue byte j goes to column col + j
+        const uint64_t al = lo << (8 * ph);
+        const uint32_t x0 = uint32_t(al) ^ 0x80808080u, x1 = uint32_t(al >> 32) ^ 0x80808080u;
+        int32_t* const g = rowp + (col - ph);
+        if (ph == 0) *reinterpret_cast<int4*>(g) = make_int4(sx_byte(x0, 0x8880), sx_byte(x0, 0x9991), sx_byte(x0, 0xaaa2), sx_byte(x0, 0xbbb3));
+        else *reinterpret_cast<int2*>(g + 2) = make_int2(sx_byte(x0, 0xaaa2), sx_byte(x0, 0xbbb3));
+        if (ph + need == 8) *reinterpret_cast<int4*>(g + 4) = make_int4(sx_byte(x1, 0x8880), sx_byte(x1, 0x9991), sx_byte(x1, 0xaaa2), sx_byte(x1, 0xbbb3));
+        else *reinterpret_cast<int2*>(g + 4) = make_int2(sx_byte(x1, 0x8880), sx_byte(x1, 0x9991));
+        const int k = need;
+        drop(k);
+        col += k;
       } else write_scalars(need);
       advance_group();
     } while (cnt >= need);
