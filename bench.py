@@ -254,6 +254,9 @@ def main():
     dev = torch.device("cuda", local_rank)
     if world > 1:
         os.environ.setdefault("MASTER_ADDR", "127.0.0.1")
+        # the contract is ONE JSON line on stdout: keep NCCL's own "NCCL version ..." banner (NCCL_DEBUG=VERSION/INFO) off it
+        if os.environ.get("NCCL_DEBUG", "").upper() in ("VERSION", "INFO", "TRACE") and not os.environ.get("NCCL_DEBUG_FILE"):
+            os.environ["NCCL_DEBUG_FILE"] = "/dev/stderr"
         dist.init_process_group("nccl", device_id=dev)
     L = _lib.lib()
     # the context launches on torch's current stream so torch.cuda.Event brackets exactly the library's kernels
