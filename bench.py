@@ -344,6 +344,31 @@ def main():
     value = 4.0 * samples * world * args.steps / t_dec / 1e9
     enc_value = 4.0 * samples * world / t_enc / 1e9
 
+    # ---- tile records either side of the path: framing + CRC-32C, then validation + CRC check ------
+    records_info = None
+    if not is_f:
+        from gridfour_b200 import gvrs
+
+        rec_ms = {"pack": [], "unpack": []}
+        recs = pos = None
+        for i in range(4):
+            r0, r1, r2 = (torch.cuda.Event(enable_timing=True) for _ in range(3))
+            r0.record(stream)
+            recs, pos = gvrs.pack_tile_records_device(ctx, batch, 4096, True)
+            r1.record(stream)
+            _off, _lens, st = gvrs.unpack_tile_records_device(ctx, recs, pos - 4096, True)
+            r2.record(stream)
+            torch.cuda.synchronize(dev)
+            if i:
+                rec_ms["pack"].append(r0.elapsed_time(r1))
+                rec_ms["unpack"].append(r1.elapsed_time(r2))
+        assert int((st != 0).sum()) == 0 and torch.equal(_lens.to(torch.int64), batch.lens.to(torch.int64))
+        rb = int(recs.numel())
+        records_info = {"record_bytes": rb, "pack_ms": float(np.mean(rec_ms["pack"])), "unpack_ms": float(np.mean(rec_ms["unpack"])),
+                        "pack_gbs": rb / np.mean(rec_ms["pack"]) / 1e6, "unpack_gbs": rb / np.mean(rec_ms["unpack"]) / 1e6,
+                        "what": "g4_pack_tile_records (frame + CRC-32C) / g4_unpack_tile_records (validate + CRC-32C) over the step's "
+                                "payloads, device resident"}
+
     # ---- e2e: host buffers through the C ABI ------------------------------------------------------------------
     e2e = None
     if not args.no_e2e:
@@ -421,6 +446,7 @@ def main():
                    "tile_choice": {c: int(codec_hist[k]) for k, c in enumerate(codecs)} | {"raw": int(codec_hist[255])}},
         "bits_per_sample": bits_per_sample,
         "encode": {"value": enc_value, "unit": "GB/s", "ms": 1000.0 * t_enc, "kernel_ms": enc_kernel_ms},
+        "records": records_info,
         "roofline": roofline, "cpu_baseline": cpu, "e2e": e2e, "gpu_launches": int(launches_per_step * args.steps),
         "clocks": clocks,
     }

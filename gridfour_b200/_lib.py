@@ -23,6 +23,7 @@ EXPORTS = [
     "g4_context_create", "g4_context_destroy", "g4_context_synchronize", "g4_encode_i32", "g4_decode_i32",
     "g4_encode_f32", "g4_decode_f32", "g4_encode_tiles", "g4_decode_tiles", "g4_encode_arena_bound",
     "g4_fill_terrain", "g4_launch_count", "g4_context_set_timing", "g4_kernel_time_ms", "g4_codec_supported",
+    "g4_crc32c", "g4_tile_records_bound", "g4_pack_tile_records", "g4_unpack_tile_records",
 ]
 
 
@@ -73,6 +74,13 @@ def lib():
         L.g4_context_set_timing.argtypes = [C.c_void_p, C.c_int]
         L.g4_kernel_time_ms.argtypes = [C.c_void_p, C.c_int, C.c_int]
         L.g4_kernel_time_ms.restype = C.c_double
+        L.g4_crc32c.argtypes = [C.c_void_p, C.c_int, C.c_void_p, C.c_void_p, C.c_void_p, C.c_int, C.c_void_p]
+        L.g4_tile_records_bound.argtypes = [C.c_int, C.c_uint64]
+        L.g4_tile_records_bound.restype = C.c_uint64
+        L.g4_pack_tile_records.argtypes = [C.c_void_p, C.c_int, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_int, C.c_int, C.c_int,
+                                           C.c_uint64, C.c_void_p, C.c_uint64, C.c_void_p, C.POINTER(C.c_uint64)]
+        L.g4_unpack_tile_records.argtypes = [C.c_void_p, C.c_int, C.c_void_p, C.c_uint64, C.c_void_p, C.c_int, C.c_int, C.c_void_p,
+                                             C.c_void_p, C.c_void_p]
         _lib = L
     return _lib
 

@@ -373,6 +373,27 @@ class CodecMaster:
         check(st, "g4_encode_tiles")
         return TileBatch(arena, offsets, lens, codec, pred, status, total.value, band)
 
+    def decodeImageTiles(self, image, payload_offsets, lens, status, tilesDown, tilesAcross, tileRows, tileCols, dtype, fillValue):
+        """Decodes the tiles of a one-element raster whose payloads sit inside a GVRS file image (gvrs.GvrsImage.read_raster):
+        the image is the arena of g4_decode_tiles.  Tiles the file does not hold (status G4_DECLINED) are pointed at one
+        raw tile of fill values appended to the arena (RasterTile.setToNullState)."""
+        from ._lib import G4_DECLINED
+
+        band = self._band((tilesDown * tileRows, tilesAcross * tileCols), dtype, tileRows, tileCols,
+                          fillValue=fillValue if np.dtype(dtype) == np.int16 else None)
+        arena = np.frombuffer(image, dtype=np.uint8) if not isinstance(image, np.ndarray) else image
+        offsets = np.array(payload_offsets, dtype=np.uint64)
+        lens = np.array(lens, dtype=np.uint32)
+        absent = np.asarray(status) == G4_DECLINED
+        if absent.any():
+            fill = np.full(tileRows * tileCols, fillValue, dtype=np.dtype(dtype)).tobytes()
+            fill += bytes((-len(fill)) & 3)
+            base = (arena.size + 7) & ~7
+            arena = np.concatenate([arena, np.zeros(base - arena.size, np.uint8), np.frombuffer(fill, dtype=np.uint8)])
+            offsets[absent] = base
+            lens[absent] = len(fill)
+        return self.decodeTiles(TileBatch(arena, offsets, lens, None, None, None, int(arena.size), band))
+
     def decodeTiles(self, batch, out=None):
         """Inverse of encodeTiles.  Returns the raster (numpy for host batches, torch for device batches)."""
         L = _lib.lib()

@@ -77,6 +77,8 @@ struct g4_context {
   DevBuf jobLen, jobOff, jobOut, jobTotal, streamIn, streamOut, deflateWork;
   // staged zlib encode (streams <= deflate_staged_max() bytes): sorted positions, bucket ranks, match table, sort tables
   DevBuf stSorted, stRank, stTable, stTabs, stWork, stCounters;
+  // GVRS tile records (g4_records.cu): layout arrays and host-space staging
+  DevBuf rcPos, rcOff, rcLen, rcCrc, rcStored, rcTotal, rcData, rcOffsets, rcLens, rcIndex, rcStatus, rcOut;
   std::vector<uint64_t> hostOff;   // jobOff / jobLen mirrored on the host (chunking of the staged encode)
   std::vector<uint32_t> hostLen;
   uint64_t hostTotal = 0;
@@ -604,7 +606,8 @@ void g4_context_destroy(g4_context* ctx) {
   DevBuf* bufs[] = {&ctx->candLens, &ctx->candPreds, &ctx->candStatus, &ctx->counters, &ctx->scratch, &ctx->lists, &ctx->src,
                     &ctx->total, &ctx->coef, &ctx->defer, &ctx->lsopMeta, &ctx->wide, &ctx->encScratch, &ctx->region, &ctx->jobLen, &ctx->jobOff, &ctx->jobOut, &ctx->jobTotal,
                     &ctx->streamIn, &ctx->streamOut, &ctx->deflateWork, &ctx->stSorted, &ctx->stRank, &ctx->stTable, &ctx->stTabs,
-                    &ctx->stWork, &ctx->stCounters, &ctx->sGrid, &ctx->sArena, &ctx->sOffsets, &ctx->sLens, &ctx->sCodec, &ctx->sPred, &ctx->sStatus};
+                    &ctx->stWork, &ctx->stCounters, &ctx->rcPos, &ctx->rcOff, &ctx->rcLen, &ctx->rcCrc, &ctx->rcStored, &ctx->rcTotal,
+                    &ctx->rcData, &ctx->rcOffsets, &ctx->rcLens, &ctx->rcIndex, &ctx->rcStatus, &ctx->rcOut, &ctx->sGrid, &ctx->sArena, &ctx->sOffsets, &ctx->sLens, &ctx->sCodec, &ctx->sPred, &ctx->sStatus};
   for (DevBuf* b : bufs) b->release();
   if (ctx->ownStream) cudaStreamDestroy(ctx->stream);
   delete ctx;
@@ -644,6 +647,156 @@ double g4_kernel_time_ms(g4_context* ctx, int direction, int codec_kind) {
   if (cudaEventSynchronize(ctx->ev[direction][codec_kind][1]) != cudaSuccess) return -1.0;
   if (cudaEventElapsedTime(&ms, ctx->ev[direction][codec_kind][0], ctx->ev[direction][codec_kind][1]) != cudaSuccess) return -1.0;
   return double(ms);
+}
+
+// ---- GVRS tile records --------------------------------------------------------------------------------------------------
+int g4_crc32c(g4_context* ctx, int mem_space, const uint8_t* data, const uint64_t* offsets, const uint32_t* sizes, int n,
+              uint32_t* crc_out) {
+  if (!ctx || !data || !offsets || !sizes || !crc_out || n < 0) return G4_ERR_ARG;
+  if (n == 0) return G4_OK;
+  CK(cudaSetDevice(ctx->device));
+  if (mem_space == G4_MEM_DEVICE) {
+    CK(launch_crc32c(data, offsets, sizes, n, crc_out, 0, ctx->stream));
+    ctx->launches++;
+    return G4_OK;
+  }
+  if (mem_space != G4_MEM_HOST) return G4_ERR_ARG;
+  uint64_t bytes = 0;
+  for (int i = 0; i < n; i++) {
+    const uint64_t end = offsets[i] + sizes[i];
+    if (end > bytes) bytes = end;
+  }
+  CK(ctx->rcData.ensure(bytes + 16));
+  CK(ctx->rcOff.ensure(size_t(n) * 8));
+  CK(ctx->rcLen.ensure(size_t(n) * 4));
+  CK(ctx->rcCrc.ensure(size_t(n) * 4));
+  CK(cudaMemcpyAsync(ctx->rcData.p, data, bytes, cudaMemcpyHostToDevice, ctx->stream));
+  CK(cudaMemcpyAsync(ctx->rcOff.p, offsets, size_t(n) * 8, cudaMemcpyHostToDevice, ctx->stream));
+  CK(cudaMemcpyAsync(ctx->rcLen.p, sizes, size_t(n) * 4, cudaMemcpyHostToDevice, ctx->stream));
+  CK(launch_crc32c(ctx->rcData.as<uint8_t>(), ctx->rcOff.as<uint64_t>(), ctx->rcLen.as<uint32_t>(), n, ctx->rcCrc.as<uint32_t>(), 0,
+                   ctx->stream));
+  ctx->launches++;
+  CK(cudaMemcpyAsync(crc_out, ctx->rcCrc.p, size_t(n) * 4, cudaMemcpyDeviceToHost, ctx->stream));
+  CK(cudaStreamSynchronize(ctx->stream));
+  return G4_OK;
+}
+
+uint64_t g4_tile_records_bound(int n_tiles, uint64_t payload_bytes) {
+  if (n_tiles < 0) return 0;
+  return payload_bytes + uint64_t(n_tiles) * 32ull;  // 8 header + 4 index + 4 length + 4 checksum + at most 7 padding
+}
+
+int g4_pack_tile_records(g4_context* ctx, int mem_space, const uint8_t* arena, const uint64_t* offsets, const uint32_t* lens,
+                         const int32_t* tile_index, int first_tile_index, int n_tiles, int checksum, uint64_t base_pos,
+                         uint8_t* records, uint64_t records_cap, uint64_t* content_pos, uint64_t* total_bytes) {
+  if (!ctx || !arena || !offsets || !lens || !records || !content_pos || !total_bytes || n_tiles < 0 || (base_pos & 7)) return G4_ERR_ARG;
+  if (mem_space != G4_MEM_DEVICE && mem_space != G4_MEM_HOST) return G4_ERR_ARG;
+  *total_bytes = 0;
+  if (n_tiles == 0) return G4_OK;
+  CK(cudaSetDevice(ctx->device));
+  const int n = n_tiles;
+  const uint8_t* dArena = arena;
+  const uint64_t* dOffsets = offsets;
+  const uint32_t* dLens = lens;
+  const int32_t* dIndex = tile_index;
+  uint64_t* dPos = content_pos;
+  uint8_t* dRecords = records;
+  if (mem_space == G4_MEM_HOST) {
+    uint64_t arenaBytes = 0;
+    for (int t = 0; t < n; t++) {
+      const uint64_t end = offsets[t] + lens[t];
+      if (end > arenaBytes) arenaBytes = end;
+    }
+    CK(ctx->rcData.ensure(arenaBytes + 16));
+    CK(ctx->rcOffsets.ensure(size_t(n) * 8));
+    CK(ctx->rcLens.ensure(size_t(n) * 4));
+    CK(ctx->rcPos.ensure(size_t(n) * 8));
+    CK(ctx->rcOut.ensure(records_cap + 16));
+    CK(cudaMemcpyAsync(ctx->rcData.p, arena, arenaBytes, cudaMemcpyHostToDevice, ctx->stream));
+    CK(cudaMemcpyAsync(ctx->rcOffsets.p, offsets, size_t(n) * 8, cudaMemcpyHostToDevice, ctx->stream));
+    CK(cudaMemcpyAsync(ctx->rcLens.p, lens, size_t(n) * 4, cudaMemcpyHostToDevice, ctx->stream));
+    if (tile_index) {
+      CK(ctx->rcIndex.ensure(size_t(n) * 4));
+      CK(cudaMemcpyAsync(ctx->rcIndex.p, tile_index, size_t(n) * 4, cudaMemcpyHostToDevice, ctx->stream));
+      dIndex = ctx->rcIndex.as<int32_t>();
+    }
+    dArena = ctx->rcData.as<uint8_t>();
+    dOffsets = ctx->rcOffsets.as<uint64_t>();
+    dLens = ctx->rcLens.as<uint32_t>();
+    dPos = ctx->rcPos.as<uint64_t>();
+    dRecords = ctx->rcOut.as<uint8_t>();
+  }
+  CK(ctx->rcOff.ensure(size_t(n) * 8));
+  CK(ctx->rcLen.ensure(size_t(n) * 4));
+  CK(ctx->rcTotal.ensure(8));
+  CK(launch_record_layout(dLens, n, base_pos, dPos, ctx->rcOff.as<uint64_t>(), ctx->rcLen.as<uint32_t>(), ctx->rcTotal.as<uint64_t>(),
+                          ctx->stream));
+  uint64_t total = 0;
+  CK(cudaMemcpyAsync(&total, ctx->rcTotal.p, 8, cudaMemcpyDeviceToHost, ctx->stream));
+  CK(cudaStreamSynchronize(ctx->stream));
+  *total_bytes = total;
+  if (total > records_cap) return G4_ERR_CAPACITY;
+  CK(launch_record_pack(dArena, dOffsets, dLens, dIndex, first_tile_index, n, ctx->rcOff.as<uint64_t>(), ctx->rcLen.as<uint32_t>(), dRecords,
+                        persistent_ctas(ctx, n, 8), ctx->stream));
+  ctx->launches += 2;
+  if (checksum) {
+    CK(launch_crc32c(dRecords, ctx->rcOff.as<uint64_t>(), ctx->rcLen.as<uint32_t>(), n, nullptr, 1, ctx->stream));
+    ctx->launches++;
+  }
+  if (mem_space == G4_MEM_HOST) {
+    CK(cudaMemcpyAsync(records, dRecords, total, cudaMemcpyDeviceToHost, ctx->stream));
+    CK(cudaMemcpyAsync(content_pos, dPos, size_t(n) * 8, cudaMemcpyDeviceToHost, ctx->stream));
+    CK(cudaStreamSynchronize(ctx->stream));
+  }
+  return G4_OK;
+}
+
+int g4_unpack_tile_records(g4_context* ctx, int mem_space, const uint8_t* image, uint64_t image_len, const uint64_t* content_pos,
+                           int n_tiles, int checksum, uint64_t* payload_offsets, uint32_t* lens, int32_t* status) {
+  if (!ctx || !image || !content_pos || !payload_offsets || !lens || !status || n_tiles < 0) return G4_ERR_ARG;
+  if (mem_space != G4_MEM_DEVICE && mem_space != G4_MEM_HOST) return G4_ERR_ARG;
+  if (n_tiles == 0) return G4_OK;
+  CK(cudaSetDevice(ctx->device));
+  const int n = n_tiles;
+  const uint8_t* dImage = image;
+  const uint64_t* dPos = content_pos;
+  uint64_t* dPay = payload_offsets;
+  uint32_t* dLens = lens;
+  int32_t* dStatus = status;
+  if (mem_space == G4_MEM_HOST) {
+    CK(ctx->rcData.ensure(image_len + 16));
+    CK(ctx->rcPos.ensure(size_t(n) * 8));
+    CK(ctx->rcOffsets.ensure(size_t(n) * 8));
+    CK(ctx->rcLens.ensure(size_t(n) * 4));
+    CK(ctx->rcStatus.ensure(size_t(n) * 4));
+    CK(cudaMemcpyAsync(ctx->rcData.p, image, image_len, cudaMemcpyHostToDevice, ctx->stream));
+    CK(cudaMemcpyAsync(ctx->rcPos.p, content_pos, size_t(n) * 8, cudaMemcpyHostToDevice, ctx->stream));
+    dImage = ctx->rcData.as<uint8_t>();
+    dPos = ctx->rcPos.as<uint64_t>();
+    dPay = ctx->rcOffsets.as<uint64_t>();
+    dLens = ctx->rcLens.as<uint32_t>();
+    dStatus = ctx->rcStatus.as<int32_t>();
+  }
+  if (reinterpret_cast<uintptr_t>(dImage) & 7) return G4_ERR_ARG;
+  CK(ctx->rcOff.ensure(size_t(n) * 8));
+  CK(ctx->rcLen.ensure(size_t(n) * 4));
+  CK(ctx->rcCrc.ensure(size_t(n) * 4));
+  CK(ctx->rcStored.ensure(size_t(n) * 4));
+  CK(launch_record_unpack(dImage, image_len, dPos, n, dPay, dLens, ctx->rcOff.as<uint64_t>(), ctx->rcLen.as<uint32_t>(),
+                          ctx->rcStored.as<uint32_t>(), dStatus, ctx->stream));
+  ctx->launches++;
+  if (checksum) {
+    CK(launch_crc32c(dImage, ctx->rcOff.as<uint64_t>(), ctx->rcLen.as<uint32_t>(), n, ctx->rcCrc.as<uint32_t>(), 0, ctx->stream));
+    CK(launch_record_verify(ctx->rcCrc.as<uint32_t>(), ctx->rcStored.as<uint32_t>(), n, dStatus, ctx->stream));
+    ctx->launches += 2;
+  }
+  if (mem_space == G4_MEM_HOST) {
+    CK(cudaMemcpyAsync(payload_offsets, dPay, size_t(n) * 8, cudaMemcpyDeviceToHost, ctx->stream));
+    CK(cudaMemcpyAsync(lens, dLens, size_t(n) * 4, cudaMemcpyDeviceToHost, ctx->stream));
+    CK(cudaMemcpyAsync(status, dStatus, size_t(n) * 4, cudaMemcpyDeviceToHost, ctx->stream));
+    CK(cudaStreamSynchronize(ctx->stream));
+  }
+  return G4_OK;
 }
 
 uint64_t g4_encode_arena_bound(const g4_band_desc* b) {

@@ -26,7 +26,7 @@
 extern "C" {
 #endif
 
-#define G4_ABI_VERSION 2
+#define G4_ABI_VERSION 3
 
 /* Status codes.  G4_DECLINED is the Java `null` return of ICompressionEncoder.encode ("codec cannot or
  * should not encode this tile": all-null tile, tile too small for the predictor, singular LSOP matrix).
@@ -131,6 +131,38 @@ int g4_decode_tiles(g4_context* ctx, const g4_codec_list* codecs, const g4_band_
 
 /* Upper bound of the arena bytes g4_encode_tiles can produce for a band (4*n per tile). */
 uint64_t g4_encode_arena_bound(const g4_band_desc* band);
+
+
+/* ---- GVRS tile records: the wire format either side of the codec path -----------------------
+ * A record is [size:int32 LE][type:uint8][0,0,0] content, zero padding, [crc32c:int32 LE]; size is a multiple of 8 and
+ * counts everything (C/gvrs/RecordManager.java:70-78,137-139,161-204).  A tile record (type 2) of a one-element raster
+ * holds [tileIndex:int32][len:int32][len bytes] (RecordManager.writeTile :386-490; len == 4*nRows*nCols means raw samples,
+ * RecordManager.readTile :492-516).  The tile directory stores the position of the CONTENT (record position + 8) divided
+ * by 8 (C/gvrs/TileDirectory.java:121-146).  mem_space says where data / arena / records / image live; the small
+ * per-tile arrays (offsets, lens, positions, status) live in the same space. */
+
+/* CRC-32C of n byte ranges data[offsets[i] .. +sizes[i]) (C/util/GridfourCRC32C.java:156-163: Castagnoli polynomial,
+ * reflected, initial value and final xor 0xffffffff -- what RecordManager.fileSpaceFinishRecord stores). */
+int g4_crc32c(g4_context* ctx, int mem_space, const uint8_t* data, const uint64_t* offsets, const uint32_t* sizes, int n,
+              uint32_t* crc_out);
+
+/* Upper bound of the record bytes g4_pack_tile_records writes for n_tiles payloads of payload_bytes in total. */
+uint64_t g4_tile_records_bound(int n_tiles, uint64_t payload_bytes);
+
+/* Frames the payloads of a batch (what g4_encode_tiles returned) as consecutive tile records, the first one at file
+ * position base_pos (a multiple of 8).  tile_index may be NULL: record t then carries first_tile_index + t.  checksum != 0
+ * computes the CRC-32C of every record, otherwise the field stays zero like in the reference.  content_pos[t] receives the
+ * file position the tile directory has to store for tile t; *total_bytes the number of record bytes written. */
+int g4_pack_tile_records(g4_context* ctx, int mem_space, const uint8_t* arena, const uint64_t* offsets, const uint32_t* lens,
+                         const int32_t* tile_index, int first_tile_index, int n_tiles, int checksum, uint64_t base_pos,
+                         uint8_t* records, uint64_t records_cap, uint64_t* content_pos, uint64_t* total_bytes);
+
+/* Inverse: image is a GVRS file (or a part of one: content_pos is relative to image) of image_len bytes, content_pos[t]
+ * the directory position of tile t (0 = tile absent -> status G4_DECLINED, len 0).  Checks every record (type, sizes,
+ * bounds and, with checksum != 0, the CRC-32C) and returns payload_offsets / lens in the form g4_decode_tiles takes with
+ * `image` as its arena.  A damaged record gives status G4_ERR_FORMAT for that tile; the call itself still succeeds. */
+int g4_unpack_tile_records(g4_context* ctx, int mem_space, const uint8_t* image, uint64_t image_len, const uint64_t* content_pos,
+                           int n_tiles, int checksum, uint64_t* payload_offsets, uint32_t* lens, int32_t* status);
 
 /* ---- benchmark support --------------------------------------------------------------------------
  * Fills a device raster with the synthetic fractal terrain of include/g4terrain.h
