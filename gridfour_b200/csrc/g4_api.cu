@@ -89,6 +89,8 @@ struct g4_context {
   DevBuf sGrid, sArena, sOffsets, sLens, sCodec, sPred, sStatus;
   // host-buffer decode pipeline: payload H2D / kernels / raster D2H of consecutive chunks overlap
   cudaStream_t copyIn = nullptr, copyOut = nullptr;
+  cudaStream_t lsopStream = nullptr;  // LSOP12 decode: wavefront of chunk k beside kernels H/T of chunk k+1
+  cudaEvent_t lsopEv[5] = {};
   cudaEvent_t evIn[16] = {}, evDone[16] = {}, evStart = nullptr;
   // optional per-kernel timing (CUDA events on the launching stream): [0]=decode, [1]=encode, by codec kind
   bool timing = false;
@@ -309,10 +311,17 @@ int launch_decoder(g4_context* ctx, int codecId, DecodeArgs& a, int nCtas) {
       CK(ctx->coef.ensure(size_t(nTiles) * 12 * sizeof(float)));
       CK(ctx->defer.ensure(size_t(nTiles) * sizeof(int)));
       CK(ctx->lsopMeta.ensure(size_t(nTiles) * lsop_meta_bytes()));
+    {
+      if (!ctx->lsopStream) {
+        CK(cudaStreamCreateWithFlags(&ctx->lsopStream, cudaStreamNonBlocking));
+        for (int k = 0; k < 5; k++) CK(cudaEventCreateWithFlags(&ctx->lsopEv[k], cudaEventDisableTiming));
+      }
+      int nLaunch = 0;
       CK(launch_lsop_decode(a, ctx->coef.as<float>(), ctx->lsopMeta.as<uint8_t>(), ctx->defer.as<int>(), ctx->counters.as<int>() + 56,
-                            nCtas, nTiles, ctx->stream));
-      ctx->launches += 4;
+                            nCtas, nTiles, ctx->stream, ctx->lsopStream, ctx->lsopEv, &nLaunch));
+      ctx->launches += uint64_t(nLaunch);
       return G4_OK;
+    }
     default:
       tlsError = "codec not implemented on the GPU yet";
       return G4_ERR_UNSUPPORTED;
@@ -602,6 +611,11 @@ void g4_context_destroy(g4_context* ctx) {
     for (int k = 0; k < kMaxChunks; k++) { cudaEventDestroy(ctx->evIn[k]); cudaEventDestroy(ctx->evDone[k]); }
   }
   if (ctx->evStart) cudaEventDestroy(ctx->evStart);
+  if (ctx->lsopStream) {
+    cudaStreamSynchronize(ctx->lsopStream);
+    cudaStreamDestroy(ctx->lsopStream);
+    for (int k = 0; k < 5; k++) cudaEventDestroy(ctx->lsopEv[k]);
+  }
   for (auto& b : ctx->slots) b.release();
   DevBuf* bufs[] = {&ctx->candLens, &ctx->candPreds, &ctx->candStatus, &ctx->counters, &ctx->scratch, &ctx->lists, &ctx->src,
                     &ctx->total, &ctx->coef, &ctx->defer, &ctx->lsopMeta, &ctx->wide, &ctx->encScratch, &ctx->region, &ctx->jobLen, &ctx->jobOff, &ctx->jobOut, &ctx->jobTotal,

@@ -141,11 +141,12 @@ cudaError_t launch_deflate_decode(const DecodeArgs& a, uint8_t* region, size_t r
 cudaError_t launch_float_decode(const DecodeArgs& a, uint8_t* region, size_t regionStride, int nCtas, int nTilesUpper,
                                 cudaStream_t s);
 // coef: [nTiles][12] floats of device scratch; nTilesUpper bounds the number of LSOP tiles in the list
-// defer: nTilesUpper ints; deferCounters: 2 zeroed ints (deferred-tile count, work counter of the general kernel)
+// defer: nTilesUpper ints; deferCounters: 6 zeroed ints (deferred-tile count, work counter of the general kernel, four
+// chunk counters of the text kernel); s2 / ev (5 events): second stream for the chunked overlap, or null
 // meta: nTilesUpper * lsop_meta_bytes() bytes (interior code lengths + text position handed from kernel H to kernel T)
 size_t lsop_meta_bytes();
 cudaError_t launch_lsop_decode(const DecodeArgs& a, float* coef, uint8_t* meta, int* defer, int* deferCounters, int nCtas,
-                               int nTilesUpper, cudaStream_t s);
+                               int nTilesUpper, cudaStream_t s, cudaStream_t s2, cudaEvent_t* ev, int* launches);
 
 
 // ---- zlib-stream encode stages (g4_deflate_encode.cu, g4_lsop.cu) ------------------------------------------------
