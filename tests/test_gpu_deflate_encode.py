@@ -105,3 +105,30 @@ def test_batched_best_of_matches_codec_master(g4, oracle):
             want = oracle.master_encode_i32(ids, tile)
             assert batch.payload(t) == want, "tile %d codecs %s: %s" % (t, names, first_diff(batch.payload(t), want))
         assert np.array_equal(master.decodeTiles(batch), grid)
+
+
+def test_deflate_stream_length_edges_match_oracle(g4, oracle):
+    """Streams on both sides of the staged encoder's 65,535-byte limit (sort / match / decide / emit kernels below it, the
+    one-thread-per-stream replay above), several DEFLATE blocks per stream (> 16,383 symbols), long runs (every position
+    in one hash bucket, matches of 258) and incompressible data (stored blocks): byte-identical to the oracle's zlib."""
+    rng = np.random.default_rng(5)
+    enc = g4.CodecDeflate()
+    tiles = {}
+    # 150x150 = 22,500 cells: one-byte residuals (22.5 KB, two blocks), two-byte (45 KB), three-byte (67.5 KB > limit)
+    tiles["1byte"] = rng.integers(-60, 60, (150, 150)).cumsum(axis=1).astype(np.int32)
+    tiles["2byte"] = (rng.integers(-15000, 15000, (150, 150))).astype(np.int32)
+    tiles["3byte"] = (rng.integers(-2000000, 2000000, (150, 150))).astype(np.int32)
+    # 104x105 = 10,920 cells of 6-byte codes -> 65,520 bytes for one predictor, a few more or fewer for the others
+    tiles["near_limit"] = np.where(rng.random((104, 105)) < 0.5, 2 ** 31 - 7, -(2 ** 31) + 9).astype(np.int32)
+    tiles["zeros"] = np.zeros((200, 200), np.int32)
+    tiles["period7"] = (np.arange(180 * 240) % 7).reshape(180, 240).astype(np.int32)
+    tiles["noise"] = rng.integers(-(2 ** 31), 2 ** 31, (90, 120), dtype=np.int64).astype(np.int32)
+    for name, grid in tiles.items():
+        got = enc.encode(1, grid.shape[0], grid.shape[1], grid)
+        want, _pred = oracle.codec_encode_i32(oracle.CODEC_DEFLATE, 1, grid)
+        if want is None:
+            assert got is None, name
+            continue
+        assert got is not None and bytes(got) == bytes(want), "%s: %s" % (name, first_diff(got, want))
+        out = g4.CodecDeflate().decode(grid.shape[0], grid.shape[1], got)
+        assert np.array_equal(out, grid), name
