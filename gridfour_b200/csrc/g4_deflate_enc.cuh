@@ -762,11 +762,6 @@ G4_HD inline void deflate_decide_table(const uint8_t* in, uint32_t n, int level,
     prevMatch = matchStart;
     matchLength = kDefMinMatch - 1;
     if (lookahead >= uint32_t(kDefMinMatch) && prevLength < L.maxLazy) {
-#ifdef __CUDA_ARCH__
-      // the walk only moves forward: pull the table (and the input) a few hundred bytes ahead into L2/L1
-      asm volatile("prefetch.global.L1 [%0];" ::"l"(table + (strstart + 48u < n ? strstart + 48u : strstart)));
-      asm volatile("prefetch.global.L1 [%0];" ::"l"(in + (strstart + 256u < n ? strstart + 256u : strstart)));
-#endif
       const uint2 e = table[strstart];
       const uint32_t w = prevLength >= L.goodLength ? e.y : e.x;
       const int len = int(w & 0x1ffu);

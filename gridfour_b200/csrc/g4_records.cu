@@ -61,21 +61,74 @@ __device__ inline uint32_t crc_range(const uint32_t (*T)[256], const uint8_t* p,
 
 }  // namespace
 
-// One thread per byte range (ranges are whole records: a few KB to a few hundred KB each, thousands per launch).
+// GF(2) arithmetic for joining the CRCs of adjacent pieces (the construction of zlib's crc32_combine, with the
+// Castagnoli polynomial): crc(A||B) = crc(A) * x^(8|B|) mod P  xor  crc(B).
+__device__ inline uint32_t crc_multmodp(uint32_t a, uint32_t b) {
+  uint32_t m = 1u << 31, p = 0;
+  for (;;) {
+    if (a & m) {
+      p ^= b;
+      if ((a & (m - 1u)) == 0) break;
+    }
+    m >>= 1;
+    b = (b & 1u) ? (b >> 1) ^ kCrc32cPoly : b >> 1;
+  }
+  return p;
+}
+// x^(n * 2^k) mod P from the table of x^(2^i) mod P
+__device__ inline uint32_t crc_x2nmodp(const uint32_t* x2n, uint64_t n, uint32_t k) {
+  uint32_t p = 1u << 31;  // x^0
+  while (n) {
+    if (n & 1u) p = crc_multmodp(x2n[k & 31u], p);
+    n >>= 1;
+    k++;
+  }
+  return p;
+}
+
+// One WARP per byte range (ranges are whole records: a few KB to a few hundred KB each, thousands per launch): every
+// lane takes a contiguous piece (a multiple of 8 bytes, so that the slice-by-8 loop stays aligned), the 32 piece CRCs
+// are joined by a shuffle tree in which level d multiplies the left CRC by x^(8 * piece * 2^d).
 // storeAtEnd: also write the value, little-endian, into the four bytes that follow the range (the record's checksum field).
 __global__ void __launch_bounds__(kCrcThreads) crc32c_kernel(const uint8_t* data, const uint64_t* offsets, const uint32_t* sizes, int n,
                                                              uint32_t* out, int storeAtEnd) {
   __shared__ uint32_t T[8][256];
+  __shared__ uint32_t x2n[32];
   crc_build_tables(T);
-  const int i = blockIdx.x * kCrcThreads + threadIdx.x;
+  if (threadIdx.x == 0) {
+    uint32_t p = 1u << 30;  // x^1
+    x2n[0] = p;
+    for (int i = 1; i < 32; i++) x2n[i] = p = crc_multmodp(p, p);
+  }
+  __syncthreads();
+  const int lane = threadIdx.x & 31;
+  const int i = (blockIdx.x * kCrcThreads + threadIdx.x) >> 5;
   if (i >= n) return;
   const uint8_t* p = data + offsets[i];
   const uint32_t len = sizes[i];
-  const uint32_t c = crc_range(T, p, len);
-  if (out) out[i] = c;
-  if (storeAtEnd) {
-    uint8_t* e = const_cast<uint8_t*>(p) + len;
-    e[0] = uint8_t(c); e[1] = uint8_t(c >> 8); e[2] = uint8_t(c >> 16); e[3] = uint8_t(c >> 24);
+  // piece size: a multiple of 8, at least 64 bytes; short ranges leave the upper lanes with nothing
+  uint32_t piece = ((len + 31u) / 32u + 7u) & ~7u;
+  if (piece < 64u) piece = 64u;
+  const uint64_t begin = uint64_t(lane) * piece;
+  const uint32_t mine = begin >= len ? 0u : (len - begin < piece ? uint32_t(len - begin) : piece);
+  uint32_t c = crc_range(T, p + begin, mine);  // CRC of an empty piece is 0, the identity of the join
+  uint32_t myLen = mine;
+  // join: after level d, lanes that are multiples of 2^(d+1) hold the CRC of 2^(d+1) pieces
+#pragma unroll
+  for (int d = 0; d < 5; d++) {
+    const uint32_t rc = __shfl_down_sync(0xffffffffu, c, 1u << d);
+    const uint32_t rl = __shfl_down_sync(0xffffffffu, myLen, 1u << d);
+    if ((lane & ((2 << d) - 1)) == 0 && rl) {
+      c = crc_multmodp(crc_x2nmodp(x2n, rl, 3), c) ^ rc;
+      myLen += rl;
+    }
+  }
+  if (lane == 0) {
+    if (out) out[i] = c;
+    if (storeAtEnd) {
+      uint8_t* e = const_cast<uint8_t*>(p) + len;
+      e[0] = uint8_t(c); e[1] = uint8_t(c >> 8); e[2] = uint8_t(c >> 16); e[3] = uint8_t(c >> 24);
+    }
   }
 }
 
@@ -195,7 +248,8 @@ __global__ void __launch_bounds__(kThreads) record_verify_kernel(const uint32_t*
 cudaError_t launch_crc32c(const uint8_t* data, const uint64_t* offsets, const uint32_t* sizes, int n, uint32_t* out, int storeAtEnd,
                           cudaStream_t s) {
   if (n <= 0) return cudaSuccess;
-  crc32c_kernel<<<(n + kCrcThreads - 1) / kCrcThreads, kCrcThreads, 0, s>>>(data, offsets, sizes, n, out, storeAtEnd);
+  const int perCta = kCrcThreads / 32;
+  crc32c_kernel<<<(n + perCta - 1) / perCta, kCrcThreads, 0, s>>>(data, offsets, sizes, n, out, storeAtEnd);
   return cudaGetLastError();
 }
 cudaError_t launch_record_layout(const uint32_t* lens, int n, uint64_t basePos, uint64_t* contentPos, uint64_t* crcOff, uint32_t* crcLen,
