@@ -545,7 +545,7 @@ __device__ inline void lsop_warp_column_scan(const TileView& t, int col, int r0,
   __syncwarp();
 }
 
-__global__ void __launch_bounds__(kThreads) lsop_decode_head_kernel(DecodeArgs a, float* coefOut, uint8_t* meta, int* defer,
+__global__ void __launch_bounds__(kThreads, 5) lsop_decode_head_kernel(DecodeArgs a, float* coefOut, uint8_t* meta, int* defer,
                                                                     int* deferCount, uint32_t stageWords, int listBegin, int listEnd) {
   __shared__ CanonWarpShared WS[kWarps];
   const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
