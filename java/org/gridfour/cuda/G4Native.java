@@ -52,6 +52,21 @@ final class G4Native {
   static final MethodHandle DECODE_TILES = h("g4_decode_tiles",
     FunctionDescriptor.of(JAVA_INT, ADDRESS, ADDRESS, ADDRESS, JAVA_INT, ADDRESS, ADDRESS, ADDRESS, ADDRESS, ADDRESS));
 
+  // GVRS records (RecordManager.java:161-204,386-516; GridfourCRC32C.java): see include/g4codec.h
+  // int g4_crc32c(ctx, mem_space, data, offsets, sizes, n, crc_out)
+  static final MethodHandle CRC32C = h("g4_crc32c",
+    FunctionDescriptor.of(JAVA_INT, ADDRESS, JAVA_INT, ADDRESS, ADDRESS, ADDRESS, JAVA_INT, ADDRESS));
+  // uint64 g4_tile_records_bound(n_tiles, payload_bytes)
+  static final MethodHandle TILE_RECORDS_BOUND = h("g4_tile_records_bound", FunctionDescriptor.of(JAVA_LONG, JAVA_INT, JAVA_LONG));
+  // int g4_pack_tile_records(ctx, mem_space, arena, offsets, lens, tile_index, first_tile_index, n_tiles, checksum, base_pos,
+  //                          records, records_cap, content_pos, total_bytes)
+  static final MethodHandle PACK_TILE_RECORDS = h("g4_pack_tile_records",
+    FunctionDescriptor.of(JAVA_INT, ADDRESS, JAVA_INT, ADDRESS, ADDRESS, ADDRESS, ADDRESS, JAVA_INT, JAVA_INT, JAVA_INT, JAVA_LONG,
+      ADDRESS, JAVA_LONG, ADDRESS, ADDRESS));
+  // int g4_unpack_tile_records(ctx, mem_space, image, image_len, content_pos, n_tiles, checksum, payload_offsets, lens, status)
+  static final MethodHandle UNPACK_TILE_RECORDS = h("g4_unpack_tile_records",
+    FunctionDescriptor.of(JAVA_INT, ADDRESS, JAVA_INT, ADDRESS, JAVA_LONG, ADDRESS, JAVA_INT, JAVA_INT, ADDRESS, ADDRESS, ADDRESS));
+
   /** One context (CUDA stream + scratch) per thread: decoder instances are entered concurrently by the
    *  application thread and the read-ahead thread (TileDecompressionAssistant.java:88). */
   static final ThreadLocal<MemorySegment> CONTEXT = ThreadLocal.withInitial(() -> {
