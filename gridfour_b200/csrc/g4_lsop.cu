@@ -190,7 +190,17 @@ struct InteriorPackedSink {
   __device__ __forceinline__ void flush() {
     do {
       const int ph = col & 7;
-      if (need == 8 || (need == 6 && (ph == 0 || ph == 2))) {
+      if (need == 8) {
+        // the common case, an aligned group of eight: no variable shifts, the two leftover bytes move down
+        const uint32_t x0 = uint32_t(lo) ^ 0x80808080u, x1 = uint32_t(lo >> 32) ^ 0x80808080u;
+        int32_t* const g = rowp + col;
+        *reinterpret_cast<int4*>(g) = make_int4(sx_byte(x0, 0x8880), sx_byte(x0, 0x9991), sx_byte(x0, 0xaaa2), sx_byte(x0, 0xbbb3));
+        *reinterpret_cast<int4*>(g + 4) = make_int4(sx_byte(x1, 0x8880), sx_byte(x1, 0x9991), sx_byte(x1, 0xaaa2), sx_byte(x1, 0xbbb3));
+        lo = hi;
+        hi = 0;
+        cnt -= 8;
+        col += 8;
+      } else if (need == 6 && (ph == 0 || ph == 2)) {
         // an aligned group of eight, or the six-column group at either end of a row's interior (columns 2..7 as
         // int2 + int4, columns C-8..C-3 as int4 + int2): queue byte j goes to column col + j
         const uint64_t al = lo << (8 * ph);
