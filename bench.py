@@ -254,10 +254,19 @@ def main():
     dev = torch.device("cuda", local_rank)
     if world > 1:
         os.environ.setdefault("MASTER_ADDR", "127.0.0.1")
-        # the contract is ONE JSON line on stdout: keep NCCL's own "NCCL version ..." banner (NCCL_DEBUG=VERSION/INFO) off it
-        if os.environ.get("NCCL_DEBUG", "").upper() in ("VERSION", "INFO", "TRACE") and not os.environ.get("NCCL_DEBUG_FILE"):
-            os.environ["NCCL_DEBUG_FILE"] = "/dev/stderr"
-        dist.init_process_group("nccl", device_id=dev)
+        # the contract is ONE JSON line on stdout: NCCL prints its "NCCL version ..." banner to fd 1 when the communicator
+        # is created, so fd 1 points at stderr while the process group comes up and the first collective runs
+        sys.stdout.flush()
+        saved_fd = os.dup(1)
+        os.dup2(2, 1)
+        try:
+            dist.init_process_group("nccl", device_id=dev)
+            dist.barrier()
+            torch.cuda.synchronize(dev)
+        finally:
+            sys.stdout.flush()
+            os.dup2(saved_fd, 1)
+            os.close(saved_fd)
     L = _lib.lib()
     # the context launches on torch's current stream so torch.cuda.Event brackets exactly the library's kernels
     stream = torch.cuda.Stream(dev)
