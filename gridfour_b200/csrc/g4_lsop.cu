@@ -847,8 +847,13 @@ __global__ void __launch_bounds__(kThreads) lsop_wavefront_kernel(DecodeArgs a, 
 //   previous block, shuffled before the windows shift.
 // A row takes P = max(C,136) steps so that lanes 30,31 of a group have stored a block (and passed the __syncwarp that
 // ends their iteration) at least one iteration before the next group's feeders fetch it; groups need no drain.
+// Three CTAs per SM on purpose.  Every lane streams its own raster row, 16 bytes per iteration, and lives off L1: the
+// 128-byte line a lane touches must survive the eight iterations that consume it.  24 warps x 32 rows keep 768 lines
+// live; measured on the config-3 shard: 3 CTAs/SM 1.46 ms, 4 CTAs/SM 1.49 ms, 5 CTAs/SM (1280 lines) 18 ms -- past that
+// point the lines are evicted between iterations and every load becomes a scattered 32-byte DRAM access.  L1-bypassing
+// loads (ld.global.cg) show the same collapse at any occupancy (16-18 ms), and so does a second load in flight per lane.
 // mode 0: every tile of [listBegin, listEnd); 1: only tiles the fast text kernel decoded (meta T0 != 0); 2: only the others
-__global__ void __launch_bounds__(kThreads, 4) lsop_wavefront4_kernel(DecodeArgs a, const float* coef, const uint8_t* meta, int listBegin,
+__global__ void __launch_bounds__(kThreads, 3) lsop_wavefront4_kernel(DecodeArgs a, const float* coef, const uint8_t* meta, int listBegin,
                                                                       int listEnd, int mode) {
   const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
   const int li = listBegin + blockIdx.x * kWarps + warp;
