@@ -18,6 +18,7 @@
 #include "g4_kernels.h"
 #include "g4_predict.cuh"
 #include "g4_huffdec.cuh"
+#include "g4_huff_fast.cuh"
 
 namespace g4 {
 
@@ -353,8 +354,13 @@ __global__ void __launch_bounds__(kThreads) huffman_encode_kernel(EncodeArgs a) 
 // =================================================================================================
 // Decode (stream decoder in g4_huffdec.cuh)
 // =================================================================================================
-__global__ void __launch_bounds__(kThreads) huffman_decode_kernel(DecodeArgs a) {
-  __shared__ HuffDecShared S;
+// stageWords: capacity of the fast decoder's staging buffer (dynamic shared memory sized by the launcher from the tile
+// size); a packing that does not fit, or is not 4-byte aligned, takes the general decoder over HBM.
+__global__ void __launch_bounds__(kThreads, 4) huffman_decode_kernel(DecodeArgs a, uint32_t stageWords) {
+  extern __shared__ __align__(16) unsigned char huffDecSmem[];
+  HuffDecShared& S = *reinterpret_cast<HuffDecShared*>(huffDecSmem);
+  HuffFastShared& F = *reinterpret_cast<HuffFastShared*>(huffDecSmem);
+  __shared__ uint32_t scanSm[kWarps + 1];
   __shared__ int sTile;
   const int tid = threadIdx.x;
   for (;;) {
@@ -376,21 +382,33 @@ __global__ void __launch_bounds__(kThreads) huffman_decode_kernel(DecodeArgs a) 
     const uint32_t expect = pred == G4_PRED_DIFF_NULLS ? uint32_t(n) : uint32_t(n - 1);
     if (len < 12 || pred < 1 || pred > 4 || nM32 < expect || nM32 > uint32_t(6 * n)) status = G4_ERR_FORMAT;
     if (status == G4_OK) {
-      BitSrc src;
-      src.init(packing + 10, len - 10);
       uint8_t* m32 = a.scratch + size_t(blockIdx.x) * a.scratchStride;
       uint32_t endBit;
-      if (!huffman_decode_stream(S, src, 0, nM32, m32, &endBit)) status = G4_ERR_FORMAT;
+      bool ok;
+      const uint32_t nW = (len - 8u + 3u) >> 2;  // words from byte 8 (4-byte aligned) to the end of the packing
+      if ((reinterpret_cast<uintptr_t>(packing) & 3) == 0 && nW <= stageWords) {
+        const uint32_t* g = reinterpret_cast<const uint32_t*>(packing + 8);
+        for (uint32_t i = tid; i < nW; i += kThreads) F.sw[i] = __ldg(g + i);
+        if (tid < 8) F.sw[nW + tid] = 0;
+        __syncthreads();
+        if (tid == 0 && (len & 3)) F.sw[nW - 1] &= (1u << (8 * (len & 3))) - 1u;  // bytes past the packing read as zero
+        ok = huff_fast_decode_stream(F, 16u, (len - 8u) * 8u, nM32, m32, &endBit);
+      } else {
+        BitSrc src;
+        src.init(packing + 10, len - 10);
+        ok = huffman_decode_stream(S, src, 0, nM32, m32, &endBit);
+      }
+      if (!ok) status = G4_ERR_FORMAT;
       else {
         __syncthreads();
-        if (!m32_parse_to_cells(m32, nM32, pred, t, expect, S.scan)) status = G4_ERR_FORMAT;
+        if (!m32_parse_to_cells(m32, nM32, pred, t, expect, scanSm)) status = G4_ERR_FORMAT;
         else {
           __syncthreads();
           if (pred == G4_PRED_DIFF_NULLS) predictor_inverse_nulls(t, seed);
           else {
             if (tid == 0) t.at(0, 0) = seed;
             __syncthreads();
-            predictor_inverse(pred, t, S.scan);
+            predictor_inverse(pred, t, scanSm);
           }
         }
       }
@@ -411,7 +429,24 @@ cudaError_t launch_huffman_encode(const EncodeArgs& a, int nCtas, cudaStream_t s
 }
 
 cudaError_t launch_huffman_decode(const DecodeArgs& a, int nCtas, cudaStream_t s) {
-  huffman_decode_kernel<<<nCtas, kThreads, 0, s>>>(a);
+  // staging capacity of the fast decoder: 6 bits per sample of the tile (legacy Huffman over M32 bytes takes 4-5 bits
+  // per sample on terrain), at most 160 KB (one CTA per SM)
+  uint64_t bytes = uint64_t(a.band.tile_rows) * uint64_t(a.band.tile_cols) * 6 / 8 + 64;
+  if (bytes > 160u * 1024u) bytes = 160u * 1024u;
+  uint32_t stageWords = uint32_t((bytes + 3) / 4);
+  if (stageWords < uint32_t(kHfStageWordsMin)) stageWords = kHfStageWordsMin;
+  static const bool fastOn = !(getenv("G4_HUFF_FAST") && atoi(getenv("G4_HUFF_FAST")) == 0);
+  if (!fastOn) stageWords = 0;
+  size_t smem = huff_fast_smem_bytes(stageWords);
+  if (smem < sizeof(HuffDecShared)) smem = sizeof(HuffDecShared);
+  static bool attr = false;
+  if (!attr) {
+    cudaError_t e = cudaFuncSetAttribute(huffman_decode_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                         int(huff_fast_smem_bytes(160 * 1024 / 4 + 16)));
+    if (e != cudaSuccess) return e;
+    attr = true;
+  }
+  huffman_decode_kernel<<<nCtas, kThreads, smem, s>>>(a, stageWords);
   return cudaGetLastError();
 }
 
