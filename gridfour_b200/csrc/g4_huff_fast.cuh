@@ -84,17 +84,19 @@ __device__ inline void hf_parse_tree(HuffFastShared& S, uint32_t startBit, uint3
   stack[0] = 0;
   slot[0] = 0;
   S.leafSym[0] = -1;
+  HfCursor cur;  // register bit buffer: the tree is read one and eight bits at a time while 255 threads wait
+  cur.init(S, pos);
   while (leaves < L) {
-    if (sp == 0 || nodes >= 511 || pos + 9 > nBits + 8) { S.error = 1; return; }
+    if (sp == 0 || nodes >= 511 || cur.pos + 9 > nBits + 8) { S.error = 1; return; }
     const int parent = stack[sp - 1];
-    const uint32_t bit = src.bits(pos, 1);
-    pos += 1;
+    const uint32_t bit = cur.peek() & 1u;
+    cur.skip(S, 1);
     const int id = nodes++;
     S.kid[parent][slot[parent]++] = uint16_t(id);
     if (bit) {
-      S.leafSym[id] = int16_t(src.bits(pos, 8));
+      S.leafSym[id] = int16_t(cur.peek() & 0xffu);
       slot[id] = 2;
-      pos += 8;
+      cur.skip(S, 8);
       leaves++;
       while (sp > 0 && slot[stack[sp - 1]] == 2) sp--;
     } else {
@@ -104,6 +106,7 @@ __device__ inline void hf_parse_tree(HuffFastShared& S, uint32_t startBit, uint3
       stack[sp++] = uint16_t(id);
     }
   }
+  pos = cur.pos;
   if (sp != 0 || pos > nBits) { S.error = 1; return; }
   S.treeBits = pos;
 }
