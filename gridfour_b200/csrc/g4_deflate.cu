@@ -14,10 +14,12 @@
 namespace g4 {
 
 // ---- CodecDeflate --------------------------------------------------------------------------------------
-__global__ void __launch_bounds__(kThreads) deflate_inflate_kernel(DecodeArgs a, uint8_t* region, size_t regionStride) {
-  __shared__ InflateWarpShared S[kWarps];
-  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-  const int li = blockIdx.x * kWarps + warp;
+// One warp per CTA: streams differ a lot in length, and a CTA of eight warps keeps its slot until the longest is through
+// (measured on CodecFloat: 24 % warps active with eight-warp CTAs).
+__global__ void __launch_bounds__(32) deflate_inflate_kernel(DecodeArgs a, uint8_t* region, size_t regionStride) {
+  __shared__ InflateWarpShared S[1];
+  const int warp = 0, lane = threadIdx.x & 31;
+  const int li = blockIdx.x;
   if (li >= *a.listCount) return;
   const int tIdx = a.list[li];
   const int n = a.band.tile_rows * a.band.tile_cols;
@@ -72,10 +74,10 @@ __global__ void __launch_bounds__(kThreads) deflate_finish_kernel(DecodeArgs a, 
 // ---- CodecFloat ----------------------------------------------------------------------------------------
 // packing = [codecIndex][0] + 5 x ([len:int32 LE][zlib stream]): sign bitmap, exponent bytes, three
 // row-delta coded mantissa byte planes (CodecFloat.java:377-387).  Staging per tile: 5 planes of n bytes.
-__global__ void __launch_bounds__(kThreads) float_inflate_kernel(DecodeArgs a, uint8_t* region, size_t regionStride) {
-  __shared__ InflateWarpShared S[kWarps];
-  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-  const int job = blockIdx.x * kWarps + warp;
+__global__ void __launch_bounds__(32) float_inflate_kernel(DecodeArgs a, uint8_t* region, size_t regionStride) {
+  __shared__ InflateWarpShared S[1];
+  const int warp = 0, lane = threadIdx.x & 31;
+  const int job = blockIdx.x;
   const int li = job / 5, plane = job - li * 5;
   if (li >= *a.listCount) return;
   const int tIdx = a.list[li];
@@ -177,7 +179,7 @@ __global__ void __launch_bounds__(kThreads) float_finish_kernel(DecodeArgs a, co
 
 cudaError_t launch_deflate_decode(const DecodeArgs& a, uint8_t* region, size_t regionStride, int nCtas, int nTilesUpper,
                                   cudaStream_t s) {
-  deflate_inflate_kernel<<<(nTilesUpper + kWarps - 1) / kWarps, kThreads, 0, s>>>(a, region, regionStride);
+  deflate_inflate_kernel<<<nTilesUpper, 32, 0, s>>>(a, region, regionStride);
   cudaError_t e = cudaGetLastError();
   if (e != cudaSuccess) return e;
   deflate_finish_kernel<<<nCtas, kThreads, 0, s>>>(a, region, regionStride);
@@ -186,7 +188,7 @@ cudaError_t launch_deflate_decode(const DecodeArgs& a, uint8_t* region, size_t r
 
 cudaError_t launch_float_decode(const DecodeArgs& a, uint8_t* region, size_t regionStride, int nCtas, int nTilesUpper,
                                 cudaStream_t s) {
-  float_inflate_kernel<<<(nTilesUpper * 5 + kWarps - 1) / kWarps, kThreads, 0, s>>>(a, region, regionStride);
+  float_inflate_kernel<<<nTilesUpper * 5, 32, 0, s>>>(a, region, regionStride);
   cudaError_t e = cudaGetLastError();
   if (e != cudaSuccess) return e;
   float_finish_kernel<<<nCtas, kThreads, 0, s>>>(a, region, regionStride);
