@@ -114,3 +114,27 @@ def test_terrain_generator_matches_cpu(g4, oracle):
     ctx.fill_terrain(f.data_ptr(), 1, 5, 7, 33, 65)
     ctx.synchronize()
     assert np.array_equal(f.cpu().numpy(), oracle.terrain_f32(5, 7, 33, 65))
+
+
+def test_general_decoder_still_decodes(oracle):
+    """The staged fast path (g4_huff_fast.cuh) takes every packing that fits its staging buffer; the general decoder over
+    HBM (g4_huffdec.cuh) stays for the rest.  G4_HUFF_FAST=0 sends everything through it (read once per process, hence
+    the subprocess): same bit-exact result."""
+    import os
+    import subprocess
+    import sys
+
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    code = (
+        "import sys; sys.path.insert(0, %r); sys.path.insert(0, %r)\n"
+        "import numpy as np, gridfour_b200 as g4\n"
+        "from oracle import g4oracle as o\n"
+        "from gpu_common import parity_grids\n"
+        "c = g4.CodecHuffman()\n"
+        "for name, grid in parity_grids(o).items():\n"
+        "    p, _ = o.codec_encode_i32(o.CODEC_HUFFMAN, 0, grid)\n"
+        "    assert np.array_equal(c.decode(grid.shape[0], grid.shape[1], p), grid), name\n"
+        "print('general ok')\n" % (root, os.path.join(root, "tests")))
+    env = dict(os.environ, G4_HUFF_FAST="0")
+    r = subprocess.run([sys.executable, "-c", code], capture_output=True, text=True, env=env, timeout=600)
+    assert r.returncode == 0 and "general ok" in r.stdout, r.stderr[-2000:]
