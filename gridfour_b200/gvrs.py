@@ -13,7 +13,8 @@ Everything that walks sample bytes runs on the GPU through the C ABI: record che
 (g4_pack_tile_records), record validation + payload location (g4_unpack_tile_records) and the codecs themselves
 (g4_encode_tiles / g4_decode_tiles with the file image as the arena).  The batched tile entry points serve rasters with
 one element per tile (the BASELINE configurations); files with several elements are parsed and re-framed record by
-record, with the GPU computing the checksums.
+record with the GPU computing the checksums, and read element by element (read_raster walks the [len][bytes] chains
+on the host and hands the payload offsets to g4_decode_tiles).
 """
 import ctypes as C
 import struct
@@ -253,23 +254,53 @@ class GvrsImage:
         return len(off)
 
     def read_raster(self, master, element=0, verify=True):
-        """Decodes every tile of a one-element raster on the GPU straight from the file image: record validation and
-        payload location by g4_unpack_tile_records, decoding by g4_decode_tiles with the image as the arena.  Tiles that
-        are absent from the file come back filled with the element's fill value (RasterTile.setToNullState)."""
+        """Decodes every tile of one element of the raster on the GPU straight from the file image: the image is the arena
+        of g4_decode_tiles.  One-element rasters: record validation, checksum check and payload location by
+        g4_unpack_tile_records.  Rasters with several elements per tile: the [len][bytes] chain of every tile record is
+        walked on the host (structure only) and the record checksums are checked by g4_crc32c.  Tiles that are absent from
+        the file come back filled with the element's fill value (RasterTile.setToNullState)."""
+        from ._lib import G4_DECLINED
+
         spec = self.spec
-        if len(spec.elements) != 1 or element != 0:
-            raise NotImplementedError("batched tile I/O serves rasters with one element per tile")
-        e = spec.elements[0]
+        if not 0 <= element < len(spec.elements):
+            raise ValueError("no such element")
+        e = spec.elements[element]
         n_tiles = spec.tiles_down * spec.tiles_across
         directory = self.tile_directory()
         pos = np.zeros(n_tiles, dtype=np.uint64)
         for t, p in directory.items():
             pos[t] = p
         ctx = master._context()
-        payload_off, lens, status = unpack_tile_records(ctx, self.image, pos, checksum=verify and spec.checksum)
-        bad = np.nonzero(status < 0)[0]
-        if len(bad):
-            raise IOError("damaged tile record for tile %d" % int(bad[0]))
+        if len(spec.elements) == 1:
+            payload_off, lens, status = unpack_tile_records(ctx, self.image, pos, checksum=verify and spec.checksum)
+            bad = np.nonzero(status < 0)[0]
+            if len(bad):
+                raise IOError("damaged tile record for tile %d" % int(bad[0]))
+        else:
+            b = self.image
+            payload_off = np.zeros(n_tiles, dtype=np.uint64)
+            lens = np.zeros(n_tiles, dtype=np.uint32)
+            status = np.full(n_tiles, G4_DECLINED, dtype=np.int32)
+            rec_off, rec_len, rec_crc = [], [], []
+            for t, p in directory.items():
+                size, type_code = struct.unpack_from("<iB", b, p - 8)
+                if type_code != RECORD_TILE or size < 24 or (size & 7) or p - 8 + size > len(b):
+                    raise IOError("damaged tile record for tile %d" % t)
+                q = p + 4
+                for k in range(len(spec.elements)):
+                    ln = struct.unpack_from("<i", b, q)[0]
+                    if ln < 0 or q + 4 + ln > p - 8 + size - 4:
+                        raise IOError("damaged tile record for tile %d" % t)
+                    if k == element:
+                        payload_off[t], lens[t], status[t] = q + 4, ln, 0
+                    q += 4 + ln
+                rec_off.append(p - 8)
+                rec_len.append(size - 4)
+                rec_crc.append(struct.unpack_from("<I", b, p - 8 + size - 4)[0])
+            if verify and spec.checksum and rec_off:
+                crc = crc32c_ranges(ctx, b, rec_off, rec_len)
+                if np.any(crc != np.array(rec_crc, dtype=np.uint32)):
+                    raise IOError("Checksum mismatch in a tile record")
         dtype = {ELEM_INTEGER: np.int32, ELEM_INT_CODED_FLOAT: np.int32, ELEM_FLOAT: np.float32, ELEM_SHORT: np.int16}[e.type_code]
         return master.decodeImageTiles(self.image, payload_off, lens, status, spec.tiles_down, spec.tiles_across, spec.tile_rows,
                                        spec.tile_cols, dtype, e.fill_value)

@@ -73,7 +73,7 @@ ORACLE_IDS = {"GvrsHuffman": 0, "GvrsDeflate": 1, "GvrsFloat": 2, "GvrsCanonical
 
 
 def test_gpu_decodes_reference_files_straight_from_the_image(g4, oracle):
-    """Every one-element sample file: tile records located and checked on the GPU, tiles decoded with the image as the
+    """Every sample file, every element: tile records located and checked on the GPU, tiles decoded with the image as the
     arena; compared with the oracle's decode of the same payloads (raw tiles: the little-endian samples themselves)."""
     from gridfour_b200 import gvrs
 
@@ -81,24 +81,24 @@ def test_gpu_decodes_reference_files_straight_from_the_image(g4, oracle):
     for name, image in sample_files().items():
         img = gvrs.GvrsImage.parse(image)
         s = img.spec
-        if len(s.elements) != 1:
-            continue
-        e = s.elements[0]
         master = _master_for(g4, s.codecs)
-        got = img.read_raster(master)
-        assert got.shape == (s.tiles_down * s.tile_rows, s.tiles_across * s.tile_cols)
         ids = [ORACLE_IDS[c] for c in s.codecs]
         n = s.tile_rows * s.tile_cols
         directory = img.tile_directory()
-        for t in range(s.tiles_down * s.tiles_across):
+        for k, e in enumerate(s.elements):
+          got = img.read_raster(master, element=k)
+          assert got.shape == (s.tiles_down * s.tile_rows, s.tiles_across * s.tile_cols)
+          for t in range(s.tiles_down * s.tiles_across):
             tr, tc = divmod(t, s.tiles_across)
             tile = got[tr * s.tile_rows:(tr + 1) * s.tile_rows, tc * s.tile_cols:(tc + 1) * s.tile_cols]
             if t not in directory:
                 want = np.full((s.tile_rows, s.tile_cols), e.fill_value, dtype=tile.dtype)
             else:
-                pos = directory[t]
-                ln = struct.unpack_from("<i", image, pos + 4)[0]
-                payload = image[pos + 8:pos + 8 + ln]
+                pos = directory[t] + 4
+                for _ in range(k):
+                    pos += 4 + struct.unpack_from("<i", image, pos)[0]
+                ln = struct.unpack_from("<i", image, pos)[0]
+                payload = image[pos + 4:pos + 4 + ln]
                 if ln == e.standard_size(n):
                     want = np.frombuffer(payload[:n * tile.dtype.itemsize], dtype=tile.dtype).reshape(s.tile_rows, s.tile_cols)
                 elif e.type_code == gvrs.ELEM_FLOAT:
@@ -109,7 +109,7 @@ def test_gpu_decodes_reference_files_straight_from_the_image(g4, oracle):
                         want = want.astype(np.int16)
             assert np.array_equal(tile.view(np.uint8), np.ascontiguousarray(want).view(np.uint8)), (name, t)
         n_files += 1
-    assert n_files >= 12
+    assert n_files == 17
 
 
 def test_gpu_written_file_round_trip(g4, oracle):
