@@ -253,8 +253,9 @@ class GvrsImage:
             raise IOError("Checksum mismatch in record at file position %d" % int(off[bad[0]]))
         return len(off)
 
-    def read_raster(self, master, element=0, verify=True):
-        """Decodes every tile of one element of the raster on the GPU straight from the file image: the image is the arena
+    def read_raster(self, master, element=0, verify=True, crop=False):
+        """crop=True returns the n_rows x n_cols raster without the fill-valued margin of the edge tiles.
+        Decodes every tile of one element of the raster on the GPU straight from the file image: the image is the arena
         of g4_decode_tiles.  One-element rasters: record validation, checksum check and payload location by
         g4_unpack_tile_records.  Rasters with several elements per tile: the [len][bytes] chain of every tile record is
         walked on the host (structure only) and the record checksums are checked by g4_crc32c.  Tiles that are absent from
@@ -302,8 +303,9 @@ class GvrsImage:
                 if np.any(crc != np.array(rec_crc, dtype=np.uint32)):
                     raise IOError("Checksum mismatch in a tile record")
         dtype = {ELEM_INTEGER: np.int32, ELEM_INT_CODED_FLOAT: np.int32, ELEM_FLOAT: np.float32, ELEM_SHORT: np.int16}[e.type_code]
-        return master.decodeImageTiles(self.image, payload_off, lens, status, spec.tiles_down, spec.tiles_across, spec.tile_rows,
+        grid = master.decodeImageTiles(self.image, payload_off, lens, status, spec.tiles_down, spec.tiles_across, spec.tile_rows,
                                        spec.tile_cols, dtype, e.fill_value)
+        return grid[:spec.n_rows, :spec.n_cols] if crop else grid
 
 
 # ---- GPU-backed primitives -------------------------------------------------------------------------------------------
@@ -501,6 +503,22 @@ class GvrsWriter:
         for t, p in zip(idx, pos):
             self.tile_positions[int(t)] = int(p)
         return pos
+
+    def add_raster(self, master, grid):
+        """A whole one-element raster (numpy, n_rows x n_cols): the cells of the edge tiles that lie outside the raster hold
+        the element's fill value, as a RasterTile that was never written there does (TileElementInt/Float/Short
+        constructors fill the tile); encodeTiles on the GPU, then the tile records.  Returns the TileBatch."""
+        spec = self.spec
+        if len(spec.elements) != 1 or grid.shape != (spec.n_rows, spec.n_cols):
+            raise ValueError("add_raster: a one-element raster of the specified dimensions")
+        e = spec.elements[0]
+        dtype = {ELEM_INTEGER: np.int32, ELEM_INT_CODED_FLOAT: np.int32, ELEM_FLOAT: np.float32, ELEM_SHORT: np.int16}[e.type_code]
+        full = np.full((spec.tiles_down * spec.tile_rows, spec.tiles_across * spec.tile_cols), e.fill_value, dtype=dtype)
+        full[:spec.n_rows, :spec.n_cols] = grid
+        batch = master.encodeTiles(full, spec.tile_rows, spec.tile_cols,
+                                   fillValue=e.fill_value if e.type_code == ELEM_SHORT else None)
+        self.add_tile_records(master._context(), batch.arena, batch.offsets, batch.lens)
+        return batch
 
     def add_tile_record_host(self, tile_index, element_payloads, size=None):
         """One tile record with any number of elements: [tileIndex] then [len][bytes] per element (multi-element files)."""

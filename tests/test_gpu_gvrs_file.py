@@ -174,3 +174,41 @@ def test_gpu_record_errors_are_reported_per_tile(g4):
         assert int(st[0]) == -2
     _, _, st = gvrs.unpack_tile_records(ctx, bytes(image), np.array([0, 3, 1 << 40], dtype=np.uint64), True)
     assert [int(x) for x in st] == [1, -2, -2]
+
+
+def test_partial_edge_tiles_round_trip(g4, oracle):
+    """A raster whose dimensions are not multiples of the tile size: the edge tiles are full tiles whose outside cells
+    hold the fill value (here the integer null code, so the edge tiles go through the nulls predictor); every packing is
+    the oracle's, and the cropped read is the input."""
+    from gridfour_b200 import gvrs
+
+    INT_NULL = -2147483648
+    codecs = ["GvrsHuffman", "GvrsDeflate", "LSOP12"]
+    master = _master_for(g4, codecs)
+    ids = [ORACLE_IDS[c] for c in codecs]
+    for fill in (INT_NULL, -9999):
+        grid = oracle.terrain_i32(100, 200, 500, 700)
+        spec = gvrs.GvrsSpec(500, 700, 90, 120, [gvrs.ElementSpec.integer("z", fill_value=fill)], codecs, checksum=True)
+        assert (spec.tiles_down, spec.tiles_across) == (6, 6)
+        w = gvrs.GvrsWriter(spec, uuid=bytes(16), time_modified=1)
+        batch = w.add_raster(master, grid)
+        image = w.finish(master._context())
+        full = np.full((540, 720), fill, dtype=np.int32)
+        full[:500, :700] = grid
+        n_null_pred = 0
+        for t in range(36):
+            tr, tc = divmod(t, 6)
+            tile = np.ascontiguousarray(full[tr * 90:(tr + 1) * 90, tc * 120:(tc + 1) * 120])
+            want = oracle.master_encode_i32(ids, tile)
+            got = batch.payload(t)
+            if not want:                       # nothing compressed: the raw tile
+                assert len(got) == 4 * 90 * 120 and np.array_equal(np.frombuffer(got, np.int32), tile.ravel()), t
+            else:
+                assert got == want, t
+                n_null_pred += got[1] == 4
+        if fill == INT_NULL:
+            assert n_null_pred >= 11          # the 11 edge tiles can only be predicted by the nulls model
+        img = gvrs.GvrsImage.parse(image)
+        assert img.verify_checksums(master._context()) == len(img.records) + 1
+        assert np.array_equal(img.read_raster(master, crop=True), grid)
+        assert np.array_equal(img.read_raster(master), full)
