@@ -266,6 +266,9 @@ __device__ inline bool huff_fast_decode_stream(HuffFastShared& S, uint32_t start
     S.cnt[i] = uint16_t(c);
     S.startv[i] = i > 0 ? 0xffffffffu : T0;
   }
+  // Chaotic relaxation on purpose: a thread may read vend[i-1] in the same pass in which its owner rewrites it (racecheck
+  // reports this read/write pair).  Either value is a 32-bit end position that was valid at some point, the writer raises
+  // `changed`, and the loop only ends after a pass in which nobody wrote -- every read of that pass saw final values.
   volatile uint32_t* vend = S.endpos;
   for (int pass = 0; pass <= nSub; pass++) {
     __syncthreads();
