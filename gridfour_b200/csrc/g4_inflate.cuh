@@ -175,6 +175,7 @@ __device__ inline int inflate_warp(InflateWarpShared& S, const uint8_t* in, uint
       __syncwarp();
       pos = __shfl_sync(0xffffffffu, pos, 0);
       if (!S.ok) { status = kInfDataError; break; }
+      __syncwarp();  // every lane has read S.ok before lane 0 rewrites it below
     }
     if (lane == 0) {
       int ok = canon_build_tables(S.lens, 288, S.litFirst, S.litCount, S.litOffset, S.litSorted) ? 1 : 0;
