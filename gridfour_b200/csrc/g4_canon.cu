@@ -154,13 +154,14 @@ __global__ void __launch_bounds__(kThreads) canon_encode_kernel(EncodeArgs a) {
     bool bug = false;
     for (int p = firstPred; p < lastPred; p++) {
       PredResidualGet get{t, p + 1, seedNulls};
-      if (!canon_histogram(S.E, get, nRes)) { bug = true; break; }
+      const bool clean = canon_histogram(S.E, get, nRes);
       canon_build_code(S.E, pm);
+      if (!clean && !canon_reconcile_escapes(S.E, get, nRes)) { bug = true; break; }
       built = p;
       unsigned long long bytes = 6ull + (S.E.totalBits + 7ull) / 8ull;
       if (bytes < best) { best = bytes; win = p; }
     }
-    if (bug) {  // reference escape-range inconsistency (see g4_canon_enc.cuh): decline
+    if (bug) {  // reference escape-range inconsistency with no code for the written symbol (see g4_canon_enc.cuh): decline
       if (tid == 0) { a.lens[tIdx] = 0; a.preds[tIdx] = 0; a.status[tIdx] = G4_DECLINED; }
       continue;
     }

@@ -50,9 +50,16 @@ __device__ __forceinline__ int canon_classify(int32_t s, int* nEsc2, int* nEsc8)
   return (s >> 24) + 128;
 }
 // The reference's encode() tests -8333608 where countSymbols() tests -8388608 (CanonicalHuffman.java:258 vs
-// :395): values in [-8388608, -8333609] are counted as 16-bit escapes but written as 24-bit escapes with a
-// symbol that may have no code.  Such a tile cannot be encoded consistently; the GPU path declines it.
+// :395): values in [-8388608, -8333609] are COUNTED as 16-bit escapes (symbol (s>>16)+128, two byte escapes) but WRITTEN
+// as 24-bit escapes (symbol (s>>24)+128 = 127, three byte escapes).  The text still decodes as long as symbol 127 has a
+// code (it is the symbol of the value -1), so the GPU path does the same: the histogram follows countSymbols, the text
+// pass follows encode (canon_classify_emit), and canon_reconcile_escapes puts the size right and declines the stream
+// when symbol 127 has no code (the reference would write a text that cannot be decoded).
 __device__ __forceinline__ bool canon_value_hits_reference_bug(int32_t s) { return s >= -8388608 && s <= -8333609; }
+__device__ __forceinline__ int canon_classify_emit(int32_t s, int* nEsc2, int* nEsc8) {
+  if (canon_value_hits_reference_bug(s)) { *nEsc2 = 0; *nEsc8 = 3; return (s >> 24) + 128; }
+  return canon_classify(s, nEsc2, nEsc8);
+}
 
 // ---- serial pieces (one thread) ----------------------------------------------------------------------
 // Huffman code lengths for the symbols listed in order[0..k) (ascending keys).  TreeBuilder.java:132-178.
@@ -272,6 +279,24 @@ __device__ inline bool canon_histogram(CanonEncShared& S, Get get, uint32_t N) {
   return __syncthreads_or(bug ? 1 : 0) == 0;
 }
 
+// For a stream whose histogram pass returned false (values in the inconsistent escape range), after canon_build_code:
+// S.totalBits becomes what the text pass will write.  Returns false when the stream cannot be written.  All threads call.
+template <class Get>
+__device__ inline bool canon_reconcile_escapes(CanonEncShared& S, Get get, uint32_t N) {
+  long long delta = 0;
+  bool dead = false;
+  for (uint32_t k = threadIdx.x; k < N; k += kThreads) {
+    const int32_t v = get(k);
+    if (!canon_value_hits_reference_bug(v)) continue;
+    int e2, e8;
+    const int counted = canon_classify(v, &e2, &e8), written = (v >> 24) + 128;
+    if (S.len[written] == 0) dead = true;
+    delta += (int(S.len[written]) + 3 * (int(S.len[kSymEsc8]) + 8)) - (int(S.len[counted]) + 2 * (int(S.len[kSymEsc8]) + 8));
+  }
+  if (delta) atomicAdd(&S.totalBits, (unsigned long long)delta);
+  return __syncthreads_or(dead ? 1 : 0) == 0;
+}
+
 // Writes tables + text + end-of-text for a stream whose code has been built in S.  All threads call.
 template <class Get>
 __device__ inline void canon_emit_stream(CanonEncShared& S, BitWindow& W, BitOut& o, Get get, uint32_t N) {
@@ -308,7 +333,7 @@ __device__ inline void canon_emit_stream(CanonEncShared& S, BitWindow& W, BitOut
       if (k < N) {
         v[j] = get(k);
         int e2, e8;
-        int sym = canon_classify(v[j], &e2, &e8);
+        int sym = canon_classify_emit(v[j], &e2, &e8);
         myBits += S.len[sym] + e2 * (S.len[kSymEsc2] + 2) + e8 * (S.len[kSymEsc8] + 8);
         nv = j + 1;
       }
@@ -323,7 +348,7 @@ __device__ inline void canon_emit_stream(CanonEncShared& S, BitWindow& W, BitOut
       if (j < nv) {
         int32_t s = v[j];
         int e2, e8;
-        int sym = canon_classify(s, &e2, &e8);
+        int sym = canon_classify_emit(s, &e2, &e8);
         tb.put(S.rcode[sym], S.len[sym]);
         for (int q = e2 - 1; q >= 0; q--) { tb.put(S.rcode[kSymEsc2], S.len[kSymEsc2]); tb.put((uint32_t(s) >> (2 * q)) & 3u, 2); }
         for (int q = e8 - 1; q >= 0; q--) { tb.put(S.rcode[kSymEsc8], S.len[kSymEsc8]); tb.put((uint32_t(s) >> (8 * q)) & 0xffu, 8); }

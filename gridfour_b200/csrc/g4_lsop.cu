@@ -1084,6 +1084,7 @@ __global__ void __launch_bounds__(kThreads) lsop_encode_kernel(EncodeArgs a) {
   extern __shared__ __align__(16) unsigned char smemRaw[];
   LsopEncShared& S = *reinterpret_cast<LsopEncShared*>(smemRaw);
   __shared__ int sTile;
+  __shared__ uint32_t sMaxAbs;
   const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
   const int nTiles = a.band.tiles_down * a.band.tiles_across;
   uint8_t* pm = a.scratch + size_t(blockIdx.x) * a.scratchStride;
@@ -1106,6 +1107,20 @@ __global__ void __launch_bounds__(kThreads) lsop_encode_kernel(EncodeArgs a) {
       const int role = warp & 3, group = warp >> 2;
       const int w = C - 4;
       const int nInterior = (R - 2) * w;
+      // largest sample magnitude of the tile: decides below whether the partitioned sums are exact
+      if (tid == 0) sMaxAbs = 0u;
+      __syncthreads();
+      {
+        uint32_t mx = 0u;
+        for (int m = tid; m < R * C; m += kThreads) {
+          const int rr = m / C;
+          const int32_t v = t.row(rr)[m - rr * C];
+          const uint32_t av = v < 0 ? 0u - uint32_t(v) : uint32_t(v);
+          mx = mx > av ? mx : av;
+        }
+        mx = __reduce_max_sync(0xffffffffu, mx);
+        if (lane == 0) atomicMax(&sMaxAbs, mx);
+      }
       double acc[kMomentPerRole];
 #pragma unroll
       for (int i = 0; i < kMomentPerRole; i++) acc[i] = 0.0;
@@ -1135,6 +1150,23 @@ __global__ void __launch_bounds__(kThreads) lsop_encode_kernel(EncodeArgs a) {
       }
       __syncthreads();
       if (tid < kMomentQuantities) S.sums[tid] = S.part[tid & 3][tid >> 2] + S.part[(tid & 3) + 4][tid >> 2];
+      // The partition above adds in another order than the reference's single loop.  That is the same number as long as
+      // every partial sum is an exactly representable integer: nInterior * max|z|^2 < 2^53 (terrain: about 2^42).
+      // Otherwise (full-range samples) each quantity is re-accumulated by one thread in the reference's cell order.
+      const double mag = double(sMaxAbs);
+      if (!(double(nInterior) * mag * mag < 9007199254740992.0) && tid < kMomentQuantities) {
+        const int dr[13] = {0, 0, -1, -1, -1, -1, 0, -1, -2, -2, -2, -2, -2};
+        const int dc[13] = {0, -1, -1, 0, 1, 2, -2, -2, -2, -1, 0, 1, 2};
+        const int qi = tid < 13 ? tid : moment_i(tid), qj = tid < 13 ? -1 : moment_j(tid);
+        double accq = 0.0;
+        for (int r = 2; r < R; r++) {
+          const int32_t* ri = t.row(r + dr[qi]) + dc[qi];
+          const int32_t* rj = qj >= 0 ? t.row(r + dr[qj]) + dc[qj] : ri;
+          if (qj < 0) for (int c = 2; c < C - 2; c++) accq += double(ri[c]);
+          else for (int c = 2; c < C - 2; c++) accq += double(ri[c]) * double(rj[c]);
+        }
+        S.sums[tid] = accq;
+      }
       __syncthreads();
     }
     if (tid == 0) {
@@ -1181,15 +1213,15 @@ __global__ void __launch_bounds__(kThreads) lsop_encode_kernel(EncodeArgs a) {
     LsInitGet g1{t};
     LsInteriorGet g2{t, S.u};
     bool bad = false;
-    if (!canon_histogram(S.E, g1, nInit)) bad = true;
+    bool clean = canon_histogram(S.E, g1, nInit);
+    canon_build_code(S.E, pm);
+    if (!clean && !canon_reconcile_escapes(S.E, g1, nInit)) bad = true;  // see g4_canon_enc.cuh
     else {
-      canon_build_code(S.E, pm);
       canon_emit_stream(S.E, S.W, o, g1, nInit);
-      if (!canon_histogram(S.E, g2, nInterior)) bad = true;
-      else {
-        canon_build_code(S.E, pm);
-        canon_emit_stream(S.E, S.W, o, g2, nInterior);
-      }
+      clean = canon_histogram(S.E, g2, nInterior);
+      canon_build_code(S.E, pm);
+      if (!clean && !canon_reconcile_escapes(S.E, g2, nInterior)) bad = true;
+      else canon_emit_stream(S.E, S.W, o, g2, nInterior);
     }
     if (bad) {
       if (tid == 0) { a.lens[tIdx] = 0; a.preds[tIdx] = 0; a.status[tIdx] = G4_DECLINED; }

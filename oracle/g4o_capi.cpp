@@ -99,6 +99,9 @@ uint32_t g4o_crc32c(const uint8_t* p, long n) { return crc32c(p, size_t(n)); }
 
 // returns packing length, -1 when the codec declines (Java null), -2 cap too small, -3 exception
 long g4o_codec_encode_i32(int codec, int codecIndex, int nr, int nc, const int32_t* v, uint8_t* out, long cap, int* predictor) {
+  // the reference's Linear predictor reads columns 0 and 1 of every row (PredictorModelLinear.java:120-150): one-column
+  // tiles are outside its domain (ArrayIndexOutOfBoundsException there), refused here
+  if (nr < 1 || nc < 2) return -3;
   G4O_TRY
   std::vector<uint8_t> p;
   EncodeInfo info;
@@ -118,6 +121,7 @@ long g4o_codec_encode_i32(int codec, int codecIndex, int nr, int nc, const int32
   G4O_CATCH(-3)
 }
 long g4o_lsop12_encode_opts(int codecIndex, int nr, int nc, const int32_t* v, uint8_t* out, long cap, int deflateEnabled, int checksum) {
+  if (nr < 1 || nc < 2) return -3;
   G4O_TRY
   std::vector<uint8_t> p;
   if (!codec_lsop12_encode(codecIndex, nr, nc, v, p, deflateEnabled != 0, checksum != 0, nullptr)) return -1;
@@ -151,6 +155,7 @@ int g4o_codec_decode_f32(int nr, int nc, const uint8_t* p, long len, float* out)
   G4O_TRY codec_float_decode(nr, nc, p, size_t(len), out); return 0; G4O_CATCH(-1)
 }
 long g4o_master_encode_i32(const int* ids, int nIds, int nr, int nc, const int32_t* v, uint8_t* out, long cap) {
+  if (nr < 1 || nc < 2) return -3;
   G4O_TRY
   std::vector<uint8_t> p;
   master_encode_i32(ids, nIds, nr, nc, v, p);
