@@ -201,10 +201,8 @@ def test_partial_edge_tiles_round_trip(g4, oracle):
             tile = np.ascontiguousarray(full[tr * 90:(tr + 1) * 90, tc * 120:(tc + 1) * 120])
             want = oracle.master_encode_i32(ids, tile)
             got = batch.payload(t)
-            if not want:                       # nothing compressed: the raw tile
-                assert len(got) == 4 * 90 * 120 and np.array_equal(np.frombuffer(got, np.int32), tile.ravel()), t
-            else:
-                assert got == want, t
+            assert got == want, t              # (the oracle returns the raw tile when nothing compresses)
+            if len(got) < 4 * 90 * 120:
                 n_null_pred += got[1] == 4
         if fill == INT_NULL:
             assert n_null_pred >= 11          # the 11 edge tiles can only be predicted by the nulls model
