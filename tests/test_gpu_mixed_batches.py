@@ -78,3 +78,96 @@ def test_mixed_batches_match_oracle_selection(g4, oracle, shape):
             tag = "%s tile %d (%s) codecs %s" % (shape, t, kind, names)
             assert got == want, tag + ": " + first_diff(got, want)      # the oracle returns the raw tile when nothing wins
         assert np.array_equal(master.decodeTiles(batch), grid), "%s %s" % (shape, names)
+
+
+def _ftile(oracle, rng, kind, r, c, k):
+    t = oracle.terrain_f32(50 * k, 31 * k, r, c).copy()
+    if kind == "terrain":
+        return t
+    if kind == "constant":
+        return np.full((r, c), 2.5, np.float32)
+    if kind == "nan_fill":
+        return np.full((r, c), np.nan, np.float32)
+    if kind == "noise":
+        return rng.standard_normal((r, c)).astype(np.float32)
+    if kind == "bits":
+        return rng.integers(0, 2 ** 32, (r, c), dtype=np.uint64).astype(np.uint32).view(np.float32)   # every bit pattern
+    if kind == "specials":
+        return rng.choice(np.array([0.0, -0.0, np.inf, -np.inf, np.nan, 1e-45, -1e-40, 3.4e38], np.float32), (r, c))
+    if kind == "nan_void":
+        t[r // 4:r // 2, c // 4:c // 2] = np.nan
+        return t
+    raise AssertionError(kind)
+
+
+FKINDS = ["terrain", "constant", "nan_fill", "noise", "bits", "specials", "nan_void"]
+
+
+@pytest.mark.parametrize("shape", [(8, 8), (17, 23), (60, 60), (90, 120)])
+def test_mixed_float_batches_match_oracle_selection(g4, oracle, shape):
+    r, c = shape
+    rng = np.random.default_rng(2000 + r)
+    td, ta = 2, 7
+    kinds = [FKINDS[i % len(FKINDS)] for i in rng.permutation(td * ta)]
+    grid = np.zeros((td * r, ta * c), np.float32)
+    for t, kind in enumerate(kinds):
+        tr, tc = divmod(t, ta)
+        grid[tr * r:(tr + 1) * r, tc * c:(tc + 1) * c] = _ftile(oracle, rng, kind, r, c, t)
+    for names, ids in ((["GvrsFloat"], [2]), (["GvrsHuffman", "GvrsFloat", "LSOP12"], [0, 2, 4])):
+        spec = g4.CodecSpecification(default=False)
+        for nme in names:
+            cls = {"GvrsFloat": ("CodecFloat", "CodecFloat")}.get(nme) or STD[nme][:2]
+            spec.addCompressionCodec(nme, getattr(g4, cls[0]), getattr(g4, cls[1]))
+        master = g4.CodecMaster(spec)
+        batch = master.encodeTiles(grid, r, c)
+        for t, kind in enumerate(kinds):
+            tr, tc = divmod(t, ta)
+            tile = np.ascontiguousarray(grid[tr * r:(tr + 1) * r, tc * c:(tc + 1) * c])
+            want = oracle.master_encode_f32(ids, tile)
+            got = batch.payload(t)
+            assert got == want, "%s tile %d (%s) codecs %s: %s" % (shape, t, kind, names, first_diff(got, want))
+        out = master.decodeTiles(batch)
+        assert np.array_equal(out.view(np.uint32), grid.view(np.uint32)), "%s %s" % (shape, names)
+
+
+def test_mixed_short_batches(g4, oracle):
+    """Short elements: the fill value is coded as null, every other 16-bit value (extremes included) survives; the fill
+    value itself comes back the way the reference gives it back."""
+    rng = np.random.default_rng(31)
+    r, c, td, ta = 30, 40, 3, 4
+    for fill in (-32768, 0, 32767, -9999):
+        grid = np.zeros((td * r, ta * c), np.int16)
+        for t in range(td * ta):
+            tr, tc = divmod(t, ta)
+            kind = t % 6
+            if kind == 0:
+                tile = (oracle.terrain_i32(7 * t, 3 * t, r, c) % 30000).astype(np.int16)
+            elif kind == 1:
+                tile = rng.integers(-32768, 32768, (r, c)).astype(np.int16)
+            elif kind == 2:
+                tile = np.full((r, c), fill, np.int16)
+            elif kind == 3:
+                tile = np.full((r, c), 1234, np.int16)
+            elif kind == 4:
+                tile = rng.integers(-3, 4, (r, c)).astype(np.int16)
+                tile[rng.random((r, c)) < 0.1] = fill
+            else:
+                tile = rng.choice(np.array([-32768, -32767, -1, 0, 1, 32766, 32767], np.int16), (r, c))
+            grid[tr * r:(tr + 1) * r, tc * c:(tc + 1) * c] = tile
+        master = g4.CodecMaster()
+        batch = master.encodeTiles(grid, r, c, fillValue=fill)
+        out = master.decodeTiles(batch)
+        assert out.dtype == np.int16
+        # TileElementShort.decode (gvrs/TileElementShort.java:232-247): a compressed tile gives the null code back as
+        # SHORT_NULL_CODE (-32768) whatever the element's fill value is; a raw tile gives the stored shorts back.
+        want = grid.copy()
+        n_raw = 0
+        for t in range(td * ta):
+            tr, tc = divmod(t, ta)
+            if int(batch.lens[t]) == (2 * r * c + 3) // 4 * 4:
+                n_raw += 1
+                continue
+            w = want[tr * r:(tr + 1) * r, tc * c:(tc + 1) * c]
+            w[w == fill] = -32768
+        assert 0 < n_raw < td * ta
+        assert np.array_equal(out, want), fill
