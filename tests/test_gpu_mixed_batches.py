@@ -171,3 +171,34 @@ def test_mixed_short_batches(g4, oracle):
             w[w == fill] = -32768
         assert 0 < n_raw < td * ta
         assert np.array_equal(out, want), fill
+
+
+@pytest.mark.parametrize("shape,tiles", [((90, 121), (3, 3)), ((45, 62), (4, 5)), ((180, 243), (2, 3)), ((127, 509), (2, 2)),
+                                          ((512, 512), (1, 2)), ((1024, 1024), (1, 1)), ((1000, 1047), (1, 1))])
+def test_unaligned_and_large_tiles(g4, oracle, shape, tiles):
+    """Tile widths that are not multiples of four (tiles start at unaligned addresses: the run sinks and the deferred LSOP
+    path instead of the packed 16-byte stores) and tiles up to the library's limit of 2^20 samples (staging larger than
+    the default shared-memory carve-out): packings are the oracle's, batches decode to the input."""
+    r, c = shape
+    td, ta = tiles
+    grid = oracle.terrain_i32(321, 123, td * r, ta * c, n_threads=8)
+    names = ["GvrsHuffman", "GvrsDeflate", "LSOP12"]
+    spec = g4.CodecSpecification(default=False)
+    for nme in names:
+        spec.addCompressionCodec(nme, getattr(g4, STD[nme][0]), getattr(g4, STD[nme][1]))
+    ids = [STD[nme][2] for nme in names]
+    master = g4.CodecMaster(spec)
+    batch = master.encodeTiles(grid, r, c)
+    for t in range(td * ta):
+        tr, tc = divmod(t, ta)
+        tile = np.ascontiguousarray(grid[tr * r:(tr + 1) * r, tc * c:(tc + 1) * c])
+        want = oracle.master_encode_i32(ids, tile)
+        got = batch.payload(t)
+        assert got == want, "%s tile %d: %s" % (shape, t, first_diff(got, want))
+    assert np.array_equal(master.decodeTiles(batch), grid)
+    # every codec on its own, so that the ones that lose the selection are decoded too
+    for nme in names:
+        s1 = g4.CodecSpecification(default=False)
+        s1.addCompressionCodec(nme, getattr(g4, STD[nme][0]), getattr(g4, STD[nme][1]))
+        m1 = g4.CodecMaster(s1)
+        assert np.array_equal(m1.decodeTiles(m1.encodeTiles(grid, r, c)), grid), nme
