@@ -903,6 +903,10 @@ int g4_decode_tiles(g4_context* ctx, const g4_codec_list* codecs, const g4_band_
       if (end > arenaBytes) arenaBytes = end;
     }
     const size_t gridBytes = band_samples(*band) * elem_bytes(*band);
+    const size_t rowBytes = size_t(band->grid_pitch) * elem_bytes(*band);
+    const size_t bandRowBytes = size_t(band->tiles_across) * band->tile_cols * elem_bytes(*band);
+    const size_t bandRows = size_t(band->tiles_down) * band->tile_rows;
+    const bool pitched = rowBytes != bandRowBytes;
     CK(ctx->sGrid.ensure(gridBytes));
     CK(ctx->sArena.ensure(arenaBytes + 16));
     CK(ctx->sOffsets.ensure(size_t(nTiles) * 8));
@@ -930,12 +934,14 @@ int g4_decode_tiles(g4_context* ctx, const g4_codec_list* codecs, const g4_band_
       rc = decode_device(ctx, codecs, band, ctx->sArena.as<uint8_t>(), ctx->sOffsets.as<uint64_t>(), ctx->sLens.as<uint32_t>(),
                          ctx->sGrid.p, ctx->sStatus.as<int32_t>());
       if (rc != G4_OK) return rc;
-      CK(cudaMemcpyAsync(grid, ctx->sGrid.p, gridBytes, cudaMemcpyDeviceToHost, ctx->stream));
+      if (pitched)  // a band inside a wider host raster: only the band's columns go back
+        CK(cudaMemcpy2DAsync(grid, rowBytes, ctx->sGrid.p, rowBytes, bandRowBytes, bandRows, cudaMemcpyDeviceToHost, ctx->stream));
+      else
+        CK(cudaMemcpyAsync(grid, ctx->sGrid.p, gridBytes, cudaMemcpyDeviceToHost, ctx->stream));
     } else {
       CK(cudaEventRecord(ctx->evStart, ctx->stream));
       CK(cudaStreamWaitEvent(ctx->copyIn, ctx->evStart, 0));   // the staging buffers may still be in use by an earlier call
       CK(cudaStreamWaitEvent(ctx->copyOut, ctx->evStart, 0));
-      const size_t rowBytes = size_t(band->grid_pitch) * elem_bytes(*band);
       for (int k = 0; k < nChunks; k++) {
         const int r0 = int(int64_t(band->tiles_down) * k / nChunks), r1 = int(int64_t(band->tiles_down) * (k + 1) / nChunks);
         const int t0 = r0 * band->tiles_across, t1 = r1 * band->tiles_across;
@@ -953,8 +959,9 @@ int g4_decode_tiles(g4_context* ctx, const g4_codec_list* codecs, const g4_band_
         CK(cudaStreamWaitEvent(ctx->copyOut, ctx->evDone[k], 0));
         const size_t rows = size_t(r1 - r0) * band->tile_rows;
         const size_t bytes = k == nChunks - 1 ? gridBytes - size_t(r0) * band->tile_rows * rowBytes : rows * rowBytes;
-        CK(cudaMemcpyAsync(static_cast<uint8_t*>(grid) + size_t(r0) * band->tile_rows * rowBytes, gdev, bytes, cudaMemcpyDeviceToHost,
-                           ctx->copyOut));
+        uint8_t* ghost = static_cast<uint8_t*>(grid) + size_t(r0) * band->tile_rows * rowBytes;
+        if (pitched) CK(cudaMemcpy2DAsync(ghost, rowBytes, gdev, rowBytes, bandRowBytes, rows, cudaMemcpyDeviceToHost, ctx->copyOut));
+        else CK(cudaMemcpyAsync(ghost, gdev, bytes, cudaMemcpyDeviceToHost, ctx->copyOut));
       }
       CK(cudaEventRecord(ctx->evIn[0], ctx->copyOut));
       CK(cudaStreamWaitEvent(ctx->stream, ctx->evIn[0], 0));  // the call's stream completes only after the last D2H

@@ -202,3 +202,73 @@ def test_unaligned_and_large_tiles(g4, oracle, shape, tiles):
         s1.addCompressionCodec(nme, getattr(g4, STD[nme][0]), getattr(g4, STD[nme][1]))
         m1 = g4.CodecMaster(s1)
         assert np.array_equal(m1.decodeTiles(m1.encodeTiles(grid, r, c)), grid), nme
+
+
+@pytest.mark.parametrize("space", ["host", "device"])
+@pytest.mark.parametrize("dtype", [np.int32, np.int16, np.float32])
+def test_band_inside_a_wider_raster(g4, oracle, space, dtype):
+    """g4_band_desc.grid_pitch larger than the band's width (a band cut out of a wider raster, the way a tile-cache window
+    sits in a page): the same payloads as for the compact band, and the decode writes nothing outside the band."""
+    import ctypes as C
+
+    from gridfour_b200 import _lib
+    from gridfour_b200._lib import G4_MEM_DEVICE, G4_MEM_HOST
+
+    r, c, td, ta, pitch, col0 = 30, 44, 3, 4, 4 * 44 + 37, 5       # col0 = 5: band rows start at unaligned addresses
+    if dtype == np.float32:
+        compact = oracle.terrain_f32(10, 20, td * r, ta * c)
+    else:
+        compact = (oracle.terrain_i32(10, 20, td * r, ta * c) % 20000).astype(dtype)
+    wide = np.full((td * r, pitch), 77, dtype)
+    wide[:, col0:col0 + ta * c] = compact
+    master = g4.CodecMaster()
+    ref = master.encodeTiles(compact, r, c)
+    L = _lib.lib()
+    cl = master.spec.native_list()
+    band = master._band(compact.shape, dtype, r, c, pitch=pitch)
+    nT = td * ta
+    cap = int(L.g4_encode_arena_bound(C.byref(band)))
+    total = C.c_uint64(0)
+    item = np.dtype(dtype).itemsize
+    if space == "host":
+        arena = np.empty(cap, np.uint8)
+        offsets, lens = np.empty(nT, np.uint64), np.empty(nT, np.uint32)
+        codec, pred, status = np.empty(nT, np.uint8), np.empty(nT, np.uint8), np.empty(nT, np.int32)
+        ptr = lambda a: a.ctypes.data
+        mem, src = G4_MEM_HOST, wide
+        grid_ptr = wide.ctypes.data + col0 * item
+    else:
+        import torch
+
+        dev = torch.device("cuda:0")
+        arena = torch.empty(cap, dtype=torch.uint8, device=dev)
+        offsets, lens = torch.empty(nT, dtype=torch.int64, device=dev), torch.empty(nT, dtype=torch.int32, device=dev)
+        codec, pred = torch.empty(nT, dtype=torch.uint8, device=dev), torch.empty(nT, dtype=torch.uint8, device=dev)
+        status = torch.empty(nT, dtype=torch.int32, device=dev)
+        ptr = lambda a: a.data_ptr()
+        mem, src = G4_MEM_DEVICE, torch.from_numpy(wide).to(dev)
+        grid_ptr = src.data_ptr() + col0 * item
+    st = L.g4_encode_tiles(master._context()._h, C.byref(cl), C.byref(band), mem, grid_ptr, ptr(arena), cap, ptr(offsets), ptr(lens),
+                           ptr(codec), ptr(pred), ptr(status), C.byref(total))
+    assert st == 0
+    to_np = (lambda a: a) if space == "host" else (lambda a: a.cpu().numpy())
+    a_np, o_np, l_np = to_np(arena), to_np(offsets).astype(np.uint64), to_np(lens).astype(np.uint32)
+    for t in range(nT):
+        got = a_np[int(o_np[t]):int(o_np[t]) + int(l_np[t])].tobytes()
+        assert got == ref.payload(t), "tile %d: %s" % (t, first_diff(got, ref.payload(t)))
+    # decode into a fresh wide raster: the band is the input, everything around it keeps its marker
+    if space == "host":
+        out = np.full((td * r, pitch), 55, dtype)
+        out_ptr = out.ctypes.data + col0 * item
+    else:
+        out_t = torch.full((td * r, pitch), 55, dtype=src.dtype, device=dev)
+        out_ptr = out_t.data_ptr() + col0 * item
+    st = L.g4_decode_tiles(master._context()._h, C.byref(cl), C.byref(band), mem, ptr(arena), ptr(offsets), ptr(lens), out_ptr, ptr(status))
+    assert st == 0
+    if space == "device":
+        master._context().synchronize()
+        out = out_t.cpu().numpy()
+    assert np.array_equal(out[:, col0:col0 + ta * c].view(np.uint8), compact.view(np.uint8))
+    outside = np.ones(out.shape, bool)
+    outside[:, col0:col0 + ta * c] = False
+    assert np.all(out[outside] == 55)
