@@ -33,3 +33,27 @@ def test_host_decode_pipeline_matches_input():
         pos += (n + 7) & ~7
     b2 = g4.TileBatch(arena2, off2, batch.lens, None, None, None, pos, batch.band)
     assert np.array_equal(master.decodeTiles(b2), grid)
+
+
+def test_host_decode_pipeline_into_a_wider_raster():
+    """The chunked path with grid_pitch wider than the band: every chunk copies back only the band's columns."""
+    import ctypes as C
+
+    import gridfour_b200 as g4
+    from gridfour_b200 import _lib
+    from gridfour_b200._lib import G4_MEM_HOST
+    from oracle import g4oracle
+
+    rows, cols, tr, tc, pitch, col0 = 33 * 90, 24 * 120, 90, 120, 24 * 120 + 50, 13
+    grid = g4oracle.terrain_i32(50, 60, rows, cols, n_threads=8)
+    master = g4.CodecMaster()
+    batch = master.encodeTiles(grid, tr, tc)
+    band = master._band(grid.shape, np.int32, tr, tc, pitch=pitch)
+    out = np.full((rows, pitch), 55, np.int32)
+    status = np.empty(33 * 24, np.int32)
+    cl = master.spec.native_list()
+    st = _lib.lib().g4_decode_tiles(master._context()._h, C.byref(cl), C.byref(band), G4_MEM_HOST, batch.arena.ctypes.data,
+                                    batch.offsets.ctypes.data, batch.lens.ctypes.data, out.ctypes.data + 4 * col0, status.ctypes.data)
+    assert st == 0
+    assert np.array_equal(out[:, col0:col0 + cols], grid)
+    assert np.all(out[:, :col0] == 55) and np.all(out[:, col0 + cols:] == 55)
