@@ -81,7 +81,8 @@ typedef struct {
   int32_t elem_type; /* G4_ELEM_I32, G4_ELEM_F32 or G4_ELEM_I16 */
   int32_t tile_rows, tile_cols;
   int32_t tiles_down, tiles_across;
-  int64_t grid_pitch; /* samples per raster row (>= tiles_across*tile_cols) */
+  int64_t grid_pitch; /* samples per raster row (>= tiles_across*tile_cols); a band may sit inside a wider raster:
+                         decode writes the band's columns only, in host and in device memory */
   int32_t fill_value; /* G4_ELEM_I16 encode only: the element's fill value, coded as null */
   int32_t reserved;
 } g4_band_desc;
