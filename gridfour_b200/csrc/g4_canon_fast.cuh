@@ -20,7 +20,6 @@ namespace g4 {
 
 constexpr int kFastStageWords = 7168;  // 28 KB of packing (5.3 bits/sample for a 180x240 tile)
 constexpr int kFastMaxSub = 1280;
-constexpr int kFastRounds = kFastMaxSub / kThreads;
 #ifndef G4_FAST_SUBBITS
 #define G4_FAST_SUBBITS 160
 #endif
@@ -43,7 +42,7 @@ struct CanonFastShared {
   uint32_t startv[kFastMaxSub];       // start position endpos[i] was computed from
   uint16_t cnt[kFastMaxSub];
   uint8_t eot[kFastMaxSub];
-  uint32_t scan[kWarps + 1];
+  uint32_t scan[33];
   uint32_t textStart, endBit;
   int error, changed, firstEot;
   // staged packing, word 0 = packing bytes 0..3.  LAST member: a kernel may allocate more dynamic shared memory than
@@ -224,12 +223,13 @@ __device__ __forceinline__ void canon_fast_count(const CanonFastShared& S, uint3
 
 // Parallel construction of firstCode / count / offset / sorted from S.lens (CanonHuffTreeDecoder.java:68-129 builds
 // the equivalent tree).  Sets S.error for an over-subscribed or empty code.  All threads call.
+template <int NT = kThreads>
 __device__ inline void canon_fast_tables_cta(CanonFastShared& S) {
   __shared__ uint32_t cnt32[17];
   const int tid = threadIdx.x;
   if (tid < 17) cnt32[tid] = 0;
   __syncthreads();
-  for (int i = tid; i < kCanonSymbols; i += kThreads) {
+  for (int i = tid; i < kCanonSymbols; i += NT) {
     int l = S.lens[i];
     if (l > 15) S.error = 1;
     else if (l) atomicAdd(&cnt32[l], 1u);
@@ -251,7 +251,7 @@ __device__ inline void canon_fast_tables_cta(CanonFastShared& S) {
     if (off == 0 || S.lens[kSymEot] == 0) S.error = 1;
   }
   __syncthreads();
-  for (int i = tid; i < kCanonSymbols; i += kThreads) {
+  for (int i = tid; i < kCanonSymbols; i += NT) {
     const int l = S.lens[i];
     if (l == 0 || l > 15) continue;
     int rank = 0;
@@ -262,8 +262,9 @@ __device__ inline void canon_fast_tables_cta(CanonFastShared& S) {
 }
 
 // 11-bit lookup table: thread per prefix, canonical arithmetic on the bit-reversed prefix.  All threads call.
+template <int NT = kThreads>
 __device__ inline void canon_fast_build_lut(CanonFastShared& S) {
-  for (int e = threadIdx.x; e < (1 << kFastLutBits); e += kThreads) {
+  for (int e = threadIdx.x; e < (1 << kFastLutBits); e += NT) {
     uint32_t v = __brev(uint32_t(e));
     uint16_t entry = 0;
     for (int len = 1; len <= kFastLutBits; len++) {
@@ -279,7 +280,7 @@ __device__ inline void canon_fast_build_lut(CanonFastShared& S) {
   }
   __syncthreads();
   // multi-symbol table: the plain values whose codes lie completely inside the 11-bit window (at most 3)
-  for (int e = threadIdx.x; e < (1 << kFastLutBits); e += kThreads) {
+  for (int e = threadIdx.x; e < (1 << kFastLutBits); e += NT) {
     uint32_t used = 0, n = 0, syms = 0;
     while (n < 3) {
       const uint32_t x = S.lut[(uint32_t(e) >> used) & ((1u << kFastLutBits) - 1u)];
@@ -298,9 +299,11 @@ __device__ inline void canon_fast_build_lut(CanonFastShared& S) {
 // *endBit are absolute bit positions inside the packing, nBits = 8 * packing length.  The sink receives runs:
 // begin(firstValueIndex), put(value) ..., end().  hintBits bounds the region searched first (0 = everything).
 // All threads call.
-template <class Sink>
+template <class Sink, int NT = kThreads>
 __device__ bool canon_fast_decode_text(CanonFastShared& S, uint32_t nBits, const uint32_t T0, uint32_t maxValues, uint32_t hintBits,
                                        Sink sink, uint32_t* endBit, uint32_t* nValues) {
+  constexpr int kThreads = NT;                       // shadows the global: every loop below strides by the CTA size
+  constexpr int kFastRounds = kFastMaxSub / NT;      // sub-sequences per thread (5 with 256 threads, 2 with 512)
   const int tid = threadIdx.x;
   uint32_t regionEnd = nBits;
   if (hintBits && T0 + hintBits < regionEnd) regionEnd = T0 + hintBits;
@@ -383,7 +386,7 @@ __device__ bool canon_fast_decode_text(CanonFastShared& S, uint32_t nBits, const
       mySum += (i <= fe && i < nSub) ? S.cnt[i] : 0u;
     }
     uint32_t total;
-    uint32_t ex = block_exclusive_scan(mySum, S.scan, &total);
+    uint32_t ex = block_exclusive_scan<NT>(mySum, S.scan, &total);
     if (total > maxValues) return false;
     if (tid == 0) S.endBit = S.endpos[fe];
     __syncthreads();

@@ -44,7 +44,9 @@ __device__ __forceinline__ TileView tile_view(const g4_band_desc& b, void* grid,
 // Block-wide exclusive scan of one uint32 per thread (kThreads threads).  `sm` = kWarps+1 words.
 // Returns the exclusive prefix; *total receives the block sum.  Contains two __syncthreads().
 // ------------------------------------------------------------------------------------------------
+template <int NT = kThreads>
 __device__ __forceinline__ uint32_t block_exclusive_scan(uint32_t x, uint32_t* sm, uint32_t* total) {
+  constexpr int kWarps = NT / 32;  // sm holds NT/32 + 1 words
   const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
   uint32_t inc = x;
 #pragma unroll

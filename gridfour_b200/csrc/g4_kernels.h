@@ -145,9 +145,41 @@ cudaError_t launch_float_decode(const DecodeArgs& a, uint8_t* region, size_t reg
 // chunk counters of the text kernel); s2 / ev (5 events): second stream for the chunked overlap, or null
 // meta: nTilesUpper * lsop_meta_bytes() bytes (interior code lengths + text position handed from kernel H to kernel T)
 size_t lsop_meta_bytes();
-cudaError_t launch_lsop_decode(const DecodeArgs& a, float* coef, uint8_t* meta, int* defer, int* deferCounters, int nCtas,
-                               int nTilesUpper, cudaStream_t s, cudaStream_t s2, cudaEvent_t* ev, int* launches);
 
+
+// LSOP12 decode, fast path (g4_lsop_fast.cu): byte hand-over between the text kernel and a TMA-fed wavefront kernel.
+struct LsopFastGeom {
+  int R, C;
+  int nB;         // 4-column blocks per row (C / 4)
+  int nLanes;     // lanes of a wavefront warp in use: min(32, nB); lanes 0,1 carry the two finished rows above a group
+  int rpg;        // rows per group = nLanes - 2
+  int nGroups;
+  int laneBytes;  // one lane's residual stream in the scratch image, == 4 (mod 16)
+  int tileBytes;  // 32 * laneBytes: the image one tile writes
+  int tilePitch;  // bytes between the images of consecutive tiles: a multiple of laneBytes - 4 (tensor map stride rule)
+  int nIter;      // wavefront iterations, a multiple of 16
+  int wide;       // 256-bit raster stores
+};
+struct LsopFastArgs {
+  DecodeArgs a;
+  float* coef;        // [nTiles][12]
+  uint8_t* meta;      // [nTiles][lsop_meta_bytes()]
+  int4* side;         // [nTiles][R]: {v[r][0], v[r][1], D2[r], D1[r]}
+  uint32_t* exc;      // [nTiles][128]: residuals that are no byte
+  uint8_t* resid;     // residual scratch (lsop_fast_resid_bytes)
+  int* defer;         // tiles for the general kernels
+  int* deferCount;
+  LsopFastGeom g;
+};
+bool lsop_fast_geometry(const g4_band_desc& band, const void* grid, LsopFastGeom* out);
+size_t lsop_fast_side_bytes(const LsopFastGeom& g, int nTiles);
+size_t lsop_fast_exc_bytes(int nTiles);
+size_t lsop_fast_resid_bytes(const LsopFastGeom& g, int nTiles);
+cudaError_t launch_lsop_decode_fast(const LsopFastArgs& A, int nTilesUpper, int smCount, int* textCounter, cudaStream_t s, int* launches);
+// fast: scratch of the fast path (side / exc / resid / g filled in), or null -> the round-1 kernels only
+cudaError_t launch_lsop_decode(const DecodeArgs& a, float* coef, uint8_t* meta, int* defer, int* deferCounters, int nCtas,
+                               int nTilesUpper, cudaStream_t s, cudaStream_t s2, cudaEvent_t* ev, int* launches,
+                               const LsopFastArgs* fast = nullptr, int smCount = 148);
 
 // ---- zlib-stream encode stages (g4_deflate_encode.cu, g4_lsop.cu) ------------------------------------------------
 size_t deflate_work_bytes();
