@@ -67,27 +67,30 @@ struct SmemBitSrc {
   }
 };
 
-// 64-bit register bit buffer over S.sw; at least 32 valid bits after every skip().  The staged words are addressed
-// through the shared-memory struct itself so that the loads stay LDS with an immediate base.
+// Register bit window over S.sw: two staged words (64 bits) of which `used` < 32 are consumed, so peek() always has 32
+// valid bits.  The position is kept RELATIVE to a limit (rem = limit - position), which is what the decoding loops
+// compare against; pos(limit) recovers the absolute position.  The staged words are addressed through the
+// shared-memory struct itself so that the loads stay LDS with an immediate base.
 struct BitCursor {
-  uint32_t pos, next;
-  uint64_t buf;
-  int avail;
-  __device__ __forceinline__ void init(const CanonFastShared& S, uint32_t p) {
-    pos = p;
-    uint32_t i = p >> 5, s = p & 31;
-    buf = ((uint64_t(S.sw[i + 1]) << 32) | S.sw[i]) >> s;
-    avail = 64 - int(s);
+  uint32_t lo, hi, used, next;
+  int rem;
+  __device__ __forceinline__ void init(const CanonFastShared& S, uint32_t p, uint32_t limit) {
+    const uint32_t i = p >> 5;
+    lo = S.sw[i];
+    hi = S.sw[i + 1];
+    used = p & 31u;
     next = i + 2;
+    rem = int(limit) - int(p);
   }
-  __device__ __forceinline__ uint32_t peek() const { return uint32_t(buf); }
-  __device__ __forceinline__ void skip(const CanonFastShared& S, uint32_t n) {
-    buf >>= n;
-    avail -= int(n);
-    pos += n;
-    if (avail < 32) {
-      buf |= uint64_t(S.sw[next++]) << avail;
-      avail += 32;
+  __device__ __forceinline__ uint32_t peek() const { return __funnelshift_r(lo, hi, used); }
+  __device__ __forceinline__ uint32_t pos(uint32_t limit) const { return uint32_t(int(limit) - rem); }
+  __device__ __forceinline__ void skip(const CanonFastShared& S, uint32_t n) {  // n <= 32
+    used += n;
+    rem -= int(n);
+    if (used >= 32u) {
+      lo = hi;
+      hi = S.sw[next++];
+      used -= 32u;
     }
   }
 };
@@ -182,12 +185,11 @@ __device__ __forceinline__ int canon_fast_rare_symbol(const CanonFastShared& S, 
 __device__ __forceinline__ void canon_fast_count(const CanonFastShared& S, uint32_t nBits, uint32_t start, uint32_t limit,
                                                  uint32_t* endOut, uint32_t* cntOut, int* flagOut) {
   BitCursor cur;
-  cur.init(S, start);
+  cur.init(S, start, limit);
   uint32_t c = 0, end;
   int flag = 0;
   for (;;) {
-    const uint32_t p0 = cur.pos;
-    if (p0 + uint32_t(kFastLutBits) <= limit) {
+    if (cur.rem >= kFastLutBits) {
       // the whole 11-bit window lies before the limit: every value coded inside it is consumed (up to 3 per lookup)
       const uint32_t m = S.mlut[cur.peek() & ((1u << kFastLutBits) - 1u)];
       if (m >> 28) {
@@ -198,11 +200,12 @@ __device__ __forceinline__ void canon_fast_count(const CanonFastShared& S, uint3
     }
     const uint32_t e = S.lut[cur.peek() & ((1u << kFastLutBits) - 1u)];
     if (e - 1u < 0x7fffu) {  // LUT hit on a plain value: e = sym | len << 9
-      if (p0 >= limit) { end = p0; break; }
+      if (cur.rem <= 0) { end = cur.pos(limit); break; }
       cur.skip(S, e >> 9);
       c++;
       continue;
     }
+    const uint32_t p0 = cur.pos(limit);
     uint32_t after;
     const int sym = canon_fast_rare_symbol(S, e, p0, nBits, &after);
     if (sym < 0) { flag = 2; end = p0; break; }
@@ -214,7 +217,7 @@ __device__ __forceinline__ void canon_fast_count(const CanonFastShared& S, uint3
       if (sym == kSymEot) { flag = 1; end = after; break; }
       c++;  // long-code value or null symbol
     }
-    cur.init(S, after);
+    cur.init(S, after, limit);
   }
   *endOut = end;
   *cntOut = c;
@@ -251,12 +254,21 @@ __device__ inline void canon_fast_tables_cta(CanonFastShared& S) {
     if (off == 0 || S.lens[kSymEot] == 0) S.error = 1;
   }
   __syncthreads();
-  for (int i = tid; i < kCanonSymbols; i += NT) {
-    const int l = S.lens[i];
-    if (l == 0 || l > 15) continue;
-    int rank = 0;
-    for (int j = 0; j < i; j++) rank += S.lens[j] == l;
-    S.sorted[S.offset[l] + rank] = uint16_t(i);
+  if (tid < 32) {  // sorted[]: symbols by (length, symbol); one warp, 32 symbols per round, ranks by __match_any_sync
+    __shared__ uint32_t nextSlot[17];
+    if (tid < 17) nextSlot[tid] = S.offset[tid];
+    __syncwarp();
+    for (int i0 = 0; i0 < kCanonSymbols; i0 += 32) {
+      const int i = i0 + tid;
+      int l = i < kCanonSymbols ? S.lens[i] : 0;
+      if (l > 15) l = 0;
+      const uint32_t same = __match_any_sync(0xffffffffu, l);
+      const uint32_t before = same & ((1u << tid) - 1u);
+      if (l) S.sorted[nextSlot[l] + __popc(before)] = uint16_t(i);
+      __syncwarp();
+      if (l && before == 0u) nextSlot[l] += __popc(same);
+      __syncwarp();
+    }
   }
   __syncthreads();
 }
@@ -299,7 +311,7 @@ __device__ inline void canon_fast_build_lut(CanonFastShared& S) {
 // *endBit are absolute bit positions inside the packing, nBits = 8 * packing length.  The sink receives runs:
 // begin(firstValueIndex), put(value) ..., end().  hintBits bounds the region searched first (0 = everything).
 // All threads call.
-template <class Sink, int NT = kThreads>
+template <class Sink, int NT = kThreads, uint32_t SUBBITS = kFastSubBits>
 __device__ bool canon_fast_decode_text(CanonFastShared& S, uint32_t nBits, const uint32_t T0, uint32_t maxValues, uint32_t hintBits,
                                        Sink sink, uint32_t* endBit, uint32_t* nValues) {
   constexpr int kThreads = NT;                       // shadows the global: every loop below strides by the CTA size
@@ -310,7 +322,7 @@ __device__ bool canon_fast_decode_text(CanonFastShared& S, uint32_t nBits, const
   for (;;) {  // region growth until the end-of-text code is inside the region
     const uint32_t avail = regionEnd - T0;
     // sub-sequence size: about kFastSubBits, adjusted so that the sub-sequences fill whole rounds of kThreads threads
-    uint32_t rounds = (avail / kFastSubBits + kThreads - 1) / kThreads;
+    uint32_t rounds = (avail / SUBBITS + kThreads - 1) / kThreads;
     if (rounds < 1u) rounds = 1u;
     if (rounds > uint32_t(kFastRounds)) rounds = kFastRounds;
     uint32_t B = (avail + rounds * kThreads - 1) / (rounds * kThreads);
@@ -336,10 +348,8 @@ __device__ bool canon_fast_decode_text(CanonFastShared& S, uint32_t nBits, const
     // the previous pass's value (both are candidates); the loop ends only after a pass in which nothing was rewritten,
     // and in that pass every start was compared against final values.
     volatile uint32_t* vend = S.endpos;
+    __syncthreads();
     for (int pass = 0; pass <= nSub; pass++) {
-      __syncthreads();
-      if (tid == 0) S.changed = 0;
-      __syncthreads();
       bool any = false;
 #pragma unroll 1
       for (int i = tid; i < nSub; i += kThreads) {
@@ -358,9 +368,7 @@ __device__ bool canon_fast_decode_text(CanonFastShared& S, uint32_t nBits, const
           any = true;
         }
       }
-      if (any) S.changed = 1;
-      __syncthreads();
-      if (!S.changed) break;
+      if (!__syncthreads_or(any ? 1 : 0)) break;  // one barrier per pass: it also orders this pass's writes before the next pass's reads
     }
     __syncthreads();
     if (tid == 0) S.firstEot = nSub;
@@ -417,12 +425,11 @@ __device__ bool canon_fast_decode_text(CanonFastShared& S, uint32_t nBits, const
         uint32_t limit = T0 + uint32_t(i1 + 1) * B;
         if (limit > regionEnd) limit = regionEnd;
         BitCursor cur;
-        cur.init(S, S.startv[i0]);
+        cur.init(S, S.startv[i0], limit);
         sink.begin(offv[i0]);
         bool have = false;
         for (;;) {
-          const uint32_t p0 = cur.pos;
-          if (p0 + uint32_t(kFastLutBits) <= limit) {
+          if (cur.rem >= kFastLutBits) {
             const uint32_t m = S.mlut[cur.peek() & ((1u << kFastLutBits) - 1u)];
             const uint32_t n = m >> 28;
             if (n) {
@@ -434,12 +441,13 @@ __device__ bool canon_fast_decode_text(CanonFastShared& S, uint32_t nBits, const
           }
           const uint32_t e = S.lut[cur.peek() & ((1u << kFastLutBits) - 1u)];
           if (e - 1u < 0x7fffu) {  // plain value
-            if (p0 >= limit) break;
+            if (cur.rem <= 0) break;
             cur.skip(S, e >> 9);
             sink.push(e & 0xffu, 1);
             have = true;
             continue;
           }
+          const uint32_t p0 = cur.pos(limit);
           uint32_t after;
           const int sym = canon_fast_rare_symbol(S, e, p0, nBits, &after);
           if (sym < 0) { bad = true; break; }
@@ -457,7 +465,7 @@ __device__ bool canon_fast_decode_text(CanonFastShared& S, uint32_t nBits, const
             else sink.push(uint32_t(sym), 1);  // a byte value with a code longer than the LUT
             have = true;
           }
-          cur.init(S, after);
+          cur.init(S, after, limit);
         }
         sink.end();
       }
@@ -466,13 +474,13 @@ __device__ bool canon_fast_decode_text(CanonFastShared& S, uint32_t nBits, const
       uint32_t limit = T0 + uint32_t(i1 + 1) * B;
       if (limit > regionEnd) limit = regionEnd;
       BitCursor cur;
-      cur.init(S, S.startv[i0]);
+      cur.init(S, S.startv[i0], limit);
       sink.begin(offv[i0]);
       bool have = false;
       uint32_t v = 0;
       for (;;) {
-        const uint32_t p0 = cur.pos;
-        if (p0 + uint32_t(kFastLutBits) <= limit) {
+        const uint32_t p0 = cur.pos(limit);
+        if (cur.rem >= kFastLutBits) {
           const uint32_t m = S.mlut[cur.peek() & ((1u << kFastLutBits) - 1u)];
           const uint32_t n = m >> 28;
           if (n) {
@@ -517,7 +525,7 @@ __device__ bool canon_fast_decode_text(CanonFastShared& S, uint32_t nBits, const
           have = true;
           v = sym == kSymNull ? uint32_t(INT32_MIN) : uint32_t(sym - 128);
         }
-        cur.init(S, after);
+        cur.init(S, after, limit);
       }
       if (have) sink.put(int32_t(v));
       sink.end();

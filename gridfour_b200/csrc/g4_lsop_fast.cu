@@ -43,6 +43,7 @@ namespace g4 {
 namespace {
 
 constexpr int kTextThreads = 512;
+constexpr uint32_t kTextSubBits = 320;        // target sub-sequence size of the text kernel: one sub-sequence per thread for a 180x240 tile
 constexpr int kExcWords = 128;               // per tile: [0] count, [2+2i] interior index, [3+2i] value
 constexpr int kExcCap = (kExcWords - 2) / 2;  // 63 exceptions; more -> general path
 constexpr int kResidGuard = 256;             // bytes in front of the first tile of the residual scratch
@@ -192,22 +193,34 @@ struct ByteTileSink {
   static constexpr bool kPacked = true;
   uint8_t* tile;       // shared memory, tileBytes
   uint32_t* exc;       // this tile's exception list (global)
-  LsopFastGeom g;
-  int w;               // C - 4
+  int w;               // C - 4, bytes per row
+  int L, nB4, nLanes, rpg;  // lane pitch, 4 * nB, lanes in use, rows per group (LsopFastGeom)
   uint32_t addr;       // word-aligned image offset of queue byte 0
   int left;            // bytes from addr to the end of the row
-  int row;
+  uint32_t rowOff;     // image offset of the current row
+  int lane, rowBase;   // the current row = rowBase + lane, lane in [2, nLanes)
   int head;            // dummy bytes at the front of the queue (run head inside a word), 0 after the first store
   int cnt;             // queued bytes, dummies included; < 4 between calls
   uint64_t q;
   int excK, excSlot;   // the last exception this thread recorded
   int32_t excV;
 
-  __device__ __forceinline__ void begin(uint32_t k0) {
+  __device__ __forceinline__ void init(uint8_t* img, uint32_t* e, const LsopFastGeom& g) {
+    tile = img;
+    exc = e;
     w = g.C - 4;
+    L = g.laneBytes;
+    nB4 = 4 * g.nB;
+    nLanes = g.nLanes;
+    rpg = g.rpg;
+  }
+  __device__ __forceinline__ void begin(uint32_t k0) {
     const int rr = int(k0) / w, cc = int(k0) - rr * w;
-    row = 2 + rr;
-    const uint32_t a0 = lane_row_offset(g, row) + uint32_t(cc);
+    const int gi = rr / rpg;
+    lane = 2 + rr - gi * rpg;
+    rowBase = gi * rpg;
+    rowOff = uint32_t(lane) * uint32_t(L) + 4u + uint32_t(gi) * uint32_t(nB4);
+    const uint32_t a0 = rowOff + uint32_t(cc);
     head = int(a0 & 3u);
     addr = a0 & ~3u;
     left = w - (cc & ~3);
@@ -217,13 +230,17 @@ struct ByteTileSink {
     excSlot = 0;
     excV = 0;
   }
-  __device__ __forceinline__ uint32_t row_start() const { return lane_row_offset(g, row); }
   __device__ __forceinline__ int cur_k() const {  // interior index of the value that will be queued next
-    return (row - 2) * w + int(addr - row_start()) + cnt;
+    return (rowBase + lane - 2) * w + int(addr - rowOff) + cnt;
   }
   __device__ __forceinline__ void next_row() {
-    row++;
-    addr = lane_row_offset(g, row);
+    rowOff += uint32_t(L);
+    if (++lane == nLanes) {  // the next group's first row: back to lane 2, one row period further
+      lane = 2;
+      rowBase += rpg;
+      rowOff += uint32_t(nB4) - uint32_t(rpg) * uint32_t(L);
+    }
+    addr = rowOff;
     left = w;
   }
   __device__ __forceinline__ void store_word() {  // cnt >= 4
@@ -235,7 +252,7 @@ struct ByteTileSink {
     cnt -= 4;
     addr += 4;
     left -= 4;
-    if (left == 0) next_row();
+    if (__builtin_expect(left == 0, 0)) next_row();
   }
   __device__ __forceinline__ void push(uint32_t bytes, int n) {  // n = 1..3 symbol bytes, first value in the low byte
     q |= uint64_t(bytes) << (8 * cnt);
@@ -273,7 +290,12 @@ struct ByteTileSink {
     } else {  // already in the image: the byte in front of addr + cnt, or the last byte of the previous row
       // (cnt == head: with head != 0 nothing of this run was stored yet, which `have` in the caller excludes)
       uint32_t p = addr + uint32_t(cnt);
-      p = p > row_start() ? p - 1 : lane_row_offset(g, row - 1) + uint32_t(w) - 1;
+      if (p > rowOff) p -= 1;
+      else {
+        uint32_t prevOff = rowOff - uint32_t(L);
+        if (lane == 2) prevOff = rowOff - uint32_t(nB4) + uint32_t(rpg - 1) * uint32_t(L);
+        p = prevOff + uint32_t(w) - 1;
+      }
       b = tile[p];
       tile[p] = 0;
     }
@@ -339,10 +361,8 @@ __global__ void __launch_bounds__(kTextThreads, 2) lsop2_text_kernel(LsopFastArg
       uint32_t endBit = 0, nv = 0;
       const uint32_t nInterior = uint32_t(A.g.R - 2) * uint32_t(A.g.C - 4);
       ByteTileSink sink;
-      sink.tile = tileImg;
-      sink.exc = A.exc + size_t(tIdx) * kExcWords;
-      sink.g = A.g;
-      ok = canon_fast_decode_text<ByteTileSink, kTextThreads>(F, span * 8u, T0 + 8u * delta, nInterior, 0u, sink, &endBit, &nv) &&
+      sink.init(tileImg, A.exc + size_t(tIdx) * kExcWords, A.g);
+      ok = canon_fast_decode_text<ByteTileSink, kTextThreads, kTextSubBits>(F, span * 8u, T0 + 8u * delta, nInterior, 0u, sink, &endBit, &nv) &&
            nv == nInterior;
     }
     __syncthreads();
@@ -372,7 +392,7 @@ __device__ __noinline__ int32_t wave_exception(const uint32_t* exc, int n, int k
 }
 
 template <bool WIDE>
-__global__ void __launch_bounds__(kThreads, 3)
+__global__ void __launch_bounds__(kThreads, 2)
     lsop2_wave_kernel(const __grid_constant__ CUtensorMap tmap, LsopFastArgs A, int listBegin, int listEnd) {
   extern __shared__ __align__(1024) unsigned char waveSmem[];
   const DecodeArgs& a = A.a;
@@ -415,7 +435,8 @@ __global__ void __launch_bounds__(kThreads, 3)
   for (int i = 0; i < 12; i++) u[i] = computing ? A.coef[size_t(tIdx) * 12 + i] : 0.f;
   const float bias = feeder ? kMagicInt : 2.f * kMagicInt + 128.f;  // x - bias == float(residual) - 1.5*2^23 (feeder: value - 1.5*2^23)
   const int4* side = A.side + size_t(tIdx) * R;
-  bool bad = false;
+  uint32_t badBits = 0;  // nonzero: some cell left the range of the fast arithmetic
+  const int32_t lim = int32_t(kRange);
   // feeder stream of group 0: rows 0 and 1 (written by kernel H), block b = columns 4b+2 .. 4b+5; the wrap block holds
   // the rows' last two columns and columns 0,1 of the feeder's next row (rows rpg, rpg+1)
   for (int idx = lane; idx < 2 * nB; idx += 32) {
@@ -431,12 +452,12 @@ __global__ void __launch_bounds__(kThreads, 3)
       const int4 s = rpg + f < R ? side[rpg + f] : make_int4(0, 0, 0, 0);
       v2 = s.x; v3 = s.y;
     }
-    const int32_t lim = int32_t(kRange);
-    if (v0 <= -lim || v0 >= lim || v1 <= -lim || v1 >= lim || v2 <= -lim || v2 >= lim || v3 <= -lim || v3 >= lim) bad = true;
+    if (v0 <= -lim || v0 >= lim || v1 <= -lim || v1 >= lim || v2 <= -lim || v2 >= lim || v3 <= -lim || v3 >= lim) badBits = 1u;
     rowbuf[idx] = make_float4(float(v0), float(v1), float(v2), float(v3));
   }
   // columns 0,1 of every lane's first row (the virtual block at stream word 0)
-  int4 sideCur = make_int4(0, 0, 0, 0), sideNext = make_int4(0, 0, 0, 0);
+  int32_t curD2 = 0, curD1 = 0;
+  int4 sideNext = make_int4(0, 0, 0, 0);
   if (lane < nLanes && lane < R) sideNext = side[lane];
   __syncwarp();
 
@@ -446,148 +467,162 @@ __global__ void __launch_bounds__(kThreads, 3)
   float f1 = 0.f, f2 = 0.f;        // own row, columns c-1 and c-2
   int32_t pi2 = 0, pi3 = 0;        // own outputs 2,3 of the previous block
   int4 sqPrev = make_int4(0, 0, 0, 0);
-  int b = lane < nLanes ? nB - 1 - lane : 0;  // block inside the row; every lane starts with its virtual wrap block
+  int32_t w0 = 0, w1 = 0, w2 = 0, w3 = 0;      // wrap-block values (set in the wrap block, read only there)
+  float g0 = 0.f, g1 = 0.f, g2 = 0.f, g3 = 0.f;
+  const uint32_t wrapB16 = uint32_t(nB - 1) * 16u, preB16 = wrapB16 - 16u;
+  uint32_t b16 = lane < nLanes ? uint32_t(nB - 1 - lane) * 16u : 0u;  // 16 x block inside the row; every lane starts towards its virtual wrap block
   int row = lane - rpg;                       // row of the current stream position (virtual row before the first)
-  bool valid = false;                         // row is a tile row this lane computes
-  bool started = false;                       // past the virtual block in front of the lane's first row
-  int32_t* rowp = t.base + int64_t(row) * t.pitch;  // dereferenced only while valid
-  const int64_t groupStep = int64_t(rpg) * t.pitch;
+  uint32_t validM = 0u;                       // 0xFF800000 while `row` is a tile row this lane computes
+  uint32_t started = 0u;                      // past the virtual block in front of the lane's first row
+  char* rowp = reinterpret_cast<char*>(t.base + int64_t(row) * t.pitch);  // dereferenced only while valid
+  const int64_t groupStep = int64_t(rpg) * t.pitch * 4;
   const int wInterior = C - 4;
-  const int swz = (lane >> 1) & 3;
+  const uint32_t ringLane = ring0 + 64u * uint32_t(lane);
+  const uint32_t swz16 = uint32_t((lane >> 1) & 3) * 16u;
+  const uint32_t rbRead = smem_u32(rowbuf) + uint32_t(lane & 1) * uint32_t(nB) * 16u;
+  const uint32_t rbWrite = smem_u32(rowbuf) + uint32_t(lane == nLanes - 1 ? nB : 0) * 16u;
+  const uint32_t feederM = feeder ? 1u : 0u, writerM = writer ? 1u : 0u;
   const int nChunks = G.nIter >> 4;
-  for (int chunk = 0; chunk < nChunks; chunk++) {
-    if (lane == 0 && chunk + 1 < nChunks) issue(chunk + 1);
-    mbar_wait(bar0 + 8u * (chunk & 1), uint32_t(chunk >> 1) & 1u);
-    const unsigned char* stage = ring + kWaveStageBytes * (chunk & 1) + 64 * lane;
-#pragma unroll 1
-    for (int pair = 0; pair < 8; pair++) {
-      const uint2 rw2 = *reinterpret_cast<const uint2*>(stage + 16 * ((pair >> 1) ^ swz) + 8 * (pair & 1));
-#pragma unroll
-      for (int half = 0; half < 2; half++) {
-        const uint32_t rw = half ? rw2.y : rw2.x;
-        const bool wrap = b == nB - 1;
-        // ---- inputs of the four positions: residual bytes (biased floats) or the feeder's finished values
-        float x0, x1, x2, x3;
-        if (feeder) {
-          const float4 fin = rowbuf[lane * nB + b];
-          x0 = fin.x; x1 = fin.y; x2 = fin.z; x3 = fin.w;
-        } else {
-          x0 = __uint_as_float(__byte_perm(rw, 0x4B400000u, 0x7640));
-          x1 = __uint_as_float(__byte_perm(rw, 0x4B400000u, 0x7641));
-          x2 = __uint_as_float(__byte_perm(rw, 0x4B400000u, 0x7642));
-          x3 = __uint_as_float(__byte_perm(rw, 0x4B400000u, 0x7643));
-        }
-        // ---- wrap block: the row's last two columns (Triangle predictor folded into D2/D1 by kernel H) and columns 0,1
-        // of the lane's next row.  Feeders take theirs from the stream except before their first row.
-        const bool fix = wrap && (!feeder || !started);
-        int32_t w0 = 0, w1 = 0, w2 = 0, w3 = 0;
-        float g0 = 0.f, g1 = 0.f, g2 = 0.f, g3 = 0.f;
-        if (fix) {
-          w0 = int32_t(uint32_t(pi3) + uint32_t(sideCur.z));
-          w1 = int32_t(uint32_t(w0) + uint32_t(sideCur.w));
-          w2 = sideNext.x;
-          w3 = sideNext.y;
-          g0 = float(w0); g1 = float(w1); g2 = float(w2); g3 = float(w3);
-          const int32_t lim = int32_t(kRange);
-          const bool cur = valid && (w0 <= -lim || w0 >= lim || w1 <= -lim || w1 >= lim);
-          const bool nxt = computing && row + rpg < R && (w2 <= -lim || w2 >= lim || w3 <= -lim || w3 >= lim);
-          if (cur || nxt) bad = true;
-        }
-        // ---- exceptions: a zero byte in a tile that has an exception list
-        bool general = false;
-        if (nExc > 0) {
-          const bool z = ((rw - 0x01010101u) & ~rw & 0x80808080u) != 0u;
-          general = __any_sync(0xffffffffu, z && valid && !wrap);
-        }
-        int32_t ex[4] = {0, 0, 0, 0};
-        if (general) {
-#pragma unroll
-          for (int j = 0; j < 4; j++) {
-            const uint32_t byte = (rw >> (8 * j)) & 0xffu;
-            ex[j] = int32_t(byte) - 128;
-            if (byte == 0u && valid && !wrap) ex[j] = wave_exception(exc, nExc, (row - 2) * wInterior + 4 * b + j);
-          }
-        }
-#pragma unroll
-        for (int i = 0; i < 4; i++) { av[i] = av[i + 4]; bv[i] = bv[i + 4]; }
-        int32_t out[4];
-        float fout[4];
-        bool over = false;
-        // one block of four cells; GEN = the rare form with full-width residuals (exception list)
-        auto cells = [&](auto genTag) {
-          constexpr bool GEN = decltype(genTag)::value;
-#pragma unroll
-          for (int j = 0; j < 4; j++) {
-            av[4 + j] = __shfl_up_sync(0xffffffffu, f2, 1);
-            bv[4 + j] = __shfl_up_sync(0xffffffffu, av[j], 1);
-            // LsDecoder12.java:424-438 -- evaluated left to right in float32, no fused multiply-add
-            float p = u[0] * f1;
-            p = p + u[1] * av[j + 1];
-            p = p + u[2] * av[j + 2];
-            p = p + u[3] * av[j + 3];
-            p = p + u[4] * av[j + 4];
-            p = p + u[5] * f2;
-            p = p + u[6] * av[j];
-            p = p + u[7] * bv[j];
-            p = p + u[8] * bv[j + 1];
-            p = p + u[9] * bv[j + 2];
-            p = p + u[10] * bv[j + 3];
-            p = p + u[11] * bv[j + 4];
-            over |= !(fabsf(p) < kRange);
-            const float t2 = __fadd_rd(__fadd_rd(p, kMagicHalf), kMagicHalfUp);  // 1.5*2^23 + StrictMath.round(p)
-            const float xj = j == 0 ? x0 : j == 1 ? x1 : j == 2 ? x2 : x3;
-            float fv = t2 + (xj - bias);
-            int32_t iv;
-            if constexpr (GEN) {
-              iv = int32_t(uint32_t(__float_as_int(t2)) - 0x4B400000u + uint32_t(ex[j]));
-              if (!feeder) fv = float(iv);
-            } else iv = int32_t(uint32_t(__float_as_int(t2)) + __float_as_uint(xj) - 0x96800080u);  // round(p) + byte - 128
-            if (fix) {
-              fv = j == 0 ? g0 : j == 1 ? g1 : j == 2 ? g2 : g3;
-              iv = j == 0 ? w0 : j == 1 ? w1 : j == 2 ? w2 : w3;
-            }
-            out[j] = iv;
-            fout[j] = fv;
-            f2 = f1;
-            f1 = fv;
-          }
-        };
-        if (general) cells(std::true_type{});
-        else cells(std::false_type{});
-        if (over && valid && !wrap) bad = true;
-        // ---- stores: columns 4b .. 4b+3 of the row (two from the previous block); whole sectors when WIDE
-        const int4 sq = make_int4(pi2, pi3, out[0], out[1]);
-        if (WIDE) {
-          if (valid && (b & 1)) {
-            int32_t* dst = rowp + 4 * (b - 1);
-            asm volatile("st.global.v8.b32 [%0], {%1,%2,%3,%4,%5,%6,%7,%8};" ::"l"(dst), "r"(sqPrev.x), "r"(sqPrev.y), "r"(sqPrev.z),
-                         "r"(sqPrev.w), "r"(sq.x), "r"(sq.y), "r"(sq.z), "r"(sq.w)
-                         : "memory");
-          }
-          sqPrev = sq;
-        } else if (valid) *reinterpret_cast<int4*>(rowp + 4 * b) = sq;
-        if (writer && started) rowbuf[(lane - (nLanes - 2)) * nB + b] = make_float4(fout[0], fout[1], fout[2], fout[3]);
-        pi2 = out[2];
-        pi3 = out[3];
-        // ---- advance
-        if (b == nB - 2 && started) {  // side record of the next row, one block before it is needed
+
+  // one iteration: the block of four cells at 16-byte block offset b16 of the lane's current row
+  auto step = [&](const uint32_t rw) {
+    // ---- the rare blocks of a row, one branch: the block after the wrap (next row), the block before it (side record
+    // of the next row, one block early), the wrap block itself (the row's last two columns -- Triangle predictor folded
+    // into D2/D1 by kernel H -- and columns 0,1 of the lane's next row; feeders take theirs from the stream except
+    // before their first row)
+    bool fix = false;
+    uint32_t badM = validM;
+    if (b16 >= preB16) {
+      if (b16 > wrapB16) {
+        b16 = 0;
+        row += rpg;
+        rowp += groupStep;
+        curD2 = sideNext.z;
+        curD1 = sideNext.w;
+        validM = (computing && row < R) ? 0xFF800000u : 0u;
+        badM = validM;
+        started = 1u;
+      } else if (b16 == preB16) {
+        if (started) {
           const int nr = row + rpg;
           sideNext = (computing && nr < R) ? side[nr] : make_int4(0, 0, 0, 0);
         }
-        b++;
-        if (wrap) {
-          b = 0;
-          row += rpg;
-          rowp += groupStep;
-          sideCur = sideNext;
-          valid = computing && row < R;
-          started = true;
+      } else {
+        badM = 0u;  // the stencil results of the wrap block are discarded
+        if (!feeder || !started) {
+          fix = true;
+          w0 = int32_t(uint32_t(pi3) + uint32_t(curD2));
+          w1 = int32_t(uint32_t(w0) + uint32_t(curD1));
+          w2 = sideNext.x;
+          w3 = sideNext.y;
+          g0 = float(w0); g1 = float(w1); g2 = float(w2); g3 = float(w3);
+          const bool cur = validM != 0u && (w0 <= -lim || w0 >= lim || w1 <= -lim || w1 >= lim);
+          const bool nxt = computing && row + rpg < R && (w2 <= -lim || w2 >= lim || w3 <= -lim || w3 >= lim);
+          if (cur || nxt) badBits = 1u;
         }
-        __syncwarp();
       }
     }
+    // ---- inputs of the four positions: residual bytes (biased floats) or the feeder's finished values
+    float x0 = __uint_as_float(__byte_perm(rw, 0x4B400000u, 0x7640));
+    float x1 = __uint_as_float(__byte_perm(rw, 0x4B400000u, 0x7641));
+    float x2 = __uint_as_float(__byte_perm(rw, 0x4B400000u, 0x7642));
+    float x3 = __uint_as_float(__byte_perm(rw, 0x4B400000u, 0x7643));
+    asm volatile("{ .reg .pred p; setp.ne.b32 p, %4, 0; @p ld.shared.v4.f32 {%0, %1, %2, %3}, [%5]; }"
+                 : "+f"(x0), "+f"(x1), "+f"(x2), "+f"(x3)
+                 : "r"(feederM), "r"(rbRead + b16));
+#pragma unroll
+    for (int i = 0; i < 4; i++) { av[i] = av[i + 4]; bv[i] = bv[i + 4]; }
+    int32_t out[4];
+    float fout[4];
+    uint32_t acc = 0;  // exponent bits of t1 that differ from those of [2^22, 2^23): nonzero <=> p outside [-2^21, 2^21) or NaN
+    auto cells = [&](auto genTag, const int32_t* ex) {
+      constexpr bool GEN = decltype(genTag)::value;
+#pragma unroll
+      for (int j = 0; j < 4; j++) {
+        av[4 + j] = __shfl_up_sync(0xffffffffu, f2, 1);
+        bv[4 + j] = __shfl_up_sync(0xffffffffu, av[j], 1);
+        // LsDecoder12.java:424-438 -- evaluated left to right in float32, no fused multiply-add
+        float p = u[0] * f1;
+        p = p + u[1] * av[j + 1];
+        p = p + u[2] * av[j + 2];
+        p = p + u[3] * av[j + 3];
+        p = p + u[4] * av[j + 4];
+        p = p + u[5] * f2;
+        p = p + u[6] * av[j];
+        p = p + u[7] * bv[j];
+        p = p + u[8] * bv[j + 1];
+        p = p + u[9] * bv[j + 2];
+        p = p + u[10] * bv[j + 3];
+        p = p + u[11] * bv[j + 4];
+        const float t1 = __fadd_rd(p, kMagicHalf);
+        acc |= __float_as_uint(t1) ^ 0x4A800000u;
+        const float t2 = __fadd_rd(t1, kMagicHalfUp);  // 1.5*2^23 + StrictMath.round(p)
+        const float xj = j == 0 ? x0 : j == 1 ? x1 : j == 2 ? x2 : x3;
+        float fv = t2 + (xj - bias);
+        int32_t iv;
+        if constexpr (GEN) {
+          iv = int32_t(uint32_t(__float_as_int(t2)) - 0x4B400000u + uint32_t(ex[j]));
+          if (!feeder) fv = float(iv);
+        } else iv = int32_t(uint32_t(__float_as_int(t2)) + __float_as_uint(xj) - 0x96800080u);  // round(p) + byte - 128
+        if (fix) {
+          fv = j == 0 ? g0 : j == 1 ? g1 : j == 2 ? g2 : g3;
+          iv = j == 0 ? w0 : j == 1 ? w1 : j == 2 ? w2 : w3;
+        }
+        out[j] = iv;
+        fout[j] = fv;
+        f2 = f1;
+        f1 = fv;
+      }
+    };
+    // ---- exceptions: a zero byte in a tile that has an exception list -> the general form of the block
+    bool general = false;
+    if (nExc > 0) {
+      const bool z = ((rw - 0x01010101u) & ~rw & 0x80808080u) != 0u;
+      general = __any_sync(0xffffffffu, z && badM != 0u);
+    }
+    if (general) {
+      int32_t ex[4];
+#pragma unroll
+      for (int j = 0; j < 4; j++) {
+        const uint32_t byte = (rw >> (8 * j)) & 0xffu;
+        ex[j] = int32_t(byte) - 128;
+        if (byte == 0u && badM != 0u) ex[j] = wave_exception(exc, nExc, (row - 2) * wInterior + int(b16 >> 2) + j);
+      }
+      cells(std::true_type{}, ex);
+    } else cells(std::false_type{}, nullptr);
+    badBits |= acc & badM;
+    // ---- stores: columns 4b .. 4b+3 of the row (two from the previous block); whole sectors when WIDE
+    const int4 sq = make_int4(pi2, pi3, out[0], out[1]);
+    if (WIDE) {
+      asm volatile("{ .reg .pred p; setp.ne.b32 p, %9, 0; @p st.global.v8.b32 [%0], {%1,%2,%3,%4,%5,%6,%7,%8}; }" ::"l"(rowp + b16 - 16), "r"(sqPrev.x),
+                   "r"(sqPrev.y), "r"(sqPrev.z), "r"(sqPrev.w), "r"(sq.x), "r"(sq.y), "r"(sq.z), "r"(sq.w), "r"(validM & (b16 << 19) & 0x00800000u)
+                   : "memory");
+      sqPrev = sq;
+    } else if (validM) *reinterpret_cast<int4*>(rowp + b16) = sq;
+    asm volatile("{ .reg .pred p; setp.ne.b32 p, %0, 0; @p st.shared.v4.f32 [%1], {%2, %3, %4, %5}; }" ::"r"(writerM & started), "r"(rbWrite + b16),
+                 "f"(fout[0]), "f"(fout[1]), "f"(fout[2]), "f"(fout[3])
+                 : "memory");
+    pi2 = out[2];
+    pi3 = out[3];
+    b16 += 16u;
+    __syncwarp();
+  };
+
+  for (int chunk = 0; chunk < nChunks; chunk++) {
+    if (lane == 0 && chunk + 1 < nChunks) issue(chunk + 1);
+    mbar_wait(bar0 + 8u * (chunk & 1), uint32_t(chunk >> 1) & 1u);
+    const uint32_t stage = ringLane + uint32_t(kWaveStageBytes) * (chunk & 1);
+#pragma unroll 1
+    for (uint32_t quad = 0; quad < 4; quad++) {  // sixteen residual bytes = four iterations per shared-memory read
+      uint32_t r0, r1, r2, r3;
+      asm volatile("ld.shared.v4.b32 {%0, %1, %2, %3}, [%4];" : "=r"(r0), "=r"(r1), "=r"(r2), "=r"(r3) : "r"(stage + ((quad * 16u) ^ swz16)));
+      step(r0);
+      step(r1);
+      step(r2);
+      step(r3);
+    }
   }
-  if (__any_sync(0xffffffffu, bad)) {  // outside the fast arithmetic's range: the general kernels redo the tile
+  if (__any_sync(0xffffffffu, badBits != 0u)) {  // outside the fast arithmetic's range: the general kernels redo the tile
     if (lane == 0) A.defer[atomicAdd(A.deferCount, 1)] = tIdx;
   }
 }
