@@ -95,35 +95,60 @@ class ClockSampler(threading.Thread):
                 "samples": len(sm)}
 
 
-def cpu_arm(cfg, threads, budget_s, oracle):
-    """Times the oracle's decode (and encode) of a bounded sample: whole tile columns of the workload's first tile row."""
+def workload_string(cfg, codecs, missing=()):
+    """config.workload of BOTH arms (the driver compares the strings)."""
+    return "%s, codecs=%s%s" % (cfg["name"], "+".join(codecs), (" (not yet on the GPU: %s)" % "+".join(missing)) if missing else "")
+
+
+def cpu_sample(cfg, threads, budget_s, oracle):
+    """The bounded CPU sample of the workload: whole tile rows from the top of rank 0's shard, encoded ONCE by the oracle.
+    The number of tile rows is grown until one decode pass takes about budget_s / 8 (or the shard is exhausted)."""
     ids = [ORACLE_IDS[c] for c in cfg["codecs"]]
     tr, tc = cfg["tr"], cfg["tc"]
-    across = cfg["cols"] // tc
     is_f = cfg["dtype"] == "float32"
-    n_tiles = min(across, 24)
+    max_rows = cfg["rows"] // tr
+    n_rows = 1
     while True:
         gen = oracle.terrain_f32 if is_f else oracle.terrain_i32
-        grid = gen(0, 0, tr, n_tiles * tc, n_threads=threads)
+        grid = gen(0, 0, n_rows * tr, cfg["cols"], n_threads=threads)
         t0 = time.perf_counter()
         arena, slot, lens = oracle.encode_grid(ids, grid, tr, tc, n_threads=threads)
         t_enc = time.perf_counter() - t0
         off = (np.arange(lens.size) * slot).astype(np.uint64)
         t0 = time.perf_counter()
-        out = oracle.decode_grid(ids, arena, off, lens, tr, n_tiles * tc, tr, tc, dtype=np.float32 if is_f else np.int32, n_threads=threads)
+        out = oracle.decode_grid(ids, arena, off, lens, grid.shape[0], grid.shape[1], tr, tc, dtype=np.float32 if is_f else np.int32,
+                                 n_threads=threads)
         t_dec = time.perf_counter() - t0
         assert np.array_equal(out.view(np.uint32), grid.view(np.uint32))
-        if t_enc + t_dec > budget_s / 4 or n_tiles >= across:
+        if t_dec > budget_s / 8 or t_enc > budget_s / 6 or n_rows >= max_rows:
             break
-        n_tiles = min(across, n_tiles * 4)
+        n_rows = min(max_rows, n_rows * 3)
+    return dict(ids=ids, grid=grid, arena=arena, off=off, lens=lens, t_enc=t_enc, tiles=int(lens.size), tile_rows=n_rows)
+
+
+def cpu_decode_pass(cfg, smp, threads, oracle):
+    tr, tc = cfg["tr"], cfg["tc"]
+    is_f = cfg["dtype"] == "float32"
+    t0 = time.perf_counter()
+    oracle.decode_grid(smp["ids"], smp["arena"], smp["off"], smp["lens"], smp["grid"].shape[0], smp["grid"].shape[1], tr, tc,
+                       dtype=np.float32 if is_f else np.int32, n_threads=threads)
+    return time.perf_counter() - t0
+
+
+def cpu_arm(cfg, threads, budget_s, oracle):
+    """Oracle decode (and encode) throughput on the bounded sample; used for cpu_baseline of our own arm."""
+    smp = cpu_sample(cfg, threads, budget_s, oracle)
+    t_dec = min(cpu_decode_pass(cfg, smp, threads, oracle) for _ in range(2))
+    grid, lens = smp["grid"], smp["lens"]
     raw = grid.size * 4
-    res = {"decode_gbs": raw / t_dec / 1e9, "encode_gbs": raw / t_enc / 1e9, "tiles": n_tiles, "dec_s": t_dec, "enc_s": t_enc,
-           "bits_per_sample": 8.0 * float(lens.sum()) / grid.size}
-    if not is_f:
+    tr, tc = cfg["tr"], cfg["tc"]
+    res = {"decode_gbs": raw / t_dec / 1e9, "encode_gbs": raw / smp["t_enc"] / 1e9, "tiles": smp["tiles"], "dec_s": t_dec,
+           "enc_s": smp["t_enc"], "bits_per_sample": 8.0 * float(lens.sum()) / grid.size}
+    if cfg["dtype"] != "float32":
         # input distribution check (SURVEY.md 8d): Triangle-predictor M32 stream of the sample's first tiles
         one_byte, total_codes, hist = 0, 0, np.zeros(256, np.int64)
-        for k in range(min(n_tiles, 8)):
-            n, _seed, m32 = oracle.predictor_encode(oracle.PRED_TRIANGLE, grid[:, k * tc:(k + 1) * tc])
+        for k in range(min(smp["tiles"], 8)):
+            n, _seed, m32 = oracle.predictor_encode(oracle.PRED_TRIANGLE, grid[:tr, k * tc:(k + 1) * tc])
             b = np.frombuffer(m32, np.uint8)
             hist += np.bincount(b, minlength=256)
             total_codes += tr * tc - 1
@@ -135,33 +160,31 @@ def cpu_arm(cfg, threads, budget_s, oracle):
 
 
 def run_reference(args, rank, cfg):
+    """--impl reference: the reference's own CPU algorithm (C++ restatement: no JVM in this image) on all host threads.
+    The sample is generated and ENCODED ONCE; every warm-up / timed step is one whole decode pass over it."""
     if rank != 0:
         return
     from oracle import g4oracle as oracle
 
     oracle.build()
     threads = oracle.hardware_threads()
-    vals = []
-    res = None
+    smp = cpu_sample(cfg, threads, 24.0, oracle)
     for _ in range(args.warmup):
-        res = cpu_arm(cfg, threads, 6.0, oracle)
-    t0 = time.perf_counter()
-    for _ in range(args.steps):
-        res = cpu_arm(cfg, threads, 6.0, oracle)
-        vals.append(res["decode_gbs"])
-    wall = time.perf_counter() - t0
-    v = float(np.mean(vals))
-    sample = "%d tiles of %dx%d (first tile row of the workload) per step, decode timed separately from encode" % (
-        res["tiles"], cfg["tr"], cfg["tc"])
+        cpu_decode_pass(cfg, smp, threads, oracle)
+    times = [cpu_decode_pass(cfg, smp, threads, oracle) for _ in range(args.steps)]
+    raw = smp["grid"].size * 4
+    v = raw * len(times) / sum(times) / 1e9
+    sample = ("%d tiles of %dx%d = the first %d tile row(s) of rank 0's shard, encoded once; one step = one decode pass over "
+              "them; C++ restatement of the Java reference (no JVM in this image), tile thread pool over %d threads") % (
+                  smp["tiles"], cfg["tr"], cfg["tc"], smp["tile_rows"], threads)
     metric = METRIC if args.config == 3 else "GVRS tile decode GB/s of raw samples (%s)" % cfg["name"].split(":")[0]
     line = {
         "impl": "reference", "metric": metric, "value": v, "unit": "GB/s", "n_gpus": args.gpus, "steps": args.steps,
-        "warmup": args.warmup, "ms_per_step": 1000.0 * wall / max(1, args.steps), "higher_is_better": True, "scaling": "weak",
+        "warmup": args.warmup, "ms_per_step": 1000.0 * sum(times) / max(1, len(times)), "higher_is_better": True, "scaling": "weak",
         "vs_baseline": None, "dtype": cfg["dtype"], "data": "synthetic",
-        "config": {"workload": "%s, codecs=%s; C++ restatement of the reference (no JVM in this image), tile thread pool" % (
-            cfg["name"], "+".join(cfg["codecs"]))},
+        "config": {"workload": workload_string(cfg, cfg["codecs"])},
         "cpu_baseline": {"value": v, "unit": "GB/s", "cores": threads, "kind": "port", "sample": sample,
-                         "encode_value": res["encode_gbs"], "bits_per_sample": res["bits_per_sample"]},
+                         "encode_value": raw / smp["t_enc"] / 1e9, "bits_per_sample": 8.0 * float(smp["lens"].sum()) / smp["grid"].size},
         "e2e": {"value": v, "unit": "GB/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
     }
     print(json.dumps(line))
@@ -222,6 +245,54 @@ def run_sweep(args, torch, dist, g4, L, ctx, dev, stream, rank, world, barrier):
                           "peak": peak, "peak_source": peak_src, "sweep": sweep}))
 
 
+def bind_to_gpu_numa_node(local_rank):
+    """Best effort: run this rank's host threads (and first-touch its pinned buffers) on the NUMA node of its GPU."""
+    try:
+        import torch
+
+        bus = torch.cuda.get_device_properties(local_rank).pci_bus_id if hasattr(torch.cuda.get_device_properties(local_rank), "pci_bus_id") else None
+        q = subprocess.run(["nvidia-smi", "-i", str(local_rank), "--query-gpu=pci.bus_id", "--format=csv,noheader"], capture_output=True,
+                           text=True).stdout.strip().lower()
+        bus = q[4:] if q.startswith("0000") and len(q) > 12 else q  # sysfs uses a 4-digit domain
+        node = int(open("/sys/bus/pci/devices/%s/numa_node" % bus).read())
+        if node < 0:
+            return {"numa_node": node, "bound": False}
+        cpus = open("/sys/devices/system/node/node%d/cpulist" % node).read().strip()
+        ids = set()
+        for part in cpus.split(","):
+            lo, _, hi = part.partition("-")
+            ids.update(range(int(lo), int(hi or lo) + 1))
+        allowed = ids & os.sched_getaffinity(0)
+        if allowed:
+            os.sched_setaffinity(0, allowed)
+        return {"numa_node": node, "bound": bool(allowed), "cpus": len(allowed)}
+    except Exception as e:  # containers often hide the topology
+        return {"numa_node": None, "bound": False, "why": type(e).__name__}
+
+
+def measure_pcie(torch, dev, barrier, world, dist, nbytes=1 << 30):
+    """Plain pinned-memory copies of 1 GiB per rank, ALL ranks at once: the platform's D2H / H2D ceiling that the e2e line
+    (1.87 GB of decoded raster back to the host per step) runs into.  Returns GB/s per GPU (min over ranks)."""
+    h = torch.empty(nbytes, dtype=torch.uint8).pin_memory()
+    d = torch.empty(nbytes, dtype=torch.uint8, device=dev)
+    res = {}
+    for name, (dst, src) in {"d2h": (h, d), "h2d": (d, h)}.items():
+        dst.copy_(src, non_blocking=True)
+        barrier()
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record()
+        for _ in range(3):
+            dst.copy_(src, non_blocking=True)
+        e1.record()
+        barrier()
+        t = torch.tensor([e0.elapsed_time(e1) / 3000.0], dtype=torch.float64, device=dev)
+        if world > 1:
+            dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        res[name + "_gbs_per_gpu"] = nbytes / float(t[0]) / 1e9
+    del h, d
+    return res
+
+
 def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
@@ -232,6 +303,8 @@ def main():
     ap.add_argument("--tile-rows", type=int, default=0, help="tile rows per GPU (default: the config's own)")
     ap.add_argument("--cpu-seconds", type=float, default=12.0)
     ap.add_argument("--no-e2e", action="store_true")
+    ap.add_argument("--strong", action="store_true",
+                    help="config 3, strong scaling: the WHOLE 43200x86400 grid (240 tile rows) split over the ranks (N=1: one GPU holds it all)")
     args = ap.parse_args()
     args.warmup = max(args.warmup, 3)
     rank = int(os.environ.get("RANK", "0"))
@@ -240,6 +313,10 @@ def main():
     cfg = dict(CONFIGS[3 if args.config == 5 else args.config])
     if args.tile_rows:
         cfg["rows"] = args.tile_rows * cfg["tr"]
+    if args.strong and args.config == 3:
+        cfg["rows"] = (GLOBAL_TILE_ROWS // world) * cfg["tr"]
+        cfg["name"] = "config3 strong scaling: 43200x86400 int32 over %d GPU(s), %d tiles of 180x240 per GPU" % (
+            world, (GLOBAL_TILE_ROWS // world) * (cfg["cols"] // cfg["tc"]))
     if args.impl == "reference":
         run_reference(args, rank, cfg)
         return
@@ -252,6 +329,7 @@ def main():
 
     torch.cuda.set_device(local_rank)
     dev = torch.device("cuda", local_rank)
+    numa = bind_to_gpu_numa_node(local_rank)
     if world > 1:
         os.environ.setdefault("MASTER_ADDR", "127.0.0.1")
         # the contract is ONE JSON line on stdout: NCCL prints its "NCCL version ..." banner to fd 1 when the communicator
@@ -306,14 +384,31 @@ def main():
     ctx.set_timing(True)
     enc_ms = []
     batch = None
-    for i in range(3):
+    band_rows = 30 * TILE_R  # encode at most one config-3 shard at a time (bounds the candidate slots of the encoder)
+    n_bands = (rows + band_rows - 1) // band_rows if (args.strong and rows > band_rows) else 1
+    for i in range(3 if n_bands == 1 else 1):
         e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
         barrier()
         e0.record(stream)
-        batch = master.encodeTiles(grid, TILE_R, TILE_C)
+        if n_bands == 1:
+            batch = master.encodeTiles(grid, TILE_R, TILE_C)
+        else:
+            parts, base = [], 0
+            for b in range(n_bands):
+                pb = master.encodeTiles(grid[b * band_rows:(b + 1) * band_rows], TILE_R, TILE_C)
+                used = (pb.total_bytes + 7) & ~7
+                parts.append((pb.arena[:used].clone(), pb.offsets + base, pb.lens, pb.codec, pb.predictor, pb.status))
+                base += used
+                del pb
+            band = master._band((rows, cols), np.int32, TILE_R, TILE_C)
+            batch = g4.TileBatch(torch.cat([p[0] for p in parts]), torch.cat([p[1] for p in parts]), torch.cat([p[2] for p in parts]),
+                                 torch.cat([p[3] for p in parts]), torch.cat([p[4] for p in parts]), torch.cat([p[5] for p in parts]), base, band)
+            del parts
         e1.record(stream)
         torch.cuda.synchronize(dev)
         enc_ms.append(e0.elapsed_time(e1))
+    if len(enc_ms) == 1:
+        enc_ms = enc_ms * 2
     enc_kernel_ms = {c: ctx.kernel_time_ms(1, ORACLE_IDS[c]) for c in codecs}
     lens = batch.lens.cpu().numpy().astype(np.int64)
     codec_of_tile = batch.codec.cpu().numpy()
@@ -332,18 +427,22 @@ def main():
     sampler = ClockSampler(local_rank)
     sampler.start()
     time.sleep(0.3)
-    kernel_ms = {}
     barrier()
     e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     e0.record(stream)
-    for _ in range(args.steps):
+    for _ in range(args.steps):  # the timed region: K decode passes, nothing else
         master.decodeTiles(batch, out=out)
+    e1.record(stream)
+    barrier()
+    # per-kernel-set device time (CUDA events inside the library, on the launching stream): separate, untimed passes
+    kernel_ms = {}
+    for _ in range(min(args.steps, 5)):
+        master.decodeTiles(batch, out=out)
+        torch.cuda.synchronize(dev)
         for c in codecs:
             ms = ctx.kernel_time_ms(0, ORACLE_IDS[c])
             if ms is not None:
                 kernel_ms.setdefault(c, []).append(ms)
-    e1.record(stream)
-    barrier()
     t_dec = e0.elapsed_time(e1) / 1000.0
     clocks = sampler.finish()
     t = torch.tensor([t_dec, float(np.mean(enc_ms[1:])) / 1000.0], dtype=torch.float64, device=dev)
@@ -380,7 +479,7 @@ def main():
 
     # ---- e2e: host buffers through the C ABI ------------------------------------------------------------------
     e2e = None
-    if not args.no_e2e:
+    if not args.no_e2e and samples * 4 <= (4 << 30):  # (a 15 GB pinned raster for the whole grid on one GPU is left out)
         h_arena = torch.empty(batch.total_bytes, dtype=torch.uint8).pin_memory()
         h_arena.copy_(batch.arena[: batch.total_bytes])
         h_off = batch.offsets.cpu().numpy().astype(np.uint64)
@@ -401,9 +500,15 @@ def main():
         if world > 1:
             dist.all_reduce(tt, op=dist.ReduceOp.MAX)
         assert np.array_equal(h_grid.numpy()[:TILE_R].view(np.uint32), grid[:TILE_R].cpu().numpy().view(np.uint32))
-        e2e = {"value": 4.0 * samples * world * e2e_steps / float(tt[0]) / 1e9, "unit": "GB/s",
+        del h_grid, h_arena, hb
+        pcie = measure_pcie(torch, dev, barrier, world, dist)
+        e2e_total = 4.0 * samples * world * e2e_steps / float(tt[0]) / 1e9
+        e2e = {"value": e2e_total, "unit": "GB/s",
                "h2d_bytes_per_step": int(batch.total_bytes + h_off.nbytes + h_len.nbytes),
-               "d2h_bytes_per_step": int(samples * 4 + n_tiles * 4), "steps": e2e_steps}
+               "d2h_bytes_per_step": int(samples * 4 + n_tiles * 4), "steps": e2e_steps,
+               "per_gpu": e2e_total / world, "pcie_copy_peak": pcie, "frac_of_d2h_peak": e2e_total / world / pcie["d2h_gbs_per_gpu"],
+               "host_binding": numa,
+               "note": "the decoded raster (4 B/sample) crossing PCIe bounds this line; pcie_copy_peak = plain pinned copies, all ranks at once"}
 
     if rank != 0:
         if world > 1:
@@ -447,10 +552,9 @@ def main():
     metric = METRIC if args.config == 3 else "GVRS tile decode GB/s of raw samples (%s)" % cfg["name"].split(":")[0]
     line = {
         "metric": metric, "value": value, "unit": "GB/s", "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
-        "ms_per_step": 1000.0 * t_dec / args.steps, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
+        "ms_per_step": 1000.0 * t_dec / args.steps, "higher_is_better": True, "scaling": "strong" if args.strong else "weak", "vs_baseline": None,
         "dtype": cfg["dtype"], "data": "synthetic",
-        "config": {"workload": "%s, codecs=%s%s" % (cfg["name"], "+".join(codecs),
-                                                    (" (not yet on the GPU: %s)" % "+".join(missing)) if missing else ""),
+        "config": {"workload": workload_string(cfg, codecs, missing),
                    "l2": "inputs larger than L2 (payload %.0f MB + raster %.0f MB per step)" % (total_payload / 1e6, samples * 4 / 1e6),
                    "tile_choice": {c: int(codec_hist[k]) for k, c in enumerate(codecs)} | {"raw": int(codec_hist[255])}},
         "bits_per_sample": bits_per_sample,

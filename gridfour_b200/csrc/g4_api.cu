@@ -72,7 +72,7 @@ struct g4_context {
   DevBuf coef;         // LSOP12 decode: 12 float32 coefficients per tile
   DevBuf defer;        // LSOP12 decode: tiles the fast entropy kernel hands to the general one
   DevBuf lsopMeta;     // LSOP12 decode: interior code lengths + text position, kernel H -> kernel T
-  DevBuf lsopSide, lsopExc, lsopResid;  // LSOP12 decode, fast path (g4_lsop_fast.cu): side records, exception lists, residual bytes
+  DevBuf lsopSide, lsopExc, lsopResid, lsopStage;  // LSOP12 decode, fast path (g4_lsop_fast.cu): side records, exception lists, residual bytes
   DevBuf wide;         // TileElementShort: int32 staging raster around the integer codecs
   // zlib-stream encode stages (CodecDeflate, CodecFloat, LSOP12 Deflate alternative)
   DevBuf jobLen, jobOff, jobOut, jobTotal, streamIn, streamOut, deflateWork;
@@ -328,6 +328,8 @@ int launch_decoder(g4_context* ctx, int codecId, DecodeArgs& a, int nCtas) {
         fast.side = ctx->lsopSide.as<int4>();
         fast.exc = ctx->lsopExc.as<uint32_t>();
         fast.resid = ctx->lsopResid.as<uint8_t>();
+        if (lsop_fast_stage_bytes(ctx->smCount)) CK(ctx->lsopStage.ensure(lsop_fast_stage_bytes(ctx->smCount)));
+        fast.textStage = ctx->lsopStage.as<uint8_t>();
       }
       CK(launch_lsop_decode(a, ctx->coef.as<float>(), ctx->lsopMeta.as<uint8_t>(), ctx->defer.as<int>(), ctx->counters.as<int>() + 56,
                             nCtas, nTiles, ctx->stream, ctx->lsopStream, ctx->lsopEv, &nLaunch, useFast ? &fast : nullptr, ctx->smCount));
@@ -630,7 +632,7 @@ void g4_context_destroy(g4_context* ctx) {
   }
   for (auto& b : ctx->slots) b.release();
   DevBuf* bufs[] = {&ctx->candLens, &ctx->candPreds, &ctx->candStatus, &ctx->counters, &ctx->scratch, &ctx->lists, &ctx->src,
-                    &ctx->total, &ctx->coef, &ctx->defer, &ctx->lsopMeta, &ctx->lsopSide, &ctx->lsopExc, &ctx->lsopResid, &ctx->wide, &ctx->encScratch, &ctx->region, &ctx->jobLen, &ctx->jobOff, &ctx->jobOut, &ctx->jobTotal,
+                    &ctx->total, &ctx->coef, &ctx->defer, &ctx->lsopMeta, &ctx->lsopSide, &ctx->lsopExc, &ctx->lsopResid, &ctx->lsopStage, &ctx->wide, &ctx->encScratch, &ctx->region, &ctx->jobLen, &ctx->jobOff, &ctx->jobOut, &ctx->jobTotal,
                     &ctx->streamIn, &ctx->streamOut, &ctx->deflateWork, &ctx->stSorted, &ctx->stRank, &ctx->stTable,
                     &ctx->stWork, &ctx->stCounters, &ctx->rcPos, &ctx->rcOff, &ctx->rcLen, &ctx->rcCrc, &ctx->rcStored, &ctx->rcTotal,
                     &ctx->rcData, &ctx->rcOffsets, &ctx->rcLens, &ctx->rcIndex, &ctx->rcStatus, &ctx->rcOut, &ctx->sGrid, &ctx->sArena, &ctx->sOffsets, &ctx->sLens, &ctx->sCodec, &ctx->sPred, &ctx->sStatus};

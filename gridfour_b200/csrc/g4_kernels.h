@@ -167,6 +167,7 @@ struct LsopFastArgs {
   int4* side;         // [nTiles][R]: {v[r][0], v[r][1], D2[r], D1[r]}
   uint32_t* exc;      // [nTiles][128]: residuals that are no byte
   uint8_t* resid;     // residual scratch (lsop_fast_resid_bytes)
+  uint8_t* textStage; // staging slots of the text kernel, one area per persistent CTA (lsop_fast_stage_bytes)
   int* defer;         // tiles for the general kernels
   int* deferCount;
   LsopFastGeom g;
@@ -174,6 +175,7 @@ struct LsopFastArgs {
 bool lsop_fast_geometry(const g4_band_desc& band, const void* grid, LsopFastGeom* out);
 size_t lsop_fast_side_bytes(const LsopFastGeom& g, int nTiles);
 size_t lsop_fast_exc_bytes(int nTiles);
+size_t lsop_fast_stage_bytes(int smCount);
 size_t lsop_fast_resid_bytes(const LsopFastGeom& g, int nTiles);
 cudaError_t launch_lsop_decode_fast(const LsopFastArgs& A, int nTilesUpper, int smCount, int* textCounter, cudaStream_t s, int* launches);
 // fast: scratch of the fast path (side / exc / resid / g filled in), or null -> the round-1 kernels only

@@ -46,6 +46,14 @@ constexpr int kTextThreads = 512;
 constexpr uint32_t kTextSubBits = 320;        // target sub-sequence size of the text kernel: one sub-sequence per thread for a 180x240 tile
 constexpr int kExcWords = 128;               // per tile: [0] count, [2+2i] interior index, [3+2i] value
 constexpr int kExcCap = (kExcWords - 2) / 2;  // 63 exceptions; more -> general path
+// Staged form of the text decode (lsop_text_decode below): measured on the config-3 shard it executes fewer instructions
+// (0.79 G against 0.86 G warp instructions) but runs 1.43 ms against 1.25 ms -- its one long pass between two barriers leaves the
+// SM idle at the barrier (4.5 barrier stalls per issue).  Kept for reference, off by default.
+#ifndef G4_TEXT_STAGED
+#define G4_TEXT_STAGED 0
+#endif
+constexpr bool kTextStaged = G4_TEXT_STAGED != 0;
+constexpr uint32_t kTextStageBytes = 256u * 1024u;  // staging slots of one text CTA (global memory, L2 resident)
 constexpr int kResidGuard = 256;             // bytes in front of the first tile of the residual scratch
 constexpr float kMagicHalf = 6291456.0f;     // 1.5 * 2^22
 constexpr float kMagicHalfUp = 6291456.5f;   // 1.5 * 2^22 + 1/2
@@ -306,6 +314,246 @@ struct ByteTileSink {
   }
 };
 
+// ---- staged text decode -------------------------------------------------------------------------------------------
+// canon_fast_decode_text decodes every bit at least twice: once to COUNT the values of each sub-sequence (their output
+// positions are a prefix sum of the counts) and once to write them.  Here the counting pass also keeps the symbol
+// bytes it sees: each sub-sequence has a fixed slot in a per-CTA staging area (global memory, a few hundred bytes per
+// slot, re-used tile after tile and therefore L2 resident), and after the prefix sum the bytes are COPIED from the
+// slot to their place in the tile image instead of being decoded again.  Sub-sequences that hold a value that is no
+// byte (escape, null) are walked once more by text_exceptions_sub, which records the exception list entries.
+constexpr int kSubRare = 4;  // S.eot[] flag: the sub-sequence holds an escape or a null
+
+// Like canon_fast_count; additionally stores the symbol byte of every counted value to slot[0 ..) (4-byte words).
+__device__ __forceinline__ void text_stage_sub(const CanonFastShared& S, uint32_t nBits, uint32_t start, uint32_t limit, uint32_t* slot,
+                                               uint32_t* endOut, uint32_t* cntOut, int* flagOut) {
+  BitCursor cur;
+  cur.init(S, start, limit);
+  uint32_t c = 0, end;
+  int flag = 0;
+  uint64_t q = 0;
+  uint32_t qc = 0;
+  uint32_t* wp = slot;
+  for (;;) {
+    if (cur.rem >= kFastLutBits) {
+      const uint32_t m = S.mlut[cur.peek() & ((1u << kFastLutBits) - 1u)];
+      const uint32_t n = m >> 28;
+      if (n) {
+        cur.skip(S, (m >> 24) & 15u);
+        c += n;
+        q |= uint64_t(m & 0xffffffu) << (8 * qc);
+        qc += n;
+        if (qc >= 4) { *wp++ = uint32_t(q); q >>= 32; qc -= 4; }
+        continue;
+      }
+    }
+    const uint32_t e = S.lut[cur.peek() & ((1u << kFastLutBits) - 1u)];
+    uint32_t byte;
+    if (e - 1u < 0x7fffu) {  // LUT hit on a plain value: e = sym | len << 9
+      if (cur.rem <= 0) { end = cur.pos(limit); break; }
+      cur.skip(S, e >> 9);
+      byte = e & 0xffu;
+    } else {
+      const uint32_t p0 = cur.pos(limit);
+      uint32_t after;
+      const int sym = canon_fast_rare_symbol(S, e, p0, nBits, &after);
+      if (sym < 0) { flag = 2; end = p0; break; }
+      if (sym == kSymEsc2 || sym == kSymEsc8) {
+        after += sym == kSymEsc2 ? 2u : 8u;
+        if (after > nBits) { flag = 2; end = p0; break; }
+        flag |= kSubRare;
+        cur.init(S, after, limit);
+        continue;
+      }
+      if (p0 >= limit) { end = p0; break; }
+      if (sym == kSymEot) { flag |= 1; end = after; break; }
+      if (sym == kSymNull) { flag |= kSubRare; byte = 0u; }
+      else byte = uint32_t(sym);  // a byte value with a code longer than the LUT
+      cur.init(S, after, limit);
+    }
+    c++;
+    q |= uint64_t(byte) << (8 * qc);
+    qc += 1;
+    if (qc >= 4) { *wp++ = uint32_t(q); q >>= 32; qc -= 4; }
+  }
+  if (qc) *wp = uint32_t(q);
+  *endOut = end;
+  *cntOut = c;
+  *flagOut = flag;
+}
+
+// Exception-list entries of one sub-sequence whose values start at interior index k0 (the bytes are in the image).
+__device__ __noinline__ void text_exceptions_sub(const CanonFastShared& S, uint32_t nBits, uint32_t start, uint32_t limit, uint32_t k0,
+                                                 uint8_t* tile, uint32_t* exc, int w, int L, int nB4, int rpg) {
+  auto image_offset = [&](uint32_t k) {
+    const int rr = int(k) / w, cc = int(k) - rr * w, gi = rr / rpg, l = 2 + rr - gi * rpg;
+    return uint32_t(l) * uint32_t(L) + 4u + uint32_t(gi) * uint32_t(nB4) + uint32_t(cc);
+  };
+  auto add = [&](uint32_t k, int32_t v) {
+    const uint32_t slot = atomicAdd(exc, 1u);
+    if (slot < uint32_t(kExcCap)) {
+      exc[2 + 2 * slot] = k;
+      exc[3 + 2 * slot] = uint32_t(v);
+    }
+  };
+  SmemBitSrc src{S.sw, nBits};
+  uint32_t pos = start, k = k0, pk = 0;
+  bool pending = false;
+  int32_t pv = 0;
+  for (;;) {
+    const uint32_t e = S.lut[src.peek32(pos) & ((1u << kFastLutBits) - 1u)];
+    int sym;
+    uint32_t after;
+    if (e - 1u < 0x7fffu) { sym = int(e & 0xffu); after = pos + (e >> 9); }
+    else {
+      sym = canon_fast_rare_symbol(S, e, pos, nBits, &after);
+      if (sym < 0) break;
+    }
+    if (sym == kSymEsc2 || sym == kSymEsc8) {  // extends the value before it (CanonicalHuffman.java:495-504): v = (v << nb) | bits
+      const int nb = sym == kSymEsc2 ? 2 : 8;
+      if (after + nb > nBits || k == k0) break;
+      if (!pending) {
+        pk = k - 1;
+        const uint32_t o = image_offset(pk);
+        if (tile[o] != 0u || true) pv = int32_t(tile[o]) - 128;
+        tile[o] = 0;
+        pending = true;
+      }
+      pv = int32_t((uint32_t(pv) << nb) | src.bits(after, nb));
+      after += nb;
+    } else {
+      if (pending) { add(pk, pv); pending = false; }
+      if (pos >= limit || sym == kSymEot) break;
+      if (sym == kSymNull) add(k, INT32_MIN);
+      k++;
+    }
+    pos = after;
+  }
+  if (pending) add(pk, pv);
+}
+
+// Decodes the interior text (tables and LUT ready, text at bit T0) into the tile image.  All kTextThreads threads call.
+// Returns 0 = done, 1 = malformed stream, 2 = the staging slots are too small for this code (caller defers the tile).
+__device__ int lsop_text_decode(CanonFastShared& S, uint32_t nBits, const uint32_t T0, uint32_t nInterior, uint8_t* stage,
+                                uint32_t stageBytes, ByteTileSink sink) {
+  constexpr int NT = kTextThreads;
+  constexpr int kRounds = kFastMaxSub / NT;
+  const int tid = threadIdx.x;
+  const uint32_t avail = nBits - T0;
+  uint32_t rounds = (avail / kTextSubBits + NT - 1) / NT;
+  if (rounds < 1u) rounds = 1u;
+  if (rounds > uint32_t(kRounds)) rounds = kRounds;
+  uint32_t B = (avail + rounds * NT - 1) / (rounds * NT);
+  if (B < 96u) B = 96u;
+  const int nSub = int((avail + B - 1) / B);
+  // slot size: a sub-sequence spans at most B + 84 bits (it ends with the first value that starts at or after its
+  // limit, and it may start up to one value late), every counted value has a code of at least minLen bits
+  uint32_t minLen = 1;
+  while (minLen < 15u && S.count[minLen] == 0) minLen++;
+  const uint32_t slotBytes = (((B + 192u) / minLen + 8u) + 15u) & ~15u;
+  if (uint64_t(slotBytes) * uint64_t(nSub) > stageBytes) return 2;
+  if (tid == 0) S.firstEot = nSub;
+  // pass 0: only the END of every sub-sequence matters here, so start kFastLookback bits before the limit and rely on
+  // self-synchronisation; sub-sequence 0 starts at the true text start.
+#pragma unroll 1
+  for (int i = tid; i < nSub; i += NT) {
+    uint32_t limit = T0 + uint32_t(i + 1) * B;
+    if (limit > nBits) limit = nBits;
+    uint32_t from = T0 + uint32_t(i) * B;
+    if (limit - from > kFastLookback) from = limit - kFastLookback;  // sub-sequence 0 as well: every thread does the same amount
+    uint32_t e, c;
+    int f;
+    canon_fast_count(S, nBits, from, limit, &e, &c, &f);
+    S.endpos[i] = e;
+    S.startv[i] = 0xffffffffu;  // forces the exact decode of every sub-sequence in the first pass below
+  }
+  // synchronisation passes: sub-sequence i must start where i-1 ended (see canon_fast_decode_text)
+  volatile uint32_t* vend = S.endpos;
+  __syncthreads();
+  for (int pass = 0; pass <= nSub; pass++) {
+    bool any = false;
+#pragma unroll 1
+    for (int i = tid; i < nSub; i += NT) {
+      const uint32_t ns = i ? vend[i - 1] : T0;
+      if (ns != S.startv[i]) {
+        S.startv[i] = ns;
+        uint32_t limit = T0 + uint32_t(i + 1) * B;
+        if (limit > nBits) limit = nBits;
+        uint32_t e, c;
+        int f;
+        text_stage_sub(S, nBits, ns, limit, reinterpret_cast<uint32_t*>(stage + size_t(i) * slotBytes), &e, &c, &f);
+        vend[i] = e;
+        S.cnt[i] = uint16_t(c);
+        S.eot[i] = uint8_t(f);
+        any = true;
+      }
+    }
+    if (!__syncthreads_or(any ? 1 : 0)) break;
+  }
+#pragma unroll 1
+  for (int i = tid; i < nSub; i += NT)
+    if (S.eot[i] & 3) atomicMin(&S.firstEot, i);
+  __syncthreads();
+  const int fe = S.firstEot;
+  if (fe == nSub || (S.eot[fe] & 3) == 2) return 1;  // no end-of-text, an invalid code, or the data ended early
+  // value offsets: thread tid owns sub-sequences tid*kRounds .. +kRounds-1 for the scan
+  uint32_t mySum = 0;
+#pragma unroll
+  for (int j = 0; j < kRounds; j++) {
+    const int i = tid * kRounds + j;
+    mySum += (i <= fe && i < nSub) ? S.cnt[i] : 0u;
+  }
+  uint32_t total;
+  const uint32_t ex = block_exclusive_scan<NT>(mySum, S.scan, &total);
+  if (total != nInterior) return 1;
+  uint32_t* offv = S.endpos;  // end positions are no longer needed: the array now holds the first value index of every sub-sequence
+  {
+    uint32_t run = ex;
+#pragma unroll
+    for (int j = 0; j < kRounds; j++) {
+      const int i = tid * kRounds + j;
+      if (i < nSub) {
+        offv[i] = run;
+        run += (i <= fe) ? S.cnt[i] : 0u;
+      }
+    }
+  }
+  __syncthreads();
+  // copy pass: slot -> image
+#pragma unroll 1
+  for (int i = tid; i <= fe; i += NT) {
+    const uint32_t n = S.cnt[i];
+    if (n == 0) continue;
+    const uint4* sp = reinterpret_cast<const uint4*>(stage + size_t(i) * slotBytes);
+    sink.begin(offv[i]);
+    // the slot's words are fetched four 16-byte pieces at a time, all four loads in flight before the first is used
+    for (uint32_t done = 0; done < n; done += 64u) {
+      uint4 x[4];
+#pragma unroll
+      for (int v = 0; v < 4; v++) x[v] = done + 16u * v < n ? __ldcg(sp + v) : make_uint4(0, 0, 0, 0);
+      sp += 4;
+#pragma unroll
+      for (int v = 0; v < 4; v++) {
+        const uint32_t xs[4] = {x[v].x, x[v].y, x[v].z, x[v].w};
+#pragma unroll
+        for (int j = 0; j < 4; j++) {
+          const uint32_t at = done + 16u * v + 4u * j;
+          if (at < n) {
+            const uint32_t m = n - at;
+            sink.push(m >= 4u ? xs[j] : (xs[j] & ((1u << (8 * m)) - 1u)), m >= 4u ? 4 : int(m));
+          }
+        }
+      }
+    }
+    sink.end();
+    if (S.eot[i] & kSubRare) {
+      uint32_t limit = T0 + uint32_t(i + 1) * B;
+      if (limit > nBits) limit = nBits;
+      text_exceptions_sub(S, nBits, S.startv[i], limit, offv[i], sink.tile, sink.exc, sink.w, sink.L, sink.nB4, sink.rpg);
+    }
+  }
+  return 0;
+}
+
 __global__ void __launch_bounds__(kTextThreads, 2) lsop2_text_kernel(LsopFastArgs A, uint32_t stageWords, int listBegin, int listEnd) {
   extern __shared__ __align__(128) unsigned char textSmem[];
   CanonFastShared& F = *reinterpret_cast<CanonFastShared*>(textSmem);
@@ -357,18 +605,26 @@ __global__ void __launch_bounds__(kTextThreads, 2) lsop2_text_kernel(LsopFastArg
     if (nBulk) mbar_wait(bar, parity);
     parity ^= nBulk ? 1u : 0u;
     __syncthreads();
+    int rc = ok ? 0 : 1;
     if (ok) {
-      uint32_t endBit = 0, nv = 0;
       const uint32_t nInterior = uint32_t(A.g.R - 2) * uint32_t(A.g.C - 4);
       ByteTileSink sink;
       sink.init(tileImg, A.exc + size_t(tIdx) * kExcWords, A.g);
-      ok = canon_fast_decode_text<ByteTileSink, kTextThreads, kTextSubBits>(F, span * 8u, T0 + 8u * delta, nInterior, 0u, sink, &endBit, &nv) &&
-           nv == nInterior;
+      if (kTextStaged) rc = lsop_text_decode(F, span * 8u, T0 + 8u * delta, nInterior, A.textStage + size_t(blockIdx.x) * kTextStageBytes, kTextStageBytes, sink);
+      else {
+        uint32_t endBit = 0, nv = 0;
+        rc = (canon_fast_decode_text<ByteTileSink, kTextThreads, kTextSubBits>(F, span * 8u, T0 + 8u * delta, nInterior, 0u, sink, &endBit, &nv) &&
+              nv == nInterior) ? 0 : 1;
+      }
+      ok = rc == 0;
     }
     __syncthreads();
     if (tid == 0) {
-      if (!ok) a.status[tIdx] = G4_ERR_FORMAT;
-      else if (A.exc[size_t(tIdx) * kExcWords] > uint32_t(kExcCap)) A.defer[atomicAdd(A.deferCount, 1)] = tIdx;  // general kernels
+      if (rc == 1) a.status[tIdx] = G4_ERR_FORMAT;
+      else if (rc == 2 || A.exc[size_t(tIdx) * kExcWords] > uint32_t(kExcCap)) {  // general kernels
+        A.exc[size_t(tIdx) * kExcWords] = uint32_t(kExcCap) + 1u;                  // (the wavefront kernel skips the tile)
+        A.defer[atomicAdd(A.deferCount, 1)] = tIdx;
+      }
       else {
         asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
         uint8_t* dst = A.resid + kResidGuard + size_t(tIdx) * size_t(A.g.tilePitch);
@@ -681,6 +937,7 @@ bool lsop_fast_geometry(const g4_band_desc& band, const void* grid, LsopFastGeom
 }
 size_t lsop_fast_side_bytes(const LsopFastGeom& g, int nTiles) { return size_t(nTiles) * size_t(g.R) * sizeof(int4); }
 size_t lsop_fast_exc_bytes(int nTiles) { return size_t(nTiles) * kExcWords * sizeof(uint32_t); }
+size_t lsop_fast_stage_bytes(int smCount) { return kTextStaged ? size_t(smCount) * 2 * size_t(kTextStageBytes) : 0; }
 size_t lsop_fast_resid_bytes(const LsopFastGeom& g, int nTiles) { return size_t(kResidGuard) + size_t(nTiles) * size_t(g.tilePitch) + size_t(g.tileBytes) + 4096; }
 
 // Kernels H, T and W over the list positions [0, nTilesUpper).  Tiles the fast path cannot take are appended to
