@@ -94,6 +94,20 @@ int g4o_length_encode(int n, const int* codeLen, int* codes, int* runs) {
 int g4o_lsop12_coefficients(int nr, int nc, const int32_t* v, double* ud) {
   return lsop12_coefficients(nr, nc, v, ud) ? 1 : 0;
 }
+int g4o_lsop12_residual_streams(int nr, int nc, const int32_t* v, int32_t* seed, float* u, uint8_t* initCodes, long* nInit,
+                                uint8_t* interiorCodes, long* nInterior) {
+  G4O_TRY return lsop12_residual_streams(nr, nc, v, seed, u, initCodes, nInit, interiorCodes, nInterior) ? 1 : 0; G4O_CATCH(-1)
+}
+// Huffman decode that starts at bit *bitpos of `in` (two streams back to back in one bit store, LsDecoder12.java:119-124)
+int g4o_huffman_decode_at(const uint8_t* in, long nbytes, int nsym, uint8_t* out, long* bitpos) {
+  G4O_TRY
+  BitIn b(in, size_t(nbytes));
+  b.iBit = *bitpos;
+  huffman_decode(b, nsym, out);
+  *bitpos = long(b.position());
+  return 0;
+  G4O_CATCH(-1)
+}
 int32_t g4o_java_round(float a) { return java_round_float(a); }
 uint32_t g4o_crc32c(const uint8_t* p, long n) { return crc32c(p, size_t(n)); }
 

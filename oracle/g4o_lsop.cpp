@@ -354,3 +354,21 @@ void codec_lsop12_decode(int nRows, int nCols, const uint8_t* packing, size_t le
 }
 
 }  // namespace g4o
+
+// Test infrastructure: the predictor half of LsOptimalPredictor12.encode (:109-292) on its own -- seed, the twelve float32
+// coefficients and the two M32-coded residual streams (LsOptimalPredictorResult.java:44-76).  Returns false where encode
+// returns null.  Buffers must hold 6 bytes per residual.
+namespace g4o {
+bool lsop12_residual_streams(int nRows, int nCols, const int32_t* v, int32_t* seed, float u[12], uint8_t* initCodes, long* nInit,
+                             uint8_t* interiorCodes, long* nInterior) {
+  LsResult R;
+  if (!ls_predict(nRows, nCols, v, R)) return false;
+  *seed = R.seed;
+  for (int i = 0; i < 12; i++) u[i] = R.u[i];
+  std::copy(R.initCodes.begin(), R.initCodes.end(), initCodes);
+  std::copy(R.interiorCodes.begin(), R.interiorCodes.end(), interiorCodes);
+  *nInit = long(R.initCodes.size());
+  *nInterior = long(R.interiorCodes.size());
+  return true;
+}
+}  // namespace g4o

@@ -148,7 +148,9 @@ int length_encode(int n, const int* codeLen, int* codes, int* runs);            
 // ---------------------------------------------------------------------------------------------
 // LSOP12 (C/lsop/*.java, C/util/jama/LUDecomposition.java)
 // ---------------------------------------------------------------------------------------------
-bool lsop12_coefficients(int nRows, int nCols, const int32_t* values, double ud[12]);  // LsOptimalPredictor12.java:311-383
+bool lsop12_coefficients(int nRows, int nCols, const int32_t* values, double ud[12]);
+bool lsop12_residual_streams(int nRows, int nCols, const int32_t* v, int32_t* seed, float u[12], uint8_t* initCodes, long* nInit,
+                             uint8_t* interiorCodes, long* nInterior);  // LsOptimalPredictor12.java:109-292 (test infrastructure)  // LsOptimalPredictor12.java:311-383
 int32_t java_round_float(float a);                                                     // StrictMath.round(float)
 uint32_t crc32c(const uint8_t* p, size_t n);                                           // C/util/GridfourCRC32C.java
 

@@ -185,6 +185,31 @@ def lsop12_coefficients(tile):
     return ud if ok else None
 
 
+def lsop12_residual_streams(tile):
+    """(seed, 12 float32 coefficients, initializer M32 bytes, interior M32 bytes) of LsOptimalPredictor12.encode, or None."""
+    t = _i32(tile)
+    nr, nc = t.shape
+    seed = C.c_int32(0)
+    u = np.zeros(12, np.float32)
+    a, b = np.zeros(t.size * 6 + 64, np.uint8), np.zeros(t.size * 6 + 64, np.uint8)
+    na, nb = C.c_long(0), C.c_long(0)
+    ok = lib().g4o_lsop12_residual_streams(nr, nc, _p(t), C.byref(seed), _p(u), _p(a), C.byref(na), _p(b), C.byref(nb))
+    if ok != 1:
+        return None
+    return seed.value, u, a[: na.value].tobytes(), b[: nb.value].tobytes()
+
+
+def huffman_decode_at(data, nsym, bitpos):
+    """Legacy Huffman decode of nsym symbols starting at bit `bitpos`; returns (symbols, bit position after the stream)."""
+    b = _u8(data)
+    out = np.zeros(max(1, nsym), np.uint8)
+    pos = C.c_long(bitpos)
+    rc = lib().g4o_huffman_decode_at(_p(b), C.c_long(b.size), C.c_int(nsym), _p(out), C.byref(pos))
+    if rc:
+        raise ValueError("huffman decode failed")
+    return out[:nsym].tobytes(), pos.value
+
+
 def java_round(x):
     return lib().g4o_java_round(C.c_float(x))
 

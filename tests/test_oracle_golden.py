@@ -111,3 +111,116 @@ def test_java_round(oracle):
 
 def test_crc32c_known_answer(oracle):
     assert oracle.crc32c(b"123456789") == 0xE3069283  # CRC-32C (Castagnoli) check value
+
+
+# ---- encode-side pins: what the reference's own sample files fix about the ENCODERS (README.txt:26-55) -------------------
+# No reference test holds an encoder's output, but the sample files do: their payloads were written by the Java encoders,
+# and the closed-form grids they were written from are documented.  Re-encoding those grids must give the same bytes.
+
+def sample14_grid():
+    exp = np.zeros((101, 101), np.int32)
+    for r in range(101):
+        for c in range(101):
+            z = math.sin(c / 100.0 * math.pi) * math.sin(r / 100.0 * math.pi)
+            exp[r, c] = math.floor(z * 1000.0 + 0.5)
+    return exp
+
+
+def sample14_parts():
+    """Legacy LsHeader (LsHeader.java:139-160): [codecIndex][12][seed][12 x float32][nInit][nInterior][type]."""
+    p = bytes.fromhex(GOLD["Sample14_LSOP"]["tiles"]["0"])
+    assert p[1] == 12
+    seed = int.from_bytes(p[2:6], "little", signed=True)
+    coef = np.frombuffer(p[6:54], dtype="<f4")
+    n_init = int.from_bytes(p[54:58], "little")
+    n_interior = int.from_bytes(p[58:62], "little")
+    assert p[62] & 0x0F == 0  # COMPRESSION_TYPE_HUFFMAN
+    return p, seed, coef, n_init, n_interior, p[63:]
+
+
+def test_sample14_pins_lsop_coefficients(oracle):
+    """L2 / L2b: the twelve coefficients the JVM computed for Sample14 are in its header; the oracle's FP64 normal equations
+    + JAMA LU + float cast must give the same 48 bytes."""
+    _p, seed, coef, _ni, _nn, _body = sample14_parts()
+    got = oracle.lsop12_residual_streams(sample14_grid())
+    assert got is not None
+    assert got[0] == seed
+    assert got[1].astype("<f4").tobytes() == coef.tobytes()
+
+
+def test_sample14_pins_residual_streams_and_huffman_bits(oracle):
+    """L1 / L3 / M1 / H1 / H2: the fixture's two legacy-Huffman streams decode to the M32 bytes of the initializer and
+    interior residuals; the oracle's predictor must produce the same bytes, and re-encoding them with the oracle's
+    HuffmanEncoder must reproduce the fixture's bits (tree shape, tie-breaking, code assignment)."""
+    _p, _seed, _coef, n_init, n_interior, body = sample14_parts()
+    init_m32, pos1 = oracle.huffman_decode_at(body, n_init, 0)
+    inter_m32, pos2 = oracle.huffman_decode_at(body, n_interior, pos1)
+    assert (n_init, n_interior) == (597, 9603)
+    assert len(body) == (pos2 + 7) // 8
+    got = oracle.lsop12_residual_streams(sample14_grid())
+    assert got[2] == init_m32 and got[3] == inter_m32
+    bits = np.unpackbits(np.frombuffer(body, np.uint8), bitorder="little")
+    e1, nb1 = oracle.huffman_encode(init_m32)
+    e2, nb2 = oracle.huffman_encode(inter_m32)
+    assert (nb1, nb2) == (pos1, pos2 - pos1)
+    assert np.array_equal(np.unpackbits(np.frombuffer(e1, np.uint8), bitorder="little")[:nb1], bits[:pos1])
+    assert np.array_equal(np.unpackbits(np.frombuffer(e2, np.uint8), bitorder="little")[:nb2], bits[pos1:pos2])
+
+
+@pytest.mark.parametrize("sample", ["Sample04_ShortComp", "Sample05_IntComp", "Sample07_ICFComp"])
+def test_deflate_fixtures_pin_the_encoder(oracle, sample):
+    """D1 + P1-P3 + M1: CodecDeflate.encode of the documented grid reproduces the JDK-written packing byte for byte
+    (predictor choice, M32 stream, zlib level 6 -- system zlib 1.3 and the JDK's zlib agree on these inputs)."""
+    s = GOLD[sample]
+    for k, hexs in s["tiles"].items():
+        want = bytes.fromhex(hexs)
+        tile = expected_tile(sample, int(k)).astype(np.int32)
+        got, pred = oracle.codec_encode_i32(CODEC_IDS["GvrsDeflate"], want[0], tile)
+        assert pred == want[1]
+        assert got == want, "tile %s: %d vs %d bytes" % (k, len(got), len(want))
+
+
+def float_planes(tile):
+    """CodecFloat.encodeFloats (:328-392): sign bitmap, exponents, three mantissa byte planes as row-wise differences."""
+    bits = np.ascontiguousarray(tile, dtype="<f4").view("<u4")
+    nr, nc = bits.shape
+    sign = np.packbits((bits >> 31).astype(np.uint8).ravel(), bitorder="little").tobytes()
+    expo = ((bits >> 23) & 0xFF).astype(np.uint8).tobytes()
+    planes = [sign, expo]
+    for shift, mask in ((16, 0x7F), (8, 0xFF), (0, 0xFF)):
+        v = ((bits >> shift) & mask).astype(np.int32)
+        d = np.empty_like(v)
+        d[:, 1:] = v[:, 1:] - v[:, :-1]
+        d[0, 0] = v[0, 0]
+        d[1:, 0] = v[1:, 0] - v[:-1, 0]
+        planes.append((d & 0xFF).astype(np.uint8).tobytes())
+    return planes
+
+
+def test_float_fixture_pins_the_plane_split(oracle):
+    """F1: Sample06 predates Deflater(9) (its planes are 78 9c level-6 streams), so the whole packing cannot be
+    reproduced by today's CodecFloat -- but every plane must inflate to exactly the bytes the documented split gives,
+    and recompressing those bytes at level 6 must reproduce the stored stream."""
+    import zlib
+
+    s = GOLD["Sample06_FltComp"]
+    for k, hexs in s["tiles"].items():
+        p = bytes.fromhex(hexs)
+        tile = expected_tile("Sample06_FltComp", int(k)).astype(np.float32)
+        want = float_planes(tile)
+        off = 2
+        for i in range(5):
+            n = int.from_bytes(p[off:off + 4], "little")
+            stream = p[off + 4:off + 4 + n]
+            off += 4 + n
+            assert stream[:2] == b"\x78\x9c"
+            assert zlib.decompress(stream) == want[i], "tile %s plane %d" % (k, i)
+            assert zlib.compress(want[i], 6) == stream, "tile %s plane %d (level 6)" % (k, i)
+        assert off == len(p)
+        # and the oracle's own packing (level 9) carries the same planes
+        q = oracle.codec_encode_f32(p[0], tile)
+        off = 2
+        for i in range(5):
+            n = int.from_bytes(q[off:off + 4], "little")
+            assert zlib.decompress(q[off + 4:off + 4 + n]) == want[i]
+            off += 4 + n
