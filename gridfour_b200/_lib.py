@@ -23,7 +23,7 @@ EXPORTS = [
     "g4_context_create", "g4_context_destroy", "g4_context_synchronize", "g4_encode_i32", "g4_decode_i32",
     "g4_encode_f32", "g4_decode_f32", "g4_encode_tiles", "g4_decode_tiles", "g4_encode_arena_bound",
     "g4_fill_terrain", "g4_launch_count", "g4_context_set_timing", "g4_kernel_time_ms", "g4_codec_supported",
-    "g4_crc32c", "g4_tile_records_bound", "g4_pack_tile_records", "g4_unpack_tile_records",
+    "g4_crc32c", "g4_tile_records_bound", "g4_pack_tile_records", "g4_unpack_tile_records", "g4_context_order_stream", "g4_decode_tiles_bounded",
 ]
 
 
@@ -55,6 +55,7 @@ def lib():
         L.g4_context_create.argtypes = [C.c_int, C.c_void_p, C.POINTER(C.c_void_p)]
         L.g4_context_destroy.argtypes = [C.c_void_p]
         L.g4_context_synchronize.argtypes = [C.c_void_p]
+        L.g4_context_order_stream.argtypes = [C.c_void_p, C.c_void_p, C.c_int]
         L.g4_launch_count.argtypes = [C.c_void_p]
         L.g4_launch_count.restype = C.c_uint64
         L.g4_encode_arena_bound.argtypes = [C.POINTER(BandDesc)]
@@ -70,6 +71,8 @@ def lib():
                                       C.POINTER(C.c_uint64)]
         L.g4_decode_tiles.argtypes = [C.c_void_p, C.POINTER(CodecList), C.POINTER(BandDesc), C.c_int, C.c_void_p, C.c_void_p,
                                       C.c_void_p, C.c_void_p, C.c_void_p]
+        L.g4_decode_tiles_bounded.argtypes = [C.c_void_p, C.POINTER(CodecList), C.POINTER(BandDesc), C.c_int, C.c_void_p, C.c_uint64,
+                                              C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p]
         L.g4_fill_terrain.argtypes = [C.c_void_p, C.c_int, C.c_uint64, C.c_int64, C.c_int64, C.c_int64, C.c_int64, C.c_void_p]
         L.g4_context_set_timing.argtypes = [C.c_void_p, C.c_int]
         L.g4_kernel_time_ms.argtypes = [C.c_void_p, C.c_int, C.c_int]

@@ -7,6 +7,7 @@ Reference (paths under /root/reference/core/src/main/java/org/gridfour/):
 Everything that touches sample data is a call into libg4codec.so (CUDA); nothing is computed in Python.
 """
 import ctypes as C
+import threading
 
 import numpy as np
 
@@ -18,9 +19,11 @@ INT4_NULL_CODE = -(2 ** 31)  # util/GridfourConstants.java:61
 
 
 class Context:
-    """One CUDA stream + scratch (g4_context).  Not shareable between threads."""
+    """One CUDA stream + scratch (g4_context).  Not shareable between threads: Context.default() hands every THREAD its
+    own context per device (the reference enters one decoder instance from the application thread and from the
+    read-ahead thread, TileDecompressionAssistant.java:88; here each of them works on its own stream and scratch)."""
 
-    _default = {}
+    _default = threading.local()
 
     def __init__(self, device=0, stream=None):
         self._h = C.c_void_p()
@@ -30,9 +33,27 @@ class Context:
 
     @classmethod
     def default(cls, device=0):
-        if device not in cls._default:
-            cls._default[device] = cls(device)
-        return cls._default[device]
+        table = getattr(cls._default, "table", None)
+        if table is None:
+            table = cls._default.table = {}
+        if device not in table:
+            table[device] = cls(device)
+        return table[device]
+
+    def after_torch_stream(self, device):
+        """Device tensors produced by kernels still pending on torch's current stream are complete before this context's
+        next launch (g4_context_order_stream, events only)."""
+        import torch
+
+        check(_lib.lib().g4_context_order_stream(self._h, C.c_void_p(torch.cuda.current_stream(device).cuda_stream), 1),
+              "g4_context_order_stream")
+
+    def before_torch_stream(self, device):
+        """torch's current stream continues only after everything this context has launched so far."""
+        import torch
+
+        check(_lib.lib().g4_context_order_stream(self._h, C.c_void_p(torch.cuda.current_stream(device).cuda_stream), 0),
+              "g4_context_order_stream")
 
     def synchronize(self):
         check(_lib.lib().g4_context_synchronize(self._h))
@@ -367,9 +388,12 @@ class CodecMaster:
         codec = torch.empty(nT, dtype=torch.uint8, device=dev)
         pred = torch.empty(nT, dtype=torch.uint8, device=dev)
         status = torch.empty(nT, dtype=torch.int32, device=dev)
-        st = L.g4_encode_tiles(self._context()._h, C.byref(cl), C.byref(band), G4_MEM_DEVICE, grid.data_ptr(), arena.data_ptr(), cap,
+        ctx = self._context()
+        ctx.after_torch_stream(dev)  # `grid` may come from kernels still queued on torch's stream
+        st = L.g4_encode_tiles(ctx._h, C.byref(cl), C.byref(band), G4_MEM_DEVICE, grid.data_ptr(), arena.data_ptr(), cap,
                                offsets.data_ptr(), lens.data_ptr(), codec.data_ptr(), pred.data_ptr(), status.data_ptr(),
                                C.byref(total))
+        ctx.before_torch_stream(dev)
         check(st, "g4_encode_tiles")
         return TileBatch(arena, offsets, lens, codec, pred, status, total.value, band)
 
@@ -407,8 +431,8 @@ class CodecMaster:
             arena = np.ascontiguousarray(batch.arena)
             offsets = np.ascontiguousarray(batch.offsets, dtype=np.uint64)
             lens = np.ascontiguousarray(batch.lens, dtype=np.uint32)
-            st = L.g4_decode_tiles(self._context()._h, C.byref(cl), C.byref(band), G4_MEM_HOST, arena.ctypes.data, offsets.ctypes.data,
-                                   lens.ctypes.data, grid.ctypes.data, status.ctypes.data)
+            st = L.g4_decode_tiles_bounded(self._context()._h, C.byref(cl), C.byref(band), G4_MEM_HOST, arena.ctypes.data, int(arena.size),
+                                           offsets.ctypes.data, lens.ctypes.data, grid.ctypes.data, status.ctypes.data)
             self.lastStatus = status
             check(st, "g4_decode_tiles")
             return grid
@@ -417,8 +441,11 @@ class CodecMaster:
         dt = torch.float32 if band.elem_type == G4_ELEM_F32 else torch.int16 if band.elem_type == G4_ELEM_I16 else torch.int32
         grid = out if out is not None else torch.empty((rows, cols), dtype=dt, device=batch.arena.device)
         status = torch.empty(band.tiles_down * band.tiles_across, dtype=torch.int32, device=batch.arena.device)
-        st = L.g4_decode_tiles(self._context()._h, C.byref(cl), C.byref(band), G4_MEM_DEVICE, batch.arena.data_ptr(),
-                               batch.offsets.data_ptr(), batch.lens.data_ptr(), grid.data_ptr(), status.data_ptr())
+        ctx = self._context()
+        ctx.after_torch_stream(batch.arena.device)  # the payloads and `out` may still be in use on torch's stream
+        st = L.g4_decode_tiles_bounded(ctx._h, C.byref(cl), C.byref(band), G4_MEM_DEVICE, batch.arena.data_ptr(), int(batch.arena.numel()),
+                                       batch.offsets.data_ptr(), batch.lens.data_ptr(), grid.data_ptr(), status.data_ptr())
+        ctx.before_torch_stream(batch.arena.device)
         self.lastStatus = status
         check(st, "g4_decode_tiles")
         return grid

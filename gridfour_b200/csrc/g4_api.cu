@@ -54,6 +54,24 @@ struct DevBuf {
 
 size_t round_up(size_t x, size_t a) { return (x + a - 1) / a * a; }
 
+// Every entry point runs on its context's device and leaves the caller's current device as it found it (hosts that
+// drive several GPUs from one thread -- torch, a JVM -- rely on that).
+struct DeviceGuard {
+  int prev = -1;
+  cudaError_t err = cudaSuccess;
+  explicit DeviceGuard(int device) {
+    if (cudaGetDevice(&prev) != cudaSuccess) prev = -1;
+    if (prev != device) err = cudaSetDevice(device);
+    else prev = -1;
+  }
+  ~DeviceGuard() {
+    if (prev >= 0) cudaSetDevice(prev);
+  }
+};
+#define ENTER(ctx)                                                     \
+  DeviceGuard guard_((ctx)->device);                                  \
+  if (guard_.err != cudaSuccess) return cuda_fail(guard_.err, "cudaSetDevice")
+
 }  // namespace
 
 struct g4_context {
@@ -85,6 +103,7 @@ struct g4_context {
   uint64_t hostTotal = 0;
   int deflateWorkers = 0;   // resident stream-worker threads (0 = default, see g4_context_create)
   uint64_t stagedChunkBytes = 2ull << 30;  // staged zlib encode: input bytes per chunk (scratch = 12x)
+  uint64_t arenaLimit = ~0ull;  // g4_decode_tiles_bounded: bytes addressable behind the arena of the running call
   bool lsopDeflate = true;  // LsEncoder12.deflateEnabled (lsop/LsEncoder12.java:78)
   // staging used by the host-memory entry points
   DevBuf sGrid, sArena, sOffsets, sLens, sCodec, sPred, sStatus;
@@ -92,7 +111,7 @@ struct g4_context {
   cudaStream_t copyIn = nullptr, copyOut = nullptr;
   cudaStream_t lsopStream = nullptr;  // LSOP12 decode: wavefront of chunk k beside kernels H/T of chunk k+1
   cudaEvent_t lsopEv[5] = {};
-  cudaEvent_t evIn[16] = {}, evDone[16] = {}, evStart = nullptr;
+  cudaEvent_t evIn[16] = {}, evDone[16] = {}, evStart = nullptr, evOrder = nullptr;
   // optional per-kernel timing (CUDA events on the launching stream): [0]=decode, [1]=encode, by codec kind
   bool timing = false;
   cudaEvent_t ev[2][G4_CODEC_COUNT + 1][2] = {};
@@ -458,6 +477,7 @@ int decode_device_i32(g4_context* ctx, const g4_codec_list* codecs, const g4_ban
   cl.rawLen = rawShorts ? ((2u * uint32_t(n) + 3u) & ~3u) : uint32_t(n) * 4u;
   cl.codecs = *codecs;
   cl.arena = arena;
+  cl.arenaLen = ctx->arenaLimit;
   cl.offsets = offsets;
   cl.lens = lens;
   cl.lists = ctx->lists.as<int>();
@@ -593,29 +613,54 @@ int g4_context_create(int device, void* cuda_stream, g4_context** out) {
     return G4_ERR_CUDA;
   }
   if (device < 0 || device >= nDev) return G4_ERR_ARG;
-  CK(cudaSetDevice(device));
+  DeviceGuard guard(device);
+  if (guard.err != cudaSuccess) return cuda_fail(guard.err, "cudaSetDevice");
   g4_context* ctx = new g4_context();
   ctx->device = device;
+  auto fail = [&](cudaError_t err, const char* what) {
+    if (ctx->ownStream && ctx->stream) cudaStreamDestroy(ctx->stream);
+    delete ctx;
+    return cuda_fail(err, what);
+  };
   cudaDeviceProp prop;
-  CK(cudaGetDeviceProperties(&prop, device));
+  if ((e = cudaGetDeviceProperties(&prop, device)) != cudaSuccess) return fail(e, "cudaGetDeviceProperties");
   ctx->smCount = prop.multiProcessorCount;
   // resident zlib-stream worker threads: each owns a ~310 KB hash/symbol work area in HBM
   ctx->deflateWorkers = ctx->smCount * 256;
-  if (const char* e = std::getenv("G4_DEFLATE_WORKERS")) { int v = std::atoi(e); if (v >= 32) ctx->deflateWorkers = v; }
-  if (const char* e = std::getenv("G4_STAGED_CHUNK_MB")) { long v = std::atol(e); if (v >= 1) ctx->stagedChunkBytes = uint64_t(v) << 20; }
+  if (const char* ev = std::getenv("G4_DEFLATE_WORKERS")) { int v = std::atoi(ev); if (v >= 32) ctx->deflateWorkers = v; }
+  if (const char* ev = std::getenv("G4_STAGED_CHUNK_MB")) { long v = std::atol(ev); if (v >= 1) ctx->stagedChunkBytes = uint64_t(v) << 20; }
   if (cuda_stream) ctx->stream = static_cast<cudaStream_t>(cuda_stream);
   else {
-    CK(cudaStreamCreateWithFlags(&ctx->stream, cudaStreamNonBlocking));
+    if ((e = cudaStreamCreateWithFlags(&ctx->stream, cudaStreamNonBlocking)) != cudaSuccess) return fail(e, "cudaStreamCreateWithFlags");
     ctx->ownStream = true;
   }
-  CK(cudaEventCreateWithFlags(&ctx->evStart, cudaEventDisableTiming));
+  if ((e = cudaEventCreateWithFlags(&ctx->evStart, cudaEventDisableTiming)) != cudaSuccess) return fail(e, "cudaEventCreateWithFlags");
+  if ((e = cudaEventCreateWithFlags(&ctx->evOrder, cudaEventDisableTiming)) != cudaSuccess) return fail(e, "cudaEventCreateWithFlags");
   *out = ctx;
+  return G4_OK;
+}
+
+// Stream ordering for G4_MEM_DEVICE callers whose buffers are produced / consumed on ANOTHER stream (torch's current
+// stream, a JVM's copy stream): work already queued on `other` completes before anything this context launches next
+// (before = 1), or everything this context has launched so far completes before `other` continues (before = 0).
+int g4_context_order_stream(g4_context* ctx, void* other_stream, int before) {
+  if (!ctx) return G4_ERR_ARG;
+  cudaStream_t other = static_cast<cudaStream_t>(other_stream);
+  if (other == ctx->stream) return G4_OK;
+  ENTER(ctx);
+  if (before) {
+    CK(cudaEventRecord(ctx->evOrder, other));
+    CK(cudaStreamWaitEvent(ctx->stream, ctx->evOrder, 0));
+  } else {
+    CK(cudaEventRecord(ctx->evOrder, ctx->stream));
+    CK(cudaStreamWaitEvent(other, ctx->evOrder, 0));
+  }
   return G4_OK;
 }
 
 void g4_context_destroy(g4_context* ctx) {
   if (!ctx) return;
-  cudaSetDevice(ctx->device);
+  DeviceGuard guard(ctx->device);
   cudaStreamSynchronize(ctx->stream);
   if (ctx->copyIn) {
     cudaStreamSynchronize(ctx->copyIn);
@@ -625,6 +670,7 @@ void g4_context_destroy(g4_context* ctx) {
     for (int k = 0; k < kMaxChunks; k++) { cudaEventDestroy(ctx->evIn[k]); cudaEventDestroy(ctx->evDone[k]); }
   }
   if (ctx->evStart) cudaEventDestroy(ctx->evStart);
+  if (ctx->evOrder) cudaEventDestroy(ctx->evOrder);
   if (ctx->lsopStream) {
     cudaStreamSynchronize(ctx->lsopStream);
     cudaStreamDestroy(ctx->lsopStream);
@@ -682,7 +728,7 @@ int g4_crc32c(g4_context* ctx, int mem_space, const uint8_t* data, const uint64_
               uint32_t* crc_out) {
   if (!ctx || !data || !offsets || !sizes || !crc_out || n < 0) return G4_ERR_ARG;
   if (n == 0) return G4_OK;
-  CK(cudaSetDevice(ctx->device));
+  ENTER(ctx);
   if (mem_space == G4_MEM_DEVICE) {
     CK(launch_crc32c(data, offsets, sizes, n, crc_out, 0, ctx->stream));
     ctx->launches++;
@@ -721,7 +767,7 @@ int g4_pack_tile_records(g4_context* ctx, int mem_space, const uint8_t* arena, c
   if (mem_space != G4_MEM_DEVICE && mem_space != G4_MEM_HOST) return G4_ERR_ARG;
   *total_bytes = 0;
   if (n_tiles == 0) return G4_OK;
-  CK(cudaSetDevice(ctx->device));
+  ENTER(ctx);
   const int n = n_tiles;
   const uint8_t* dArena = arena;
   const uint64_t* dOffsets = offsets;
@@ -784,7 +830,7 @@ int g4_unpack_tile_records(g4_context* ctx, int mem_space, const uint8_t* image,
   if (!ctx || !image || !content_pos || !payload_offsets || !lens || !status || n_tiles < 0) return G4_ERR_ARG;
   if (mem_space != G4_MEM_DEVICE && mem_space != G4_MEM_HOST) return G4_ERR_ARG;
   if (n_tiles == 0) return G4_OK;
-  CK(cudaSetDevice(ctx->device));
+  ENTER(ctx);
   const int n = n_tiles;
   const uint8_t* dImage = image;
   const uint64_t* dPos = content_pos;
@@ -836,7 +882,7 @@ uint64_t g4_encode_arena_bound(const g4_band_desc* b) {
 int g4_fill_terrain(g4_context* ctx, int elem_type, uint64_t seed, int64_t row0, int64_t col0, int64_t n_rows, int64_t n_cols,
                     void* device_out) {
   if (!ctx || !device_out || n_rows < 1 || n_cols < 1) return G4_ERR_ARG;
-  CK(cudaSetDevice(ctx->device));
+  ENTER(ctx);
   CK(launch_fill_terrain(elem_type, seed, row0, col0, n_rows, n_cols, device_out, ctx->stream));
   ctx->launches++;
   return G4_OK;
@@ -849,7 +895,7 @@ int g4_encode_tiles(g4_context* ctx, const g4_codec_list* codecs, const g4_band_
   int rc = check_band(band);
   if (rc != G4_OK) return rc;
   if (codecs->n_codecs < 0 || codecs->n_codecs > G4_MAX_CODECS) return G4_ERR_ARG;
-  CK(cudaSetDevice(ctx->device));
+  ENTER(ctx);
   const int nTiles = band->tiles_down * band->tiles_across;
   const size_t n = size_t(band->tile_rows) * band->tile_cols;
   const size_t slotBytes = round_up(n * 4 + 64, 16);
@@ -902,7 +948,7 @@ int g4_decode_tiles(g4_context* ctx, const g4_codec_list* codecs, const g4_band_
   int rc = check_band(band);
   if (rc != G4_OK) return rc;
   if (codecs->n_codecs < 0 || codecs->n_codecs > G4_MAX_CODECS) return G4_ERR_ARG;
-  CK(cudaSetDevice(ctx->device));
+  ENTER(ctx);
   const int nTiles = band->tiles_down * band->tiles_across;
   std::vector<int32_t> st(nTiles);
   if (mem_space == G4_MEM_DEVICE) {
@@ -921,6 +967,7 @@ int g4_decode_tiles(g4_context* ctx, const g4_codec_list* codecs, const g4_band_
     const size_t bandRowBytes = size_t(band->tiles_across) * band->tile_cols * elem_bytes(*band);
     const size_t bandRows = size_t(band->tiles_down) * band->tile_rows;
     const bool pitched = rowBytes != bandRowBytes;
+    if (ctx->arenaLimit != ~0ull && arenaBytes > ctx->arenaLimit) return G4_ERR_FORMAT;  // the directory points past the caller's arena
     CK(ctx->sGrid.ensure(gridBytes));
     CK(ctx->sArena.ensure(arenaBytes + 16));
     CK(ctx->sOffsets.ensure(size_t(nTiles) * 8));
@@ -989,6 +1036,15 @@ int g4_decode_tiles(g4_context* ctx, const g4_codec_list* codecs, const g4_band_
   return first_bad_status(st);
 }
 
+int g4_decode_tiles_bounded(g4_context* ctx, const g4_codec_list* codecs, const g4_band_desc* band, int mem_space, const uint8_t* arena,
+                            uint64_t arena_len, const uint64_t* offsets, const uint32_t* lens, void* grid, int32_t* status) {
+  if (!ctx) return G4_ERR_ARG;
+  ctx->arenaLimit = arena_len;
+  const int rc = g4_decode_tiles(ctx, codecs, band, mem_space, arena, offsets, lens, grid, status);
+  ctx->arenaLimit = ~0ull;
+  return rc;
+}
+
 // ---- per-tile entry points: one-tile bands through the same kernels --------------------------------
 
 static int encode_one(g4_context* ctx, int codec_id, int codec_index, int elem, int n_rows, int n_cols, const void* values,
@@ -998,8 +1054,11 @@ static int encode_one(g4_context* ctx, int codec_id, int codec_index, int elem, 
   if (codec_is_float(codec_id) != (elem == G4_ELEM_F32)) return G4_DECLINED;  // e.g. CodecHuffman.encodeFloats -> null
   g4_band_desc band{elem, n_rows, n_cols, 1, 1, n_cols};
   int rc = check_band(&band);
+  // a shape the kernels do not take (a one-row / one-column tile, more than 2^20 samples): the codec declines like a
+  // reference codec that returns null, and CodecMaster / TileElement store the tile raw (ICompressionEncoder.java:61)
+  if (rc == G4_ERR_UNSUPPORTED) return G4_DECLINED;
   if (rc != G4_OK) return rc;
-  CK(cudaSetDevice(ctx->device));
+  ENTER(ctx);
   const size_t n = size_t(n_rows) * n_cols;
   const size_t slotBytes = round_up(n * 6 + 1024, 16);  // worst case of any codec stream for this tile
   CK(ctx->sGrid.ensure(n * 4));
@@ -1029,6 +1088,7 @@ static int encode_one(g4_context* ctx, int codec_id, int codec_index, int elem, 
   CK(cudaMemcpyAsync(&st, a.status, 4, cudaMemcpyDeviceToHost, ctx->stream));
   CK(cudaMemcpyAsync(&pred, a.preds, 1, cudaMemcpyDeviceToHost, ctx->stream));
   CK(cudaStreamSynchronize(ctx->stream));
+  if (st == G4_ERR_CAPACITY) return G4_DECLINED;  // a packing that outgrows its slot is longer than the raw tile anyway
   if (st != G4_OK) return st;
   *out_len = len;
   if (predictor) *predictor = pred;
@@ -1045,7 +1105,7 @@ static int decode_one(g4_context* ctx, int codec_id, int elem, int n_rows, int n
   g4_band_desc band{elem, n_rows, n_cols, 1, 1, n_cols};
   int rc = check_band(&band);
   if (rc != G4_OK) return rc;
-  CK(cudaSetDevice(ctx->device));
+  ENTER(ctx);
   const size_t n = size_t(n_rows) * n_cols;
   CK(ctx->sGrid.ensure(n * 4));
   CK(ctx->sArena.ensure(len + 16));

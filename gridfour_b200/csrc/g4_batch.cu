@@ -136,7 +136,10 @@ __global__ void classify_kernel(ClassifyArgs a) {
   const uint32_t len = a.lens[t];
   int kind;
   int st = G4_OK;
-  if (len == a.rawLen) kind = G4_CODEC_COUNT;
+  // a payload must lie inside the arena; one longer than the raw tile is never written (TileElementInt.encode :196-205
+  // stores the raw samples instead) and would overflow the decoders' per-tile bounds
+  if (len > a.rawLen || a.offsets[t] > a.arenaLen || uint64_t(len) > a.arenaLen - a.offsets[t]) { kind = -1; st = G4_ERR_FORMAT; }
+  else if (len == a.rawLen) kind = G4_CODEC_COUNT;
   else if (len == 0) { kind = -1; st = G4_ERR_FORMAT; }
   else {
     int index = a.arena[a.offsets[t]];

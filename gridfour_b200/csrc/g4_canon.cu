@@ -197,12 +197,11 @@ cudaError_t launch_canon_encode(const EncodeArgs& a, int nCtas, cudaStream_t s) 
 }
 
 cudaError_t launch_canon_decode(const DecodeArgs& a, int nCtas, cudaStream_t s) {
-  static bool attr = false;
-  if (!attr) {
-    cudaError_t e = cudaFuncSetAttribute(canon_decode_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, int(sizeof(CanonDecodeSmem)));
-    if (e != cudaSuccess) return e;
-    attr = true;
-  }
+  static std::atomic<uint64_t> attr{0};
+  cudaError_t ea = once_per_device(attr, [] {
+    return cudaFuncSetAttribute(canon_decode_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, int(sizeof(CanonDecodeSmem)));
+  });
+  if (ea != cudaSuccess) return ea;
   canon_decode_kernel<<<nCtas, kThreads, sizeof(CanonDecodeSmem), s>>>(a);
   return cudaGetLastError();
 }

@@ -656,12 +656,11 @@ cudaError_t launch_deflate_streams(const StreamArgs& a, int nWorkers, cudaStream
 uint32_t deflate_staged_max() { return kDefStagedMax; }
 size_t deflate_blocks_bytes() { return sizeof(DeflateBlocks); }
 cudaError_t launch_deflate_staged(const StagedArgs& a, int smCount, cudaStream_t s) {
-  static bool attr = false;
-  if (!attr) {
-    cudaError_t ea = cudaFuncSetAttribute(deflate_sort_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, kDefWSize * 2);
-    if (ea != cudaSuccess) return ea;
-    attr = true;
-  }
+  static std::atomic<uint64_t> attr{0};
+  cudaError_t ea = once_per_device(attr, [] {
+    return cudaFuncSetAttribute(deflate_sort_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, kDefWSize * 2);
+  });
+  if (ea != cudaSuccess) return ea;
   const int nChunk = a.jEnd - a.jBegin;
   const int sortCtas = nChunk < smCount * 3 ? nChunk : smCount * 3;
   deflate_sort_kernel<<<sortCtas, kSortThreads, kDefWSize * 2, s>>>(a);

@@ -418,12 +418,11 @@ __global__ void __launch_bounds__(kThreads, 4) huffman_decode_kernel(DecodeArgs 
 }
 
 cudaError_t launch_huffman_encode(const EncodeArgs& a, int nCtas, cudaStream_t s) {
-  static bool attr = false;
-  if (!attr) {
-    cudaError_t e = cudaFuncSetAttribute(huffman_encode_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, int(sizeof(HuffEncShared)));
-    if (e != cudaSuccess) return e;
-    attr = true;
-  }
+  static std::atomic<uint64_t> attr{0};
+  cudaError_t ea = once_per_device(attr, [] {
+    return cudaFuncSetAttribute(huffman_encode_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, int(sizeof(HuffEncShared)));
+  });
+  if (ea != cudaSuccess) return ea;
   huffman_encode_kernel<<<nCtas, kThreads, sizeof(HuffEncShared), s>>>(a);
   return cudaGetLastError();
 }
@@ -439,13 +438,12 @@ cudaError_t launch_huffman_decode(const DecodeArgs& a, int nCtas, cudaStream_t s
   if (!fastOn) stageWords = 0;
   size_t smem = huff_fast_smem_bytes(stageWords);
   if (smem < sizeof(HuffDecShared)) smem = sizeof(HuffDecShared);
-  static bool attr = false;
-  if (!attr) {
-    cudaError_t e = cudaFuncSetAttribute(huffman_decode_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
-                                         int(huff_fast_smem_bytes(160 * 1024 / 4 + 16)));
-    if (e != cudaSuccess) return e;
-    attr = true;
-  }
+  static std::atomic<uint64_t> attr{0};
+  cudaError_t ea = once_per_device(attr, [] {
+    return cudaFuncSetAttribute(huffman_decode_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                int(huff_fast_smem_bytes(160 * 1024 / 4 + 16)));
+  });
+  if (ea != cudaSuccess) return ea;
   huffman_decode_kernel<<<nCtas, kThreads, smem, s>>>(a, stageWords);
   return cudaGetLastError();
 }

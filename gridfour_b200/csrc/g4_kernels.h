@@ -2,10 +2,24 @@
 #pragma once
 #include <cstddef>
 #include <cstdint>
+#include <atomic>
 #include <cuda_runtime.h>
 #include "../../include/g4codec.h"
 
 namespace g4 {
+
+// cudaFuncSetAttribute is per DEVICE: `done` holds one bit per device ordinal.  Setting an attribute twice is harmless, so
+// two threads racing on the same device need no lock.
+template <class Fn>
+inline cudaError_t once_per_device(std::atomic<uint64_t>& done, Fn set) {
+  int d = 0;
+  cudaGetDevice(&d);
+  const uint64_t bit = 1ull << (d & 63);
+  if (done.load(std::memory_order_acquire) & bit) return cudaSuccess;
+  const cudaError_t e = set();
+  if (e == cudaSuccess) done.fetch_or(bit, std::memory_order_release);
+  return e;
+}
 
 struct DeflateBlocks;  // g4_deflate_enc.cuh
 
@@ -76,6 +90,7 @@ struct ClassifyArgs {
   uint32_t rawLen;
   g4_codec_list codecs;
   const uint8_t* arena;
+  uint64_t arenaLen;  // bytes addressable behind `arena` (UINT64_MAX = the caller vouches for the directory)
   const uint64_t* offsets;
   const uint32_t* lens;
   int* lists;    // [G4_CODEC_COUNT + 1][nTiles]

@@ -1013,12 +1013,11 @@ cudaError_t launch_lsop_pick(const EncodeArgs& a, const uint32_t* inLen, const u
 }
 
 cudaError_t launch_lsop_encode(const EncodeArgs& a, int nCtas, cudaStream_t s) {
-  static bool attr = false;
-  if (!attr) {
-    cudaError_t e = cudaFuncSetAttribute(lsop_encode_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, int(sizeof(LsopEncShared)));
-    if (e != cudaSuccess) return e;
-    attr = true;
-  }
+  static std::atomic<uint64_t> attr{0};
+  cudaError_t ea = once_per_device(attr, [] {
+    return cudaFuncSetAttribute(lsop_encode_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, int(sizeof(LsopEncShared)));
+  });
+  if (ea != cudaSuccess) return ea;
   lsop_encode_kernel<<<nCtas, kThreads, sizeof(LsopEncShared), s>>>(a);
   return cudaGetLastError();
 }
@@ -1058,14 +1057,16 @@ cudaError_t launch_lsop_decode(const DecodeArgs& a, float* coef, uint8_t* meta, 
   if (stageWords > kMaxStageWords) stageWords = kMaxStageWords;
   stageWords = (stageWords + 255u) & ~255u;
   const size_t textSmem = canon_fast_smem_bytes(stageWords);
-  static bool attr = false;
-  if (!attr) {
-    const int maxSmem = int(canon_fast_smem_bytes(kMaxStageWords));
-    cudaError_t ea = cudaFuncSetAttribute(lsop_decode_text_kernel<InteriorRunSink>, cudaFuncAttributeMaxDynamicSharedMemorySize, maxSmem);
-    if (ea == cudaSuccess)
-      ea = cudaFuncSetAttribute(lsop_decode_text_kernel<InteriorPackedSink>, cudaFuncAttributeMaxDynamicSharedMemorySize, maxSmem);
+  static std::atomic<uint64_t> attr{0};
+  {
+    cudaError_t ea = once_per_device(attr, [] {
+      const int maxSmem = int(canon_fast_smem_bytes(kMaxStageWords));
+      cudaError_t e1 = cudaFuncSetAttribute(lsop_decode_text_kernel<InteriorRunSink>, cudaFuncAttributeMaxDynamicSharedMemorySize, maxSmem);
+      if (e1 == cudaSuccess)
+        e1 = cudaFuncSetAttribute(lsop_decode_text_kernel<InteriorPackedSink>, cudaFuncAttributeMaxDynamicSharedMemorySize, maxSmem);
+      return e1;
+    });
     if (ea != cudaSuccess) return ea;
-    attr = true;
   }
   const bool aligned = (a.band.tile_cols % 4) == 0 && (a.band.grid_pitch % 4) == 0 && a.band.tile_cols >= 8 &&
                        (reinterpret_cast<uintptr_t>(a.grid) & 15) == 0;

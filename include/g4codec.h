@@ -26,7 +26,7 @@
 extern "C" {
 #endif
 
-#define G4_ABI_VERSION 3
+#define G4_ABI_VERSION 4
 
 /* Status codes.  G4_DECLINED is the Java `null` return of ICompressionEncoder.encode ("codec cannot or
  * should not encode this tile": all-null tile, tile too small for the predictor, singular LSOP matrix).
@@ -101,6 +101,14 @@ const char* g4_codec_name(int codec_id);
 int g4_context_create(int device, void* cuda_stream, g4_context** out);
 void g4_context_destroy(g4_context* ctx);
 int g4_context_synchronize(g4_context* ctx);
+/* Stream ordering for G4_MEM_DEVICE buffers that another stream produces or consumes.  A context launches on ITS stream
+ * only; device buffers handed to it must be complete on that stream, and results are complete on that stream.  A caller
+ * that works on another stream (torch's current stream, a copy stream of the JVM) brackets a call with
+ *   g4_context_order_stream(ctx, other, 1);   -- what `other` has queued so far completes before the context's next launch
+ *   ... g4_encode_tiles / g4_decode_tiles (G4_MEM_DEVICE) ...
+ *   g4_context_order_stream(ctx, other, 0);   -- `other` continues only after what the context has launched so far
+ * (events, no host synchronisation).  Passing the context's own stream is a no-op. */
+int g4_context_order_stream(g4_context* ctx, void* other_stream, int before);
 
 /* ---- per-tile entry points (exact ICompressionEncoder / ICompressionDecoder semantics) ----------
  * Host buffers.  encode: packing[0] == codec_index; returns G4_DECLINED where the Java codec returns
@@ -129,6 +137,13 @@ int g4_encode_tiles(g4_context* ctx, const g4_codec_list* codecs, const g4_band_
 int g4_decode_tiles(g4_context* ctx, const g4_codec_list* codecs, const g4_band_desc* band, int mem_space,
                     const uint8_t* arena, const uint64_t* offsets, const uint32_t* lens, void* grid,
                     int32_t* status);
+
+/* g4_decode_tiles for an UNTRUSTED tile directory: arena_len = bytes addressable behind `arena`.  A tile whose
+ * offsets[t] + lens[t] leaves the arena, or whose payload is longer than the raw tile, gets status G4_ERR_FORMAT and is
+ * never dereferenced.  (g4_decode_tiles itself trusts the directory, e.g. one that g4_unpack_tile_records validated.) */
+int g4_decode_tiles_bounded(g4_context* ctx, const g4_codec_list* codecs, const g4_band_desc* band, int mem_space,
+                            const uint8_t* arena, uint64_t arena_len, const uint64_t* offsets, const uint32_t* lens,
+                            void* grid, int32_t* status);
 
 /* Upper bound of the arena bytes g4_encode_tiles can produce for a band (4*n per tile). */
 uint64_t g4_encode_arena_bound(const g4_band_desc* band);
