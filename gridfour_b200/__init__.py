@@ -11,3 +11,7 @@ from .codecs import (  # noqa: F401
 from ._lib import FormatError, G4Error  # noqa: F401
 from . import gvrs  # noqa: F401
 from .sharding import gather_layout, record_offsets, shard_tile_rows, tile_content, tile_record_is_compressed  # noqa: F401
+from .predictors import (  # noqa: F401
+    IPredictorModel, PredictorModelDifferencing, PredictorModelDifferencingWithNulls, PredictorModelLinear, PredictorModelTriangle,
+    PredictorModelType,
+)

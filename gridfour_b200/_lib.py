@@ -23,7 +23,8 @@ EXPORTS = [
     "g4_context_create", "g4_context_destroy", "g4_context_synchronize", "g4_encode_i32", "g4_decode_i32",
     "g4_encode_f32", "g4_decode_f32", "g4_encode_tiles", "g4_decode_tiles", "g4_encode_arena_bound",
     "g4_fill_terrain", "g4_launch_count", "g4_context_set_timing", "g4_kernel_time_ms", "g4_codec_supported",
-    "g4_crc32c", "g4_tile_records_bound", "g4_pack_tile_records", "g4_unpack_tile_records", "g4_context_order_stream", "g4_decode_tiles_bounded",
+    "g4_crc32c", "g4_tile_records_bound", "g4_pack_tile_records", "g4_unpack_tile_records", "g4_context_order_stream", "g4_decode_tiles_bounded", "g4_predictor_encode", "g4_predictor_encode_int", "g4_predictor_decode",
+    "g4_predictor_decode_int", "g4_predictor_tiles",
 ]
 
 
@@ -73,6 +74,13 @@ def lib():
                                       C.c_void_p, C.c_void_p, C.c_void_p]
         L.g4_decode_tiles_bounded.argtypes = [C.c_void_p, C.POINTER(CodecList), C.POINTER(BandDesc), C.c_int, C.c_void_p, C.c_uint64,
                                               C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p]
+        L.g4_predictor_encode.argtypes = [C.c_void_p, C.c_int, C.c_int, C.c_int, C.c_void_p, C.POINTER(C.c_int32), C.c_void_p, C.c_size_t,
+                                          C.POINTER(C.c_size_t)]
+        L.g4_predictor_encode_int.argtypes = L.g4_predictor_encode.argtypes
+        L.g4_predictor_decode.argtypes = [C.c_void_p, C.c_int, C.c_int32, C.c_int, C.c_int, C.c_void_p, C.c_size_t, C.c_void_p]
+        L.g4_predictor_decode_int.argtypes = L.g4_predictor_decode.argtypes
+        L.g4_predictor_tiles.argtypes = [C.c_void_p, C.c_int, C.c_int, C.c_int, C.POINTER(BandDesc), C.c_void_p, C.c_void_p, C.c_uint64,
+                                         C.c_void_p, C.c_void_p, C.c_void_p]
         L.g4_fill_terrain.argtypes = [C.c_void_p, C.c_int, C.c_uint64, C.c_int64, C.c_int64, C.c_int64, C.c_int64, C.c_void_p]
         L.g4_context_set_timing.argtypes = [C.c_void_p, C.c_int]
         L.g4_kernel_time_ms.argtypes = [C.c_void_p, C.c_int, C.c_int]

@@ -957,6 +957,20 @@ int g4_decode_tiles(g4_context* ctx, const g4_codec_list* codecs, const g4_band_
     CK(cudaMemcpyAsync(st.data(), status, size_t(nTiles) * 4, cudaMemcpyDeviceToHost, ctx->stream));
     CK(cudaStreamSynchronize(ctx->stream));
   } else if (mem_space == G4_MEM_HOST) {
+    // a directory entry that leaves the caller's arena (g4_decode_tiles_bounded) or is longer than the raw tile is never
+    // staged: it reaches the device as an empty payload, which classify_kernel reports as G4_ERR_FORMAT for that tile
+    std::vector<uint64_t> offSafe;
+    std::vector<uint32_t> lenSafe;
+    const uint32_t rawLen = standard_size(*band);
+    for (int t = 0; t < nTiles; t++) {
+      const bool bad = lens[t] > rawLen || (ctx->arenaLimit != ~0ull && (offsets[t] > ctx->arenaLimit || lens[t] > ctx->arenaLimit - offsets[t]));
+      if (bad && offSafe.empty()) {
+        offSafe.assign(offsets, offsets + nTiles);
+        lenSafe.assign(lens, lens + nTiles);
+      }
+      if (bad) { offSafe[size_t(t)] = 0; lenSafe[size_t(t)] = 0; }
+    }
+    if (!offSafe.empty()) { offsets = offSafe.data(); lens = lenSafe.data(); }
     uint64_t arenaBytes = 0;
     for (int t = 0; t < nTiles; t++) {
       uint64_t end = offsets[t] + lens[t];
@@ -967,7 +981,6 @@ int g4_decode_tiles(g4_context* ctx, const g4_codec_list* codecs, const g4_band_
     const size_t bandRowBytes = size_t(band->tiles_across) * band->tile_cols * elem_bytes(*band);
     const size_t bandRows = size_t(band->tiles_down) * band->tile_rows;
     const bool pitched = rowBytes != bandRowBytes;
-    if (ctx->arenaLimit != ~0ull && arenaBytes > ctx->arenaLimit) return G4_ERR_FORMAT;  // the directory points past the caller's arena
     CK(ctx->sGrid.ensure(gridBytes));
     CK(ctx->sArena.ensure(arenaBytes + 16));
     CK(ctx->sOffsets.ensure(size_t(nTiles) * 8));
@@ -1147,6 +1160,93 @@ static int decode_one(g4_context* ctx, int codec_id, int elem, int n_rows, int n
   CK(cudaMemcpyAsync(out, ctx->sGrid.p, n * 4, cudaMemcpyDeviceToHost, ctx->stream));
   CK(cudaStreamSynchronize(ctx->stream));
   return G4_OK;
+}
+
+// ---- predictor models on their own (IPredictorModel.java:42-173) ---------------------------------------------------
+int g4_predictor_tiles(g4_context* ctx, int model, int int_flavour, int decode, const g4_band_desc* band, void* grid, uint8_t* slots,
+                       uint64_t slot_bytes, uint32_t* lens, int32_t* seeds, int32_t* status) {
+  if (!ctx || !band || !grid || !slots || !lens || !seeds || !status) return G4_ERR_ARG;
+  if (model < G4_PRED_DIFFERENCING || model > G4_PRED_DIFF_NULLS || band->elem_type != G4_ELEM_I32) return G4_ERR_ARG;
+  int rc = check_band(band);
+  if (rc != G4_OK) return rc;
+  const uint64_t n = uint64_t(band->tile_rows) * uint64_t(band->tile_cols);
+  if ((slot_bytes & 15) != 0 || slot_bytes < (int_flavour ? 4 * n : 6 * n + 16) || (reinterpret_cast<uintptr_t>(slots) & 15) != 0) return G4_ERR_ARG;
+  ENTER(ctx);
+  PredictorArgs a{};
+  a.band = *band;
+  a.grid = grid;
+  a.model = model;
+  a.intFlavour = int_flavour ? 1 : 0;
+  a.slots = slots;
+  a.slotBytes = size_t(slot_bytes);
+  a.lens = lens;
+  a.seeds = seeds;
+  a.status = status;
+  const int nTiles = band->tiles_down * band->tiles_across;
+  CK(launch_predictor(a, decode, persistent_ctas(ctx, nTiles, 8), ctx->stream));
+  ctx->launches++;
+  return G4_OK;
+}
+
+static int predictor_one(g4_context* ctx, int model, int int_flavour, int decode, int32_t* seed, int n_rows, int n_cols, int32_t* values,
+                         void* stream, size_t stream_cap, size_t* n_stream) {
+  if (!ctx || !values || !stream || !seed || !n_stream) return G4_ERR_ARG;
+  g4_band_desc band{G4_ELEM_I32, n_rows, n_cols, 1, 1, n_cols};
+  int rc = check_band(&band);
+  if (rc == G4_ERR_UNSUPPORTED && !decode) return G4_DECLINED;
+  if (rc != G4_OK) return rc;
+  ENTER(ctx);
+  const size_t n = size_t(n_rows) * n_cols;
+  const size_t slotBytes = round_up(n * 6 + 64, 16);
+  CK(ctx->sGrid.ensure(n * 4));
+  CK(ctx->scratch.ensure(slotBytes));
+  CK(ctx->sLens.ensure(4));
+  CK(ctx->sStatus.ensure(4));
+  CK(ctx->sOffsets.ensure(8));
+  uint32_t len32 = 0;
+  if (decode) {
+    const size_t bytes = int_flavour ? *n_stream * 4 : *n_stream;
+    if (bytes + 16 > slotBytes || *n_stream > 0xffffffffull) return G4_ERR_FORMAT;
+    len32 = uint32_t(*n_stream);
+    CK(cudaMemsetAsync(ctx->scratch.p, 0, slotBytes, ctx->stream));
+    CK(cudaMemcpyAsync(ctx->scratch.p, stream, bytes, cudaMemcpyHostToDevice, ctx->stream));
+    CK(cudaMemcpyAsync(ctx->sLens.p, &len32, 4, cudaMemcpyHostToDevice, ctx->stream));
+    CK(cudaMemcpyAsync(ctx->sOffsets.p, seed, 4, cudaMemcpyHostToDevice, ctx->stream));
+  } else CK(cudaMemcpyAsync(ctx->sGrid.p, values, n * 4, cudaMemcpyHostToDevice, ctx->stream));
+  rc = g4_predictor_tiles(ctx, model, int_flavour, decode, &band, ctx->sGrid.p, ctx->scratch.as<uint8_t>(), slotBytes, ctx->sLens.as<uint32_t>(),
+                          ctx->sOffsets.as<int32_t>(), ctx->sStatus.as<int32_t>());
+  if (rc != G4_OK) return rc;
+  int32_t st = 0;
+  CK(cudaMemcpyAsync(&st, ctx->sStatus.p, 4, cudaMemcpyDeviceToHost, ctx->stream));
+  CK(cudaMemcpyAsync(&len32, ctx->sLens.p, 4, cudaMemcpyDeviceToHost, ctx->stream));
+  if (!decode) CK(cudaMemcpyAsync(seed, ctx->sOffsets.p, 4, cudaMemcpyDeviceToHost, ctx->stream));
+  CK(cudaStreamSynchronize(ctx->stream));
+  if (st != G4_OK) return st;
+  if (decode) CK(cudaMemcpyAsync(values, ctx->sGrid.p, n * 4, cudaMemcpyDeviceToHost, ctx->stream));
+  else {
+    const size_t bytes = int_flavour ? size_t(len32) * 4 : size_t(len32);
+    *n_stream = len32;
+    if (bytes > stream_cap) return G4_ERR_CAPACITY;
+    CK(cudaMemcpyAsync(stream, ctx->scratch.p, bytes, cudaMemcpyDeviceToHost, ctx->stream));
+  }
+  CK(cudaStreamSynchronize(ctx->stream));
+  return G4_OK;
+}
+
+int g4_predictor_encode(g4_context* ctx, int model, int n_rows, int n_cols, const int32_t* values, int32_t* seed, uint8_t* m32_out,
+                        size_t out_cap, size_t* n_bytes) {
+  return predictor_one(ctx, model, 0, 0, seed, n_rows, n_cols, const_cast<int32_t*>(values), m32_out, out_cap, n_bytes);
+}
+int g4_predictor_encode_int(g4_context* ctx, int model, int n_rows, int n_cols, const int32_t* values, int32_t* seed, int32_t* residuals_out,
+                            size_t out_cap, size_t* n_residuals) {
+  return predictor_one(ctx, model, 1, 0, seed, n_rows, n_cols, const_cast<int32_t*>(values), residuals_out, out_cap * 4, n_residuals);
+}
+int g4_predictor_decode(g4_context* ctx, int model, int32_t seed, int n_rows, int n_cols, const uint8_t* m32, size_t n_bytes, int32_t* values_out) {
+  return predictor_one(ctx, model, 0, 1, &seed, n_rows, n_cols, values_out, const_cast<uint8_t*>(m32), 0, &n_bytes);
+}
+int g4_predictor_decode_int(g4_context* ctx, int model, int32_t seed, int n_rows, int n_cols, const int32_t* residuals, size_t n_residuals,
+                            int32_t* values_out) {
+  return predictor_one(ctx, model, 1, 1, &seed, n_rows, n_cols, values_out, const_cast<int32_t*>(residuals), 0, &n_residuals);
 }
 
 int g4_encode_i32(g4_context* ctx, int codec_id, int codec_index, int n_rows, int n_cols, const int32_t* values, uint8_t* out,

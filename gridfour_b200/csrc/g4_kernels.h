@@ -198,6 +198,20 @@ cudaError_t launch_lsop_decode(const DecodeArgs& a, float* coef, uint8_t* meta, 
                                int nTilesUpper, cudaStream_t s, cudaStream_t s2, cudaEvent_t* ev, int* launches,
                                const LsopFastArgs* fast = nullptr, int smCount = 148);
 
+// Predictor models on their own (g4_predictor.cu): IPredictorModel.encode / decode / encodeInt / decodeInt over a band.
+struct PredictorArgs {
+  g4_band_desc band;
+  void* grid;          // int32 raster: source of encode, destination of decode
+  int model;           // G4_PRED_DIFFERENCING .. G4_PRED_DIFF_NULLS
+  int intFlavour;      // 1: residual ints (encodeInt / decodeInt), 0: M32 bytes
+  uint8_t* slots;      // tile t at slots + t * slotBytes (16-byte aligned; M32 input padded by 16 readable bytes)
+  size_t slotBytes;
+  uint32_t* lens;      // bytes / ints per tile
+  int32_t* seeds;
+  int32_t* status;
+};
+cudaError_t launch_predictor(const PredictorArgs& a, int decode, int nCtas, cudaStream_t s);
+
 // ---- zlib-stream encode stages (g4_deflate_encode.cu, g4_lsop.cu) ------------------------------------------------
 size_t deflate_work_bytes();
 size_t deflate_blocks_bytes();

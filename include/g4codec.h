@@ -122,6 +122,28 @@ int g4_encode_f32(g4_context* ctx, int codec_id, int codec_index, int n_rows, in
 int g4_decode_f32(g4_context* ctx, int codec_id, int n_rows, int n_cols, const uint8_t* packing, size_t len,
                   float* out);
 
+/* ---- predictor models on their own: IPredictorModel (compress/IPredictorModel.java:42-173) ------------------------------
+ * model = G4_PRED_DIFFERENCING / LINEAR / TRIANGLE / DIFF_NULLS.  Host buffers, one tile.
+ * g4_predictor_encode      = IPredictorModel.encode:    M32 bytes (capacity 6 * n_rows * n_cols, CodecM32.java:180) + getSeed()
+ * g4_predictor_encode_int  = IPredictorModel.encodeInt: residual ints (capacity n_rows * n_cols) + getSeed()
+ * g4_predictor_decode(_int)= IPredictorModel.decode / decodeInt.
+ * G4_DECLINED where the model returns -1 (Triangle on a one-row tile, the nulls model on a tile of nothing but nulls);
+ * G4_ERR_FORMAT for an M32 stream that does not hold exactly the residuals the model needs (the reference reads
+ * unchecked, CodecM32.java:321-330). */
+int g4_predictor_encode(g4_context* ctx, int model, int n_rows, int n_cols, const int32_t* values, int32_t* seed,
+                        uint8_t* m32_out, size_t out_cap, size_t* n_bytes);
+int g4_predictor_encode_int(g4_context* ctx, int model, int n_rows, int n_cols, const int32_t* values, int32_t* seed,
+                            int32_t* residuals_out, size_t out_cap, size_t* n_residuals);
+int g4_predictor_decode(g4_context* ctx, int model, int32_t seed, int n_rows, int n_cols, const uint8_t* m32, size_t n_bytes,
+                        int32_t* values_out);
+int g4_predictor_decode_int(g4_context* ctx, int model, int32_t seed, int n_rows, int n_cols, const int32_t* residuals,
+                            size_t n_residuals, int32_t* values_out);
+/* The same for every tile of a band, device buffers: tile t's stream at slots + t * slot_bytes (16-byte aligned; slot_bytes a
+ * multiple of 16 and at least 6 * n + 16 for M32 bytes, 4 * n for ints), lens[t] bytes / ints, seeds[t], status[t].
+ * decode != 0 runs the inverse (streams -> raster). */
+int g4_predictor_tiles(g4_context* ctx, int model, int int_flavour, int decode, const g4_band_desc* band, void* grid,
+                       uint8_t* slots, uint64_t slot_bytes, uint32_t* lens, int32_t* seeds, int32_t* status);
+
 /* ---- batched entry points (new) -----------------------------------------------------------------
  * encode: for every tile run every integer (or float) codec of `codecs`, keep the strictly smallest
  * (ties -> lowest index, CodecMaster.encodeSingleThread), store raw little-endian samples when nothing
