@@ -15,3 +15,4 @@ from .predictors import (  # noqa: F401
     IPredictorModel, PredictorModelDifferencing, PredictorModelDifferencingWithNulls, PredictorModelLinear, PredictorModelTriangle,
     PredictorModelType,
 )
+from .tilecache import RasterTileCache  # noqa: F401

@@ -24,12 +24,17 @@ EXPORTS = [
     "g4_encode_f32", "g4_decode_f32", "g4_encode_tiles", "g4_decode_tiles", "g4_encode_arena_bound",
     "g4_fill_terrain", "g4_launch_count", "g4_context_set_timing", "g4_kernel_time_ms", "g4_codec_supported",
     "g4_crc32c", "g4_tile_records_bound", "g4_pack_tile_records", "g4_unpack_tile_records", "g4_context_order_stream", "g4_decode_tiles_bounded", "g4_predictor_encode", "g4_predictor_encode_int", "g4_predictor_decode",
-    "g4_predictor_decode_int", "g4_predictor_tiles",
+    "g4_predictor_decode_int", "g4_predictor_tiles", "g4_encode_tile_list", "g4_decode_tile_list",
 ]
 
 
 class CodecList(C.Structure):
     _fields_ = [("n_codecs", C.c_int32), ("codec_ids", C.c_int32 * G4_MAX_CODECS)]
+
+
+class TileRef(C.Structure):
+    """g4_tile_ref: where one tile of a tile-list call lives (samples from the base, samples per raster row)."""
+    _fields_ = [("offset", C.c_int64), ("pitch", C.c_int64)]
 
 
 class BandDesc(C.Structure):
@@ -81,6 +86,11 @@ def lib():
         L.g4_predictor_decode_int.argtypes = L.g4_predictor_decode.argtypes
         L.g4_predictor_tiles.argtypes = [C.c_void_p, C.c_int, C.c_int, C.c_int, C.POINTER(BandDesc), C.c_void_p, C.c_void_p, C.c_uint64,
                                          C.c_void_p, C.c_void_p, C.c_void_p]
+        L.g4_encode_tile_list.argtypes = [C.c_void_p, C.POINTER(CodecList), C.c_int, C.c_int, C.c_int, C.c_int, C.c_int, C.c_void_p, C.c_void_p,
+                                          C.c_void_p, C.c_uint64, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p,
+                                          C.POINTER(C.c_uint64)]
+        L.g4_decode_tile_list.argtypes = [C.c_void_p, C.POINTER(CodecList), C.c_int, C.c_int, C.c_int, C.c_int, C.c_int, C.c_void_p, C.c_uint64,
+                                          C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p]
         L.g4_fill_terrain.argtypes = [C.c_void_p, C.c_int, C.c_uint64, C.c_int64, C.c_int64, C.c_int64, C.c_int64, C.c_void_p]
         L.g4_context_set_timing.argtypes = [C.c_void_p, C.c_int]
         L.g4_kernel_time_ms.argtypes = [C.c_void_p, C.c_int, C.c_int]

@@ -397,6 +397,92 @@ class CodecMaster:
         check(st, "g4_encode_tiles")
         return TileBatch(arena, offsets, lens, codec, pred, status, total.value, band)
 
+    # -- tile lists (new): scattered tiles of one size, each with its own {offset, pitch} -- the tile cache's calls -----
+    @staticmethod
+    def _refs(refs):
+        from ._lib import TileRef
+
+        arr = (TileRef * len(refs))()
+        for k, (off, pitch) in enumerate(refs):
+            arr[k].offset, arr[k].pitch = int(off), int(pitch)
+        return arr
+
+    def encodeTileList(self, base, refs, tileRows, tileCols):
+        """base: numpy array (host) or torch CUDA tensor holding the tiles; refs: [(offset, pitch)] in samples from base's
+        first element (RasterTileCache.flush: whatever tiles are dirty, gvrs/RasterTileCache.java:286-294).  Returns a
+        TileBatch whose tile t is list position t."""
+        L = _lib.lib()
+        cl = self.spec.native_list()
+        n = len(refs)
+        total = C.c_uint64(0)
+        tiles = self._refs(refs)
+        cap = n * 4 * tileRows * tileCols + 64
+        if isinstance(base, np.ndarray):
+            if base.dtype not in (np.int32, np.float32) or not base.flags["C_CONTIGUOUS"]:
+                raise ValueError("a contiguous int32 or float32 array")
+            elem = G4_ELEM_F32 if base.dtype == np.float32 else G4_ELEM_I32
+            arena, offsets, lens = np.empty(cap, np.uint8), np.empty(n, np.uint64), np.empty(n, np.uint32)
+            codec, pred, status = np.empty(n, np.uint8), np.empty(n, np.uint8), np.empty(n, np.int32)
+            st = L.g4_encode_tile_list(self._context()._h, C.byref(cl), elem, tileRows, tileCols, n, G4_MEM_HOST, base.ctypes.data, tiles,
+                                       arena.ctypes.data, cap, offsets.ctypes.data, lens.ctypes.data, codec.ctypes.data, pred.ctypes.data,
+                                       status.ctypes.data, C.byref(total))
+            check(st, "g4_encode_tile_list")
+            band = self._band((tileRows, n * tileCols), base.dtype, tileRows, tileCols)
+            return TileBatch(arena[: total.value], offsets, lens, codec, pred, status, total.value, band)
+        import torch
+
+        if not (isinstance(base, torch.Tensor) and base.is_cuda and base.is_contiguous()):
+            raise ValueError("expected a contiguous CUDA tensor")
+        elem = G4_ELEM_F32 if base.dtype == torch.float32 else G4_ELEM_I32
+        dev = base.device
+        arena = torch.empty(cap, dtype=torch.uint8, device=dev)
+        offsets = torch.empty(n, dtype=torch.int64, device=dev)
+        lens = torch.empty(n, dtype=torch.int32, device=dev)
+        codec, pred = torch.empty(n, dtype=torch.uint8, device=dev), torch.empty(n, dtype=torch.uint8, device=dev)
+        status = torch.empty(n, dtype=torch.int32, device=dev)
+        ctx = self._context()
+        ctx.after_torch_stream(dev)
+        st = L.g4_encode_tile_list(ctx._h, C.byref(cl), elem, tileRows, tileCols, n, G4_MEM_DEVICE, base.data_ptr(), tiles, arena.data_ptr(), cap,
+                                   offsets.data_ptr(), lens.data_ptr(), codec.data_ptr(), pred.data_ptr(), status.data_ptr(), C.byref(total))
+        ctx.before_torch_stream(dev)
+        check(st, "g4_encode_tile_list")
+        band = self._band((tileRows, n * tileCols), np.float32 if elem == G4_ELEM_F32 else np.int32, tileRows, tileCols)
+        return TileBatch(arena, offsets, lens, codec, pred, status, total.value, band)
+
+    def decodeTileList(self, arena, offsets, lens, base, refs, tileRows, tileCols):
+        """Decodes payload t (arena[offsets[t] : +lens[t]]) into the tile at refs[t] of `base` (numpy or torch CUDA; all
+        buffers in the same memory space).  RasterTileCache.readTileUsingAssistant / a bulk readBlock
+        (gvrs/RasterTileCache.java:339-426, gvrs/GvrsElement.java:298-404): every missing tile of a window in one call."""
+        L = _lib.lib()
+        cl = self.spec.native_list()
+        n = len(refs)
+        tiles = self._refs(refs)
+        if isinstance(base, np.ndarray):
+            if base.dtype not in (np.int32, np.float32) or not base.flags["C_CONTIGUOUS"]:
+                raise ValueError("a contiguous int32 or float32 array")
+            elem = G4_ELEM_F32 if base.dtype == np.float32 else G4_ELEM_I32
+            a = np.frombuffer(arena, dtype=np.uint8) if not isinstance(arena, np.ndarray) else np.ascontiguousarray(arena)
+            off = np.ascontiguousarray(offsets, dtype=np.uint64)
+            ln = np.ascontiguousarray(lens, dtype=np.uint32)
+            status = np.empty(n, np.int32)
+            st = L.g4_decode_tile_list(self._context()._h, C.byref(cl), elem, tileRows, tileCols, n, G4_MEM_HOST, a.ctypes.data, int(a.size),
+                                       off.ctypes.data, ln.ctypes.data, base.ctypes.data, tiles, status.ctypes.data)
+            self.lastStatus = status
+            check(st, "g4_decode_tile_list")
+            return base
+        import torch
+
+        elem = G4_ELEM_F32 if base.dtype == torch.float32 else G4_ELEM_I32
+        status = torch.empty(n, dtype=torch.int32, device=base.device)
+        ctx = self._context()
+        ctx.after_torch_stream(base.device)
+        st = L.g4_decode_tile_list(ctx._h, C.byref(cl), elem, tileRows, tileCols, n, G4_MEM_DEVICE, arena.data_ptr(), int(arena.numel()),
+                                   offsets.data_ptr(), lens.data_ptr(), base.data_ptr(), tiles, status.data_ptr())
+        ctx.before_torch_stream(base.device)
+        self.lastStatus = status
+        check(st, "g4_decode_tile_list")
+        return base
+
     def decodeImageTiles(self, image, payload_offsets, lens, status, tilesDown, tilesAcross, tileRows, tileCols, dtype, fillValue):
         """Decodes the tiles of a one-element raster whose payloads sit inside a GVRS file image (gvrs.GvrsImage.read_raster):
         the image is the arena of g4_decode_tiles.  Tiles the file does not hold (status G4_DECLINED) are pointed at one

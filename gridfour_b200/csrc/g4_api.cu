@@ -103,6 +103,9 @@ struct g4_context {
   uint64_t hostTotal = 0;
   int deflateWorkers = 0;   // resident stream-worker threads (0 = default, see g4_context_create)
   uint64_t stagedChunkBytes = 2ull << 30;  // staged zlib encode: input bytes per chunk (scratch = 12x)
+  const int64_t* curTileOffset = nullptr;  // tile-list calls: device {offset, pitch} tables of the running call
+  const int64_t* curTilePitch = nullptr;
+  DevBuf tileRefs;      // device copy of the tile references of a tile-list call
   uint64_t arenaLimit = ~0ull;  // g4_decode_tiles_bounded: bytes addressable behind the arena of the running call
   bool lsopDeflate = true;  // LsEncoder12.deflateEnabled (lsop/LsEncoder12.java:78)
   // staging used by the host-memory entry points
@@ -415,6 +418,8 @@ int encode_device_i32(g4_context* ctx, const g4_codec_list* codecs, const g4_ban
     CK(ctx->slots[c].ensure(size_t(nTiles) * slotBytes));
     EncodeArgs a{};
     a.band = *band;
+    a.band.tileOffset = ctx->curTileOffset;
+    a.band.tilePitch = ctx->curTilePitch;
     a.grid = grid;
     a.slots = ctx->slots[c].as<uint8_t>();
     a.slotBytes = slotBytes;
@@ -444,6 +449,8 @@ int encode_device_i32(g4_context* ctx, const g4_codec_list* codecs, const g4_ban
   CK(launch_select(sel, ctx->stream));
   CK(launch_offsets(lens, offsets, nTiles, ctx->total.as<uint64_t>(), ctx->stream));
   cmp.band = *band;
+  cmp.band.tileOffset = ctx->curTileOffset;
+  cmp.band.tilePitch = ctx->curTilePitch;
   cmp.grid = grid;
   cmp.slotBytes = slotBytes;
   cmp.lens = lens;
@@ -498,6 +505,8 @@ int decode_device_i32(g4_context* ctx, const g4_codec_list* codecs, const g4_ban
     if (kind < G4_CODEC_COUNT && !present[kind]) continue;
     DecodeArgs a{};
     a.band = *band;
+    a.band.tileOffset = ctx->curTileOffset;
+    a.band.tilePitch = ctx->curTilePitch;
     a.grid = grid;
     a.arena = arena;
     a.offsets = offsets;
@@ -678,7 +687,7 @@ void g4_context_destroy(g4_context* ctx) {
   }
   for (auto& b : ctx->slots) b.release();
   DevBuf* bufs[] = {&ctx->candLens, &ctx->candPreds, &ctx->candStatus, &ctx->counters, &ctx->scratch, &ctx->lists, &ctx->src,
-                    &ctx->total, &ctx->coef, &ctx->defer, &ctx->lsopMeta, &ctx->lsopSide, &ctx->lsopExc, &ctx->lsopResid, &ctx->lsopStage, &ctx->wide, &ctx->encScratch, &ctx->region, &ctx->jobLen, &ctx->jobOff, &ctx->jobOut, &ctx->jobTotal,
+                    &ctx->total, &ctx->coef, &ctx->defer, &ctx->lsopMeta, &ctx->lsopSide, &ctx->lsopExc, &ctx->lsopResid, &ctx->lsopStage, &ctx->tileRefs, &ctx->wide, &ctx->encScratch, &ctx->region, &ctx->jobLen, &ctx->jobOff, &ctx->jobOut, &ctx->jobTotal,
                     &ctx->streamIn, &ctx->streamOut, &ctx->deflateWork, &ctx->stSorted, &ctx->stRank, &ctx->stTable,
                     &ctx->stWork, &ctx->stCounters, &ctx->rcPos, &ctx->rcOff, &ctx->rcLen, &ctx->rcCrc, &ctx->rcStored, &ctx->rcTotal,
                     &ctx->rcData, &ctx->rcOffsets, &ctx->rcLens, &ctx->rcIndex, &ctx->rcStatus, &ctx->rcOut, &ctx->sGrid, &ctx->sArena, &ctx->sOffsets, &ctx->sLens, &ctx->sCodec, &ctx->sPred, &ctx->sStatus};
@@ -888,9 +897,27 @@ int g4_fill_terrain(g4_context* ctx, int elem_type, uint64_t seed, int64_t row0,
   return G4_OK;
 }
 
-int g4_encode_tiles(g4_context* ctx, const g4_codec_list* codecs, const g4_band_desc* band, int mem_space, const void* grid,
-                    uint8_t* arena, uint64_t arena_cap, uint64_t* offsets, uint32_t* lens, uint8_t* codec_out,
-                    uint8_t* predictor_out, int32_t* status, uint64_t* total_bytes) {
+// Tile-list calls: `refs` (host array, one {offset, pitch} per tile, in samples relative to `grid`) replaces the tile grid
+// of the band, which is then a list of band->tiles_across tiles.  Device rasters are addressed in place through the
+// per-tile tables of BandEx; host rasters are staged tile under tile by 2-D copies (no host gather).
+static int upload_tile_refs(g4_context* ctx, const g4_tile_ref* refs, int nTiles) {
+  std::vector<int64_t> h(size_t(nTiles) * 2);
+  for (int t = 0; t < nTiles; t++) { h[size_t(t)] = refs[t].offset; h[size_t(nTiles) + t] = refs[t].pitch; }
+  CK(ctx->tileRefs.ensure(h.size() * 8));
+  CK(cudaMemcpyAsync(ctx->tileRefs.p, h.data(), h.size() * 8, cudaMemcpyHostToDevice, ctx->stream));
+  CK(cudaStreamSynchronize(ctx->stream));  // h goes out of scope
+  ctx->curTileOffset = ctx->tileRefs.as<int64_t>();
+  ctx->curTilePitch = ctx->tileRefs.as<int64_t>() + nTiles;
+  return G4_OK;
+}
+struct TileRefScope {  // the tables are valid for one call only
+  g4_context* c;
+  ~TileRefScope() { c->curTileOffset = nullptr; c->curTilePitch = nullptr; }
+};
+
+static int encode_tiles_impl(g4_context* ctx, const g4_codec_list* codecs, const g4_band_desc* band, int mem_space, const void* grid,
+                             const g4_tile_ref* refs, uint8_t* arena, uint64_t arena_cap, uint64_t* offsets, uint32_t* lens,
+                             uint8_t* codec_out, uint8_t* predictor_out, int32_t* status, uint64_t* total_bytes) {
   if (!ctx || !codecs || !grid || !arena || !offsets || !lens || !codec_out || !predictor_out || !status) return G4_ERR_ARG;
   int rc = check_band(band);
   if (rc != G4_OK) return rc;
@@ -902,14 +929,22 @@ int g4_encode_tiles(g4_context* ctx, const g4_codec_list* codecs, const g4_band_
   const size_t eb = elem_bytes(*band);
   std::vector<int32_t> st(nTiles);
   uint64_t total = 0;
+  TileRefScope scope{ctx};
   if (mem_space == G4_MEM_DEVICE) {
+    if (refs && (rc = upload_tile_refs(ctx, refs, nTiles)) != G4_OK) return rc;
     rc = encode_device(ctx, codecs, band, const_cast<void*>(grid), arena, arena_cap, offsets, lens, codec_out, predictor_out,
                        status, &total, slotBytes);
     if (rc != G4_OK) return rc;
     CK(cudaMemcpyAsync(st.data(), status, size_t(nTiles) * 4, cudaMemcpyDeviceToHost, ctx->stream));
     CK(cudaStreamSynchronize(ctx->stream));
   } else if (mem_space == G4_MEM_HOST) {
-    const size_t gridBytes = band_samples(*band) * eb;
+    g4_band_desc staged = *band;
+    if (refs) {  // the tiles go tile under tile into one staging raster of pitch tile_cols
+      staged.tiles_down = nTiles;
+      staged.tiles_across = 1;
+      staged.grid_pitch = band->tile_cols;
+    }
+    const size_t gridBytes = band_samples(staged) * eb;
     const uint64_t bound = g4_encode_arena_bound(band);
     CK(ctx->sGrid.ensure(gridBytes));
     CK(ctx->sArena.ensure(bound + 16));
@@ -918,7 +953,13 @@ int g4_encode_tiles(g4_context* ctx, const g4_codec_list* codecs, const g4_band_
     CK(ctx->sCodec.ensure(nTiles));
     CK(ctx->sPred.ensure(nTiles));
     CK(ctx->sStatus.ensure(size_t(nTiles) * 4));
-    CK(cudaMemcpyAsync(ctx->sGrid.p, grid, gridBytes, cudaMemcpyHostToDevice, ctx->stream));
+    if (refs) {
+      for (int t = 0; t < nTiles; t++)
+        CK(cudaMemcpy2DAsync(ctx->sGrid.as<uint8_t>() + size_t(t) * n * eb, size_t(band->tile_cols) * eb,
+                             static_cast<const uint8_t*>(grid) + refs[t].offset * int64_t(eb), size_t(refs[t].pitch) * eb,
+                             size_t(band->tile_cols) * eb, size_t(band->tile_rows), cudaMemcpyHostToDevice, ctx->stream));
+    } else CK(cudaMemcpyAsync(ctx->sGrid.p, grid, gridBytes, cudaMemcpyHostToDevice, ctx->stream));
+    band = &staged;
     rc = encode_device(ctx, codecs, band, ctx->sGrid.p, ctx->sArena.as<uint8_t>(), bound, ctx->sOffsets.as<uint64_t>(),
                        ctx->sLens.as<uint32_t>(), ctx->sCodec.as<uint8_t>(), ctx->sPred.as<uint8_t>(), ctx->sStatus.as<int32_t>(),
                        &total, slotBytes);
@@ -942,8 +983,41 @@ int g4_encode_tiles(g4_context* ctx, const g4_codec_list* codecs, const g4_band_
   return first_bad_status(st);
 }
 
-int g4_decode_tiles(g4_context* ctx, const g4_codec_list* codecs, const g4_band_desc* band, int mem_space, const uint8_t* arena,
-                    const uint64_t* offsets, const uint32_t* lens, void* grid, int32_t* status) {
+int g4_encode_tiles(g4_context* ctx, const g4_codec_list* codecs, const g4_band_desc* band, int mem_space, const void* grid,
+                    uint8_t* arena, uint64_t arena_cap, uint64_t* offsets, uint32_t* lens, uint8_t* codec_out,
+                    uint8_t* predictor_out, int32_t* status, uint64_t* total_bytes) {
+  return encode_tiles_impl(ctx, codecs, band, mem_space, grid, nullptr, arena, arena_cap, offsets, lens, codec_out, predictor_out, status,
+                           total_bytes);
+}
+
+// The band a tile list runs as: one row of n tiles.  grid_pitch only carries the ALIGNMENT the kernels may rely on (the
+// vectorised LSOP12 paths test it modulo 4 and 8); the per-tile tables give the real geometry.
+static int tile_list_band(int elem_type, int tile_rows, int tile_cols, int n_tiles, const g4_tile_ref* refs, g4_band_desc* out) {
+  if (!refs || n_tiles < 1 || (elem_type != G4_ELEM_I32 && elem_type != G4_ELEM_F32)) return elem_type == G4_ELEM_I16 ? G4_ERR_UNSUPPORTED : G4_ERR_ARG;
+  int align = 8;
+  for (int t = 0; t < n_tiles; t++) {
+    if (refs[t].pitch < tile_cols || refs[t].offset < 0) return G4_ERR_ARG;
+    while (align > 1 && ((refs[t].offset % align) != 0 || (refs[t].pitch % align) != 0)) align >>= 1;
+  }
+  int64_t rep = ((int64_t(n_tiles) * tile_cols + 7) / 8) * 8;
+  if (align == 4) rep += 4;
+  else if (align < 4) rep += 1;
+  *out = g4_band_desc{elem_type, tile_rows, tile_cols, 1, n_tiles, rep, 0, 0};
+  return G4_OK;
+}
+
+int g4_encode_tile_list(g4_context* ctx, const g4_codec_list* codecs, int elem_type, int tile_rows, int tile_cols, int n_tiles,
+                        int mem_space, const void* base, const g4_tile_ref* tiles, uint8_t* arena, uint64_t arena_cap, uint64_t* offsets,
+                        uint32_t* lens, uint8_t* codec_out, uint8_t* predictor_out, int32_t* status, uint64_t* total_bytes) {
+  g4_band_desc band;
+  const int rc = tile_list_band(elem_type, tile_rows, tile_cols, n_tiles, tiles, &band);
+  if (rc != G4_OK) return rc;
+  return encode_tiles_impl(ctx, codecs, &band, mem_space, base, tiles, arena, arena_cap, offsets, lens, codec_out, predictor_out, status,
+                           total_bytes);
+}
+
+static int decode_tiles_impl(g4_context* ctx, const g4_codec_list* codecs, const g4_band_desc* band, int mem_space, const uint8_t* arena,
+                             const uint64_t* offsets, const uint32_t* lens, void* grid, const g4_tile_ref* refs, int32_t* status) {
   if (!ctx || !codecs || !grid || !arena || !offsets || !lens || !status) return G4_ERR_ARG;
   int rc = check_band(band);
   if (rc != G4_OK) return rc;
@@ -951,7 +1025,9 @@ int g4_decode_tiles(g4_context* ctx, const g4_codec_list* codecs, const g4_band_
   ENTER(ctx);
   const int nTiles = band->tiles_down * band->tiles_across;
   std::vector<int32_t> st(nTiles);
+  TileRefScope scope{ctx};
   if (mem_space == G4_MEM_DEVICE) {
+    if (refs && (rc = upload_tile_refs(ctx, refs, nTiles)) != G4_OK) return rc;
     rc = decode_device(ctx, codecs, band, arena, offsets, lens, grid, status);
     if (rc != G4_OK) return rc;
     CK(cudaMemcpyAsync(st.data(), status, size_t(nTiles) * 4, cudaMemcpyDeviceToHost, ctx->stream));
@@ -976,6 +1052,13 @@ int g4_decode_tiles(g4_context* ctx, const g4_codec_list* codecs, const g4_band_
       uint64_t end = offsets[t] + lens[t];
       if (end > arenaBytes) arenaBytes = end;
     }
+    g4_band_desc staged = *band;
+    if (refs) {  // decode tile under tile into one staging raster of pitch tile_cols, then one 2-D copy per tile
+      staged.tiles_down = nTiles;
+      staged.tiles_across = 1;
+      staged.grid_pitch = band->tile_cols;
+      band = &staged;
+    }
     const size_t gridBytes = band_samples(*band) * elem_bytes(*band);
     const size_t rowBytes = size_t(band->grid_pitch) * elem_bytes(*band);
     const size_t bandRowBytes = size_t(band->tiles_across) * band->tile_cols * elem_bytes(*band);
@@ -994,7 +1077,7 @@ int g4_decode_tiles(g4_context* ctx, const g4_codec_list* codecs, const g4_band_
     bool ascending = true;
     for (int t = 1; t < nTiles && ascending; t++) ascending = offsets[t] >= offsets[t - 1] + lens[t - 1];
     int nChunks = ascending ? (band->tiles_down < kMaxChunks ? band->tiles_down : kMaxChunks) : 1;
-    if (gridBytes < (size_t(32) << 20)) nChunks = 1;  // small bands: the fixed cost per chunk is not worth it
+    if (gridBytes < (size_t(32) << 20) || refs) nChunks = 1;  // small bands: the fixed cost per chunk is not worth it
     if (nChunks > 1 && !ctx->copyIn) {
       CK(cudaStreamCreateWithFlags(&ctx->copyIn, cudaStreamNonBlocking));
       CK(cudaStreamCreateWithFlags(&ctx->copyOut, cudaStreamNonBlocking));
@@ -1008,7 +1091,13 @@ int g4_decode_tiles(g4_context* ctx, const g4_codec_list* codecs, const g4_band_
       rc = decode_device(ctx, codecs, band, ctx->sArena.as<uint8_t>(), ctx->sOffsets.as<uint64_t>(), ctx->sLens.as<uint32_t>(),
                          ctx->sGrid.p, ctx->sStatus.as<int32_t>());
       if (rc != G4_OK) return rc;
-      if (pitched)  // a band inside a wider host raster: only the band's columns go back
+      if (refs) {
+        const size_t eb = elem_bytes(*band), tileBytes = size_t(band->tile_rows) * band->tile_cols * eb;
+        for (int t = 0; t < nTiles; t++)
+          CK(cudaMemcpy2DAsync(static_cast<uint8_t*>(grid) + refs[t].offset * int64_t(eb), size_t(refs[t].pitch) * eb,
+                               ctx->sGrid.as<uint8_t>() + size_t(t) * tileBytes, size_t(band->tile_cols) * eb, size_t(band->tile_cols) * eb,
+                               size_t(band->tile_rows), cudaMemcpyDeviceToHost, ctx->stream));
+      } else if (pitched)  // a band inside a wider host raster: only the band's columns go back
         CK(cudaMemcpy2DAsync(grid, rowBytes, ctx->sGrid.p, rowBytes, bandRowBytes, bandRows, cudaMemcpyDeviceToHost, ctx->stream));
       else
         CK(cudaMemcpyAsync(grid, ctx->sGrid.p, gridBytes, cudaMemcpyDeviceToHost, ctx->stream));
@@ -1047,6 +1136,24 @@ int g4_decode_tiles(g4_context* ctx, const g4_codec_list* codecs, const g4_band_
     return G4_ERR_ARG;
   }
   return first_bad_status(st);
+}
+
+int g4_decode_tiles(g4_context* ctx, const g4_codec_list* codecs, const g4_band_desc* band, int mem_space, const uint8_t* arena,
+                    const uint64_t* offsets, const uint32_t* lens, void* grid, int32_t* status) {
+  return decode_tiles_impl(ctx, codecs, band, mem_space, arena, offsets, lens, grid, nullptr, status);
+}
+
+int g4_decode_tile_list(g4_context* ctx, const g4_codec_list* codecs, int elem_type, int tile_rows, int tile_cols, int n_tiles,
+                        int mem_space, const uint8_t* arena, uint64_t arena_len, const uint64_t* offsets, const uint32_t* lens, void* base,
+                        const g4_tile_ref* tiles, int32_t* status) {
+  g4_band_desc band;
+  int rc = tile_list_band(elem_type, tile_rows, tile_cols, n_tiles, tiles, &band);
+  if (rc != G4_OK) return rc;
+  if (!ctx) return G4_ERR_ARG;
+  ctx->arenaLimit = arena_len;
+  rc = decode_tiles_impl(ctx, codecs, &band, mem_space, arena, offsets, lens, base, tiles, status);
+  ctx->arenaLimit = ~0ull;
+  return rc;
 }
 
 int g4_decode_tiles_bounded(g4_context* ctx, const g4_codec_list* codecs, const g4_band_desc* band, int mem_space, const uint8_t* arena,

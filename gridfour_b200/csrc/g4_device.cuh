@@ -30,13 +30,28 @@ struct TileView {
   __device__ __forceinline__ int32_t& at(int r, int c) const { return base[int64_t(r) * pitch + c]; }
 };
 
-__device__ __forceinline__ TileView tile_view(const g4_band_desc& b, void* grid, int t) {
-  int tr = t / b.tiles_across, tc = t - tr * b.tiles_across;
+// A band as the kernels see it: the public descriptor plus, for tile-LIST calls (g4_encode_tile_list /
+// g4_decode_tile_list), one {offset, pitch} pair per tile -- scattered tiles that share nothing but their size, e.g.
+// the int[] buffers of a tile cache (gvrs/RasterTileCache.java:253-294) or a window inside a user's block.
+struct BandEx : g4_band_desc {
+  const int64_t* tileOffset = nullptr;  // samples from the raster base to tile t's cell (0,0); null: tile grid of the band
+  const int64_t* tilePitch = nullptr;   // samples per row of the raster tile t lives in; null: grid_pitch
+  BandEx() = default;
+  BandEx(const g4_band_desc& b) : g4_band_desc(b) {}
+};
+
+__device__ __forceinline__ TileView tile_view(const BandEx& b, void* grid, int t) {
   TileView v;
-  v.base = static_cast<int32_t*>(grid) + int64_t(tr) * b.tile_rows * b.grid_pitch + int64_t(tc) * b.tile_cols;
-  v.pitch = b.grid_pitch;
   v.R = b.tile_rows;
   v.C = b.tile_cols;
+  if (b.tileOffset) {
+    v.base = static_cast<int32_t*>(grid) + b.tileOffset[t];
+    v.pitch = b.tilePitch ? b.tilePitch[t] : b.grid_pitch;
+    return v;
+  }
+  int tr = t / b.tiles_across, tc = t - tr * b.tiles_across;
+  v.base = static_cast<int32_t*>(grid) + int64_t(tr) * b.tile_rows * b.grid_pitch + int64_t(tc) * b.tile_cols;
+  v.pitch = b.grid_pitch;
   return v;
 }
 

@@ -5,6 +5,7 @@
 #include <atomic>
 #include <cuda_runtime.h>
 #include "../../include/g4codec.h"
+#include "g4_device.cuh"
 
 namespace g4 {
 
@@ -26,7 +27,7 @@ struct DeflateBlocks;  // g4_deflate_enc.cuh
 // One candidate-encoder launch: every tile of the band is encoded by ONE codec into its own fixed-size
 // slot (slot t at slots + t*slotBytes, 16-byte aligned).  lens[t] = packing length (0 = declined).
 struct EncodeArgs {
-  g4_band_desc band;
+  BandEx band;
   void* grid;           // device raster (band upper-left cell)
   uint8_t* slots;
   size_t slotBytes;
@@ -41,7 +42,7 @@ struct EncodeArgs {
 
 // One decoder launch over the tiles of one codec kind: list[0..*listCount) are tile indices.
 struct DecodeArgs {
-  g4_band_desc band;
+  BandEx band;
   void* grid;
   const uint8_t* arena;
   const uint64_t* offsets;
@@ -70,7 +71,7 @@ struct SelectArgs {
 };
 
 struct CompactArgs {
-  g4_band_desc band;
+  BandEx band;
   void* grid;
   const uint8_t* slots[G4_MAX_CODECS];
   size_t slotBytes;
@@ -200,7 +201,7 @@ cudaError_t launch_lsop_decode(const DecodeArgs& a, float* coef, uint8_t* meta, 
 
 // Predictor models on their own (g4_predictor.cu): IPredictorModel.encode / decode / encodeInt / decodeInt over a band.
 struct PredictorArgs {
-  g4_band_desc band;
+  BandEx band;
   void* grid;          // int32 raster: source of encode, destination of decode
   int model;           // G4_PRED_DIFFERENCING .. G4_PRED_DIFF_NULLS
   int intFlavour;      // 1: residual ints (encodeInt / decodeInt), 0: M32 bytes

@@ -253,25 +253,19 @@ class GvrsImage:
             raise IOError("Checksum mismatch in record at file position %d" % int(off[bad[0]]))
         return len(off)
 
-    def read_raster(self, master, element=0, verify=True, crop=False):
-        """crop=True returns the n_rows x n_cols raster without the fill-valued margin of the edge tiles.
-        Decodes every tile of one element of the raster on the GPU straight from the file image: the image is the arena
-        of g4_decode_tiles.  One-element rasters: record validation, checksum check and payload location by
-        g4_unpack_tile_records.  Rasters with several elements per tile: the [len][bytes] chain of every tile record is
-        walked on the host (structure only) and the record checksums are checked by g4_crc32c.  Tiles that are absent from
-        the file come back filled with the element's fill value (RasterTile.setToNullState)."""
+    def locate_payloads(self, ctx, element=0, verify=True):
+        """(payload offsets, lengths, status) of one element of every tile, as g4_decode_tiles takes them with the file image
+        as its arena; status G4_DECLINED marks tiles the file does not hold."""
         from ._lib import G4_DECLINED
 
         spec = self.spec
         if not 0 <= element < len(spec.elements):
             raise ValueError("no such element")
-        e = spec.elements[element]
         n_tiles = spec.tiles_down * spec.tiles_across
         directory = self.tile_directory()
         pos = np.zeros(n_tiles, dtype=np.uint64)
         for t, p in directory.items():
             pos[t] = p
-        ctx = master._context()
         if len(spec.elements) == 1:
             payload_off, lens, status = unpack_tile_records(ctx, self.image, pos, checksum=verify and spec.checksum)
             bad = np.nonzero(status < 0)[0]
@@ -302,6 +296,18 @@ class GvrsImage:
                 crc = crc32c_ranges(ctx, b, rec_off, rec_len)
                 if np.any(crc != np.array(rec_crc, dtype=np.uint32)):
                     raise IOError("Checksum mismatch in a tile record")
+        return payload_off, lens, status
+
+    def read_raster(self, master, element=0, verify=True, crop=False):
+        """crop=True returns the n_rows x n_cols raster without the fill-valued margin of the edge tiles.
+        Decodes every tile of one element of the raster on the GPU straight from the file image: the image is the arena
+        of g4_decode_tiles.  One-element rasters: record validation, checksum check and payload location by
+        g4_unpack_tile_records.  Rasters with several elements per tile: the [len][bytes] chain of every tile record is
+        walked on the host (structure only) and the record checksums are checked by g4_crc32c.  Tiles that are absent from
+        the file come back filled with the element's fill value (RasterTile.setToNullState)."""
+        spec = self.spec
+        e = spec.elements[element] if 0 <= element < len(spec.elements) else None
+        payload_off, lens, status = self.locate_payloads(master._context(), element, verify)
         dtype = {ELEM_INTEGER: np.int32, ELEM_INT_CODED_FLOAT: np.int32, ELEM_FLOAT: np.float32, ELEM_SHORT: np.int16}[e.type_code]
         grid = master.decodeImageTiles(self.image, payload_off, lens, status, spec.tiles_down, spec.tiles_across, spec.tile_rows,
                                        spec.tile_cols, dtype, e.fill_value)

@@ -167,6 +167,26 @@ int g4_decode_tiles_bounded(g4_context* ctx, const g4_codec_list* codecs, const 
                             const uint8_t* arena, uint64_t arena_len, const uint64_t* offsets, const uint32_t* lens,
                             void* grid, int32_t* status);
 
+/* ---- tile LISTS: scattered tiles of one size (the tile cache's callers) -------------------------------------------------
+ * The band calls above take one rectangle of one raster.  A tile cache flushes whatever tiles are dirty, each in its own
+ * int[] (gvrs/RasterTileCache.java:253-294, RasterTile.getCompressedPacking :234-256), and a block read lands tiles in a
+ * window of the caller's array (gvrs/GvrsElement.java:298-404).  Here every tile has its own reference:
+ *   offset = samples from `base` to the tile's cell (0,0), pitch = samples per row of the raster it lives in.
+ * `tiles` is a HOST array in both memory spaces; everything else is as in g4_encode_tiles / g4_decode_tiles_bounded
+ * (tile t of the call = list position t).  Host rasters are staged by 2-D DMA copies, one per tile -- no host gather.
+ * int32 and float32 elements (short elements need the band form: their widening pass works on a rectangle). */
+typedef struct g4_tile_ref {
+  int64_t offset;
+  int64_t pitch;
+} g4_tile_ref;
+int g4_encode_tile_list(g4_context* ctx, const g4_codec_list* codecs, int elem_type, int tile_rows, int tile_cols, int n_tiles,
+                        int mem_space, const void* base, const g4_tile_ref* tiles, uint8_t* arena, uint64_t arena_cap,
+                        uint64_t* offsets, uint32_t* lens, uint8_t* codec_out, uint8_t* predictor_out, int32_t* status,
+                        uint64_t* total_bytes);
+int g4_decode_tile_list(g4_context* ctx, const g4_codec_list* codecs, int elem_type, int tile_rows, int tile_cols, int n_tiles,
+                        int mem_space, const uint8_t* arena, uint64_t arena_len, const uint64_t* offsets, const uint32_t* lens,
+                        void* base, const g4_tile_ref* tiles, int32_t* status);
+
 /* Upper bound of the arena bytes g4_encode_tiles can produce for a band (4*n per tile). */
 uint64_t g4_encode_arena_bound(const g4_band_desc* band);
 
