@@ -56,8 +56,12 @@ def test_tile_list_host_matches_oracle(g4, oracle, shape):
     for k, t in enumerate(tiles):
         assert batch.payload(k) == oracle.master_encode_i32(ids, t), "tile %d" % k
     # decode into ANOTHER scattering (reversed order, different pitches)
-    out = np.full(flat.size + 1000, -5, np.int32)
-    refs2 = [(off + 11 + 3 * k, pitch + 2) for k, (off, pitch) in enumerate(refs)]
+    refs2, pos = [], 11
+    for k, (_off, pitch) in reversed(list(enumerate(refs))):
+        refs2.append((pos, pitch + 2))
+        pos += tr * (pitch + 2) + 3 * k + 1
+    refs2 = refs2[::-1]   # tile k of the batch goes to refs2[k]: the tiles end up in reverse order in memory
+    out = np.full(pos + 100, -5, np.int32)
     master.decodeTileList(batch.arena, batch.offsets, batch.lens, out, refs2, tr, tc)
     touched = np.zeros(out.size, bool)
     for k, (off, pitch) in enumerate(refs2):
@@ -150,9 +154,15 @@ def test_tile_cache_on_reference_sample_files(g4, oracle):
     from gridfour_b200 import gvrs
     from gvrs_common import sample_files
 
-    master = g4.CodecMaster(g4.CodecSpecification())
+    std = {"GvrsHuffman": (g4.CodecHuffman, g4.CodecHuffman), "GvrsDeflate": (g4.CodecDeflate, g4.CodecDeflate),
+           "LSOP12": (g4.LsEncoder12, g4.LsDecoder12), "GvrsFloat": (g4.CodecFloat, g4.CodecFloat),
+           "GvrsCanonicalHuffman": (g4.CodecCanonHuffman, g4.CodecCanonHuffman)}
     for name, data in sample_files().items():
         img = gvrs.GvrsImage.parse(data)
+        spec = g4.CodecSpecification(default=False)
+        for c in img.spec.codecs:
+            spec.addCompressionCodec(c, *std[c])
+        master = g4.CodecMaster(spec)
         for e, el in enumerate(img.spec.elements):
             if el.type_code == gvrs.ELEM_SHORT:
                 continue
