@@ -8,7 +8,7 @@ from .codecs import (  # noqa: F401
     CodecCanonHuffman, CodecDeflate, CodecFloat, CodecHuffman, CodecMaster, CodecSpecification, Context,
     ICompressionDecoder, ICompressionEncoder, LsDecoder12, LsEncoder12, TileBatch, INT4_NULL_CODE,
 )
-from ._lib import FormatError, G4Error  # noqa: F401
+from ._lib import FormatError, G4Error, ValueChecksumWarning  # noqa: F401
 from . import gvrs  # noqa: F401
 from .sharding import gather_layout, record_offsets, shard_tile_rows, tile_content, tile_record_is_compressed  # noqa: F401
 from .predictors import (  # noqa: F401

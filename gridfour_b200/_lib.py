@@ -9,7 +9,7 @@ import os
 _HERE = os.path.dirname(os.path.abspath(__file__))
 LIB_PATH = os.path.join(_HERE, "libg4codec.so")
 
-G4_OK, G4_DECLINED = 0, 1
+G4_OK, G4_DECLINED, G4_CHECKSUM_MISMATCH = 0, 1, 2
 G4_ERR_ARG, G4_ERR_FORMAT, G4_ERR_CAPACITY, G4_ERR_CUDA, G4_ERR_UNSUPPORTED = -1, -2, -3, -4, -5
 G4_CODEC_HUFFMAN, G4_CODEC_DEFLATE, G4_CODEC_FLOAT, G4_CODEC_CANON_HUFFMAN, G4_CODEC_LSOP12 = 0, 1, 2, 3, 4
 G4_ELEM_I32, G4_ELEM_F32, G4_ELEM_I16 = 0, 1, 2
@@ -119,8 +119,18 @@ class FormatError(G4Error, IOError):
     """Malformed packing -- the reference throws IOException here."""
 
 
+class ValueChecksumWarning(UserWarning):
+    """An LSOP12 packing carries a value checksum that its decoded values do not match.  The reference prints the two
+    numbers and returns the values (lsop/LsDecoder12.java:153-158); here the values are returned and this is warned."""
+
+
 def check(status, where=""):
     if status == G4_OK:
+        return
+    if status == G4_CHECKSUM_MISMATCH:
+        import warnings
+
+        warnings.warn("%s: LSOP12 value checksum mismatch" % (where or "decode"), ValueChecksumWarning, stacklevel=3)
         return
     if status == G4_ERR_FORMAT:
         raise FormatError(status, where)

@@ -90,7 +90,7 @@ struct g4_context {
   DevBuf coef;         // LSOP12 decode: 12 float32 coefficients per tile
   DevBuf defer;        // LSOP12 decode: tiles the fast entropy kernel hands to the general one
   DevBuf lsopMeta;     // LSOP12 decode: interior code lengths + text position, kernel H -> kernel T
-  DevBuf lsopSide, lsopExc, lsopResid, lsopStage;  // LSOP12 decode, fast path (g4_lsop_fast.cu): side records, exception lists, residual bytes
+  DevBuf lsopSide, lsopExc, lsopResid, lsopStage, lsopCks;  // LSOP12 decode, fast path (g4_lsop_fast.cu): side records, exception lists, residual bytes
   DevBuf wide;         // TileElementShort: int32 staging raster around the integer codecs
   // zlib-stream encode stages (CodecDeflate, CodecFloat, LSOP12 Deflate alternative)
   DevBuf jobLen, jobOff, jobOut, jobTotal, streamIn, streamOut, deflateWork;
@@ -334,6 +334,9 @@ int launch_decoder(g4_context* ctx, int codecId, DecodeArgs& a, int nCtas) {
       CK(ctx->coef.ensure(size_t(nTiles) * 12 * sizeof(float)));
       CK(ctx->defer.ensure(size_t(nTiles) * sizeof(int)));
       CK(ctx->lsopMeta.ensure(size_t(nTiles) * lsop_meta_bytes()));
+      CK(ctx->lsopCks.ensure(size_t(nTiles) * 8));
+      CK(cudaMemsetAsync(ctx->lsopCks.p, 0, size_t(nTiles) * 8, ctx->stream));
+      a.lsopCks = ctx->lsopCks.as<uint32_t>();
     {
       if (!ctx->lsopStream) {
         CK(cudaStreamCreateWithFlags(&ctx->lsopStream, cudaStreamNonBlocking));
@@ -355,7 +358,8 @@ int launch_decoder(g4_context* ctx, int codecId, DecodeArgs& a, int nCtas) {
       }
       CK(launch_lsop_decode(a, ctx->coef.as<float>(), ctx->lsopMeta.as<uint8_t>(), ctx->defer.as<int>(), ctx->counters.as<int>() + 56,
                             nCtas, nTiles, ctx->stream, ctx->lsopStream, ctx->lsopEv, &nLaunch, useFast ? &fast : nullptr, ctx->smCount));
-      ctx->launches += uint64_t(nLaunch);
+      CK(launch_lsop_value_checksum(a, nTiles, ctx->stream));
+      ctx->launches += uint64_t(nLaunch) + 1;
       return G4_OK;
     }
     default:
@@ -569,10 +573,13 @@ int decode_device(g4_context* ctx, const g4_codec_list* codecs, const g4_band_de
   return G4_OK;
 }
 
-int first_bad_status(const std::vector<int32_t>& st) {
-  for (int32_t s : st)
-    if (s != G4_OK) return s;
-  return G4_OK;
+int first_bad_status(const std::vector<int32_t>& st) {  // errors before notes (G4_DECLINED, G4_CHECKSUM_MISMATCH)
+  int32_t note = G4_OK;
+  for (int32_t s : st) {
+    if (s < 0) return s;
+    if (s != G4_OK && note == G4_OK) note = s;
+  }
+  return note;
 }
 
 }  // namespace
@@ -687,7 +694,7 @@ void g4_context_destroy(g4_context* ctx) {
   }
   for (auto& b : ctx->slots) b.release();
   DevBuf* bufs[] = {&ctx->candLens, &ctx->candPreds, &ctx->candStatus, &ctx->counters, &ctx->scratch, &ctx->lists, &ctx->src,
-                    &ctx->total, &ctx->coef, &ctx->defer, &ctx->lsopMeta, &ctx->lsopSide, &ctx->lsopExc, &ctx->lsopResid, &ctx->lsopStage, &ctx->tileRefs, &ctx->wide, &ctx->encScratch, &ctx->region, &ctx->jobLen, &ctx->jobOff, &ctx->jobOut, &ctx->jobTotal,
+                    &ctx->total, &ctx->coef, &ctx->defer, &ctx->lsopMeta, &ctx->lsopSide, &ctx->lsopExc, &ctx->lsopResid, &ctx->lsopStage, &ctx->tileRefs, &ctx->lsopCks, &ctx->wide, &ctx->encScratch, &ctx->region, &ctx->jobLen, &ctx->jobOff, &ctx->jobOut, &ctx->jobTotal,
                     &ctx->streamIn, &ctx->streamOut, &ctx->deflateWork, &ctx->stSorted, &ctx->stRank, &ctx->stTable,
                     &ctx->stWork, &ctx->stCounters, &ctx->rcPos, &ctx->rcOff, &ctx->rcLen, &ctx->rcCrc, &ctx->rcStored, &ctx->rcTotal,
                     &ctx->rcData, &ctx->rcOffsets, &ctx->rcLens, &ctx->rcIndex, &ctx->rcStatus, &ctx->rcOut, &ctx->sGrid, &ctx->sArena, &ctx->sOffsets, &ctx->sLens, &ctx->sCodec, &ctx->sPred, &ctx->sStatus};
@@ -1263,10 +1270,10 @@ static int decode_one(g4_context* ctx, int codec_id, int elem, int n_rows, int n
   int32_t st = 0;
   CK(cudaMemcpyAsync(&st, ctx->sStatus.p, 4, cudaMemcpyDeviceToHost, ctx->stream));
   CK(cudaStreamSynchronize(ctx->stream));
-  if (st != G4_OK) return st;
+  if (st != G4_OK && st != G4_CHECKSUM_MISMATCH) return st;
   CK(cudaMemcpyAsync(out, ctx->sGrid.p, n * 4, cudaMemcpyDeviceToHost, ctx->stream));
   CK(cudaStreamSynchronize(ctx->stream));
-  return G4_OK;
+  return st;  // G4_OK, or G4_CHECKSUM_MISMATCH with the values delivered
 }
 
 // ---- predictor models on their own (IPredictorModel.java:42-173) ---------------------------------------------------

@@ -54,6 +54,7 @@ struct DecodeArgs {
   uint8_t* scratch;     // per-CTA scratch (M32 bytes etc.), blockIdx.x * scratchStride
   size_t scratchStride;
   int rawShorts;        // raw tiles hold 2-byte samples (TileElementShort): widen them into the int32 raster
+  uint32_t* lsopCks;    // LSOP12: [tile][2] = {packing carries a value checksum, its value}; zeroed before the launch set, or null
 };
 
 struct SelectArgs {
@@ -246,6 +247,9 @@ cudaError_t launch_record_pack(const uint8_t* arena, const uint64_t* offsets, co
                                cudaStream_t s);
 cudaError_t launch_record_unpack(const uint8_t* image, uint64_t imageLen, const uint64_t* contentPos, int n, uint64_t* payloadOff,
                                  uint32_t* lens, uint64_t* crcOff, uint32_t* crcLen, uint32_t* storedCrc, int32_t* status, cudaStream_t s);
+// LSOP12 value checksum (LsDecoder12.java:153-158): CRC-32C of every decoded tile whose packing carries one, compared with the
+// stored value; a mismatch leaves status G4_CHECKSUM_MISMATCH (the values stay delivered: the reference only prints).
+cudaError_t launch_lsop_value_checksum(const DecodeArgs& a, int nTilesUpper, cudaStream_t s);
 cudaError_t launch_record_verify(const uint32_t* computed, const uint32_t* stored, int n, int32_t* status, cudaStream_t s);
 
 }  // namespace g4

@@ -248,6 +248,7 @@ __global__ void __launch_bounds__(kThreads, 5) lsop_decode_head_kernel(DecodeArg
   const uint8_t* packing = a.arena + a.offsets[tIdx];
   const uint32_t len = a.lens[tIdx];
   LsHeaderInfo h = parse_ls_header(packing, len, coefOut + size_t(tIdx) * 12, lane == 0);
+  if (lane == 0 && a.lsopCks && h.ok && h.hasChecksum) { a.lsopCks[2 * tIdx] = 1u; a.lsopCks[2 * tIdx + 1] = h.valueChecksum; }
   if (!h.ok || R < 6 || C < 6) {
     if (lane == 0) a.status[tIdx] = G4_ERR_FORMAT;
     return;
@@ -369,6 +370,7 @@ __global__ void __launch_bounds__(kThreads) lsop_decode_entropy_kernel(DecodeArg
     const uint32_t len = a.lens[tIdx];
     int status = G4_OK;
     LsHeaderInfo h = parse_ls_header(packing, len, coefOut + size_t(tIdx) * 12, tid == 0);
+    if (tid == 0 && a.lsopCks && h.ok && h.hasChecksum) { a.lsopCks[2 * tIdx] = 1u; a.lsopCks[2 * tIdx + 1] = h.valueChecksum; }
     const uint32_t nInit = uint32_t(4 * R + 2 * C - 9);
     const uint32_t nInterior = uint32_t(R - 2) * uint32_t(C - 4);
     if (!h.ok || R < 6 || C < 6) status = G4_ERR_FORMAT;

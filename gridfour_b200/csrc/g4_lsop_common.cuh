@@ -32,6 +32,8 @@ struct LsHeaderInfo {
   uint32_t nInitCodes, nInteriorCodes;
   uint32_t headerSize;
   bool ok;
+  bool hasChecksum;        // LsHeader.valueChecksumIncluded (bit 7 of the type byte)
+  uint32_t valueChecksum;  // CRC-32C of the tile's values as little-endian int32 (LsHeader.computeChecksum :391-406)
 };
 
 // LsHeader(byte[],int) (LsHeader.java:104-189).  Coefficients are written to coef[0..11].
@@ -42,6 +44,8 @@ __device__ inline LsHeaderInfo parse_ls_header(const uint8_t* p, uint32_t len, f
   h.seed = 0;
   h.nInitCodes = h.nInteriorCodes = 0;
   h.headerSize = 0;
+  h.hasChecksum = false;
+  h.valueChecksum = 0;
   if (len < 3 + 4 + 48) return h;
   uint32_t off = 1;
   bool legacy = (p[1] & 0x40) == 0;
@@ -74,7 +78,12 @@ __device__ inline LsHeaderInfo parse_ls_header(const uint8_t* p, uint32_t len, f
     h.nInteriorCodes = load_le32(p + off + 4);
     off += 8;
   }
-  if (cks) off += 4;
+  if (cks) {
+    if (off + 4 > len) return h;
+    h.hasChecksum = true;
+    h.valueChecksum = load_le32(p + off);
+    off += 4;
+  }
   if (off > len || h.type < 0 || h.type > 2) return h;
   h.headerSize = off;
   h.ok = true;

@@ -122,6 +122,7 @@ __global__ void __launch_bounds__(kThreads, 3) lsop2_head_kernel(LsopFastArgs A,
   const uint8_t* packing = a.arena + a.offsets[tIdx];
   const uint32_t len = a.lens[tIdx];
   LsHeaderInfo h = parse_ls_header(packing, len, A.coef + size_t(tIdx) * 12, lane == 0);
+  if (lane == 0 && a.lsopCks && h.ok && h.hasChecksum) { a.lsopCks[2 * tIdx] = 1u; a.lsopCks[2 * tIdx + 1] = h.valueChecksum; }
   if (!h.ok) {
     if (lane == 0) a.status[tIdx] = G4_ERR_FORMAT;
     return;

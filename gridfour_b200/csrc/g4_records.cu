@@ -132,6 +132,71 @@ __global__ void __launch_bounds__(kCrcThreads) crc32c_kernel(const uint8_t* data
   }
 }
 
+// LSOP12 value checksum (LsHeader.computeChecksum :391-406, checked in LsDecoder12.decode :153-158): CRC-32C of the tile's
+// nRows x nColumns values as little-endian int32, row-major.  One WARP per tile of the list whose packing carries the
+// checksum; every lane takes a contiguous run of values (an even number: the slice-by-8 step eats two), the 32 pieces are
+// joined like in crc32c_kernel.  The tile is a strided window of the raster, so the values are read cell by cell.
+__global__ void __launch_bounds__(kCrcThreads) lsop_value_checksum_kernel(DecodeArgs a) {
+  __shared__ uint32_t T[8][256];
+  __shared__ uint32_t x2n[32];
+  crc_build_tables(T);
+  if (threadIdx.x == 0) {
+    uint32_t p = 1u << 30;  // x^1
+    x2n[0] = p;
+    for (int i = 1; i < 32; i++) x2n[i] = p = crc_multmodp(p, p);
+  }
+  __syncthreads();
+  const int lane = threadIdx.x & 31;
+  const int li = (blockIdx.x * kCrcThreads + threadIdx.x) >> 5;
+  if (li >= *a.listCount) return;
+  const int tIdx = a.list[li];
+  if (a.lsopCks[2 * tIdx] == 0u || a.status[tIdx] != G4_OK) return;
+  const TileView t = tile_view(a.band, a.grid, tIdx);
+  const uint32_t n = uint32_t(t.R) * uint32_t(t.C);
+  uint32_t piece = ((n + 31u) / 32u + 1u) & ~1u;
+  if (piece < 16u) piece = 16u;
+  const uint32_t begin = uint32_t(lane) * piece;
+  const uint32_t mine = begin >= n ? 0u : (n - begin < piece ? n - begin : piece);
+  uint32_t c = 0xffffffffu;
+  {
+    int r = int(begin / uint32_t(t.C)), col = int(begin - uint32_t(r) * uint32_t(t.C));
+    const int32_t* row = t.row(r < t.R ? r : 0);
+    auto next = [&]() {
+      const uint32_t v = uint32_t(row[col]);
+      if (++col == t.C) { col = 0; row += t.pitch; }
+      return v;
+    };
+    uint32_t k = 0;
+    for (; k + 2 <= mine; k += 2) {
+      const uint32_t a0 = next() ^ c, b0 = next();
+      c = T[7][a0 & 0xffu] ^ T[6][(a0 >> 8) & 0xffu] ^ T[5][(a0 >> 16) & 0xffu] ^ T[4][a0 >> 24] ^ T[3][b0 & 0xffu] ^ T[2][(b0 >> 8) & 0xffu] ^
+          T[1][(b0 >> 16) & 0xffu] ^ T[0][b0 >> 24];
+    }
+    if (k < mine) {
+      uint32_t v = next();
+      for (int i = 0; i < 4; i++, v >>= 8) c = T[0][(c ^ v) & 0xffu] ^ (c >> 8);
+    }
+  }
+  c = mine ? c ^ 0xffffffffu : 0u;  // CRC of an empty piece is 0, the identity of the join
+  uint32_t myLen = 4u * mine;
+#pragma unroll
+  for (int d = 0; d < 5; d++) {
+    const uint32_t rc = __shfl_down_sync(0xffffffffu, c, 1u << d);
+    const uint32_t rl = __shfl_down_sync(0xffffffffu, myLen, 1u << d);
+    if ((lane & ((2 << d) - 1)) == 0 && rl) {
+      c = crc_multmodp(crc_x2nmodp(x2n, rl, 3), c) ^ rc;
+      myLen += rl;
+    }
+  }
+  if (lane == 0 && c != a.lsopCks[2 * tIdx + 1]) a.status[tIdx] = G4_CHECKSUM_MISMATCH;
+}
+
+cudaError_t launch_lsop_value_checksum(const DecodeArgs& a, int nTilesUpper, cudaStream_t s) {
+  const int warpsPerCta = kCrcThreads / 32;
+  lsop_value_checksum_kernel<<<(nTilesUpper + warpsPerCta - 1) / warpsPerCta, kCrcThreads, 0, s>>>(a);
+  return cudaGetLastError();
+}
+
 // Record sizes and positions of a batch of single-element tile records: size = multipleOf8(12 + 4 + 4 + len), exclusive
 // scan from basePos.  contentPos[t] = record position + 8 (what the tile directory stores, RecordManager.java:218-219);
 // crcOff/crcLen describe the checksummed part of every record relative to `records`.  One CTA.

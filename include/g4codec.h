@@ -35,6 +35,8 @@ extern "C" {
 enum {
   G4_OK = 0,
   G4_DECLINED = 1,
+  G4_CHECKSUM_MISMATCH = 2, /* decode: the tile's values were delivered, but the value checksum its LSOP12 packing carries
+                               does not match them (the reference prints both numbers and carries on, lsop/LsDecoder12.java:153-158) */
   G4_ERR_ARG = -1,      /* bad argument (IllegalArgumentException in the reference) */
   G4_ERR_FORMAT = -2,   /* malformed packing (IOException) */
   G4_ERR_CAPACITY = -3, /* caller's output buffer too small; *out_len holds the size needed */

@@ -177,3 +177,50 @@ def test_batch_best_of_three_matches_oracle(g4, oracle):
         assert batch.payload(t) == best, "tile %d: %s" % (t, first_diff(batch.payload(t), best))
     out = master.decodeTiles(batch)
     assert np.array_equal(out, grid)
+
+
+def test_lsop_value_checksum_is_verified_on_the_gpu(g4, oracle):
+    """LsDecoder12.java:153-158 recomputes the CRC-32C of the decoded values and prints on a mismatch.  The GPU does the
+    same check per tile: a matching checksum is silent, a wrong one still delivers the values and is reported
+    (status G4_CHECKSUM_MISMATCH -> ValueChecksumWarning), per tile in a batch."""
+    import warnings
+
+    tr, tc = 180, 240
+    grid = oracle.terrain_i32(700, 900, tr, 3 * tc)
+    tiles = [np.ascontiguousarray(grid[:, k * tc:(k + 1) * tc]) for k in range(3)]
+    for deflate in (False, True):
+        packs = [oracle.lsop12_encode(0, t, deflate=deflate, checksum=True) for t in tiles]
+        assert all(p[1] & 0x80 for p in packs)
+        dec = g4.LsDecoder12()
+        with warnings.catch_warnings():
+            warnings.simplefilter("error")
+            assert np.array_equal(dec.decode(tr, tc, packs[0]), tiles[0])
+        # the stored value is the reference's: CRC-32C of the little-endian samples
+        hdr = 55 if not deflate else 63
+        if packs[0][1] & 0x0F != 2:
+            hdr = 63
+        stored = int.from_bytes(packs[0][hdr:hdr + 4], "little")
+        assert stored == oracle.crc32c(tiles[0].astype("<i4").tobytes())
+        bad = bytearray(packs[1])
+        bad[hdr] ^= 0x01
+        with pytest.warns(g4.ValueChecksumWarning):
+            out = dec.decode(tr, tc, bytes(bad))
+        assert np.array_equal(out, tiles[1])
+        # batched: only the damaged tile is flagged
+        spec = g4.CodecSpecification(default=False)
+        spec.addCompressionCodec("LSOP12", g4.LsEncoder12, g4.LsDecoder12)
+        master = g4.CodecMaster(spec)
+        arena = bytearray()
+        offsets, lens = [], []
+        for p in (packs[0], bytes(bad), packs[2]):
+            arena += bytes((-len(arena)) & 7)
+            offsets.append(len(arena))
+            lens.append(len(p))
+            arena += p
+        band = master._band((tr, 3 * tc), np.int32, tr, tc)
+        b = g4.TileBatch(np.frombuffer(bytes(arena) + bytes(16), np.uint8), np.array(offsets, np.uint64), np.array(lens, np.uint32), None, None,
+                         None, len(arena), band)
+        with pytest.warns(g4.ValueChecksumWarning):
+            got = master.decodeTiles(b)
+        assert np.array_equal(got, grid)
+        assert master.lastStatus.tolist() == [0, 2, 0]
