@@ -196,13 +196,13 @@ def test_lsop_value_checksum_is_verified_on_the_gpu(g4, oracle):
             warnings.simplefilter("error")
             assert np.array_equal(dec.decode(tr, tc, packs[0]), tiles[0])
         # the stored value is the reference's: CRC-32C of the little-endian samples
-        hdr = 55 if not deflate else 63
-        if packs[0][1] & 0x0F != 2:
-            hdr = 63
-        stored = int.from_bytes(packs[0][hdr:hdr + 4], "little")
+        def cks_pos(p):  # revised header (LsHeader.java:220-245): the two M32 lengths are present unless the body is canonical
+            return 55 if (p[1] & 0x0F) == 2 else 63
+
+        stored = int.from_bytes(packs[0][cks_pos(packs[0]):cks_pos(packs[0]) + 4], "little")
         assert stored == oracle.crc32c(tiles[0].astype("<i4").tobytes())
         bad = bytearray(packs[1])
-        bad[hdr] ^= 0x01
+        bad[cks_pos(packs[1])] ^= 0x01
         with pytest.warns(g4.ValueChecksumWarning):
             out = dec.decode(tr, tc, bytes(bad))
         assert np.array_equal(out, tiles[1])
