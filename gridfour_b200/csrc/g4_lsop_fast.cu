@@ -46,14 +46,12 @@ constexpr int kTextThreads = 512;
 constexpr uint32_t kTextSubBits = 320;        // target sub-sequence size of the text kernel: one sub-sequence per thread for a 180x240 tile
 constexpr int kExcWords = 128;               // per tile: [0] count, [2+2i] interior index, [3+2i] value
 constexpr int kExcCap = (kExcWords - 2) / 2;  // 63 exceptions; more -> general path
-// Staged form of the text decode (lsop_text_decode below): measured on the config-3 shard it executes fewer instructions
-// (0.79 G against 0.86 G warp instructions) but runs 1.43 ms against 1.25 ms -- its one long pass between two barriers leaves the
-// SM idle at the barrier (4.5 barrier stalls per issue).  Kept for reference, off by default.
+// Staged form of the text decode (lsop_text_decode below), on unless built with -DG4_TEXT_STAGED=0.
 #ifndef G4_TEXT_STAGED
-#define G4_TEXT_STAGED 0
+#define G4_TEXT_STAGED 1
 #endif
 constexpr bool kTextStaged = G4_TEXT_STAGED != 0;
-constexpr uint32_t kTextStageBytes = 256u * 1024u;  // staging slots of one text CTA (global memory, L2 resident)
+constexpr int kStageWordsPerThread = 22;  // registers that carry a thread's staged symbol bytes across the barrier
 constexpr int kResidGuard = 256;             // bytes in front of the first tile of the residual scratch
 constexpr float kMagicHalf = 6291456.0f;     // 1.5 * 2^22
 constexpr float kMagicHalfUp = 6291456.5f;   // 1.5 * 2^22 + 1/2
@@ -318,22 +316,23 @@ struct ByteTileSink {
 // ---- staged text decode -------------------------------------------------------------------------------------------
 // canon_fast_decode_text decodes every bit at least twice: once to COUNT the values of each sub-sequence (their output
 // positions are a prefix sum of the counts) and once to write them.  Here the counting pass also keeps the symbol
-// bytes it sees: each sub-sequence has a fixed slot in a per-CTA staging area (global memory, a few hundred bytes per
-// slot, re-used tile after tile and therefore L2 resident), and after the prefix sum the bytes are COPIED from the
-// slot to their place in the tile image instead of being decoded again.  Sub-sequences that hold a value that is no
-// byte (escape, null) are walked once more by text_exceptions_sub, which records the exception list entries.
-constexpr int kSubRare = 4;  // S.eot[] flag: the sub-sequence holds an escape or a null
+// bytes it sees: every sub-sequence has a small slot in the tile image itself (the image is not written before the
+// prefix sum is known, so it is free), and after the prefix sum each thread takes its slot into registers, the CTA
+// synchronises, and the bytes go to their place in the image -- a copy instead of a second decode.  A sub-sequence that
+// outgrows its slot (the slots hold about 10 % more than the average) is decoded a second time like before; one that
+// holds a value that is no byte (escape, null) is walked once more by text_exceptions_sub for the exception list.
+constexpr int kSubRare = 4;      // S.eot[] flag: the sub-sequence holds an escape or a null
+constexpr int kSubOverflow = 8;  // S.eot[] flag: more values than the slot holds
 
-// Like canon_fast_count; additionally stores the symbol byte of every counted value to slot[0 ..) (4-byte words).
+// Like canon_fast_count; additionally stores the symbol byte of every counted value to slot[0 .. slotWords) (shared memory).
 __device__ __forceinline__ void text_stage_sub(const CanonFastShared& S, uint32_t nBits, uint32_t start, uint32_t limit, uint32_t* slot,
-                                               uint32_t* endOut, uint32_t* cntOut, int* flagOut) {
+                                               uint32_t slotWords, uint32_t* endOut, uint32_t* cntOut, int* flagOut) {
   BitCursor cur;
   cur.init(S, start, limit);
   uint32_t c = 0, end;
   int flag = 0;
   uint64_t q = 0;
-  uint32_t qc = 0;
-  uint32_t* wp = slot;
+  uint32_t qc = 0, w = 0;
   for (;;) {
     if (cur.rem >= kFastLutBits) {
       const uint32_t m = S.mlut[cur.peek() & ((1u << kFastLutBits) - 1u)];
@@ -343,7 +342,12 @@ __device__ __forceinline__ void text_stage_sub(const CanonFastShared& S, uint32_
         c += n;
         q |= uint64_t(m & 0xffffffu) << (8 * qc);
         qc += n;
-        if (qc >= 4) { *wp++ = uint32_t(q); q >>= 32; qc -= 4; }
+        if (qc >= 4) {
+          if (w < slotWords) slot[w] = uint32_t(q);
+          w++;
+          q >>= 32;
+          qc -= 4;
+        }
         continue;
       }
     }
@@ -374,12 +378,70 @@ __device__ __forceinline__ void text_stage_sub(const CanonFastShared& S, uint32_
     c++;
     q |= uint64_t(byte) << (8 * qc);
     qc += 1;
-    if (qc >= 4) { *wp++ = uint32_t(q); q >>= 32; qc -= 4; }
+    if (qc >= 4) {
+      if (w < slotWords) slot[w] = uint32_t(q);
+      w++;
+      q >>= 32;
+      qc -= 4;
+    }
   }
-  if (qc) *wp = uint32_t(q);
+  if (qc) {
+    if (w < slotWords) slot[w] = uint32_t(q);
+    w++;
+  }
+  if (w > slotWords) flag |= kSubOverflow;
   *endOut = end;
   *cntOut = c;
   *flagOut = flag;
+}
+
+// The write pass of canon_fast_decode_text for ONE sub-sequence (values from `start` up to the first value at or after
+// `limit`), for the sub-sequences that did not fit their slot.  Returns false for a malformed stream.
+__device__ __forceinline__ bool text_write_sub(const CanonFastShared& S, uint32_t nBits, uint32_t start, uint32_t limit, uint32_t k0,
+                                            ByteTileSink& sink) {
+  BitCursor cur;
+  cur.init(S, start, limit);
+  sink.begin(k0);
+  bool have = false, ok = true;
+  for (;;) {
+    if (cur.rem >= kFastLutBits) {
+      const uint32_t m = S.mlut[cur.peek() & ((1u << kFastLutBits) - 1u)];
+      const uint32_t n = m >> 28;
+      if (n) {
+        cur.skip(S, (m >> 24) & 15u);
+        sink.push(m & 0xffffffu, int(n));
+        have = true;
+        continue;
+      }
+    }
+    const uint32_t e = S.lut[cur.peek() & ((1u << kFastLutBits) - 1u)];
+    if (e - 1u < 0x7fffu) {  // plain value
+      if (cur.rem <= 0) break;
+      cur.skip(S, e >> 9);
+      sink.push(e & 0xffu, 1);
+      have = true;
+      continue;
+    }
+    const uint32_t p0 = cur.pos(limit);
+    uint32_t after;
+    const int sym = canon_fast_rare_symbol(S, e, p0, nBits, &after);
+    if (sym < 0) { ok = false; break; }
+    if (sym == kSymEsc2 || sym == kSymEsc8) {
+      const int nb = sym == kSymEsc2 ? 2 : 8;
+      if (!have || after + nb > nBits) { ok = false; break; }
+      SmemBitSrc src{S.sw, nBits};
+      sink.amend(nb, src.bits(after, nb));
+      after += nb;
+    } else {
+      if (p0 >= limit || sym == kSymEot) break;
+      if (sym == kSymNull) sink.put_rare(INT32_MIN);
+      else sink.push(uint32_t(sym), 1);  // a byte value with a code longer than the LUT
+      have = true;
+    }
+    cur.init(S, after, limit);
+  }
+  sink.end();
+  return ok;
 }
 
 // Exception-list entries of one sub-sequence whose values start at interior index k0 (the bytes are in the image).
@@ -415,7 +477,7 @@ __device__ __noinline__ void text_exceptions_sub(const CanonFastShared& S, uint3
       if (!pending) {
         pk = k - 1;
         const uint32_t o = image_offset(pk);
-        if (tile[o] != 0u || true) pv = int32_t(tile[o]) - 128;
+        pv = int32_t(tile[o]) - 128;
         tile[o] = 0;
         pending = true;
       }
@@ -433,9 +495,9 @@ __device__ __noinline__ void text_exceptions_sub(const CanonFastShared& S, uint3
 }
 
 // Decodes the interior text (tables and LUT ready, text at bit T0) into the tile image.  All kTextThreads threads call.
-// Returns 0 = done, 1 = malformed stream, 2 = the staging slots are too small for this code (caller defers the tile).
-__device__ int lsop_text_decode(CanonFastShared& S, uint32_t nBits, const uint32_t T0, uint32_t nInterior, uint8_t* stage,
-                                uint32_t stageBytes, ByteTileSink sink) {
+// Returns 0 = done, 1 = malformed stream, 2 = the tile does not suit the staged form (caller uses canon_fast_decode_text).
+__device__ int lsop_text_decode(CanonFastShared& S, uint32_t nBits, const uint32_t T0, uint32_t nInterior, uint32_t imageBytes,
+                                ByteTileSink sink) {
   constexpr int NT = kTextThreads;
   constexpr int kRounds = kFastMaxSub / NT;
   const int tid = threadIdx.x;
@@ -446,21 +508,21 @@ __device__ int lsop_text_decode(CanonFastShared& S, uint32_t nBits, const uint32
   uint32_t B = (avail + rounds * NT - 1) / (rounds * NT);
   if (B < 96u) B = 96u;
   const int nSub = int((avail + B - 1) / B);
-  // slot size: a sub-sequence spans at most B + 84 bits (it ends with the first value that starts at or after its
-  // limit, and it may start up to one value late), every counted value has a code of at least minLen bits
-  uint32_t minLen = 1;
-  while (minLen < 15u && S.count[minLen] == 0) minLen++;
-  const uint32_t slotBytes = (((B + 192u) / minLen + 8u) + 15u) & ~15u;
-  if (uint64_t(slotBytes) * uint64_t(nSub) > stageBytes) return 2;
+  // slots: the image cut into nSub equal pieces, capped by what a thread can carry in registers
+  uint32_t slotWords = (imageBytes / uint32_t(nSub)) >> 2;
+  if (slotWords > uint32_t(kStageWordsPerThread) / rounds) slotWords = uint32_t(kStageWordsPerThread) / rounds;
+  // not worth it unless the slots hold the average sub-sequence with some room (else most of them overflow)
+  if (uint64_t(slotWords) * 4u * uint64_t(nSub) * 10u < uint64_t(nInterior) * 11u) return 2;
+  uint32_t* const image32 = reinterpret_cast<uint32_t*>(sink.tile);
   if (tid == 0) S.firstEot = nSub;
   // pass 0: only the END of every sub-sequence matters here, so start kFastLookback bits before the limit and rely on
-  // self-synchronisation; sub-sequence 0 starts at the true text start.
+  // self-synchronisation (sub-sequence 0 as well: every thread does the same amount)
 #pragma unroll 1
   for (int i = tid; i < nSub; i += NT) {
     uint32_t limit = T0 + uint32_t(i + 1) * B;
     if (limit > nBits) limit = nBits;
     uint32_t from = T0 + uint32_t(i) * B;
-    if (limit - from > kFastLookback) from = limit - kFastLookback;  // sub-sequence 0 as well: every thread does the same amount
+    if (limit - from > kFastLookback) from = limit - kFastLookback;
     uint32_t e, c;
     int f;
     canon_fast_count(S, nBits, from, limit, &e, &c, &f);
@@ -481,7 +543,7 @@ __device__ int lsop_text_decode(CanonFastShared& S, uint32_t nBits, const uint32
         if (limit > nBits) limit = nBits;
         uint32_t e, c;
         int f;
-        text_stage_sub(S, nBits, ns, limit, reinterpret_cast<uint32_t*>(stage + size_t(i) * slotBytes), &e, &c, &f);
+        text_stage_sub(S, nBits, ns, limit, image32 + size_t(i) * slotWords, slotWords, &e, &c, &f);
         vend[i] = e;
         S.cnt[i] = uint16_t(c);
         S.eot[i] = uint8_t(f);
@@ -518,41 +580,52 @@ __device__ int lsop_text_decode(CanonFastShared& S, uint32_t nBits, const uint32
       }
     }
   }
-  __syncthreads();
-  // copy pass: slot -> image
-#pragma unroll 1
-  for (int i = tid; i <= fe; i += NT) {
-    const uint32_t n = S.cnt[i];
-    if (n == 0) continue;
-    const uint4* sp = reinterpret_cast<const uint4*>(stage + size_t(i) * slotBytes);
-    sink.begin(offv[i]);
-    // the slot's words are fetched four 16-byte pieces at a time, all four loads in flight before the first is used
-    for (uint32_t done = 0; done < n; done += 64u) {
-      uint4 x[4];
+  // slots -> registers (every thread: sub-sequences tid and tid + NT), barrier, registers -> their place in the image
+  uint32_t r[kStageWordsPerThread];
 #pragma unroll
-      for (int v = 0; v < 4; v++) x[v] = done + 16u * v < n ? __ldcg(sp + v) : make_uint4(0, 0, 0, 0);
-      sp += 4;
+  for (int j = 0; j < kStageWordsPerThread; j++) r[j] = 0;
+  {
+    const uint32_t perSub = uint32_t(kStageWordsPerThread) / rounds;
+    for (uint32_t s = 0; s < rounds; s++) {
+      const int i = tid + int(s) * NT;
+      if (i <= fe && !(S.eot[i] & kSubOverflow)) {
+        const uint32_t* slot = image32 + size_t(i) * slotWords;
 #pragma unroll
-      for (int v = 0; v < 4; v++) {
-        const uint32_t xs[4] = {x[v].x, x[v].y, x[v].z, x[v].w};
-#pragma unroll
-        for (int j = 0; j < 4; j++) {
-          const uint32_t at = done + 16u * v + 4u * j;
-          if (at < n) {
-            const uint32_t m = n - at;
-            sink.push(m >= 4u ? xs[j] : (xs[j] & ((1u << (8 * m)) - 1u)), m >= 4u ? 4 : int(m));
-          }
-        }
+        for (int j = 0; j < kStageWordsPerThread; j++)
+          if (uint32_t(j) >= s * perSub && uint32_t(j) < s * perSub + slotWords) r[j] = slot[uint32_t(j) - s * perSub];
       }
     }
-    sink.end();
-    if (S.eot[i] & kSubRare) {
+  }
+  __syncthreads();
+  bool bad = false;
+  {
+    const uint32_t perSub = uint32_t(kStageWordsPerThread) / rounds;
+    for (uint32_t s = 0; s < rounds; s++) {
+      const int i = tid + int(s) * NT;
+      if (i > fe) continue;
+      const uint32_t n = S.cnt[i];
+      const int flags = S.eot[i];
       uint32_t limit = T0 + uint32_t(i + 1) * B;
       if (limit > nBits) limit = nBits;
-      text_exceptions_sub(S, nBits, S.startv[i], limit, offv[i], sink.tile, sink.exc, sink.w, sink.L, sink.nB4, sink.rpg);
+      if (flags & kSubOverflow) {
+        if (!text_write_sub(S, nBits, S.startv[i], limit, offv[i], sink)) bad = true;
+        continue;
+      }
+      if (n == 0) continue;
+      sink.begin(offv[i]);
+#pragma unroll
+      for (int j = 0; j < kStageWordsPerThread; j++) {
+        const uint32_t at = (uint32_t(j) - s * perSub) * 4u;  // byte position of word j inside this sub-sequence's slot
+        if (uint32_t(j) >= s * perSub && at < n) {
+          const uint32_t m = n - at;
+          sink.push(m >= 4u ? r[j] : (r[j] & ((1u << (8 * m)) - 1u)), m >= 4u ? 4 : int(m));
+        }
+      }
+      sink.end();
+      if (flags & kSubRare) text_exceptions_sub(S, nBits, S.startv[i], limit, offv[i], sink.tile, sink.exc, sink.w, sink.L, sink.nB4, sink.rpg);
     }
   }
-  return 0;
+  return __syncthreads_or(bad ? 1 : 0) ? 1 : 0;
 }
 
 __global__ void __launch_bounds__(kTextThreads, 2) lsop2_text_kernel(LsopFastArgs A, uint32_t stageWords, int listBegin, int listEnd) {
@@ -611,8 +684,9 @@ __global__ void __launch_bounds__(kTextThreads, 2) lsop2_text_kernel(LsopFastArg
       const uint32_t nInterior = uint32_t(A.g.R - 2) * uint32_t(A.g.C - 4);
       ByteTileSink sink;
       sink.init(tileImg, A.exc + size_t(tIdx) * kExcWords, A.g);
-      if (kTextStaged) rc = lsop_text_decode(F, span * 8u, T0 + 8u * delta, nInterior, A.textStage + size_t(blockIdx.x) * kTextStageBytes, kTextStageBytes, sink);
-      else {
+      if (kTextStaged) rc = lsop_text_decode(F, span * 8u, T0 + 8u * delta, nInterior, uint32_t(A.g.tileBytes), sink);
+      else rc = 2;
+      if (rc == 2) {  // (uniform) the two-pass form
         uint32_t endBit = 0, nv = 0;
         rc = (canon_fast_decode_text<ByteTileSink, kTextThreads, kTextSubBits>(F, span * 8u, T0 + 8u * delta, nInterior, 0u, sink, &endBit, &nv) &&
               nv == nInterior) ? 0 : 1;
@@ -622,7 +696,7 @@ __global__ void __launch_bounds__(kTextThreads, 2) lsop2_text_kernel(LsopFastArg
     __syncthreads();
     if (tid == 0) {
       if (rc == 1) a.status[tIdx] = G4_ERR_FORMAT;
-      else if (rc == 2 || A.exc[size_t(tIdx) * kExcWords] > uint32_t(kExcCap)) {  // general kernels
+      else if (A.exc[size_t(tIdx) * kExcWords] > uint32_t(kExcCap)) {  // general kernels
         A.exc[size_t(tIdx) * kExcWords] = uint32_t(kExcCap) + 1u;                  // (the wavefront kernel skips the tile)
         A.defer[atomicAdd(A.deferCount, 1)] = tIdx;
       }
@@ -938,7 +1012,7 @@ bool lsop_fast_geometry(const g4_band_desc& band, const void* grid, LsopFastGeom
 }
 size_t lsop_fast_side_bytes(const LsopFastGeom& g, int nTiles) { return size_t(nTiles) * size_t(g.R) * sizeof(int4); }
 size_t lsop_fast_exc_bytes(int nTiles) { return size_t(nTiles) * kExcWords * sizeof(uint32_t); }
-size_t lsop_fast_stage_bytes(int smCount) { return kTextStaged ? size_t(smCount) * 2 * size_t(kTextStageBytes) : 0; }
+size_t lsop_fast_stage_bytes(int) { return 0; }
 size_t lsop_fast_resid_bytes(const LsopFastGeom& g, int nTiles) { return size_t(kResidGuard) + size_t(nTiles) * size_t(g.tilePitch) + size_t(g.tileBytes) + 4096; }
 
 // Kernels H, T and W over the list positions [0, nTilesUpper).  Tiles the fast path cannot take are appended to
