@@ -73,16 +73,20 @@ def test_float_codec_on_odd_shapes(g4, oracle):
             assert np.array_equal(out.view(np.uint32), tile.view(np.uint32)), tag
 
 
-def test_tiles_thinner_than_two_cells_are_refused(g4):
+def test_tiles_thinner_than_two_cells_are_declined(g4):
     """The Linear predictor reads columns 0 and 1 of every row (PredictorModelLinear.java:120-150), so the reference
-    has no defined result for a one-column tile; the library refuses tiles thinner than 2 in either direction instead of
-    guessing (g4codec.h, G4_ERR_UNSUPPORTED)."""
+    has no defined result for a one-column tile.  The per-tile ENCODE entry declines such tiles like a reference codec
+    that returns null (CodecMaster then stores the tile raw: ICompressionEncoder.java:61); the band entry points and
+    decode refuse the shape (g4codec.h, G4_ERR_UNSUPPORTED)."""
     for shape in ((1, 8), (8, 1), (1, 1)):
         tile = np.zeros(shape, np.int32)
-        with pytest.raises(Exception):
-            g4.CodecHuffman().encode(0, shape[0], shape[1], tile)
+        assert g4.CodecHuffman().encode(0, shape[0], shape[1], tile) is None
+        assert g4.LsEncoder12().encode(0, shape[0], shape[1], tile) is None
+        assert g4.CodecMaster().encode(shape[0], shape[1], tile) is None  # every codec declines -> the caller stores raw
         with pytest.raises(Exception):
             g4.CodecMaster().encodeTiles(tile, shape[0], shape[1])
+        with pytest.raises(Exception):
+            g4.CodecHuffman().decode(shape[0], shape[1], bytes(16))
 
 
 def test_canonical_inconsistent_escape_range_follows_the_reference(g4, oracle):
