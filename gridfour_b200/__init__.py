@@ -16,3 +16,4 @@ from .predictors import (  # noqa: F401
     PredictorModelType,
 )
 from .tilecache import RasterTileCache  # noqa: F401
+from .stats import CodecStats, analyze_tiles  # noqa: F401

@@ -24,7 +24,7 @@ EXPORTS = [
     "g4_encode_f32", "g4_decode_f32", "g4_encode_tiles", "g4_decode_tiles", "g4_encode_arena_bound",
     "g4_fill_terrain", "g4_launch_count", "g4_context_set_timing", "g4_kernel_time_ms", "g4_codec_supported",
     "g4_crc32c", "g4_tile_records_bound", "g4_pack_tile_records", "g4_unpack_tile_records", "g4_context_order_stream", "g4_decode_tiles_bounded", "g4_predictor_encode", "g4_predictor_encode_int", "g4_predictor_decode",
-    "g4_predictor_decode_int", "g4_predictor_tiles", "g4_encode_tile_list", "g4_decode_tile_list",
+    "g4_predictor_decode_int", "g4_predictor_tiles", "g4_encode_tile_list", "g4_decode_tile_list", "g4_analyze_tiles",
 ]
 
 
@@ -91,6 +91,8 @@ def lib():
                                           C.POINTER(C.c_uint64)]
         L.g4_decode_tile_list.argtypes = [C.c_void_p, C.POINTER(CodecList), C.c_int, C.c_int, C.c_int, C.c_int, C.c_int, C.c_void_p, C.c_uint64,
                                           C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p]
+        L.g4_analyze_tiles.argtypes = [C.c_void_p, C.POINTER(CodecList), C.POINTER(BandDesc), C.c_int, C.c_void_p, C.c_uint64, C.c_void_p,
+                                       C.c_void_p, C.c_void_p, C.c_void_p]
         L.g4_fill_terrain.argtypes = [C.c_void_p, C.c_int, C.c_uint64, C.c_int64, C.c_int64, C.c_int64, C.c_int64, C.c_void_p]
         L.g4_context_set_timing.argtypes = [C.c_void_p, C.c_int]
         L.g4_kernel_time_ms.argtypes = [C.c_void_p, C.c_int, C.c_int]

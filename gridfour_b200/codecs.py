@@ -15,6 +15,8 @@ from . import _lib
 from ._lib import (G4_CODEC_CANON_HUFFMAN, G4_CODEC_DEFLATE, G4_CODEC_FLOAT, G4_CODEC_HUFFMAN, G4_CODEC_LSOP12, G4_DECLINED,
                    G4_ELEM_F32, G4_ELEM_I16, G4_ELEM_I32, G4_MEM_DEVICE, G4_MEM_HOST, G4_OK, BandDesc, CodecList, check)
 
+from .stats import AnalysisMixin  # noqa: E402
+
 INT4_NULL_CODE = -(2 ** 31)  # util/GridfourConstants.java:61
 
 
@@ -175,7 +177,8 @@ class ICompressionDecoder:
         check(st, "g4_decode_f32")
         return out
 
-    # analysis hooks of the interface: reporting only, kept as no-ops
+    # analysis hooks of the interface: the M32-based codecs (CodecHuffman, CodecDeflate) implement them through
+    # g4_analyze_tiles (stats.AnalysisMixin); the others keep no statistics here
     def analyze(self, nRows, nColumns, packing):
         pass
 
@@ -191,14 +194,17 @@ class _Codec(ICompressionEncoder, ICompressionDecoder):
         ICompressionEncoder.__init__(self, context)
 
 
-class CodecHuffman(_Codec):
+class CodecHuffman(AnalysisMixin, _Codec):
     """compress/CodecHuffman.java"""
     codec_id = G4_CODEC_HUFFMAN
+    _report_title = "Gridfour_Huffman"
+    _with_tree = True
 
 
-class CodecDeflate(_Codec):
+class CodecDeflate(AnalysisMixin, _Codec):
     """compress/CodecDeflate.java"""
     codec_id = G4_CODEC_DEFLATE
+    _report_title = "Gridfour_Deflate"
 
 
 class CodecFloat(_Codec):

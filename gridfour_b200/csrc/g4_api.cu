@@ -9,6 +9,7 @@
 #include <cstdlib>
 #include <cstring>
 #include <string>
+#include <algorithm>
 #include <vector>
 #include "g4_kernels.h"
 
@@ -1274,6 +1275,70 @@ static int decode_one(g4_context* ctx, int codec_id, int elem, int n_rows, int n
   CK(cudaMemcpyAsync(out, ctx->sGrid.p, n * 4, cudaMemcpyDeviceToHost, ctx->stream));
   CK(cudaStreamSynchronize(ctx->stream));
   return st;  // G4_OK, or G4_CHECKSUM_MISMATCH with the values delivered
+}
+
+// ---- ICompressionDecoder.analyze ----------------------------------------------------------------------------------------
+int g4_analyze_tiles(g4_context* ctx, const g4_codec_list* codecs, const g4_band_desc* band, int mem_space, const uint8_t* arena,
+                     uint64_t arena_len, const uint64_t* offsets, const uint32_t* lens, g4_tile_stats* stats, uint64_t* pair_counts) {
+  if (!ctx || !codecs || !band || !arena || !offsets || !lens || !stats) return G4_ERR_ARG;
+  int rc = check_band(band);
+  if (rc != G4_OK) return rc;
+  if (codecs->n_codecs < 0 || codecs->n_codecs > G4_MAX_CODECS) return G4_ERR_ARG;
+  ENTER(ctx);
+  const int nTiles = band->tiles_down * band->tiles_across;
+  const size_t n = size_t(band->tile_rows) * band->tile_cols;
+  const int nCtas = persistent_ctas(ctx, nTiles, 4);
+  const size_t stride = round_up(n * 6 + 64, 16);
+  CK(ctx->scratch.ensure(stride * nCtas));
+  AnalyzeArgs a{};
+  a.nTiles = nTiles;
+  a.nCells = uint32_t(n);
+  a.rawLen = standard_size(*band);
+  a.codecs = *codecs;
+  a.scratch = ctx->scratch.as<uint8_t>();
+  a.scratchStride = stride;
+  constexpr size_t kPairBytes = size_t(2) * 5 * 65536 * 8;
+  if (mem_space == G4_MEM_DEVICE) {
+    a.arena = arena;
+    a.arenaLen = arena_len;
+    a.offsets = offsets;
+    a.lens = lens;
+    a.stats = stats;
+    a.pairs = reinterpret_cast<unsigned long long*>(pair_counts);
+    CK(launch_analyze(a, nCtas, ctx->stream));
+    ctx->launches++;
+    CK(cudaStreamSynchronize(ctx->stream));
+    return G4_OK;
+  }
+  if (mem_space != G4_MEM_HOST) return G4_ERR_ARG;
+  uint64_t arenaBytes = 0;
+  std::vector<uint64_t> off(offsets, offsets + nTiles);
+  std::vector<uint32_t> ln(lens, lens + nTiles);
+  for (int t = 0; t < nTiles; t++) {
+    if (off[size_t(t)] > arena_len || ln[size_t(t)] > arena_len - off[size_t(t)]) { off[size_t(t)] = 0; ln[size_t(t)] = 0; }  // -> G4_ERR_FORMAT for the tile
+    arenaBytes = std::max<uint64_t>(arenaBytes, off[size_t(t)] + ln[size_t(t)]);
+  }
+  CK(ctx->sArena.ensure(arenaBytes + 16));
+  CK(ctx->sOffsets.ensure(size_t(nTiles) * 8));
+  CK(ctx->sLens.ensure(size_t(nTiles) * 4));
+  CK(ctx->sGrid.ensure(round_up(size_t(nTiles) * sizeof(g4_tile_stats), 16) + (pair_counts ? kPairBytes : 0)));
+  CK(cudaMemcpyAsync(ctx->sArena.p, arena, arenaBytes, cudaMemcpyHostToDevice, ctx->stream));
+  CK(cudaMemcpyAsync(ctx->sOffsets.p, off.data(), size_t(nTiles) * 8, cudaMemcpyHostToDevice, ctx->stream));
+  CK(cudaMemcpyAsync(ctx->sLens.p, ln.data(), size_t(nTiles) * 4, cudaMemcpyHostToDevice, ctx->stream));
+  uint8_t* dPairs = ctx->sGrid.as<uint8_t>() + round_up(size_t(nTiles) * sizeof(g4_tile_stats), 16);
+  if (pair_counts) CK(cudaMemcpyAsync(dPairs, pair_counts, kPairBytes, cudaMemcpyHostToDevice, ctx->stream));
+  a.arena = ctx->sArena.as<uint8_t>();
+  a.arenaLen = arenaBytes;
+  a.offsets = ctx->sOffsets.as<uint64_t>();
+  a.lens = ctx->sLens.as<uint32_t>();
+  a.stats = ctx->sGrid.as<g4_tile_stats>();
+  a.pairs = pair_counts ? reinterpret_cast<unsigned long long*>(dPairs) : nullptr;
+  CK(launch_analyze(a, nCtas, ctx->stream));
+  ctx->launches++;
+  CK(cudaMemcpyAsync(stats, a.stats, size_t(nTiles) * sizeof(g4_tile_stats), cudaMemcpyDeviceToHost, ctx->stream));
+  if (pair_counts) CK(cudaMemcpyAsync(pair_counts, dPairs, kPairBytes, cudaMemcpyDeviceToHost, ctx->stream));
+  CK(cudaStreamSynchronize(ctx->stream));
+  return G4_OK;
 }
 
 // ---- predictor models on their own (IPredictorModel.java:42-173) ---------------------------------------------------

@@ -200,6 +200,23 @@ cudaError_t launch_lsop_decode(const DecodeArgs& a, float* coef, uint8_t* meta, 
                                int nTilesUpper, cudaStream_t s, cudaStream_t s2, cudaEvent_t* ev, int* launches,
                                const LsopFastArgs* fast = nullptr, int smCount = 148);
 
+// ICompressionDecoder.analyze (g4_analyze.cu): per-tile M32 statistics of CodecHuffman / CodecDeflate packings.
+struct AnalyzeArgs {
+  int nTiles;
+  uint32_t nCells;    // tile_rows * tile_cols
+  uint32_t rawLen;
+  g4_codec_list codecs;
+  const uint8_t* arena;
+  uint64_t arenaLen;
+  const uint64_t* offsets;
+  const uint32_t* lens;
+  uint8_t* scratch;   // per-CTA M32 scratch, blockIdx.x * scratchStride (6 * nCells + 64, 16-byte aligned)
+  size_t scratchStride;
+  g4_tile_stats* stats;        // [nTiles]
+  unsigned long long* pairs;   // [2 codecs][5 predictor codes][65536] successor counts (CodecStats.sB), or null
+};
+cudaError_t launch_analyze(const AnalyzeArgs& a, int nCtas, cudaStream_t s);
+
 // Predictor models on their own (g4_predictor.cu): IPredictorModel.encode / decode / encodeInt / decodeInt over a band.
 struct PredictorArgs {
   BandEx band;

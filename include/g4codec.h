@@ -189,6 +189,29 @@ int g4_decode_tile_list(g4_context* ctx, const g4_codec_list* codecs, int elem_t
                         int mem_space, const uint8_t* arena, uint64_t arena_len, const uint64_t* offsets, const uint32_t* lens,
                         void* base, const g4_tile_ref* tiles, int32_t* status);
 
+/* ---- ICompressionDecoder.analyze (compress/ICompressionDecoder.java:79-92) ------------------------------------------------
+ * What CodecHuffman.analyze (:172-199) and CodecDeflate.analyze (:71-106) hand to compress/CodecStats.java:100-155 for
+ * one tile: addToCounts(n_bytes, n_symbols, n_bits_overhead) and, from addCountsForM32, the M32 length, the number of
+ * distinct M32 bytes and the first-order entropy of the tile's M32 stream (bits per byte).  status: G4_OK, G4_DECLINED for
+ * tiles that carry no M32 statistics (raw tiles, the other codecs), G4_ERR_FORMAT for a malformed packing. */
+typedef struct g4_tile_stats {
+  int32_t codec_kind;       /* G4_CODEC_* of the packing, -1 for a raw tile */
+  int32_t predictor;        /* packing[1] */
+  uint32_t n_bytes;         /* packing length - 10 */
+  uint32_t n_symbols;       /* n_rows * n_cols */
+  uint32_t n_bits_overhead; /* HuffmanDecoder.getBitsInTreeCount(); 0 for CodecDeflate */
+  uint32_t n_m32;
+  uint32_t observed;        /* distinct M32 byte values */
+  int32_t status;
+  double entropy;
+} g4_tile_stats;
+/* Every tile of a batch (arguments as in g4_decode_tiles_bounded).  pair_counts (optional, same memory space, caller-zeroed):
+ * [2][5][65536] uint64 successor counts CodecStats.sB -- first index 0 = CodecHuffman, 1 = CodecDeflate, second = the
+ * predictor code -- which the calls ADD to (CodecStats.getH2 :133-165 works on these; sA is the column sum of sB). */
+int g4_analyze_tiles(g4_context* ctx, const g4_codec_list* codecs, const g4_band_desc* band, int mem_space, const uint8_t* arena,
+                     uint64_t arena_len, const uint64_t* offsets, const uint32_t* lens, g4_tile_stats* stats,
+                     uint64_t* pair_counts);
+
 /* Upper bound of the arena bytes g4_encode_tiles can produce for a band (4*n per tile). */
 uint64_t g4_encode_arena_bound(const g4_band_desc* band);
 

@@ -366,3 +366,48 @@ def terrain_f32(row0, col0, nr, nc, seed=TERRAIN_SEED, n_threads=1):
     out = np.zeros((nr, nc), np.float32)
     lib().g4o_terrain_f32(C.c_uint64(seed), C.c_long(row0), C.c_long(col0), C.c_long(nr), C.c_long(nc), _p(out), n_threads)
     return out
+
+
+# ---- ICompressionDecoder.analyze (test infrastructure) ------------------------------------------------------------------
+def analyze_m32(codec, nr, nc, packing):
+    """What CodecHuffman.analyze (compress/CodecHuffman.java:172-199) or CodecDeflate.analyze (compress/CodecDeflate.java:71-106)
+    hands to CodecStats (compress/CodecStats.java:84-131) for one tile, restated with numpy:
+    (predictor, nBytes, nSymbols, nBitsOverhead, nM32, observed, entropy, successor-pair counts[65536])."""
+    import math
+    import zlib
+
+    p = bytes(packing)
+    n_m32 = int.from_bytes(p[6:10], "little")
+    overhead = 0
+    if codec == CODEC_HUFFMAN:
+        m32, _pos = huffman_decode_at(p[10:], n_m32, 0)
+        bits = np.unpackbits(np.frombuffer(p[10:], np.uint8), bitorder="little")
+        n_leaf = int(p[10]) + 1
+        if n_leaf == 1:
+            overhead = 8 + 1 + 8                      # HuffmanDecoder.decodeTree :67-77
+        else:
+            pos, leaves = 8, 0
+            while leaves < n_leaf:                    # pre-order: branch '0', leaf '1' + 8-bit symbol (:80-159)
+                if bits[pos]:
+                    pos += 9
+                    leaves += 1
+                else:
+                    pos += 1
+            overhead = pos
+    elif codec == CODEC_DEFLATE:
+        m32 = zlib.decompress(p[10:])
+        assert len(m32) == n_m32
+    else:
+        raise ValueError("analyze_m32: CodecHuffman or CodecDeflate")
+    b = np.frombuffer(m32, np.uint8)
+    counts = np.bincount(b, minlength=256)
+    d = float(n_m32)
+    s = 0.0
+    for i in range(256):                              # CodecStats.addCountsForM32 :118-125, same order
+        if counts[i] > 0:
+            pr = counts[i] / d
+            s += pr * math.log(pr) / math.log(2.0)
+    pairs = np.zeros(65536, np.uint64)
+    if n_m32 >= 2:
+        np.add.at(pairs, (b[:-1].astype(np.int64) << 8) | b[1:].astype(np.int64), 1)
+    return p[1], len(p) - 10, nr * nc, overhead, n_m32, int((counts > 0).sum()), -s, pairs
