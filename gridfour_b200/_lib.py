@@ -12,6 +12,7 @@ LIB_PATH = os.path.join(_HERE, "libg4codec.so")
 G4_OK, G4_DECLINED, G4_CHECKSUM_MISMATCH = 0, 1, 2
 G4_ERR_ARG, G4_ERR_FORMAT, G4_ERR_CAPACITY, G4_ERR_CUDA, G4_ERR_UNSUPPORTED = -1, -2, -3, -4, -5
 G4_CODEC_HUFFMAN, G4_CODEC_DEFLATE, G4_CODEC_FLOAT, G4_CODEC_CANON_HUFFMAN, G4_CODEC_LSOP12 = 0, 1, 2, 3, 4
+G4_CODEC_LSOP08 = 5
 G4_ELEM_I32, G4_ELEM_F32, G4_ELEM_I16 = 0, 1, 2
 G4_MEM_HOST, G4_MEM_DEVICE = 0, 1
 G4_MAX_CODECS = 16

@@ -12,7 +12,7 @@ import threading
 import numpy as np
 
 from . import _lib
-from ._lib import (G4_CODEC_CANON_HUFFMAN, G4_CODEC_DEFLATE, G4_CODEC_FLOAT, G4_CODEC_HUFFMAN, G4_CODEC_LSOP12, G4_DECLINED,
+from ._lib import (G4_CODEC_CANON_HUFFMAN, G4_CODEC_DEFLATE, G4_CODEC_FLOAT, G4_CODEC_HUFFMAN, G4_CODEC_LSOP08, G4_CODEC_LSOP12, G4_DECLINED,
                    G4_ELEM_F32, G4_ELEM_I16, G4_ELEM_I32, G4_MEM_DEVICE, G4_MEM_HOST, G4_OK, BandDesc, CodecList, check)
 
 from .stats import AnalysisMixin  # noqa: E402
@@ -227,12 +227,25 @@ class LsDecoder12(ICompressionDecoder):
     codec_id = G4_CODEC_LSOP12
 
 
+class LsDecoder08(ICompressionDecoder):
+    """lsop/LsDecoder08.java -- the legacy 8-coefficient codec, decode only (the reference no longer registers it,
+    lsop/LsCodecUtility.java:73)."""
+    codec_id = G4_CODEC_LSOP08
+
+
+class LsEncoder08(ICompressionEncoder):
+    """lsop/LsEncoder08.java is not built on the GPU: every encode is declined (None), so CodecMaster falls through to the
+    next codec or to raw storage.  The class exists so that a codec list naming LSOP08 can be registered for reading."""
+    codec_id = G4_CODEC_LSOP08
+
+
 _STANDARD = {
     "GvrsHuffman": (CodecHuffman, CodecHuffman),
     "GvrsDeflate": (CodecDeflate, CodecDeflate),
     "GvrsFloat": (CodecFloat, CodecFloat),
     "GvrsCanonicalHuffman": (CodecCanonHuffman, CodecCanonHuffman),
     "LSOP12": (LsEncoder12, LsDecoder12),
+    "LSOP08": (LsEncoder08, LsDecoder08),
 }
 
 

@@ -363,6 +363,11 @@ int launch_decoder(g4_context* ctx, int codecId, DecodeArgs& a, int nCtas) {
       ctx->launches += uint64_t(nLaunch) + 1;
       return G4_OK;
     }
+    case G4_CODEC_LSOP08:
+      CK(ctx->coef.ensure(size_t(nTiles) * 12 * sizeof(float)));
+      CK(launch_lsop08_decode(a, ctx->coef.as<float>(), nCtas, nTiles, ctx->stream));
+      ctx->launches += 2;
+      return G4_OK;
     default:
       tlsError = "codec not implemented on the GPU yet";
       return G4_ERR_UNSUPPORTED;
@@ -408,6 +413,7 @@ int encode_device_i32(g4_context* ctx, const g4_codec_list* codecs, const g4_ban
   for (int k = 0; k < codecs->n_codecs; k++) {
     int id = codecs->codec_ids[k];
     if (id < 0 || id >= G4_CODEC_COUNT) return G4_ERR_ARG;
+    if (id == G4_CODEC_LSOP08) continue;  // decode-only legacy codec: its encoder declines every tile
     if (codec_is_float(id) == isFloat) cand[nCand++] = k;
   }
   CK(ctx->candLens.ensure(size_t(nCand + 1) * nTiles * 4));
@@ -610,7 +616,7 @@ int g4_device_count(void) {
   return n;
 }
 
-static const char* kCodecNames[G4_CODEC_COUNT] = {"GvrsHuffman", "GvrsDeflate", "GvrsFloat", "GvrsCanonicalHuffman", "LSOP12"};
+static const char* kCodecNames[G4_CODEC_COUNT] = {"GvrsHuffman", "GvrsDeflate", "GvrsFloat", "GvrsCanonicalHuffman", "LSOP12", "LSOP08"};
 
 int g4_codec_id_from_name(const char* name) {
   if (!name) return -1;
@@ -727,6 +733,7 @@ int g4_codec_supported(int codec_id, int direction) {
     case G4_CODEC_FLOAT: return 1;
     case G4_CODEC_CANON_HUFFMAN: return 1;
     case G4_CODEC_LSOP12: return 1;
+    case G4_CODEC_LSOP08: return direction == 0 ? 1 : 0;  // legacy codec: decode only
     default: return 0;
   }
 }
@@ -1180,6 +1187,7 @@ static int encode_one(g4_context* ctx, int codec_id, int codec_index, int elem, 
   if (!ctx || !values || !out || !out_len) return G4_ERR_ARG;
   if (codec_id < 0 || codec_id >= G4_CODEC_COUNT || codec_index < 0 || codec_index > 255) return G4_ERR_ARG;
   if (codec_is_float(codec_id) != (elem == G4_ELEM_F32)) return G4_DECLINED;  // e.g. CodecHuffman.encodeFloats -> null
+  if (codec_id == G4_CODEC_LSOP08) return G4_DECLINED;  // decode-only legacy codec (include/g4codec.h)
   g4_band_desc band{elem, n_rows, n_cols, 1, 1, n_cols};
   int rc = check_band(&band);
   // a shape the kernels do not take (a one-row / one-column tile, more than 2^20 samples): the codec declines like a

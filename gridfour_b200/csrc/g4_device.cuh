@@ -18,6 +18,8 @@ constexpr int32_t kNull = INT32_MIN;  // util/GridfourConstants.java:61
 // residual stream orders beyond the predictor codes (used with stream_to_cell)
 constexpr int kStreamLsopInit = 5;
 constexpr int kStreamLsopInterior = 6;
+constexpr int kStreamLsop8Init = 7;      // LSOP08: row 0 | row 1 (all columns) | columns 0,1 of every row from 2
+constexpr int kStreamLsop8Interior = 8;  // LSOP08: rows 2.., columns 2..C-1
 
 // ------------------------------------------------------------------------------------------------
 // Tile view: a tile is a strided window of the row-major raster held in HBM.
@@ -191,6 +193,17 @@ __device__ __forceinline__ void stream_to_cell(int pred, int k, int R, int C, in
     k -= R - 2;
     *r = 2 + (k >> 1);
     *c = C - 2 + (k & 1);
+  } else if (pred == kStreamLsop8Init) {
+    // LsOptimalPredictor08.java:70-104: row 0 (C-1) | row 1 (C) | for r = 2..R-1: (r,0), (r,1)
+    if (k < C - 1) { *r = 0; *c = k + 1; return; }
+    k -= C - 1;
+    if (k < C) { *r = 1; *c = k; return; }
+    k -= C;
+    *r = 2 + (k >> 1);
+    *c = k & 1;
+  } else if (pred == kStreamLsop8Interior) {
+    int rr = k / (C - 2);
+    *r = 2 + rr; *c = 2 + k - rr * (C - 2);
   } else if (pred == kStreamLsopInterior) {
     // LsOptimalPredictor12.java:254-282: rows 2.., columns 2..C-3, row-major
     int rr = k / (C - 4);

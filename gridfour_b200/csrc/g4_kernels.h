@@ -162,6 +162,8 @@ cudaError_t launch_float_decode(const DecodeArgs& a, uint8_t* region, size_t reg
 // chunk counters of the text kernel); s2 / ev (5 events): second stream for the chunked overlap, or null
 // meta: nTilesUpper * lsop_meta_bytes() bytes (interior code lengths + text position handed from kernel H to kernel T)
 size_t lsop_meta_bytes();
+// LSOP08, the legacy 8-coefficient codec (decode only): entropy stage + initializers, then the wavefront
+cudaError_t launch_lsop08_decode(const DecodeArgs& a, float* coef, int nCtas, int nTilesUpper, cudaStream_t s);
 
 
 // LSOP12 decode, fast path (g4_lsop_fast.cu): byte hand-over between the text kernel and a TMA-fed wavefront kernel.

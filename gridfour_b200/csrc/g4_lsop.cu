@@ -430,6 +430,147 @@ __global__ void __launch_bounds__(kThreads) lsop_decode_entropy_kernel(DecodeArg
   }
 }
 
+// ---- LSOP08: the legacy 8-coefficient codec (decode only) ------------------------------------------------------------
+// lsop/LsDecoder08.java:65-163.  Same header class as LSOP12 (eight coefficients), legacy Huffman or two zlib streams over
+// M32 bytes, other initializers (rows 0 and 1 whole, columns 0 and 1 of the rest), an 8-tap stencil that only looks up and
+// left, and the estimate is (int)(p + 0.5f) -- float addition, then truncation -- instead of StrictMath.round.
+// The reference no longer registers this codec (lsop/LsCodecUtility.java:73), so it gets the plain general form.
+__global__ void __launch_bounds__(kThreads) lsop08_decode_entropy_kernel(DecodeArgs a, float* coefOut) {
+  __shared__ LsopDecShared S;
+  __shared__ int sTile;
+  __shared__ uint32_t scanM[kWarps + 1];
+  __shared__ int sInfOk;
+  const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+  for (;;) {
+    __syncthreads();
+    if (tid == 0) sTile = atomicAdd(a.counter, 1);
+    __syncthreads();
+    const int li = sTile;
+    if (li >= *a.listCount) break;
+    const int tIdx = a.list[li];
+    const TileView t = tile_view(a.band, a.grid, tIdx);
+    const int R = t.R, C = t.C;
+    const uint8_t* packing = a.arena + a.offsets[tIdx];
+    const uint32_t len = a.lens[tIdx];
+    int status = G4_OK;
+    LsHeaderInfo h = parse_ls_header(packing, len, coefOut + size_t(tIdx) * 12, tid == 0, 8);
+    const uint32_t nInit = uint32_t((C - 1) + C + 2 * (R - 2));
+    const uint32_t nInterior = uint32_t(R - 2) * uint32_t(C - 2);
+    if (!h.ok || R < 3 || C < 3) status = G4_ERR_FORMAT;
+    else if (h.nInitCodes < nInit || h.nInitCodes > 6 * nInit || h.nInteriorCodes < nInterior || h.nInteriorCodes > 6 * nInterior)
+      status = G4_ERR_FORMAT;
+    if (status == G4_OK) {
+      uint8_t* m32a = a.scratch + size_t(blockIdx.x) * a.scratchStride;
+      uint8_t* m32b = m32a + ((size_t(h.nInitCodes) + 31) & ~size_t(15));
+      bool entropyOk;
+      if (h.type != 0) {  // LsDecoder08.java:83-105: everything but type 0 is two zlib streams
+        if (warp == 0) {
+          const uint8_t* z = packing + h.headerSize;
+          const uint32_t zLen = len - h.headerSize;
+          uint32_t produced = 0, consumed = 0;
+          int rc = inflate_warp(S.inf, z, zLen, m32a, h.nInitCodes, &produced, &consumed);
+          bool ok = rc == kInfOk && produced == h.nInitCodes && consumed <= zLen;
+          if (ok) {
+            const uint32_t c1 = consumed;
+            rc = inflate_warp(S.inf, z + c1, zLen - c1, m32b, h.nInteriorCodes, &produced, &consumed);
+            ok = rc == kInfOk && produced == h.nInteriorCodes;
+          }
+          if (lane == 0) sInfOk = ok ? 1 : 0;
+        }
+        __syncthreads();
+        entropyOk = sInfOk != 0;
+      } else {
+        BitSrc src;
+        src.init(packing + h.headerSize, len - h.headerSize);
+        uint32_t endBit = 0;
+        entropyOk = huffman_decode_stream(S.h, src, 0, h.nInitCodes, m32a, &endBit) &&
+                    huffman_decode_stream(S.h, src, endBit, h.nInteriorCodes, m32b, &endBit);
+      }
+      if (!entropyOk) status = G4_ERR_FORMAT;
+      else {
+        __syncthreads();
+        if (!m32_parse_to_cells(m32a, h.nInitCodes, kStreamLsop8Init, t, nInit, scanM)) status = G4_ERR_FORMAT;
+        else if (!m32_parse_to_cells(m32b, h.nInteriorCodes, kStreamLsop8Interior, t, nInterior, scanM)) status = G4_ERR_FORMAT;
+      }
+    }
+    if (status == G4_OK) {
+      // LsDecoder08.unpackInitializers (:115-135)
+      __syncthreads();
+      if (tid == 0) t.at(0, 0) = h.seed;
+      __syncthreads();
+      if (warp == 0) row_scan_warp(t.row(0), C, 0);            // v[0][c] = seed + d[1] + ... + d[c]
+      if (warp == 1) row_scan_warp(t.row(1), C, 0);            // running sum of row 1's differences
+      __syncthreads();
+      for (int c = tid; c < C; c += kThreads) t.at(1, c) = int32_t(uint32_t(t.at(1, c)) + uint32_t(h.seed));
+      __syncthreads();
+      uint32_t carry = uint32_t(t.at(1, 0));                   // column 0 from row 2: v[r][0] = v[r-1][0] + d
+      for (int r0 = 2; r0 < R; r0 += kThreads) {
+        const int r = r0 + tid;
+        const uint32_t x = r < R ? uint32_t(t.at(r, 0)) : 0u;
+        uint32_t tot;
+        const uint32_t ex = block_exclusive_scan(x, scanM, &tot);
+        if (r < R) {
+          const uint32_t v0 = carry + ex + x;
+          t.at(r, 0) = int32_t(v0);
+          t.at(r, 1) = int32_t(v0 + uint32_t(t.at(r, 1)));   // v[r][1] = v[r][0] + d
+        }
+        carry += tot;
+      }
+    }
+    __syncthreads();
+    if (tid == 0) a.status[tIdx] = status;
+  }
+}
+
+// One warp per tile, lane = row, one column behind the lane above (the stencil never looks right of its own column).
+__global__ void __launch_bounds__(kThreads) lsop08_wavefront_kernel(DecodeArgs a, const float* coef) {
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  const int li = blockIdx.x * kWarps + warp;
+  if (li >= *a.listCount) return;
+  const int tIdx = a.list[li];
+  if (a.status[tIdx] != G4_OK) return;
+  const TileView t = tile_view(a.band, a.grid, tIdx);
+  const int R = t.R, C = t.C;
+  float u[8];
+#pragma unroll
+  for (int i = 0; i < 8; i++) u[i] = coef[size_t(tIdx) * 12 + i];
+  for (int r0 = 2; r0 < R; r0 += 32) {
+    const int r = r0 + lane;
+    const bool active = r < R;
+    const int rr = active ? r : R - 1;
+    int32_t* rowp = t.row(rr);
+    const int32_t* up1 = t.row(rr - 1);
+    const int32_t* up2 = t.row(rr - 2);
+    float v1 = float(rowp[1]), v2 = float(rowp[0]);  // own row, columns c-1 and c-2
+    const int lastLane = (R - 1 - r0) < 31 ? (R - 1 - r0) : 31;
+    const int nSteps = (C - 2) + lastLane;
+    __syncwarp();
+    for (int s = 0; s < nSteps; s++) {
+      const int c = 2 + s - lane;
+      if (active && c >= 2 && c < C) {
+        // rows r-1 and r-2 up to column c were finished in earlier steps (or by the previous row group)
+        const float a1 = float(__ldcg(up1 + c - 1)), a0 = float(__ldcg(up1 + c)), a2 = float(__ldcg(up1 + c - 2));
+        const float b2 = float(__ldcg(up2 + c - 2)), b1 = float(__ldcg(up2 + c - 1)), b0 = float(__ldcg(up2 + c));
+        // LsDecoder08.java:151-159 -- evaluated left to right in float32, no fused multiply-add
+        float p = u[0] * v1;
+        p = p + u[1] * a1;
+        p = p + u[2] * a0;
+        p = p + u[3] * v2;
+        p = p + u[4] * a2;
+        p = p + u[5] * b2;
+        p = p + u[6] * b1;
+        p = p + u[7] * b0;
+        const int32_t val = int32_t(uint32_t(__float2int_rz(p + 0.5f)) + uint32_t(rowp[c]));  // (int)(p + 0.5f) + residual
+        rowp[c] = val;
+        v2 = v1;
+        v1 = float(val);
+      }
+      __threadfence_block();
+      __syncwarp();
+    }
+  }
+}
+
 // ---- kernel B: wavefront ------------------------------------------------------------------------------
 __global__ void __launch_bounds__(kThreads) lsop_wavefront_kernel(DecodeArgs a, const float* coef) {
   const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
@@ -1025,6 +1166,14 @@ cudaError_t launch_lsop_encode(const EncodeArgs& a, int nCtas, cudaStream_t s) {
 }
 
 size_t lsop_meta_bytes() { return kLsopMetaBytes; }
+
+cudaError_t launch_lsop08_decode(const DecodeArgs& a, float* coef, int nCtas, int nTilesUpper, cudaStream_t s) {
+  lsop08_decode_entropy_kernel<<<nCtas < 296 ? nCtas : 296, kThreads, 0, s>>>(a, coef);
+  cudaError_t e = cudaGetLastError();
+  if (e != cudaSuccess) return e;
+  lsop08_wavefront_kernel<<<(nTilesUpper + kWarps - 1) / kWarps, kThreads, 0, s>>>(a, coef);
+  return cudaGetLastError();
+}
 
 cudaError_t launch_lsop_decode(const DecodeArgs& a, float* coef, uint8_t* meta, int* defer, int* deferCounters, int nCtas,
                                int nTilesUpper, cudaStream_t s, cudaStream_t s2, cudaEvent_t* ev, int* launches,

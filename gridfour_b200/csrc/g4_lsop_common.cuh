@@ -37,7 +37,7 @@ struct LsHeaderInfo {
 };
 
 // LsHeader(byte[],int) (LsHeader.java:104-189).  Coefficients are written to coef[0..11].
-__device__ inline LsHeaderInfo parse_ls_header(const uint8_t* p, uint32_t len, float* coef, bool writeCoef) {
+__device__ inline LsHeaderInfo parse_ls_header(const uint8_t* p, uint32_t len, float* coef, bool writeCoef, int nCoef = 12) {
   LsHeaderInfo h;
   h.ok = false;
   h.type = -1;
@@ -46,21 +46,21 @@ __device__ inline LsHeaderInfo parse_ls_header(const uint8_t* p, uint32_t len, f
   h.headerSize = 0;
   h.hasChecksum = false;
   h.valueChecksum = 0;
-  if (len < 3 + 4 + 48) return h;
+  if (len < uint32_t(3 + 4 + 4 * nCoef)) return h;
   uint32_t off = 1;
   bool legacy = (p[1] & 0x40) == 0;
   bool cks;
   if (legacy) {
-    if (p[off++] != 12) return h;
+    if (p[off++] != nCoef) return h;
   } else {
     h.type = p[off] & 0x0f;
     cks = (p[off] & 0x80) != 0;
     off++;
-    if (p[off++] != 12) return h;
+    if (p[off++] != nCoef) return h;
   }
   h.seed = int32_t(load_le32(p + off));
   off += 4;
-  for (int i = 0; i < 12; i++) {
+  for (int i = 0; i < nCoef; i++) {
     if (writeCoef) coef[i] = __uint_as_float(load_le32(p + off));
     off += 4;
   }

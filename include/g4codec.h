@@ -52,7 +52,9 @@ enum {
   G4_CODEC_FLOAT = 2,         /* "GvrsFloat"            C/compress/CodecFloat.java */
   G4_CODEC_CANON_HUFFMAN = 3, /* "GvrsCanonicalHuffman" C/compress/canonicalHuffman/CodecCanonHuffman.java */
   G4_CODEC_LSOP12 = 4,        /* "LSOP12"               C/lsop/LsEncoder12.java + LsDecoder12.java */
-  G4_CODEC_COUNT = 5
+  G4_CODEC_LSOP08 = 5,        /* "LSOP08"               C/lsop/LsDecoder08.java -- legacy, DECODE ONLY (the reference itself no
+                                                         longer registers it, C/lsop/LsCodecUtility.java:73); encode declines */
+  G4_CODEC_COUNT = 6
 };
 
 /* Predictor codes stored in packing[1] (C/compress/PredictorModelType.java:46-63). */

@@ -108,6 +108,22 @@ int g4o_huffman_decode_at(const uint8_t* in, long nbytes, int nsym, uint8_t* out
   return 0;
   G4O_CATCH(-1)
 }
+// LSOP08: returns the packing length, -1 when the codec declines (null / singular matrix), -2 cap too small, -3 exception
+long g4o_lsop08_encode(int codecIndex, int nr, int nc, const int32_t* v, uint8_t* out, long cap) {
+  G4O_TRY
+  std::vector<uint8_t> p;
+  if (!codec_lsop08_encode(codecIndex, nr, nc, v, p)) return -1;
+  if (long(p.size()) > cap) return -2;
+  std::copy(p.begin(), p.end(), out);
+  return long(p.size());
+  G4O_CATCH(-3)
+}
+int g4o_lsop08_decode(int nr, int nc, const uint8_t* packing, long len, int32_t* out) {
+  G4O_TRY
+  codec_lsop08_decode(nr, nc, packing, size_t(len), out);
+  return 0;
+  G4O_CATCH(-1)
+}
 int32_t g4o_java_round(float a) { return java_round_float(a); }
 uint32_t g4o_crc32c(const uint8_t* p, long n) { return crc32c(p, size_t(n)); }
 

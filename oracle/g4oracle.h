@@ -149,6 +149,10 @@ int length_encode(int n, const int* codeLen, int* codes, int* runs);            
 // LSOP12 (C/lsop/*.java, C/util/jama/LUDecomposition.java)
 // ---------------------------------------------------------------------------------------------
 bool lsop12_coefficients(int nRows, int nCols, const int32_t* values, double ud[12]);
+// LSOP08 (legacy 8-coefficient codec): lsop/LsOptimalPredictor08.java, LsEncoder08.java, LsDecoder08.java (g4o_lsop08.cpp)
+bool lsop08_coefficients(int nRows, int nCols, const int32_t* values, double ud[8]);
+bool codec_lsop08_encode(int codecIndex, int nRows, int nCols, const int32_t* v, std::vector<uint8_t>& out);
+void codec_lsop08_decode(int nRows, int nCols, const uint8_t* packing, size_t len, int32_t* values);
 bool lsop12_residual_streams(int nRows, int nCols, const int32_t* v, int32_t* seed, float u[12], uint8_t* initCodes, long* nInit,
                              uint8_t* interiorCodes, long* nInterior);  // LsOptimalPredictor12.java:109-292 (test infrastructure)  // LsOptimalPredictor12.java:311-383
 int32_t java_round_float(float a);                                                     // StrictMath.round(float)

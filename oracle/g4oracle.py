@@ -39,6 +39,7 @@ def lib():
         L.g4o_canon_encode.restype = C.c_long
         L.g4o_codec_encode_i32.restype = C.c_long
         L.g4o_lsop12_encode_opts.restype = C.c_long
+        L.g4o_lsop08_encode.restype = C.c_long
         L.g4o_codec_encode_f32.restype = C.c_long
         L.g4o_master_encode_i32.restype = C.c_long
         L.g4o_master_encode_f32.restype = C.c_long
@@ -183,6 +184,28 @@ def lsop12_coefficients(tile):
     ud = np.zeros(12, np.float64)
     ok = lib().g4o_lsop12_coefficients(nr, nc, _p(t), _p(ud))
     return ud if ok else None
+
+
+def lsop08_encode(codec_index, tile):
+    """LsEncoder08.encode (legacy 8-coefficient codec); None where the reference returns null / throws on a singular matrix."""
+    t = _i32(tile)
+    nr, nc = t.shape
+    cap = t.size * 8 + 4096
+    out = np.zeros(cap, np.uint8)
+    n = lib().g4o_lsop08_encode(codec_index, nr, nc, _p(t), _p(out), C.c_long(cap))
+    if n == -1:
+        return None
+    if n < 0:
+        raise ValueError("oracle LSOP08 encode failed (%d)" % n)
+    return out[:n].tobytes()
+
+
+def lsop08_decode(nr, nc, packing):
+    b = _u8(packing)
+    out = np.zeros((nr, nc), np.int32)
+    if lib().g4o_lsop08_decode(nr, nc, _p(b), C.c_long(b.size), _p(out)):
+        raise IOError("oracle LSOP08 decode failed")
+    return out
 
 
 def lsop12_residual_streams(tile):

@@ -282,3 +282,20 @@ def test_terrain_statistics(oracle):
     assert n < 1.25 * t.size
     f = oracle.terrain_f32(3, 5, 8, 8)
     assert np.all(np.abs(f * 10 - np.round(f * 10)) < 1e-2)
+
+
+def test_lsop08_oracle_round_trip(oracle):
+    """LsEncoder08 / LsDecoder08 restatement (oracle/g4o_lsop08.cpp): lossless on terrain, ramps and noise; both body types."""
+    rng = np.random.default_rng(11)
+    kinds = set()
+    grids = [oracle.terrain_i32(0, 0, 90, 120), oracle.terrain_i32(4000, 100, 37, 41),
+             rng.integers(-3, 4, (33, 47)).astype(np.int32), rng.integers(-40000, 40000, (31, 29)).astype(np.int32),
+             rng.integers(-(2 ** 31), 2 ** 31, (20, 30), dtype=np.int64).astype(np.int32)]
+    for g in grids:
+        p = oracle.lsop08_encode(2, g)
+        assert p is not None and p[0] == 2 and p[2] == 8
+        kinds.add(p[1] & 0x0F)
+        assert np.array_equal(oracle.lsop08_decode(g.shape[0], g.shape[1], p), g)
+    assert kinds == {0, 1}
+    assert oracle.lsop08_encode(0, np.full((12, 17), 42, np.int32)) is None  # singular normal equations
+    assert oracle.lsop08_encode(0, np.zeros((3, 9), np.int32)) is None       # LsOptimalPredictor08.java:60-62
