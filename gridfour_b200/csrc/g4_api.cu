@@ -356,6 +356,8 @@ int launch_decoder(g4_context* ctx, int codecId, DecodeArgs& a, int nCtas) {
         fast.resid = ctx->lsopResid.as<uint8_t>();
         if (lsop_fast_stage_bytes(ctx->smCount)) CK(ctx->lsopStage.ensure(lsop_fast_stage_bytes(ctx->smCount)));
         fast.textStage = ctx->lsopStage.as<uint8_t>();
+        static const int lookbackEnv = getenv("G4_TEXT_LOOKBACK") ? atoi(getenv("G4_TEXT_LOOKBACK")) : 0;
+        fast.textLookback = lookbackEnv > 0 ? uint32_t(lookbackEnv) : 96u;
       }
       CK(launch_lsop_decode(a, ctx->coef.as<float>(), ctx->lsopMeta.as<uint8_t>(), ctx->defer.as<int>(), ctx->counters.as<int>() + 56,
                             nCtas, nTiles, ctx->stream, ctx->lsopStream, ctx->lsopEv, &nLaunch, useFast ? &fast : nullptr, ctx->smCount));

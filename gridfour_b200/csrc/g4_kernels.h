@@ -186,7 +186,8 @@ struct LsopFastArgs {
   int4* side;         // [nTiles][R]: {v[r][0], v[r][1], D2[r], D1[r]}
   uint32_t* exc;      // [nTiles][128]: residuals that are no byte
   uint8_t* resid;     // residual scratch (lsop_fast_resid_bytes)
-  uint8_t* textStage; // staging slots of the text kernel, one area per persistent CTA (lsop_fast_stage_bytes)
+  uint8_t* textStage; // spill words behind the staging slots of the text kernel, one area per persistent CTA (lsop_fast_stage_bytes)
+  uint32_t textLookback;  // bits before a sub-sequence limit at which the text kernel's first pass starts decoding
   int* defer;         // tiles for the general kernels
   int* deferCount;
   LsopFastGeom g;

@@ -52,6 +52,8 @@ constexpr int kExcCap = (kExcWords - 2) / 2;  // 63 exceptions; more -> general 
 #endif
 constexpr bool kTextStaged = G4_TEXT_STAGED != 0;
 constexpr int kStageWordsPerThread = 22;  // registers that carry a thread's staged symbol bytes across the barrier
+constexpr int kSpillWords = 8;            // words behind every slot in a per-CTA global scratch (stays in L2): the slots hold only
+                                          // about 7 % more than the average sub-sequence, so the longer ones spill their tail
 constexpr int kResidGuard = 256;             // bytes in front of the first tile of the residual scratch
 constexpr float kMagicHalf = 6291456.0f;     // 1.5 * 2^22
 constexpr float kMagicHalfUp = 6291456.5f;   // 1.5 * 2^22 + 1/2
@@ -326,7 +328,7 @@ constexpr int kSubOverflow = 8;  // S.eot[] flag: more values than the slot hold
 
 // Like canon_fast_count; additionally stores the symbol byte of every counted value to slot[0 .. slotWords) (shared memory).
 __device__ __forceinline__ void text_stage_sub(const CanonFastShared& S, uint32_t nBits, uint32_t start, uint32_t limit, uint32_t* slot,
-                                               uint32_t slotWords, uint32_t* endOut, uint32_t* cntOut, int* flagOut) {
+                                               uint32_t slotWords, uint32_t* spill, uint32_t* endOut, uint32_t* cntOut, int* flagOut) {
   BitCursor cur;
   cur.init(S, start, limit);
   uint32_t c = 0, end;
@@ -344,6 +346,7 @@ __device__ __forceinline__ void text_stage_sub(const CanonFastShared& S, uint32_
         qc += n;
         if (qc >= 4) {
           if (w < slotWords) slot[w] = uint32_t(q);
+          else if (w - slotWords < uint32_t(kSpillWords)) spill[w - slotWords] = uint32_t(q);
           w++;
           q >>= 32;
           qc -= 4;
@@ -380,6 +383,7 @@ __device__ __forceinline__ void text_stage_sub(const CanonFastShared& S, uint32_
     qc += 1;
     if (qc >= 4) {
       if (w < slotWords) slot[w] = uint32_t(q);
+      else if (w - slotWords < uint32_t(kSpillWords)) spill[w - slotWords] = uint32_t(q);
       w++;
       q >>= 32;
       qc -= 4;
@@ -387,9 +391,10 @@ __device__ __forceinline__ void text_stage_sub(const CanonFastShared& S, uint32_
   }
   if (qc) {
     if (w < slotWords) slot[w] = uint32_t(q);
+    else if (w - slotWords < uint32_t(kSpillWords)) spill[w - slotWords] = uint32_t(q);
     w++;
   }
-  if (w > slotWords) flag |= kSubOverflow;
+  if (w > slotWords + uint32_t(kSpillWords)) flag |= kSubOverflow;
   *endOut = end;
   *cntOut = c;
   *flagOut = flag;
@@ -497,7 +502,7 @@ __device__ __noinline__ void text_exceptions_sub(const CanonFastShared& S, uint3
 // Decodes the interior text (tables and LUT ready, text at bit T0) into the tile image.  All kTextThreads threads call.
 // Returns 0 = done, 1 = malformed stream, 2 = the tile does not suit the staged form (caller uses canon_fast_decode_text).
 __device__ int lsop_text_decode(CanonFastShared& S, uint32_t nBits, const uint32_t T0, uint32_t nInterior, uint32_t imageBytes,
-                                ByteTileSink sink) {
+                                ByteTileSink sink, uint32_t* spillArea, uint32_t lookback) {
   constexpr int NT = kTextThreads;
   constexpr int kRounds = kFastMaxSub / NT;
   const int tid = threadIdx.x;
@@ -511,8 +516,8 @@ __device__ int lsop_text_decode(CanonFastShared& S, uint32_t nBits, const uint32
   // slots: the image cut into nSub equal pieces, capped by what a thread can carry in registers
   uint32_t slotWords = (imageBytes / uint32_t(nSub)) >> 2;
   if (slotWords > uint32_t(kStageWordsPerThread) / rounds) slotWords = uint32_t(kStageWordsPerThread) / rounds;
-  // not worth it unless the slots hold the average sub-sequence with some room (else most of them overflow)
-  if (uint64_t(slotWords) * 4u * uint64_t(nSub) * 10u < uint64_t(nInterior) * 11u) return 2;
+  // not worth it unless slot + spill hold the average sub-sequence with room to spare (else most of them decode twice)
+  if (uint64_t(slotWords + uint32_t(kSpillWords)) * 4u * uint64_t(nSub) * 3u < uint64_t(nInterior) * 4u) return 2;
   uint32_t* const image32 = reinterpret_cast<uint32_t*>(sink.tile);
   if (tid == 0) S.firstEot = nSub;
   // pass 0: only the END of every sub-sequence matters here, so start kFastLookback bits before the limit and rely on
@@ -522,7 +527,7 @@ __device__ int lsop_text_decode(CanonFastShared& S, uint32_t nBits, const uint32
     uint32_t limit = T0 + uint32_t(i + 1) * B;
     if (limit > nBits) limit = nBits;
     uint32_t from = T0 + uint32_t(i) * B;
-    if (limit - from > kFastLookback) from = limit - kFastLookback;
+    if (limit - from > lookback) from = limit - lookback;
     uint32_t e, c;
     int f;
     canon_fast_count(S, nBits, from, limit, &e, &c, &f);
@@ -543,7 +548,7 @@ __device__ int lsop_text_decode(CanonFastShared& S, uint32_t nBits, const uint32
         if (limit > nBits) limit = nBits;
         uint32_t e, c;
         int f;
-        text_stage_sub(S, nBits, ns, limit, image32 + size_t(i) * slotWords, slotWords, &e, &c, &f);
+        text_stage_sub(S, nBits, ns, limit, image32 + size_t(i) * slotWords, slotWords, spillArea + size_t(i) * kSpillWords, &e, &c, &f);
         vend[i] = e;
         S.cnt[i] = uint16_t(c);
         S.eot[i] = uint8_t(f);
@@ -616,9 +621,16 @@ __device__ int lsop_text_decode(CanonFastShared& S, uint32_t nBits, const uint32
 #pragma unroll
       for (int j = 0; j < kStageWordsPerThread; j++) {
         const uint32_t at = (uint32_t(j) - s * perSub) * 4u;  // byte position of word j inside this sub-sequence's slot
-        if (uint32_t(j) >= s * perSub && at < n) {
+        if (uint32_t(j) >= s * perSub && uint32_t(j) < s * perSub + slotWords && at < n) {
           const uint32_t m = n - at;
           sink.push(m >= 4u ? r[j] : (r[j] & ((1u << (8 * m)) - 1u)), m >= 4u ? 4 : int(m));
+        }
+      }
+      if (n > slotWords * 4u) {  // the tail this thread spilled in the staging pass
+        const uint32_t* sp = spillArea + size_t(i) * kSpillWords;
+        for (uint32_t at = slotWords * 4u; at < n; at += 4u) {
+          const uint32_t wv = *sp++, m = n - at;
+          sink.push(m >= 4u ? wv : (wv & ((1u << (8 * m)) - 1u)), m >= 4u ? 4 : int(m));
         }
       }
       sink.end();
@@ -684,7 +696,9 @@ __global__ void __launch_bounds__(kTextThreads, 2) lsop2_text_kernel(LsopFastArg
       const uint32_t nInterior = uint32_t(A.g.R - 2) * uint32_t(A.g.C - 4);
       ByteTileSink sink;
       sink.init(tileImg, A.exc + size_t(tIdx) * kExcWords, A.g);
-      if (kTextStaged) rc = lsop_text_decode(F, span * 8u, T0 + 8u * delta, nInterior, uint32_t(A.g.tileBytes), sink);
+      if (kTextStaged)
+        rc = lsop_text_decode(F, span * 8u, T0 + 8u * delta, nInterior, uint32_t(A.g.tileBytes), sink,
+                              reinterpret_cast<uint32_t*>(A.textStage) + size_t(blockIdx.x) * (kFastMaxSub * kSpillWords), A.textLookback);
       else rc = 2;
       if (rc == 2) {  // (uniform) the two-pass form
         uint32_t endBit = 0, nv = 0;
@@ -713,6 +727,9 @@ __global__ void __launch_bounds__(kTextThreads, 2) lsop2_text_kernel(LsopFastArg
 }
 
 // ---- kernel W -----------------------------------------------------------------------------------------------------
+#ifndef G4_WAVE_CTAS
+#define G4_WAVE_CTAS 2
+#endif
 constexpr int kWaveStageBytes = 2048;  // one TMA box: 32 lanes x 64 bytes = sixteen iterations
 
 // The value of an exceptional cell (byte 0 in the scratch): its list entry, or -128 when the byte was genuine.
@@ -723,7 +740,7 @@ __device__ __noinline__ int32_t wave_exception(const uint32_t* exc, int n, int k
 }
 
 template <bool WIDE>
-__global__ void __launch_bounds__(kThreads, 2)
+__global__ void __launch_bounds__(kThreads, G4_WAVE_CTAS)
     lsop2_wave_kernel(const __grid_constant__ CUtensorMap tmap, LsopFastArgs A, int listBegin, int listEnd) {
   extern __shared__ __align__(1024) unsigned char waveSmem[];
   const DecodeArgs& a = A.a;
@@ -800,7 +817,7 @@ __global__ void __launch_bounds__(kThreads, 2)
   int4 sqPrev = make_int4(0, 0, 0, 0);
   int32_t w0 = 0, w1 = 0, w2 = 0, w3 = 0;      // wrap-block values (set in the wrap block, read only there)
   float g0 = 0.f, g1 = 0.f, g2 = 0.f, g3 = 0.f;
-  const uint32_t wrapB16 = uint32_t(nB - 1) * 16u, preB16 = wrapB16 - 16u;
+  const uint32_t wrapB16 = uint32_t(nB - 1) * 16u;
   uint32_t b16 = lane < nLanes ? uint32_t(nB - 1 - lane) * 16u : 0u;  // 16 x block inside the row; every lane starts towards its virtual wrap block
   int row = lane - rpg;                       // row of the current stream position (virtual row before the first)
   uint32_t validM = 0u;                       // 0xFF800000 while `row` is a tile row this lane computes
@@ -817,13 +834,13 @@ __global__ void __launch_bounds__(kThreads, 2)
 
   // one iteration: the block of four cells at 16-byte block offset b16 of the lane's current row
   auto step = [&](const uint32_t rw) {
-    // ---- the rare blocks of a row, one branch: the block after the wrap (next row), the block before it (side record
-    // of the next row, one block early), the wrap block itself (the row's last two columns -- Triangle predictor folded
+    // ---- the rare blocks of a row, one branch: the block after the wrap (next row; also fetches the side record of the
+    // row after it), the wrap block itself (the row's last two columns -- Triangle predictor folded
     // into D2/D1 by kernel H -- and columns 0,1 of the lane's next row; feeders take theirs from the stream except
     // before their first row)
     bool fix = false;
     uint32_t badM = validM;
-    if (b16 >= preB16) {
+    if (b16 >= wrapB16) {
       if (b16 > wrapB16) {
         b16 = 0;
         row += rpg;
@@ -833,11 +850,9 @@ __global__ void __launch_bounds__(kThreads, 2)
         validM = (computing && row < R) ? 0xFF800000u : 0u;
         badM = validM;
         started = 1u;
-      } else if (b16 == preB16) {
-        if (started) {
-          const int nr = row + rpg;
-          sideNext = (computing && nr < R) ? side[nr] : make_int4(0, 0, 0, 0);
-        }
+        // the side record of the row after this one: needed in this row's wrap block, a whole row of iterations from now
+        const int nr = row + rpg;
+        sideNext = (computing && nr < R) ? side[nr] : make_int4(0, 0, 0, 0);
       } else {
         badM = 0u;  // the stencil results of the wrap block are discarded
         if (!feeder || !started) {
@@ -1012,7 +1027,7 @@ bool lsop_fast_geometry(const g4_band_desc& band, const void* grid, LsopFastGeom
 }
 size_t lsop_fast_side_bytes(const LsopFastGeom& g, int nTiles) { return size_t(nTiles) * size_t(g.R) * sizeof(int4); }
 size_t lsop_fast_exc_bytes(int nTiles) { return size_t(nTiles) * kExcWords * sizeof(uint32_t); }
-size_t lsop_fast_stage_bytes(int) { return 0; }
+size_t lsop_fast_stage_bytes(int smCount) { return size_t(smCount) * 2 * kFastMaxSub * kSpillWords * sizeof(uint32_t); }  // text kernel: <= 2 CTAs per SM
 size_t lsop_fast_resid_bytes(const LsopFastGeom& g, int nTiles) { return size_t(kResidGuard) + size_t(nTiles) * size_t(g.tilePitch) + size_t(g.tileBytes) + 4096; }
 
 // Kernels H, T and W over the list positions [0, nTilesUpper).  Tiles the fast path cannot take are appended to
