@@ -169,14 +169,15 @@ cudaError_t launch_lsop08_decode(const DecodeArgs& a, float* coef, int nCtas, in
 // LSOP12 decode, fast path (g4_lsop_fast.cu): byte hand-over between the text kernel and a TMA-fed wavefront kernel.
 struct LsopFastGeom {
   int R, C;
-  int nB;         // 4-column blocks per row (C / 4)
-  int nLanes;     // lanes of a wavefront warp in use: min(32, nB); lanes 0,1 carry the two finished rows above a group
-  int rpg;        // rows per group = nLanes - 2
-  int nGroups;
-  int laneBytes;  // one lane's residual stream in the scratch image, == 4 (mod 16)
-  int tileBytes;  // 32 * laneBytes: the image one tile writes
-  int tilePitch;  // bytes between the images of consecutive tiles: a multiple of laneBytes - 4 (tensor map stride rule)
-  int nIter;      // wavefront iterations, a multiple of 16
+  int W;          // strip width in columns: 4, 8 or 16 (C is a multiple of W)
+  int logW;
+  int nStrips;    // lanes of a wavefront warp in use: strip k = columns 2 + k W .. 2 + k W + W - 1; ceil((C - 2) / W) <= 32
+  int P;          // bytes per row of the residual image = nStrips * W
+  int nSteps;     // wavefront steps = R - 2 + nStrips - 1 (lane k works on row s - k + 2 at step s)
+  int chunkRows;  // image rows per bulk copy of the wavefront kernel = 128 / W (chunk = chunkRows * P <= 4096 bytes)
+  int nChunks;
+  int tileBytes;  // nChunks * chunkRows * P: the image one tile writes
+  int tilePitch;  // bytes between the images of consecutive tiles (a multiple of 128)
   int wide;       // 256-bit raster stores
 };
 struct LsopFastArgs {

@@ -15,12 +15,16 @@
 //      leave as ONE BYTE each (symbol = residual + 128) into a shared-memory image of the tile's residual scratch,
 //      which goes to HBM with one bulk-async store.  Residuals that do not fit a byte (escapes, nulls) are written as
 //      byte 0 plus an entry in a small per-tile exception list.
-//   W  lsop2_wave_kernel   one warp per tile.  The causal 12-tap float32 stencil as a wavefront (lane = row, one
-//      4-column block behind the lane above).  The residual scratch is laid out per LANE (all rows a lane will ever
-//      own, back to back) with a lane pitch L = 4 (mod 16): a tensor map whose row stride is L - 4 then hands the
-//      warp a 32 x 64-byte box in which every lane finds ITS next sixteen blocks at the same offset -- the 4-byte
-//      skew between lanes is absorbed by the descriptor.  One TMA box load per sixteen iterations, double buffered,
-//      completion by mbarrier; values leave as whole 32-byte sectors (256-bit stores).
+//   W  lsop3_wave_kernel   one warp per tile.  The causal 12-tap float32 stencil as a wavefront over COLUMN STRIPS:
+//      lane k owns the W columns 2 + k W .. (W = 4, 8 or 16), walks down the rows and is one ROW behind lane k - 1
+//      (row r of strip k needs row r of strip k - 1 and rows r - 1, r - 2 of strip k + 1).  Every lane is at the same
+//      cell of its strip at the same time, so the control flow is uniform: no per-lane row ends, no wrap blocks; the
+//      first two columns enter lane 0 as its "left neighbour", the Triangle-predicted last two columns are two cells of
+//      the last lane.  Per row a lane receives its two left values by shuffle-up, two right values of the row above
+//      by shuffle-down, reads its W residual bytes with one shared-memory load and writes one aligned 4 W-byte
+//      piece of the raster row {left2, left1, cells 0 .. W-3}.  The residual image is laid out by the text kernel
+//      in STEP order (image row s = strip k of tile row s - k, for all k): a wavefront step reads nStrips * W
+//      contiguous bytes, fetched 128 / W steps at a time by cp.async.bulk + mbarrier into a two-stage ring.
 //
 // Arithmetic of one cell (bit-identical to the reference for |p| < 2^21, checked per cell):
 //   p   = u1*z1 + ... + u12*z12          strictly left to right, float32, no FMA (-fmad=false)
@@ -76,14 +80,12 @@ __device__ __forceinline__ void mbar_wait(uint32_t bar, uint32_t parity) {
                  : "memory");
 }
 
-// stream geometry shared by the three kernels (LsopFastGeom in g4_kernels.h):
-//   lane l in [2, nLanes) owns rows l, l + rpg, l + 2 rpg, ...  (group g = row / rpg ... row = g * rpg + l)
-//   word q of a lane's stream: q = 0 is a virtual block (columns 0,1 of the lane's first row); q = 1 + g * nB + b holds
-//   the four residual bytes of columns 4b+2 .. 4b+5 of row g * rpg + l (b < nB - 1; block nB - 1 is the wrap block: the
-//   row's last two columns and the next row's first two, no residual bytes)
-__device__ __forceinline__ uint32_t lane_row_offset(const LsopFastGeom& g, int row) {
-  const int gi = (row - 2) / g.rpg, l = 2 + (row - 2) - gi * g.rpg;
-  return uint32_t(l) * uint32_t(g.laneBytes) + 4u * uint32_t(1 + gi * g.nB);
+// residual image shared by kernels T and W (LsopFastGeom in g4_kernels.h): interior cell (row r, column c), r >= 2,
+// 2 <= c < C - 2, has data column p = c - 2 and lies in strip p / W; wavefront step s = (r - 2) + p / W reads it, so its
+// byte sits at image row s, byte p.  Data words (4 bytes, p a multiple of 4) never straddle a strip.
+__device__ __forceinline__ uint32_t image_offset(uint32_t w, int logW, uint32_t P, uint32_t k) {  // w = C - 4
+  const uint32_t rr = k / w, pp = k - rr * w;
+  return (rr + (pp >> logW)) * P + pp;
 }
 
 // ---- kernel H -----------------------------------------------------------------------------------------------------
@@ -202,56 +204,42 @@ struct ByteTileSink {
   static constexpr bool kPacked = true;
   uint8_t* tile;       // shared memory, tileBytes
   uint32_t* exc;       // this tile's exception list (global)
-  int w;               // C - 4, bytes per row
-  int L, nB4, nLanes, rpg;  // lane pitch, 4 * nB, lanes in use, rows per group (LsopFastGeom)
+  int w;               // C - 4, data bytes per row
+  int logW;
+  uint32_t P, Wm1;     // image row pitch, W - 1
   uint32_t addr;       // word-aligned image offset of queue byte 0
-  int left;            // bytes from addr to the end of the row
-  uint32_t rowOff;     // image offset of the current row
-  int lane, rowBase;   // the current row = rowBase + lane, lane in [2, nLanes)
+  uint32_t rowBase;    // image offset of data column 0 of the current row
+  int left;            // data bytes from addr to the end of the row (a multiple of 4)
+  int kAddr;           // interior index of the byte at addr
   int head;            // dummy bytes at the front of the queue (run head inside a word), 0 after the first store
   int cnt;             // queued bytes, dummies included; < 4 between calls
   uint64_t q;
   int excK, excSlot;   // the last exception this thread recorded
   int32_t excV;
 
-  __device__ __forceinline__ void init(uint8_t* img, uint32_t* e, const LsopFastGeom& g) {
+  __device__ __forceinline__ void init(uint8_t* img, uint32_t* e, const LsopFastGeom& geom) {
     tile = img;
     exc = e;
-    w = g.C - 4;
-    L = g.laneBytes;
-    nB4 = 4 * g.nB;
-    nLanes = g.nLanes;
-    rpg = g.rpg;
+    logW = geom.logW;
+    w = geom.C - 4;
+    P = uint32_t(geom.P);
+    Wm1 = uint32_t(geom.W - 1);
   }
   __device__ __forceinline__ void begin(uint32_t k0) {
-    const int rr = int(k0) / w, cc = int(k0) - rr * w;
-    const int gi = rr / rpg;
-    lane = 2 + rr - gi * rpg;
-    rowBase = gi * rpg;
-    rowOff = uint32_t(lane) * uint32_t(L) + 4u + uint32_t(gi) * uint32_t(nB4);
-    const uint32_t a0 = rowOff + uint32_t(cc);
-    head = int(a0 & 3u);
+    const int rr = int(k0) / w, pp = int(k0) - rr * w;
+    rowBase = uint32_t(rr) * P;
+    const uint32_t a0 = rowBase + (uint32_t(pp) >> logW) * P + uint32_t(pp);
+    head = pp & 3;
     addr = a0 & ~3u;
-    left = w - (cc & ~3);
+    left = w - (pp & ~3);
+    kAddr = int(k0) - head;
     cnt = head;
     q = 0;
     excK = -1;
     excSlot = 0;
     excV = 0;
   }
-  __device__ __forceinline__ int cur_k() const {  // interior index of the value that will be queued next
-    return (rowBase + lane - 2) * w + int(addr - rowOff) + cnt;
-  }
-  __device__ __forceinline__ void next_row() {
-    rowOff += uint32_t(L);
-    if (++lane == nLanes) {  // the next group's first row: back to lane 2, one row period further
-      lane = 2;
-      rowBase += rpg;
-      rowOff += uint32_t(nB4) - uint32_t(rpg) * uint32_t(L);
-    }
-    addr = rowOff;
-    left = w;
-  }
+  __device__ __forceinline__ int cur_k() const { return kAddr + cnt; }  // interior index of the value that will be queued next
   __device__ __forceinline__ void store_word() {  // cnt >= 4
     if (head) {
       for (int i = head; i < 4; i++) tile[addr + i] = uint8_t(q >> (8 * i));
@@ -260,10 +248,22 @@ struct ByteTileSink {
     q >>= 32;
     cnt -= 4;
     addr += 4;
+    kAddr += 4;
     left -= 4;
-    if (__builtin_expect(left == 0, 0)) next_row();
+    if ((addr & Wm1) == 0u) {  // next strip: one image row further down; at the end of the row back to strip 0 of the next row
+      addr += P;
+      if (left == 0) {
+        rowBase += P;
+        addr = rowBase;
+        left = w;
+      }
+    } else if (__builtin_expect(left == 0, 0)) {  // (a row that ends inside a strip)
+      rowBase += P;
+      addr = rowBase;
+      left = w;
+    }
   }
-  __device__ __forceinline__ void push(uint32_t bytes, int n) {  // n = 1..3 symbol bytes, first value in the low byte
+  __device__ __forceinline__ void push(uint32_t bytes, int n) {  // n = 1..4 symbol bytes, first value in the low byte
     q |= uint64_t(bytes) << (8 * cnt);
     cnt += n;
     if (cnt >= 4) store_word();
@@ -296,17 +296,11 @@ struct ByteTileSink {
       const int sh = 8 * (cnt - 1);
       b = uint32_t(q >> sh) & 0xffu;
       q &= ~(0xffull << sh);
-    } else {  // already in the image: the byte in front of addr + cnt, or the last byte of the previous row
+    } else {  // already in the image
       // (cnt == head: with head != 0 nothing of this run was stored yet, which `have` in the caller excludes)
-      uint32_t p = addr + uint32_t(cnt);
-      if (p > rowOff) p -= 1;
-      else {
-        uint32_t prevOff = rowOff - uint32_t(L);
-        if (lane == 2) prevOff = rowOff - uint32_t(nB4) + uint32_t(rpg - 1) * uint32_t(L);
-        p = prevOff + uint32_t(w) - 1;
-      }
-      b = tile[p];
-      tile[p] = 0;
+      const uint32_t o = image_offset(uint32_t(w), logW, P, uint32_t(kp));
+      b = tile[o];
+      tile[o] = 0;
     }
     add_exception(kp, int32_t(((b - 128u) << nb) | bits));
   }
@@ -451,11 +445,8 @@ __device__ __forceinline__ bool text_write_sub(const CanonFastShared& S, uint32_
 
 // Exception-list entries of one sub-sequence whose values start at interior index k0 (the bytes are in the image).
 __device__ __noinline__ void text_exceptions_sub(const CanonFastShared& S, uint32_t nBits, uint32_t start, uint32_t limit, uint32_t k0,
-                                                 uint8_t* tile, uint32_t* exc, int w, int L, int nB4, int rpg) {
-  auto image_offset = [&](uint32_t k) {
-    const int rr = int(k) / w, cc = int(k) - rr * w, gi = rr / rpg, l = 2 + rr - gi * rpg;
-    return uint32_t(l) * uint32_t(L) + 4u + uint32_t(gi) * uint32_t(nB4) + uint32_t(cc);
-  };
+                                                 uint8_t* tile, uint32_t* exc, int w, int logW, uint32_t P) {
+  auto image_off = [&](uint32_t k) { return image_offset(uint32_t(w), logW, P, k); };
   auto add = [&](uint32_t k, int32_t v) {
     const uint32_t slot = atomicAdd(exc, 1u);
     if (slot < uint32_t(kExcCap)) {
@@ -481,7 +472,7 @@ __device__ __noinline__ void text_exceptions_sub(const CanonFastShared& S, uint3
       if (after + nb > nBits || k == k0) break;
       if (!pending) {
         pk = k - 1;
-        const uint32_t o = image_offset(pk);
+        const uint32_t o = image_off(pk);
         pv = int32_t(tile[o]) - 128;
         tile[o] = 0;
         pending = true;
@@ -634,7 +625,7 @@ __device__ int lsop_text_decode(CanonFastShared& S, uint32_t nBits, const uint32
         }
       }
       sink.end();
-      if (flags & kSubRare) text_exceptions_sub(S, nBits, S.startv[i], limit, offv[i], sink.tile, sink.exc, sink.w, sink.L, sink.nB4, sink.rpg);
+      if (flags & kSubRare) text_exceptions_sub(S, nBits, S.startv[i], limit, offv[i], sink.tile, sink.exc, sink.w, sink.logW, sink.P);
     }
   }
   return __syncthreads_or(bad ? 1 : 0) ? 1 : 0;
@@ -730,7 +721,7 @@ __global__ void __launch_bounds__(kTextThreads, 2) lsop2_text_kernel(LsopFastArg
 #ifndef G4_WAVE_CTAS
 #define G4_WAVE_CTAS 2
 #endif
-constexpr int kWaveStageBytes = 2048;  // one TMA box: 32 lanes x 64 bytes = sixteen iterations
+constexpr int kWaveChunkBytes = 4096;  // ring stage: one bulk copy of 128 / W image rows (<= 32 strips x W bytes each)
 
 // The value of an exceptional cell (byte 0 in the scratch): its list entry, or -128 when the byte was genuine.
 __device__ __noinline__ int32_t wave_exception(const uint32_t* exc, int n, int k) {
@@ -739,10 +730,15 @@ __device__ __noinline__ int32_t wave_exception(const uint32_t* exc, int n, int k
   return -128;
 }
 
-template <bool WIDE>
-__global__ void __launch_bounds__(kThreads, G4_WAVE_CTAS)
-    lsop2_wave_kernel(const __grid_constant__ CUtensorMap tmap, LsopFastArgs A, int listBegin, int listEnd) {
-  extern __shared__ __align__(1024) unsigned char waveSmem[];
+// floats of rows 0 and 1 of the tile (written by kernel H), columns 0 .. C + 3 (zeros past C - 1), per warp
+__device__ __forceinline__ int wave_rowbuf_floats(int C) { return (C + 4 + 3) & ~3; }
+
+template <int W, bool WIDE>
+__global__ void __launch_bounds__(kThreads, G4_WAVE_CTAS) lsop3_wave_kernel(LsopFastArgs A, int listBegin, int listEnd) {
+  extern __shared__ __align__(128) unsigned char waveSmem[];
+  constexpr int CR = 128 / W;   // image rows per chunk
+  constexpr int NW = W / 4;     // residual words per lane and step
+  constexpr int E = W - 4;      // the last strip: cells E, E + 1 are the row's last two columns (C a multiple of W)
   const DecodeArgs& a = A.a;
   const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
   const int li = listBegin + blockIdx.x * kWarps + warp;
@@ -754,236 +750,199 @@ __global__ void __launch_bounds__(kThreads, G4_WAVE_CTAS)
   const int nExc = int(exc[0]);
   if (nExc > kExcCap) return;  // deferred by kernel T
   const LsopFastGeom& G = A.g;
-  const int R = G.R, C = G.C, nB = G.nB, nLanes = G.nLanes, rpg = G.rpg;
+  const int R = G.R, C = G.C, nS = G.nStrips, P = G.P;
   const TileView t = tile_view(a.band, a.grid, tIdx);
-  unsigned char* ring = waveSmem + size_t(warp) * (2 * kWaveStageBytes);
-  float4* rowbuf = reinterpret_cast<float4*>(waveSmem + size_t(kWarps) * (2 * kWaveStageBytes)) + size_t(warp) * (2 * nB);
-  uint64_t* bars = reinterpret_cast<uint64_t*>(waveSmem + size_t(kWarps) * (2 * kWaveStageBytes) + size_t(kWarps) * (2 * nB) * sizeof(float4)) + 2 * warp;
+  const int rbFloats = wave_rowbuf_floats(C);
+  unsigned char* ring = waveSmem + size_t(warp) * (2 * kWaveChunkBytes);
+  float* rowbuf = reinterpret_cast<float*>(waveSmem + size_t(kWarps) * (2 * kWaveChunkBytes)) + size_t(warp) * (2 * rbFloats);
+  uint64_t* bars = reinterpret_cast<uint64_t*>(waveSmem + size_t(kWarps) * (2 * kWaveChunkBytes) + size_t(kWarps) * (2 * rbFloats) * sizeof(float)) + 2 * warp;
   const uint32_t bar0 = smem_u32(bars), ring0 = smem_u32(ring);
-  const bool feeder = lane < 2;
-  const bool computing = lane >= 2 && lane < nLanes;
-  const bool writer = lane >= nLanes - 2 && lane < nLanes;  // its rows become the next group's feeder rows
+  const bool active = lane < nS, isFirst = lane == 0, isLast = lane == nS - 1;
   if (lane == 0) {
     mbar_init(bar0, 1);
     mbar_init(bar0 + 8, 1);
     asm volatile("fence.mbarrier_init.release.cluster;");
   }
   __syncwarp();
-  auto issue = [&](int chunk) {  // lane 0: box of iterations 16 chunk .. 16 chunk + 15 into stage chunk & 1
-    const uint32_t bar = bar0 + 8u * (chunk & 1), dst = ring0 + uint32_t(kWaveStageBytes) * (chunk & 1);
-    mbar_expect_tx(bar, kWaveStageBytes);
-    asm volatile("cp.async.bulk.tensor.3d.shared::cluster.global.tile.mbarrier::complete_tx::bytes [%0], [%1, {%2, %3, %4}], [%5];" ::"r"(dst),
-                 "l"(reinterpret_cast<uint64_t>(&tmap)), "r"(64 * chunk), "r"(0), "r"(tIdx), "r"(bar)
+  const uint8_t* img = A.resid + kResidGuard + size_t(tIdx) * size_t(G.tilePitch);
+  const uint32_t chunkBytes = uint32_t(CR * P);
+  const int nChunks = G.nChunks;
+  auto issue = [&](int chunk) {  // lane 0: image rows CR chunk .. CR chunk + CR - 1 into stage chunk & 1
+    const uint32_t bar = bar0 + 8u * (chunk & 1), dst = ring0 + uint32_t(kWaveChunkBytes) * (chunk & 1);
+    mbar_expect_tx(bar, chunkBytes);
+    asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(dst),
+                 "l"(img + size_t(chunk) * chunkBytes), "r"(chunkBytes), "r"(bar)
                  : "memory");
   };
   if (lane == 0) issue(0);
 
   float u[12];
 #pragma unroll
-  for (int i = 0; i < 12; i++) u[i] = computing ? A.coef[size_t(tIdx) * 12 + i] : 0.f;
-  const float bias = feeder ? kMagicInt : 2.f * kMagicInt + 128.f;  // x - bias == float(residual) - 1.5*2^23 (feeder: value - 1.5*2^23)
-  const int4* side = A.side + size_t(tIdx) * R;
-  uint32_t badBits = 0;  // nonzero: some cell left the range of the fast arithmetic
-  const int32_t lim = int32_t(kRange);
-  // feeder stream of group 0: rows 0 and 1 (written by kernel H), block b = columns 4b+2 .. 4b+5; the wrap block holds
-  // the rows' last two columns and columns 0,1 of the feeder's next row (rows rpg, rpg+1)
-  for (int idx = lane; idx < 2 * nB; idx += 32) {
-    const int f = idx >= nB ? 1 : 0, b = idx - f * nB;
-    const int32_t* rowf = t.row(f);
-    int32_t v0, v1, v2, v3;
-    if (b < nB - 1) {
-      const int2 lo = *reinterpret_cast<const int2*>(rowf + 4 * b + 2), hi = *reinterpret_cast<const int2*>(rowf + 4 * b + 4);
-      v0 = lo.x; v1 = lo.y; v2 = hi.x; v3 = hi.y;
-    } else {
-      const int2 lo = *reinterpret_cast<const int2*>(rowf + C - 2);
-      v0 = lo.x; v1 = lo.y;
-      const int4 s = rpg + f < R ? side[rpg + f] : make_int4(0, 0, 0, 0);
-      v2 = s.x; v3 = s.y;
-    }
-    if (v0 <= -lim || v0 >= lim || v1 <= -lim || v1 >= lim || v2 <= -lim || v2 >= lim || v3 <= -lim || v3 >= lim) badBits = 1u;
-    rowbuf[idx] = make_float4(float(v0), float(v1), float(v2), float(v3));
+  for (int i = 0; i < 12; i++) u[i] = active ? A.coef[size_t(tIdx) * 12 + i] : 0.f;
+  // rows 0 and 1 as floats (int -> float exactly as the reference converts them)
+  for (int c = lane; c < rbFloats; c += 32) {
+    rowbuf[c] = c < C ? float(t.row(0)[c]) : 0.f;
+    rowbuf[rbFloats + c] = c < C ? float(t.row(1)[c]) : 0.f;
   }
-  // columns 0,1 of every lane's first row (the virtual block at stream word 0)
-  int32_t curD2 = 0, curD1 = 0;
-  int4 sideNext = make_int4(0, 0, 0, 0);
-  if (lane < nLanes && lane < R) sideNext = side[lane];
+  const int4* side = A.side + size_t(tIdx) * R;
+  const bool needSide = active && (isFirst || isLast);
+  int r = 2 - lane;                                  // the row this lane works on in the coming step
+  int4 sideCur = make_int4(0, 0, 0, 0), sideNext = make_int4(0, 0, 0, 0);
+  if (needSide && r + 0 >= 2 && r < R) sideNext = side[r];   // (lane 0; the last lane fetches when its rows begin)
+  char* rowp = reinterpret_cast<char*>(t.base + int64_t(r) * t.pitch + lane * W);  // dereferenced only for valid rows
+  const int64_t rowStep = int64_t(t.pitch) * 4;
+  const uint32_t ringLane = ring0 + uint32_t(lane * W);
+  const uint32_t rb0 = smem_u32(rowbuf) + uint32_t(lane * W) * 4u, rb1 = rb0 + uint32_t(rbFloats) * 4u;
+  const int wInterior = C - 4;
+  uint32_t badBits = 0;  // nonzero: some cell left the range of the fast arithmetic
+  float a0[W + 4], a1[W + 4], a2[W + 4];  // three rows of the strip, columns 2 + kW - 2 .. 2 + kW + W + 1, rotating roles
+#pragma unroll
+  for (int i = 0; i < W + 4; i++) { a0[i] = 0.f; a1[i] = 0.f; a2[i] = 0.f; }
+  int32_t pa = 0, pb = 0;        // own outputs of cells W - 2, W - 1 of the previous step (the right neighbour's left values)
+  float h0 = 0.f, h1 = 0.f;      // row 1 right of the strip, used in the lane's first step instead of the shuffle
   __syncwarp();
 
-  float av[8], bv[8];  // rows r-1 / r-2, columns c-2 .. c+5 relative to the block's first column
-#pragma unroll
-  for (int i = 0; i < 8; i++) { av[i] = 0.f; bv[i] = 0.f; }
-  float f1 = 0.f, f2 = 0.f;        // own row, columns c-1 and c-2
-  int32_t pi2 = 0, pi3 = 0;        // own outputs 2,3 of the previous block
-  int4 sqPrev = make_int4(0, 0, 0, 0);
-  int32_t w0 = 0, w1 = 0, w2 = 0, w3 = 0;      // wrap-block values (set in the wrap block, read only there)
-  float g0 = 0.f, g1 = 0.f, g2 = 0.f, g3 = 0.f;
-  const uint32_t wrapB16 = uint32_t(nB - 1) * 16u;
-  uint32_t b16 = lane < nLanes ? uint32_t(nB - 1 - lane) * 16u : 0u;  // 16 x block inside the row; every lane starts towards its virtual wrap block
-  int row = lane - rpg;                       // row of the current stream position (virtual row before the first)
-  uint32_t validM = 0u;                       // 0xFF800000 while `row` is a tile row this lane computes
-  uint32_t started = 0u;                      // past the virtual block in front of the lane's first row
-  char* rowp = reinterpret_cast<char*>(t.base + int64_t(row) * t.pitch);  // dereferenced only while valid
-  const int64_t groupStep = int64_t(rpg) * t.pitch * 4;
-  const int wInterior = C - 4;
-  const uint32_t ringLane = ring0 + 64u * uint32_t(lane);
-  const uint32_t swz16 = uint32_t((lane >> 1) & 3) * 16u;
-  const uint32_t rbRead = smem_u32(rowbuf) + uint32_t(lane & 1) * uint32_t(nB) * 16u;
-  const uint32_t rbWrite = smem_u32(rowbuf) + uint32_t(lane == nLanes - 1 ? nB : 0) * 16u;
-  const uint32_t feederM = feeder ? 1u : 0u, writerM = writer ? 1u : 0u;
-  const int nChunks = G.nIter >> 4;
-
-  // one iteration: the block of four cells at 16-byte block offset b16 of the lane's current row
-  auto step = [&](const uint32_t rw) {
-    // ---- the rare blocks of a row, one branch: the block after the wrap (next row; also fetches the side record of the
-    // row after it), the wrap block itself (the row's last two columns -- Triangle predictor folded
-    // into D2/D1 by kernel H -- and columns 0,1 of the lane's next row; feeders take theirs from the stream except
-    // before their first row)
-    bool fix = false;
-    uint32_t badM = validM;
-    if (b16 >= wrapB16) {
-      if (b16 > wrapB16) {
-        b16 = 0;
-        row += rpg;
-        rowp += groupStep;
-        curD2 = sideNext.z;
-        curD1 = sideNext.w;
-        validM = (computing && row < R) ? 0xFF800000u : 0u;
-        badM = validM;
-        started = 1u;
-        // the side record of the row after this one: needed in this row's wrap block, a whole row of iterations from now
-        const int nr = row + rpg;
-        sideNext = (computing && nr < R) ? side[nr] : make_int4(0, 0, 0, 0);
-      } else {
-        badM = 0u;  // the stencil results of the wrap block are discarded
-        if (!feeder || !started) {
-          fix = true;
-          w0 = int32_t(uint32_t(pi3) + uint32_t(curD2));
-          w1 = int32_t(uint32_t(w0) + uint32_t(curD1));
-          w2 = sideNext.x;
-          w3 = sideNext.y;
-          g0 = float(w0); g1 = float(w1); g2 = float(w2); g3 = float(w3);
-          const bool cur = validM != 0u && (w0 <= -lim || w0 >= lim || w1 <= -lim || w1 >= lim);
-          const bool nxt = computing && row + rpg < R && (w2 <= -lim || w2 >= lim || w3 <= -lim || w3 >= lim);
-          if (cur || nxt) badBits = 1u;
-        }
+  // one step: row r of the strip into cur[]; am1 / am2 hold rows r - 1 / r - 2
+  auto step = [&](float (&am2)[W + 4], float (&am1)[W + 4], float (&cur)[W + 4], const int s) {
+    if ((s & (CR - 1)) == 0) {  // (uniform) next chunk of the residual image
+      const int chunk = s / CR;
+      if (chunk < nChunks) {
+        if (lane == 0 && chunk + 1 < nChunks) issue(chunk + 1);
+        mbar_wait(bar0 + 8u * (chunk & 1), uint32_t(chunk >> 1) & 1u);
       }
     }
-    // ---- inputs of the four positions: residual bytes (biased floats) or the feeder's finished values
-    float x0 = __uint_as_float(__byte_perm(rw, 0x4B400000u, 0x7640));
-    float x1 = __uint_as_float(__byte_perm(rw, 0x4B400000u, 0x7641));
-    float x2 = __uint_as_float(__byte_perm(rw, 0x4B400000u, 0x7642));
-    float x3 = __uint_as_float(__byte_perm(rw, 0x4B400000u, 0x7643));
-    asm volatile("{ .reg .pred p; setp.ne.b32 p, %4, 0; @p ld.shared.v4.f32 {%0, %1, %2, %3}, [%5]; }"
-                 : "+f"(x0), "+f"(x1), "+f"(x2), "+f"(x3)
-                 : "r"(feederM), "r"(rbRead + b16));
+    const bool valid = active && r >= 2 && r < R;
+    const bool first = r == 2;
+    if (first && active) {  // (one lane per step, the first nStrips steps) rows 0 and 1 from the row buffer
 #pragma unroll
-    for (int i = 0; i < 4; i++) { av[i] = av[i + 4]; bv[i] = bv[i + 4]; }
-    int32_t out[4];
-    float fout[4];
-    uint32_t acc = 0;  // exponent bits of t1 that differ from those of [2^22, 2^23): nonzero <=> p outside [-2^21, 2^21) or NaN
-    auto cells = [&](auto genTag, const int32_t* ex) {
-      constexpr bool GEN = decltype(genTag)::value;
-#pragma unroll
-      for (int j = 0; j < 4; j++) {
-        av[4 + j] = __shfl_up_sync(0xffffffffu, f2, 1);
-        bv[4 + j] = __shfl_up_sync(0xffffffffu, av[j], 1);
-        // LsDecoder12.java:424-438 -- evaluated left to right in float32, no fused multiply-add
-        float p = u[0] * f1;
-        p = p + u[1] * av[j + 1];
-        p = p + u[2] * av[j + 2];
-        p = p + u[3] * av[j + 3];
-        p = p + u[4] * av[j + 4];
-        p = p + u[5] * f2;
-        p = p + u[6] * av[j];
-        p = p + u[7] * bv[j];
-        p = p + u[8] * bv[j + 1];
-        p = p + u[9] * bv[j + 2];
-        p = p + u[10] * bv[j + 3];
-        p = p + u[11] * bv[j + 4];
-        const float t1 = __fadd_rd(p, kMagicHalf);
-        acc |= __float_as_uint(t1) ^ 0x4A800000u;
-        const float t2 = __fadd_rd(t1, kMagicHalfUp);  // 1.5*2^23 + StrictMath.round(p)
-        const float xj = j == 0 ? x0 : j == 1 ? x1 : j == 2 ? x2 : x3;
-        float fv = t2 + (xj - bias);
-        int32_t iv;
-        if constexpr (GEN) {
-          iv = int32_t(uint32_t(__float_as_int(t2)) - 0x4B400000u + uint32_t(ex[j]));
-          if (!feeder) fv = float(iv);
-        } else iv = int32_t(uint32_t(__float_as_int(t2)) + __float_as_uint(xj) - 0x96800080u);  // round(p) + byte - 128
-        if (fix) {
-          fv = j == 0 ? g0 : j == 1 ? g1 : j == 2 ? g2 : g3;
-          iv = j == 0 ? w0 : j == 1 ? w1 : j == 2 ? w2 : w3;
-        }
-        out[j] = iv;
-        fout[j] = fv;
-        f2 = f1;
-        f1 = fv;
+      for (int i = 0; i < W + 4; i += 4) {
+        float4 x, y;
+        asm volatile("ld.shared.v4.f32 {%0, %1, %2, %3}, [%4];" : "=f"(x.x), "=f"(x.y), "=f"(x.z), "=f"(x.w) : "r"(rb0 + 4u * i));
+        asm volatile("ld.shared.v4.f32 {%0, %1, %2, %3}, [%4];" : "=f"(y.x), "=f"(y.y), "=f"(y.z), "=f"(y.w) : "r"(rb1 + 4u * i));
+        am2[i] = x.x; am2[i + 1] = x.y; am2[i + 2] = x.z; am2[i + 3] = x.w;
+        am1[i] = y.x; am1[i + 1] = y.y; am1[i + 2] = y.z; am1[i + 3] = y.w;
       }
-    };
-    // ---- exceptions: a zero byte in a tile that has an exception list -> the general form of the block
+      h0 = am1[W + 2];
+      h1 = am1[W + 3];
+    }
+    // side record of this row (lane 0: columns 0,1; last lane: D2, D1), the next row's fetched now
+    sideCur = sideNext;
+    if (needSide && r + 1 >= 2 && r + 1 < R) sideNext = side[r + 1];
+    // residual bytes of the strip
+    uint32_t rw[NW];
+    {
+      const uint32_t at = ringLane + uint32_t(kWaveChunkBytes) * ((s / CR) & 1) + uint32_t(s & (CR - 1)) * uint32_t(P);
+      if constexpr (NW == 1) asm volatile("ld.shared.b32 %0, [%1];" : "=r"(rw[0]) : "r"(at));
+      else if constexpr (NW == 2) asm volatile("ld.shared.v2.b32 {%0, %1}, [%2];" : "=r"(rw[0]), "=r"(rw[1]) : "r"(at));
+      else asm volatile("ld.shared.v4.b32 {%0, %1, %2, %3}, [%4];" : "=r"(rw[0]), "=r"(rw[1]), "=r"(rw[2]), "=r"(rw[3]) : "r"(at));
+    }
+    // left values: cells W-2, W-1 of row r in the strip to the left (finished one step ago: its am1), or columns 0,1
+    float l2 = __shfl_up_sync(0xffffffffu, am1[W], 1), l1 = __shfl_up_sync(0xffffffffu, am1[W + 1], 1);
+    int32_t li2 = __shfl_up_sync(0xffffffffu, pa, 1), li1 = __shfl_up_sync(0xffffffffu, pb, 1);
+    if (isFirst) { li2 = sideCur.x; li1 = sideCur.y; l2 = float(li2); l1 = float(li1); }
+    cur[0] = l2;
+    cur[1] = l1;
+    // exceptions: a zero byte in a tile that has an exception list -> the general form of the step
     bool general = false;
     if (nExc > 0) {
-      const bool z = ((rw - 0x01010101u) & ~rw & 0x80808080u) != 0u;
-      general = __any_sync(0xffffffffu, z && badM != 0u);
-    }
-    if (general) {
-      int32_t ex[4];
+      bool z = false;
 #pragma unroll
-      for (int j = 0; j < 4; j++) {
-        const uint32_t byte = (rw >> (8 * j)) & 0xffu;
-        ex[j] = int32_t(byte) - 128;
-        if (byte == 0u && badM != 0u) ex[j] = wave_exception(exc, nExc, (row - 2) * wInterior + int(b16 >> 2) + j);
+      for (int i = 0; i < NW; i++) z = z || ((rw[i] - 0x01010101u) & ~rw[i] & 0x80808080u) != 0u;
+      general = __any_sync(0xffffffffu, z && valid);
+    }
+    int32_t oi[W];
+    uint32_t accLo = 0, accHi = 0;  // exponent bits of t1 that differ from those of [2^22, 2^23): nonzero <=> p outside [-2^21, 2^21) or NaN
+    auto cells = [&](auto genTag) {
+      constexpr bool GEN = decltype(genTag)::value;
+#pragma unroll
+      for (int j = 0; j < W; j++) {
+        constexpr int dummy = 0;
+        (void)dummy;
+        const int c = j + 2;
+        if (j == 2) {  // cells 0,1 of row r - 1 in the strip to the right were computed a moment ago (its cur[2], cur[3])
+          const float s0 = __shfl_down_sync(0xffffffffu, cur[2], 1), s1 = __shfl_down_sync(0xffffffffu, cur[3], 1);
+          am1[W + 2] = first ? h0 : s0;
+          am1[W + 3] = first ? h1 : s1;
+        }
+        // LsDecoder12.java:424-438 -- evaluated left to right in float32, no fused multiply-add
+        float p = u[0] * cur[c - 1];
+        p = p + u[1] * am1[c - 1];
+        p = p + u[2] * am1[c];
+        p = p + u[3] * am1[c + 1];
+        p = p + u[4] * am1[c + 2];
+        p = p + u[5] * cur[c - 2];
+        p = p + u[6] * am1[c - 2];
+        p = p + u[7] * am2[c - 2];
+        p = p + u[8] * am2[c - 1];
+        p = p + u[9] * am2[c];
+        p = p + u[10] * am2[c + 1];
+        p = p + u[11] * am2[c + 2];
+        const float t1 = __fadd_rd(p, kMagicHalf);
+        if (j < E) accLo |= __float_as_uint(t1) ^ 0x4A800000u;
+        else accHi |= __float_as_uint(t1) ^ 0x4A800000u;
+        const float t2 = __fadd_rd(t1, kMagicHalfUp);  // 1.5*2^23 + StrictMath.round(p)
+        const uint32_t word = rw[j >> 2];
+        const float xj = __uint_as_float(__byte_perm(word, 0x4B400000u, 0x7640 + (j & 3)));  // 1.5*2^23 + residual + 128
+        float fv = t2 + (xj - (2.f * kMagicInt + 128.f));  // exact: float(round(p) + residual)
+        int32_t iv;
+        if constexpr (GEN) {
+          const uint32_t byte = (word >> (8 * (j & 3))) & 0xffu;
+          int32_t ex = int32_t(byte) - 128;
+          if (byte == 0u && valid) ex = wave_exception(exc, nExc, (r - 2) * wInterior + lane * W + j);
+          iv = int32_t(uint32_t(__float_as_int(t2)) - 0x4B400000u + uint32_t(ex));
+          fv = float(iv);
+        } else iv = int32_t(uint32_t(__float_as_int(t2)) + __float_as_uint(xj) - 0x96800080u);  // round(p) + byte - 128
+        if (j == E || j == E + 1) {  // the last strip: Triangle predictor folded into D2 / D1 by kernel H (LsDecoder12.java:459-468)
+          const int32_t prev = j == 0 ? li1 : oi[j > 0 ? j - 1 : 0];
+          const int32_t sv = int32_t(uint32_t(prev) + uint32_t(j == E ? sideCur.z : sideCur.w));
+          if (isLast) { iv = sv; fv = float(sv); }
+        }
+        oi[j] = iv;
+        cur[c] = fv;
       }
-      cells(std::true_type{}, ex);
-    } else cells(std::false_type{}, nullptr);
-    badBits |= acc & badM;
-    // ---- stores: columns 4b .. 4b+3 of the row (two from the previous block); whole sectors when WIDE
-    const int4 sq = make_int4(pi2, pi3, out[0], out[1]);
-    if (WIDE) {
-      asm volatile("{ .reg .pred p; setp.ne.b32 p, %9, 0; @p st.global.v8.b32 [%0], {%1,%2,%3,%4,%5,%6,%7,%8}; }" ::"l"(rowp + b16 - 16), "r"(sqPrev.x),
-                   "r"(sqPrev.y), "r"(sqPrev.z), "r"(sqPrev.w), "r"(sq.x), "r"(sq.y), "r"(sq.z), "r"(sq.w), "r"(validM & (b16 << 19) & 0x00800000u)
-                   : "memory");
-      sqPrev = sq;
-    } else if (validM) *reinterpret_cast<int4*>(rowp + b16) = sq;
-    asm volatile("{ .reg .pred p; setp.ne.b32 p, %0, 0; @p st.shared.v4.f32 [%1], {%2, %3, %4, %5}; }" ::"r"(writerM & started), "r"(rbWrite + b16),
-                 "f"(fout[0]), "f"(fout[1]), "f"(fout[2]), "f"(fout[3])
-                 : "memory");
-    pi2 = out[2];
-    pi3 = out[3];
-    b16 += 16u;
+    };
+    if (general) cells(std::true_type{});
+    else cells(std::false_type{});
+    if (valid) badBits |= (accLo | (isLast ? 0u : accHi)) & 0xFF800000u;
+    // raster: columns k W .. k W + W - 1 of row r = {left2, left1, cells 0 .. W - 3}
+    if (valid) {
+      if constexpr (W == 4) *reinterpret_cast<int4*>(rowp) = make_int4(li2, li1, oi[0], oi[1]);
+      else {
+        if (WIDE) {
+          asm volatile("st.global.v8.b32 [%0], {%1,%2,%3,%4,%5,%6,%7,%8};" ::"l"(rowp), "r"(li2), "r"(li1), "r"(oi[0]), "r"(oi[1]), "r"(oi[2]),
+                       "r"(oi[3]), "r"(oi[4]), "r"(oi[5])
+                       : "memory");
+          if constexpr (W == 16)
+            asm volatile("st.global.v8.b32 [%0], {%1,%2,%3,%4,%5,%6,%7,%8};" ::"l"(rowp + 32), "r"(oi[6]), "r"(oi[7]), "r"(oi[8]), "r"(oi[9]),
+                         "r"(oi[10]), "r"(oi[11]), "r"(oi[12]), "r"(oi[13])
+                         : "memory");
+        } else {
+          *reinterpret_cast<int4*>(rowp) = make_int4(li2, li1, oi[0], oi[1]);
+          *reinterpret_cast<int4*>(rowp + 16) = make_int4(oi[2], oi[3], oi[4], oi[5]);
+          if constexpr (W == 16) {
+            *reinterpret_cast<int4*>(rowp + 32) = make_int4(oi[6], oi[7], oi[8], oi[9]);
+            *reinterpret_cast<int4*>(rowp + 48) = make_int4(oi[10], oi[11], oi[12], oi[13]);
+          }
+        }
+      }
+    }
+    pa = oi[W - 2];
+    pb = oi[W - 1];
+    r++;
+    rowp += rowStep;
     __syncwarp();
   };
 
-  for (int chunk = 0; chunk < nChunks; chunk++) {
-    if (lane == 0 && chunk + 1 < nChunks) issue(chunk + 1);
-    mbar_wait(bar0 + 8u * (chunk & 1), uint32_t(chunk >> 1) & 1u);
-    const uint32_t stage = ringLane + uint32_t(kWaveStageBytes) * (chunk & 1);
+  const int nSteps = G.nSteps;
 #pragma unroll 1
-    for (uint32_t quad = 0; quad < 4; quad++) {  // sixteen residual bytes = four iterations per shared-memory read
-      uint32_t r0, r1, r2, r3;
-      asm volatile("ld.shared.v4.b32 {%0, %1, %2, %3}, [%4];" : "=r"(r0), "=r"(r1), "=r"(r2), "=r"(r3) : "r"(stage + ((quad * 16u) ^ swz16)));
-      step(r0);
-      step(r1);
-      step(r2);
-      step(r3);
-    }
+  for (int s = 0; s < nSteps; s += 3) {
+    step(a0, a1, a2, s);
+    step(a1, a2, a0, s + 1);
+    step(a2, a0, a1, s + 2);
   }
   if (__any_sync(0xffffffffu, badBits != 0u)) {  // outside the fast arithmetic's range: the general kernels redo the tile
     if (lane == 0) A.defer[atomicAdd(A.deferCount, 1)] = tIdx;
   }
-}
-
-typedef CUresult (*TensorMapEncodeFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*, const cuuint64_t*,
-                                      const cuuint32_t*, const cuuint32_t*, CUtensorMapInterleave, CUtensorMapSwizzle,
-                                      CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
-TensorMapEncodeFn tensor_map_encoder() {
-  static TensorMapEncodeFn fn = [] {
-    void* p = nullptr;
-    cudaDriverEntryPointQueryResult qr;
-    if (cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &p, cudaEnableDefault, &qr) != cudaSuccess || qr != cudaDriverEntryPointSuccess) p = nullptr;
-    return reinterpret_cast<TensorMapEncodeFn>(p);
-  }();
-  return fn;
 }
 
 size_t head_smem_bytes(const LsopFastGeom& g) {
@@ -1000,7 +959,22 @@ size_t text_smem_bytes(const LsopFastGeom& g) {
   return ((canon_fast_smem_bytes(text_stage_words(g)) + 127) & ~size_t(127)) + size_t(g.tileBytes);
 }
 size_t wave_smem_bytes(const LsopFastGeom& g) {
-  return size_t(kWarps) * (2 * kWaveStageBytes) + size_t(kWarps) * (2 * g.nB) * sizeof(float4) + size_t(kWarps) * 16;
+  const size_t rbFloats = size_t((g.C + 4 + 3) & ~3);
+  return size_t(kWarps) * (2 * kWaveChunkBytes) + size_t(kWarps) * (2 * rbFloats) * sizeof(float) + size_t(kWarps) * 16;
+}
+
+template <int W>
+cudaError_t launch_wave(const LsopFastArgs& A, int nCtas, int nTilesUpper, cudaStream_t s) {
+  const size_t smem = wave_smem_bytes(A.g);
+  cudaError_t e;
+  if (A.g.wide) {
+    if ((e = cudaFuncSetAttribute(lsop3_wave_kernel<W, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, int(smem))) != cudaSuccess) return e;
+    lsop3_wave_kernel<W, true><<<nCtas, kThreads, smem, s>>>(A, 0, nTilesUpper);
+  } else {
+    if ((e = cudaFuncSetAttribute(lsop3_wave_kernel<W, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, int(smem))) != cudaSuccess) return e;
+    lsop3_wave_kernel<W, false><<<nCtas, kThreads, smem, s>>>(A, 0, nTilesUpper);
+  }
+  return cudaGetLastError();
 }
 
 }  // namespace
@@ -1010,25 +984,29 @@ bool lsop_fast_geometry(const g4_band_desc& band, const void* grid, LsopFastGeom
   g.R = band.tile_rows;
   g.C = band.tile_cols;
   if (g.R < 6 || g.C < 16 || (g.C & 3) != 0 || (band.grid_pitch & 3) != 0 || (reinterpret_cast<uintptr_t>(grid) & 15) != 0) return false;
-  g.nB = g.C / 4;
-  g.nLanes = g.nB < 32 ? g.nB : 32;
-  g.rpg = g.nLanes - 2;
-  g.nGroups = (g.R - 2 + g.rpg - 1) / g.rpg;
-  const int words = 1 + g.nGroups * g.nB;
-  g.laneBytes = ((4 * words + 15) & ~15) + 4;  // == 4 (mod 16): the tensor map's row stride laneBytes - 4 is a multiple of 16
-  g.tileBytes = 32 * g.laneBytes;
-  g.tilePitch = ((g.tileBytes + g.laneBytes - 5) / (g.laneBytes - 4)) * (g.laneBytes - 4);  // every tensor stride a multiple of the one before
-  g.nIter = (words + g.nLanes + 15) & ~15;
-  g.wide = ((g.C & 7) == 0 && (band.grid_pitch & 7) == 0 && (reinterpret_cast<uintptr_t>(grid) & 31) == 0) ? 1 : 0;
+  // strip width: the narrowest that covers the columns with 32 lanes; C has to be a multiple of it (the last strip then
+  // ends with the row's last two columns)
+  if (g.C <= 128) g.W = 4;
+  else if (g.C <= 256 && (g.C & 7) == 0) g.W = 8;
+  else if (g.C <= 512 && (g.C & 15) == 0) g.W = 16;
+  else return false;
+  g.logW = g.W == 4 ? 2 : g.W == 8 ? 3 : 4;
+  g.nStrips = (g.C - 2 + g.W - 1) / g.W;
+  g.P = g.nStrips * g.W;
+  g.nSteps = g.R - 2 + g.nStrips - 1;
+  g.chunkRows = 128 / g.W;
+  g.nChunks = (g.nSteps + g.chunkRows - 1) / g.chunkRows;
+  g.tileBytes = g.nChunks * g.chunkRows * g.P;  // a multiple of 128
+  g.tilePitch = g.tileBytes;
+  g.wide = ((band.grid_pitch & 7) == 0 && (reinterpret_cast<uintptr_t>(grid) & 31) == 0) ? 1 : 0;
   if (text_smem_bytes(g) > 224u * 1024u || head_smem_bytes(g) > 224u * 1024u || wave_smem_bytes(g) > 224u * 1024u) return false;
-  if (!tensor_map_encoder()) return false;
   *out = g;
   return true;
 }
 size_t lsop_fast_side_bytes(const LsopFastGeom& g, int nTiles) { return size_t(nTiles) * size_t(g.R) * sizeof(int4); }
 size_t lsop_fast_exc_bytes(int nTiles) { return size_t(nTiles) * kExcWords * sizeof(uint32_t); }
 size_t lsop_fast_stage_bytes(int smCount) { return size_t(smCount) * 2 * kFastMaxSub * kSpillWords * sizeof(uint32_t); }  // text kernel: <= 2 CTAs per SM
-size_t lsop_fast_resid_bytes(const LsopFastGeom& g, int nTiles) { return size_t(kResidGuard) + size_t(nTiles) * size_t(g.tilePitch) + size_t(g.tileBytes) + 4096; }
+size_t lsop_fast_resid_bytes(const LsopFastGeom& g, int nTiles) { return size_t(kResidGuard) + size_t(nTiles) * size_t(g.tilePitch) + 4096; }
 
 // Kernels H, T and W over the list positions [0, nTilesUpper).  Tiles the fast path cannot take are appended to
 // A.defer / A.deferCount for the general kernels, which the caller launches AFTER this returns.
@@ -1038,27 +1016,7 @@ cudaError_t launch_lsop_decode_fast(const LsopFastArgs& A, int nTilesUpper, int 
   {
     cudaError_t e = cudaFuncSetAttribute(lsop2_head_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, int(head_smem_bytes(g)));
     if (e == cudaSuccess) e = cudaFuncSetAttribute(lsop2_text_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, int(text_smem_bytes(g)));
-    if (e == cudaSuccess) {
-      if (g.wide) e = cudaFuncSetAttribute(lsop2_wave_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, int(wave_smem_bytes(g)));
-      else e = cudaFuncSetAttribute(lsop2_wave_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, int(wave_smem_bytes(g)));
-    }
     if (e != cudaSuccess) return e;
-  }
-  // residual scratch as a 3-D tensor {byte x, lane, tile}: lane stride laneBytes - 4, so that box row l starts 4 l
-  // bytes EARLIER in lane l's stream -- at iteration `it` every lane needs word it - l of its stream
-  alignas(64) CUtensorMap tmap;
-  {
-    cuuint64_t dims[3] = {cuuint64_t(g.laneBytes) + 256, 32, cuuint64_t(A.a.band.tiles_down) * cuuint64_t(A.a.band.tiles_across)};
-    cuuint64_t strides[2] = {cuuint64_t(g.laneBytes - 4), cuuint64_t(g.tilePitch)};
-    cuuint32_t box[3] = {64, 32, 1};
-    cuuint32_t es[3] = {1, 1, 1};
-    const CUresult r = tensor_map_encoder()(&tmap, CU_TENSOR_MAP_DATA_TYPE_UINT8, 3, A.resid + kResidGuard, dims, strides, box, es,
-                                            CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_64B, CU_TENSOR_MAP_L2_PROMOTION_L2_128B,
-                                            CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
-    if (r != CUDA_SUCCESS) {
-      fprintf(stderr, "g4: cuTensorMapEncodeTiled failed (%d), laneBytes %d tilePitch %d\n", int(r), g.laneBytes, g.tilePitch);
-      return cudaErrorNotSupported;
-    }
   }
   const uint32_t stageWords = text_stage_words(g);
   const int nCtasWarp = (nTilesUpper + kWarps - 1) / kWarps;
@@ -1075,9 +1033,9 @@ cudaError_t launch_lsop_decode_fast(const LsopFastArgs& A, int nTilesUpper, int 
   if (ctas > nTilesUpper) ctas = nTilesUpper;
   lsop2_text_kernel<<<ctas, kTextThreads, textSmem, s>>>(T, stageWords, 0, nTilesUpper);
   if ((e = cudaGetLastError()) != cudaSuccess) return e;
-  if (g.wide) lsop2_wave_kernel<true><<<nCtasWarp, kThreads, wave_smem_bytes(g), s>>>(tmap, A, 0, nTilesUpper);
-  else lsop2_wave_kernel<false><<<nCtasWarp, kThreads, wave_smem_bytes(g), s>>>(tmap, A, 0, nTilesUpper);
-  if ((e = cudaGetLastError()) != cudaSuccess) return e;
+  e = g.W == 4 ? launch_wave<4>(A, nCtasWarp, nTilesUpper, s) : g.W == 8 ? launch_wave<8>(A, nCtasWarp, nTilesUpper, s)
+                                                                            : launch_wave<16>(A, nCtasWarp, nTilesUpper, s);
+  if (e != cudaSuccess) return e;
   if (launches) *launches += 3;
   return cudaSuccess;
 }
