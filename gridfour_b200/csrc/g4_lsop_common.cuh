@@ -90,7 +90,11 @@ __device__ inline LsHeaderInfo parse_ls_header(const uint8_t* p, uint32_t len, f
   return h;
 }
 
-constexpr int kLsopMetaBytes = 272;  // [0..3] interior text start (absolute bit, 0 = tile not on the fast path), [8..267] lengths
+// per-tile record handed from the head kernels to the text kernels: [0..3] interior text start (absolute bit, 0 = tile not
+// on the fast path), [8..267] code lengths, and (fast path) the decoding tables built from them: [272..791] sorted[260],
+// [792..825] firstCode[17], [826..859] count[17], [860..893] offset[17] (uint16 each)
+constexpr int kLsopMetaBytes = 896;
+constexpr int kLsopMetaSorted = 272, kLsopMetaFirst = 792, kLsopMetaCount = 826, kLsopMetaOffset = 860;
 
 struct CanonWarpShared {
   uint8_t lens[kCanonSymbols + 4];

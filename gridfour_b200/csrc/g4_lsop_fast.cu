@@ -155,7 +155,15 @@ __global__ void __launch_bounds__(kThreads, 3) lsop2_head_kernel(LsopFastArgs A,
     canon_warp_parse_header(W, src, endBit);  // interior stream: tables only, exported for kernel T
     if (W.error) status = G4_ERR_FORMAT;
     else {
-      for (int i = lane; i < kCanonSymbols; i += 32) m[8 + i] = W.lens[i];
+      for (int i = lane; i < kCanonSymbols; i += 32) {
+        m[8 + i] = W.lens[i];
+        reinterpret_cast<uint16_t*>(m + kLsopMetaSorted)[i] = W.sorted[i];
+      }
+      if (lane < 17) {  // the decoding tables, so that kernel T does not build them a second time
+        reinterpret_cast<uint16_t*>(m + kLsopMetaFirst)[lane] = W.firstCode[lane];
+        reinterpret_cast<uint16_t*>(m + kLsopMetaCount)[lane] = W.count[lane];
+        reinterpret_cast<uint16_t*>(m + kLsopMetaOffset)[lane] = W.offset[lane];
+      }
       if (lane == 0) *reinterpret_cast<uint32_t*>(m) = W.textStart;
     }
   }
@@ -635,7 +643,7 @@ __global__ void __launch_bounds__(kTextThreads, 2) lsop2_text_kernel(LsopFastArg
   extern __shared__ __align__(128) unsigned char textSmem[];
   CanonFastShared& F = *reinterpret_cast<CanonFastShared*>(textSmem);
   uint8_t* tileImg = textSmem + ((canon_fast_smem_bytes(stageWords) + 127) & ~size_t(127));
-  __shared__ int sTile;
+  __shared__ int sTile[2];
   __shared__ __align__(8) uint64_t sBar;
   const DecodeArgs& a = A.a;
   const int tid = threadIdx.x;
@@ -643,16 +651,15 @@ __global__ void __launch_bounds__(kTextThreads, 2) lsop2_text_kernel(LsopFastArg
   if (tid == 0) {
     mbar_init(bar, 1);
     asm volatile("fence.mbarrier_init.release.cluster;");
+    sTile[0] = listBegin + atomicAdd(a.counter, 1);
   }
+  __syncthreads();
   uint32_t parity = 0;
-  for (;;) {
-    if (tid == 0) {
-      asm volatile("cp.async.bulk.wait_group.read 0;" ::: "memory");  // the previous tile's image has left shared memory
-      sTile = listBegin + atomicAdd(a.counter, 1);
-    }
-    __syncthreads();
-    const int li = sTile;
+  for (int phase = 0;; phase ^= 1) {
+    const int li = sTile[phase];
     if (li >= listEnd || li >= *a.listCount) break;
+    // the tile after this one: fetched now, read after the barriers of this iteration
+    if (tid == 0) sTile[phase ^ 1] = listBegin + atomicAdd(a.counter, 1);
     const int tIdx = a.list[li];
     const uint8_t* m = A.meta + size_t(tIdx) * kLsopMetaBytes;
     const uint32_t T0 = *reinterpret_cast<const uint32_t*>(m);
@@ -673,12 +680,17 @@ __global__ void __launch_bounds__(kTextThreads, 2) lsop2_text_kernel(LsopFastArg
       const uint32_t i = nBulk + uint32_t(tid);
       reinterpret_cast<uint8_t*>(F.sw)[i] = i < span ? src16[i] : uint8_t(0);
     }
-    for (int i = tid; i < kCanonSymbols; i += kTextThreads) F.lens[i] = m[8 + i];
+    // decoding tables as kernel H built (and validated) them
+    for (int i = tid; i < kCanonSymbols; i += kTextThreads) F.sorted[i] = reinterpret_cast<const uint16_t*>(m + kLsopMetaSorted)[i];
+    if (tid < 17) {
+      F.firstCode[tid] = reinterpret_cast<const uint16_t*>(m + kLsopMetaFirst)[tid];
+      F.count[tid] = reinterpret_cast<const uint16_t*>(m + kLsopMetaCount)[tid];
+      F.offset[tid] = reinterpret_cast<const uint16_t*>(m + kLsopMetaOffset)[tid];
+    }
     if (tid == 0) F.error = 0;
     __syncthreads();
-    canon_fast_tables_cta<kTextThreads>(F);
-    bool ok = F.error == 0;
-    if (ok) canon_fast_build_lut<kTextThreads>(F);
+    bool ok = true;
+    canon_fast_build_lut<kTextThreads>(F);
     if (nBulk) mbar_wait(bar, parity);
     parity ^= nBulk ? 1u : 0u;
     __syncthreads();
@@ -687,6 +699,8 @@ __global__ void __launch_bounds__(kTextThreads, 2) lsop2_text_kernel(LsopFastArg
       const uint32_t nInterior = uint32_t(A.g.R - 2) * uint32_t(A.g.C - 4);
       ByteTileSink sink;
       sink.init(tileImg, A.exc + size_t(tIdx) * kExcWords, A.g);
+      // the previous tile's image has left shared memory (a barrier follows before the image is written again)
+      if (tid == 0) asm volatile("cp.async.bulk.wait_group.read 0;" ::: "memory");
       if (kTextStaged)
         rc = lsop_text_decode(F, span * 8u, T0 + 8u * delta, nInterior, uint32_t(A.g.tileBytes), sink,
                               reinterpret_cast<uint32_t*>(A.textStage) + size_t(blockIdx.x) * (kFastMaxSub * kSpillWords), A.textLookback);
@@ -786,12 +800,16 @@ __global__ void __launch_bounds__(kThreads, G4_WAVE_CTAS) lsop3_wave_kernel(Lsop
   }
   const int4* side = A.side + size_t(tIdx) * R;
   const bool needSide = active && (isFirst || isLast);
-  int r = 2 - lane;                                  // the row this lane works on in the coming step
+  // rr = (row this lane works on in the coming step) - 2; lanes that hold no strip never become valid
+  uint32_t rr = active ? uint32_t(-lane) : 0x40000000u;
+  const uint32_t nRowsIn = uint32_t(R - 2);
   int4 sideCur = make_int4(0, 0, 0, 0), sideNext = make_int4(0, 0, 0, 0);
-  if (needSide && r + 0 >= 2 && r < R) sideNext = side[r];   // (lane 0; the last lane fetches when its rows begin)
-  char* rowp = reinterpret_cast<char*>(t.base + int64_t(r) * t.pitch + lane * W);  // dereferenced only for valid rows
+  if (needSide && rr < nRowsIn) sideNext = side[2 + rr];   // (lane 0; the last lane fetches when its rows begin)
+  const int4* sideAt = side + 3 - lane;                   // record of the row after the coming step's (dereferenced for valid rows)
+  char* rowp = reinterpret_cast<char*>(t.base + int64_t(2 - lane) * t.pitch + lane * W);  // dereferenced only for valid rows
   const int64_t rowStep = int64_t(t.pitch) * 4;
   const uint32_t ringLane = ring0 + uint32_t(lane * W);
+  uint32_t ringAt = ringLane;                             // this lane's residual bytes of the coming step
   const uint32_t rb0 = smem_u32(rowbuf) + uint32_t(lane * W) * 4u, rb1 = rb0 + uint32_t(rbFloats) * 4u;
   const int wInterior = C - 4;
   uint32_t badBits = 0;  // nonzero: some cell left the range of the fast arithmetic
@@ -810,10 +828,12 @@ __global__ void __launch_bounds__(kThreads, G4_WAVE_CTAS) lsop3_wave_kernel(Lsop
         if (lane == 0 && chunk + 1 < nChunks) issue(chunk + 1);
         mbar_wait(bar0 + 8u * (chunk & 1), uint32_t(chunk >> 1) & 1u);
       }
+      ringAt = ringLane + uint32_t(kWaveChunkBytes) * (chunk & 1);
     }
-    const bool valid = active && r >= 2 && r < R;
-    const bool first = r == 2;
-    if (first && active) {  // (one lane per step, the first nStrips steps) rows 0 and 1 from the row buffer
+    const bool valid = rr < nRowsIn;
+    const bool first = rr == 0u;
+    if (s < nS) {  // (uniform) the steps in which some lane begins
+     if (first) {  // (one lane per step) rows 0 and 1 from the row buffer
 #pragma unroll
       for (int i = 0; i < W + 4; i += 4) {
         float4 x, y;
@@ -824,14 +844,17 @@ __global__ void __launch_bounds__(kThreads, G4_WAVE_CTAS) lsop3_wave_kernel(Lsop
       }
       h0 = am1[W + 2];
       h1 = am1[W + 3];
+     }
     }
     // side record of this row (lane 0: columns 0,1; last lane: D2, D1), the next row's fetched now
     sideCur = sideNext;
-    if (needSide && r + 1 >= 2 && r + 1 < R) sideNext = side[r + 1];
+    if (needSide && rr + 1u < nRowsIn) sideNext = *sideAt;
+    sideAt++;
     // residual bytes of the strip
     uint32_t rw[NW];
     {
-      const uint32_t at = ringLane + uint32_t(kWaveChunkBytes) * ((s / CR) & 1) + uint32_t(s & (CR - 1)) * uint32_t(P);
+      const uint32_t at = ringAt;
+      ringAt += uint32_t(P);
       if constexpr (NW == 1) asm volatile("ld.shared.b32 %0, [%1];" : "=r"(rw[0]) : "r"(at));
       else if constexpr (NW == 2) asm volatile("ld.shared.v2.b32 {%0, %1}, [%2];" : "=r"(rw[0]), "=r"(rw[1]) : "r"(at));
       else asm volatile("ld.shared.v4.b32 {%0, %1, %2, %3}, [%4];" : "=r"(rw[0]), "=r"(rw[1]), "=r"(rw[2]), "=r"(rw[3]) : "r"(at));
@@ -888,7 +911,7 @@ __global__ void __launch_bounds__(kThreads, G4_WAVE_CTAS) lsop3_wave_kernel(Lsop
         if constexpr (GEN) {
           const uint32_t byte = (word >> (8 * (j & 3))) & 0xffu;
           int32_t ex = int32_t(byte) - 128;
-          if (byte == 0u && valid) ex = wave_exception(exc, nExc, (r - 2) * wInterior + lane * W + j);
+          if (byte == 0u && valid) ex = wave_exception(exc, nExc, int(rr) * wInterior + lane * W + j);
           iv = int32_t(uint32_t(__float_as_int(t2)) - 0x4B400000u + uint32_t(ex));
           fv = float(iv);
         } else iv = int32_t(uint32_t(__float_as_int(t2)) + __float_as_uint(xj) - 0x96800080u);  // round(p) + byte - 128
@@ -928,7 +951,7 @@ __global__ void __launch_bounds__(kThreads, G4_WAVE_CTAS) lsop3_wave_kernel(Lsop
     }
     pa = oi[W - 2];
     pb = oi[W - 1];
-    r++;
+    rr++;
     rowp += rowStep;
     __syncwarp();
   };
