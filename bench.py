@@ -303,6 +303,8 @@ def main():
     ap.add_argument("--tile-rows", type=int, default=0, help="tile rows per GPU (default: the config's own)")
     ap.add_argument("--cpu-seconds", type=float, default=12.0)
     ap.add_argument("--no-e2e", action="store_true")
+    ap.add_argument("--codecs", default="", help="comma-separated codec list instead of the config's own (e.g. GvrsHuffman: the "
+                                                 "Huffman/Triangle half of the config-3 path on its own)")
     ap.add_argument("--strong", action="store_true",
                     help="config 3, strong scaling: the WHOLE 43200x86400 grid (240 tile rows) split over the ranks (N=1: one GPU holds it all)")
     args = ap.parse_args()
@@ -311,6 +313,8 @@ def main():
     local_rank = int(os.environ.get("LOCAL_RANK", "0"))
     world = int(os.environ.get("WORLD_SIZE", "1"))
     cfg = dict(CONFIGS[3 if args.config == 5 else args.config])
+    if args.codecs:
+        cfg["codecs"] = [c for c in args.codecs.split(",") if c]
     if args.tile_rows:
         cfg["rows"] = args.tile_rows * cfg["tr"]
     if args.strong and args.config == 3:

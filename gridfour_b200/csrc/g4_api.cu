@@ -309,10 +309,15 @@ int launch_decoder(g4_context* ctx, int codecId, DecodeArgs& a, int nCtas) {
   KernelTimer timer(ctx, 0, codecId);
   const int nTiles = a.band.tiles_down * a.band.tiles_across;
   switch (codecId) {
-    case G4_CODEC_HUFFMAN:
-      CK(launch_huffman_decode(a, nCtas, ctx->stream));
-      ctx->launches++;
+    case G4_CODEC_HUFFMAN: {
+      CK(ctx->defer.ensure(size_t(nTiles) * sizeof(int)));
+      CK(ctx->lsopStage.ensure(huffman2_spill_bytes(ctx->smCount)));
+      HuffFusedScratch fused{ctx->lsopStage.as<uint32_t>(), ctx->defer.as<int>(), ctx->counters.as<int>() + 48, ctx->smCount};
+      int nLaunch = 0;
+      CK(launch_huffman_decode(a, nCtas, ctx->stream, &fused, &nLaunch));
+      ctx->launches += uint64_t(nLaunch);
       return G4_OK;
+    }
     case G4_CODEC_CANON_HUFFMAN:
       CK(launch_canon_decode(a, nCtas, ctx->stream));
       ctx->launches++;

@@ -1,0 +1,488 @@
+// g4_huff2.cuh -- CodecHuffman decode, fused fast path for sm_100a: the M32 bytes never leave shared memory.
+//
+// Reference (under /root/reference/core/src/main/java/org/gridfour/compress/): CodecHuffman.java:133-153 (decode),
+// HuffmanDecoder.java:65-187 (tree + text), CodecM32.java:313-356 (one-byte codes), PredictorModelTriangle.java:160-198
+// (decode).
+//
+// One CTA per tile, persistent.  The packing is staged into shared memory by ONE bulk-async copy (cp.async.bulk +
+// mbarrier); the legacy Huffman tree is parsed by one thread, an 11-bit single + multi-symbol table is built by all; the
+// text is decoded by self-synchronising sub-sequences whose counting pass also stages the symbol bytes (slots inside the
+// destination buffer, a small L2-resident spill behind them), so that after the prefix sum of the counts the bytes are
+// COPIED to their place instead of being decoded a second time (the scheme of the LSOP12 text kernel, g4_lsop_fast.cu).
+// The common case -- Triangle predictor, every M32 code one byte long (nM32 == cells - 1) -- is then finished in place:
+// the residual field F (F[0][0] = seed, row 0 / column 0 / interior residuals in their stream order) is turned into its
+// 2-D inclusive prefix sum band by band: warps scan rows out of the byte buffer into a 32-row band of int32 in shared
+// memory (which reuses the packing's staging area), then one thread per column adds the band to its running column sum
+// and writes the raster rows, coalesced, exactly once.  Every other tile (another predictor, a multi-byte M32 code, a
+// single-symbol tree, an oversized packing) is handed to huffman_decode_kernel through a defer list.
+#pragma once
+#include "g4_huff_fast.cuh"
+
+namespace g4 {
+
+constexpr int kH2MaxSub = 1024;
+constexpr uint32_t kH2SubBits = 320;   // target sub-sequence size
+constexpr uint32_t kH2Lookback = 96;   // the first pass starts this many bits before a sub-sequence limit
+constexpr int kH2StageWords = 22;      // registers that carry a thread's staged symbol bytes across the barrier
+constexpr int kH2SpillWords = 8;       // words behind every slot in the per-CTA global scratch
+constexpr int kH2BandRows = 32;
+constexpr int kH2PadWords = 16;        // zero words behind the staged packing (a long code may be walked past the end)
+constexpr int kH2FlagBad = 1, kH2FlagOverflow = 2;
+
+struct Huff2Shared {
+  uint32_t mlut[1 << kLutBits];  // up to 3 symbols per lookup: s1 | s2 << 8 | s3 << 16 | bits << 24 | n << 28
+  uint16_t lut[1 << kLutBits];   // sym | len << 9; bit 15: code longer than the table, low 9 bits = tree node reached
+  uint16_t kid[512][2];
+  int16_t leafSym[512];
+  uint32_t endpos[kH2MaxSub];
+  uint32_t startv[kH2MaxSub];
+  uint16_t cnt[kH2MaxSub];
+  uint8_t flag[kH2MaxSub];
+  uint16_t pstack[260];          // tree parse (one thread)
+  uint8_t pslot[512];
+  uint32_t scan[33];
+  uint32_t treeBits;
+  int nLeaf, single, error;
+};
+
+struct Huff2Geom {
+  uint32_t stageBytes;  // staging area of the packing (also holds the band of the Triangle pass)
+  uint32_t m32Cap;      // byte buffer of the M32 codes
+};
+
+__device__ __forceinline__ uint32_t h2_smem_u32(const void* p) { return uint32_t(__cvta_generic_to_shared(p)); }
+
+struct H2Cursor {  // register bit window over the staged words, position kept relative to a limit (see BitCursor)
+  uint32_t lo, hi, used, next;
+  int rem;
+  __device__ __forceinline__ void init(const uint32_t* sw, uint32_t p, uint32_t limit) {
+    const uint32_t i = p >> 5;
+    lo = sw[i];
+    hi = sw[i + 1];
+    used = p & 31u;
+    next = i + 2;
+    rem = int(limit) - int(p);
+  }
+  __device__ __forceinline__ uint32_t peek() const { return __funnelshift_r(lo, hi, used); }
+  __device__ __forceinline__ uint32_t pos(uint32_t limit) const { return uint32_t(int(limit) - rem); }
+  __device__ __forceinline__ void skip(const uint32_t* sw, uint32_t n) {
+    used += n;
+    rem -= int(n);
+    if (used >= 32u) {
+      lo = hi;
+      hi = sw[next++];
+      used -= 32u;
+    }
+  }
+};
+
+// HuffmanDecoder.decodeTree (:65-161) over the staged words, bounds-checked.  One thread.
+__device__ inline void h2_parse_tree(Huff2Shared& S, const uint32_t* sw, uint32_t startBit, uint32_t nBits) {
+  auto bits = [&](uint32_t pos, int n) {
+    const uint32_t i = pos >> 5;
+    return __funnelshift_r(sw[i], sw[i + 1], pos & 31u) & ((1u << n) - 1u);
+  };
+  S.error = 0;
+  S.single = -1;
+  if (startBit + 17 > nBits) { S.error = 1; return; }
+  const int L = int(bits(startBit, 8)) + 1;
+  S.nLeaf = L;
+  uint32_t pos = startBit + 8;
+  if (bits(pos, 1)) {
+    S.single = int(bits(pos + 1, 8));
+    S.treeBits = startBit + 17;
+    return;
+  }
+  pos = startBit + 9;
+  int nodes = 1, sp = 1, leaves = 0;
+  S.pstack[0] = 0;
+  S.pslot[0] = 0;
+  S.leafSym[0] = -1;
+  while (leaves < L) {
+    if (sp == 0 || nodes >= 511 || pos + 9 > nBits + 8) { S.error = 1; return; }
+    const int parent = S.pstack[sp - 1];
+    const uint32_t x = bits(pos, 9);
+    const int id = nodes++;
+    S.kid[parent][S.pslot[parent]++] = uint16_t(id);
+    if (x & 1u) {
+      S.leafSym[id] = int16_t((x >> 1) & 0xffu);
+      S.pslot[id] = 2;
+      pos += 9;
+      leaves++;
+      while (sp > 0 && S.pslot[S.pstack[sp - 1]] == 2) sp--;
+    } else {
+      if (sp >= 258) { S.error = 1; return; }
+      S.leafSym[id] = -1;
+      S.pslot[id] = 0;
+      S.pstack[sp++] = uint16_t(id);
+      pos += 1;
+    }
+  }
+  if (sp != 0 || pos > nBits) { S.error = 1; return; }
+  S.treeBits = pos;
+}
+
+template <int NT>
+__device__ inline void h2_build_lut(Huff2Shared& S) {
+  for (int e = threadIdx.x; e < (1 << kLutBits); e += NT) {
+    int n = 0, d = 0;
+    uint16_t entry = 0;
+    for (; d < kLutBits; d++) {
+      n = S.kid[n][(e >> d) & 1];
+      if (S.leafSym[n] >= 0) { entry = uint16_t(S.leafSym[n] | ((d + 1) << 9)); break; }
+    }
+    if (d == kLutBits) entry = uint16_t(0x8000u | n);
+    S.lut[e] = entry;
+  }
+  __syncthreads();
+  for (int e = threadIdx.x; e < (1 << kLutBits); e += NT) {
+    uint32_t used = 0, n = 0, syms = 0;
+    while (n < 3) {
+      const uint32_t x = S.lut[(uint32_t(e) >> used) & ((1u << kLutBits) - 1u)];
+      const uint32_t len = (x >> 9) & 15u;
+      if ((x & 0x8000u) || used + len > uint32_t(kLutBits)) break;
+      syms |= (x & 0xffu) << (8 * n);
+      used += len;
+      n++;
+    }
+    S.mlut[e] = syms | (used << 24) | (n << 28);
+  }
+  __syncthreads();
+}
+
+// One symbol whose code is longer than the table: walk the tree from the node the table entry names.
+__device__ __forceinline__ int h2_long_symbol(const Huff2Shared& S, const uint32_t* sw, uint32_t e, uint32_t p0, uint32_t* after) {
+  int n = int(e & 0x1ffu);
+  uint32_t p = p0 + uint32_t(kLutBits);
+  while (S.leafSym[n] < 0) {
+    n = S.kid[n][(sw[p >> 5] >> (p & 31u)) & 1u];
+    p++;
+  }
+  *after = p;
+  return S.leafSym[n];
+}
+
+// Decodes one sub-sequence: from `start` to the first symbol boundary at or after `limit` (<= nBits).  With STORE the
+// symbol bytes go to slot[0 .. slotWords) (shared memory) and on to spill[0 .. kH2SpillWords) (global).
+template <bool STORE>
+__device__ __forceinline__ void h2_sub(const Huff2Shared& S, const uint32_t* sw, uint32_t nBits, uint32_t start, uint32_t limit, uint32_t* slot,
+                                       uint32_t slotWords, uint32_t* spill, uint32_t* endOut, uint32_t* cntOut, int* flagOut) {
+  H2Cursor cur;
+  cur.init(sw, start, limit);
+  uint32_t c = 0, end, w = 0, qc = 0;
+  uint64_t q = 0;
+  int flag = 0;
+  auto flush = [&]() {
+    if (STORE) {
+      if (w < slotWords) slot[w] = uint32_t(q);
+      else if (w - slotWords < uint32_t(kH2SpillWords)) spill[w - slotWords] = uint32_t(q);
+    }
+    w++;
+  };
+  for (;;) {
+    if (cur.rem >= kLutBits) {  // the whole window lies before the limit: every symbol coded inside it is consumed
+      const uint32_t m = S.mlut[cur.peek() & ((1u << kLutBits) - 1u)];
+      const uint32_t n = m >> 28;
+      if (n) {
+        cur.skip(sw, (m >> 24) & 15u);
+        c += n;
+        if (STORE) {
+          q |= uint64_t(m & 0xffffffu) << (8 * qc);
+          qc += n;
+          if (qc >= 4) {
+            flush();
+            q >>= 32;
+            qc -= 4;
+          }
+        }
+        continue;
+      }
+    }
+    if (cur.rem <= 0) { end = cur.pos(limit); break; }
+    const uint32_t e = S.lut[cur.peek() & ((1u << kLutBits) - 1u)];
+    uint32_t byte;
+    if (!(e & 0x8000u)) {
+      cur.skip(sw, (e >> 9) & 15u);
+      byte = e & 0xffu;
+    } else {
+      const uint32_t p0 = cur.pos(limit);
+      uint32_t after;
+      byte = uint32_t(h2_long_symbol(S, sw, e, p0, &after));
+      if (after > nBits + 32u * kH2PadWords - 64u) { flag |= kH2FlagBad; end = p0; break; }
+      cur.init(sw, after, limit);
+    }
+    c++;
+    if (STORE) {
+      q |= uint64_t(byte) << (8 * qc);
+      qc += 1;
+      if (qc >= 4) {
+        flush();
+        q >>= 32;
+        qc -= 4;
+      }
+    }
+  }
+  if (STORE) {
+    if (qc) flush();
+    if (w > slotWords + uint32_t(kH2SpillWords)) flag |= kH2FlagOverflow;
+  }
+  *endOut = end;
+  *cntOut = c;
+  *flagOut = flag;
+}
+
+// Linear byte sink of the copy pass: a run starts at any byte; its head goes out byte by byte up to the next word, the
+// rest as aligned words, the tail by bytes (neighbouring runs share words, never bytes).
+struct H2ByteSink {
+  uint8_t* base;
+  uint32_t addr;  // word-aligned offset of queue byte 0
+  int head, cnt;
+  uint64_t q;
+  __device__ __forceinline__ void begin(uint8_t* b, uint32_t o0) {
+    base = b;
+    head = int(o0 & 3u);
+    addr = o0 & ~3u;
+    cnt = head;
+    q = 0;
+  }
+  __device__ __forceinline__ void push(uint32_t bytes, int n) {  // n = 1..4
+    q |= uint64_t(bytes) << (8 * cnt);
+    cnt += n;
+    if (cnt >= 4) {
+      if (head) {
+        for (int i = head; i < 4; i++) base[addr + i] = uint8_t(q >> (8 * i));
+        head = 0;
+      } else *reinterpret_cast<uint32_t*>(base + addr) = uint32_t(q);
+      q >>= 32;
+      cnt -= 4;
+      addr += 4;
+    }
+  }
+  __device__ __forceinline__ void end() {
+    for (int i = head; i < cnt; i++) base[addr + i] = uint8_t(q >> (8 * i));
+  }
+};
+
+// Decodes the text (tables ready, text at staged bit T0, nBits = end of the packing) into out[0 .. nSym).  `out` is a
+// 16-byte aligned shared-memory buffer of outCap bytes.  All NT threads call.
+// Returns 0 = done, 1 = malformed stream, 2 = a sub-sequence outgrew slot + spill (the caller defers the tile).
+template <int NT>
+__device__ int h2_decode_text(Huff2Shared& S, const uint32_t* sw, uint32_t nBits, const uint32_t T0, uint32_t nSym, uint8_t* out,
+                              uint32_t outCap, uint32_t* spillArea) {
+  constexpr int kRounds = kH2MaxSub / NT;
+  const int tid = threadIdx.x;
+  if (T0 > nBits) return 1;
+  const uint32_t avail = nBits - T0;
+  uint32_t rounds = (avail / kH2SubBits + NT - 1) / NT;
+  if (rounds < 1u) rounds = 1u;
+  if (rounds > uint32_t(kRounds)) rounds = kRounds;
+  uint32_t B = (avail + rounds * NT - 1) / (rounds * NT);
+  if (B < 96u) B = 96u;
+  const int nSub = int((avail + B - 1) / B);
+  if (nSub == 0) return nSym == 0 ? 0 : 1;
+  const uint32_t perSub = uint32_t(kH2StageWords) / rounds;
+  uint32_t slotWords = (outCap / uint32_t(nSub)) >> 2;
+  if (slotWords > perSub) slotWords = perSub;
+  uint32_t* const out32 = reinterpret_cast<uint32_t*>(out);
+  // pass 0: only the END of every sub-sequence matters here, so start kH2Lookback bits before the limit and rely on
+  // self-synchronisation (a wrong guess is repaired by the passes below; the result never depends on it)
+#pragma unroll 1
+  for (int i = tid; i < nSub; i += NT) {
+    uint32_t limit = T0 + uint32_t(i + 1) * B;
+    if (limit > nBits) limit = nBits;
+    uint32_t from = T0 + uint32_t(i) * B;
+    if (limit - from > kH2Lookback) from = limit - kH2Lookback;
+    uint32_t e, c;
+    int f;
+    h2_sub<false>(S, sw, nBits, from, limit, nullptr, 0, nullptr, &e, &c, &f);
+    S.endpos[i] = e;
+    S.startv[i] = 0xffffffffu;  // forces the exact decode of every sub-sequence in the first pass below
+  }
+  // synchronisation passes: sub-sequence i must start where i-1 ended.  Reads of endpos[i-1] may see this pass's or the
+  // previous pass's value (both are candidates); the loop ends only after a pass in which nothing was rewritten.
+  volatile uint32_t* vend = S.endpos;
+  __syncthreads();
+  for (int pass = 0; pass <= nSub; pass++) {
+    bool any = false;
+#pragma unroll 1
+    for (int i = tid; i < nSub; i += NT) {
+      const uint32_t ns = i ? vend[i - 1] : T0;
+      if (ns != S.startv[i]) {
+        S.startv[i] = ns;
+        uint32_t limit = T0 + uint32_t(i + 1) * B;
+        if (limit > nBits) limit = nBits;
+        uint32_t e, c;
+        int f;
+        h2_sub<true>(S, sw, nBits, ns, limit, out32 + size_t(i) * slotWords, slotWords, spillArea + size_t(i) * kH2SpillWords, &e, &c, &f);
+        vend[i] = e;
+        S.cnt[i] = uint16_t(c);
+        S.flag[i] = uint8_t(f);
+        any = true;
+      }
+    }
+    if (!__syncthreads_or(any ? 1 : 0)) break;
+  }
+  // symbol offsets: thread tid owns sub-sequences tid*kRounds .. +kRounds-1 for the scan
+  uint32_t mySum = 0;
+  int myFlags = 0;
+#pragma unroll
+  for (int j = 0; j < kRounds; j++) {
+    const int i = tid * kRounds + j;
+    if (i < nSub) {
+      mySum += S.cnt[i];
+      myFlags |= S.flag[i];
+    }
+  }
+  uint32_t total;
+  const uint32_t ex = block_exclusive_scan<NT>(mySum, S.scan, &total);
+  const int flags = __syncthreads_or(myFlags);
+  if (total < nSym) return 1;  // text shorter than the header claims
+  if (flags & kH2FlagOverflow) return 2;
+  uint32_t* offv = S.endpos;  // end positions are no longer needed: the array now holds the first symbol index of every sub-sequence
+  {
+    uint32_t run = ex;
+#pragma unroll
+    for (int j = 0; j < kRounds; j++) {
+      const int i = tid * kRounds + j;
+      if (i < nSub) {
+        offv[i] = run;
+        run += S.cnt[i];
+      }
+    }
+  }
+  __syncthreads();
+  // slots -> registers (every thread: sub-sequences tid, tid + NT, ...), barrier, registers -> their place in the buffer
+  uint32_t r[kH2StageWords];
+#pragma unroll
+  for (int j = 0; j < kH2StageWords; j++) r[j] = 0;
+  for (uint32_t s = 0; s < rounds; s++) {
+    const int i = tid + int(s) * NT;
+    if (i < nSub) {
+      const uint32_t* slot = out32 + size_t(i) * slotWords;
+#pragma unroll
+      for (int j = 0; j < kH2StageWords; j++)
+        if (uint32_t(j) >= s * perSub && uint32_t(j) < s * perSub + slotWords) r[j] = slot[uint32_t(j) - s * perSub];
+    }
+  }
+  __syncthreads();
+  bool bad = false;
+  for (uint32_t s = 0; s < rounds; s++) {
+    const int i = tid + int(s) * NT;
+    if (i >= nSub) continue;
+    const uint32_t o0 = offv[i];
+    if (o0 >= nSym) continue;  // padding bits behind the text that decode to symbols
+    uint32_t n = S.cnt[i];
+    if (n > nSym - o0) n = nSym - o0;
+    if (S.flag[i] & kH2FlagBad) bad = true;  // an invalid code inside the text proper
+    if (n == 0) continue;
+    H2ByteSink sink;
+    sink.begin(out, o0);
+#pragma unroll
+    for (int j = 0; j < kH2StageWords; j++) {
+      const uint32_t at = (uint32_t(j) - s * perSub) * 4u;  // byte position of word j inside this sub-sequence's slot
+      if (uint32_t(j) >= s * perSub && uint32_t(j) < s * perSub + slotWords && at < n) {
+        const uint32_t m = n - at;
+        sink.push(m >= 4u ? r[j] : (r[j] & ((1u << (8 * m)) - 1u)), m >= 4u ? 4 : int(m));
+      }
+    }
+    if (n > slotWords * 4u) {  // the tail this thread spilled in the staging pass
+      const uint32_t* sp = spillArea + size_t(i) * kH2SpillWords;
+      for (uint32_t at = slotWords * 4u; at < n; at += 4u) {
+        const uint32_t wv = *sp++, m = n - at;
+        sink.push(m >= 4u ? wv : (wv & ((1u << (8 * m)) - 1u)), m >= 4u ? 4 : int(m));
+      }
+    }
+    sink.end();
+  }
+  return __syncthreads_or(bad ? 1 : 0) ? 1 : 0;
+}
+
+// Triangle predictor, every residual a one-byte M32 code: raster = 2-D inclusive prefix sum of the residual field.
+// m32 = the nM32 = R*C - 1 code bytes in stream order (row 0 from column 1, column 0 from row 1, interior
+// row-major), readable from m32 - 4; band = kH2BandRows * C int32 of shared memory.  All NT threads call.
+template <int NT>
+__device__ inline void h2_triangle_bytes(const uint8_t* m32, int32_t seed, const TileView& t, int32_t* band) {
+  const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+  constexpr int kW = NT / 32;
+  const int R = t.R, C = t.C;
+  uint32_t run0 = 0, run1 = 0;  // running column sums of columns tid and tid + NT
+  auto value = [](uint32_t b) { return b == 0x80u ? uint32_t(INT32_MIN) : uint32_t(int32_t(int8_t(b))); };  // CodecM32.java:313-324
+  for (int r0 = 0; r0 < R; r0 += kH2BandRows) {
+    const int nr = R - r0 < kH2BandRows ? R - r0 : kH2BandRows;
+    for (int i = warp; i < nr; i += kW) {  // row scans: band[i][c] = F[r][0] + ... + F[r][c]
+      const int r = r0 + i;
+      const int baseR = r == 0 ? 0 : (C + R - 2) + (r - 1) * (C - 1);  // stream index of F[r][1]
+      const uint32_t f0 = r == 0 ? uint32_t(seed) : value(m32[C - 1 + (r - 1)]);
+      uint32_t carry = 0;
+      for (int c0 = 0; c0 < C; c0 += 256) {
+        const int c = c0 + 8 * lane;
+        const int o = baseR + c - 1;  // stream index of element (r, c); -1 for c == 0
+        const int a = o & ~3;
+        uint32_t lo = 0, hi = 0;
+        if (c < C) {
+          const uint32_t w0 = *reinterpret_cast<const uint32_t*>(m32 + a), w1 = *reinterpret_cast<const uint32_t*>(m32 + a + 4),
+                         w2 = *reinterpret_cast<const uint32_t*>(m32 + a + 8);
+          const uint32_t sh = uint32_t(o & 3) * 8u;
+          lo = __funnelshift_r(w0, w1, sh);
+          hi = __funnelshift_r(w1, w2, sh);
+        }
+        uint32_t e[8];
+#pragma unroll
+        for (int j = 0; j < 8; j++) {
+          const uint32_t word = j < 4 ? lo : hi;
+          // sign-extended byte j: prmt with the sign-replicating selector nibbles (8 | byte index); __byte_perm masks that bit away
+          asm("prmt.b32 %0, %1, %2, %3;" : "=r"(e[j]) : "r"(word), "r"(0u), "r"(0x8880u | (uint32_t(j & 3) * 0x1111u)));
+        }
+        // the INT_MIN code 0x80 (rare): patch by value
+        if (__any_sync(0xffffffffu, (((lo ^ 0x80808080u) - 0x01010101u) & ~(lo ^ 0x80808080u) & 0x80808080u) != 0u ||
+                                        (((hi ^ 0x80808080u) - 0x01010101u) & ~(hi ^ 0x80808080u) & 0x80808080u) != 0u)) {
+#pragma unroll
+          for (int j = 0; j < 8; j++) {
+            const uint32_t b = ((j < 4 ? lo : hi) >> (8 * (j & 3))) & 0xffu;
+            if (b == 0x80u) e[j] = uint32_t(INT32_MIN);
+          }
+        }
+        if (c == 0) e[0] = f0;
+#pragma unroll
+        for (int j = 0; j < 8; j++)
+          if (c + j >= C) e[j] = 0u;
+        uint32_t loc = 0;
+#pragma unroll
+        for (int j = 0; j < 8; j++) { loc += e[j]; e[j] = loc; }
+        const uint32_t inc = warp_inclusive_scan(loc);
+        const uint32_t base = carry + inc - loc;
+        carry += __shfl_sync(0xffffffffu, inc, 31);
+        int32_t* dst = band + size_t(i) * C + c;
+        if (c + 8 <= C && (C & 3) == 0) {
+          *reinterpret_cast<int4*>(dst) = make_int4(int32_t(e[0] + base), int32_t(e[1] + base), int32_t(e[2] + base), int32_t(e[3] + base));
+          *reinterpret_cast<int4*>(dst + 4) = make_int4(int32_t(e[4] + base), int32_t(e[5] + base), int32_t(e[6] + base), int32_t(e[7] + base));
+        } else {
+#pragma unroll
+          for (int j = 0; j < 8; j++)
+            if (c + j < C) dst[j] = int32_t(e[j] + base);
+        }
+      }
+    }
+    __syncthreads();
+    // column sums: thread c adds the band's rows to its running sum and writes the raster, one row per step
+    if (tid < C) {
+      const int32_t* b = band + tid;
+      int32_t* o = t.row(r0) + tid;
+      for (int i = 0; i < nr; i++) {
+        run0 += uint32_t(b[size_t(i) * C]);
+        o[int64_t(i) * t.pitch] = int32_t(run0);
+      }
+    }
+    if (tid + NT < C) {
+      const int32_t* b = band + tid + NT;
+      int32_t* o = t.row(r0) + tid + NT;
+      for (int i = 0; i < nr; i++) {
+        run1 += uint32_t(b[size_t(i) * C]);
+        o[int64_t(i) * t.pitch] = int32_t(run1);
+      }
+    }
+    __syncthreads();
+  }
+}
+
+}  // namespace g4

@@ -19,6 +19,7 @@
 #include "g4_predict.cuh"
 #include "g4_huffdec.cuh"
 #include "g4_huff_fast.cuh"
+#include "g4_huff2.cuh"
 
 namespace g4 {
 
@@ -417,6 +418,96 @@ __global__ void __launch_bounds__(kThreads, 4) huffman_decode_kernel(DecodeArgs 
   }
 }
 
+// =================================================================================================
+// Fused fast path (g4_huff2.cuh): Triangle predictor + one-byte M32 codes finished in shared memory; everything else is
+// appended to defer[] for huffman_decode_kernel.  spill: kH2MaxSub * kH2SpillWords words per CTA.
+template <int NT>
+__global__ void __launch_bounds__(NT, NT == 512 ? 2 : 4)
+    huffman2_decode_kernel(DecodeArgs a, Huff2Geom g, uint32_t* spill, int* defer, int* deferCount) {
+  extern __shared__ __align__(128) unsigned char h2Smem[];
+  Huff2Shared& S = *reinterpret_cast<Huff2Shared*>(h2Smem);
+  uint32_t* sw = reinterpret_cast<uint32_t*>(h2Smem + ((sizeof(Huff2Shared) + 127) & ~size_t(127)));
+  uint8_t* m32 = reinterpret_cast<uint8_t*>(sw) + g.stageBytes + 16;  // 16 bytes in front: the Triangle pass reads m32[-4 ..]
+  __shared__ int sTile[2];
+  __shared__ __align__(8) uint64_t sBar;
+  const int tid = threadIdx.x;
+  const uint32_t bar = h2_smem_u32(&sBar);
+  if (tid == 0) {
+    asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(bar), "r"(1));
+    asm volatile("fence.mbarrier_init.release.cluster;");
+    sTile[0] = atomicAdd(a.counter, 1);
+  }
+  __syncthreads();
+  uint32_t parity = 0;
+  uint32_t* spillArea = spill + size_t(blockIdx.x) * (kH2MaxSub * kH2SpillWords);
+  for (int phase = 0;; phase ^= 1) {
+    const int li = sTile[phase];
+    if (li >= *a.listCount) break;
+    if (tid == 0) sTile[phase ^ 1] = atomicAdd(a.counter, 1);  // the tile after this one, read after this iteration's barriers
+    const int tIdx = a.list[li];
+    const TileView t = tile_view(a.band, a.grid, tIdx);
+    const int n = t.R * t.C;
+    const uint8_t* packing = a.arena + a.offsets[tIdx];
+    const uint32_t len = a.lens[tIdx];
+    // CodecHuffman.decode header (CodecHuffman.java:134-143)
+    const int pred = len >= 10 ? int(packing[1]) : 0;
+    const int32_t seed = len >= 10 ? int32_t(load_le32(packing + 2)) : 0;
+    const uint32_t nM32 = len >= 10 ? load_le32(packing + 6) : 0;
+    const uint32_t expect = pred == G4_PRED_DIFF_NULLS ? uint32_t(n) : uint32_t(n - 1);
+    if (len < 12 || pred < 1 || pred > 4 || nM32 < expect || nM32 > uint32_t(6 * n)) {
+      if (tid == 0) a.status[tIdx] = G4_ERR_FORMAT;
+      __syncthreads();
+      continue;
+    }
+    const uint32_t delta = uint32_t(reinterpret_cast<uintptr_t>(packing) & 15u);
+    const uint32_t span = len + delta;
+    bool fast = pred == G4_PRED_TRIANGLE && nM32 == uint32_t(n - 1) && span + 4u * kH2PadWords + 16u <= g.stageBytes &&
+                nM32 + 32u <= g.m32Cap && t.C <= 2 * NT && size_t(kH2BandRows) * t.C * 4 <= g.stageBytes;
+    int rc = 0;
+    if (fast) {
+      // stage: the packing from its 16-byte line start; whole 16-byte pieces by ONE bulk-async copy, the tail by bytes
+      const uint8_t* src16 = packing - delta;
+      const uint32_t nBulk = span & ~15u;
+      if (tid == 0 && nBulk) {
+        asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(bar), "r"(nBulk) : "memory");
+        asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(h2_smem_u32(sw)), "l"(src16),
+                     "r"(nBulk), "r"(bar)
+                     : "memory");
+      }
+      if (tid < 16 + 4 * kH2PadWords) {  // tail bytes and zero padding
+        const uint32_t i = nBulk + uint32_t(tid);
+        reinterpret_cast<uint8_t*>(sw)[i] = i < span ? src16[i] : uint8_t(0);
+      }
+      if (nBulk) {
+        uint32_t done = 0;
+        while (!done)
+          asm volatile("{ .reg .pred p; mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2; selp.u32 %0, 1, 0, p; }"
+                       : "=r"(done)
+                       : "r"(bar), "r"(parity)
+                       : "memory");
+        parity ^= 1u;
+      }
+      __syncthreads();
+      const uint32_t nBits = span * 8u;
+      if (tid == 0) h2_parse_tree(S, sw, (delta + 10u) * 8u, nBits);
+      __syncthreads();
+      if (S.error) rc = 1;
+      else if (S.single >= 0) fast = false;  // one-symbol tree: no text in the stream
+      else {
+        h2_build_lut<NT>(S);
+        rc = h2_decode_text<NT>(S, sw, nBits, S.treeBits, nM32, m32, g.m32Cap - 16u, spillArea);
+        if (rc == 2) { fast = false; rc = 0; }
+        else if (rc == 0) h2_triangle_bytes<NT>(m32, seed, t, reinterpret_cast<int32_t*>(sw));  // (ends with a barrier)
+      }
+    }
+    if (tid == 0) {
+      if (!fast) defer[atomicAdd(deferCount, 1)] = tIdx;
+      else a.status[tIdx] = rc ? G4_ERR_FORMAT : G4_OK;
+    }
+    __syncthreads();
+  }
+}
+
 cudaError_t launch_huffman_encode(const EncodeArgs& a, int nCtas, cudaStream_t s) {
   static std::atomic<uint64_t> attr{0};
   cudaError_t ea = once_per_device(attr, [] {
@@ -427,7 +518,25 @@ cudaError_t launch_huffman_encode(const EncodeArgs& a, int nCtas, cudaStream_t s
   return cudaGetLastError();
 }
 
-cudaError_t launch_huffman_decode(const DecodeArgs& a, int nCtas, cudaStream_t s) {
+template <int NT>
+static cudaError_t launch_huffman2(const DecodeArgs& a, const Huff2Geom& g, size_t smem, int smCount, int nTilesUpper, uint32_t* spill, int* defer,
+                                   int* deferCount, cudaStream_t s) {
+  cudaError_t e = cudaFuncSetAttribute(huffman2_decode_kernel<NT>, cudaFuncAttributeMaxDynamicSharedMemorySize, int(smem));
+  if (e != cudaSuccess) return e;
+  int perSm = int((227u * 1024u) / (smem + 1024));
+  const int cap = NT == 512 ? 2 : 4;
+  if (perSm > cap) perSm = cap;
+  if (perSm < 1) perSm = 1;
+  int ctas = smCount * perSm;
+  if (ctas > nTilesUpper) ctas = nTilesUpper;
+  huffman2_decode_kernel<NT><<<ctas, NT, smem, s>>>(a, g, spill, defer, deferCount);
+  return cudaGetLastError();
+}
+
+size_t huffman2_spill_bytes(int smCount) { return size_t(smCount) * 4 * kH2MaxSub * kH2SpillWords * sizeof(uint32_t); }
+
+// fused: scratch of the fast path (spill of huffman2_spill_bytes, defer list of nTilesUpper ints, two zeroed counters), or null
+cudaError_t launch_huffman_decode(const DecodeArgs& a, int nCtas, cudaStream_t s, const HuffFusedScratch* fused, int* launches) {
   // staging capacity of the fast decoder: 6 bits per sample of the tile (legacy Huffman over M32 bytes takes 4-5 bits
   // per sample on terrain), at most 160 KB (one CTA per SM)
   uint64_t bytes = uint64_t(a.band.tile_rows) * uint64_t(a.band.tile_cols) * 6 / 8 + 64;
@@ -435,6 +544,7 @@ cudaError_t launch_huffman_decode(const DecodeArgs& a, int nCtas, cudaStream_t s
   uint32_t stageWords = uint32_t((bytes + 3) / 4);
   if (stageWords < uint32_t(kHfStageWordsMin)) stageWords = kHfStageWordsMin;
   static const bool fastOn = !(getenv("G4_HUFF_FAST") && atoi(getenv("G4_HUFF_FAST")) == 0);
+  static const bool fusedOn = !(getenv("G4_HUFF_FUSED") && atoi(getenv("G4_HUFF_FUSED")) == 0);
   if (!fastOn) stageWords = 0;
   size_t smem = huff_fast_smem_bytes(stageWords);
   if (smem < sizeof(HuffDecShared)) smem = sizeof(HuffDecShared);
@@ -444,7 +554,29 @@ cudaError_t launch_huffman_decode(const DecodeArgs& a, int nCtas, cudaStream_t s
                                 int(huff_fast_smem_bytes(160 * 1024 / 4 + 16)));
   });
   if (ea != cudaSuccess) return ea;
-  huffman_decode_kernel<<<nCtas, kThreads, smem, s>>>(a, stageWords);
+  DecodeArgs rest = a;
+  if (fused && fastOn && fusedOn && a.band.elem_type == G4_ELEM_I32) {
+    const uint32_t n = uint32_t(a.band.tile_rows) * uint32_t(a.band.tile_cols);
+    Huff2Geom g;
+    uint32_t stage = (n * 6u / 8u + 256u + 15u) & ~15u;
+    const uint32_t bandBytes = uint32_t(kH2BandRows) * uint32_t(a.band.tile_cols) * 4u;
+    if (stage < bandBytes) stage = (bandBytes + 15u) & ~15u;
+    g.stageBytes = stage;
+    g.m32Cap = (n + 48u + 15u) & ~15u;
+    const size_t smem2 = ((sizeof(Huff2Shared) + 127) & ~size_t(127)) + g.stageBytes + 16 + g.m32Cap;
+    if (smem2 <= 112u * 1024u) {  // two 512-thread CTAs (or four 256-thread CTAs) per SM
+      const int nTilesUpper = a.band.tiles_down * a.band.tiles_across;
+      cudaError_t e = n <= 16384u ? launch_huffman2<256>(a, g, smem2, fused->smCount, nTilesUpper, fused->spill, fused->defer, fused->counters, s)
+                                  : launch_huffman2<512>(a, g, smem2, fused->smCount, nTilesUpper, fused->spill, fused->defer, fused->counters, s);
+      if (e != cudaSuccess) return e;
+      if (launches) (*launches)++;
+      rest.list = fused->defer;
+      rest.listCount = fused->counters;
+      rest.counter = fused->counters + 1;
+    }
+  }
+  huffman_decode_kernel<<<nCtas, kThreads, smem, s>>>(rest, stageWords);
+  if (launches) (*launches)++;
   return cudaGetLastError();
 }
 
