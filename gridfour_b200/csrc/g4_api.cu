@@ -312,7 +312,8 @@ int launch_decoder(g4_context* ctx, int codecId, DecodeArgs& a, int nCtas) {
     case G4_CODEC_HUFFMAN: {
       CK(ctx->defer.ensure(size_t(nTiles) * sizeof(int)));
       CK(ctx->lsopStage.ensure(huffman2_spill_bytes(ctx->smCount)));
-      HuffFusedScratch fused{ctx->lsopStage.as<uint32_t>(), ctx->defer.as<int>(), ctx->counters.as<int>() + 48, ctx->smCount};
+      CK(ctx->lsopMeta.ensure(huffman2_tree_bytes(nTiles)));
+      HuffFusedScratch fused{ctx->lsopStage.as<uint32_t>(), ctx->lsopMeta.as<uint8_t>(), ctx->defer.as<int>(), ctx->counters.as<int>() + 48, ctx->smCount};
       int nLaunch = 0;
       CK(launch_huffman_decode(a, nCtas, ctx->stream, &fused, &nLaunch));
       ctx->launches += uint64_t(nLaunch);

@@ -21,13 +21,18 @@
 namespace g4 {
 
 constexpr int kH2MaxSub = 1024;
-constexpr uint32_t kH2SubBits = 320;   // target sub-sequence size
-constexpr uint32_t kH2Lookback = 96;   // the first pass starts this many bits before a sub-sequence limit
+constexpr uint32_t kH2SubBits = 448;   // target sub-sequence size (one round of sub-sequences for a 180x240 tile in a 512-thread CTA)
+constexpr uint32_t kH2Lookback = 192;  // the first pass starts this many bits before a sub-sequence limit (swept: 64 .. 320)
 constexpr int kH2StageWords = 22;      // registers that carry a thread's staged symbol bytes across the barrier
-constexpr int kH2SpillWords = 8;       // words behind every slot in the per-CTA global scratch
+constexpr int kH2SpillWords = 16;      // words behind every slot in the per-CTA global scratch
 constexpr int kH2BandRows = 32;
 constexpr int kH2PadWords = 16;        // zero words behind the staged packing (a long code may be walked past the end)
 constexpr int kH2FlagBad = 1, kH2FlagOverflow = 2;
+
+struct H2TreeMeta {
+  uint32_t treeBits;
+  int nLeaf, single, error;
+};
 
 struct Huff2Shared {
   uint32_t mlut[1 << kLutBits];  // up to 3 symbols per lookup: s1 | s2 << 8 | s3 << 16 | bits << 24 | n << 28
@@ -38,16 +43,18 @@ struct Huff2Shared {
   uint32_t startv[kH2MaxSub];
   uint16_t cnt[kH2MaxSub];
   uint8_t flag[kH2MaxSub];
-  uint16_t pstack[260];          // tree parse (one thread)
-  uint8_t pslot[512];
   uint32_t scan[33];
-  uint32_t treeBits;
-  int nLeaf, single, error;
+  H2TreeMeta tree;
 };
+
+// Per-tile record of the tree kernel (huffman2_tree_kernel): kid[512][2] (2048 B), leafSym[512] (1024 B), H2TreeMeta (16 B)
+constexpr int kH2TreeBytes = 2048 + 1024 + 16;
 
 struct Huff2Geom {
   uint32_t stageBytes;  // staging area of the packing (also holds the band of the Triangle pass)
   uint32_t m32Cap;      // byte buffer of the M32 codes
+  uint32_t subBits;     // target sub-sequence size
+  uint32_t lookback;    // the first pass starts this many bits before a sub-sequence limit
 };
 
 __device__ __forceinline__ uint32_t h2_smem_u32(const void* p) { return uint32_t(__cvta_generic_to_shared(p)); }
@@ -77,49 +84,89 @@ struct H2Cursor {  // register bit window over the staged words, position kept r
 };
 
 // HuffmanDecoder.decodeTree (:65-161) over the staged words, bounds-checked.  One thread.
-__device__ inline void h2_parse_tree(Huff2Shared& S, const uint32_t* sw, uint32_t startBit, uint32_t nBits) {
+// Nodes are numbered in pre-order, so the LEFT child of branch n is n + 1 and only the right links are stored
+// (kid[n][1]; kid[n][0] = n + 1 is written as well for the walkers).  The path from the root is kept in two register
+// bit masks (expR: the node at that depth has its left subtree done; amR: the node at that depth is a right child), so
+// the dependent chain of a token is a few shifts: the only shared-memory read (the parent's id, for the right link) feeds
+// a store, not the control flow.  Depth is limited to 62; deeper trees set S.error = 2 (the caller defers the tile).
+// Output: kid / leafSym (512 nodes each), pstack = 64 entries of scratch, meta = {treeBits (position after the tree, same
+// origin as startBit), nLeaf, single symbol or -1, error}.  word(i) returns 32-bit word i of the bit stream.
+template <class WordFn>
+__device__ __forceinline__ void h2_parse_tree(uint16_t (*kid)[2], int16_t* leafSym, uint16_t* pstack, H2TreeMeta& M, WordFn word, uint32_t startBit,
+                                              uint32_t nBits) {
   auto bits = [&](uint32_t pos, int n) {
     const uint32_t i = pos >> 5;
-    return __funnelshift_r(sw[i], sw[i + 1], pos & 31u) & ((1u << n) - 1u);
+    return __funnelshift_r(word(i), word(i + 1), pos & 31u) & ((1u << n) - 1u);
   };
-  S.error = 0;
-  S.single = -1;
-  if (startBit + 17 > nBits) { S.error = 1; return; }
+  M.error = 0;
+  M.single = -1;
+  if (startBit + 17 > nBits) { M.error = 1; return; }
   const int L = int(bits(startBit, 8)) + 1;
-  S.nLeaf = L;
+  M.nLeaf = L;
   uint32_t pos = startBit + 8;
   if (bits(pos, 1)) {
-    S.single = int(bits(pos + 1, 8));
-    S.treeBits = startBit + 17;
+    M.single = int(bits(pos + 1, 8));
+    M.treeBits = startBit + 17;
     return;
   }
   pos = startBit + 9;
-  int nodes = 1, sp = 1, leaves = 0;
-  S.pstack[0] = 0;
-  S.pslot[0] = 0;
-  S.leafSym[0] = -1;
+  // register bit buffer with the next word fetched one refill ahead
+  uint32_t wi = pos >> 5;
+  uint64_t buf = ((uint64_t(word(wi + 1)) << 32) | word(wi)) >> (pos & 31u);
+  int avail = 64 - int(pos & 31u);
+  wi += 2;
+  uint32_t nextWord = word(wi);
+  uint64_t expR = 0, amR = 0;
+  int depth = 0, nodes = 1, leaves = 0;
+  bool done = false;
+  leafSym[0] = -1;
+  kid[0][0] = 1;
+  pstack[0] = 0;  // node id at every depth of the current path
   while (leaves < L) {
-    if (sp == 0 || nodes >= 511 || pos + 9 > nBits + 8) { S.error = 1; return; }
-    const int parent = S.pstack[sp - 1];
-    const uint32_t x = bits(pos, 9);
+    if (done || nodes >= 511 || pos + 9 > nBits + 8) { M.error = 1; return; }
+    const uint32_t x = uint32_t(buf) & 0x1ffu;
     const int id = nodes++;
-    S.kid[parent][S.pslot[parent]++] = uint16_t(id);
+    const bool isRight = (expR >> depth) & 1ull;
+    if (isRight) kid[pstack[depth]][1] = uint16_t(id);
+    int used;
     if (x & 1u) {
-      S.leafSym[id] = int16_t((x >> 1) & 0xffu);
-      S.pslot[id] = 2;
-      pos += 9;
+      leafSym[id] = int16_t((x >> 1) & 0xffu);
+      used = 9;
       leaves++;
-      while (sp > 0 && S.pslot[S.pstack[sp - 1]] == 2) sp--;
+      if (!isRight) expR |= 1ull << depth;  // the parent now expects its right child
+      else {
+        // the parent is complete, and so is every ancestor that is itself a right child: climb to the first node that is a
+        // left child (amR bit clear); its parent now expects the right child
+        const uint64_t cand = ~amR & ((2ull << depth) - 1ull);  // bit 0 (the root) is always a candidate
+        const int d = 63 - __clzll((long long)cand);
+        if (d == 0) done = true;  // the root is complete
+        else {
+          depth = d - 1;
+          expR |= 1ull << depth;
+        }
+      }
     } else {
-      if (sp >= 258) { S.error = 1; return; }
-      S.leafSym[id] = -1;
-      S.pslot[id] = 0;
-      S.pstack[sp++] = uint16_t(id);
-      pos += 1;
+      if (depth >= 61) { M.error = 2; return; }
+      leafSym[id] = -1;
+      kid[id][0] = uint16_t(id + 1);
+      used = 1;
+      depth++;
+      pstack[depth] = uint16_t(id);
+      const uint64_t bit = 1ull << depth;
+      expR &= ~bit;
+      amR = isRight ? (amR | bit) : (amR & ~bit);
+    }
+    buf >>= used;
+    avail -= used;
+    pos += uint32_t(used);
+    if (avail < 32) {
+      buf |= uint64_t(nextWord) << avail;
+      avail += 32;
+      nextWord = word(++wi);
     }
   }
-  if (sp != 0 || pos > nBits) { S.error = 1; return; }
-  S.treeBits = pos;
+  if (!done || pos > nBits) { M.error = 1; return; }
+  M.treeBits = pos;
 }
 
 template <int NT>
@@ -268,12 +315,12 @@ struct H2ByteSink {
 // Returns 0 = done, 1 = malformed stream, 2 = a sub-sequence outgrew slot + spill (the caller defers the tile).
 template <int NT>
 __device__ int h2_decode_text(Huff2Shared& S, const uint32_t* sw, uint32_t nBits, const uint32_t T0, uint32_t nSym, uint8_t* out,
-                              uint32_t outCap, uint32_t* spillArea) {
+                              uint32_t outCap, uint32_t* spillArea, uint32_t subBits, uint32_t lookbackBits) {
   constexpr int kRounds = kH2MaxSub / NT;
   const int tid = threadIdx.x;
   if (T0 > nBits) return 1;
   const uint32_t avail = nBits - T0;
-  uint32_t rounds = (avail / kH2SubBits + NT - 1) / NT;
+  uint32_t rounds = (avail / subBits + NT - 1) / NT;
   if (rounds < 1u) rounds = 1u;
   if (rounds > uint32_t(kRounds)) rounds = kRounds;
   uint32_t B = (avail + rounds * NT - 1) / (rounds * NT);
@@ -291,7 +338,8 @@ __device__ int h2_decode_text(Huff2Shared& S, const uint32_t* sw, uint32_t nBits
     uint32_t limit = T0 + uint32_t(i + 1) * B;
     if (limit > nBits) limit = nBits;
     uint32_t from = T0 + uint32_t(i) * B;
-    if (limit - from > kH2Lookback) from = limit - kH2Lookback;
+    const uint32_t lookback = B >= 256u ? lookbackBits : (lookbackBits * 2u) / 3u;
+    if (limit - from > lookback) from = limit - lookback;
     uint32_t e, c;
     int f;
     h2_sub<false>(S, sw, nBits, from, limit, nullptr, 0, nullptr, &e, &c, &f);
@@ -400,20 +448,39 @@ __device__ int h2_decode_text(Huff2Shared& S, const uint32_t* sw, uint32_t nBits
 // Triangle predictor, every residual a one-byte M32 code: raster = 2-D inclusive prefix sum of the residual field.
 // m32 = the nM32 = R*C - 1 code bytes in stream order (row 0 from column 1, column 0 from row 1, interior
 // row-major), readable from m32 - 4; band = kH2BandRows * C int32 of shared memory.  All NT threads call.
+// Per band of 32 rows: (1) warps turn rows of bytes into row prefix sums (int32, band); (2) the column sums run over
+// (4-column quad, 4-row group) tasks in two passes -- group totals, then every task starts from the running column sum
+// plus the totals of the groups above it and writes its four rows as 16-byte pieces, whole rows coalesced.  The group
+// totals and the running column sums live in the sub-sequence arrays of S, which the decode no longer needs.
 template <int NT>
-__device__ inline void h2_triangle_bytes(const uint8_t* m32, int32_t seed, const TileView& t, int32_t* band) {
+__device__ inline void h2_triangle_bytes(Huff2Shared& S, const uint8_t* m32, int32_t seed, const TileView& t, int32_t* band) {
   const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
   constexpr int kW = NT / 32;
+  constexpr int kGroups = kH2BandRows / 4;
   const int R = t.R, C = t.C;
-  uint32_t run0 = 0, run1 = 0;  // running column sums of columns tid and tid + NT
+  const int Q = C >> 2;
+  // quads: C a multiple of 4, 16-byte aligned raster rows, group totals (kGroups * Q int4) and two carries (2 * Q int4) fit S
+  const bool quads = (C & 3) == 0 && (t.pitch & 3) == 0 && (reinterpret_cast<uintptr_t>(t.base) & 15) == 0 &&
+                     size_t(kGroups) * Q * 16 <= sizeof(S.endpos) + sizeof(S.startv) && size_t(2) * Q * 16 <= sizeof(S.cnt) + sizeof(S.flag);
+  int4* gsum = reinterpret_cast<int4*>(S.endpos);   // endpos and startv are adjacent
+  int4* carry = reinterpret_cast<int4*>(S.cnt);     // cnt and flag are adjacent; two buffers of Q
+  if (quads)
+    for (int q = tid; q < 2 * Q; q += NT) carry[q] = make_int4(0, 0, 0, 0);
+  uint32_t run0 = 0, run1 = 0;  // (general form) running column sums of columns tid and tid + NT
   auto value = [](uint32_t b) { return b == 0x80u ? uint32_t(INT32_MIN) : uint32_t(int32_t(int8_t(b))); };  // CodecM32.java:313-324
+  int cb = 0;  // carry buffer in use
   for (int r0 = 0; r0 < R; r0 += kH2BandRows) {
     const int nr = R - r0 < kH2BandRows ? R - r0 : kH2BandRows;
-    for (int i = warp; i < nr; i += kW) {  // row scans: band[i][c] = F[r][0] + ... + F[r][c]
+    for (int i = warp; i < kH2BandRows; i += kW) {  // row scans: band[i][c] = F[r][0] + ... + F[r][c]; zeros below the tile
       const int r = r0 + i;
+      if (i >= nr) {
+        if (quads)
+          for (int q = lane; q < Q; q += 32) reinterpret_cast<int4*>(band + size_t(i) * C)[q] = make_int4(0, 0, 0, 0);
+        continue;
+      }
       const int baseR = r == 0 ? 0 : (C + R - 2) + (r - 1) * (C - 1);  // stream index of F[r][1]
       const uint32_t f0 = r == 0 ? uint32_t(seed) : value(m32[C - 1 + (r - 1)]);
-      uint32_t carry = 0;
+      uint32_t rowCarry = 0;
       for (int c0 = 0; c0 < C; c0 += 256) {
         const int c = c0 + 8 * lane;
         const int o = baseR + c - 1;  // stream index of element (r, c); -1 for c == 0
@@ -443,15 +510,17 @@ __device__ inline void h2_triangle_bytes(const uint8_t* m32, int32_t seed, const
           }
         }
         if (c == 0) e[0] = f0;
+        if (c + 8 > C) {
 #pragma unroll
-        for (int j = 0; j < 8; j++)
-          if (c + j >= C) e[j] = 0u;
+          for (int j = 0; j < 8; j++)
+            if (c + j >= C) e[j] = 0u;
+        }
         uint32_t loc = 0;
 #pragma unroll
         for (int j = 0; j < 8; j++) { loc += e[j]; e[j] = loc; }
         const uint32_t inc = warp_inclusive_scan(loc);
-        const uint32_t base = carry + inc - loc;
-        carry += __shfl_sync(0xffffffffu, inc, 31);
+        const uint32_t base = rowCarry + inc - loc;
+        rowCarry += __shfl_sync(0xffffffffu, inc, 31);
         int32_t* dst = band + size_t(i) * C + c;
         if (c + 8 <= C && (C & 3) == 0) {
           *reinterpret_cast<int4*>(dst) = make_int4(int32_t(e[0] + base), int32_t(e[1] + base), int32_t(e[2] + base), int32_t(e[3] + base));
@@ -464,21 +533,54 @@ __device__ inline void h2_triangle_bytes(const uint8_t* m32, int32_t seed, const
       }
     }
     __syncthreads();
-    // column sums: thread c adds the band's rows to its running sum and writes the raster, one row per step
-    if (tid < C) {
-      const int32_t* b = band + tid;
-      int32_t* o = t.row(r0) + tid;
-      for (int i = 0; i < nr; i++) {
-        run0 += uint32_t(b[size_t(i) * C]);
-        o[int64_t(i) * t.pitch] = int32_t(run0);
+    if (quads) {
+      auto add4 = [](int4 a, int4 b) {
+        return make_int4(int32_t(uint32_t(a.x) + uint32_t(b.x)), int32_t(uint32_t(a.y) + uint32_t(b.y)), int32_t(uint32_t(a.z) + uint32_t(b.z)),
+                         int32_t(uint32_t(a.w) + uint32_t(b.w)));
+      };
+      const int nTasks = kGroups * Q;
+      for (int task = tid; task < nTasks; task += NT) {  // pass 1: totals of every (group, quad)
+        const int g = task / Q, q = task - g * Q;
+        const int4* b = reinterpret_cast<const int4*>(band + size_t(4 * g) * C) + q;
+        int4 s4 = b[0];
+        s4 = add4(s4, b[Q]);
+        s4 = add4(s4, b[2 * Q]);
+        s4 = add4(s4, b[3 * Q]);
+        gsum[task] = s4;
       }
-    }
-    if (tid + NT < C) {
-      const int32_t* b = band + tid + NT;
-      int32_t* o = t.row(r0) + tid + NT;
-      for (int i = 0; i < nr; i++) {
-        run1 += uint32_t(b[size_t(i) * C]);
-        o[int64_t(i) * t.pitch] = int32_t(run1);
+      __syncthreads();
+      for (int task = tid; task < nTasks; task += NT) {  // pass 2: running sums and the raster rows
+        const int g = task / Q, q = task - g * Q;
+        int4 run = carry[cb * Q + q];
+        for (int gg = 0; gg < g; gg++) run = add4(run, gsum[gg * Q + q]);
+        const int4* b = reinterpret_cast<const int4*>(band + size_t(4 * g) * C) + q;
+        int4* o = reinterpret_cast<int4*>(t.row(r0 + 4 * g)) + q;
+        const int64_t pitch4 = t.pitch >> 2;
+#pragma unroll
+        for (int i = 0; i < 4; i++) {
+          run = add4(run, b[i * Q]);
+          if (4 * g + i < nr) o[i * pitch4] = run;
+        }
+        if (g == kGroups - 1) carry[(cb ^ 1) * Q + q] = run;  // the column sums through this band (rows below the tile add zero)
+      }
+      cb ^= 1;
+    } else {
+      // general form: thread c adds the band's rows to its running sum and writes the raster, one row per step
+      if (tid < C) {
+        const int32_t* b = band + tid;
+        int32_t* o = t.row(r0) + tid;
+        for (int i = 0; i < nr; i++) {
+          run0 += uint32_t(b[size_t(i) * C]);
+          o[int64_t(i) * t.pitch] = int32_t(run0);
+        }
+      }
+      if (tid + NT < C) {
+        const int32_t* b = band + tid + NT;
+        int32_t* o = t.row(r0) + tid + NT;
+        for (int i = 0; i < nr; i++) {
+          run1 += uint32_t(b[size_t(i) * C]);
+          o[int64_t(i) * t.pitch] = int32_t(run1);
+        }
       }
     }
     __syncthreads();

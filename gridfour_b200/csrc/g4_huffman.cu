@@ -419,11 +419,46 @@ __global__ void __launch_bounds__(kThreads, 4) huffman_decode_kernel(DecodeArgs 
 }
 
 // =================================================================================================
+// Tree kernel of the fused fast path: ONE THREAD per tile parses the legacy Huffman tree (a serial job of a few hundred
+// dependent steps) straight from the packing in global memory and leaves kid / leafSym / H2TreeMeta in a per-tile record,
+// so that the decode CTAs load 3 KB instead of waiting for one of their threads.  Ten thousand parses run side by side.
+__global__ void __launch_bounds__(64) huffman2_tree_kernel(DecodeArgs a, uint8_t* trees) {
+  const int li = blockIdx.x * blockDim.x + threadIdx.x;
+  if (li >= *a.listCount) return;
+  const int tIdx = a.list[li];
+  const uint8_t* packing = a.arena + a.offsets[tIdx];
+  const uint32_t len = a.lens[tIdx];
+  uint8_t* rec = trees + size_t(tIdx) * kH2TreeBytes;
+  H2TreeMeta M;
+  M.treeBits = 0;
+  M.nLeaf = 0;
+  M.single = -1;
+  M.error = 1;
+  if (len >= 12) {
+    // words of the packing from its 4-byte line start; the last, partial word is assembled from bytes
+    const uint32_t delta = uint32_t(reinterpret_cast<uintptr_t>(packing) & 3u);
+    const uint32_t* gw = reinterpret_cast<const uint32_t*>(packing - delta);
+    const uint32_t span = len + delta;
+    auto word = [&](uint32_t i) -> uint32_t {
+      if (4u * i + 4u <= span) return __ldg(gw + i);
+      uint32_t v = 0;
+      for (uint32_t b = 0; b < 4u; b++)
+        if (4u * i + b < span) v |= uint32_t(packing[4u * i + b - delta]) << (8u * b);
+      return v;
+    };
+    uint16_t pstack[64];
+    h2_parse_tree(reinterpret_cast<uint16_t(*)[2]>(rec), reinterpret_cast<int16_t*>(rec + 2048), pstack, M, word, (delta + 10u) * 8u, span * 8u);
+    M.treeBits -= 8u * delta;  // bit position inside the packing
+  }
+  *reinterpret_cast<H2TreeMeta*>(rec + 3072) = M;
+}
+
+// =================================================================================================
 // Fused fast path (g4_huff2.cuh): Triangle predictor + one-byte M32 codes finished in shared memory; everything else is
 // appended to defer[] for huffman_decode_kernel.  spill: kH2MaxSub * kH2SpillWords words per CTA.
 template <int NT>
 __global__ void __launch_bounds__(NT, NT == 512 ? 2 : 4)
-    huffman2_decode_kernel(DecodeArgs a, Huff2Geom g, uint32_t* spill, int* defer, int* deferCount) {
+    huffman2_decode_kernel(DecodeArgs a, Huff2Geom g, uint32_t* spill, const uint8_t* trees, int* defer, int* deferCount) {
   extern __shared__ __align__(128) unsigned char h2Smem[];
   Huff2Shared& S = *reinterpret_cast<Huff2Shared*>(h2Smem);
   uint32_t* sw = reinterpret_cast<uint32_t*>(h2Smem + ((sizeof(Huff2Shared) + 127) & ~size_t(127)));
@@ -478,6 +513,12 @@ __global__ void __launch_bounds__(NT, NT == 512 ? 2 : 4)
         const uint32_t i = nBulk + uint32_t(tid);
         reinterpret_cast<uint8_t*>(sw)[i] = i < span ? src16[i] : uint8_t(0);
       }
+      {  // the tree as huffman2_tree_kernel left it: kid, leafSym (adjacent in S) and the meta words
+        const uint32_t* rec = reinterpret_cast<const uint32_t*>(trees + size_t(tIdx) * kH2TreeBytes);
+        uint32_t* dstw = reinterpret_cast<uint32_t*>(&S.kid[0][0]);
+        for (int i = tid; i < 768; i += NT) dstw[i] = __ldg(rec + i);
+        if (tid < 4) reinterpret_cast<uint32_t*>(&S.tree)[tid] = __ldg(rec + 768 + tid);
+      }
       if (nBulk) {
         uint32_t done = 0;
         while (!done)
@@ -489,15 +530,14 @@ __global__ void __launch_bounds__(NT, NT == 512 ? 2 : 4)
       }
       __syncthreads();
       const uint32_t nBits = span * 8u;
-      if (tid == 0) h2_parse_tree(S, sw, (delta + 10u) * 8u, nBits);
-      __syncthreads();
-      if (S.error) rc = 1;
-      else if (S.single >= 0) fast = false;  // one-symbol tree: no text in the stream
+      if (S.tree.error == 2) fast = false;  // a tree deeper than the parser's path masks
+      else if (S.tree.error) rc = 1;
+      else if (S.tree.single >= 0) fast = false;  // one-symbol tree: no text in the stream
       else {
         h2_build_lut<NT>(S);
-        rc = h2_decode_text<NT>(S, sw, nBits, S.treeBits, nM32, m32, g.m32Cap - 16u, spillArea);
+        rc = h2_decode_text<NT>(S, sw, nBits, S.tree.treeBits + 8u * delta, nM32, m32, g.m32Cap - 16u, spillArea, g.subBits, g.lookback);
         if (rc == 2) { fast = false; rc = 0; }
-        else if (rc == 0) h2_triangle_bytes<NT>(m32, seed, t, reinterpret_cast<int32_t*>(sw));  // (ends with a barrier)
+        else if (rc == 0) h2_triangle_bytes<NT>(S, m32, seed, t, reinterpret_cast<int32_t*>(sw));  // (ends with a barrier)
       }
     }
     if (tid == 0) {
@@ -519,8 +559,8 @@ cudaError_t launch_huffman_encode(const EncodeArgs& a, int nCtas, cudaStream_t s
 }
 
 template <int NT>
-static cudaError_t launch_huffman2(const DecodeArgs& a, const Huff2Geom& g, size_t smem, int smCount, int nTilesUpper, uint32_t* spill, int* defer,
-                                   int* deferCount, cudaStream_t s) {
+static cudaError_t launch_huffman2(const DecodeArgs& a, const Huff2Geom& g, size_t smem, int smCount, int nTilesUpper, uint32_t* spill,
+                                   const uint8_t* trees, int* defer, int* deferCount, cudaStream_t s) {
   cudaError_t e = cudaFuncSetAttribute(huffman2_decode_kernel<NT>, cudaFuncAttributeMaxDynamicSharedMemorySize, int(smem));
   if (e != cudaSuccess) return e;
   int perSm = int((227u * 1024u) / (smem + 1024));
@@ -529,11 +569,12 @@ static cudaError_t launch_huffman2(const DecodeArgs& a, const Huff2Geom& g, size
   if (perSm < 1) perSm = 1;
   int ctas = smCount * perSm;
   if (ctas > nTilesUpper) ctas = nTilesUpper;
-  huffman2_decode_kernel<NT><<<ctas, NT, smem, s>>>(a, g, spill, defer, deferCount);
+  huffman2_decode_kernel<NT><<<ctas, NT, smem, s>>>(a, g, spill, trees, defer, deferCount);
   return cudaGetLastError();
 }
 
 size_t huffman2_spill_bytes(int smCount) { return size_t(smCount) * 4 * kH2MaxSub * kH2SpillWords * sizeof(uint32_t); }
+size_t huffman2_tree_bytes(int nTiles) { return size_t(nTiles) * kH2TreeBytes; }
 
 // fused: scratch of the fast path (spill of huffman2_spill_bytes, defer list of nTilesUpper ints, two zeroed counters), or null
 cudaError_t launch_huffman_decode(const DecodeArgs& a, int nCtas, cudaStream_t s, const HuffFusedScratch* fused, int* launches) {
@@ -563,13 +604,19 @@ cudaError_t launch_huffman_decode(const DecodeArgs& a, int nCtas, cudaStream_t s
     if (stage < bandBytes) stage = (bandBytes + 15u) & ~15u;
     g.stageBytes = stage;
     g.m32Cap = (n + 48u + 15u) & ~15u;
+    static const int subEnv = getenv("G4_H2_SUBBITS") ? atoi(getenv("G4_H2_SUBBITS")) : 0, lbEnv = getenv("G4_H2_LOOKBACK") ? atoi(getenv("G4_H2_LOOKBACK")) : 0;
+    g.subBits = subEnv > 0 ? uint32_t(subEnv) : kH2SubBits;
+    g.lookback = lbEnv > 0 ? uint32_t(lbEnv) : kH2Lookback;
     const size_t smem2 = ((sizeof(Huff2Shared) + 127) & ~size_t(127)) + g.stageBytes + 16 + g.m32Cap;
     if (smem2 <= 112u * 1024u) {  // two 512-thread CTAs (or four 256-thread CTAs) per SM
       const int nTilesUpper = a.band.tiles_down * a.band.tiles_across;
-      cudaError_t e = n <= 16384u ? launch_huffman2<256>(a, g, smem2, fused->smCount, nTilesUpper, fused->spill, fused->defer, fused->counters, s)
-                                  : launch_huffman2<512>(a, g, smem2, fused->smCount, nTilesUpper, fused->spill, fused->defer, fused->counters, s);
+      huffman2_tree_kernel<<<(nTilesUpper + 63) / 64, 64, 0, s>>>(a, fused->trees);
+      cudaError_t e = cudaGetLastError();
       if (e != cudaSuccess) return e;
-      if (launches) (*launches)++;
+      e = n <= 16384u ? launch_huffman2<256>(a, g, smem2, fused->smCount, nTilesUpper, fused->spill, fused->trees, fused->defer, fused->counters, s)
+                      : launch_huffman2<512>(a, g, smem2, fused->smCount, nTilesUpper, fused->spill, fused->trees, fused->defer, fused->counters, s);
+      if (e != cudaSuccess) return e;
+      if (launches) (*launches) += 2;
       rest.list = fused->defer;
       rest.listCount = fused->counters;
       rest.counter = fused->counters + 1;

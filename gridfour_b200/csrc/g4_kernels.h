@@ -151,11 +151,13 @@ cudaError_t launch_huffman_encode(const EncodeArgs& a, int nCtas, cudaStream_t s
 // fused fast path of the legacy Huffman decoder (g4_huff2.cuh): per-context scratch
 struct HuffFusedScratch {
   uint32_t* spill;   // huffman2_spill_bytes(smCount)
+  uint8_t* trees;    // huffman2_tree_bytes(nTiles): per-tile tree records of huffman2_tree_kernel
   int* defer;        // nTiles ints: tiles left to huffman_decode_kernel
   int* counters;     // [0] defer count, [1] tile counter of the second kernel; both zero before the launch
   int smCount;
 };
 size_t huffman2_spill_bytes(int smCount);
+size_t huffman2_tree_bytes(int nTiles);
 cudaError_t launch_huffman_decode(const DecodeArgs& a, int nCtas, cudaStream_t s, const HuffFusedScratch* fused = nullptr, int* launches = nullptr);
 cudaError_t launch_canon_decode(const DecodeArgs& a, int nCtas, cudaStream_t s);
 cudaError_t launch_canon_encode(const EncodeArgs& a, int nCtas, cudaStream_t s);  // needs 32 KB scratch per CTA
