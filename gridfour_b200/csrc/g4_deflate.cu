@@ -13,13 +13,20 @@
 
 namespace g4 {
 
+#ifndef G4_INF_GROUP
+#define G4_INF_GROUP 16
+#endif
+constexpr int kInfGroup = G4_INF_GROUP;                      // lanes per zlib stream in the stand-alone inflate kernels (measured on config 4: 8 -> 27.5 ms, 16 -> 23.1 ms, 32 -> 25.5 ms)
+constexpr int kInfPerWarp = 32 / kInfGroup;       // streams a warp inflates side by side
+
 // ---- CodecDeflate --------------------------------------------------------------------------------------
 // One warp per CTA: streams differ a lot in length, and a CTA of eight warps keeps its slot until the longest is through
-// (measured on CodecFloat: 24 % warps active with eight-warp CTAs).
+// (measured on CodecFloat: 24 % warps active with eight-warp CTAs).  A warp inflates 32 / kInfGroup streams side by side.
 __global__ void __launch_bounds__(32) deflate_inflate_kernel(DecodeArgs a, uint8_t* region, size_t regionStride) {
-  __shared__ InflateWarpShared S[1];
-  const int warp = 0, lane = threadIdx.x & 31;
-  const int li = blockIdx.x;
+  constexpr int kG = kInfGroup, kPerWarp = 32 / kG;  // streams per warp (g4_inflate.cuh)
+  __shared__ InflateWarpShared S[kPerWarp];
+  const int lane = threadIdx.x & 31, grp = lane / kG, sub = lane % kG;
+  const int li = blockIdx.x * kPerWarp + grp;
   if (li >= *a.listCount) return;
   const int tIdx = a.list[li];
   const int n = a.band.tile_rows * a.band.tile_cols;
@@ -32,10 +39,10 @@ __global__ void __launch_bounds__(32) deflate_inflate_kernel(DecodeArgs a, uint8
   if (len < 12 || pred < 1 || pred > 4 || nM32 < expect || nM32 > uint32_t(6 * n)) status = G4_ERR_FORMAT;
   else {
     uint32_t produced = 0, consumed = 0;
-    int rc = inflate_warp(S[warp], packing + 10, len - 10, region + size_t(li) * regionStride, nM32, &produced, &consumed);
+    int rc = inflate_group<kG>(S[grp], packing + 10, len - 10, region + size_t(li) * regionStride, nM32, &produced, &consumed);
     if (rc != kInfOk || produced != nM32) status = G4_ERR_FORMAT;  // DataFormatException -> IOException (:150-152)
   }
-  if (lane == 0) a.status[tIdx] = status;
+  if (sub == 0) a.status[tIdx] = status;
 }
 
 __global__ void __launch_bounds__(kThreads) deflate_finish_kernel(DecodeArgs a, const uint8_t* region, size_t regionStride) {
@@ -74,11 +81,16 @@ __global__ void __launch_bounds__(kThreads) deflate_finish_kernel(DecodeArgs a, 
 // ---- CodecFloat ----------------------------------------------------------------------------------------
 // packing = [codecIndex][0] + 5 x ([len:int32 LE][zlib stream]): sign bitmap, exponent bytes, three
 // row-delta coded mantissa byte planes (CodecFloat.java:377-387).  Staging per tile: 5 planes of n bytes.
-__global__ void __launch_bounds__(32) float_inflate_kernel(DecodeArgs a, uint8_t* region, size_t regionStride) {
-  __shared__ InflateWarpShared S[1];
-  const int warp = 0, lane = threadIdx.x & 31;
-  const int job = blockIdx.x;
-  const int li = job / 5, plane = job - li * 5;
+// Jobs are plane-major: the four streams of a warp are the SAME plane of four consecutive tiles, so that they have the same
+// character (the exponent plane is all matches, the low mantissa plane all literals) and the four walking lanes stay in
+// step; mixing the planes of one tile in a warp serialises them (each waits at the others' events) and was slower than one
+// stream per warp.
+__global__ void __launch_bounds__(32) float_inflate_kernel(DecodeArgs a, uint8_t* region, size_t regionStride, int nTilesUpper) {
+  __shared__ InflateWarpShared S[kInfPerWarp];
+  const int lane = threadIdx.x & 31, grp = lane / kInfGroup, sub = lane % kInfGroup;
+  const int perPlane = (nTilesUpper + kInfPerWarp - 1) / kInfPerWarp;  // warps per plane
+  const int plane = blockIdx.x / perPlane;
+  const int li = (blockIdx.x - plane * perPlane) * kInfPerWarp + grp;
   if (li >= *a.listCount) return;
   const int tIdx = a.list[li];
   const uint32_t n = uint32_t(a.band.tile_rows) * uint32_t(a.band.tile_cols);
@@ -100,11 +112,11 @@ __global__ void __launch_bounds__(32) float_inflate_kernel(DecodeArgs a, uint8_t
   else {
     const uint32_t want = plane == 0 ? (n + 7) / 8 : n;
     uint32_t produced = 0, consumed = 0;
-    int rc = inflate_warp(S[warp], packing + off, secLen, region + size_t(li) * regionStride + size_t(plane) * planeStride, want,
-                          &produced, &consumed);
+    int rc = inflate_group<kInfGroup>(S[grp], packing + off, secLen, region + size_t(li) * regionStride + size_t(plane) * planeStride, want,
+                                      &produced, &consumed);
     if (rc != kInfOk || produced != want) status = G4_ERR_FORMAT;  // "Inflate failed" (CodecFloat.java:285-298)
   }
-  if (lane == 0 && status != G4_OK) atomicMin(&a.status[tIdx], status);
+  if (sub == 0 && status != G4_OK) atomicMin(&a.status[tIdx], status);
 }
 
 __global__ void __launch_bounds__(kThreads) float_finish_kernel(DecodeArgs a, const uint8_t* region, size_t regionStride) {
@@ -179,7 +191,7 @@ __global__ void __launch_bounds__(kThreads) float_finish_kernel(DecodeArgs a, co
 
 cudaError_t launch_deflate_decode(const DecodeArgs& a, uint8_t* region, size_t regionStride, int nCtas, int nTilesUpper,
                                   cudaStream_t s) {
-  deflate_inflate_kernel<<<nTilesUpper, 32, 0, s>>>(a, region, regionStride);
+  deflate_inflate_kernel<<<(nTilesUpper + kInfPerWarp - 1) / kInfPerWarp, 32, 0, s>>>(a, region, regionStride);
   cudaError_t e = cudaGetLastError();
   if (e != cudaSuccess) return e;
   deflate_finish_kernel<<<nCtas, kThreads, 0, s>>>(a, region, regionStride);
@@ -188,7 +200,7 @@ cudaError_t launch_deflate_decode(const DecodeArgs& a, uint8_t* region, size_t r
 
 cudaError_t launch_float_decode(const DecodeArgs& a, uint8_t* region, size_t regionStride, int nCtas, int nTilesUpper,
                                 cudaStream_t s) {
-  float_inflate_kernel<<<nTilesUpper * 5, 32, 0, s>>>(a, region, regionStride);
+  float_inflate_kernel<<<5 * ((nTilesUpper + kInfPerWarp - 1) / kInfPerWarp), 32, 0, s>>>(a, region, regionStride, nTilesUpper);
   cudaError_t e = cudaGetLastError();
   if (e != cudaSuccess) return e;
   float_finish_kernel<<<nCtas, kThreads, 0, s>>>(a, region, regionStride);

@@ -267,9 +267,11 @@ struct BitSrc {
 };
 
 // 64-bit register bit buffer over a global-memory BitSrc (clamped word reads); >= 32 valid bits after every skip().
+// The word after the buffered ones is fetched one refill AHEAD (`ahead`), so that the load's latency is not on the
+// decoding loop's dependent chain.
 struct GlobalCursor {
   const BitSrc* src;
-  uint32_t pos, next;
+  uint32_t pos, next, ahead;
   uint64_t buf;
   int avail;
   __device__ __forceinline__ uint32_t word(uint32_t i) const { return i <= src->lastWord ? __ldg(src->words + i) : 0u; }
@@ -280,6 +282,7 @@ struct GlobalCursor {
     buf = ((uint64_t(word(i + 1)) << 32) | word(i)) >> sh;
     avail = 64 - int(sh);
     next = i + 2;
+    ahead = word(next);
   }
   __device__ __forceinline__ uint32_t peek() const { return uint32_t(buf); }
   __device__ __forceinline__ void skip(uint32_t n) {
@@ -287,8 +290,9 @@ struct GlobalCursor {
     avail -= int(n);
     pos += n;
     if (avail < 32) {
-      buf |= uint64_t(word(next++)) << avail;
+      buf |= uint64_t(ahead) << avail;
       avail += 32;
+      ahead = word(++next);
     }
   }
 };

@@ -5,8 +5,12 @@
 // compress/CodecFloat.java:285-298, lsop/LsDecoder12.java:126-145.  `new Inflater()` expects the zlib wrapper
 // and verifies the Adler-32 trailer once the final block has been consumed; so does this decoder.
 //
-// Lane 0 walks the bit stream (table-driven: 10-bit root table for literal/length codes, 8-bit for distances,
-// canonical arithmetic for longer codes); all 32 lanes build the tables and perform the LZ77 copies.
+// A GROUP of G lanes (G = 8 or 32, template parameter) owns a stream: the group's first lane walks the bit stream
+// (table-driven: 10-bit root table for literal/length codes, 8-bit for distances, canonical arithmetic for longer codes);
+// all G lanes build the tables and perform the LZ77 copies.  With G = 8 a warp inflates FOUR streams side by side: the four
+// walking lanes execute the symbol loop in the same instructions, which is where the time goes (the loop is a chain of
+// dependent one-lane instructions), at the price of narrower copies and table builds.  Groups only ever synchronise among
+// themselves (__syncwarp / __shfl_sync with the group's lane mask).
 #pragma once
 #include "g4_device.cuh"
 #include "g4_canon.cuh"  // canon_build_tables / canon_slow_symbol (DEFLATE uses the same canonical convention)
@@ -38,10 +42,11 @@ static __constant__ uint8_t kInfDistExtra[30] = {0, 0, 0, 0, 1, 1, 2, 2, 3, 3, 4
                                                  13, 13};
 static __constant__ uint8_t kInfClOrder[19] = {16, 17, 18, 0, 8, 7, 9, 6, 10, 5, 11, 4, 12, 3, 13, 2, 14, 1, 15};
 
+template <int G>
 __device__ inline void inflate_build_lut(const uint16_t* first, const uint16_t* count, const uint16_t* offset,
-                                         const uint16_t* sorted, uint16_t* lut, int lutBits) {
-  const int lane = threadIdx.x & 31;
-  for (int e = lane; e < (1 << lutBits); e += 32) {
+                                         const uint16_t* sorted, uint16_t* lut, int lutBits, uint32_t gmask) {
+  const int sub = threadIdx.x & (G - 1);
+  for (int e = sub; e < (1 << lutBits); e += G) {
     uint32_t v = __brev(uint32_t(e));
     uint16_t entry = 0;
     for (int len = 1; len <= lutBits; len++) {
@@ -51,7 +56,7 @@ __device__ inline void inflate_build_lut(const uint16_t* first, const uint16_t* 
     }
     lut[e] = entry;
   }
-  __syncwarp();
+  __syncwarp(gmask);
 }
 
 __device__ __forceinline__ int inflate_symbol(const uint16_t* lut, int lutBits, const uint16_t* first, const uint16_t* count,
@@ -62,12 +67,13 @@ __device__ __forceinline__ int inflate_symbol(const uint16_t* lut, int lutBits, 
   return canon_slow_symbol(first, count, offset, sorted, src, pos, lutBits + 1);
 }
 
-// Adler-32 of out[0..n) by one warp.
-__device__ inline uint32_t adler32_warp(const uint8_t* out, uint32_t n) {
-  const int lane = threadIdx.x & 31;
+// Adler-32 of out[0..n) by one group of G lanes.
+template <int G>
+__device__ inline uint32_t adler32_group(const uint8_t* out, uint32_t n, uint32_t gmask) {
+  const int lane = threadIdx.x & (G - 1);
   // s1 = 1 + sum b_i ; s2 = n + sum (n - i) * b_i   (mod 65521), i = 0..n-1
   unsigned long long a = 0, b = 0;
-  for (uint32_t i = lane; i < n; i += 32) {
+  for (uint32_t i = lane; i < n; i += G) {
     uint32_t x = out[i];
     a += x;
     b += (unsigned long long)(n - i) * x;  // n <= 6.3e6: no 64-bit overflow
@@ -75,21 +81,23 @@ __device__ inline uint32_t adler32_warp(const uint8_t* out, uint32_t n) {
   a %= 65521ull;
   b %= 65521ull;
 #pragma unroll
-  for (int d = 16; d >= 1; d >>= 1) {
-    a += __shfl_xor_sync(0xffffffffu, a, d);
-    b += __shfl_xor_sync(0xffffffffu, b, d);
+  for (int d = G / 2; d >= 1; d >>= 1) {
+    a += __shfl_xor_sync(gmask, a, d);
+    b += __shfl_xor_sync(gmask, b, d);
   }
   uint32_t s1 = uint32_t((1ull + a) % 65521ull);
   uint32_t s2 = uint32_t((uint64_t(n % 65521u) + b) % 65521ull);
   return (s2 << 16) | s1;
 }
 
-// Inflates one zlib stream with a full warp.  Output stops at `cap` bytes (Inflater.inflate(byte[]) with an
+// Inflates one zlib stream with a group of G lanes (every lane of the group calls with the group's arguments).  Output stops at `cap` bytes (Inflater.inflate(byte[]) with an
 // exactly sized buffer); the end-of-block code and the trailer are still consumed when they follow directly,
 // as zlib does.  *produced / *consumed as Inflater.inflate()'s return value / getBytesRead().
-__device__ inline int inflate_warp(InflateWarpShared& S, const uint8_t* in, uint32_t inLen, uint8_t* out, uint32_t cap,
-                                   uint32_t* produced, uint32_t* consumed) {
-  const int lane = threadIdx.x & 31;
+template <int G>
+__device__ inline int inflate_group(InflateWarpShared& S, const uint8_t* in, uint32_t inLen, uint8_t* out, uint32_t cap,
+                                    uint32_t* produced, uint32_t* consumed) {
+  const int lane = threadIdx.x & (G - 1);  // lane inside the group
+  const uint32_t gmask = G == 32 ? 0xffffffffu : (((1u << (G & 31)) - 1u) << ((threadIdx.x & 31) & ~(G - 1)));
   *produced = 0;
   *consumed = 0;
   if (inLen < 2) return kInfTruncated;
@@ -117,8 +125,8 @@ __device__ inline int inflate_warp(InflateWarpShared& S, const uint8_t* in, uint
       if (pos + len * 8 > src.nBits) { status = kInfTruncated; break; }
       uint32_t take = len < cap - op ? len : cap - op;
       const uint8_t* sp = in + 2 + (pos >> 3);
-      for (uint32_t i = lane; i < take; i += 32) out[op + i] = sp[i];
-      __syncwarp();
+      for (uint32_t i = lane; i < take; i += G) out[op + i] = sp[i];
+      __syncwarp(gmask);
       op += take;
       pos += take * 8;
       if (take < len) { stopped = true; break; }  // output full
@@ -128,10 +136,9 @@ __device__ inline int inflate_warp(InflateWarpShared& S, const uint8_t* in, uint
     // ---- code lengths -----------------------------------------------------------------------------------
     int nLit = 288, nDist = 30;
     if (type == 1) {
-      for (int i = lane; i < 288; i += 32) S.lens[i] = i < 144 ? 8 : i < 256 ? 9 : i < 280 ? 7 : 8;
-      if (lane < 30) S.lens[288 + lane] = 5;
-      if (lane >= 30) S.lens[288 + lane] = 0;
-      __syncwarp();
+      for (int i = lane; i < 288; i += G) S.lens[i] = i < 144 ? 8 : i < 256 ? 9 : i < 280 ? 7 : 8;
+      for (int i = lane; i < 32; i += G) S.lens[288 + i] = i < 30 ? 5 : 0;
+      __syncwarp(gmask);
     } else {
       int ok = 1;
       if (lane == 0) {
@@ -172,10 +179,10 @@ __device__ inline int inflate_warp(InflateWarpShared& S, const uint8_t* in, uint
         }
         S.ok = ok;
       }
-      __syncwarp();
-      pos = __shfl_sync(0xffffffffu, pos, 0);
+      __syncwarp(gmask);
+      pos = __shfl_sync(gmask, pos, 0, G);
       if (!S.ok) { status = kInfDataError; break; }
-      __syncwarp();  // every lane has read S.ok before lane 0 rewrites it below
+      __syncwarp(gmask);  // every lane has read S.ok before lane 0 rewrites it below
     }
     if (lane == 0) {
       int ok = canon_build_tables(S.lens, 288, S.litFirst, S.litCount, S.litOffset, S.litSorted) ? 1 : 0;
@@ -185,20 +192,22 @@ __device__ inline int inflate_warp(InflateWarpShared& S, const uint8_t* in, uint
       else for (int l = 0; l <= 16; l++) { S.distFirst[l] = 0; S.distCount[l] = 0; S.distOffset[l] = 0; }
       S.ok = ok;
     }
-    __syncwarp();
+    __syncwarp(gmask);
     if (!S.ok) { status = kInfDataError; break; }
-    inflate_build_lut(S.litFirst, S.litCount, S.litOffset, S.litSorted, S.litLut, kInfLitBits);
-    inflate_build_lut(S.distFirst, S.distCount, S.distOffset, S.distSorted, S.distLut, kInfDistBits);
+    inflate_build_lut<G>(S.litFirst, S.litCount, S.litOffset, S.litSorted, S.litLut, kInfLitBits, gmask);
+    inflate_build_lut<G>(S.distFirst, S.distCount, S.distOffset, S.distSorted, S.distLut, kInfDistBits, gmask);
     // ---- symbols ------------------------------------------------------------------------------------------
     bool full = false;
+    // 64-bit register bit buffer of the walking lane: one LUT read per symbol, a global word load every 32 consumed bits.
+    // It lives across the matches of a block (re-initialising it after every match put two dependent global loads on
+    // the critical path of every match).
+    GlobalCursor cur;
+    if (lane == 0) cur.init(src, pos);
     for (;;) {
       // lane 0 decodes literals until it meets a match, the end of block, or an error
       int ev = 0;  // 1 = match, 2 = end of block, 3 = error/truncated, 4 = output full
       uint32_t mlen = 0, mdist = 0;
       if (lane == 0) {
-        // 64-bit register bit buffer: one LUT read per symbol, a global word load every 32 consumed bits
-        GlobalCursor cur;
-        cur.init(src, pos);
         for (;;) {
           if (cur.pos >= src.nBits) { ev = 3; break; }
           const uint32_t p0 = cur.pos;
@@ -245,17 +254,21 @@ __device__ inline int inflate_warp(InflateWarpShared& S, const uint8_t* in, uint
         }
         pos = cur.pos;
       }
-      ev = __shfl_sync(0xffffffffu, ev, 0);
-      pos = __shfl_sync(0xffffffffu, pos, 0);
-      op = __shfl_sync(0xffffffffu, op, 0);
+      ev = __shfl_sync(gmask, ev, 0, G);
+      pos = __shfl_sync(gmask, pos, 0, G);
+      op = __shfl_sync(gmask, op, 0, G);
       if (ev == 1) {
-        mlen = __shfl_sync(0xffffffffu, mlen, 0);
-        mdist = __shfl_sync(0xffffffffu, mdist, 0);
+        mlen = __shfl_sync(gmask, mlen, 0, G);
+        mdist = __shfl_sync(gmask, mdist, 0, G);
         uint32_t take = mlen < cap - op ? mlen : cap - op;
-        __syncwarp();
+        __syncwarp(gmask);
         // overlapping copies repeat the last `mdist` bytes: source index wraps modulo the distance
-        for (uint32_t i = lane; i < take; i += 32) out[op + i] = out[op - mdist + (i % mdist)];
-        __syncwarp();
+        if (mdist >= take) {
+          for (uint32_t i = lane; i < take; i += G) out[op + i] = out[op - mdist + i];
+        } else {
+          for (uint32_t i = lane; i < take; i += G) out[op + i] = out[op - mdist + (i % mdist)];
+        }
+        __syncwarp(gmask);
         op += take;
         if (take < mlen) { full = true; break; }
         continue;
@@ -267,7 +280,7 @@ __device__ inline int inflate_warp(InflateWarpShared& S, const uint8_t* in, uint
     }
     if (full) { stopped = true; break; }
   }
-  __syncwarp();
+  __syncwarp(gmask);
   *produced = op;
   uint32_t usedBytes = 2 + ((pos + 7) >> 3);
   if (status == kInfOk && last && !stopped) {
@@ -277,7 +290,7 @@ __device__ inline int inflate_warp(InflateWarpShared& S, const uint8_t* in, uint
     if (2 + tp + 4 <= inLen) {
       const uint8_t* tr = in + 2 + tp;
       uint32_t want = (uint32_t(tr[0]) << 24) | (uint32_t(tr[1]) << 16) | (uint32_t(tr[2]) << 8) | uint32_t(tr[3]);
-      uint32_t got = adler32_warp(out, op);
+      uint32_t got = adler32_group<G>(out, op, gmask);
       if (want != got) status = kInfDataError;
       usedBytes += 4;
     } else {
@@ -286,6 +299,12 @@ __device__ inline int inflate_warp(InflateWarpShared& S, const uint8_t* in, uint
   }
   *consumed = usedBytes;
   return status;
+}
+
+// One warp, one stream (the callers that inflate inside a larger kernel).
+__device__ inline int inflate_warp(InflateWarpShared& S, const uint8_t* in, uint32_t inLen, uint8_t* out, uint32_t cap,
+                                   uint32_t* produced, uint32_t* consumed) {
+  return inflate_group<32>(S, in, inLen, out, cap, produced, consumed);
 }
 
 }  // namespace g4
