@@ -44,7 +44,7 @@ CONFIGS = {
             dtype="float32", codecs=["GvrsFloat"]),
 }
 SWEEP_TILES = [(60, 60), (90, 120), (120, 120), (128, 128), (180, 240), (256, 256), (512, 512)]
-SWEEP_GRID = (23040, 7680)  # rows = lcm of the tile heights, cols = lcm of the tile widths; 0.71 GB raw per GPU
+SWEEP_GRID = (23040, 15360)  # rows = lcm of the tile heights, cols = 2 x lcm of the tile widths; 1.42 GB raw per GPU (11x the L2)
 METRIC = "GVRS tile decode GB/s of raw samples (config 3 shard, 180x240 tiles)"
 
 
