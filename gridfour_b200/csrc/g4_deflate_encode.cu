@@ -666,8 +666,10 @@ cudaError_t launch_deflate_staged(const StagedArgs& a, int smCount, cudaStream_t
   deflate_sort_kernel<<<sortCtas, kSortThreads, kDefWSize * 2, s>>>(a);
   cudaError_t e = cudaGetLastError();
   if (e != cudaSuccess) return e;
+  static const int matchPerSm = getenv("G4_MATCH_CTAS_PER_SM") ? atoi(getenv("G4_MATCH_CTAS_PER_SM")) : 8;
+  const int matchCtas0 = smCount * (matchPerSm >= 1 && matchPerSm <= 8 ? matchPerSm : 8);
   const int matchCtas = nChunk < smCount * 8 ? nChunk : smCount * 8;
-  deflate_match_kernel<<<matchCtas, kThreads, 0, s>>>(a);
+  deflate_match_kernel<<<nChunk < matchCtas0 ? nChunk : matchCtas0, kThreads, 0, s>>>(a);
   e = cudaGetLastError();
   if (e != cudaSuccess) return e;
   deflate_decide_kernel<<<(nChunk + 31) / 32, 32, 0, s>>>(a);
