@@ -255,8 +255,11 @@ struct ByteTileSink {
     } else *reinterpret_cast<uint32_t*>(tile + addr) = uint32_t(q);
     q >>= 32;
     cnt -= 4;
-    addr += 4;
     kAddr += 4;
+    step();
+  }
+  __device__ __forceinline__ void step() {  // on to the next word of the interior's row-major order
+    addr += 4;
     left -= 4;
     if ((addr & Wm1) == 0u) {  // next strip: one image row further down; at the end of the row back to strip 0 of the next row
       addr += P;
@@ -270,6 +273,13 @@ struct ByteTileSink {
       addr = rowBase;
       left = w;
     }
+  }
+  // word copy of the staged form: bytes lo .. hi-1 of the destination word at addr are data (hi may exceed 4)
+  __device__ __forceinline__ void put_word(uint32_t dw, int lo, int hi) {
+    if (lo == 0 && hi >= 4) *reinterpret_cast<uint32_t*>(tile + addr) = dw;
+    else
+      for (int b = lo; b < hi && b < 4; b++) tile[addr + b] = uint8_t(dw >> (8 * b));
+    step();
   }
   __device__ __forceinline__ void push(uint32_t bytes, int n) {  // n = 1..4 symbol bytes, first value in the low byte
     q |= uint64_t(bytes) << (8 * cnt);
@@ -617,6 +627,26 @@ __device__ int lsop_text_decode(CanonFastShared& S, uint32_t nBits, const uint32
       }
       if (n == 0) continue;
       sink.begin(offv[i]);
+      if (rounds == 1u) {
+        // one sub-sequence per thread (the usual case): destination words are the source words funnel-shifted by the
+        // run's byte offset inside its first word -- no byte queue; source word d = r[d], then the spilled tail
+        const int head = sink.head;
+        const uint32_t sh = 8u * uint32_t(head);
+        const int nD = int((n + uint32_t(head) + 3u) >> 2);  // destination words touched
+        const uint32_t* sp = spillArea + size_t(i) * kSpillWords;
+        uint32_t prev = 0;
+#pragma unroll
+        for (int d = 0; d < kStageWordsPerThread + kSpillWords + 1; d++) {
+          if (d >= nD) break;
+          uint32_t cur = 0;
+          if (d < kStageWordsPerThread && uint32_t(d) < slotWords) cur = r[d];
+          else if (uint32_t(d) >= slotWords && uint32_t(d) - slotWords < uint32_t(kSpillWords) && 4u * uint32_t(d) < n) cur = sp[uint32_t(d) - slotWords];
+          sink.put_word(__funnelshift_l(prev, cur, sh), d == 0 ? head : 0, int(n) + head - 4 * d);
+          prev = cur;
+        }
+        if (flags & kSubRare) text_exceptions_sub(S, nBits, S.startv[i], limit, offv[i], sink.tile, sink.exc, sink.w, sink.logW, sink.P);
+        continue;
+      }
 #pragma unroll
       for (int j = 0; j < kStageWordsPerThread; j++) {
         const uint32_t at = (uint32_t(j) - s * perSub) * 4u;  // byte position of word j inside this sub-sequence's slot
