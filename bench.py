@@ -270,6 +270,21 @@ def bind_to_gpu_numa_node(local_rank):
         return {"numa_node": None, "bound": False, "why": type(e).__name__}
 
 
+def gpu_topology():
+    """CPU / NUMA affinity of every GPU as `nvidia-smi topo -m` reports it (rank 0 only): names the host links the e2e copies share."""
+    try:
+        out = subprocess.run(["nvidia-smi", "topo", "-m"], capture_output=True, text=True, timeout=20).stdout
+        rows = {}
+        for line in out.splitlines():
+            f = line.split()
+            if f and f[0].startswith("GPU") and f[0][3:].isdigit():
+                tail = [x for x in f[1:] if not (x == "X" or x.startswith(("NV", "PIX", "PXB", "PHB", "NODE", "SYS")))]
+                rows[f[0]] = " ".join(tail)  # what is left: CPU affinity, NUMA affinity, GPU NUMA id
+        return rows or None
+    except Exception:
+        return None
+
+
 def measure_pcie(torch, dev, barrier, world, dist, nbytes=1 << 30):
     """Plain pinned-memory copies of 1 GiB per rank, ALL ranks at once: the platform's D2H / H2D ceiling that the e2e line
     (1.87 GB of decoded raster back to the host per step) runs into.  Returns GB/s per GPU (min over ranks)."""
@@ -511,7 +526,7 @@ def main():
                "h2d_bytes_per_step": int(batch.total_bytes + h_off.nbytes + h_len.nbytes),
                "d2h_bytes_per_step": int(samples * 4 + n_tiles * 4), "steps": e2e_steps,
                "per_gpu": e2e_total / world, "pcie_copy_peak": pcie, "frac_of_d2h_peak": e2e_total / world / pcie["d2h_gbs_per_gpu"],
-               "host_binding": numa,
+               "host_binding": numa, "topology": gpu_topology() if rank == 0 else None,
                "note": "the decoded raster (4 B/sample) crossing PCIe bounds this line; pcie_copy_peak = plain pinned copies, all ranks at once"}
 
     if rank != 0:
