@@ -211,67 +211,92 @@ __device__ __forceinline__ int h2_long_symbol(const Huff2Shared& S, const uint32
 
 // Decodes one sub-sequence: from `start` to the first symbol boundary at or after `limit` (<= nBits).  With STORE the
 // symbol bytes go to slot[0 .. slotWords) (shared memory) and on to spill[0 .. kH2SpillWords) (global).
+// Byte accumulator of the staging pass: the pending (< 4) bytes sit TOP-justified in `acc`, so that they and the (up to
+// three) symbol bytes of a lookup are contiguous in the pair (acc, m): the next output word is one funnel shift left, the
+// new accumulator one funnel shift right.  qc8 = 8 x pending bytes.
+struct H2ByteAcc {
+  uint32_t acc, qc8, w;
+  __device__ __forceinline__ void init() { acc = 0; qc8 = 0; w = 0; }
+  __device__ __forceinline__ void put(uint32_t out, uint32_t* slot, uint32_t slotWords, uint32_t* spill) {
+    if (w < slotWords) slot[w] = out;
+    else if (w - slotWords < uint32_t(kH2SpillWords)) spill[w - slotWords] = out;
+    w++;
+  }
+  // m24: symbol bytes in the low bytes (byte 3 zero), n8 = 8 x their number (8, 16 or 24)
+  __device__ __forceinline__ void append(uint32_t m24, uint32_t n8, uint32_t* slot, uint32_t slotWords, uint32_t* spill) {
+    const uint32_t out = __funnelshift_l(acc, m24, qc8);
+    acc = __funnelshift_r(acc, m24, n8);
+    qc8 += n8;
+    if (qc8 >= 32u) {
+      put(out, slot, slotWords, spill);
+      qc8 -= 32u;
+    }
+  }
+  __device__ __forceinline__ void finish(uint32_t* slot, uint32_t slotWords, uint32_t* spill) {
+    if (qc8) put(acc >> (32u - qc8), slot, slotWords, spill);
+  }
+};
+
+struct H2PosCursor {  // two staged words and the absolute bit position; a refill is due when a skip crosses a word boundary
+  uint32_t lo, hi, next, pos;
+  __device__ __forceinline__ void init(const uint32_t* sw, uint32_t p) {
+    const uint32_t i = p >> 5;
+    lo = sw[i];
+    hi = sw[i + 1];
+    next = i + 2;
+    pos = p;
+  }
+  __device__ __forceinline__ uint32_t peek() const { return __funnelshift_r(lo, hi, pos); }
+  __device__ __forceinline__ void skip(const uint32_t* sw, uint32_t n) {
+    const uint32_t np = pos + n;
+    if ((np ^ pos) & 32u) {
+      lo = hi;
+      hi = sw[next++];
+    }
+    pos = np;
+  }
+};
+
 template <bool STORE>
 __device__ __forceinline__ void h2_sub(const Huff2Shared& S, const uint32_t* sw, uint32_t nBits, uint32_t start, uint32_t limit, uint32_t* slot,
                                        uint32_t slotWords, uint32_t* spill, uint32_t* endOut, uint32_t* cntOut, int* flagOut) {
-  H2Cursor cur;
-  cur.init(sw, start, limit);
-  uint32_t c = 0, end, w = 0, qc = 0;
-  uint64_t q = 0;
+  H2PosCursor cur;
+  cur.init(sw, start);
+  const int lastFull = int(limit) - kLutBits;  // the whole table window lies before the limit up to this position
+  uint32_t c = 0, end;
+  H2ByteAcc A;
+  A.init();
   int flag = 0;
-  auto flush = [&]() {
-    if (STORE) {
-      if (w < slotWords) slot[w] = uint32_t(q);
-      else if (w - slotWords < uint32_t(kH2SpillWords)) spill[w - slotWords] = uint32_t(q);
-    }
-    w++;
-  };
   for (;;) {
-    if (cur.rem >= kLutBits) {  // the whole window lies before the limit: every symbol coded inside it is consumed
+    if (int(cur.pos) <= lastFull) {  // every symbol coded inside the window is consumed
       const uint32_t m = S.mlut[cur.peek() & ((1u << kLutBits) - 1u)];
       const uint32_t n = m >> 28;
       if (n) {
         cur.skip(sw, (m >> 24) & 15u);
         c += n;
-        if (STORE) {
-          q |= uint64_t(m & 0xffffffu) << (8 * qc);
-          qc += n;
-          if (qc >= 4) {
-            flush();
-            q >>= 32;
-            qc -= 4;
-          }
-        }
+        if (STORE) A.append(m & 0xffffffu, (m >> 25) & 0x18u, slot, slotWords, spill);
         continue;
       }
     }
-    if (cur.rem <= 0) { end = cur.pos(limit); break; }
+    if (cur.pos >= limit) { end = cur.pos; break; }
     const uint32_t e = S.lut[cur.peek() & ((1u << kLutBits) - 1u)];
     uint32_t byte;
     if (!(e & 0x8000u)) {
       cur.skip(sw, (e >> 9) & 15u);
       byte = e & 0xffu;
     } else {
-      const uint32_t p0 = cur.pos(limit);
+      const uint32_t p0 = cur.pos;
       uint32_t after;
       byte = uint32_t(h2_long_symbol(S, sw, e, p0, &after));
       if (after > nBits + 32u * kH2PadWords - 64u) { flag |= kH2FlagBad; end = p0; break; }
-      cur.init(sw, after, limit);
+      cur.init(sw, after);
     }
     c++;
-    if (STORE) {
-      q |= uint64_t(byte) << (8 * qc);
-      qc += 1;
-      if (qc >= 4) {
-        flush();
-        q >>= 32;
-        qc -= 4;
-      }
-    }
+    if (STORE) A.append(byte, 8u, slot, slotWords, spill);
   }
   if (STORE) {
-    if (qc) flush();
-    if (w > slotWords + uint32_t(kH2SpillWords)) flag |= kH2FlagOverflow;
+    A.finish(slot, slotWords, spill);
+    if (A.w > slotWords + uint32_t(kH2SpillWords)) flag |= kH2FlagOverflow;
   }
   *endOut = end;
   *cntOut = c;

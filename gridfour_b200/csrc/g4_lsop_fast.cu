@@ -339,41 +339,84 @@ constexpr int kSubRare = 4;      // S.eot[] flag: the sub-sequence holds an esca
 constexpr int kSubOverflow = 8;  // S.eot[] flag: more values than the slot holds
 
 // Like canon_fast_count; additionally stores the symbol byte of every counted value to slot[0 .. slotWords) (shared memory).
+// Bit window of the staging pass: two staged words and the absolute bit position (the funnel shift takes it modulo 32;
+// a refill is due when a skip crosses a word boundary).
+struct PosCursor {
+  uint32_t lo, hi, next, pos;
+  __device__ __forceinline__ void init(const uint32_t* sw, uint32_t p) {
+    const uint32_t i = p >> 5;
+    lo = sw[i];
+    hi = sw[i + 1];
+    next = i + 2;
+    pos = p;
+  }
+  __device__ __forceinline__ uint32_t peek() const { return __funnelshift_r(lo, hi, pos); }
+  __device__ __forceinline__ void skip(const uint32_t* sw, uint32_t n) {  // n <= 32
+    const uint32_t np = pos + n;
+    if ((np ^ pos) & 32u) {
+      lo = hi;
+      hi = sw[next++];
+    }
+    pos = np;
+  }
+};
+
+// Byte accumulator of the staging pass: the pending (< 4) bytes sit TOP-justified in `acc`, so that they and the (up to
+// three) symbol bytes of a lookup are contiguous in the pair (acc, m): the next output word is one funnel shift left, the
+// new accumulator one funnel shift right -- no 64-bit queue.  qc8 = 8 x pending bytes.
+struct ByteAcc {
+  uint32_t acc, qc8, w;
+  __device__ __forceinline__ void init() { acc = 0; qc8 = 0; w = 0; }
+  // m24: symbol bytes in the low bytes (byte 3 zero), n8 = 8 x their number (8, 16 or 24)
+  __device__ __forceinline__ void append(uint32_t m24, uint32_t n8, uint32_t* slot, uint32_t slotWords, uint32_t* spill) {
+    const uint32_t out = __funnelshift_l(acc, m24, qc8);
+    acc = __funnelshift_r(acc, m24, n8);
+    qc8 += n8;
+    if (qc8 >= 32u) {
+      if (w < slotWords) slot[w] = out;
+      else if (w - slotWords < uint32_t(kSpillWords)) spill[w - slotWords] = out;
+      w++;
+      qc8 -= 32u;
+    }
+  }
+  __device__ __forceinline__ void finish(uint32_t* slot, uint32_t slotWords, uint32_t* spill) {
+    if (qc8) {
+      const uint32_t out = acc >> (32u - qc8);
+      if (w < slotWords) slot[w] = out;
+      else if (w - slotWords < uint32_t(kSpillWords)) spill[w - slotWords] = out;
+      w++;
+    }
+  }
+};
+
 __device__ __forceinline__ void text_stage_sub(const CanonFastShared& S, uint32_t nBits, uint32_t start, uint32_t limit, uint32_t* slot,
                                                uint32_t slotWords, uint32_t* spill, uint32_t* endOut, uint32_t* cntOut, int* flagOut) {
-  BitCursor cur;
-  cur.init(S, start, limit);
+  PosCursor cur;
+  cur.init(S.sw, start);
+  const int lastFull = int(limit) - kFastLutBits;  // the 11-bit window lies before the limit up to this position
   uint32_t c = 0, end;
   int flag = 0;
-  uint64_t q = 0;
-  uint32_t qc = 0, w = 0;
+  ByteAcc A;
+  A.init();
   for (;;) {
-    if (cur.rem >= kFastLutBits) {
+    if (int(cur.pos) <= lastFull) {
       const uint32_t m = S.mlut[cur.peek() & ((1u << kFastLutBits) - 1u)];
       const uint32_t n = m >> 28;
       if (n) {
-        cur.skip(S, (m >> 24) & 15u);
+        cur.skip(S.sw, (m >> 24) & 15u);
         c += n;
-        q |= uint64_t(m & 0xffffffu) << (8 * qc);
-        qc += n;
-        if (qc >= 4) {
-          if (w < slotWords) slot[w] = uint32_t(q);
-          else if (w - slotWords < uint32_t(kSpillWords)) spill[w - slotWords] = uint32_t(q);
-          w++;
-          q >>= 32;
-          qc -= 4;
-        }
+        A.append(m & 0xffffffu, (m >> 25) & 0x18u, slot, slotWords, spill);
         continue;
       }
     }
     const uint32_t e = S.lut[cur.peek() & ((1u << kFastLutBits) - 1u)];
     uint32_t byte;
     if (e - 1u < 0x7fffu) {  // LUT hit on a plain value: e = sym | len << 9
-      if (cur.rem <= 0) { end = cur.pos(limit); break; }
-      cur.skip(S, e >> 9);
+      if (cur.pos >= limit) { end = cur.pos; break; }
+      cur.skip(S.sw, e >> 9);
       byte = e & 0xffu;
     } else {
-      const uint32_t p0 = cur.pos(limit);
+      const uint32_t p0 = cur.pos;
       uint32_t after;
       const int sym = canon_fast_rare_symbol(S, e, p0, nBits, &after);
       if (sym < 0) { flag = 2; end = p0; break; }
@@ -381,32 +424,20 @@ __device__ __forceinline__ void text_stage_sub(const CanonFastShared& S, uint32_
         after += sym == kSymEsc2 ? 2u : 8u;
         if (after > nBits) { flag = 2; end = p0; break; }
         flag |= kSubRare;
-        cur.init(S, after, limit);
+        cur.init(S.sw, after);
         continue;
       }
       if (p0 >= limit) { end = p0; break; }
       if (sym == kSymEot) { flag |= 1; end = after; break; }
       if (sym == kSymNull) { flag |= kSubRare; byte = 0u; }
       else byte = uint32_t(sym);  // a byte value with a code longer than the LUT
-      cur.init(S, after, limit);
+      cur.init(S.sw, after);
     }
     c++;
-    q |= uint64_t(byte) << (8 * qc);
-    qc += 1;
-    if (qc >= 4) {
-      if (w < slotWords) slot[w] = uint32_t(q);
-      else if (w - slotWords < uint32_t(kSpillWords)) spill[w - slotWords] = uint32_t(q);
-      w++;
-      q >>= 32;
-      qc -= 4;
-    }
+    A.append(byte, 8u, slot, slotWords, spill);
   }
-  if (qc) {
-    if (w < slotWords) slot[w] = uint32_t(q);
-    else if (w - slotWords < uint32_t(kSpillWords)) spill[w - slotWords] = uint32_t(q);
-    w++;
-  }
-  if (w > slotWords + uint32_t(kSpillWords)) flag |= kSubOverflow;
+  A.finish(slot, slotWords, spill);
+  if (A.w > slotWords + uint32_t(kSpillWords)) flag |= kSubOverflow;
   *endOut = end;
   *cntOut = c;
   *flagOut = flag;
