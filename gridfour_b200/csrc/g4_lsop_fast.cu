@@ -796,6 +796,10 @@ __global__ void __launch_bounds__(kTextThreads, 2) lsop2_text_kernel(LsopFastArg
 #ifndef G4_WAVE_CTAS
 #define G4_WAVE_CTAS 2
 #endif
+#ifndef G4_WAVE_WARPS
+#define G4_WAVE_WARPS 8
+#endif
+constexpr int kWaveWarps = G4_WAVE_WARPS;  // warps (= tiles) per CTA of the wavefront kernel
 constexpr int kWaveChunkBytes = 4096;  // ring stage: one bulk copy of 128 / W image rows (<= 32 strips x W bytes each)
 
 // The value of an exceptional cell (byte 0 in the scratch): its list entry, or -128 when the byte was genuine.
@@ -809,14 +813,14 @@ __device__ __noinline__ int32_t wave_exception(const uint32_t* exc, int n, int k
 __device__ __forceinline__ int wave_rowbuf_floats(int C) { return (C + 4 + 3) & ~3; }
 
 template <int W, bool WIDE>
-__global__ void __launch_bounds__(kThreads, G4_WAVE_CTAS) lsop3_wave_kernel(LsopFastArgs A, int listBegin, int listEnd) {
+__global__ void __launch_bounds__(32 * kWaveWarps, G4_WAVE_CTAS) lsop3_wave_kernel(LsopFastArgs A, int listBegin, int listEnd) {
   extern __shared__ __align__(128) unsigned char waveSmem[];
   constexpr int CR = 128 / W;   // image rows per chunk
   constexpr int NW = W / 4;     // residual words per lane and step
   constexpr int E = W - 4;      // the last strip: cells E, E + 1 are the row's last two columns (C a multiple of W)
   const DecodeArgs& a = A.a;
   const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
-  const int li = listBegin + blockIdx.x * kWarps + warp;
+  const int li = listBegin + blockIdx.x * kWaveWarps + warp;
   if (li >= listEnd || li >= *a.listCount) return;
   const int tIdx = a.list[li];
   if (a.status[tIdx] != G4_OK) return;
@@ -829,8 +833,8 @@ __global__ void __launch_bounds__(kThreads, G4_WAVE_CTAS) lsop3_wave_kernel(Lsop
   const TileView t = tile_view(a.band, a.grid, tIdx);
   const int rbFloats = wave_rowbuf_floats(C);
   unsigned char* ring = waveSmem + size_t(warp) * (2 * kWaveChunkBytes);
-  float* rowbuf = reinterpret_cast<float*>(waveSmem + size_t(kWarps) * (2 * kWaveChunkBytes)) + size_t(warp) * (2 * rbFloats);
-  uint64_t* bars = reinterpret_cast<uint64_t*>(waveSmem + size_t(kWarps) * (2 * kWaveChunkBytes) + size_t(kWarps) * (2 * rbFloats) * sizeof(float)) + 2 * warp;
+  float* rowbuf = reinterpret_cast<float*>(waveSmem + size_t(kWaveWarps) * (2 * kWaveChunkBytes)) + size_t(warp) * (2 * rbFloats);
+  uint64_t* bars = reinterpret_cast<uint64_t*>(waveSmem + size_t(kWaveWarps) * (2 * kWaveChunkBytes) + size_t(kWaveWarps) * (2 * rbFloats) * sizeof(float)) + 2 * warp;
   const uint32_t bar0 = smem_u32(bars), ring0 = smem_u32(ring);
   const bool active = lane < nS, isFirst = lane == 0, isLast = lane == nS - 1;
   if (lane == 0) {
@@ -1044,7 +1048,7 @@ size_t text_smem_bytes(const LsopFastGeom& g) {
 }
 size_t wave_smem_bytes(const LsopFastGeom& g) {
   const size_t rbFloats = size_t((g.C + 4 + 3) & ~3);
-  return size_t(kWarps) * (2 * kWaveChunkBytes) + size_t(kWarps) * (2 * rbFloats) * sizeof(float) + size_t(kWarps) * 16;
+  return size_t(kWaveWarps) * (2 * kWaveChunkBytes) + size_t(kWaveWarps) * (2 * rbFloats) * sizeof(float) + size_t(kWaveWarps) * 16;
 }
 
 template <int W>
@@ -1053,10 +1057,10 @@ cudaError_t launch_wave(const LsopFastArgs& A, int nCtas, int nTilesUpper, cudaS
   cudaError_t e;
   if (A.g.wide) {
     if ((e = cudaFuncSetAttribute(lsop3_wave_kernel<W, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, int(smem))) != cudaSuccess) return e;
-    lsop3_wave_kernel<W, true><<<nCtas, kThreads, smem, s>>>(A, 0, nTilesUpper);
+    lsop3_wave_kernel<W, true><<<nCtas, 32 * kWaveWarps, smem, s>>>(A, 0, nTilesUpper);
   } else {
     if ((e = cudaFuncSetAttribute(lsop3_wave_kernel<W, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, int(smem))) != cudaSuccess) return e;
-    lsop3_wave_kernel<W, false><<<nCtas, kThreads, smem, s>>>(A, 0, nTilesUpper);
+    lsop3_wave_kernel<W, false><<<nCtas, 32 * kWaveWarps, smem, s>>>(A, 0, nTilesUpper);
   }
   return cudaGetLastError();
 }
@@ -1117,8 +1121,9 @@ cudaError_t launch_lsop_decode_fast(const LsopFastArgs& A, int nTilesUpper, int 
   if (ctas > nTilesUpper) ctas = nTilesUpper;
   lsop2_text_kernel<<<ctas, kTextThreads, textSmem, s>>>(T, stageWords, 0, nTilesUpper);
   if ((e = cudaGetLastError()) != cudaSuccess) return e;
-  e = g.W == 4 ? launch_wave<4>(A, nCtasWarp, nTilesUpper, s) : g.W == 8 ? launch_wave<8>(A, nCtasWarp, nTilesUpper, s)
-                                                                            : launch_wave<16>(A, nCtasWarp, nTilesUpper, s);
+  const int nCtasWave = (nTilesUpper + kWaveWarps - 1) / kWaveWarps;
+  e = g.W == 4 ? launch_wave<4>(A, nCtasWave, nTilesUpper, s) : g.W == 8 ? launch_wave<8>(A, nCtasWave, nTilesUpper, s)
+                                                                            : launch_wave<16>(A, nCtasWave, nTilesUpper, s);
   if (e != cudaSuccess) return e;
   if (launches) *launches += 3;
   return cudaSuccess;
