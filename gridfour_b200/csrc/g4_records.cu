@@ -139,6 +139,16 @@ __global__ void __launch_bounds__(kCrcThreads) crc32c_kernel(const uint8_t* data
 __global__ void __launch_bounds__(kCrcThreads) lsop_value_checksum_kernel(DecodeArgs a) {
   __shared__ uint32_t T[8][256];
   __shared__ uint32_t x2n[32];
+  const int lane = threadIdx.x & 31;
+  const int li = (blockIdx.x * kCrcThreads + threadIdx.x) >> 5;
+  // (uniform per warp) does this warp's tile carry a checksum at all?  Most files do not: leave before building the tables.
+  bool need = false;
+  int tIdx = 0;
+  if (li < *a.listCount) {
+    tIdx = a.list[li];
+    need = a.lsopCks[2 * tIdx] != 0u && a.status[tIdx] == G4_OK;
+  }
+  if (!__syncthreads_or(need ? 1 : 0)) return;
   crc_build_tables(T);
   if (threadIdx.x == 0) {
     uint32_t p = 1u << 30;  // x^1
@@ -146,11 +156,7 @@ __global__ void __launch_bounds__(kCrcThreads) lsop_value_checksum_kernel(Decode
     for (int i = 1; i < 32; i++) x2n[i] = p = crc_multmodp(p, p);
   }
   __syncthreads();
-  const int lane = threadIdx.x & 31;
-  const int li = (blockIdx.x * kCrcThreads + threadIdx.x) >> 5;
-  if (li >= *a.listCount) return;
-  const int tIdx = a.list[li];
-  if (a.lsopCks[2 * tIdx] == 0u || a.status[tIdx] != G4_OK) return;
+  if (!need) return;
   const TileView t = tile_view(a.band, a.grid, tIdx);
   const uint32_t n = uint32_t(t.R) * uint32_t(t.C);
   uint32_t piece = ((n + 31u) / 32u + 1u) & ~1u;

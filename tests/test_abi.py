@@ -31,10 +31,12 @@ def test_codec_names_round_trip():
     from gridfour_b200 import _lib
 
     L = _lib.lib()
-    for i, name in enumerate([b"GvrsHuffman", b"GvrsDeflate", b"GvrsFloat", b"GvrsCanonicalHuffman", b"LSOP12"]):
+    for i, name in enumerate([b"GvrsHuffman", b"GvrsDeflate", b"GvrsFloat", b"GvrsCanonicalHuffman", b"LSOP12", b"LSOP08"]):
         assert L.g4_codec_id_from_name(name) == i
         assert L.g4_codec_name(i) == name
     assert L.g4_codec_id_from_name(b"nope") == -1
+    # LSOP08 is the legacy decode-only codec (lsop/LsCodecUtility.java:73): kernels for decode (direction 0), none for encode
+    assert L.g4_codec_supported(5, 0) == 1 and L.g4_codec_supported(5, 1) == 0
 
 
 def test_no_cpu_fallback_without_gpu():
