@@ -813,24 +813,15 @@ __device__ __noinline__ int32_t wave_exception(const uint32_t* exc, int n, int k
 __device__ __forceinline__ int wave_rowbuf_floats(int C) { return (C + 4 + 3) & ~3; }
 
 template <int W, bool WIDE>
-__global__ void __launch_bounds__(32 * kWaveWarps, G4_WAVE_CTAS) lsop3_wave_kernel(LsopFastArgs A, int listBegin, int listEnd) {
+__global__ void __launch_bounds__(32 * kWaveWarps, G4_WAVE_CTAS) lsop3_wave_kernel(LsopFastArgs A, int* tileCounter, int listBegin, int listEnd) {
   extern __shared__ __align__(128) unsigned char waveSmem[];
   constexpr int CR = 128 / W;   // image rows per chunk
   constexpr int NW = W / 4;     // residual words per lane and step
   constexpr int E = W - 4;      // the last strip: cells E, E + 1 are the row's last two columns (C a multiple of W)
   const DecodeArgs& a = A.a;
   const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
-  const int li = listBegin + blockIdx.x * kWaveWarps + warp;
-  if (li >= listEnd || li >= *a.listCount) return;
-  const int tIdx = a.list[li];
-  if (a.status[tIdx] != G4_OK) return;
-  if (*reinterpret_cast<const uint32_t*>(A.meta + size_t(tIdx) * kLsopMetaBytes) == 0u) return;  // general path
-  const uint32_t* exc = A.exc + size_t(tIdx) * kExcWords;
-  const int nExc = int(exc[0]);
-  if (nExc > kExcCap) return;  // deferred by kernel T
   const LsopFastGeom& G = A.g;
   const int R = G.R, C = G.C, nS = G.nStrips, P = G.P;
-  const TileView t = tile_view(a.band, a.grid, tIdx);
   const int rbFloats = wave_rowbuf_floats(C);
   unsigned char* ring = waveSmem + size_t(warp) * (2 * kWaveChunkBytes);
   float* rowbuf = reinterpret_cast<float*>(waveSmem + size_t(kWaveWarps) * (2 * kWaveChunkBytes)) + size_t(warp) * (2 * rbFloats);
@@ -843,11 +834,27 @@ __global__ void __launch_bounds__(32 * kWaveWarps, G4_WAVE_CTAS) lsop3_wave_kern
     asm volatile("fence.mbarrier_init.release.cluster;");
   }
   __syncwarp();
+  // persistent warps: every warp fetches its next tile when it is through with one (no wave quantisation of a static grid);
+  // gchunk counts the chunks this warp has fetched so far -- ring stage and mbarrier parity follow from it across tiles
+  uint32_t gchunk = 0;
+  for (;;) {
+  int li = 0;
+  if (lane == 0) li = listBegin + atomicAdd(tileCounter, 1);
+  li = __shfl_sync(0xffffffffu, li, 0);
+  if (li >= listEnd || li >= *a.listCount) break;
+  const int tIdx = a.list[li];
+  if (a.status[tIdx] != G4_OK) continue;
+  if (*reinterpret_cast<const uint32_t*>(A.meta + size_t(tIdx) * kLsopMetaBytes) == 0u) continue;  // general path
+  const uint32_t* exc = A.exc + size_t(tIdx) * kExcWords;
+  const int nExc = int(exc[0]);
+  if (nExc > kExcCap) continue;  // deferred by kernel T
+  const TileView t = tile_view(a.band, a.grid, tIdx);
   const uint8_t* img = A.resid + kResidGuard + size_t(tIdx) * size_t(G.tilePitch);
   const uint32_t chunkBytes = uint32_t(CR * P);
   const int nChunks = G.nChunks;
-  auto issue = [&](int chunk) {  // lane 0: image rows CR chunk .. CR chunk + CR - 1 into stage chunk & 1
-    const uint32_t bar = bar0 + 8u * (chunk & 1), dst = ring0 + uint32_t(kWaveChunkBytes) * (chunk & 1);
+  auto issue = [&](int chunk) {  // lane 0: image rows CR chunk .. CR chunk + CR - 1 into the next ring stage
+    const uint32_t g = gchunk + uint32_t(chunk);
+    const uint32_t bar = bar0 + 8u * (g & 1u), dst = ring0 + uint32_t(kWaveChunkBytes) * (g & 1u);
     mbar_expect_tx(bar, chunkBytes);
     asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(dst),
                  "l"(img + size_t(chunk) * chunkBytes), "r"(chunkBytes), "r"(bar)
@@ -891,9 +898,10 @@ __global__ void __launch_bounds__(32 * kWaveWarps, G4_WAVE_CTAS) lsop3_wave_kern
       const int chunk = s / CR;
       if (chunk < nChunks) {
         if (lane == 0 && chunk + 1 < nChunks) issue(chunk + 1);
-        mbar_wait(bar0 + 8u * (chunk & 1), uint32_t(chunk >> 1) & 1u);
+        const uint32_t g = gchunk + uint32_t(chunk);
+        mbar_wait(bar0 + 8u * (g & 1u), (g >> 1) & 1u);
       }
-      ringAt = ringLane + uint32_t(kWaveChunkBytes) * (chunk & 1);
+      ringAt = ringLane + uint32_t(kWaveChunkBytes) * ((gchunk + uint32_t(chunk)) & 1u);
     }
     const bool valid = rr < nRowsIn;
     const bool first = rr == 0u;
@@ -1031,6 +1039,8 @@ __global__ void __launch_bounds__(32 * kWaveWarps, G4_WAVE_CTAS) lsop3_wave_kern
   if (__any_sync(0xffffffffu, badBits != 0u)) {  // outside the fast arithmetic's range: the general kernels redo the tile
     if (lane == 0) A.defer[atomicAdd(A.deferCount, 1)] = tIdx;
   }
+  gchunk += uint32_t(nChunks);
+  }
 }
 
 size_t head_smem_bytes(const LsopFastGeom& g) {
@@ -1052,15 +1062,15 @@ size_t wave_smem_bytes(const LsopFastGeom& g) {
 }
 
 template <int W>
-cudaError_t launch_wave(const LsopFastArgs& A, int nCtas, int nTilesUpper, cudaStream_t s) {
+cudaError_t launch_wave(const LsopFastArgs& A, int nCtas, int nTilesUpper, int* tileCounter, cudaStream_t s) {
   const size_t smem = wave_smem_bytes(A.g);
   cudaError_t e;
   if (A.g.wide) {
     if ((e = cudaFuncSetAttribute(lsop3_wave_kernel<W, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, int(smem))) != cudaSuccess) return e;
-    lsop3_wave_kernel<W, true><<<nCtas, 32 * kWaveWarps, smem, s>>>(A, 0, nTilesUpper);
+    lsop3_wave_kernel<W, true><<<nCtas, 32 * kWaveWarps, smem, s>>>(A, tileCounter, 0, nTilesUpper);
   } else {
     if ((e = cudaFuncSetAttribute(lsop3_wave_kernel<W, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, int(smem))) != cudaSuccess) return e;
-    lsop3_wave_kernel<W, false><<<nCtas, 32 * kWaveWarps, smem, s>>>(A, 0, nTilesUpper);
+    lsop3_wave_kernel<W, false><<<nCtas, 32 * kWaveWarps, smem, s>>>(A, tileCounter, 0, nTilesUpper);
   }
   return cudaGetLastError();
 }
@@ -1121,9 +1131,11 @@ cudaError_t launch_lsop_decode_fast(const LsopFastArgs& A, int nTilesUpper, int 
   if (ctas > nTilesUpper) ctas = nTilesUpper;
   lsop2_text_kernel<<<ctas, kTextThreads, textSmem, s>>>(T, stageWords, 0, nTilesUpper);
   if ((e = cudaGetLastError()) != cudaSuccess) return e;
-  const int nCtasWave = (nTilesUpper + kWaveWarps - 1) / kWaveWarps;
-  e = g.W == 4 ? launch_wave<4>(A, nCtasWave, nTilesUpper, s) : g.W == 8 ? launch_wave<8>(A, nCtasWave, nTilesUpper, s)
-                                                                            : launch_wave<16>(A, nCtasWave, nTilesUpper, s);
+  int nCtasWave = (nTilesUpper + kWaveWarps - 1) / kWaveWarps;
+  if (nCtasWave > smCount * G4_WAVE_CTAS) nCtasWave = smCount * G4_WAVE_CTAS;  // persistent: one resident set of CTAs
+  int* waveCounter = textCounter + 1;
+  e = g.W == 4 ? launch_wave<4>(A, nCtasWave, nTilesUpper, waveCounter, s) : g.W == 8 ? launch_wave<8>(A, nCtasWave, nTilesUpper, waveCounter, s)
+                                                                                          : launch_wave<16>(A, nCtasWave, nTilesUpper, waveCounter, s);
   if (e != cudaSuccess) return e;
   if (launches) *launches += 3;
   return cudaSuccess;
