@@ -119,6 +119,7 @@ __device__ __forceinline__ void h2_parse_tree(uint16_t (*kid)[2], int16_t* leafS
   uint64_t expR = 0, amR = 0;
   int depth = 0, nodes = 1, leaves = 0;
   bool done = false;
+  int pendParent = -1, pendId = 0;
   leafSym[0] = -1;
   kid[0][0] = 1;
   pstack[0] = 0;  // node id at every depth of the current path
@@ -127,7 +128,11 @@ __device__ __forceinline__ void h2_parse_tree(uint16_t (*kid)[2], int16_t* leafS
     const uint32_t x = uint32_t(buf) & 0x1ffu;
     const int id = nodes++;
     const bool isRight = (expR >> depth) & 1ull;
-    if (isRight) kid[pstack[depth]][1] = uint16_t(id);
+    // the right link of the parent: its id is read now, the store waits until the next token so that the (local-memory)
+    // read is not what the in-order pipeline stalls on
+    if (pendParent >= 0) kid[pendParent][1] = uint16_t(pendId);
+    pendParent = isRight ? int(pstack[depth]) : -1;
+    pendId = id;
     int used;
     if (x & 1u) {
       leafSym[id] = int16_t((x >> 1) & 0xffu);
@@ -165,6 +170,7 @@ __device__ __forceinline__ void h2_parse_tree(uint16_t (*kid)[2], int16_t* leafS
       nextWord = word(++wi);
     }
   }
+  if (pendParent >= 0) kid[pendParent][1] = uint16_t(pendId);
   if (!done || pos > nBits) { M.error = 1; return; }
   M.treeBits = pos;
 }
