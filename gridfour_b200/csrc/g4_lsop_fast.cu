@@ -46,7 +46,9 @@ namespace g4 {
 
 namespace {
 
-constexpr int kTextThreads = 512;
+constexpr int kTextThreads = 512;              // text kernel: threads per CTA for tiles of more than kTextSmallTile samples
+constexpr int kTextThreadsSmall = 256;         // ... and for smaller tiles (four CTAs per SM instead of two)
+constexpr uint32_t kTextSmallTile = 16384;
 constexpr uint32_t kTextSubBits = 320;        // target sub-sequence size of the text kernel: one sub-sequence per thread for a 180x240 tile
 constexpr int kExcWords = 128;               // per tile: [0] count, [2+2i] interior index, [3+2i] value
 constexpr int kExcCap = (kExcWords - 2) / 2;  // 63 exceptions; more -> general path
@@ -65,6 +67,11 @@ constexpr float kMagicInt = 12582912.0f;     // 1.5 * 2^23, bits 0x4B400000
 constexpr float kRange = 2097152.0f;         // 2^21
 
 __device__ __forceinline__ uint32_t smem_u32(const void* p) { return uint32_t(__cvta_generic_to_shared(p)); }
+// shared memory of the text kernel in front of the tile image: CanonFastShared with a staging array of stageWords (+ 8) words --
+// its LAST member, so the struct may be allocated shorter or longer than its declared size
+__host__ __device__ constexpr size_t text_fast_bytes(uint32_t stageWords) {
+  return (offsetof(CanonFastShared, sw) + size_t(stageWords + 8u) * 4u + 127u) & ~size_t(127);
+}
 __device__ __forceinline__ void mbar_init(uint32_t bar, uint32_t count) {
   asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(bar), "r"(count));
 }
@@ -541,9 +548,9 @@ __device__ __noinline__ void text_exceptions_sub(const CanonFastShared& S, uint3
 
 // Decodes the interior text (tables and LUT ready, text at bit T0) into the tile image.  All kTextThreads threads call.
 // Returns 0 = done, 1 = malformed stream, 2 = the tile does not suit the staged form (caller uses canon_fast_decode_text).
+template <int NT>
 __device__ int lsop_text_decode(CanonFastShared& S, uint32_t nBits, const uint32_t T0, uint32_t nInterior, uint32_t imageBytes,
                                 ByteTileSink sink, uint32_t* spillArea, uint32_t lookback) {
-  constexpr int NT = kTextThreads;
   constexpr int kRounds = kFastMaxSub / NT;
   const int tid = threadIdx.x;
   const uint32_t avail = nBits - T0;
@@ -700,10 +707,11 @@ __device__ int lsop_text_decode(CanonFastShared& S, uint32_t nBits, const uint32
   return __syncthreads_or(bad ? 1 : 0) ? 1 : 0;
 }
 
-__global__ void __launch_bounds__(kTextThreads, 2) lsop2_text_kernel(LsopFastArgs A, uint32_t stageWords, int listBegin, int listEnd) {
+template <int NT>
+__global__ void __launch_bounds__(NT, NT == 512 ? 2 : 4) lsop2_text_kernel(LsopFastArgs A, uint32_t stageWords, int listBegin, int listEnd) {
   extern __shared__ __align__(128) unsigned char textSmem[];
   CanonFastShared& F = *reinterpret_cast<CanonFastShared*>(textSmem);
-  uint8_t* tileImg = textSmem + ((canon_fast_smem_bytes(stageWords) + 127) & ~size_t(127));
+  uint8_t* tileImg = textSmem + text_fast_bytes(stageWords);
   __shared__ int sTile[2];
   __shared__ __align__(8) uint64_t sBar;
   const DecodeArgs& a = A.a;
@@ -742,7 +750,7 @@ __global__ void __launch_bounds__(kTextThreads, 2) lsop2_text_kernel(LsopFastArg
       reinterpret_cast<uint8_t*>(F.sw)[i] = i < span ? src16[i] : uint8_t(0);
     }
     // decoding tables as kernel H built (and validated) them
-    for (int i = tid; i < kCanonSymbols; i += kTextThreads) F.sorted[i] = reinterpret_cast<const uint16_t*>(m + kLsopMetaSorted)[i];
+    for (int i = tid; i < kCanonSymbols; i += NT) F.sorted[i] = reinterpret_cast<const uint16_t*>(m + kLsopMetaSorted)[i];
     if (tid < 17) {
       F.firstCode[tid] = reinterpret_cast<const uint16_t*>(m + kLsopMetaFirst)[tid];
       F.count[tid] = reinterpret_cast<const uint16_t*>(m + kLsopMetaCount)[tid];
@@ -751,7 +759,7 @@ __global__ void __launch_bounds__(kTextThreads, 2) lsop2_text_kernel(LsopFastArg
     if (tid == 0) F.error = 0;
     __syncthreads();
     bool ok = true;
-    canon_fast_build_lut<kTextThreads>(F);
+    canon_fast_build_lut<NT>(F);
     if (nBulk) mbar_wait(bar, parity);
     parity ^= nBulk ? 1u : 0u;
     __syncthreads();
@@ -763,12 +771,12 @@ __global__ void __launch_bounds__(kTextThreads, 2) lsop2_text_kernel(LsopFastArg
       // the previous tile's image has left shared memory (a barrier follows before the image is written again)
       if (tid == 0) asm volatile("cp.async.bulk.wait_group.read 0;" ::: "memory");
       if (kTextStaged)
-        rc = lsop_text_decode(F, span * 8u, T0 + 8u * delta, nInterior, uint32_t(A.g.tileBytes), sink,
+        rc = lsop_text_decode<NT>(F, span * 8u, T0 + 8u * delta, nInterior, uint32_t(A.g.tileBytes), sink,
                               reinterpret_cast<uint32_t*>(A.textStage) + size_t(blockIdx.x) * (kFastMaxSub * kSpillWords), A.textLookback);
       else rc = 2;
       if (rc == 2) {  // (uniform) the two-pass form
         uint32_t endBit = 0, nv = 0;
-        rc = (canon_fast_decode_text<ByteTileSink, kTextThreads, kTextSubBits>(F, span * 8u, T0 + 8u * delta, nInterior, 0u, sink, &endBit, &nv) &&
+        rc = (canon_fast_decode_text<ByteTileSink, NT, kTextSubBits>(F, span * 8u, T0 + 8u * delta, nInterior, 0u, sink, &endBit, &nv) &&
               nv == nInterior) ? 0 : 1;
       }
       ok = rc == 0;
@@ -1048,14 +1056,13 @@ size_t head_smem_bytes(const LsopFastGeom& g) {
   return size_t(kWarps) * (((sizeof(CanonWarpShared) + 15) & ~size_t(15)) + ((nInit * 4 + 15) & ~size_t(15))) + 16;
 }
 uint32_t text_stage_words(const LsopFastGeom& g) {
-  // 5 bits per sample of the tile, at least the default 28 KB
-  uint32_t w = uint32_t((uint64_t(g.R) * uint64_t(g.C) * 5 / 8 + 3) / 4);
-  if (w < uint32_t(kFastStageWords)) w = kFastStageWords;
+  // 5 bits per sample of the tile plus the headers, at least 2 KB (a packing that does not fit goes to the general kernels)
+  uint32_t w = uint32_t((uint64_t(g.R) * uint64_t(g.C) * 5 / 8 + 3) / 4) + 128u;
+  if (w < 512u) w = 512u;
   return (w + 255u) & ~255u;
 }
-size_t text_smem_bytes(const LsopFastGeom& g) {
-  return ((canon_fast_smem_bytes(text_stage_words(g)) + 127) & ~size_t(127)) + size_t(g.tileBytes);
-}
+size_t text_smem_bytes(const LsopFastGeom& g) { return text_fast_bytes(text_stage_words(g)) + size_t(g.tileBytes); }
+bool text_small(const LsopFastGeom& g) { return uint32_t(g.R) * uint32_t(g.C) <= kTextSmallTile; }
 size_t wave_smem_bytes(const LsopFastGeom& g) {
   const size_t rbFloats = size_t((g.C + 4 + 3) & ~3);
   return size_t(kWaveWarps) * (2 * kWaveChunkBytes) + size_t(kWaveWarps) * (2 * rbFloats) * sizeof(float) + size_t(kWaveWarps) * 16;
@@ -1103,7 +1110,7 @@ bool lsop_fast_geometry(const g4_band_desc& band, const void* grid, LsopFastGeom
 }
 size_t lsop_fast_side_bytes(const LsopFastGeom& g, int nTiles) { return size_t(nTiles) * size_t(g.R) * sizeof(int4); }
 size_t lsop_fast_exc_bytes(int nTiles) { return size_t(nTiles) * kExcWords * sizeof(uint32_t); }
-size_t lsop_fast_stage_bytes(int smCount) { return size_t(smCount) * 2 * kFastMaxSub * kSpillWords * sizeof(uint32_t); }  // text kernel: <= 2 CTAs per SM
+size_t lsop_fast_stage_bytes(int smCount) { return size_t(smCount) * 4 * kFastMaxSub * kSpillWords * sizeof(uint32_t); }  // text kernel: <= 4 CTAs per SM
 size_t lsop_fast_resid_bytes(const LsopFastGeom& g, int nTiles) { return size_t(kResidGuard) + size_t(nTiles) * size_t(g.tilePitch) + 4096; }
 
 // Kernels H, T and W over the list positions [0, nTilesUpper).  Tiles the fast path cannot take are appended to
@@ -1113,7 +1120,9 @@ cudaError_t launch_lsop_decode_fast(const LsopFastArgs& A, int nTilesUpper, int 
   // dynamic shared memory opt-in: per device and per geometry, so simply set before every launch set (host-side only)
   {
     cudaError_t e = cudaFuncSetAttribute(lsop2_head_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, int(head_smem_bytes(g)));
-    if (e == cudaSuccess) e = cudaFuncSetAttribute(lsop2_text_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, int(text_smem_bytes(g)));
+    if (e == cudaSuccess)
+      e = text_small(g) ? cudaFuncSetAttribute(lsop2_text_kernel<kTextThreadsSmall>, cudaFuncAttributeMaxDynamicSharedMemorySize, int(text_smem_bytes(g)))
+                        : cudaFuncSetAttribute(lsop2_text_kernel<kTextThreads>, cudaFuncAttributeMaxDynamicSharedMemorySize, int(text_smem_bytes(g)));
     if (e != cudaSuccess) return e;
   }
   const uint32_t stageWords = text_stage_words(g);
@@ -1125,11 +1134,13 @@ cudaError_t launch_lsop_decode_fast(const LsopFastArgs& A, int nTilesUpper, int 
   T.a.counter = textCounter;
   const size_t textSmem = text_smem_bytes(g);
   int perSm = int((227u * 1024u) / (textSmem + 1024));
+  const int perSmCap = text_small(g) ? 4 : 2;  // 64 registers per thread: 1,024 threads per SM
   if (perSm < 1) perSm = 1;
-  if (perSm > 2) perSm = 2;
+  if (perSm > perSmCap) perSm = perSmCap;
   int ctas = smCount * perSm;
   if (ctas > nTilesUpper) ctas = nTilesUpper;
-  lsop2_text_kernel<<<ctas, kTextThreads, textSmem, s>>>(T, stageWords, 0, nTilesUpper);
+  if (text_small(g)) lsop2_text_kernel<kTextThreadsSmall><<<ctas, kTextThreadsSmall, textSmem, s>>>(T, stageWords, 0, nTilesUpper);
+  else lsop2_text_kernel<kTextThreads><<<ctas, kTextThreads, textSmem, s>>>(T, stageWords, 0, nTilesUpper);
   if ((e = cudaGetLastError()) != cudaSuccess) return e;
   int nCtasWave = (nTilesUpper + kWaveWarps - 1) / kWaveWarps;
   if (nCtasWave > smCount * G4_WAVE_CTAS) nCtasWave = smCount * G4_WAVE_CTAS;  // persistent: one resident set of CTAs
