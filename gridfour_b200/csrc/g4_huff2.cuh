@@ -17,6 +17,7 @@
 // single-symbol tree, an oversized packing) is handed to huffman_decode_kernel through a defer list.
 #pragma once
 #include "g4_huff_fast.cuh"
+#include "g4_predict.cuh"  // the M32 byte automaton (m32_byte_map / m32_compose / m32_apply)
 
 namespace g4 {
 
@@ -28,6 +29,8 @@ constexpr int kH2SpillWords = 16;      // words behind every slot in the per-CTA
 constexpr int kH2BandRows = 32;
 constexpr int kH2PadWords = 16;        // zero words behind the staged packing (a long code may be walked past the end)
 constexpr int kH2FlagBad = 1, kH2FlagOverflow = 2;
+constexpr uint32_t kH2ExcCap = 1024;  // multi-byte residuals a tile may hold on the fast path ((index, value) pairs over the dead LUT)
+constexpr uint32_t kH2CompactChunk = 88;  // M32 bytes per thread of h2_m32_compact
 
 struct H2TreeMeta {
   uint32_t treeBits;
@@ -44,6 +47,7 @@ struct Huff2Shared {
   uint16_t cnt[kH2MaxSub];
   uint8_t flag[kH2MaxSub];
   uint32_t scan[33];
+  uint32_t nExc;                 // residuals whose M32 code is longer than one byte (h2_m32_compact)
   H2TreeMeta tree;
 };
 
@@ -476,6 +480,96 @@ __device__ int h2_decode_text(Huff2Shared& S, const uint32_t* sw, uint32_t nBits
   return __syncthreads_or(bad ? 1 : 0) ? 1 : 0;
 }
 
+// Tiles with M32 codes longer than one byte (spikes in the terrain): the code bytes in m32[0 .. nM32) are rewritten IN PLACE
+// into one byte per residual -- byte k = the one-byte code of residual k, or 0 for a residual with a longer code, whose value
+// goes to exc[] as (k, value) -- so that the Triangle pass below can run unchanged and add the few long values afterwards.
+// Code boundaries come from a prefix scan over the START / CONT byte automaton (CodecM32.java:327-356, g4_predict.cuh).
+// tmp: NT * 24 words of global scratch (the bytes a thread produces wait there until every thread has read its chunk).
+// All NT threads call.  Returns 0 = done, 1 = malformed stream, 2 = more long codes than exc[] holds (caller defers).
+template <int NT>
+__device__ __noinline__ int h2_m32_compact(Huff2Shared& S, uint8_t* m32, uint32_t nM32, uint32_t nVal, uint2* exc, uint32_t* tmp) {
+  const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+  constexpr int kW = NT / 32;
+  const uint32_t chunk = (nM32 + NT - 1) / NT;  // <= kH2CompactChunk (checked by the caller)
+  const uint32_t b0 = uint32_t(tid) * chunk < nM32 ? uint32_t(tid) * chunk : nM32;
+  const uint32_t b1 = b0 + chunk < nM32 ? b0 + chunk : nM32;
+  if (tid == 0) S.nExc = 0;
+  uint32_t f = 2u;  // identity
+  for (uint32_t b = b0; b < b1; b++) f = m32_compose(f, m32_byte_map(m32[b]));
+  uint32_t inc = f;
+#pragma unroll
+  for (int d = 1; d < 32; d <<= 1) {
+    const uint32_t y = __shfl_up_sync(0xffffffffu, inc, d);
+    if (lane >= d) inc = m32_compose(y, inc);
+  }
+  __syncthreads();
+  if (lane == 31) S.scan[warp] = inc;
+  __syncthreads();
+  uint32_t pre = 2u, all = 2u;
+#pragma unroll
+  for (int w = 0; w < kW; w++) {
+    const uint32_t m = S.scan[w];
+    if (w < warp) pre = m32_compose(pre, m);
+    all = m32_compose(all, m);
+  }
+  uint32_t excl = __shfl_up_sync(0xffffffffu, inc, 1);
+  if (lane == 0) excl = 2u;
+  const uint32_t state0 = m32_apply(m32_compose(pre, excl), 0u);
+  if (m32_apply(all, 0u) != 0u) return 1;  // (uniform) the stream ends inside a code
+  uint32_t cnt = 0;
+  {
+    uint32_t st = state0;
+    for (uint32_t b = b0; b < b1; b++) {
+      if (st == 0u) cnt++;
+      st = m32_apply(m32_byte_map(m32[b]), st);
+    }
+  }
+  uint32_t total;
+  const uint32_t k0 = block_exclusive_scan<NT>(cnt, S.scan, &total);
+  if (total != nVal) return 1;  // (uniform)
+  // my residual bytes -> scratch, long codes -> exception list
+  bool bad = false;
+  {
+    uint32_t* out = tmp + size_t(tid) * 24u;
+    uint32_t st = state0, k = k0, acc = 0, nb = 0, w = 0;
+    for (uint32_t b = b0; b < b1; b++) {
+      const uint32_t byte = m32[b];
+      if (st == 0u) {
+        uint32_t r = byte;
+        if (byte == 0x7Fu || byte == 0x81u) {
+          int32_t val;
+          if (m32_decode_at(m32, b, nM32, &val) == 0) bad = true;
+          const uint32_t slot = atomicAdd(&S.nExc, 1u);
+          if (slot < kH2ExcCap) exc[slot] = make_uint2(k, uint32_t(val));
+          r = 0u;
+        }
+        acc |= r << (8u * nb);
+        if (++nb == 4u) {
+          out[w++] = acc;
+          acc = 0;
+          nb = 0;
+        }
+        k++;
+      }
+      st = m32_apply(m32_byte_map(byte), st);
+    }
+    if (nb) out[w] = acc;
+  }
+  if (__syncthreads_or(bad ? 1 : 0)) return 1;  // (also: every thread has read its chunk of m32)
+  if (cnt) {
+    const uint32_t* in = tmp + size_t(tid) * 24u;
+    H2ByteSink sink;
+    sink.begin(m32, k0);
+    for (uint32_t at = 0; at < cnt; at += 4u) {
+      const uint32_t wv = in[at >> 2], m = cnt - at;
+      sink.push(m >= 4u ? wv : (wv & ((1u << (8 * m)) - 1u)), m >= 4u ? 4 : int(m));
+    }
+    sink.end();
+  }
+  __syncthreads();
+  return S.nExc > kH2ExcCap ? 2 : 0;
+}
+
 // Triangle predictor, every residual a one-byte M32 code: raster = 2-D inclusive prefix sum of the residual field.
 // m32 = the nM32 = R*C - 1 code bytes in stream order (row 0 from column 1, column 0 from row 1, interior
 // row-major), readable from m32 - 4; band = kH2BandRows * C int32 of shared memory.  All NT threads call.
@@ -484,7 +578,8 @@ __device__ int h2_decode_text(Huff2Shared& S, const uint32_t* sw, uint32_t nBits
 // plus the totals of the groups above it and writes its four rows as 16-byte pieces, whole rows coalesced.  The group
 // totals and the running column sums live in the sub-sequence arrays of S, which the decode no longer needs.
 template <int NT>
-__device__ inline void h2_triangle_bytes(Huff2Shared& S, const uint8_t* m32, int32_t seed, const TileView& t, int32_t* band) {
+__device__ inline void h2_triangle_bytes(Huff2Shared& S, const uint8_t* m32, int32_t seed, const TileView& t, int32_t* band, const uint2* exc,
+                                         uint32_t nExc) {
   const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
   constexpr int kW = NT / 32;
   constexpr int kGroups = kH2BandRows / 4;
@@ -564,6 +659,22 @@ __device__ inline void h2_triangle_bytes(Huff2Shared& S, const uint8_t* m32, int
       }
     }
     __syncthreads();
+    if (nExc) {  // (uniform) residuals with long M32 codes: their byte is 0, their value is added to the rest of their row now
+      for (uint32_t e = uint32_t(warp); e < nExc; e += uint32_t(kW)) {
+        const uint32_t k = exc[e].x, val = exc[e].y;
+        int r, c;
+        if (k < uint32_t(C - 1)) { r = 0; c = int(k) + 1; }
+        else if (k < uint32_t(C + R - 2)) { r = int(k) - (C - 1) + 1; c = 0; }
+        else {
+          const uint32_t j = k - uint32_t(C + R - 2);
+          r = 1 + int(j / uint32_t(C - 1));
+          c = 1 + int(j % uint32_t(C - 1));
+        }
+        if (r >= r0 && r < r0 + nr)
+          for (int cc = c + lane; cc < C; cc += 32) atomicAdd(reinterpret_cast<unsigned int*>(band + size_t(r - r0) * C + cc), val);
+      }
+      __syncthreads();
+    }
     if (quads) {
       auto add4 = [](int4 a, int4 b) {
         return make_int4(int32_t(uint32_t(a.x) + uint32_t(b.x)), int32_t(uint32_t(a.y) + uint32_t(b.y)), int32_t(uint32_t(a.z) + uint32_t(b.z)),

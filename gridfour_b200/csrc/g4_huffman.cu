@@ -496,8 +496,8 @@ __global__ void __launch_bounds__(NT, NT == 512 ? 2 : 4)
     }
     const uint32_t delta = uint32_t(reinterpret_cast<uintptr_t>(packing) & 15u);
     const uint32_t span = len + delta;
-    bool fast = pred == G4_PRED_TRIANGLE && nM32 == uint32_t(n - 1) && span + 4u * kH2PadWords + 16u <= g.stageBytes &&
-                nM32 + 32u <= g.m32Cap && t.C <= 2 * NT && size_t(kH2BandRows) * t.C * 4 <= g.stageBytes;
+    bool fast = pred == G4_PRED_TRIANGLE && span + 4u * kH2PadWords + 16u <= g.stageBytes && nM32 + 32u <= g.m32Cap &&
+                nM32 <= kH2CompactChunk * uint32_t(NT) && t.C <= 2 * NT && size_t(kH2BandRows) * t.C * 4 <= g.stageBytes;
     int rc = 0;
     if (fast) {
       // stage: the packing from its 16-byte line start; whole 16-byte pieces by ONE bulk-async copy, the tail by bytes
@@ -537,7 +537,17 @@ __global__ void __launch_bounds__(NT, NT == 512 ? 2 : 4)
         h2_build_lut<NT>(S);
         rc = h2_decode_text<NT>(S, sw, nBits, S.tree.treeBits + 8u * delta, nM32, m32, g.m32Cap - 16u, spillArea, g.subBits, g.lookback);
         if (rc == 2) { fast = false; rc = 0; }
-        else if (rc == 0) h2_triangle_bytes<NT>(S, m32, seed, t, reinterpret_cast<int32_t*>(sw));  // (ends with a barrier)
+        else if (rc == 0) {
+          uint2* exc = reinterpret_cast<uint2*>(S.mlut);  // the tables are dead once the text is decoded
+          uint32_t nExc = 0;
+          if (nM32 != uint32_t(n - 1)) {  // codes longer than one byte: one byte per residual + an exception list
+            const int rc2 = h2_m32_compact<NT>(S, m32, nM32, uint32_t(n - 1), exc, spillArea);
+            if (rc2 == 1) rc = 1;
+            else if (rc2 == 2) fast = false;
+            nExc = S.nExc;
+          }
+          if (rc == 0 && fast) h2_triangle_bytes<NT>(S, m32, seed, t, reinterpret_cast<int32_t*>(sw), exc, nExc);  // (ends with a barrier)
+        }
       }
     }
     if (tid == 0) {
@@ -603,7 +613,7 @@ cudaError_t launch_huffman_decode(const DecodeArgs& a, int nCtas, cudaStream_t s
     const uint32_t bandBytes = uint32_t(kH2BandRows) * uint32_t(a.band.tile_cols) * 4u;
     if (stage < bandBytes) stage = (bandBytes + 15u) & ~15u;
     g.stageBytes = stage;
-    g.m32Cap = (n + 48u + 15u) & ~15u;
+    g.m32Cap = (n + n / 16u + 48u + 15u) & ~15u;  // room for some codes longer than one byte
     static const int subEnv = getenv("G4_H2_SUBBITS") ? atoi(getenv("G4_H2_SUBBITS")) : 0, lbEnv = getenv("G4_H2_LOOKBACK") ? atoi(getenv("G4_H2_LOOKBACK")) : 0;
     g.subBits = subEnv > 0 ? uint32_t(subEnv) : kH2SubBits;
     g.lookback = lbEnv > 0 ? uint32_t(lbEnv) : kH2Lookback;

@@ -144,3 +144,37 @@ def test_deep_tree_goes_to_the_general_kernel(g4, oracle):
     assert nn == n
     got = g4.CodecHuffman().decode(r, c, p)
     assert np.array_equal(got, grid), first_diff(got, grid)
+
+
+@pytest.mark.parametrize("shape,nspikes", [((90, 120), 1), ((90, 120), 40), ((180, 240), 7), ((180, 240), 900), ((64, 260), 12),
+                                           ((48, 64), 3000)])
+def test_triangle_tiles_with_multi_byte_codes(g4, oracle, shape, nspikes):
+    """Spikes make some Triangle residuals need 2..6 M32 bytes: the fast path keeps one byte per residual plus an exception
+    list (up to its capacity), beyond that -- or when the code bytes outgrow its buffer -- the tile goes to the general kernel."""
+    r, c = shape
+    rng = np.random.default_rng(r + c + nspikes)
+    grid = (np.add.outer(np.arange(r) * 2, np.arange(c) * 3) + rng.integers(-15, 16, (r, c))).astype(np.int64)
+    rr = rng.integers(0, r, nspikes)
+    cc = rng.integers(0, c, nspikes)
+    mag = rng.choice([200, 300, 20000, 3000000, 400000000, -2 ** 31 + 5], nspikes)
+    grid[rr, cc] += mag
+    grid = grid.astype(np.int32)  # wraps like Java ints
+    p, n = _packing(oracle, 3, grid)
+    assert n > r * c - 1
+    want = oracle.codec_decode_i32(oracle.CODEC_HUFFMAN, r, c, p)
+    assert np.array_equal(want, grid)
+    got = g4.CodecHuffman().decode(r, c, p)
+    assert np.array_equal(got, grid), first_diff(got, grid)
+
+
+def test_multi_byte_stream_that_ends_inside_a_code(g4, oracle):
+    """nM32 one byte short of a multi-byte code's end: the reference reads past its array (an exception); here a format error."""
+    r, c = 40, 52
+    grid = np.add.outer(np.arange(r), np.arange(c)).astype(np.int32)
+    grid[r - 1, c - 1] += 100000  # the last residual takes several bytes
+    n, seed, m32 = oracle.predictor_encode(3, grid)
+    m = np.frombuffer(m32, np.uint8)[:-1]  # drop the final byte of the last code
+    text, _ = oracle.huffman_encode(m)
+    p = bytes([0, 3]) + int(seed).to_bytes(4, "little", signed=True) + int(n - 1).to_bytes(4, "little") + text
+    with pytest.raises(IOError):
+        g4.CodecHuffman().decode(r, c, p)
