@@ -64,6 +64,11 @@ class Context:
     def launch_count(self):
         return int(_lib.lib().g4_launch_count(self._h))
 
+    def set_async(self, enabled):
+        """Device batches are only enqueued on the context's stream (decodeTiles returns at once, the per-tile status tensor
+        is valid after synchronize()): lets a caller keep several windows of tiles in flight."""
+        check(_lib.lib().g4_context_set_async(self._h, int(bool(enabled))))
+
     def set_timing(self, enabled):
         check(_lib.lib().g4_context_set_timing(self._h, int(bool(enabled))))
 

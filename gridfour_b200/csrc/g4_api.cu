@@ -118,6 +118,7 @@ struct g4_context {
   cudaEvent_t evIn[16] = {}, evDone[16] = {}, evStart = nullptr, evOrder = nullptr;
   // optional per-kernel timing (CUDA events on the launching stream): [0]=decode, [1]=encode, by codec kind
   bool timing = false;
+  bool asyncDevice = false;  // g4_context_set_async: device batches are enqueued, not awaited
   cudaEvent_t ev[2][G4_CODEC_COUNT + 1][2] = {};
   bool evUsed[2][G4_CODEC_COUNT + 1] = {};
 };
@@ -726,6 +727,12 @@ int g4_context_synchronize(g4_context* ctx) {
 
 uint64_t g4_launch_count(const g4_context* ctx) { return ctx ? ctx->launches : 0; }
 
+int g4_context_set_async(g4_context* ctx, int enabled) {
+  if (!ctx) return G4_ERR_ARG;
+  ctx->asyncDevice = enabled != 0;
+  return G4_OK;
+}
+
 int g4_context_set_timing(g4_context* ctx, int enabled) {
   if (!ctx) return G4_ERR_ARG;
   ctx->timing = enabled != 0;
@@ -1053,6 +1060,7 @@ static int decode_tiles_impl(g4_context* ctx, const g4_codec_list* codecs, const
     if (refs && (rc = upload_tile_refs(ctx, refs, nTiles)) != G4_OK) return rc;
     rc = decode_device(ctx, codecs, band, arena, offsets, lens, grid, status);
     if (rc != G4_OK) return rc;
+    if (ctx->asyncDevice && !refs) return G4_OK;  // enqueued; status[] is read by the caller after g4_context_synchronize
     CK(cudaMemcpyAsync(st.data(), status, size_t(nTiles) * 4, cudaMemcpyDeviceToHost, ctx->stream));
     CK(cudaStreamSynchronize(ctx->stream));
   } else if (mem_space == G4_MEM_HOST) {

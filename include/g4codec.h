@@ -26,7 +26,7 @@
 extern "C" {
 #endif
 
-#define G4_ABI_VERSION 4
+#define G4_ABI_VERSION 5
 
 /* Status codes.  G4_DECLINED is the Java `null` return of ICompressionEncoder.encode ("codec cannot or
  * should not encode this tile": all-null tile, tile too small for the predictor, singular LSOP matrix).
@@ -260,6 +260,12 @@ uint64_t g4_launch_count(const g4_context* ctx);
  * context's stream.  g4_kernel_time_ms returns the duration of the most recent launch of the decode
  * (direction 0) or encode (direction 1) kernel of `codec_kind` (G4_CODEC_COUNT = raw copy); < 0 if none. */
 int g4_context_set_timing(g4_context* ctx, int enabled);
+/* Pipelined device calls.  By default g4_decode_tiles / g4_decode_tile_list with G4_MEM_DEVICE wait for the batch and
+ * return the first failing tile's status.  With `enabled` they only ENQUEUE the batch on the context's stream and return
+ * G4_OK: `status[]` (device memory) holds the per-tile results once the stream has run (g4_context_synchronize), so a tile
+ * cache can keep several windows of tiles in flight (C/gvrs/RasterTileCache.java:339-426 reads ahead the same way with its
+ * TileDecompressionAssistant).  Host-memory calls are not affected. */
+int g4_context_set_async(g4_context* ctx, int enabled);
 /* 1 when the CUDA kernels for codec_id exist for direction (0 = decode, 1 = encode), else 0. */
 int g4_codec_supported(int codec_id, int direction);
 double g4_kernel_time_ms(g4_context* ctx, int direction, int codec_kind);

@@ -24,7 +24,7 @@ def test_library_exports_every_declared_symbol():
     for s in syms:
         assert hasattr(L, s), "libg4codec.so does not export %s" % s
     assert sorted(_lib.EXPORTS) == syms
-    assert L.g4_abi_version() == 4
+    assert L.g4_abi_version() == 5
 
 
 def test_codec_names_round_trip():

@@ -122,3 +122,42 @@ def test_contexts_on_two_devices_in_one_process(oracle):
         assert np.array_equal(g4.LsDecoder12(ctx).decode(180, 240, want), tile)
         assert np.array_equal(g4.CodecHuffman(ctx).decode(180, 240, g4.CodecHuffman(ctx).encode(0, 180, 240, tile)), tile)
         ctx.close()
+
+
+def test_pipelined_device_calls(oracle):
+    """g4_context_set_async: device batches are only enqueued; the per-tile status (device memory) is valid after the
+    context's stream has run, a malformed tile shows there instead of in the return code."""
+    import torch
+
+    import gridfour_b200 as g4
+
+    tr, tc = 60, 80
+    grid = torch.from_numpy(oracle.terrain_i32(300, 700, 2 * tr, 3 * tc)).cuda()
+    spec = g4.CodecSpecification(default=False)
+    spec.addCompressionCodec("GvrsHuffman", g4.CodecHuffman)
+    spec.addCompressionCodec("LSOP12", g4.LsEncoder12, g4.LsDecoder12)
+    master = g4.CodecMaster(spec)
+    batch = master.encodeTiles(grid, tr, tc)
+    ctx = master._context()
+    out = torch.zeros_like(grid)
+    ctx.set_async(True)
+    try:
+        for _ in range(3):  # three batches in flight on the context's stream
+            master.decodeTiles(batch, out=out)
+        ctx.synchronize()
+        torch.cuda.synchronize()
+        assert int((master.lastStatus != 0).sum()) == 0 and torch.equal(out, grid)
+        # a corrupted tile: the call itself still returns (nothing was awaited), the status tensor carries the error
+        bad = batch.arena.clone()
+        o = int(batch.offsets[4])
+        bad[o + 1] = 77  # unknown predictor / header byte
+        b2 = g4.TileBatch(bad, batch.offsets, batch.lens, batch.codec, batch.predictor, batch.status, batch.total_bytes, batch.band)
+        master.decodeTiles(b2, out=out)
+        ctx.synchronize()
+        torch.cuda.synchronize()
+        st = master.lastStatus.cpu().numpy()
+        assert st[4] < 0 and (np.delete(st, 4) == 0).all(), st
+    finally:
+        ctx.set_async(False)
+    with pytest.raises(IOError):
+        master.decodeTiles(b2, out=out)  # awaited again: the first failing tile's status is the call's result
