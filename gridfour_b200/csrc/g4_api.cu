@@ -194,7 +194,7 @@ int run_streams(g4_context* ctx, int nStreams, int capExtra, int level, int* cou
     const int nChunk = j1 - j0;
     CK(ctx->stSorted.ensure(span * 2 + 64));
     CK(ctx->stRank.ensure(span * 2 + 64));
-    CK(ctx->stTable.ensure(span * 8 + 64));
+    CK(ctx->stTable.ensure(span * 8 + 256));
     CK(ctx->stWork.ensure(size_t(nChunk) * deflate_blocks_bytes()));
     CK(cudaMemsetAsync(ctx->stCounters.p, 0, 4 * sizeof(int), ctx->stream));
     StagedArgs st{};
@@ -208,7 +208,11 @@ int run_streams(g4_context* ctx, int nStreams, int capExtra, int level, int* cou
     st.baseOff = base;
     st.sorted = ctx->stSorted.as<uint16_t>();
     st.rank = ctx->stRank.as<uint16_t>();
-    st.table = ctx->stTable.as<uint2>();
+    st.table = ctx->stTable.as<uint32_t>();
+    st.tableQ = ctx->stTable.as<uint32_t>() + (span + 16);
+    st.maxLen = 0;
+    for (int j = j0; j < j1; j++)
+      if (ctx->hostLen[size_t(j)] <= stagedMax && ctx->hostLen[size_t(j)] > st.maxLen) st.maxLen = ctx->hostLen[size_t(j)];
     st.blocks = static_cast<DeflateBlocks*>(ctx->stWork.p);
     st.capExtra = capExtra;
     st.level = level;

@@ -587,7 +587,7 @@ constexpr uint32_t kDefStagedMax = 65535;
 // Table entry: match length (9 bits, 2 = none) | distance << 9.
 G4_HD __forceinline__ uint32_t def_pack_match(int len, uint32_t dist) { return uint32_t(len) | (dist << 9); }
 
-#ifdef __CUDA_ARCH__
+#ifdef __CUDACC__
 __device__ __forceinline__ uint32_t def_load32(const uint8_t* p) {
   const uintptr_t a = reinterpret_cast<uintptr_t>(p);
   const uint32_t* q = reinterpret_cast<const uint32_t*>(a & ~uintptr_t(3));

@@ -102,7 +102,7 @@ __global__ void __launch_bounds__(kSortThreads) deflate_sort_kernel(StagedArgs a
     const uint8_t* in = a.inBuf + off;
     uint16_t* sorted = a.sorted + (off - a.baseOff);
     uint16_t* rank = a.rank + (off - a.baseOff);
-    uint16_t* hashOf = reinterpret_cast<uint16_t*>(a.table + (off - a.baseOff));  // the match table is not written yet
+    uint16_t* hashOf = reinterpret_cast<uint16_t*>(a.tableQ + (off - a.baseOff));  // the match tables are not written yet
     const uint32_t nPos = n - 2;
     {
       uint4* t4 = reinterpret_cast<uint4*>(sortTab);
@@ -184,14 +184,36 @@ __global__ void __launch_bounds__(kSortThreads) deflate_sort_kernel(StagedArgs a
   }
 }
 
-// match: one CTA per stream, one thread per slot of the sorted list (neighbouring threads hold neighbouring chain
-// positions of the same bucket: their candidate lists overlap, so the loads of a warp hit the same few lines).
-__global__ void __launch_bounds__(kThreads) deflate_match_kernel(StagedArgs a) {
+// match: the chain of the position in slot i is slots i-1, i-2, ... of the sorted list,
+// so the candidates of NEIGHBOURING slots are one sliding window.  The CTA keeps, for a window of slots, the position and
+// the 8 bytes that start there (one 64-bit key); a thread compares its key with the keys behind it: XOR + mask test per
+// candidate, no byte loads and no data-dependent inner loop.  The common prefix of two positions is exact from the keys
+// while it is shorter than 8; equal keys (prefix >= 8) go on comparing the stream itself.  zlib's candidate filter
+// (match[best_len] == scan_end ...) is the statement "common prefix > best_len", which is what the mask test decides.
+// The distance rules (MAX_DIST, position 0 = NIL) cut the chain at a candidate count that is found before the walk
+// (positions fall along the chain: binary search), so the walk itself reads keys only.
+// The results are indexed by POSITION while the threads run in slot (= hash) order: written straight to HBM that is one
+// scattered 32-byte sector per entry, and DRAM's rate of such writes -- not the matching -- set the kernel's time
+// (43 GB written + 76 GB read for 1.4 GB of input, profiles/).  The table of a stream (4 bytes per position) therefore
+// fills in shared memory and leaves with coalesced stores; streams too long for that keep the scattered store.
+// W = chain length of the level (slots that must stay behind a round), SB = slots per round, tabCap = entries of the
+// shared-memory table.
+template <int W, int SB>
+__global__ void __launch_bounds__(1024) deflate_match_window_kernel(StagedArgs a, uint32_t tabCap) {
+  extern __shared__ __align__(16) unsigned char matchSm[];
+  uint2* keyS = reinterpret_cast<uint2*>(matchSm);
+  uint32_t* filtS = reinterpret_cast<uint32_t*>(matchSm + size_t(W + SB) * 8);
+  uint16_t* posS = reinterpret_cast<uint16_t*>(matchSm + size_t(W + SB) * 12);
+  uint16_t* rankS = reinterpret_cast<uint16_t*>(matchSm + size_t(W + SB) * 14);  // SB entries: the round's own slots
+  uint32_t* tabS = reinterpret_cast<uint32_t*>(matchSm + size_t(W + SB) * 14 + size_t(SB) * 2);
   __shared__ int sj;
+  const uint32_t tid = threadIdx.x, nThr = blockDim.x;
   const DeflateLevel L = deflate_level(a.level);
+  const uint32_t maxChain = uint32_t(L.maxChain) < uint32_t(W) ? uint32_t(L.maxChain) : uint32_t(W);
+  const uint32_t quarter = uint32_t(L.maxChain) >> 2;
   for (;;) {
     __syncthreads();
-    if (threadIdx.x == 0) sj = a.jBegin + atomicAdd(a.counters + 1, 1);
+    if (tid == 0) sj = a.jBegin + atomicAdd(a.counters + 1, 1);
     __syncthreads();
     const int j = sj;
     if (j >= a.jEnd) break;
@@ -201,26 +223,246 @@ __global__ void __launch_bounds__(kThreads) deflate_match_kernel(StagedArgs a) {
     const uint8_t* in = a.inBuf + off;
     const uint16_t* sorted = a.sorted + (off - a.baseOff);
     const uint16_t* rank = a.rank + (off - a.baseOff);
-    uint2* table = a.table + (off - a.baseOff);
+    uint32_t* table = a.table + (off - a.baseOff);
+    uint32_t* tableQ = a.tableQ + (off - a.baseOff);
     const uint32_t nPos = n - 2;
-    for (uint32_t slot = threadIdx.x; slot < nPos; slot += kThreads)
-      table[sorted[slot]] = def_find_match(in, n, L, sorted, slot, rank[slot]);
+    const bool inSm = nPos <= tabCap;
+    for (uint32_t base = 0; base < nPos; base += SB) {
+      const uint32_t end = base + SB < nPos ? base + SB : nPos;
+      const uint32_t first = base >= uint32_t(W) ? base - uint32_t(W) : 0u;  // window = slots [first, end), index = slot + W - base
+      __syncthreads();
+      for (uint32_t s = first + tid; s < end; s += nThr) {
+        const uint32_t p = sorted[s];
+        if (s >= base) rankS[s - base] = rank[s];
+        const uintptr_t ad = reinterpret_cast<uintptr_t>(in + p);
+        const uint32_t* q = reinterpret_cast<const uint32_t*>(ad & ~uintptr_t(3));
+        const uint32_t sh = uint32_t(ad & 3u) * 8u;
+        const uint32_t w0 = q[0], w1 = q[1], w2 = q[2];  // in[] is padded with 16 zero bytes past n
+        const uint32_t kl = __funnelshift_r(w0, w1, sh), kh = __funnelshift_r(w1, w2, sh);
+        posS[s + W - base] = uint16_t(p);
+        keyS[s + W - base] = make_uint2(kl, kh);
+        // 32-bit filter word.  Inside a hash bucket, byte 1 fixes byte 2 and the low five bits of byte 0 (the hash is
+        // b0 << 10 ^ b1 << 5 ^ b2, 15 bits), so {b0 >> 5, b1} is the whole 3-byte prefix; then bytes 3, 4 and five bits
+        // of byte 5.  Fields in byte order: a mask over the low bits tests "at least that many bytes in common".
+        filtS[s + W - base] = ((kl >> 5) & 7u) | (((kl >> 8) & 0xffu) << 3) | ((kl >> 24) << 11) | ((kh & 0xffu) << 19) | (((kh >> 8) & 31u) << 27);
+      }
+      __syncthreads();
+      for (uint32_t slot = base + tid; slot < end; slot += nThr) {
+        const uint32_t li = slot + W - base;
+        const uint2 my = keyS[li];
+        const uint32_t p = posS[li];
+        const uint32_t r = rankS[slot - base];
+        uint32_t nCand = r < maxChain ? r : maxChain;
+        const uint32_t lookahead = n - p;
+        const int maxLen = lookahead < uint32_t(kDefMaxMatch) ? int(lookahead) : kDefMaxMatch;
+        const int niceMatch = uint32_t(L.niceLength) > lookahead ? int(lookahead) : L.niceLength;
+        // the first candidate may sit at distance MAX_DIST exactly, later ones must be nearer; position 0 doubles as NIL
+        const uint32_t limit = p > uint32_t(kDefMaxDist) ? p - uint32_t(kDefMaxDist) : 0u;
+        if (nCand && uint32_t(posS[li - nCand]) <= limit) {
+          uint32_t lo = 0, hi = nCand;  // pos(lo) > limit (lo = 0: the slot itself), pos(hi) <= limit
+          while (hi - lo > 1u) {
+            const uint32_t mid = (lo + hi) >> 1;
+            if (uint32_t(posS[li - mid]) > limit) lo = mid; else hi = mid;
+          }
+          nCand = (lo == 0u && limit != 0u && uint32_t(posS[li - 1]) == limit) ? 1u : lo;
+        }
+        int bestLen = kDefMinMatch - 1;
+        uint32_t bestDist = p;
+        uint32_t mLo = 0x00ffffffu, mHi = 0u;  // bytes 0 .. bestLen of the key
+        const uint32_t myF = filtS[li];
+        uint32_t mF = 0x7ffu;  // the same bytes in the filter word (a necessary condition once bestLen reaches 5)
+        bool done = false;
+        // one candidate, exactly: true when the walk is over (nice match)
+        auto exact = [&](uint32_t k) -> bool {
+          const uint2 ck = keyS[li - k];
+          const uint32_t xl = ck.x ^ my.x, xh = ck.y ^ my.y;
+          if (((xl & mLo) | (xh & mHi)) != 0u) return false;
+          const uint32_t cur = posS[li - k];
+          int len;
+          if (xl) len = (__ffs(int(xl)) - 1) >> 3;
+          else if (xh) len = 4 + ((__ffs(int(xh)) - 1) >> 3);
+          else {
+            len = 8;
+            const uint8_t* scan = in + p;
+            const uint8_t* match = in + cur;
+            if (bestLen >= 8 && (match[bestLen] != scan[bestLen] || match[bestLen - 1] != scan[bestLen - 1])) return false;
+            bool differ = false;
+            while (len + 4 <= maxLen) {
+              const uint32_t x = def_load32(scan + len) ^ def_load32(match + len);
+              if (x) { len += (__ffs(int(x)) - 1) >> 3; differ = true; break; }
+              len += 4;
+            }
+            if (!differ)
+              while (len < maxLen && scan[len] == match[len]) len++;
+          }
+          if (len > maxLen) len = maxLen;
+          if (len > bestLen) {
+            bestLen = len;
+            bestDist = p - cur;
+            if (len >= niceMatch) { done = true; return true; }
+            const uint32_t nb8 = uint32_t(len + 1) * 8u;  // bits of the key that a better candidate must share
+            const unsigned long long m64 = nb8 >= 64u ? ~0ull : (1ull << nb8) - 1ull;
+            mLo = uint32_t(m64);
+            mHi = uint32_t(m64 >> 32);
+            const uint32_t fb = uint32_t(len) * 8u - 5u;  // 11 + 8 (len - 2) filter bits
+            mF = fb >= 32u ? 0xffffffffu : (1u << fb) - 1u;
+          }
+          return false;
+        };
+        // The walk: the first candidates one at a time (every lane of the warp finds its first matches there), then
+        // blocks of up to 32 candidates: a scan over the filter words (one 32-bit load and two logic operations per
+        // candidate, no branch) marks the candidates that may share more than bestLen bytes, and the marked ones are
+        // then taken nearest first on the 64-bit keys -- all lanes of the warp together, instead of every lane
+        // stopping the warp's scan for its own candidate.  (The mark uses bestLen of the block's start: a superset.)
+        auto walk = [&](uint32_t k0, uint32_t k1) {
+          uint32_t k = k0;
+          for (; k <= k1 && k < k0 + 4u; k++)
+            if (exact(k)) return;
+          while (k <= k1) {
+            const uint32_t left = k1 - k + 1u;
+            uint32_t pend = 0;
+            if (left >= 32u) {
+#pragma unroll
+              for (uint32_t q = 0; q < 32u; q += 4u) {
+                const uint32_t f0 = filtS[li - k - q], f1 = filtS[li - k - q - 1u], f2 = filtS[li - k - q - 2u], f3 = filtS[li - k - q - 3u];
+                if (((f0 ^ myF) & mF) == 0u) pend |= 1u << q;
+                if (((f1 ^ myF) & mF) == 0u) pend |= 2u << q;
+                if (((f2 ^ myF) & mF) == 0u) pend |= 4u << q;
+                if (((f3 ^ myF) & mF) == 0u) pend |= 8u << q;
+              }
+            } else {
+              for (uint32_t q = 0; q < left; q++)
+                if (((filtS[li - k - q] ^ myF) & mF) == 0u) pend |= 1u << q;
+            }
+            while (pend) {
+              const uint32_t q = uint32_t(__ffs(int(pend))) - 1u;
+              pend &= pend - 1u;
+              if (exact(k + q)) return;
+            }
+            k += left >= 32u ? 32u : left;
+          }
+        };
+        walk(1u, nCand < quarter ? nCand : quarter);
+        const uint32_t quarterEntry = def_pack_match(bestLen, bestDist);  // = the full result when the chain ends here
+        if (!done && nCand > quarter) walk(quarter + 1u, nCand);
+        uint32_t full = def_pack_match(bestLen, bestDist);
+        if (full != quarterEntry) { tableQ[p] = quarterEntry; full |= 0x80000000u; }  // rare: the scattered store stays
+        if (inSm) tabS[p] = full; else table[p] = full;
+      }
+    }
+    if (inSm) {
+      __syncthreads();
+      uint4* dst = reinterpret_cast<uint4*>(table);  // 64-byte aligned: stream offsets are multiples of 16 positions
+      const uint4* src = reinterpret_cast<const uint4*>(tabS);
+      for (uint32_t i = tid; i < (nPos + 3u) / 4u; i += nThr) dst[i] = src[i];
+    }
   }
 }
 
-// decide: one THREAD per stream runs the table-driven lazy loop and leaves the symbol list in the (now dead) sorted /
-// rank arrays of the stream: distances where the positions were, length codes / literals over the ranks.
-__global__ void __launch_bounds__(32) deflate_decide_kernel(StagedArgs a) {
-  // (Tried: software prefetch of the table / input a few hundred bytes ahead -- no change; one working lane out of 4 or 8
-  // so that the same streams occupy more warps -- 44 + 11 ms instead of 29 + 18 ms for the two launches of an encode pass.)
+// decide: one THREAD per stream runs the table-driven lazy loop (deflate_decide_table in g4_deflate_enc.cuh is the host
+// form) and leaves the symbol list in the (now dead) sorted / rank arrays of the stream.  The table entries and the input bytes of a
+// stream come through a per-thread shared-memory ring filled by cp.async (16 positions per chunk, kDecRing chunks in
+// flight), so that a step of the lazy loop costs a shared-memory read instead of a DRAM round trip that the 31 other
+// lanes of the warp wait for as well.
+constexpr int kDecChunk = 16, kDecRing = 4, kDecRow = kDecChunk * kDecRing;  // chunk: 16 entries = 64 bytes + 16 input bytes
+__global__ void __launch_bounds__(32) deflate_decide_ring_kernel(StagedArgs a) {
+  __shared__ __align__(16) uint32_t tabS[32][kDecRow + 4];     // +4 entries: rows 16 bytes apart in the banks
+  __shared__ __align__(16) uint8_t byteS[32][kDecRow + 16];
+  const int lane = threadIdx.x;
+  const DeflateLevel L = deflate_level(a.level);
+  const uint32_t tabBase = uint32_t(__cvta_generic_to_shared(&tabS[lane][0]));
+  const uint32_t byteBase = uint32_t(__cvta_generic_to_shared(&byteS[lane][0]));
   for (;;) {
     const int j = a.jBegin + atomicAdd(a.counters + 2, 1);
     if (j >= a.jEnd) break;
     const uint32_t n = a.inLen[j];
     if (n == 0 || n > kDefStagedMax) continue;
     const uint64_t off = a.inOff[j];
-    deflate_decide_table(a.inBuf + off, n, a.level, a.table + (off - a.baseOff), a.sorted + (off - a.baseOff),
-                         reinterpret_cast<uint8_t*>(a.rank + (off - a.baseOff)), a.blocks + (j - a.jBegin));
+    const uint8_t* in = a.inBuf + off;
+    const uint32_t* table = a.table + (off - a.baseOff);
+    const uint32_t* tableQ = a.tableQ + (off - a.baseOff);
+    uint16_t* symDist = a.sorted + (off - a.baseOff);
+    uint8_t* symLc = reinterpret_cast<uint8_t*>(a.rank + (off - a.baseOff));
+    DeflateBlocks* B = a.blocks + (j - a.jBegin);
+    const uint32_t nChunks = (n + uint32_t(kDecChunk) - 1u) / uint32_t(kDecChunk);
+    uint32_t fetched = 0, curChunk = 0xffffffffu;
+    uint32_t strstart = 0, matchStart = 0, prevMatch = 0, k = 0, inBlock = 0, nBlocks = 0;
+    int matchLength = kDefMinMatch - 1, prevLength = kDefMinMatch - 1;
+    bool matchAvailable = false;
+    uint32_t lastByte = 0;
+    auto tally = [&](uint32_t dist, uint32_t lc) -> bool {
+      symDist[k] = uint16_t(dist);
+      symLc[k] = uint8_t(lc);
+      k++;
+      return ++inBlock == uint32_t(kDefLitBufSize - 1);
+    };
+    auto flush = [&]() {
+      B->symEnd[nBlocks] = k;
+      B->posEnd[nBlocks] = strstart;
+      nBlocks++;
+      inBlock = 0;
+    };
+    while (strstart < n) {
+      const uint32_t c = strstart / uint32_t(kDecChunk);
+      if (c != curChunk) {
+        // chunks [c, c + kDecRing) must be in flight or landed; chunks skipped by a long match are committed empty.
+        // After a skip the ring slots about to be refilled may still be the target of copies in flight (two cp.async
+        // to one address are not ordered): drain first.
+        if (c != curChunk + 1u) asm volatile("cp.async.wait_group 0;" ::: "memory");
+        while (fetched < c + uint32_t(kDecRing)) {
+          if (fetched >= c && fetched < nChunks) {
+            const uint32_t slot = fetched % uint32_t(kDecRing);
+            const char* tsrc = reinterpret_cast<const char*>(table + size_t(fetched) * kDecChunk);
+            const uint32_t tdst = tabBase + slot * uint32_t(kDecChunk * 4);
+#pragma unroll
+            for (int q = 0; q < kDecChunk * 4 / 16; q++)
+              asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"(tdst + q * 16), "l"(tsrc + q * 16) : "memory");
+            asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"(byteBase + slot * uint32_t(kDecChunk)),
+                         "l"(in + size_t(fetched) * kDecChunk) : "memory");
+          }
+          asm volatile("cp.async.commit_group;" ::: "memory");
+          fetched++;
+        }
+        asm volatile("cp.async.wait_group %0;" ::"n"(kDecRing - 1) : "memory");
+        curChunk = c;
+      }
+      const uint32_t ri = strstart % uint32_t(kDecRow);
+      const uint32_t curByte = byteS[lane][ri];
+      const uint32_t lookahead = n - strstart;
+      prevLength = matchLength;
+      prevMatch = matchStart;
+      matchLength = kDefMinMatch - 1;
+      if (lookahead >= uint32_t(kDefMinMatch) && prevLength < L.maxLazy) {
+        uint32_t w = tabS[lane][ri];
+        if (w >> 31) w = prevLength >= L.goodLength ? tableQ[strstart] : (w & 0x7fffffffu);  // rare: the quarter chain differs
+        const int len = int(w & 0x1ffu);
+        if (len > prevLength) {
+          matchLength = len;
+          matchStart = strstart - (w >> 9);
+          if (matchLength == kDefMinMatch && strstart - matchStart > uint32_t(kDefTooFar)) matchLength = kDefMinMatch - 1;
+        }
+      }
+      if (prevLength >= kDefMinMatch && matchLength <= prevLength) {
+        const bool bflush = tally(strstart - 1 - prevMatch, uint32_t(prevLength - kDefMinMatch));
+        strstart += uint32_t(prevLength - 1);
+        matchAvailable = false;
+        matchLength = kDefMinMatch - 1;
+        if (bflush) flush();
+      } else if (matchAvailable) {
+        const bool bflush = tally(0, lastByte);
+        if (bflush) flush();
+        strstart++;
+        lastByte = curByte;
+      } else {
+        matchAvailable = true;
+        strstart++;
+        lastByte = curByte;
+      }
+    }
+    if (matchAvailable) tally(0, lastByte);
+    flush();
+    B->nBlocks = nBlocks;
+    asm volatile("cp.async.wait_group 0;" ::: "memory");  // nothing of this stream may land in the next one's ring
   }
 }
 
@@ -666,16 +908,35 @@ cudaError_t launch_deflate_staged(const StagedArgs& a, int smCount, cudaStream_t
   deflate_sort_kernel<<<sortCtas, kSortThreads, kDefWSize * 2, s>>>(a);
   cudaError_t e = cudaGetLastError();
   if (e != cudaSuccess) return e;
-  static const int matchPerSm = getenv("G4_MATCH_CTAS_PER_SM") ? atoi(getenv("G4_MATCH_CTAS_PER_SM")) : 8;
-  const int matchCtas0 = smCount * (matchPerSm >= 1 && matchPerSm <= 8 ? matchPerSm : 8);
-  const int matchCtas = nChunk < smCount * 8 ? nChunk : smCount * 8;
-  deflate_match_kernel<<<nChunk < matchCtas0 ? nChunk : matchCtas0, kThreads, 0, s>>>(a);
+  // match: shared memory = the candidate window + the stream's table (4 bytes per position) when that fits
+  {
+    const bool deep = deflate_level(a.level).maxChain > 128;
+    const size_t win = deep ? size_t(4096 + 2048) * 14 + 2048 * 2 : size_t(128 + 1920) * 14 + 1920 * 2;
+    const size_t smMax = 227 * 1024 - 2048;
+    size_t tabBytes = (size_t(a.maxLen) * 4 + 15) & ~size_t(15);
+    if (win + tabBytes > smMax) tabBytes = 0;  // too long: scattered stores
+    const size_t sm = win + tabBytes;
+    int perSm = int(smMax / sm);
+    if (perSm > 8) perSm = 8;
+    if (deep && perSm > 2) perSm = 2;
+    const int threads = perSm == 1 ? 1024 : perSm <= 3 ? 512 : 256;
+    const int ctas = nChunk < smCount * perSm ? nChunk : smCount * perSm;
+    static std::atomic<uint64_t> attrW{0};
+    ea = once_per_device(attrW, [] {
+      cudaError_t e1 = cudaFuncSetAttribute(deflate_match_window_kernel<128, 1920>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024 - 2048);
+      if (e1 != cudaSuccess) return e1;
+      return cudaFuncSetAttribute(deflate_match_window_kernel<4096, 2048>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024 - 2048);
+    });
+    if (ea != cudaSuccess) return ea;
+    if (deep) deflate_match_window_kernel<4096, 2048><<<ctas, threads, sm, s>>>(a, uint32_t(tabBytes / 4));
+    else deflate_match_window_kernel<128, 1920><<<ctas, threads, sm, s>>>(a, uint32_t(tabBytes / 4));
+  }
   e = cudaGetLastError();
   if (e != cudaSuccess) return e;
-  deflate_decide_kernel<<<(nChunk + 31) / 32, 32, 0, s>>>(a);
+  deflate_decide_ring_kernel<<<(nChunk + 31) / 32, 32, 0, s>>>(a);
   e = cudaGetLastError();
   if (e != cudaSuccess) return e;
-  deflate_emit_kernel<<<matchCtas, kThreads, 0, s>>>(a);
+  deflate_emit_kernel<<<nChunk < smCount * 8 ? nChunk : smCount * 8, kThreads, 0, s>>>(a);
   return cudaGetLastError();
 }
 cudaError_t launch_deflate_m32_size(const EncodeArgs& a, uint32_t* inLen, int nCtas, cudaStream_t s) {

@@ -128,7 +128,9 @@ struct StagedArgs {
   uint64_t baseOff;
   uint16_t* sorted;   // positions ordered by (hash, position)
   uint16_t* rank;     // number of earlier positions in the slot's hash bucket
-  uint2* table;       // per position: longest match with the full / quarter chain
+  uint32_t* table;    // per position: longest match with the full chain (def_pack_match; bit 31: tableQ differs)
+  uint32_t* tableQ;   // per position, written only where it differs: longest match with the quarter chain
+  uint32_t maxLen;    // longest staged stream of the chunk (sizes the match kernel's shared-memory table)
   DeflateBlocks* blocks;  // per stream of the chunk: block boundaries (decide kernel -> emit kernel), deflate_blocks_bytes() each
   int capExtra, level;
   int* counters;      // 4 ints, zeroed before launch
