@@ -365,10 +365,18 @@ __global__ void __launch_bounds__(1024) deflate_match_window_kernel(StagedArgs a
 // flight), so that a step of the lazy loop costs a shared-memory read instead of a DRAM round trip that the 31 other
 // lanes of the warp wait for as well.
 constexpr int kDecChunk = 16, kDecRing = 4, kDecRow = kDecChunk * kDecRing;  // chunk: 16 entries = 64 bytes + 16 input bytes
+// LANES streams per warp: the loop is a chain of dependent instructions (about 80 per step with the ring upkeep), so
+// what it needs is warps per scheduler, not lanes per warp.
+template <int LANES>
 __global__ void __launch_bounds__(32) deflate_decide_ring_kernel(StagedArgs a) {
-  __shared__ __align__(16) uint32_t tabS[32][kDecRow + 4];     // +4 entries: rows 16 bytes apart in the banks
-  __shared__ __align__(16) uint8_t byteS[32][kDecRow + 16];
+  __shared__ __align__(16) uint32_t tabS[LANES][kDecRow + 4];  // +4 entries: rows 16 bytes apart in the banks
+  __shared__ __align__(16) uint8_t byteS[LANES][kDecRow + 16];
+  // symbols leave 16 bytes at a time (8 distances / 16 length-or-literal bytes): a warp's scalar stores are 32 L2
+  // transactions each, and at two per step they, not the loop, set the kernel's time
+  __shared__ __align__(16) uint16_t distS[LANES][8 + 8];
+  __shared__ __align__(16) uint8_t lcS[LANES][16 + 16];
   const int lane = threadIdx.x;
+  if (lane >= LANES) return;
   const DeflateLevel L = deflate_level(a.level);
   const uint32_t tabBase = uint32_t(__cvta_generic_to_shared(&tabS[lane][0]));
   const uint32_t byteBase = uint32_t(__cvta_generic_to_shared(&byteS[lane][0]));
@@ -391,9 +399,13 @@ __global__ void __launch_bounds__(32) deflate_decide_ring_kernel(StagedArgs a) {
     bool matchAvailable = false;
     uint32_t lastByte = 0;
     auto tally = [&](uint32_t dist, uint32_t lc) -> bool {
-      symDist[k] = uint16_t(dist);
-      symLc[k] = uint8_t(lc);
+      distS[lane][k & 7u] = uint16_t(dist);
+      lcS[lane][k & 15u] = uint8_t(lc);
       k++;
+      if ((k & 7u) == 0u) {
+        *reinterpret_cast<uint4*>(symDist + (k - 8u)) = *reinterpret_cast<const uint4*>(&distS[lane][0]);
+        if ((k & 15u) == 0u) *reinterpret_cast<uint4*>(symLc + (k - 16u)) = *reinterpret_cast<const uint4*>(&lcS[lane][0]);
+      }
       return ++inBlock == uint32_t(kDefLitBufSize - 1);
     };
     auto flush = [&]() {
@@ -460,6 +472,8 @@ __global__ void __launch_bounds__(32) deflate_decide_ring_kernel(StagedArgs a) {
       }
     }
     if (matchAvailable) tally(0, lastByte);
+    for (uint32_t i = k & ~7u; i < k; i++) symDist[i] = distS[lane][i & 7u];
+    for (uint32_t i = k & ~15u; i < k; i++) symLc[i] = lcS[lane][i & 15u];
     flush();
     B->nBlocks = nBlocks;
     asm volatile("cp.async.wait_group 0;" ::: "memory");  // nothing of this stream may land in the next one's ring
@@ -933,7 +947,11 @@ cudaError_t launch_deflate_staged(const StagedArgs& a, int smCount, cudaStream_t
   }
   e = cudaGetLastError();
   if (e != cudaSuccess) return e;
-  deflate_decide_ring_kernel<<<(nChunk + 31) / 32, 32, 0, s>>>(a);
+  static const int decLanes = getenv("G4_DECIDE_LANES") ? atoi(getenv("G4_DECIDE_LANES")) : 32;
+  if (decLanes >= 32) deflate_decide_ring_kernel<32><<<(nChunk + 31) / 32, 32, 0, s>>>(a);
+  else if (decLanes >= 16) deflate_decide_ring_kernel<16><<<(nChunk + 15) / 16, 32, 0, s>>>(a);
+  else if (decLanes >= 8) deflate_decide_ring_kernel<8><<<(nChunk + 7) / 8, 32, 0, s>>>(a);
+  else deflate_decide_ring_kernel<4><<<(nChunk + 3) / 4, 32, 0, s>>>(a);
   e = cudaGetLastError();
   if (e != cudaSuccess) return e;
   deflate_emit_kernel<<<nChunk < smCount * 8 ? nChunk : smCount * 8, kThreads, 0, s>>>(a);
