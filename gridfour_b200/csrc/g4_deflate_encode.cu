@@ -71,15 +71,14 @@ __global__ void __launch_bounds__(32) deflate_streams_kernel(StreamArgs a) {
 
 // ---- staged form for streams of at most kDefStagedMax bytes (g4_deflate_enc.cuh, "Staged form") ------------------------
 // sort: one 128-thread CTA per stream, bucket cursors (32768 x uint16 = 64 KB) in shared memory.
-//   pass 1 (all threads)  hash of every position, parked in rank[]; bucket counts by shared-memory atomics (order-free),
+//   pass 1 (all threads)  hash of every position, parked in a scratch array; bucket counts by shared-memory atomics,
 //   scan   (all threads)  counts -> bucket starts,
 //   pass 2 (warp 0)       slots in stream order: positions are taken 32 at a time; __match_any_sync groups the lanes
 //                         of a chunk by hash, a position's slot is (bucket cursor) + (lanes below it with the same
 //                         hash) and the highest lane of every group advances the cursor by the group's size.  Eight
-//                         chunks of hashes are loaded and grouped ahead of the serial cursor updates; the hash is
-//                         parked in rank[slot],
-//   pass 3 (all threads)  rank of a slot = slot - start of its bucket; after pass 2 the cursor of bucket h-1 is the start
-//                         of bucket h.
+//                         chunks of hashes are loaded and grouped ahead of the serial cursor updates.
+// The list alone is the result: a slot's bucket and its place in it are read off the (hash, position) order by the match
+// kernel, so no rank array is written (the scattered 2-byte stores are what this kernel's time is made of).
 // (Tried and dropped: per-position shared-memory atomics instead of the grouped update, with a fix-up of the order
 // inside a chunk -- the two extra passes over HBM cost more than the grouping, 64 ms instead of 41 ms.)
 constexpr int kSortThreads = 128;
@@ -101,7 +100,6 @@ __global__ void __launch_bounds__(kSortThreads) deflate_sort_kernel(StagedArgs a
     const uint64_t off = a.inOff[j];
     const uint8_t* in = a.inBuf + off;
     uint16_t* sorted = a.sorted + (off - a.baseOff);
-    uint16_t* rank = a.rank + (off - a.baseOff);
     uint16_t* hashOf = reinterpret_cast<uint16_t*>(a.tableQ + (off - a.baseOff));  // the match tables are not written yet
     const uint32_t nPos = n - 2;
     {
@@ -168,18 +166,11 @@ __global__ void __launch_bounds__(kSortThreads) deflate_sort_kernel(StagedArgs a
             const uint32_t cur = sortTab[h[c]];
             const uint32_t slot = cur + uint32_t(__popc(m & ltMask));
             sorted[slot] = uint16_t(base + uint32_t(c) * 32u + uint32_t(lane));
-            rank[slot] = uint16_t(h[c]);  // parked: pass 3 turns it into the rank
             if ((m >> lane) == 1u) sortTab[h[c]] = uint16_t(cur + __popc(m));
           }
           __syncwarp();
         }
       }
-    }
-    __syncthreads();
-#pragma unroll 8
-    for (uint32_t slot = tid; slot < nPos; slot += kSortThreads) {
-      const uint32_t hh = rank[slot];
-      rank[slot] = uint16_t(slot - (hh ? uint32_t(sortTab[hh - 1]) : 0u));
     }
   }
 }
@@ -203,9 +194,8 @@ __global__ void __launch_bounds__(1024) deflate_match_window_kernel(StagedArgs a
   extern __shared__ __align__(16) unsigned char matchSm[];
   uint2* keyS = reinterpret_cast<uint2*>(matchSm);
   uint32_t* filtS = reinterpret_cast<uint32_t*>(matchSm + size_t(W + SB) * 8);
-  uint16_t* posS = reinterpret_cast<uint16_t*>(matchSm + size_t(W + SB) * 12);
-  uint16_t* rankS = reinterpret_cast<uint16_t*>(matchSm + size_t(W + SB) * 14);  // SB entries: the round's own slots
-  uint32_t* tabS = reinterpret_cast<uint32_t*>(matchSm + size_t(W + SB) * 14 + size_t(SB) * 2);
+  uint32_t* hpS = reinterpret_cast<uint32_t*>(matchSm + size_t(W + SB) * 12);  // hash << 16 | position: rises with the slot
+  uint32_t* tabS = reinterpret_cast<uint32_t*>(matchSm + size_t(W + SB) * 16);
   __shared__ int sj;
   const uint32_t tid = threadIdx.x, nThr = blockDim.x;
   const DeflateLevel L = deflate_level(a.level);
@@ -222,7 +212,6 @@ __global__ void __launch_bounds__(1024) deflate_match_window_kernel(StagedArgs a
     const uint64_t off = a.inOff[j];
     const uint8_t* in = a.inBuf + off;
     const uint16_t* sorted = a.sorted + (off - a.baseOff);
-    const uint16_t* rank = a.rank + (off - a.baseOff);
     uint32_t* table = a.table + (off - a.baseOff);
     uint32_t* tableQ = a.tableQ + (off - a.baseOff);
     const uint32_t nPos = n - 2;
@@ -233,13 +222,12 @@ __global__ void __launch_bounds__(1024) deflate_match_window_kernel(StagedArgs a
       __syncthreads();
       for (uint32_t s = first + tid; s < end; s += nThr) {
         const uint32_t p = sorted[s];
-        if (s >= base) rankS[s - base] = rank[s];
         const uintptr_t ad = reinterpret_cast<uintptr_t>(in + p);
         const uint32_t* q = reinterpret_cast<const uint32_t*>(ad & ~uintptr_t(3));
         const uint32_t sh = uint32_t(ad & 3u) * 8u;
         const uint32_t w0 = q[0], w1 = q[1], w2 = q[2];  // in[] is padded with 16 zero bytes past n
         const uint32_t kl = __funnelshift_r(w0, w1, sh), kh = __funnelshift_r(w1, w2, sh);
-        posS[s + W - base] = uint16_t(p);
+        hpS[s + W - base] = (((((kl & 0xffu) << 10) ^ (((kl >> 8) & 0xffu) << 5) ^ ((kl >> 16) & 0xffu)) & uint32_t(kDefHashMask)) << 16) | p;
         keyS[s + W - base] = make_uint2(kl, kh);
         // 32-bit filter word.  Inside a hash bucket, byte 1 fixes byte 2 and the low five bits of byte 0 (the hash is
         // b0 << 10 ^ b1 << 5 ^ b2, 15 bits), so {b0 >> 5, b1} is the whole 3-byte prefix; then bytes 3, 4 and five bits
@@ -250,21 +238,24 @@ __global__ void __launch_bounds__(1024) deflate_match_window_kernel(StagedArgs a
       for (uint32_t slot = base + tid; slot < end; slot += nThr) {
         const uint32_t li = slot + W - base;
         const uint2 my = keyS[li];
-        const uint32_t p = posS[li];
-        const uint32_t r = rankS[slot - base];
-        uint32_t nCand = r < maxChain ? r : maxChain;
+        const uint32_t hp = hpS[li];
+        const uint32_t p = hp & 0xffffu;
         const uint32_t lookahead = n - p;
         const int maxLen = lookahead < uint32_t(kDefMaxMatch) ? int(lookahead) : kDefMaxMatch;
         const int niceMatch = uint32_t(L.niceLength) > lookahead ? int(lookahead) : L.niceLength;
-        // the first candidate may sit at distance MAX_DIST exactly, later ones must be nearer; position 0 doubles as NIL
+        // Candidates: the slots behind this one that hold the same hash and a position above `limit` (nearer than
+        // MAX_DIST; position 0 doubles as NIL), at most maxChain of them.  (hash, position) rises with the slot, so they
+        // are the run that ends here: lower bound by binary search.  zlib's first candidate may sit at MAX_DIST exactly.
         const uint32_t limit = p > uint32_t(kDefMaxDist) ? p - uint32_t(kDefMaxDist) : 0u;
-        if (nCand && uint32_t(posS[li - nCand]) <= limit) {
-          uint32_t lo = 0, hi = nCand;  // pos(lo) > limit (lo = 0: the slot itself), pos(hi) <= limit
+        const uint32_t want = (hp & 0xffff0000u) | (limit + 1u);
+        uint32_t nCand = slot < maxChain ? slot : maxChain;
+        if (nCand && hpS[li - nCand] < want) {
+          uint32_t lo = 0, hi = nCand;  // entry(lo) >= want (lo = 0: the slot itself), entry(hi) < want
           while (hi - lo > 1u) {
             const uint32_t mid = (lo + hi) >> 1;
-            if (uint32_t(posS[li - mid]) > limit) lo = mid; else hi = mid;
+            if (hpS[li - mid] >= want) lo = mid; else hi = mid;
           }
-          nCand = (lo == 0u && limit != 0u && uint32_t(posS[li - 1]) == limit) ? 1u : lo;
+          nCand = (lo == 0u && limit != 0u && hpS[li - 1] == want - 1u) ? 1u : lo;
         }
         int bestLen = kDefMinMatch - 1;
         uint32_t bestDist = p;
@@ -277,7 +268,7 @@ __global__ void __launch_bounds__(1024) deflate_match_window_kernel(StagedArgs a
           const uint2 ck = keyS[li - k];
           const uint32_t xl = ck.x ^ my.x, xh = ck.y ^ my.y;
           if (((xl & mLo) | (xh & mHi)) != 0u) return false;
-          const uint32_t cur = posS[li - k];
+          const uint32_t cur = hpS[li - k] & 0xffffu;
           int len;
           if (xl) len = (__ffs(int(xl)) - 1) >> 3;
           else if (xh) len = 4 + ((__ffs(int(xh)) - 1) >> 3);
@@ -331,7 +322,17 @@ __global__ void __launch_bounds__(1024) deflate_match_window_kernel(StagedArgs a
                 if (((f3 ^ myF) & mF) == 0u) pend |= 8u << q;
               }
             } else {
-              for (uint32_t q = 0; q < left; q++)
+              uint32_t q = 0;
+              for (; q + 4u <= left; q += 4u) {
+                const uint32_t f0 = filtS[li - k - q], f1 = filtS[li - k - q - 1u], f2 = filtS[li - k - q - 2u], f3 = filtS[li - k - q - 3u];
+                uint32_t hit = 0;
+                if (((f0 ^ myF) & mF) == 0u) hit |= 1u;
+                if (((f1 ^ myF) & mF) == 0u) hit |= 2u;
+                if (((f2 ^ myF) & mF) == 0u) hit |= 4u;
+                if (((f3 ^ myF) & mF) == 0u) hit |= 8u;
+                pend |= hit << q;
+              }
+              for (; q < left; q++)
                 if (((filtS[li - k - q] ^ myF) & mF) == 0u) pend |= 1u << q;
             }
             while (pend) {
@@ -925,7 +926,7 @@ cudaError_t launch_deflate_staged(const StagedArgs& a, int smCount, cudaStream_t
   // match: shared memory = the candidate window + the stream's table (4 bytes per position) when that fits
   {
     const bool deep = deflate_level(a.level).maxChain > 128;
-    const size_t win = deep ? size_t(4096 + 2048) * 14 + 2048 * 2 : size_t(128 + 1920) * 14 + 1920 * 2;
+    const size_t win = deep ? size_t(4096 + 2048) * 16 : size_t(128 + 1920) * 16;
     const size_t smMax = 227 * 1024 - 2048;
     size_t tabBytes = (size_t(a.maxLen) * 4 + 15) & ~size_t(15);
     if (win + tabBytes > smMax) tabBytes = 0;  // too long: scattered stores
