@@ -107,11 +107,21 @@ __global__ void __launch_bounds__(kSortThreads) deflate_sort_kernel(StagedArgs a
       for (int i = tid; i < kDefWSize * 2 / 16; i += kSortThreads) t4[i] = make_uint4(0, 0, 0, 0);
     }
     __syncthreads();
-#pragma unroll 8
-    for (uint32_t p = tid; p < nPos; p += kSortThreads) {
-      const uint32_t hh = def_hash3(in + p);
-      hashOf[p] = uint16_t(hh);
-      atomicAdd(&t32[hh >> 1], (hh & 1u) ? 0x10000u : 1u);
+    {  // four positions per thread and step from two aligned words (the stream starts 16-byte aligned and is zero-padded)
+      const uint32_t* in32 = reinterpret_cast<const uint32_t*>(in);
+      uint2* hash4 = reinterpret_cast<uint2*>(hashOf);
+#pragma unroll 4
+      for (uint32_t g = tid; g * 4u < nPos; g += kSortThreads) {
+        const uint32_t w0 = __ldg(in32 + g), w1 = __ldg(in32 + g + 1);
+        uint32_t hh[4];
+#pragma unroll
+        for (int i = 0; i < 4; i++) {
+          const uint32_t x = i ? __funnelshift_r(w0, w1, 8u * uint32_t(i)) : w0;
+          hh[i] = (((x & 0xffu) << 10) ^ (((x >> 8) & 0xffu) << 5) ^ ((x >> 16) & 0xffu)) & uint32_t(kDefHashMask);
+          if (g * 4u + uint32_t(i) < nPos) atomicAdd(&t32[hh[i] >> 1], (hh[i] & 1u) ? 0x10000u : 1u);
+        }
+        hash4[g] = make_uint2(hh[0] | (hh[1] << 16), hh[2] | (hh[3] << 16));
+      }
     }
     __syncthreads();
     {  // exclusive scan of the 32768 counts: every warp scans a quarter (two counts per lane and step), then the
@@ -481,24 +491,38 @@ __global__ void __launch_bounds__(32) deflate_decide_ring_kernel(StagedArgs a) {
   }
 }
 
-// emit: one CTA per stream.  Per block: symbol histogram by shared-memory atomics, trees.c on one thread over
-// shared-memory trees (def_plan_block), header by that thread, then the symbols of the block in parallel -- every
-// thread sizes four consecutive symbols, a block scan gives the bit offsets, and the codes are OR-ed into the
-// shared-memory bit window (g4_bitpack.cuh).  Adler-32 by a block reduction (s2 = n + sum (n-i) b_i).
+// emit: one CTA per stream.  The blocks of a stream are independent until their bits are laid end to end, and what a
+// block costs is trees.c on ONE thread (build_tree's heap is a chain of dependent shared-memory accesses: 60 % of the
+// kernel's samples sat at the barrier behind it).  So up to kEmitPar blocks are planned at once: their symbol
+// histograms by all threads, then one thread per block runs def_plan_block and renders the block header (type bits +
+// the three trees) into a private buffer; after that the blocks are emitted in order -- header words copied in
+// parallel, symbols in parallel (every thread sizes four consecutive symbols, a block scan gives the bit offsets, the
+// codes are OR-ed into the shared-memory bit window of g4_bitpack.cuh).  Adler-32 by a block reduction
+// (s2 = n + sum (n-i) b_i).
 namespace {
+constexpr int kEmitPar = 4;
+constexpr int kEmitHdrWords = 152;  // 3 + 14 + 19 * 3 + 316 * 14 bits at most
 struct DeflateEmitShared {
-  DeflateTrees T;
+  DeflateTrees T[kEmitPar];
   BitWindow W;
   uint32_t lhist[kDefLCodes + 2], dhist[kDefDCodes + 2];
   uint32_t scan[kWarps + 1];
-  DeflateBlockPlan plan;
-  uint32_t hdrEnd;
+  DeflateBlockPlan plan[kEmitPar];
+  uint32_t hdr[kEmitPar][kEmitHdrWords];
+  uint32_t hdrBits[kEmitPar];
   unsigned long long red[kWarps][2];
   int j;
 };
-struct WinOut {  // serial writer for block headers (the Out of def_send_all_trees)
-  WinSink s;
-  __device__ __forceinline__ void send_bits(uint32_t v, int n) { if (n) s.put(v, n); }
+struct BufOut {  // serial writer into a zeroed word buffer (the Out of def_send_all_trees)
+  uint32_t* w;
+  uint32_t pos;
+  __device__ __forceinline__ void send_bits(uint32_t v, int n) {
+    if (!n) return;
+    const uint32_t i = pos >> 5, o = pos & 31;
+    w[i] |= v << o;
+    if (o + uint32_t(n) > 32u) w[i + 1] |= v >> (32 - o);
+    pos += uint32_t(n);
+  }
 };
 __device__ __forceinline__ uint32_t emit_sym_bits(const DeflateTrees& T, bool useStatic, uint32_t dist, uint32_t lc) {
   if (dist == 0) return useStatic ? uint32_t(def_static_llen(int(lc))) : T.ltree[lc].dl;
@@ -529,7 +553,8 @@ __device__ __forceinline__ void emit_sym_put(ThreadBits& tb, const DeflateTrees&
 }  // namespace
 
 __global__ void __launch_bounds__(kThreads) deflate_emit_kernel(StagedArgs a) {
-  __shared__ DeflateEmitShared S;
+  extern __shared__ __align__(16) unsigned char emitSm[];
+  DeflateEmitShared& S = *reinterpret_cast<DeflateEmitShared*>(emitSm);
   const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
   const DeflateLevel L = deflate_level(a.level);
   for (;;) {
@@ -556,110 +581,129 @@ __global__ void __launch_bounds__(kThreads) deflate_emit_kernel(StagedArgs a) {
     }
     o.bitPos = 16;
     const uint32_t nBlocks = B.nBlocks;
-    uint32_t sym0 = 0, pos0 = 0;
-    for (uint32_t b = 0; b < nBlocks; b++) {
-      const uint32_t sym1 = B.symEnd[b], pos1 = B.posEnd[b];
-      const bool last = b + 1 == nBlocks;
-      __syncthreads();
-      for (int i = tid; i < kDefLCodes + 2; i += kThreads) S.lhist[i] = 0;
-      if (tid < kDefDCodes + 2) S.dhist[tid] = 0;
-      __syncthreads();
-      for (uint32_t i = sym0 + tid; i < sym1; i += kThreads) {
-        const uint32_t dist = symDist[i], lc = symLc[i];
-        if (dist == 0) atomicAdd(&S.lhist[lc], 1u);
-        else {
-          atomicAdd(&S.lhist[def_length_code(int(lc)) + 257], 1u);
-          atomicAdd(&S.dhist[def_dist_code(int(dist - 1))], 1u);
+    for (uint32_t b0 = 0; b0 < nBlocks; b0 += kEmitPar) {
+      const uint32_t nb = nBlocks - b0 < uint32_t(kEmitPar) ? nBlocks - b0 : uint32_t(kEmitPar);
+      // histograms of the batch's blocks, one after the other, into the blocks' own trees
+      for (uint32_t i = 0; i < nb; i++) {
+        const uint32_t sym0 = b0 + i ? B.symEnd[b0 + i - 1] : 0u, sym1 = B.symEnd[b0 + i];
+        __syncthreads();
+        for (int q = tid; q < kDefLCodes + 2; q += kThreads) S.lhist[q] = 0;
+        if (tid < kDefDCodes + 2) S.dhist[tid] = 0;
+        for (int q = tid; q < kEmitHdrWords; q += kThreads) S.hdr[i][q] = 0;
+        __syncthreads();
+        for (uint32_t q = sym0 + tid; q < sym1; q += kThreads) {
+          const uint32_t dist = symDist[q], lc = symLc[q];
+          if (dist == 0) atomicAdd(&S.lhist[lc], 1u);
+          else {
+            atomicAdd(&S.lhist[def_length_code(int(lc)) + 257], 1u);
+            atomicAdd(&S.dhist[def_dist_code(int(dist - 1))], 1u);
+          }
         }
+        __syncthreads();
+        for (int q = tid; q < kDefLCodes; q += kThreads) S.T[i].ltree[q].fc = uint16_t(q == 256 ? 1u : S.lhist[q]);
+        if (tid < kDefDCodes) S.T[i].dtree[tid].fc = uint16_t(S.dhist[tid]);
+        if (tid < kDefBlCodes) S.T[i].bltree[tid].fc = 0;
       }
       __syncthreads();
-      for (int i = tid; i < kDefLCodes; i += kThreads) S.T.ltree[i].fc = uint16_t(i == 256 ? 1u : S.lhist[i]);
-      if (tid < kDefDCodes) S.T.dtree[tid].fc = uint16_t(S.dhist[tid]);
-      if (tid < kDefBlCodes) S.T.bltree[tid].fc = 0;
-      bitwin_reserve(S.W, o, 8192);  // room for the block header (<= 17 + 57 + 316 * 14 bits); contains the barrier
-      __syncthreads();
-      if (tid == 0) {
+      if (lane == 0 && uint32_t(warp) < nb) {  // trees.c for block b0 + warp, and its header
+        const uint32_t b = b0 + uint32_t(warp);
         DeflateState st;
         st.W = nullptr;
-        st.T = &S.T;
+        st.T = &S.T[warp];
         st.optLen = st.staticLen = 0;
-        const DeflateBlockPlan P = def_plan_block(st, pos1 - pos0, true);
-        S.plan = P;
-        WinOut wo{WinSink{S.W.win, o.bitPos - o.gbase * 32u}};
-        wo.send_bits((uint32_t(P.type) << 1) + (last ? 1u : 0u), 3);
-        if (P.type == 2) def_send_all_trees(st, wo, P);
-        S.hdrEnd = wo.s.pos + o.gbase * 32u;
+        const DeflateBlockPlan P = def_plan_block(st, B.posEnd[b] - (b ? B.posEnd[b - 1] : 0u), true);
+        S.plan[warp] = P;
+        BufOut bo{S.hdr[warp], 0};
+        bo.send_bits((uint32_t(P.type) << 1) + (b + 1 == nBlocks ? 1u : 0u), 3);
+        if (P.type == 2) def_send_all_trees(st, bo, P);
+        S.hdrBits[warp] = bo.pos;
       }
       __syncthreads();
-      o.bitPos = S.hdrEnd;
-      const int type = S.plan.type;
-      if (type == 0) {
-        // stored: pad to a byte boundary, LEN, NLEN, then the raw bytes (eight per thread and step)
-        const uint32_t len = pos1 - pos0;
-        o.bitPos = (o.bitPos + 7u) & ~7u;
-        bitwin_reserve(S.W, o, 64);
-        if (tid == 0) {
-          WinSink hs{S.W.win, o.bitPos - o.gbase * 32u};
-          hs.put(len & 0xffffu, 16);
-          hs.put((~len) & 0xffffu, 16);
-        }
-        o.bitPos += 32;
-        __syncthreads();
-        for (uint32_t i0 = 0; i0 < len; i0 += kThreads * 8) {
-          const uint32_t rem = len - i0;
-          const uint32_t chunk = rem < uint32_t(kThreads * 8) ? rem : uint32_t(kThreads * 8);
-          bitwin_reserve(S.W, o, chunk * 8);
-          const uint32_t mine = i0 + uint32_t(tid) * 8u;
-          if (mine < i0 + chunk) {
+      for (uint32_t i = 0; i < nb; i++) {
+        const uint32_t b = b0 + i;
+        const uint32_t sym0 = b ? B.symEnd[b - 1] : 0u, sym1 = B.symEnd[b];
+        const uint32_t pos0 = b ? B.posEnd[b - 1] : 0u, pos1 = B.posEnd[b];
+        const DeflateTrees& T = S.T[i];
+        bitwin_reserve(S.W, o, 8192);  // room for the block header; contains the barrier
+        {
+          const uint32_t hb = S.hdrBits[i];
+          if (uint32_t(tid) * 32u < hb) {
+            const uint32_t left = hb - uint32_t(tid) * 32u;
             ThreadBits tb;
-            tb.begin(S.W, o, o.bitPos + uint32_t(tid) * 64u);
-            const uint32_t cnt = (i0 + chunk - mine) < 8u ? (i0 + chunk - mine) : 8u;
-            for (uint32_t q = 0; q < cnt; q++) tb.put(in[pos0 + mine + q], 8);
+            tb.begin(S.W, o, o.bitPos + uint32_t(tid) * 32u);
+            tb.put(S.hdr[i][tid], left < 32u ? int(left) : 32);
             tb.end();
           }
-          o.bitPos += chunk * 8;
-          __syncthreads();
+          o.bitPos += hb;
         }
-      } else {
-        const bool useStatic = type == 1;
-        constexpr int kIpt = 4;
-        for (uint32_t k0 = sym0; k0 < sym1; k0 += kThreads * kIpt) {
-          uint32_t dist[kIpt], lc[kIpt];
-          uint32_t myBits = 0;
-          int nv = 0;
-#pragma unroll
-          for (int q = 0; q < kIpt; q++) {
-            const uint32_t k = k0 + uint32_t(tid) * kIpt + q;
-            if (k < sym1) {
-              dist[q] = symDist[k];
-              lc[q] = symLc[k];
-              myBits += emit_sym_bits(S.T, useStatic, dist[q], lc[q]);
-              nv = q + 1;
-            }
-          }
-          uint32_t chunkBits;
-          const uint32_t ex = block_exclusive_scan(myBits, S.scan, &chunkBits);
-          bitwin_reserve(S.W, o, chunkBits);  // 1024 symbols * 48 bits always fit an empty window
-          ThreadBits tb;
-          tb.begin(S.W, o, o.bitPos + ex);
-#pragma unroll
-          for (int q = 0; q < kIpt; q++)
-            if (q < nv) emit_sym_put(tb, S.T, useStatic, dist[q], lc[q]);
-          tb.end();
-          o.bitPos += chunkBits;
-          __syncthreads();
-        }
-        bitwin_reserve(S.W, o, 32);
-        if (tid == 0) {
-          WinSink es{S.W.win, o.bitPos - o.gbase * 32u};
-          if (useStatic) es.put(def_static_lcode(256), 7);
-          else es.put(S.T.ltree[256].fc, S.T.ltree[256].dl);
-        }
-        o.bitPos += useStatic ? 7u : uint32_t(S.T.ltree[256].dl);
         __syncthreads();
+        const int type = S.plan[i].type;
+        if (type == 0) {
+          // stored: pad to a byte boundary, LEN, NLEN, then the raw bytes (eight per thread and step)
+          const uint32_t len = pos1 - pos0;
+          o.bitPos = (o.bitPos + 7u) & ~7u;
+          bitwin_reserve(S.W, o, 64);
+          if (tid == 0) {
+            WinSink hs{S.W.win, o.bitPos - o.gbase * 32u};
+            hs.put(len & 0xffffu, 16);
+            hs.put((~len) & 0xffffu, 16);
+          }
+          o.bitPos += 32;
+          __syncthreads();
+          for (uint32_t i0 = 0; i0 < len; i0 += kThreads * 8) {
+            const uint32_t rem = len - i0;
+            const uint32_t chunk = rem < uint32_t(kThreads * 8) ? rem : uint32_t(kThreads * 8);
+            bitwin_reserve(S.W, o, chunk * 8);
+            const uint32_t mine = i0 + uint32_t(tid) * 8u;
+            if (mine < i0 + chunk) {
+              ThreadBits tb;
+              tb.begin(S.W, o, o.bitPos + uint32_t(tid) * 64u);
+              const uint32_t cnt = (i0 + chunk - mine) < 8u ? (i0 + chunk - mine) : 8u;
+              for (uint32_t q = 0; q < cnt; q++) tb.put(in[pos0 + mine + q], 8);
+              tb.end();
+            }
+            o.bitPos += chunk * 8;
+            __syncthreads();
+          }
+        } else {
+          const bool useStatic = type == 1;
+          constexpr int kIpt = 4;
+          for (uint32_t k0 = sym0; k0 < sym1; k0 += kThreads * kIpt) {
+            uint32_t dist[kIpt], lc[kIpt];
+            uint32_t myBits = 0;
+            int nv = 0;
+#pragma unroll
+            for (int q = 0; q < kIpt; q++) {
+              const uint32_t k = k0 + uint32_t(tid) * kIpt + q;
+              if (k < sym1) {
+                dist[q] = symDist[k];
+                lc[q] = symLc[k];
+                myBits += emit_sym_bits(T, useStatic, dist[q], lc[q]);
+                nv = q + 1;
+              }
+            }
+            uint32_t chunkBits;
+            const uint32_t ex = block_exclusive_scan(myBits, S.scan, &chunkBits);
+            bitwin_reserve(S.W, o, chunkBits);  // 1024 symbols * 48 bits always fit an empty window
+            ThreadBits tb;
+            tb.begin(S.W, o, o.bitPos + ex);
+#pragma unroll
+            for (int q = 0; q < kIpt; q++)
+              if (q < nv) emit_sym_put(tb, T, useStatic, dist[q], lc[q]);
+            tb.end();
+            o.bitPos += chunkBits;
+            __syncthreads();
+          }
+          bitwin_reserve(S.W, o, 32);
+          if (tid == 0) {
+            WinSink es{S.W.win, o.bitPos - o.gbase * 32u};
+            if (useStatic) es.put(def_static_lcode(256), 7);
+            else es.put(T.ltree[256].fc, T.ltree[256].dl);
+          }
+          o.bitPos += useStatic ? 7u : uint32_t(T.ltree[256].dl);
+          __syncthreads();
+        }
       }
-      sym0 = sym1;
-      pos0 = pos1;
     }
     o.bitPos = (o.bitPos + 7u) & ~7u;  // bi_windup after the last block
     // Adler-32: s1 = 1 + sum b_i, s2 = n + sum (n - i) b_i  (mod 65521)
@@ -955,7 +999,12 @@ cudaError_t launch_deflate_staged(const StagedArgs& a, int smCount, cudaStream_t
   else deflate_decide_ring_kernel<4><<<(nChunk + 3) / 4, 32, 0, s>>>(a);
   e = cudaGetLastError();
   if (e != cudaSuccess) return e;
-  deflate_emit_kernel<<<nChunk < smCount * 8 ? nChunk : smCount * 8, kThreads, 0, s>>>(a);
+  static std::atomic<uint64_t> attrE{0};
+  ea = once_per_device(attrE, [] {
+    return cudaFuncSetAttribute(deflate_emit_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, int(sizeof(DeflateEmitShared)));
+  });
+  if (ea != cudaSuccess) return ea;
+  deflate_emit_kernel<<<nChunk < smCount * 8 ? nChunk : smCount * 8, kThreads, sizeof(DeflateEmitShared), s>>>(a);
   return cudaGetLastError();
 }
 cudaError_t launch_deflate_m32_size(const EncodeArgs& a, uint32_t* inLen, int nCtas, cudaStream_t s) {
