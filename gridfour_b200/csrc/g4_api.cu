@@ -210,6 +210,8 @@ int run_streams(g4_context* ctx, int nStreams, int capExtra, int level, int* cou
     st.rank = ctx->stRank.as<uint16_t>();
     st.table = ctx->stTable.as<uint32_t>();
     st.tableQ = ctx->stTable.as<uint32_t>() + (span + 16);
+    static const bool lazyOff = getenv("G4_DEFLATE_LAZY") && atoi(getenv("G4_DEFLATE_LAZY")) == 0;
+    st.lazy = (level >= 9 && !lazyOff) ? 1 : 0;
     st.maxLen = 0;
     for (int j = j0; j < j1; j++)
       if (ctx->hostLen[size_t(j)] <= stagedMax && ctx->hostLen[size_t(j)] > st.maxLen) st.maxLen = ctx->hostLen[size_t(j)];
@@ -218,7 +220,7 @@ int run_streams(g4_context* ctx, int nStreams, int capExtra, int level, int* cou
     st.level = level;
     st.counters = ctx->stCounters.as<int>();
     CK(launch_deflate_staged(st, ctx->smCount, ctx->stream));
-    ctx->launches += 4;
+    ctx->launches += st.lazy ? 3 : 4;
     j0 = j1;
   }
   return G4_OK;

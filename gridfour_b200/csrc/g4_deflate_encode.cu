@@ -101,6 +101,7 @@ __global__ void __launch_bounds__(kSortThreads) deflate_sort_kernel(StagedArgs a
     const uint8_t* in = a.inBuf + off;
     uint16_t* sorted = a.sorted + (off - a.baseOff);
     uint16_t* hashOf = reinterpret_cast<uint16_t*>(a.tableQ + (off - a.baseOff));  // the match tables are not written yet
+    uint16_t* slotOf = a.lazy ? a.rank + (off - a.baseOff) : nullptr;
     const uint32_t nPos = n - 2;
     {
       uint4* t4 = reinterpret_cast<uint4*>(sortTab);
@@ -176,6 +177,7 @@ __global__ void __launch_bounds__(kSortThreads) deflate_sort_kernel(StagedArgs a
             const uint32_t cur = sortTab[h[c]];
             const uint32_t slot = cur + uint32_t(__popc(m & ltMask));
             sorted[slot] = uint16_t(base + uint32_t(c) * 32u + uint32_t(lane));
+            if (slotOf) slotOf[base + uint32_t(c) * 32u + uint32_t(lane)] = uint16_t(slot);
             if ((m >> lane) == 1u) sortTab[h[c]] = uint16_t(cur + __popc(m));
           }
           __syncwarp();
@@ -367,6 +369,144 @@ __global__ void __launch_bounds__(1024) deflate_match_window_kernel(StagedArgs a
       const uint4* src = reinterpret_cast<const uint4*>(tabS);
       for (uint32_t i = tid; i < (nPos + 3u) / 4u; i += nThr) dst[i] = src[i];
     }
+  }
+}
+
+// lazy (deep levels, CodecFloat's Deflater(9)): with 4096-candidate chains the table of EVERY position costs a hundred
+// times what zlib spends, because zlib never searches the positions a match covers -- and the float planes are mostly
+// long matches.  Here ONE WARP per stream runs deflate_slow itself and searches only where zlib does; the search is what
+// the warp shares: 32 candidates of the chain (consecutive slots behind the position's slot in the sorted list) per
+// step, each lane one candidate -- distance rules, bucket membership (hash of the candidate's bytes), common prefix from
+// two 64-bit keys and then the stream itself -- and a warp reduction picks the longest, nearest first, exactly
+// longest_match()'s answer (a later candidate replaces the best only when strictly longer; the walk ends at nice_match,
+// at the chain length, at the first candidate beyond MAX_DIST or outside the bucket).
+__global__ void __launch_bounds__(128) deflate_lazy_kernel(StagedArgs a) {
+  const uint32_t lane = threadIdx.x & 31u;
+  const DeflateLevel L = deflate_level(a.level);
+  for (;;) {
+    int j = 0;
+    if (lane == 0) j = a.jBegin + atomicAdd(a.counters + 1, 1);
+    j = __shfl_sync(0xffffffffu, j, 0);
+    if (j >= a.jEnd) break;
+    const uint32_t n = a.inLen[j];
+    if (n == 0 || n > kDefStagedMax) continue;
+    const uint64_t off = a.inOff[j];
+    const uint8_t* in = a.inBuf + off;
+    const uint32_t* in32 = reinterpret_cast<const uint32_t*>(in);
+    const uint16_t* sorted = a.sorted + (off - a.baseOff);
+    const uint16_t* slotOf = a.rank + (off - a.baseOff);
+    uint16_t* symDist = reinterpret_cast<uint16_t*>(a.table + (off - a.baseOff));
+    uint8_t* symLc = reinterpret_cast<uint8_t*>(a.tableQ + (off - a.baseOff));
+    DeflateBlocks* B = a.blocks + (j - a.jBegin);
+    auto key_at = [&](uint32_t p, uint32_t& lo, uint32_t& hi) {
+      const uint32_t* q = in32 + (p >> 2);
+      const uint32_t sh = (p & 3u) * 8u;
+      const uint32_t w0 = __ldg(q), w1 = __ldg(q + 1), w2 = __ldg(q + 2);
+      lo = __funnelshift_r(w0, w1, sh);
+      hi = __funnelshift_r(w1, w2, sh);
+    };
+    uint32_t strstart = 0, matchStart = 0, prevMatch = 0, k = 0, inBlock = 0, nBlocks = 0;
+    int matchLength = kDefMinMatch - 1, prevLength = kDefMinMatch - 1;
+    bool matchAvailable = false;
+    auto tally = [&](uint32_t dist, uint32_t lc) -> bool {
+      if (lane == 0) { symDist[k] = uint16_t(dist); symLc[k] = uint8_t(lc); }
+      k++;
+      return ++inBlock == uint32_t(kDefLitBufSize - 1);
+    };
+    auto flush = [&]() {
+      if (lane == 0) { B->symEnd[nBlocks] = k; B->posEnd[nBlocks] = strstart; }
+      nBlocks++;
+      inBlock = 0;
+    };
+    while (strstart < n) {
+      const uint32_t p = strstart;
+      const uint32_t lookahead = n - p;
+      prevLength = matchLength;
+      prevMatch = matchStart;
+      matchLength = kDefMinMatch - 1;
+      if (lookahead >= uint32_t(kDefMinMatch) && prevLength < L.maxLazy) {
+        const uint32_t slot = slotOf[p];
+        const uint32_t chain = prevLength >= L.goodLength ? uint32_t(L.maxChain) >> 2 : uint32_t(L.maxChain);
+        const uint32_t nMax = slot < chain ? slot : chain;
+        const int maxLen = lookahead < uint32_t(kDefMaxMatch) ? int(lookahead) : kDefMaxMatch;
+        const int niceMatch = uint32_t(L.niceLength) > lookahead ? int(lookahead) : L.niceLength;
+        const uint32_t limit = p > uint32_t(kDefMaxDist) ? p - uint32_t(kDefMaxDist) : 0u;
+        uint32_t klo, khi;
+        key_at(p, klo, khi);
+        int bestLen = prevLength;
+        uint32_t bestStart = 0;
+        for (uint32_t k0 = 0; k0 < nMax; k0 += 32u) {
+          const uint32_t kk = k0 + lane + 1u;
+          bool valid = kk <= nMax;
+          uint32_t cur = 0, clo = 0, chi = 0;
+          if (valid) {
+            cur = sorted[slot - kk];
+            valid = kk == 1u ? !(cur == 0u || p - cur > uint32_t(kDefMaxDist)) : cur > limit;
+          }
+          if (valid) {
+            key_at(cur, clo, chi);
+            valid = ((clo ^ klo) & 0x00ffffffu) == 0u ||
+                    ((((clo & 0xffu) << 10) ^ (((clo >> 8) & 0xffu) << 5) ^ ((clo >> 16) & 0xffu)) & uint32_t(kDefHashMask)) ==
+                        ((((klo & 0xffu) << 10) ^ (((klo >> 8) & 0xffu) << 5) ^ ((klo >> 16) & 0xffu)) & uint32_t(kDefHashMask));
+          }
+          const uint32_t vmask = __ballot_sync(0xffffffffu, valid);
+          const uint32_t nv = vmask == 0xffffffffu ? 32u : uint32_t(__ffs(int(~vmask))) - 1u;  // the chain ends at the first invalid candidate
+          int len = 0;
+          if (lane < nv) {
+            const uint32_t xl = clo ^ klo, xh = chi ^ khi;
+            if (xl) len = (__ffs(int(xl)) - 1) >> 3;
+            else if (xh) len = 4 + ((__ffs(int(xh)) - 1) >> 3);
+            else {
+              len = 8;
+              const uint8_t* scan = in + p;
+              const uint8_t* match = in + cur;
+              if (bestLen >= 8 && (match[bestLen] != scan[bestLen] || match[bestLen - 1] != scan[bestLen - 1])) len = 0;
+              else {
+                bool differ = false;
+                while (len + 4 <= maxLen) {
+                  const uint32_t x = def_load32(scan + len) ^ def_load32(match + len);
+                  if (x) { len += (__ffs(int(x)) - 1) >> 3; differ = true; break; }
+                  len += 4;
+                }
+                if (!differ)
+                  while (len < maxLen && scan[len] == match[len]) len++;
+              }
+            }
+            if (len > maxLen) len = maxLen;
+          }
+          const int stepMax = __reduce_max_sync(0xffffffffu, len);
+          if (stepMax > bestLen) {
+            const uint32_t who = uint32_t(__ffs(int(__ballot_sync(0xffffffffu, len == stepMax)))) - 1u;  // nearest of the longest
+            bestLen = stepMax;
+            bestStart = __shfl_sync(0xffffffffu, cur, int(who));
+            if (bestLen >= niceMatch) break;
+          }
+          if (nv < 32u) break;
+        }
+        if (bestLen > prevLength) {
+          matchLength = bestLen;
+          matchStart = bestStart;
+          if (matchLength == kDefMinMatch && strstart - matchStart > uint32_t(kDefTooFar)) matchLength = kDefMinMatch - 1;
+        }
+      }
+      if (prevLength >= kDefMinMatch && matchLength <= prevLength) {
+        const bool bflush = tally(strstart - 1 - prevMatch, uint32_t(prevLength - kDefMinMatch));
+        strstart += uint32_t(prevLength - 1);
+        matchAvailable = false;
+        matchLength = kDefMinMatch - 1;
+        if (bflush) flush();
+      } else if (matchAvailable) {
+        const bool bflush = tally(0, in[strstart - 1]);
+        if (bflush) flush();
+        strstart++;
+      } else {
+        matchAvailable = true;
+        strstart++;
+      }
+    }
+    if (matchAvailable) tally(0, in[strstart - 1]);
+    flush();
+    if (lane == 0) B->nBlocks = nBlocks;
   }
 }
 
@@ -568,8 +708,9 @@ __global__ void __launch_bounds__(kThreads) deflate_emit_kernel(StagedArgs a) {
     if (n == 0) { if (tid == 0) a.outLen[j] = 0; continue; }
     const uint64_t off = a.inOff[j];
     const uint8_t* in = a.inBuf + off;
-    const uint16_t* symDist = a.sorted + (off - a.baseOff);
-    const uint8_t* symLc = reinterpret_cast<const uint8_t*>(a.rank + (off - a.baseOff));
+    const uint16_t* symDist = a.lazy ? reinterpret_cast<const uint16_t*>(a.table + (off - a.baseOff)) : a.sorted + (off - a.baseOff);
+    const uint8_t* symLc = a.lazy ? reinterpret_cast<const uint8_t*>(a.tableQ + (off - a.baseOff))
+                                  : reinterpret_cast<const uint8_t*>(a.rank + (off - a.baseOff));
     const DeflateBlocks& B = a.blocks[j - a.jBegin];
     const uint32_t cap = n + uint32_t(a.capExtra);
     BitOut o;
@@ -967,6 +1108,10 @@ cudaError_t launch_deflate_staged(const StagedArgs& a, int smCount, cudaStream_t
   deflate_sort_kernel<<<sortCtas, kSortThreads, kDefWSize * 2, s>>>(a);
   cudaError_t e = cudaGetLastError();
   if (e != cudaSuccess) return e;
+  if (a.lazy) {
+    const int warps = nChunk < smCount * 48 ? nChunk : smCount * 48;
+    deflate_lazy_kernel<<<(warps + 3) / 4, 128, 0, s>>>(a);
+  } else {
   // match: shared memory = the candidate window + the stream's table (4 bytes per position) when that fits
   {
     const bool deep = deflate_level(a.level).maxChain > 128;
@@ -997,6 +1142,7 @@ cudaError_t launch_deflate_staged(const StagedArgs& a, int smCount, cudaStream_t
   else if (decLanes >= 16) deflate_decide_ring_kernel<16><<<(nChunk + 15) / 16, 32, 0, s>>>(a);
   else if (decLanes >= 8) deflate_decide_ring_kernel<8><<<(nChunk + 7) / 8, 32, 0, s>>>(a);
   else deflate_decide_ring_kernel<4><<<(nChunk + 3) / 4, 32, 0, s>>>(a);
+  }
   e = cudaGetLastError();
   if (e != cudaSuccess) return e;
   static std::atomic<uint64_t> attrE{0};

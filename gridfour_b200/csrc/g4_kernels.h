@@ -131,6 +131,8 @@ struct StagedArgs {
   uint32_t* table;    // per position: longest match with the full chain (def_pack_match; bit 31: tableQ differs)
   uint32_t* tableQ;   // per position, written only where it differs: longest match with the quarter chain
   uint32_t maxLen;    // longest staged stream of the chunk (sizes the match kernel's shared-memory table)
+  int lazy;           // deep levels: the sort also writes position -> slot (into `rank`), one warp per stream parses and
+                      // searches only where zlib would (symbols then live in the table arrays)
   DeflateBlocks* blocks;  // per stream of the chunk: block boundaries (decide kernel -> emit kernel), deflate_blocks_bytes() each
   int capExtra, level;
   int* counters;      // 4 ints, zeroed before launch
