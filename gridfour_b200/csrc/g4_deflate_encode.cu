@@ -435,14 +435,13 @@ __global__ void __launch_bounds__(128) deflate_lazy_kernel(StagedArgs a) {
         key_at(p, klo, khi);
         int bestLen = prevLength;
         uint32_t bestStart = 0;
+        uint32_t curNext = lane + 1u <= nMax ? uint32_t(sorted[slot - lane - 1u]) : 0u;
         for (uint32_t k0 = 0; k0 < nMax; k0 += 32u) {
           const uint32_t kk = k0 + lane + 1u;
           bool valid = kk <= nMax;
-          uint32_t cur = 0, clo = 0, chi = 0;
-          if (valid) {
-            cur = sorted[slot - kk];
-            valid = kk == 1u ? !(cur == 0u || p - cur > uint32_t(kDefMaxDist)) : cur > limit;
-          }
+          uint32_t cur = curNext, clo = 0, chi = 0;
+          if (kk + 32u <= nMax) curNext = sorted[slot - kk - 32u];  // the next step's candidate: in flight during this one
+          if (valid) valid = kk == 1u ? !(cur == 0u || p - cur > uint32_t(kDefMaxDist)) : cur > limit;
           if (valid) {
             key_at(cur, clo, chi);
             valid = ((clo ^ klo) & 0x00ffffffu) == 0u ||
