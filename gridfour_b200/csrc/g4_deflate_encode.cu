@@ -380,7 +380,7 @@ __global__ void __launch_bounds__(1024) deflate_match_window_kernel(StagedArgs a
 // two 64-bit keys and then the stream itself -- and a warp reduction picks the longest, nearest first, exactly
 // longest_match()'s answer (a later candidate replaces the best only when strictly longer; the walk ends at nice_match,
 // at the chain length, at the first candidate beyond MAX_DIST or outside the bucket).
-__global__ void __launch_bounds__(128) deflate_lazy_kernel(StagedArgs a) {
+__global__ void __launch_bounds__(128, 12) deflate_lazy_kernel(StagedArgs a) {
   const uint32_t lane = threadIdx.x & 31u;
   const DeflateLevel L = deflate_level(a.level);
   for (;;) {
