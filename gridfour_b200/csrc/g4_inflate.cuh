@@ -209,6 +209,26 @@ __device__ inline int inflate_group(InflateWarpShared& S, const uint8_t* in, uin
       uint32_t mlen = 0, mdist = 0;
       if (lane == 0) {
         for (;;) {
+          // Two literals per turn while the stream, the bit buffer and the output have room for them: both codes come
+          // from the LUT (at most kInfLitBits bits each, the buffer holds 32 or more), one skip for the pair, no
+          // per-symbol limit checks.  Anything else -- a long code, a length code, the end of block, the last bits
+          // of the stream -- leaves the loop for the general code below.
+          while (cur.pos + 32u <= src.nBits && op + 2u <= cap) {
+            const uint32_t b = cur.peek();
+            const uint32_t e1 = S.litLut[b & ((1u << kInfLitBits) - 1)];
+            const uint32_t l1 = e1 >> 9;
+            if (e1 == 0u || (e1 & 0x100u)) break;
+            const uint32_t e2 = S.litLut[(b >> l1) & ((1u << kInfLitBits) - 1)];
+            if (e2 == 0u || (e2 & 0x100u)) {
+              out[op++] = uint8_t(e1);
+              cur.skip(l1);
+              break;
+            }
+            out[op] = uint8_t(e1);
+            out[op + 1] = uint8_t(e2);
+            op += 2;
+            cur.skip(l1 + (e2 >> 9));
+          }
           if (cur.pos >= src.nBits) { ev = 3; break; }
           const uint32_t p0 = cur.pos;
           int sym;
