@@ -209,7 +209,7 @@ __device__ inline int inflate_group(InflateWarpShared& S, const uint8_t* in, uin
       uint32_t mlen = 0, mdist = 0;
       if (lane == 0) {
         for (;;) {
-          // Two literals per turn while the stream, the bit buffer and the output have room for them: both codes come
+          // Two or three literals per turn while the stream, the bit buffer and the output have room for them: both codes come
           // from the LUT (at most kInfLitBits bits each, the buffer holds 32 or more), one skip for the pair, no
           // per-symbol limit checks.  Anything else -- a long code, a length code, the end of block, the last bits
           // of the stream -- leaves the loop for the general code below.
@@ -224,10 +224,18 @@ __device__ inline int inflate_group(InflateWarpShared& S, const uint8_t* in, uin
               cur.skip(l1);
               break;
             }
+            const uint32_t l2 = l1 + (e2 >> 9);
+            const uint32_t e3 = S.litLut[(b >> l2) & ((1u << kInfLitBits) - 1)];
             out[op] = uint8_t(e1);
             out[op + 1] = uint8_t(e2);
-            op += 2;
-            cur.skip(l1 + (e2 >> 9));
+            if (e3 == 0u || (e3 & 0x100u) || op + 3u > cap) {
+              op += 2;
+              cur.skip(l2);
+              continue;
+            }
+            out[op + 2] = uint8_t(e3);
+            op += 3;
+            cur.skip(l2 + (e3 >> 9));
           }
           if (cur.pos >= src.nBits) { ev = 3; break; }
           const uint32_t p0 = cur.pos;
