@@ -65,6 +65,36 @@ def test_float_encode_matches_oracle(g4, oracle):
         assert np.array_equal(out.view(np.uint32), t.view(np.uint32))
 
 
+def test_float_level9_parser_long_planes_match_oracle(g4, oracle):
+    """CodecFloat's Deflater(9) streams go through the warp-per-stream parser (deflate_lazy_kernel: chains of up to 4096
+    candidates searched 32 at a time, only where zlib searches).  Planes of 43,200 bytes and more: chains that reach the
+    level's limit, matches of 258 next to literal stretches, candidates beyond MAX_DIST (32,506) and an all-equal plane;
+    a batch so that several warps of a CTA run different streams.  Byte-identical to the oracle's zlib."""
+    rng = np.random.default_rng(11)
+    smooth = oracle.terrain_f32(40, 60, 180, 240)
+    steps = np.floor(oracle.terrain_f32(0, 0, 180, 240) / 7.0).astype(np.float32)  # plateaus: long runs in every plane
+    few = rng.choice(np.array([1.5, -2.25, 1024.0, 3.0e-3], np.float32), (200, 300))  # 60,000 cells, four byte patterns: deep chains
+    flat = np.full((180, 240), 12.5, np.float32)
+    enc = g4.CodecFloat()
+    for name, t in (("smooth", smooth), ("steps", steps), ("few", few), ("flat", flat)):
+        want = oracle.codec_encode_f32(0, t)
+        got = enc.encodeFloats(0, t.shape[0], t.shape[1], t)
+        assert got is not None and got == want, "%s: %s" % (name, first_diff(got, want))
+        out = g4.CodecFloat().decodeFloats(t.shape[0], t.shape[1], got)
+        assert np.array_equal(out.view(np.uint32), t.view(np.uint32)), name
+    grid = oracle.terrain_f32(0, 0, 2 * 180, 3 * 240)
+    spec = g4.CodecSpecification(default=False)
+    spec.addCompressionCodec("GvrsFloat", g4.CodecFloat, g4.CodecFloat)
+    master = g4.CodecMaster(spec)
+    batch = master.encodeTiles(grid, 180, 240)
+    for t in range(6):
+        tr, tc = divmod(t, 3)
+        tile = np.ascontiguousarray(grid[tr * 180:(tr + 1) * 180, tc * 240:(tc + 1) * 240])
+        want = oracle.codec_encode_f32(0, tile)
+        assert batch.payload(t) == want, "tile %d: %s" % (t, first_diff(batch.payload(t), want))
+    assert np.array_equal(master.decodeTiles(batch).view(np.uint32), grid.view(np.uint32))
+
+
 def test_lsop_deflate_alternative_matches_oracle(g4, oracle):
     """Repetitive tiles make LsEncoder12 prefer the two zlib streams (type 1); terrain keeps canonical Huffman (type 2)."""
     r, c = np.mgrid[0:64, 0:64]
