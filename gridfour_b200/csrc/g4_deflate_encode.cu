@@ -201,21 +201,29 @@ __global__ void __launch_bounds__(kSortThreads) deflate_sort_kernel(StagedArgs a
 // fills in shared memory and leaves with coalesced stores; streams too long for that keep the scattered store.
 // W = chain length of the level (slots that must stay behind a round), SB = slots per round, tabCap = entries of the
 // shared-memory table.
-template <int W, int SB>
+// GROUPS: the CTA works as that many independent thread groups, each with its own window, taking the rounds of a stream
+// in turn and synchronising with a named barrier of its own: while one group waits for the gathers that fill its window,
+// the other walks (with one 205 KB CTA per SM there is no second CTA to do that).
+template <int W, int SB, int GROUPS>
 __global__ void __launch_bounds__(1024) deflate_match_window_kernel(StagedArgs a, uint32_t tabCap) {
   extern __shared__ __align__(16) unsigned char matchSm[];
-  uint2* keyS = reinterpret_cast<uint2*>(matchSm);
-  uint32_t* filtS = reinterpret_cast<uint32_t*>(matchSm + size_t(W + SB) * 8);
-  uint32_t* hpS = reinterpret_cast<uint32_t*>(matchSm + size_t(W + SB) * 12);  // hash << 16 | position: rises with the slot
-  uint32_t* tabS = reinterpret_cast<uint32_t*>(matchSm + size_t(W + SB) * 16);
+  const uint32_t nThr = blockDim.x / GROUPS, grp = threadIdx.x / nThr, tid = threadIdx.x - grp * nThr;
+  unsigned char* winSm = matchSm + size_t(grp) * (size_t(W + SB) * 16);
+  uint2* keyS = reinterpret_cast<uint2*>(winSm);
+  uint32_t* filtS = reinterpret_cast<uint32_t*>(winSm + size_t(W + SB) * 8);
+  uint32_t* hpS = reinterpret_cast<uint32_t*>(winSm + size_t(W + SB) * 12);  // hash << 16 | position: rises with the slot
+  uint32_t* tabS = reinterpret_cast<uint32_t*>(matchSm + size_t(GROUPS) * size_t(W + SB) * 16);
   __shared__ int sj;
-  const uint32_t tid = threadIdx.x, nThr = blockDim.x;
+  auto group_sync = [&]() {
+    if (GROUPS == 1) __syncthreads();
+    else asm volatile("bar.sync %0, %1;" ::"r"(1u + grp), "r"(nThr) : "memory");
+  };
   const DeflateLevel L = deflate_level(a.level);
   const uint32_t maxChain = uint32_t(L.maxChain) < uint32_t(W) ? uint32_t(L.maxChain) : uint32_t(W);
   const uint32_t quarter = uint32_t(L.maxChain) >> 2;
   for (;;) {
     __syncthreads();
-    if (tid == 0) sj = a.jBegin + atomicAdd(a.counters + 1, 1);
+    if (threadIdx.x == 0) sj = a.jBegin + atomicAdd(a.counters + 1, 1);
     __syncthreads();
     const int j = sj;
     if (j >= a.jEnd) break;
@@ -228,10 +236,10 @@ __global__ void __launch_bounds__(1024) deflate_match_window_kernel(StagedArgs a
     uint32_t* tableQ = a.tableQ + (off - a.baseOff);
     const uint32_t nPos = n - 2;
     const bool inSm = nPos <= tabCap;
-    for (uint32_t base = 0; base < nPos; base += SB) {
+    for (uint32_t base = grp * uint32_t(SB); base < nPos; base += uint32_t(GROUPS) * uint32_t(SB)) {
       const uint32_t end = base + SB < nPos ? base + SB : nPos;
       const uint32_t first = base >= uint32_t(W) ? base - uint32_t(W) : 0u;  // window = slots [first, end), index = slot + W - base
-      __syncthreads();
+      group_sync();
       for (uint32_t s = first + tid; s < end; s += nThr) {
         const uint32_t p = sorted[s];
         const uintptr_t ad = reinterpret_cast<uintptr_t>(in + p);
@@ -246,7 +254,7 @@ __global__ void __launch_bounds__(1024) deflate_match_window_kernel(StagedArgs a
         // of byte 5.  Fields in byte order: a mask over the low bits tests "at least that many bytes in common".
         filtS[s + W - base] = ((kl >> 5) & 7u) | (((kl >> 8) & 0xffu) << 3) | ((kl >> 24) << 11) | ((kh & 0xffu) << 19) | (((kh >> 8) & 31u) << 27);
       }
-      __syncthreads();
+      group_sync();
       for (uint32_t slot = base + tid; slot < end; slot += nThr) {
         const uint32_t li = slot + W - base;
         const uint2 my = keyS[li];
@@ -367,7 +375,7 @@ __global__ void __launch_bounds__(1024) deflate_match_window_kernel(StagedArgs a
       __syncthreads();
       uint4* dst = reinterpret_cast<uint4*>(table);  // 64-byte aligned: stream offsets are multiples of 16 positions
       const uint4* src = reinterpret_cast<const uint4*>(tabS);
-      for (uint32_t i = tid; i < (nPos + 3u) / 4u; i += nThr) dst[i] = src[i];
+      for (uint32_t i = threadIdx.x; i < (nPos + 3u) / 4u; i += blockDim.x) dst[i] = src[i];
     }
   }
 }
@@ -1114,7 +1122,8 @@ cudaError_t launch_deflate_staged(const StagedArgs& a, int smCount, cudaStream_t
   // match: shared memory = the candidate window + the stream's table (4 bytes per position) when that fits
   {
     const bool deep = deflate_level(a.level).maxChain > 128;
-    const size_t win = deep ? size_t(4096 + 2048) * 16 : size_t(128 + 1920) * 16;
+    static const bool oneGroup = getenv("G4_MATCH_GROUPS") && atoi(getenv("G4_MATCH_GROUPS")) == 1;
+    const size_t win = deep ? size_t(4096 + 2048) * 16 : size_t(128 + 1920) * 16;  // two groups: 2 x (128 + 896) x 16, the same
     const size_t smMax = 227 * 1024 - 2048;
     size_t tabBytes = (size_t(a.maxLen) * 4 + 15) & ~size_t(15);
     if (win + tabBytes > smMax) tabBytes = 0;  // too long: scattered stores
@@ -1126,13 +1135,17 @@ cudaError_t launch_deflate_staged(const StagedArgs& a, int smCount, cudaStream_t
     const int ctas = nChunk < smCount * perSm ? nChunk : smCount * perSm;
     static std::atomic<uint64_t> attrW{0};
     ea = once_per_device(attrW, [] {
-      cudaError_t e1 = cudaFuncSetAttribute(deflate_match_window_kernel<128, 1920>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024 - 2048);
-      if (e1 != cudaSuccess) return e1;
-      return cudaFuncSetAttribute(deflate_match_window_kernel<4096, 2048>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024 - 2048);
+      const int cap = 227 * 1024 - 2048;
+      cudaError_t e1 = cudaFuncSetAttribute(deflate_match_window_kernel<128, 1920, 1>, cudaFuncAttributeMaxDynamicSharedMemorySize, cap);
+      if (e1 == cudaSuccess) e1 = cudaFuncSetAttribute(deflate_match_window_kernel<128, 896, 2>, cudaFuncAttributeMaxDynamicSharedMemorySize, cap);
+      if (e1 == cudaSuccess) e1 = cudaFuncSetAttribute(deflate_match_window_kernel<4096, 2048, 1>, cudaFuncAttributeMaxDynamicSharedMemorySize, cap);
+      return e1;
     });
     if (ea != cudaSuccess) return ea;
-    if (deep) deflate_match_window_kernel<4096, 2048><<<ctas, threads, sm, s>>>(a, uint32_t(tabBytes / 4));
-    else deflate_match_window_kernel<128, 1920><<<ctas, threads, sm, s>>>(a, uint32_t(tabBytes / 4));
+    const uint32_t cap32 = uint32_t(tabBytes / 4);
+    if (deep) deflate_match_window_kernel<4096, 2048, 1><<<ctas, threads, sm, s>>>(a, cap32);
+    else if (threads == 1024 && !oneGroup) deflate_match_window_kernel<128, 896, 2><<<ctas, threads, sm, s>>>(a, cap32);
+    else deflate_match_window_kernel<128, 1920, 1><<<ctas, threads, sm, s>>>(a, cap32);
   }
   e = cudaGetLastError();
   if (e != cudaSuccess) return e;
