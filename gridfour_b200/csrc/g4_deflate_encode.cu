@@ -204,8 +204,8 @@ __global__ void __launch_bounds__(kSortThreads) deflate_sort_kernel(StagedArgs a
 // GROUPS: the CTA works as that many independent thread groups, each with its own window, taking the rounds of a stream
 // in turn and synchronising with a named barrier of its own: while one group waits for the gathers that fill its window,
 // the other walks (with one 205 KB CTA per SM there is no second CTA to do that).
-template <int W, int SB, int GROUPS>
-__global__ void __launch_bounds__(1024) deflate_match_window_kernel(StagedArgs a, uint32_t tabCap) {
+template <int W, int SB, int GROUPS, int NT_MAX, int MIN_CTAS>
+__global__ void __launch_bounds__(NT_MAX, MIN_CTAS) deflate_match_window_kernel(StagedArgs a, uint32_t tabCap) {
   extern __shared__ __align__(16) unsigned char matchSm[];
   const uint32_t nThr = blockDim.x / GROUPS, grp = threadIdx.x / nThr, tid = threadIdx.x - grp * nThr;
   unsigned char* winSm = matchSm + size_t(grp) * (size_t(W + SB) * 16);
@@ -1136,16 +1136,18 @@ cudaError_t launch_deflate_staged(const StagedArgs& a, int smCount, cudaStream_t
     static std::atomic<uint64_t> attrW{0};
     ea = once_per_device(attrW, [] {
       const int cap = 227 * 1024 - 2048;
-      cudaError_t e1 = cudaFuncSetAttribute(deflate_match_window_kernel<128, 1920, 1>, cudaFuncAttributeMaxDynamicSharedMemorySize, cap);
-      if (e1 == cudaSuccess) e1 = cudaFuncSetAttribute(deflate_match_window_kernel<128, 896, 2>, cudaFuncAttributeMaxDynamicSharedMemorySize, cap);
-      if (e1 == cudaSuccess) e1 = cudaFuncSetAttribute(deflate_match_window_kernel<4096, 2048, 1>, cudaFuncAttributeMaxDynamicSharedMemorySize, cap);
+      cudaError_t e1 = cudaFuncSetAttribute(deflate_match_window_kernel<128, 1920, 1, 1024, 1>, cudaFuncAttributeMaxDynamicSharedMemorySize, cap);
+      if (e1 == cudaSuccess) e1 = cudaFuncSetAttribute(deflate_match_window_kernel<128, 1920, 1, 512, 3>, cudaFuncAttributeMaxDynamicSharedMemorySize, cap);
+      if (e1 == cudaSuccess) e1 = cudaFuncSetAttribute(deflate_match_window_kernel<128, 896, 2, 1024, 1>, cudaFuncAttributeMaxDynamicSharedMemorySize, cap);
+      if (e1 == cudaSuccess) e1 = cudaFuncSetAttribute(deflate_match_window_kernel<4096, 2048, 1, 1024, 1>, cudaFuncAttributeMaxDynamicSharedMemorySize, cap);
       return e1;
     });
     if (ea != cudaSuccess) return ea;
     const uint32_t cap32 = uint32_t(tabBytes / 4);
-    if (deep) deflate_match_window_kernel<4096, 2048, 1><<<ctas, threads, sm, s>>>(a, cap32);
-    else if (threads == 1024 && !oneGroup) deflate_match_window_kernel<128, 896, 2><<<ctas, threads, sm, s>>>(a, cap32);
-    else deflate_match_window_kernel<128, 1920, 1><<<ctas, threads, sm, s>>>(a, cap32);
+    if (deep) deflate_match_window_kernel<4096, 2048, 1, 1024, 1><<<ctas, threads, sm, s>>>(a, cap32);
+    else if (threads == 1024 && !oneGroup) deflate_match_window_kernel<128, 896, 2, 1024, 1><<<ctas, threads, sm, s>>>(a, cap32);
+    else if (threads == 1024) deflate_match_window_kernel<128, 1920, 1, 1024, 1><<<ctas, threads, sm, s>>>(a, cap32);
+    else deflate_match_window_kernel<128, 1920, 1, 512, 3><<<ctas, threads, sm, s>>>(a, cap32);
   }
   e = cudaGetLastError();
   if (e != cudaSuccess) return e;
