@@ -71,7 +71,11 @@ struct CtData {
 struct DeflateTrees {
   CtData ltree[kDefHeapSize], dtree[2 * kDefDCodes + 1], bltree[2 * kDefBlCodes + 1];
   int16_t heap[kDefHeapSize];
-  uint8_t depth[kDefHeapSize];
+  // Order key of the node in heap[k], k = 1 .. heapLen: frequency << 8 | depth.  trees.c's smaller(n, m) -- "freq[n] <
+  // freq[m], or equal and depth[n] <= depth[m]" -- is key(n) <= key(m), so a sift-down step reads two adjacent keys
+  // instead of chasing heap[] -> tree[].Freq -> depth[] for each child (the tree build is a chain of dependent loads on
+  // ONE thread, and the emit kernel's other 255 wait for it).
+  uint32_t hkey[kDefHeapSize];
 };
 
 // Per-stream work area in HBM (one-thread-per-stream encoder).
@@ -152,23 +156,26 @@ struct DeflateState {
   uint16_t blCount[16];
 };
 
-G4_HD __forceinline__ bool def_smaller(const CtData* tree, int n, int m, const uint8_t* depth) {
-  return tree[n].fc < tree[m].fc || (tree[n].fc == tree[m].fc && depth[n] <= depth[m]);
-}
-
-G4_HD inline void def_pqdownheap(DeflateState& s, const CtData* tree, int k) {
+G4_HD inline void def_pqdownheap(DeflateState& s, const CtData*, int k) {
   int16_t* heap = s.T->heap;
-  const uint8_t* depth = s.T->depth;
-  int v = heap[k];
+  uint32_t* hkey = s.T->hkey;
+  const int v = heap[k];
+  const uint32_t vk = hkey[k];
   int j = k << 1;
   while (j <= s.heapLen) {
-    if (j < s.heapLen && def_smaller(tree, heap[j + 1], heap[j], depth)) j++;
-    if (def_smaller(tree, v, heap[j], depth)) break;
+    uint32_t kj = hkey[j];
+    if (j < s.heapLen) {
+      const uint32_t kj1 = hkey[j + 1];
+      if (kj1 <= kj) { j++; kj = kj1; }  // smaller(heap[j + 1], heap[j])
+    }
+    if (vk <= kj) break;  // smaller(v, heap[j])
     heap[k] = heap[j];
+    hkey[k] = kj;
     k = j;
     j <<= 1;
   }
   heap[k] = int16_t(v);
+  hkey[k] = vk;
 }
 
 // trees.c gen_bitlen
@@ -219,19 +226,20 @@ G4_HD inline void def_gen_bitlen(DeflateState& s, DeflateTreeDesc& d) {
 G4_HD inline void def_build_tree(DeflateState& s, DeflateTreeDesc& d) {
   CtData* tree = d.tree;
   int16_t* heap = s.T->heap;
-  uint8_t* depth = s.T->depth;
+  uint32_t* hkey = s.T->hkey;
   const int elems = d.elems;
   int maxCode = -1;
   s.heapLen = 0;
   s.heapMax = kDefHeapSize;
   for (int n = 0; n < elems; n++) {
-    if (tree[n].fc != 0) { heap[++s.heapLen] = int16_t(maxCode = n); depth[n] = 0; }
+    const uint32_t f = tree[n].fc;
+    if (f != 0) { heap[++s.heapLen] = int16_t(maxCode = n); hkey[s.heapLen] = f << 8; }  // depth 0
     else tree[n].dl = 0;
   }
   while (s.heapLen < 2) {
     int node = heap[++s.heapLen] = int16_t(maxCode < 2 ? ++maxCode : 0);
     tree[node].fc = 1;
-    depth[node] = 0;
+    hkey[s.heapLen] = 1u << 8;
     s.optLen--;
     if (d.kind != 2) s.staticLen -= unsigned(def_static_len(d, node));
   }
@@ -239,16 +247,22 @@ G4_HD inline void def_build_tree(DeflateState& s, DeflateTreeDesc& d) {
   for (int n = s.heapLen / 2; n >= 1; n--) def_pqdownheap(s, tree, n);
   int node = elems;
   do {
-    int n = heap[1];
-    heap[1] = heap[s.heapLen--];
+    const int n = heap[1];
+    const uint32_t kn = hkey[1];
+    heap[1] = heap[s.heapLen];
+    hkey[1] = hkey[s.heapLen];
+    s.heapLen--;
     def_pqdownheap(s, tree, 1);
-    int m = heap[1];
+    const int m = heap[1];
+    const uint32_t km = hkey[1];
     heap[--s.heapMax] = int16_t(n);
     heap[--s.heapMax] = int16_t(m);
-    tree[node].fc = uint16_t(tree[n].fc + tree[m].fc);
-    depth[node] = uint8_t((depth[n] >= depth[m] ? depth[n] : depth[m]) + 1);
+    const uint32_t f = ((kn >> 8) + (km >> 8)) & 0xffffu;  // Freq is a ush
+    const uint32_t dn = kn & 0xffu, dm = km & 0xffu;
+    tree[node].fc = uint16_t(f);
     tree[n].dl = tree[m].dl = uint16_t(node);
     heap[1] = int16_t(node++);
+    hkey[1] = (f << 8) | (((dn >= dm ? dn : dm) + 1u) & 0xffu);  // depth is a uch
     def_pqdownheap(s, tree, 1);
   } while (s.heapLen >= 2);
   heap[--s.heapMax] = heap[1];

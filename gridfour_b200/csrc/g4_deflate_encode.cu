@@ -647,7 +647,7 @@ __global__ void __launch_bounds__(32) deflate_decide_ring_kernel(StagedArgs a) {
 // codes are OR-ed into the shared-memory bit window of g4_bitpack.cuh).  Adler-32 by a block reduction
 // (s2 = n + sum (n-i) b_i).
 namespace {
-constexpr int kEmitPar = 4;
+constexpr int kEmitPar = 3;  // 43 KB of M32 bytes are at most three blocks of 16,383 symbols
 constexpr int kEmitHdrWords = 152;  // 3 + 14 + 19 * 3 + 316 * 14 bits at most
 struct DeflateEmitShared {
   DeflateTrees T[kEmitPar];
