@@ -1123,14 +1123,18 @@ cudaError_t launch_deflate_staged(const StagedArgs& a, int smCount, cudaStream_t
   {
     const bool deep = deflate_level(a.level).maxChain > 128;
     static const bool oneGroup = getenv("G4_MATCH_GROUPS") && atoi(getenv("G4_MATCH_GROUPS")) == 1;
-    const size_t win = deep ? size_t(4096 + 2048) * 16 : size_t(128 + 1920) * 16;  // two groups: 2 x (128 + 896) x 16, the same
+    size_t win = deep ? size_t(4096 + 2048) * 16 : size_t(128 + 1920) * 16;  // two groups of (128 + 896) slots: the same
+    const size_t winBig = size_t(2) * (128 + 1408) * 16;                     // two groups of 1,536 slots
     const size_t smMax = 227 * 1024 - 2048;
     size_t tabBytes = (size_t(a.maxLen) * 4 + 15) & ~size_t(15);
     if (win + tabBytes > smMax) tabBytes = 0;  // too long: scattered stores
-    const size_t sm = win + tabBytes;
-    int perSm = int(smMax / sm);
+    int perSm = int(smMax / (win + tabBytes));
     if (perSm > 8) perSm = 8;
     if (deep && perSm > 2) perSm = 2;
+    // one CTA per SM anyway: the larger windows if they fit beside the table (fewer rounds, less of each window re-filled)
+    const bool big = !deep && !oneGroup && perSm == 1 && winBig + tabBytes <= smMax;
+    if (big) win = winBig;
+    const size_t sm = win + tabBytes;
     const int threads = perSm == 1 ? 1024 : perSm <= 3 ? 512 : 256;
     const int ctas = nChunk < smCount * perSm ? nChunk : smCount * perSm;
     static std::atomic<uint64_t> attrW{0};
@@ -1138,6 +1142,7 @@ cudaError_t launch_deflate_staged(const StagedArgs& a, int smCount, cudaStream_t
       const int cap = 227 * 1024 - 2048;
       cudaError_t e1 = cudaFuncSetAttribute(deflate_match_window_kernel<128, 1920, 1, 1024, 1>, cudaFuncAttributeMaxDynamicSharedMemorySize, cap);
       if (e1 == cudaSuccess) e1 = cudaFuncSetAttribute(deflate_match_window_kernel<128, 1920, 1, 512, 3>, cudaFuncAttributeMaxDynamicSharedMemorySize, cap);
+      if (e1 == cudaSuccess) e1 = cudaFuncSetAttribute(deflate_match_window_kernel<128, 1408, 2, 1024, 1>, cudaFuncAttributeMaxDynamicSharedMemorySize, cap);
       if (e1 == cudaSuccess) e1 = cudaFuncSetAttribute(deflate_match_window_kernel<128, 896, 2, 1024, 1>, cudaFuncAttributeMaxDynamicSharedMemorySize, cap);
       if (e1 == cudaSuccess) e1 = cudaFuncSetAttribute(deflate_match_window_kernel<4096, 2048, 1, 1024, 1>, cudaFuncAttributeMaxDynamicSharedMemorySize, cap);
       return e1;
@@ -1145,6 +1150,7 @@ cudaError_t launch_deflate_staged(const StagedArgs& a, int smCount, cudaStream_t
     if (ea != cudaSuccess) return ea;
     const uint32_t cap32 = uint32_t(tabBytes / 4);
     if (deep) deflate_match_window_kernel<4096, 2048, 1, 1024, 1><<<ctas, threads, sm, s>>>(a, cap32);
+    else if (big) deflate_match_window_kernel<128, 1408, 2, 1024, 1><<<ctas, threads, sm, s>>>(a, cap32);
     else if (threads == 1024 && !oneGroup) deflate_match_window_kernel<128, 896, 2, 1024, 1><<<ctas, threads, sm, s>>>(a, cap32);
     else if (threads == 1024) deflate_match_window_kernel<128, 1920, 1, 1024, 1><<<ctas, threads, sm, s>>>(a, cap32);
     else deflate_match_window_kernel<128, 1920, 1, 512, 3><<<ctas, threads, sm, s>>>(a, cap32);
